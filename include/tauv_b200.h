@@ -1,0 +1,256 @@
+/*
+ * tauv_b200.h — C ABI of libtauv_b200.so: the B200 (sm_100a) detection-head hot path of
+ * TAUV-Vision (CenterNet decode / target encode, YOLACT post-process / anchor matching).
+ *
+ * The reference (pure Python/PyTorch) has no FFI layer: callers bind module-level functions
+ * by name.  This header is the boundary a maintainer binds with ctypes;
+ * every entry point cites the reference function (file:line under /root/reference) it replaces.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers on the current CUDA device unless the name ends in _host.
+ *  - fp32 unless stated; "i64" = int64_t; booleans are uint8_t (torch.bool storage).
+ *  - Strides are in ELEMENTS (torch .stride()), passed wherever the reference hands us a
+ *    permuted view (Prediction.size/offset/depth are NCHW tensors viewed as NHWC).
+ *  - The library allocates nothing and keeps no pointer after return.  Scratch comes from the
+ *    caller: ask tauv_*_workspace_bytes(), pass a device buffer of at least that size
+ *    (256-byte aligned).  Work is enqueued on `stream` (a cudaStream_t); no call synchronises.
+ *  - Return value: 0 = OK; < 0 = argument error (TAUV_E_*); > 0 = a cudaError_t.
+ *    tauv_last_error() returns a thread-local message for the last non-zero return.
+ *  - Re-entrant: no mutable globals; concurrent calls on different streams/devices are safe.
+ *  - There is no CPU path: a device without sm_100 returns TAUV_E_ARCH.
+ */
+#ifndef TAUV_B200_H
+#define TAUV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAUV_B200_VERSION 100 /* 0.1.0 */
+
+enum {
+  TAUV_OK = 0,
+  TAUV_E_NULL = -1,      /* required pointer is NULL */
+  TAUV_E_SHAPE = -2,     /* non-positive / inconsistent shape */
+  TAUV_E_K_RANGE = -3,   /* k > C*H*W  (reference: RuntimeError "selected index k out of range") */
+  TAUV_E_KERNEL = -4,    /* even / non-positive kernel_size (reference: AssertionError decode.py:243) */
+  TAUV_E_WORKSPACE = -5, /* workspace too small or misaligned */
+  TAUV_E_UNSUPPORTED = -6, /* shape beyond what the kernels are built for (see message) */
+  TAUV_E_ARCH = -7,      /* device is not sm_100 */
+  TAUV_E_ALIGN = -8      /* pointer not aligned as required */
+};
+
+typedef void* tauv_stream_t; /* cudaStream_t */
+
+int tauv_version(void);
+const char* tauv_last_error(void);
+/* 0 when the CURRENT device can run the kernels (compute capability 10.x). */
+int tauv_check_device(void);
+
+/* ------------------------------------------------------------------------------------------
+ * CenterNet
+ * ---------------------------------------------------------------------------------------- */
+
+/* heatmap_nms(heatmap, kernel_size)            — centernet/model/decode.py:239-252
+ * out = (max_pool2d(in, k, stride 1, pad (k-1)/2) == in) * in, elementwise over [B,C,H,W]
+ * (contiguous NCHW).  apply_sigmoid != 0 first maps in -> 1/(1+exp(-in)) (decode.py:182-183
+ * fused).  k must be odd and >= 1. */
+int tauv_heatmap_nms(const float* in, float* out, int B, int C, int H, int W, int kernel_size,
+                     int apply_sigmoid, tauv_stream_t stream);
+
+/* Top-k modes for tauv_heatmap_topk */
+enum {
+  TAUV_TOPK_RAW = 0,         /* heatmap_detect on the values as given (decode.py:255-279) */
+  TAUV_TOPK_SIGMOID_PEAK = 1 /* sigmoid -> 3x3 peak suppression -> heatmap_detect, one pass
+                                (decode.py:182-184 / :56-58), never materialising the map */
+};
+
+size_t tauv_heatmap_topk_workspace_bytes(int B, int C, int H, int W, int k);
+
+/* heatmap_detect(heatmap, n_detections)        — centernet/model/decode.py:255-279
+ * Joint top-k over the flattened C*H*W of every frame.  Order: score descending, ties by
+ * flat index ascending (the order the reference's own KAT decode.py:327-339 asserts).
+ *   index [B,k,2] i64 (y,x), label [B,k] i64, score [B,k] f32.
+ * In SIGMOID_PEAK mode entries past the last positive peak have score 0 and the lowest flat
+ * indices whose suppressed value is 0, as a stable top-k of the dense suppressed map gives. */
+int tauv_heatmap_topk(const float* heatmap, int B, int C, int H, int W, int k, int mode,
+                      int64_t* index, int64_t* label, float* score, void* workspace,
+                      size_t workspace_bytes, tauv_stream_t stream);
+
+/* Box-decode modes */
+enum {
+  TAUV_BOX_DECODE = 0,   /* decode():           y = (ratio*iy + offset_y)/in_h  (fp64), depth = 1/sigmoid(d) - 1
+                                                 — decode.py:210-221, :319-324 */
+  TAUV_BOX_KEYPOINTS = 1 /* decode_keypoints(): y = iy/out_h (fp32 divide), no offset, depth = 1/sigmoid(d)
+                                                 — decode.py:65, :87-91 */
+};
+
+/* Per-detection gather + box arithmetic of decode()/decode_keypoints() for the k ranked peaks
+ * of every frame.  size/offset: logical [B,H,W,2] with element strides {b,y,x,c}; depth:
+ * logical [B,H,W(,1)] with strides {b,y,x} (NULL = no depth head).
+ *   yx [B,k,2] f64, hw [B,k,2] f32, depth_out [B,k] f32 (may be NULL iff depth NULL),
+ *   count [B] i32 = number of leading entries before the first score < score_threshold
+ *   (decode.py:208-209, compared in fp32 like torch). */
+int tauv_centernet_boxes(const int64_t* index, const float* score, int B, int k, int H, int W,
+                         const float* size, const int64_t size_strides[4], const float* offset,
+                         const int64_t offset_strides[4], const float* depth,
+                         const int64_t depth_strides[3], int mode, int downsample_ratio, int in_h,
+                         int in_w, int out_h, int out_w, float score_threshold, double* yx,
+                         float* hw, float* depth_out, int32_t* count, tauv_stream_t stream);
+
+/* decode(prediction, model_config, n_detections, score_threshold) — decode.py:179-236,
+ * device part: tauv_heatmap_topk(SIGMOID_PEAK) followed by tauv_centernet_boxes. */
+int tauv_centernet_decode(const float* heatmap_logits, int B, int C, int H, int W, int k,
+                          const float* size, const int64_t size_strides[4], const float* offset,
+                          const int64_t offset_strides[4], const float* depth,
+                          const int64_t depth_strides[3], int mode, int downsample_ratio,
+                          int in_h, int in_w, float score_threshold, int64_t* index,
+                          int64_t* label, float* score, double* yx, float* hw, float* depth_out,
+                          int32_t* count, void* workspace, size_t workspace_bytes,
+                          tauv_stream_t stream);
+
+/* Gather `nch` channels at the ranked peak positions from a strided [B, ..., H, W] map:
+ * out[b,j,c] = src[b*sb + sel(b,j)*ssel + c*sc + iy*sy + ix*sx], where sel is label[b,j]
+ * (or 0 if label is NULL).  Used for keypoint_affinity[b,label,0:2,y,x] (decode.py:121-122). */
+int tauv_gather_at(const float* src, int64_t sb, int64_t ssel, int64_t sc, int64_t sy,
+                   int64_t sx, int nch, const int64_t* index, const int64_t* label, int B, int k,
+                   float* out, tauv_stream_t stream);
+
+/* angle_decode(predicted_bin, predicted_offset, theta_range, bin_overlap) — decode.py:291-316
+ * Two-bin angle decode over n rows of 4: softmax-select the bin, centre +- pi/2 plus atan2 of the
+ * (sin, cos) offset pair, wrapped to [0, 2*pi) and rescaled by theta_range/(2*pi).
+ * (bin_overlap only shifts bin limits, which the decode never reads.)  out [n] f32. */
+int tauv_angle_decode(const float* predicted_bin, const float* predicted_offset, int64_t n,
+                      double theta_range, float* out, tauv_stream_t stream);
+
+/* depth_decode(prediction) = 1/sigmoid(d) - 1, elementwise — decode.py:319-324. */
+int tauv_depth_decode(const float* in, int64_t n, float* out, tauv_stream_t stream);
+
+/* generate_heatmap(truth, model_config, train_config, object_config) — centernet/model/loss.py:31-72
+ * out[b,c,y,x] = max over valid objects o of frame b with label c of
+ *                exp(-((x-cx)^2+(y-cy)^2) / (2*sigma^2)),   0 where no object,
+ * cy = floor(center_y*in_h/ratio) (fp32 multiply then divide, unclamped), sigma floored at 0.1.
+ * sigma is a double because the reference forms 2*sigma**2 in Python doubles before the fp32 divide.
+ *   valid [B,n] u8, label [B,n] i64, center [B,n,2] f32 (y,x), out [B,C,H,W] f32 contiguous. */
+int tauv_gaussian_encode(const uint8_t* valid, const int64_t* label, const float* center, int B,
+                         int n_objects, int C, int H, int W, int in_h, int in_w,
+                         int downsample_ratio, double sigma, float* out, tauv_stream_t stream);
+
+/* generate_keypoint_heatmap(...) — centernet/model/loss.py:75-135
+ *   kp_valid [B,m] u8, kp_label [B,m] i64, kp_center [B,m,2] f32, kp_object_index [B,m] i64,
+ *   center [B,n,2] f32 (object centres)
+ *   heatmap [B,Kp,H,W], weight [B,Kp,H,W], affinity [B,Kp,2,H,W]  (all f32 contiguous). */
+int tauv_keypoint_encode(const uint8_t* kp_valid, const int64_t* kp_label, const float* kp_center,
+                         const int64_t* kp_object_index, const float* center, int B, int m,
+                         int n_objects, int Kp, int H, int W, int in_h, int in_w,
+                         int downsample_ratio, double sigma_heatmap, double sigma_affinity,
+                         float* heatmap, float* weight, float* affinity, tauv_stream_t stream);
+
+/* out_index_for_position (loss.py:138-142) and the sub-pixel offset target (loss.py:263-264).
+ *   position [n,2] f32 -> index [n,2] i64 (clamped), offset [n,2] f32 (may be NULL). */
+int tauv_out_index_offset(const float* position, int64_t n, int in_h, int in_w,
+                          int downsample_ratio, int out_h, int out_w, int64_t* index,
+                          float* offset, tauv_stream_t stream);
+
+/* gaussian_splat(h, w, cy, cx, sigma) — missing from the reference snapshot; call sites
+ * decode.py:328-332, tests/centernet_square_detection.py:108-112.  out [h,w] f32. */
+int tauv_gaussian_splat(int h, int w, int cy, int cx, double sigma, float* out,
+                        tauv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * YOLACT
+ * ---------------------------------------------------------------------------------------- */
+
+/* get_anchor for all FPN levels concatenated — yolact/model/anchors.py:9-41, model.py:47-58.
+ * Level l has fpn_h[l] x fpn_w[l] cells; ordering inside a level is aspect-major
+ * (idx = a*H*W + i*W + j), exactly as the reference builds it.  out [sum_l A*h*w, 4] (y,x,h,w).
+ * hw_host holds the per-(level,aspect) h,w already rounded to fp32 by the caller
+ * (2*n_levels*n_aspect floats: h then w) because the reference computes them in Python doubles. */
+int tauv_yolact_anchors(const int* fpn_h_host, const int* fpn_w_host, int n_levels, int n_aspect,
+                        const float* hw_host, float* out, tauv_stream_t stream);
+
+/* box_decode(box_encoding, anchor, config) — yolact/model/boxes.py:55-61
+ *   yx = a_yx + (e_yx*v0)*a_hw ; hw = a_hw*exp(e_hw*v1).  anchor_batch is 1 (broadcast) or B. */
+int tauv_yolact_box_decode(const float* encoding, const float* anchor, int B, int N,
+                           int anchor_batch, float v0, float v1, float* out, tauv_stream_t stream);
+
+/* box_encode(box, anchor, config) — yolact/model/boxes.py:45-52
+ *   g_yx = (b_yx - a_yx)/(v0*a_hw) ; g_hw = log(b_hw/a_hw)/v1. */
+int tauv_yolact_box_encode(const float* box, const float* anchor, int B, int N, int anchor_batch,
+                           float v0, float v1, float* out, tauv_stream_t stream);
+
+/* iou_matrix(box_a, box_b) — yolact/model/boxes.py:64-85
+ *   a [Ba,Na,4], b [Bb,Nb,4] centre-size boxes, Ba/Bb in {1,B} -> out [B,Na,Nb]. */
+int tauv_iou_matrix(const float* a, const float* b, int Ba, int Bb, int Na, int Nb, float* out,
+                    tauv_stream_t stream);
+
+/* softmax(classification)[..., 1:].max(-1) — yolact/model/nms.py:9-10.
+ *   cls [B,N,C1] -> score [B,N] ; argmax_all (optional, i32 [B,N]) = argmax over all C1 classes
+ *   (yolact_node.py:129). */
+int tauv_yolact_scores(const float* cls, int B, int N, int C1, float* score, int32_t* argmax_all,
+                       tauv_stream_t stream);
+
+size_t tauv_yolact_nms_workspace_bytes(int B, int N, int C1, int top_k);
+
+/* nms(classification, box, top_k, iou_threshold, confidence_threshold) — yolact/model/nms.py:7-29
+ * Fast NMS, batched over the first n_frames frames (the reference processes frame 0 only).
+ *   cls [B,N,C1], box [B,N,4] DECODED boxes ->
+ *   keep [n_frames, top_k] i64 (prior indices, descending confidence, ties by prior index),
+ *   n_keep [n_frames] i32. */
+int tauv_yolact_fast_nms(const float* cls, const float* box, int B, int N, int C1, int n_frames,
+                         int top_k, float iou_threshold, float confidence_threshold,
+                         int64_t* keep, int32_t* n_keep, void* workspace, size_t workspace_bytes,
+                         tauv_stream_t stream);
+
+/* Fused post-process head (yolact_node.py:127-130): scores -> top_k -> box_decode of the top_k
+ * priors only -> Fast NMS.  Also returns the decoded boxes / confidence / class of the kept
+ * priors so the caller never touches the [B,N,*] tensors again.
+ *   enc [B,N,4], anchor [1 or B,N,4] ->
+ *   keep [B,top_k] i64, n_keep [B] i32, keep_box [B,top_k,4] f32, keep_score [B,top_k] f32,
+ *   keep_class [B,top_k] i32 (argmax over all C1 classes). */
+int tauv_yolact_detect(const float* cls, const float* enc, const float* anchor, int B, int N,
+                       int C1, int anchor_batch, float v0, float v1, int top_k,
+                       float iou_threshold, float confidence_threshold, int64_t* keep,
+                       int32_t* n_keep, float* keep_box, float* keep_score, int32_t* keep_class,
+                       void* workspace, size_t workspace_bytes, tauv_stream_t stream);
+
+/* assemble_mask(mask_prototype, mask_coeff, box) — yolact/model/masks.py:8-21 with
+ * box_to_mask boxes.py:88-103.   mask[i] = sigmoid(sum_p coeff[i,p]*proto[p]) * crop(box[i]).
+ * The contraction runs on the tensor cores (tcgen05, bf16 operands, fp32 accumulate in TMEM).
+ *   proto [P,H,W] f32, coeff [n,P] f32, box [n,4] f32 or NULL -> out [n,H,W] f32.
+ * logits_out (optional, [n,H,W]) receives the pre-sigmoid accumulator for tolerance checks. */
+int tauv_yolact_assemble_mask(const float* proto, const float* coeff, const float* box, int n,
+                              int P, int H, int W, float* out, float* logits_out,
+                              tauv_stream_t stream);
+
+/* Batched mask assembly straight from the detect() outputs: frame b assembles n_keep[b] masks
+ * from coeff_all[b, keep[b,i], :] and keep_box[b,i].
+ *   proto [B,P,H,W], coeff_all [B,N,P], keep [B,top_k] i64, n_keep [B] i32,
+ *   keep_box [B,top_k,4] (NULL = no crop) -> out [B,top_k,H,W] (rows >= n_keep[b] untouched). */
+int tauv_yolact_assemble_mask_batched(const float* proto, const float* coeff_all,
+                                      const int64_t* keep, const int32_t* n_keep,
+                                      const float* keep_box, int B, int N, int P, int H, int W,
+                                      int top_k, float* out, tauv_stream_t stream);
+
+/* box_to_mask(box, img_size) — yolact/model/boxes.py:88-103.  box [4] f32 -> out [H,W] {0,1}. */
+int tauv_box_to_mask(const float* box, int H, int W, float* out, tauv_stream_t stream);
+
+/* Anchor matching + regression targets — yolact/model/loss.py:16-22, :62-66
+ *   anchor [1,N,4], truth_box [B,M,4], truth_valid [B,M] u8 ->
+ *   match_index [B,N] i64 (first max on ties), match_iou [B,N] f32,
+ *   positive [B,N] u8 (iou >= pos_thr), negative [B,N] u8 (iou <= neg_thr),
+ *   target [B,N,4] f32 = box_encode(truth_box[match_index], anchor) (meaningful where positive;
+ *   may be NULL). */
+int tauv_yolact_match_anchors(const float* anchor, const float* truth_box,
+                              const uint8_t* truth_valid, int B, int N, int M, float pos_thr,
+                              float neg_thr, float v0, float v1, int64_t* match_index,
+                              float* match_iou, uint8_t* positive, uint8_t* negative,
+                              float* target, tauv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAUV_B200_H */

@@ -1,0 +1,348 @@
+"""CPU oracle — TEST INFRASTRUCTURE ONLY.
+
+A restatement, in plain torch-CPU fp32 tensor ops, of the TAUV-Vision detection-head hot path
+(scope rows a2-a19 of SURVEY.md section 8).  It exists to CHECK the CUDA path.  Only ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may
+import it; nothing under ``tauv-vision_b200/`` does, and the product has no CPU path.
+
+Why torch-CPU rather than numpy: the reference *is* a sequence of ATen calls, and its rounding
+(sigmoid = 1/(1+exp(-x)) with SLEEF exp, softmax reduction order, int64->fp32 promotion rules) is
+defined by ATen.  Re-using the same library for the arithmetic makes this port bit-identical to
+the reference on CPU, so the only thing it adds is what the reference leaves undefined: a
+canonical tie order — (score desc, flat index asc) for top-k, (confidence desc, prior index asc)
+for NMS — which is the order the reference's own known-answer check asserts (decode.py:327-339).
+
+Parity pinned: yes.  ``tests/golden/make_golden.py`` runs the REAL reference (imported from
+/root/reference/src in the build container) on seeded inputs and commits its outputs under
+``tests/golden/``; ``tests/test_oracle_vs_golden.py`` checks every function here against them,
+plus the reference's two in-module KATs (decode.py:327-339, yolact boxes.py:106-117).
+
+Each function cites the reference lines (under /root/reference/src/tauv_vision/) it follows.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from math import floor, pi, sqrt
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+# ------------------------------------------------------------------------------------------------
+# CenterNet decode                                              centernet/model/decode.py
+# ------------------------------------------------------------------------------------------------
+
+
+def heatmap_nms(heatmap: torch.Tensor, kernel_size: int) -> torch.Tensor:
+    """decode.py:239-252 — keep cells equal to their k x k neighbourhood max, zero the rest."""
+    assert kernel_size >= 1 and kernel_size % 2 == 1
+    pooled = F.max_pool2d(heatmap, kernel_size, stride=1, padding=(kernel_size - 1) // 2)
+    return (pooled == heatmap).to(torch.float32) * heatmap
+
+
+def stable_topk(scores: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Row-wise top-k with the canonical order (value desc, index asc).  scores [B, n]."""
+    B, n = scores.shape
+    if k > n:
+        raise RuntimeError("selected index k out of range")
+    vals = torch.empty((B, k), dtype=scores.dtype)
+    idxs = torch.empty((B, k), dtype=torch.int64)
+    for b in range(B):
+        row = scores[b]
+        kth = torch.topk(row, k).values[-1]
+        cand = torch.nonzero(row >= kth, as_tuple=False).flatten()  # ascending index
+        order = torch.sort(row[cand], descending=True, stable=True).indices[:k]
+        idxs[b] = cand[order]
+        vals[b] = row[idxs[b]]
+    return vals, idxs
+
+
+def heatmap_detect(heatmap: torch.Tensor, n_detections: int):
+    """decode.py:255-279 — joint top-k over C*H*W; (index [B,k,2] (y,x), label [B,k], score [B,k])."""
+    B, C, H, W = heatmap.shape
+    score, flat = stable_topk(heatmap.reshape(B, -1), n_detections)
+    label = torch.div(flat, H * W, rounding_mode="floor")
+    rem = flat - label * (H * W)
+    index = torch.stack((torch.div(rem, W, rounding_mode="floor"), rem % W), dim=-1)
+    return index, label, score
+
+
+def depth_decode(d: torch.Tensor) -> torch.Tensor:
+    """decode.py:319-324."""
+    return (1 / torch.sigmoid(d)) - 1
+
+
+def angle_get_bins(bin_overlap: float):
+    """decode.py:282-288."""
+    return (pi / 2, -bin_overlap / 2, pi + bin_overlap / 2), (-pi / 2, -pi - bin_overlap / 2, bin_overlap / 2)
+
+
+def angle_decode(predicted_bin, predicted_offset, theta_range: float, bin_overlap: float):
+    """decode.py:291-316."""
+    (c0, _, _), (c1, _, _) = angle_get_bins(bin_overlap)
+    s0 = F.softmax(predicted_bin[:, :, 0:2], dim=-1)[:, :, 1]
+    s1 = F.softmax(predicted_bin[:, :, 2:4], dim=-1)[:, :, 1]
+    a0 = c0 + torch.atan2(predicted_offset[:, :, 0], predicted_offset[:, :, 1])
+    a1 = c1 + torch.atan2(predicted_offset[:, :, 2], predicted_offset[:, :, 3])
+    ang = torch.where(s1 > s0, a1, a0) % (2 * pi)
+    return ang * (theta_range / (2 * pi))
+
+
+@dataclass
+class Packed:
+    index: torch.Tensor   # [B,k,2] i64
+    label: torch.Tensor   # [B,k] i64
+    score: torch.Tensor   # [B,k] f32
+    yx: torch.Tensor      # [B,k,2] f64
+    hw: torch.Tensor      # [B,k,2] f32
+    depth: Optional[torch.Tensor]  # [B,k] f32
+    count: torch.Tensor   # [B] i32
+
+
+def _gather_hw(t: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """t [B,H,W,ch] (any strides), index [B,k,2] -> [B,k,ch]."""
+    B = t.shape[0]
+    bi = torch.arange(B).unsqueeze(1).expand(-1, index.shape[1])
+    return t[bi, index[..., 0], index[..., 1]]
+
+
+def decode_packed(heatmap_logits, size, offset, depth, downsample_ratio: int, in_h: int, in_w: int,
+                  n_detections: int, score_threshold: float) -> Packed:
+    """decode.py:179-236 with the per-detection Python loop expressed as gathers.
+    y = (ratio*iy + offset_y)/in_h in float64 (the reference computes these in Python floats, :214-215);
+    count = entries before the first score < threshold (:208-209, fp32 compare)."""
+    hm = heatmap_nms(torch.sigmoid(heatmap_logits), 3)
+    index, label, score = heatmap_detect(hm, n_detections)
+    off = _gather_hw(offset, index).to(torch.float64)
+    yx = torch.stack(((downsample_ratio * index[..., 0].to(torch.float64) + off[..., 0]) / in_h,
+                      (downsample_ratio * index[..., 1].to(torch.float64) + off[..., 1]) / in_w), dim=-1)
+    hw = _gather_hw(size, index)
+    dep = None
+    if depth is not None:
+        d = depth if depth.dim() == 4 else depth.unsqueeze(-1)
+        dep = _gather_hw(depth_decode(d), index)[..., 0]
+    below = score < score_threshold
+    first = torch.where(below.any(dim=1), below.to(torch.int64).argmax(dim=1), torch.full((score.shape[0],), score.shape[1]))
+    return Packed(index, label, score, yx, hw, dep, first.to(torch.int32))
+
+
+def decode_keypoints_packed(heatmap_logits, size, depth, out_h: int, out_w: int, n_detections: int,
+                            score_threshold: float) -> Packed:
+    """Object half of decode_keypoints (decode.py:56-58, :65, :84-91): y = iy/out_h (fp32 divide),
+    no offset, depth = 1/sigmoid(d)."""
+    hm = heatmap_nms(torch.sigmoid(heatmap_logits), 3)
+    index, label, score = heatmap_detect(hm, n_detections)
+    yx = torch.stack(((index[..., 0] / out_h), (index[..., 1] / out_w)), dim=-1).to(torch.float64)
+    hw = _gather_hw(size, index)
+    dep = None
+    if depth is not None:
+        d = depth if depth.dim() == 4 else depth.unsqueeze(-1)
+        dep = _gather_hw(1 / torch.sigmoid(d), index)[..., 0]
+    below = score < score_threshold
+    first = torch.where(below.any(dim=1), below.to(torch.int64).argmax(dim=1), torch.full((score.shape[0],), score.shape[1]))
+    return Packed(index, label, score, yx, hw, dep, first.to(torch.int32))
+
+
+# ------------------------------------------------------------------------------------------------
+# CenterNet target encode                                        centernet/model/loss.py
+# ------------------------------------------------------------------------------------------------
+
+
+def gaussian_splat(h: int, w: int, cy: int, cx: int, sigma: float) -> torch.Tensor:
+    """Missing from the reference snapshot; semantics from loss.py:64-67 and the call sites
+    decode.py:328-332 / tests/centernet_square_detection.py:108-112."""
+    y, x = torch.meshgrid(torch.arange(0, h), torch.arange(0, w), indexing="ij")
+    return torch.exp(-((x - cx) ** 2 + (y - cy) ** 2) / (2 * sigma ** 2))
+
+
+def generate_heatmap(valid, label, center, n_labels: int, out_h: int, out_w: int, in_h: int, in_w: int,
+                     downsample_ratio: int, sigma: float) -> torch.Tensor:
+    """loss.py:31-72 — per valid object, running max of a full-plane Gaussian at the floored centre."""
+    B, n = valid.shape
+    out = torch.zeros((B, n_labels, out_h, out_w), dtype=torch.float32)
+    y, x = torch.meshgrid(torch.arange(0, out_h), torch.arange(0, out_w), indexing="ij")
+    if sigma < 0.1:
+        sigma = 0.1
+    for b in range(B):
+        for o in range(n):
+            if not valid[b, o]:
+                continue
+            cy = floor(center[b, o, 0] * in_h / downsample_ratio)
+            cx = floor(center[b, o, 1] * in_w / downsample_ratio)
+            g = torch.exp(-((x - cx) ** 2 + (y - cy) ** 2) / (2 * sigma ** 2))
+            out[b, label[b, o]] = torch.maximum(out[b, label[b, o]], g)
+    return torch.nan_to_num(out)
+
+
+def generate_keypoint_heatmap(kp_valid, kp_label, kp_center, kp_object_index, center, n_keypoints: int,
+                              out_h: int, out_w: int, in_h: int, in_w: int, downsample_ratio: int,
+                              sigma_heatmap: float, sigma_affinity: float):
+    """loss.py:75-135 — keypoint heatmap, affinity weight, and the unit vector field from the owning
+    object's centre (nearest object wins, strict '<' so the first instance wins ties)."""
+    B, m = kp_valid.shape
+    hm = torch.zeros((B, n_keypoints, out_h, out_w), dtype=torch.float32)
+    wt = torch.zeros((B, n_keypoints, out_h, out_w), dtype=torch.float32)
+    aff = torch.zeros((B, n_keypoints, 2, out_h, out_w), dtype=torch.float32)
+    dist = torch.full((B, n_keypoints, out_h, out_w), float("inf"), dtype=torch.float32)
+    y, x = torch.meshgrid(torch.arange(0, out_h), torch.arange(0, out_w), indexing="ij")
+    grid = torch.stack((y / out_h, x / out_w), dim=0)
+    for b in range(B):
+        for i in range(m):
+            if not kp_valid[b, i]:
+                continue
+            k = kp_label[b, i]
+            cy = floor(kp_center[b, i, 0] * in_h / downsample_ratio)
+            cx = floor(kp_center[b, i, 1] * in_w / downsample_ratio)
+            neg_d2 = -((x - cx) ** 2 + (y - cy) ** 2)
+            hm[b, k] = torch.maximum(hm[b, k], torch.exp(neg_d2 / (2 * sigma_heatmap ** 2)))
+            wt[b, k] = torch.maximum(wt[b, k], torch.exp(neg_d2 / (2 * sigma_affinity ** 2)))
+            disp = grid - center[b, kp_object_index[b, i]].unsqueeze(1).unsqueeze(2)
+            disp = torch.nan_to_num(disp, 0)
+            d = torch.nan_to_num(torch.sqrt(disp[0] ** 2 + disp[1] ** 2), 1)
+            unit = disp / d
+            aff[b, k] = torch.where(d < dist[b, k], unit, aff[b, k])
+            dist[b, k] = torch.min(dist[b, k], d)
+    return torch.nan_to_num(hm), torch.nan_to_num(wt), torch.nan_to_num(aff)
+
+
+def out_index_for_position(position, in_h: int, in_w: int, downsample_ratio: int, out_h: int, out_w: int):
+    """loss.py:138-142."""
+    return torch.stack((
+        torch.clamp(((position[..., 0] * in_h) / downsample_ratio).to(torch.long), 0, out_h - 1),
+        torch.clamp(((position[..., 1] * in_w) / downsample_ratio).to(torch.long), 0, out_w - 1),
+    ), dim=-1)
+
+
+def offset_target(center, in_h: int, in_w: int, downsample_ratio: int):
+    """loss.py:263-264."""
+    pix = center * torch.tensor((in_h, in_w), dtype=torch.float32)
+    return pix - downsample_ratio * (pix / downsample_ratio).to(torch.long)
+
+
+# ------------------------------------------------------------------------------------------------
+# YOLACT                                                         yolact/model/{anchors,boxes,nms,masks,loss}.py
+# ------------------------------------------------------------------------------------------------
+
+
+def get_anchor(fpn_i: int, fpn_size, anchor_scales, anchor_aspect_ratios, in_h: int, in_w: int) -> torch.Tensor:
+    """anchors.py:9-41 — [1, A*H*W, 4] (y,x,h,w), aspect-major inside the level."""
+    H, W = fpn_size
+    cy = (torch.arange(0, H) + 0.5) / H
+    cx = (torch.arange(0, W) + 0.5) / W
+    gy, gx = torch.meshgrid(cy, cx, indexing="ij")
+    gy, gx = gy.flatten(), gx.flatten()
+    rows = []
+    in_size = (in_h + in_w) / 2
+    for ar in anchor_aspect_ratios:
+        h = (anchor_scales[fpn_i] / in_size) * sqrt(ar)
+        w = (anchor_scales[fpn_i] / in_size) / sqrt(ar)
+        rows.append(torch.stack((gy, gx, torch.full_like(gy, h), torch.full_like(gx, w)), dim=-1))
+    return torch.cat(rows, dim=0).unsqueeze(0)
+
+
+def all_anchors(fpn_sizes, anchor_scales, anchor_aspect_ratios, in_h: int, in_w: int) -> torch.Tensor:
+    """model.py:47-58 — the levels concatenated."""
+    return torch.cat([get_anchor(i, s, anchor_scales, anchor_aspect_ratios, in_h, in_w)
+                      for i, s in enumerate(fpn_sizes)], dim=1)
+
+
+def box_to_corners(box):
+    """boxes.py:15-27."""
+    return torch.stack((box[..., 0] - box[..., 2] / 2, box[..., 1] - box[..., 3] / 2,
+                        box[..., 0] + box[..., 2] / 2, box[..., 1] + box[..., 3] / 2), dim=-1)
+
+
+def corners_to_box(c):
+    """boxes.py:30-42."""
+    return torch.stack(((c[..., 0] + c[..., 2]) / 2, (c[..., 1] + c[..., 3]) / 2,
+                        c[..., 2] - c[..., 0], c[..., 3] - c[..., 1]), dim=-1)
+
+
+def box_decode(enc, anchor, variances):
+    """boxes.py:55-61."""
+    return torch.cat((anchor[:, :, :2] + enc[:, :, :2] * variances[0] * anchor[:, :, 2:],
+                      anchor[:, :, 2:] * torch.exp(enc[:, :, 2:] * variances[1])), -1)
+
+
+def box_encode(box, anchor, variances):
+    """boxes.py:45-52."""
+    g_yx = (box[:, :, :2] - anchor[:, :, :2]) / (variances[0] * anchor[:, :, 2:])
+    g_hw = torch.log(box[:, :, 2:] / anchor[:, :, 2:]) / variances[1]
+    return torch.cat((g_yx, g_hw), -1)
+
+
+def iou_matrix(box_a, box_b):
+    """boxes.py:64-85 — [Ba,Na,4] x [Bb,Nb,4] -> [B,Na,Nb]; areas from (h*w), union = (a+b)-inter."""
+    ca, cb = box_to_corners(box_a), box_to_corners(box_b)
+    y0 = torch.max(ca[:, :, 0].unsqueeze(2), cb[:, :, 0].unsqueeze(1))
+    x0 = torch.max(ca[:, :, 1].unsqueeze(2), cb[:, :, 1].unsqueeze(1))
+    y1 = torch.min(ca[:, :, 2].unsqueeze(2), cb[:, :, 2].unsqueeze(1))
+    x1 = torch.min(ca[:, :, 3].unsqueeze(2), cb[:, :, 3].unsqueeze(1))
+    inter = torch.clamp(y1 - y0, min=0) * torch.clamp(x1 - x0, min=0)
+    area_a = box_a[:, :, 2] * box_a[:, :, 3]
+    area_b = box_b[:, :, 2] * box_b[:, :, 3]
+    return inter / ((area_a.unsqueeze(2) + area_b.unsqueeze(1)) - inter)
+
+
+def nms_scores(classification):
+    """nms.py:9-10 — max foreground softmax confidence per prior."""
+    return torch.max(F.softmax(classification, dim=-1)[:, :, 1:], dim=-1).values
+
+
+def nms_frame(score_row, box_row, top_k: int, iou_threshold: float, confidence_threshold: float):
+    """nms.py:12-27 for one frame given its confidences: canonical (confidence desc, prior asc) order,
+    upper-triangular IoU, column max, keep = (iou_max <= thr) & (conf >= thr)."""
+    conf, idx = torch.sort(score_row, descending=True, stable=True)
+    idx, conf = idx[:top_k], conf[:top_k]
+    b = box_row[idx].unsqueeze(0)
+    iou = torch.triu(iou_matrix(b, b), diagonal=1)
+    iou_max = torch.max(iou, dim=1).values[0]
+    keep = (iou_max <= iou_threshold) & (conf >= confidence_threshold)
+    return idx[keep], idx, conf
+
+
+def nms(classification, box, top_k: int, iou_threshold: float, confidence_threshold: float):
+    """nms.py:7-29 — frame 0 only, like the reference."""
+    return nms_frame(nms_scores(classification)[0], box[0], top_k, iou_threshold, confidence_threshold)[0]
+
+
+def box_to_mask(box, img_size):
+    """boxes.py:88-103 — inclusive crop on integer pixel coordinates."""
+    yg = torch.arange(0, img_size[0], dtype=torch.float)
+    xg = torch.arange(0, img_size[1], dtype=torch.float)
+    yc, xc = torch.meshgrid(yg, xg, indexing="ij")
+    b = box * torch.tensor([img_size[0], img_size[1], img_size[0], img_size[1]])
+    left, right = b[1] - b[3] / 2, b[1] + b[3] / 2
+    top, bottom = b[0] - b[2] / 2, b[0] + b[2] / 2
+    return ((xc >= left) & (xc <= right) & (yc >= top) & (yc <= bottom)).float()
+
+
+def mask_logits(mask_prototype, mask_coeff):
+    """masks.py:13 — sum_p coeff[i,p]*proto[p], fp32, summed over p in index order like torch.sum(dim=0)
+    on a [P,H,W] temporary."""
+    out = torch.empty((mask_coeff.shape[0],) + tuple(mask_prototype.shape[1:]), dtype=torch.float32)
+    for i in range(mask_coeff.shape[0]):
+        out[i] = torch.sum(mask_coeff[i].unsqueeze(1).unsqueeze(2) * mask_prototype, dim=0)
+    return out
+
+
+def assemble_mask(mask_prototype, mask_coeff, box):
+    """masks.py:8-21."""
+    m = torch.sigmoid(mask_logits(mask_prototype, mask_coeff))
+    if box is not None:
+        for i in range(m.shape[0]):
+            m[i] *= box_to_mask(box[i], m[i].shape)
+    return m
+
+
+def match_anchors(anchor, truth_box, truth_valid, pos_thr: float, neg_thr: float, variances):
+    """yolact/model/loss.py:16-22 (+ :62-66 box_encode of the matched truth, here dense over all
+    priors).  Returns (match_index [B,N], match_iou [B,N], positive, negative, target [B,N,4])."""
+    iou = iou_matrix(anchor, truth_box)
+    match_iou, match_index = torch.max(iou * truth_valid.unsqueeze(1).float(), dim=2)
+    positive = match_iou >= pos_thr
+    negative = match_iou <= neg_thr
+    B = truth_box.shape[0]
+    matched = truth_box[torch.arange(B).unsqueeze(1), match_index]  # [B,N,4]
+    target = box_encode(matched, anchor.expand(B, -1, -1), variances)
+    return match_index, match_iou, positive, negative, target

@@ -1,0 +1,366 @@
+"""CenterNet head decode — drop-in for ``tauv_vision.centernet.model.decode``.
+
+Same names, positional order and error behaviour as the reference
+(/root/reference/src/tauv_vision/centernet/model/decode.py): ``heatmap_nms`` (:239-252),
+``heatmap_detect`` (:255-279), ``decode`` (:179-236), ``decode_keypoints`` (:51-176),
+``angle_get_bins`` (:282-288), ``angle_decode`` (:291-316), ``depth_decode`` (:319-324) and the
+``Detection`` / ``KeypointDetection`` records (:16-48).  All tensor work happens in
+libtauv_b200 (csrc/centernet_decode.cu); Python only builds the per-frame lists the reference
+signature demands, after ONE device->host copy of the packed results (the reference does
+~8 blocking scalar reads per detection).
+
+Tie order (the reference leaves it to torch.topk): score descending, then flat index ascending —
+the order the reference's own known-answer check (decode.py:327-339) asserts.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from math import atan2, pi
+from typing import Any, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from ... import _lib
+
+TOPK_RAW = 0
+TOPK_SIGMOID_PEAK = 1
+BOX_DECODE = 0
+BOX_KEYPOINTS = 1
+
+
+@dataclass
+class Detection:
+    label: int
+    score: float
+    y: float
+    x: float
+    h: float
+    w: float
+
+    yaw: Optional[float] = None
+    pitch: Optional[float] = None
+    roll: Optional[float] = None
+
+    depth: Optional[float] = None
+
+
+@dataclass
+class KeypointDetection:
+    label: int
+    score: float
+
+    y: float
+    x: float
+
+    w: float
+    h: float
+    depth: float
+
+    keypoints: List[Optional[Tuple[float, float, float]]]
+    keypoint_scores: List[Optional[float]]
+    keypoint_affinities: List[Optional[Tuple[float, float, float]]]
+
+    cam_t_object: Any
+
+
+@dataclass
+class PackedDetections:
+    """Device-resident result of one decode launch chain (nothing here has synchronised).
+
+    index [B,k,2] i64 (y,x) · label [B,k] i64 · score [B,k] f32 · yx [B,k,2] f64 · hw [B,k,2] f32 ·
+    depth [B,k] f32 or None · count [B] i32 = entries before the first score < threshold.
+    """
+    index: torch.Tensor
+    label: torch.Tensor
+    score: torch.Tensor
+    yx: torch.Tensor
+    hw: torch.Tensor
+    depth: Optional[torch.Tensor]
+    count: torch.Tensor
+
+    def to_host(self) -> dict:
+        """One synchronising device->host transfer of everything."""
+        out = {k: getattr(self, k).cpu().numpy() for k in ("index", "label", "score", "yx", "hw", "count")}
+        out["depth"] = self.depth.cpu().numpy() if self.depth is not None else None
+        return out
+
+    def to_lists(self) -> List[List[Detection]]:
+        h = self.to_host()
+        frames = []
+        for b in range(h["count"].shape[0]):
+            dets = []
+            for i in range(int(h["count"][b])):
+                dets.append(Detection(
+                    label=int(h["label"][b, i]),
+                    score=float(h["score"][b, i]),
+                    y=float(h["yx"][b, i, 0]),
+                    x=float(h["yx"][b, i, 1]),
+                    h=float(h["hw"][b, i, 0]),
+                    w=float(h["hw"][b, i, 1]),
+                    depth=float(h["depth"][b, i]) if h["depth"] is not None else None,
+                ))
+            frames.append(dets)
+        return frames
+
+
+# ------------------------------------------------------------------------------------------------
+# heatmap_nms / heatmap_detect
+# ------------------------------------------------------------------------------------------------
+
+def _as_heatmap(heatmap: torch.Tensor) -> torch.Tensor:
+    if heatmap.dim() != 4:
+        raise ValueError(f"heatmap must be [batch, n_heatmaps, h, w]; got {tuple(heatmap.shape)}")
+    return _lib.f32c(heatmap)
+
+
+def heatmap_nms(heatmap: torch.Tensor, kernel_size: int) -> torch.Tensor:
+    """(max_pool2d(h, k, 1, (k-1)//2) == h).float() * h     — reference decode.py:239-252."""
+    assert kernel_size >= 1 and kernel_size % 2 == 1
+    dev = _lib.require_cuda(heatmap)
+    hm = _as_heatmap(heatmap)
+    out = torch.empty_like(hm)
+    B, C, H, W = hm.shape
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().tauv_heatmap_nms(_lib.fptr(hm), _lib.fptr(out), B, C, H, W, int(kernel_size), 0,
+                                                _lib.stream_ptr(dev)))
+    return out
+
+
+def _topk(hm: torch.Tensor, k: int, mode: int):
+    dev = hm.device
+    B, C, H, W = hm.shape
+    lib = _lib.load()
+    k = int(k)
+    if k > C * H * W:
+        raise RuntimeError(f"selected index k out of range (k={k} > {C * H * W})")
+    index = torch.empty((B, k, 2), dtype=torch.int64, device=dev)
+    label = torch.empty((B, k), dtype=torch.int64, device=dev)
+    score = torch.empty((B, k), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = lib.tauv_heatmap_topk_workspace_bytes(B, C, H, W, k)
+        ws = _lib.workspace(dev, nbytes)
+        _lib.check(lib.tauv_heatmap_topk(_lib.fptr(hm), B, C, H, W, k, mode, _lib.i64ptr(index), _lib.i64ptr(label),
+                                         _lib.fptr(score), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)))
+    return index, label, score
+
+
+def heatmap_detect(heatmap: torch.Tensor, n_detections: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Joint top-k over C*H*W per frame -> (index [B,k,2], label [B,k], score [B,k])   — decode.py:255-279."""
+    _lib.require_cuda(heatmap)
+    return _topk(_as_heatmap(heatmap), n_detections, TOPK_RAW)
+
+
+def heatmap_peaks(heatmap_logits: torch.Tensor, n_detections: int):
+    """sigmoid -> heatmap_nms(3) -> heatmap_detect in one pass over the logits (decode.py:182-184)."""
+    _lib.require_cuda(heatmap_logits)
+    return _topk(_as_heatmap(heatmap_logits), n_detections, TOPK_SIGMOID_PEAK)
+
+
+# ------------------------------------------------------------------------------------------------
+# decode
+# ------------------------------------------------------------------------------------------------
+
+def _depth_view(depth: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if depth is None:
+        return None
+    if depth.dim() == 4:  # [B,H,W,1] permuted view (centernet.py:89)
+        depth = depth[..., 0]
+    return depth if depth.dtype == torch.float32 else depth.to(torch.float32)
+
+
+def decode_packed(prediction, model_config, n_detections: int, score_threshold: float) -> PackedDetections:
+    """Device part of ``decode``: two kernel launches, no synchronisation, permuted views taken as-is."""
+    hm = prediction.heatmap
+    dev = _lib.require_cuda(hm, prediction.size, prediction.offset, prediction.depth)
+    hm = _as_heatmap(hm)
+    size = prediction.size if prediction.size.dtype == torch.float32 else prediction.size.float()
+    offset = prediction.offset if prediction.offset.dtype == torch.float32 else prediction.offset.float()
+    depth = _depth_view(prediction.depth)
+    B, C, H, W = hm.shape
+    k = int(n_detections)
+    if k > C * H * W:
+        raise RuntimeError(f"selected index k out of range (k={k} > {C * H * W})")
+    lib = _lib.load()
+    index = torch.empty((B, k, 2), dtype=torch.int64, device=dev)
+    label = torch.empty((B, k), dtype=torch.int64, device=dev)
+    score = torch.empty((B, k), dtype=torch.float32, device=dev)
+    yx = torch.empty((B, k, 2), dtype=torch.float64, device=dev)
+    hw = torch.empty((B, k, 2), dtype=torch.float32, device=dev)
+    depth_out = torch.empty((B, k), dtype=torch.float32, device=dev) if depth is not None else None
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = lib.tauv_heatmap_topk_workspace_bytes(B, C, H, W, k)
+        ws = _lib.workspace(dev, nbytes)
+        _lib.check(lib.tauv_centernet_decode(
+            _lib.fptr(hm), B, C, H, W, k,
+            _lib.fptr(size), _lib.strides_arg(size, 4),
+            _lib.fptr(offset), _lib.strides_arg(offset, 4),
+            _lib.fptr(depth), _lib.strides_arg(depth, 3) if depth is not None else None,
+            BOX_DECODE, int(model_config.downsample_ratio), int(model_config.in_h), int(model_config.in_w),
+            float(score_threshold),
+            _lib.i64ptr(index), _lib.i64ptr(label), _lib.fptr(score), _lib.dptr(yx), _lib.fptr(hw),
+            _lib.fptr(depth_out), _lib.i32ptr(count), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)))
+    return PackedDetections(index, label, score, yx, hw, depth_out, count)
+
+
+def decode(prediction, model_config, n_detections: int, score_threshold: float) -> List[List[Detection]]:
+    """Reference signature (decode.py:179-236): per-frame lists of ``Detection``."""
+    return decode_packed(prediction, model_config, n_detections, score_threshold).to_lists()
+
+
+# ------------------------------------------------------------------------------------------------
+# decode_keypoints
+# ------------------------------------------------------------------------------------------------
+
+def decode_keypoints(prediction, model_config, object_config, M_projection: np.ndarray,
+                     n_detections: int, keypoint_n_detections: int,
+                     score_threshold: float, keypoint_score_threshold: float,
+                     keypoint_angle_threshold: float) -> List[List[KeypointDetection]]:
+    """Reference signature (decode.py:51-176).
+
+    Device: both fused peak/top-k passes, the object box gather and the affinity gather.
+    Host (as in the reference, on <= n_detections x keypoint_n_detections scalars): the greedy
+    keypoint->object association and the optional PnP tail.  ``keypoint_angle_threshold`` is
+    accepted and unused, exactly like the reference.
+    """
+    dev = _lib.require_cuda(prediction.heatmap, prediction.keypoint_heatmap, prediction.keypoint_affinity,
+                            prediction.size, prediction.depth)
+    lib = _lib.load()
+    hm = _as_heatmap(prediction.heatmap)
+    B, C, H, W = hm.shape
+    k = int(n_detections)
+    kk = int(keypoint_n_detections)
+    index, label, score = _topk(hm, k, TOPK_SIGMOID_PEAK)
+    kp_hm = _as_heatmap(prediction.keypoint_heatmap)
+    kp_index, kp_label, kp_score = _topk(kp_hm, kk, TOPK_SIGMOID_PEAK)
+
+    size = prediction.size if prediction.size.dtype == torch.float32 else prediction.size.float()
+    depth = _depth_view(prediction.depth)
+    yx = torch.empty((B, k, 2), dtype=torch.float64, device=dev)
+    hw = torch.empty((B, k, 2), dtype=torch.float32, device=dev)
+    depth_out = torch.empty((B, k), dtype=torch.float32, device=dev) if depth is not None else None
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    aff = prediction.keypoint_affinity
+    aff = aff if aff.dtype == torch.float32 else aff.float()
+    kp_aff = torch.empty((B, kk, 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.tauv_centernet_boxes(
+            _lib.i64ptr(index), _lib.fptr(score), B, k, H, W,
+            _lib.fptr(size), _lib.strides_arg(size, 4), None, None,
+            _lib.fptr(depth), _lib.strides_arg(depth, 3) if depth is not None else None,
+            BOX_KEYPOINTS, int(model_config.downsample_ratio), int(model_config.in_h), int(model_config.in_w),
+            int(model_config.out_h), int(model_config.out_w), float(score_threshold),
+            _lib.dptr(yx), _lib.fptr(hw), _lib.fptr(depth_out), _lib.i32ptr(count), _lib.stream_ptr(dev)))
+        sb, sk, sc, sy, sx = aff.stride()
+        _lib.check(lib.tauv_gather_at(_lib.fptr(aff), sb, sk, sc, sy, sx, 2, _lib.i64ptr(kp_index),
+                                      _lib.i64ptr(kp_label), B, kk, _lib.fptr(kp_aff), _lib.stream_ptr(dev)))
+
+    # one synchronising transfer of everything the host loop needs
+    h_label, h_score, h_yx, h_hw = label.cpu().numpy(), score.cpu().numpy(), yx.cpu().numpy(), hw.cpu().numpy()
+    h_count = count.cpu().numpy()
+    h_depth = depth_out.cpu().numpy() if depth_out is not None else None
+    h_kp_index, h_kp_label = kp_index.cpu().numpy(), kp_label.cpu().numpy()
+    h_kp_score, h_kp_aff = kp_score.cpu().numpy(), kp_aff.cpu().numpy()
+    kp_thr = np.float32(keypoint_score_threshold)
+    out_h, out_w = np.float32(model_config.out_h), np.float32(model_config.out_w)
+
+    detections = []
+    for b in range(B):
+        sample = []
+        for i in range(int(h_count[b])):
+            lab = int(h_label[b, i])
+            n_kp = len(object_config.configs[lab].keypoints)
+            sample.append(KeypointDetection(
+                label=lab, score=float(h_score[b, i]),
+                y=float(h_yx[b, i, 0]), x=float(h_yx[b, i, 1]),
+                h=float(h_hw[b, i, 0]), w=float(h_hw[b, i, 1]),
+                depth=float(h_depth[b, i]) if h_depth is not None else None,
+                keypoints=[None] * n_kp, keypoint_scores=[None] * n_kp, keypoint_affinities=[None] * n_kp,
+                cam_t_object=None))
+
+        match_detection = None
+        for j in range(kk):
+            if h_kp_score[b, j] < kp_thr:  # decode.py:99-100 (fp32 compare)
+                break
+            kp_score_f = float(h_kp_score[b, j])
+            kl = int(h_kp_label[b, j])
+            obj_i, obj_kp_i = object_config.decode_keypoint_index(kl)
+            cands = [d for d in sample if d.label == obj_i and d.keypoints[obj_kp_i] is None]
+            if not cands:
+                continue
+            ky = float(np.float32(h_kp_index[b, j, 0]) / out_h)  # int64 tensor / int -> fp32 divide
+            kx = float(np.float32(h_kp_index[b, j, 1]) / out_w)
+            ay, ax = float(h_kp_aff[b, j, 0]), float(h_kp_aff[b, j, 1])
+            ang = atan2(ay, ax)
+            errs = [abs(ang - atan2(ky - d.y, kx - d.x)) for d in cands]
+            match_detection = cands[errs.index(min(errs))]
+            match_detection.keypoints[obj_kp_i] = (ky, kx)
+            match_detection.keypoint_affinities[obj_kp_i] = (ay, ax)
+            match_detection.keypoint_scores[obj_kp_i] = kp_score_f
+
+        _pnp_tail(sample, match_detection, model_config, object_config, M_projection)
+        detections.append(sample)
+    return detections
+
+
+def _pnp_tail(sample, match_detection, model_config, object_config, M_projection):
+    """decode.py:137-172 — host-side cv2.solvePnP for objects with >= 6 keypoints.  The reference
+    stores the pose on the *last matched* detection (``match_detection``), not on ``detection``;
+    that quirk is kept.  Needs cv2 (+ spatialmath for the SE3 wrapper); silently skipped without."""
+    todo = [d for d in sample if sum(kp is not None for kp in d.keypoints) >= 6]
+    if not todo or match_detection is None:
+        return
+    try:
+        import cv2
+    except ImportError:  # pragma: no cover
+        return
+    for d in todo:
+        img_pts, cam_pts = [], []
+        for i, kp in enumerate(d.keypoints):
+            if kp is not None:
+                img_pts.append([kp[1] * model_config.in_w, kp[0] * model_config.in_h])
+                cam_pts.append(object_config.configs[d.label].keypoints[i])
+        ok, rvec, tvec = cv2.solvePnP(np.array(cam_pts, dtype=np.float64), np.array(img_pts, dtype=np.float64),
+                                      M_projection, None, flags=cv2.SOLVEPNP_ITERATIVE)
+        if ok:
+            rotm, _ = cv2.Rodrigues(rvec)
+            try:
+                from spatialmath import SE3, SO3
+                match_detection.cam_t_object = SE3.Rt(SO3(rotm), tvec)
+            except ImportError:
+                match_detection.cam_t_object = (rotm, tvec)
+
+
+# ------------------------------------------------------------------------------------------------
+# angle / depth decoders (elementwise; a6 of the scope table)
+# ------------------------------------------------------------------------------------------------
+
+def angle_get_bins(bin_overlap: float):
+    """((centre, min, max) of bin 0, same of bin 1)   — decode.py:282-288."""
+    bin_0 = (pi / 2, -bin_overlap / 2, pi + bin_overlap / 2)
+    bin_1 = (-pi / 2, -pi - bin_overlap / 2, bin_overlap / 2)
+    return bin_0, bin_1
+
+
+def angle_decode(predicted_bin: torch.Tensor, predicted_offset: torch.Tensor, theta_range: float,
+                 bin_overlap: float) -> torch.Tensor:
+    """Two-bin angle decode [B,n,4]x2 -> [B,n]   — decode.py:291-316 (no live caller in the reference)."""
+    dev = _lib.require_cuda(predicted_bin, predicted_offset)
+    pb, po = _lib.f32c(predicted_bin), _lib.f32c(predicted_offset)
+    n = pb.numel() // 4
+    out = torch.empty(pb.shape[:-1], dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().tauv_angle_decode(_lib.fptr(pb), _lib.fptr(po), n, float(theta_range),
+                                                 _lib.fptr(out), _lib.stream_ptr(dev)))
+    return out
+
+
+def depth_decode(prediction: torch.Tensor) -> torch.Tensor:
+    """1/sigmoid(d) - 1, any shape   — decode.py:319-324."""
+    dev = _lib.require_cuda(prediction)
+    p = _lib.f32c(prediction)
+    out = torch.empty_like(p)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().tauv_depth_decode(_lib.fptr(p), p.numel(), _lib.fptr(out), _lib.stream_ptr(dev)))
+    return out

@@ -1,0 +1,103 @@
+"""CenterNet training-target encoding — drop-in for the target-render half of
+``tauv_vision.centernet.model.loss`` (/root/reference/src/tauv_vision/centernet/model/loss.py):
+``generate_heatmap`` (:31-72), ``generate_keypoint_heatmap`` (:75-135),
+``out_index_for_position`` (:138-142), the sub-pixel offset target (:263-264) and
+``gaussian_splat`` (missing from the snapshot; call sites decode.py:328-332).
+
+The loss arithmetic itself (focal / L1 / angle / depth terms, autograd) is out of scope: it consumes
+the tensors produced here.  Kernels: csrc/gaussian_encode.cu.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+
+from ... import _lib
+
+
+def _u8(t: torch.Tensor) -> torch.Tensor:
+    t = t.contiguous()
+    return t.view(torch.uint8) if t.dtype == torch.bool else t.to(torch.uint8)
+
+
+def _i64(t: torch.Tensor) -> torch.Tensor:
+    return t.contiguous() if t.dtype == torch.int64 else t.to(torch.int64).contiguous()
+
+
+def generate_heatmap(truth, model_config, train_config, object_config) -> torch.Tensor:
+    """[B, n_labels, out_h, out_w] Gaussian class heatmap   — reference loss.py:31-72."""
+    dev = _lib.require_cuda(truth.valid, truth.label, truth.center)
+    B, n = truth.valid.shape
+    C = int(object_config.n_labels)
+    H, W = int(model_config.out_h), int(model_config.out_w)
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+    valid, label, center = _u8(truth.valid), _i64(truth.label), _lib.f32c(truth.center)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().tauv_gaussian_encode(
+            _lib.u8ptr(valid), _lib.i64ptr(label), _lib.fptr(center), B, n, C, H, W,
+            int(model_config.in_h), int(model_config.in_w), int(model_config.downsample_ratio),
+            float(train_config.keypoint_heatmap_sigma), _lib.fptr(out), _lib.stream_ptr(dev)))
+    return out
+
+
+def generate_keypoint_heatmap(truth, model_config, train_config, object_config
+                              ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(heatmap [B,Kp,H,W], affinity_weight [B,Kp,H,W], affinity [B,Kp,2,H,W])   — loss.py:75-135."""
+    dev = _lib.require_cuda(truth.keypoint_valid, truth.keypoint_label, truth.keypoint_center,
+                            truth.keypoint_object_index, truth.center)
+    B, m = truth.keypoint_valid.shape
+    n_obj = truth.center.shape[1]
+    Kp = int(object_config.n_keypoints)
+    H, W = int(model_config.out_h), int(model_config.out_w)
+    heatmap = torch.empty((B, Kp, H, W), dtype=torch.float32, device=dev)
+    weight = torch.empty((B, Kp, H, W), dtype=torch.float32, device=dev)
+    affinity = torch.empty((B, Kp, 2, H, W), dtype=torch.float32, device=dev)
+    kv, kl = _u8(truth.keypoint_valid), _i64(truth.keypoint_label)
+    kc, ko = _lib.f32c(truth.keypoint_center), _i64(truth.keypoint_object_index)
+    center = _lib.f32c(truth.center)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().tauv_keypoint_encode(
+            _lib.u8ptr(kv), _lib.i64ptr(kl), _lib.fptr(kc), _lib.i64ptr(ko), _lib.fptr(center),
+            B, m, n_obj, Kp, H, W, int(model_config.in_h), int(model_config.in_w),
+            int(model_config.downsample_ratio), float(train_config.keypoint_heatmap_sigma),
+            float(train_config.keypoint_affinity_sigma), _lib.fptr(heatmap), _lib.fptr(weight),
+            _lib.fptr(affinity), _lib.stream_ptr(dev)))
+    return heatmap, weight, affinity
+
+
+def _index_offset(position: torch.Tensor, model_config, want_offset: bool):
+    dev = _lib.require_cuda(position)
+    pos = _lib.f32c(position)
+    n = pos.numel() // 2
+    index = torch.empty(pos.shape, dtype=torch.int64, device=dev)
+    offset = torch.empty(pos.shape, dtype=torch.float32, device=dev) if want_offset else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().tauv_out_index_offset(
+            _lib.fptr(pos), n, int(model_config.in_h), int(model_config.in_w), int(model_config.downsample_ratio),
+            int(model_config.out_h), int(model_config.out_w), _lib.i64ptr(index), _lib.fptr(offset),
+            _lib.stream_ptr(dev)))
+    return index, offset
+
+
+def out_index_for_position(position: torch.Tensor, model_config) -> torch.Tensor:
+    """[B,n,2] normalised (y,x) -> clamped output-grid cell [B,n,2] i64   — loss.py:138-142."""
+    return _index_offset(position, model_config, False)[0]
+
+
+def offset_target(center: torch.Tensor, model_config) -> torch.Tensor:
+    """Sub-pixel regression target ``pix - ratio*trunc(pix/ratio)``   — loss.py:263-264."""
+    return _index_offset(center, model_config, True)[1]
+
+
+def gaussian_splat(h: int, w: int, cy: int, cx: int, sigma: float, device=None) -> torch.Tensor:
+    """[h,w] plane exp(-((x-cx)^2+(y-cy)^2)/(2 sigma^2)); the helper the reference's own KAT
+    (decode.py:327-339) and tests/centernet_square_detection.py:108-112 import."""
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if dev.type != "cuda":
+        raise RuntimeError("tauv_vision_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+    out = torch.empty((int(h), int(w)), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().tauv_gaussian_splat(int(h), int(w), int(cy), int(cx), float(sigma), _lib.fptr(out),
+                                                   _lib.stream_ptr(dev)))
+    return out

@@ -1,0 +1,382 @@
+// gaussian_encode.cu — CenterNet training-target rendering on sm_100a.
+//
+// Replaces (reference file:line under src/tauv_vision/centernet/model/loss.py):
+//   :31-72    generate_heatmap            (B*n_objects Python iterations x 7 ATen launches)
+//   :75-135   generate_keypoint_heatmap   (~25 launches per keypoint instance)
+//   :138-142  out_index_for_position, :263-264 sub-pixel offset target
+// plus gaussian_splat (call sites decode.py:328-332).
+//
+// Both renderers are pure output-write streams: one CTA per (frame, channel) plane band, the
+// frame's objects filtered into shared memory once, then float4 stores.  exp() is monotone, and
+// the reference uses one sigma for every object, so max_o exp(-d2_o/s) == exp(-(min_o d2_o)/s):
+// one exp per pixel instead of one per (pixel, object), with bit-identical results.
+#include "common.cuh"
+
+namespace tauv {
+
+constexpr int kEncThreads = 256;
+constexpr int kEncBandElems = 16384;
+
+// cy = floor(center*in / ratio), fp32 multiply then fp32 divide (loss.py:51-52), clamped so the
+// integer distance arithmetic cannot overflow (far-away centres render as exact zeros anyway).
+__device__ __forceinline__ int grid_floor(float c, float in_sz, float ratio) {
+  float v = __fdiv_rn(__fmul_rn(c, in_sz), ratio);
+  v = floorf(v);
+  v = fminf(fmaxf(v, -1.0e9f), 1.0e9f);
+  return (int)v;
+}
+
+__device__ __forceinline__ float gauss_from_d2(long long d2, float two_sigma2) {
+  // -((x-cx)^2+(y-cy)^2) is an int64 tensor; "/ (2*sigma**2)" promotes to fp32 and divides in fp32
+  return expf(__fdiv_rn((float)(-d2), two_sigma2));
+}
+
+struct PlaneObjs {
+  int n;
+  bool big;
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(kEncThreads) gaussian_encode_kernel(
+    const uint8_t* __restrict__ valid, const int64_t* __restrict__ label, const float* __restrict__ center,
+    int n_objects, int C, int H, int W, float in_h, float in_w, float ratio, float two_sigma2, int bands,
+    int rows_per_band, float* __restrict__ out) {
+  extern __shared__ int s_obj[];  // [2*n_objects] (cy, cx) of the objects rendered into this plane
+  __shared__ int s_n;
+  __shared__ int s_big;
+  const int tid = threadIdx.x;
+  const int band = blockIdx.x % bands;
+  const long long plane = blockIdx.x / bands;
+  const int c = (int)(plane % C);
+  const long long b = plane / C;
+  if (tid == 0) { s_n = 0; s_big = 0; }
+  __syncthreads();
+  for (int o = tid; o < n_objects; o += kEncThreads) {
+    const long long i = b * n_objects + o;
+    if (valid[i] && label[i] == c) {
+      const int cy = grid_floor(center[i * 2 + 0], in_h, ratio);
+      const int cx = grid_floor(center[i * 2 + 1], in_w, ratio);
+      const int slot = atomicAdd(&s_n, 1);
+      s_obj[2 * slot] = cy;
+      s_obj[2 * slot + 1] = cx;
+      if (abs(cy) > 20000 || abs(cx) > 20000) s_big = 1;
+    }
+  }
+  __syncthreads();
+  const int n = s_n;
+  const bool big = s_big != 0 || H > 10000 || W > 10000;
+  const int y0 = band * rows_per_band;
+  const int y1 = min(H, y0 + rows_per_band);
+  float* op = out + (size_t)plane * H * W;
+
+  auto value = [&](int y, int x) -> float {
+    if (!big) {
+      int best = 0x7fffffff;
+      for (int j = 0; j < n; ++j) {
+        const int dy = y - s_obj[2 * j], dx = x - s_obj[2 * j + 1];
+        best = min(best, dy * dy + dx * dx);
+      }
+      return gauss_from_d2((long long)best, two_sigma2);
+    } else {
+      long long best = 0x7fffffffffffffffLL;
+      for (int j = 0; j < n; ++j) {
+        const long long dy = y - s_obj[2 * j], dx = x - s_obj[2 * j + 1];
+        best = min(best, dy * dy + dx * dx);
+      }
+      return gauss_from_d2(best, two_sigma2);
+    }
+  };
+
+  if (VEC) {
+    const int S = W >> 2;
+    const int total = (y1 - y0) * S;
+    float4* o4 = reinterpret_cast<float4*>(op + (size_t)y0 * W);
+    if (n == 0) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int t = tid; t < total; t += kEncThreads) o4[t] = z;
+    } else {
+      for (int t = tid; t < total; t += kEncThreads) {
+        const int y = y0 + t / S;
+        const int x = (t % S) << 2;
+        float4 v;
+        v.x = value(y, x);
+        v.y = value(y, x + 1);
+        v.z = value(y, x + 2);
+        v.w = value(y, x + 3);
+        o4[t] = v;
+      }
+    }
+  } else {
+    const int total = (y1 - y0) * W;
+    float* o = op + (size_t)y0 * W;
+    for (int t = tid; t < total; t += kEncThreads) o[t] = (n == 0) ? 0.f : value(y0 + t / W, t % W);
+  }
+}
+
+// nan_to_num(x, nan) semantics (loss.py:116-118, :131-133): NaN -> nan, +-inf -> +-FLT_MAX
+__device__ __forceinline__ float nan_to_num(float v, float nan) {
+  if (v != v) return nan;
+  if (v == __int_as_float(0x7f800000)) return 3.4028234663852886e38f;
+  if (v == __int_as_float(0xff800000)) return -3.4028234663852886e38f;
+  return v;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kEncThreads) keypoint_encode_kernel(
+    const uint8_t* __restrict__ kp_valid, const int64_t* __restrict__ kp_label, const float* __restrict__ kp_center,
+    const int64_t* __restrict__ kp_obj, const float* __restrict__ center, int m, int n_objects, int Kp, int H, int W,
+    float in_h, float in_w, float ratio, float two_sh2, float two_sa2, int bands, int rows_per_band,
+    float* __restrict__ heatmap, float* __restrict__ weight, float* __restrict__ affinity) {
+  // per matching instance, in instance order: (cy, cx) ints + owning object's centre (fp32 y, x)
+  extern __shared__ int s_raw[];
+  int* s_c = s_raw;                                        // [2*m]
+  float* s_o = reinterpret_cast<float*>(s_raw + 2 * m);    // [2*m]
+  __shared__ int s_n, s_big;
+  const int tid = threadIdx.x;
+  const int band = blockIdx.x % bands;
+  const long long plane = blockIdx.x / bands;
+  const int k = (int)(plane % Kp);
+  const long long b = plane / Kp;
+  if (tid == 0) { s_n = 0; s_big = 0; }
+  __syncthreads();
+  if (tid < 32) {  // ordered compaction by one warp: instance order decides affinity ties (loss.py:122)
+    int base = 0;
+    for (int start = 0; start < m; start += 32) {
+      const int i = start + tid;
+      bool hit = false;
+      long long gi = 0;
+      if (i < m) {
+        gi = b * m + i;
+        hit = kp_valid[gi] && kp_label[gi] == k;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int slot = base + __popc(bal & ((1u << tid) - 1u));
+        const int cy = grid_floor(kp_center[gi * 2 + 0], in_h, ratio);
+        const int cx = grid_floor(kp_center[gi * 2 + 1], in_w, ratio);
+        s_c[2 * slot] = cy;
+        s_c[2 * slot + 1] = cx;
+        long long oi = kp_obj[gi];
+        if (oi < 0) oi += n_objects;  // torch negative indexing
+        oi = max(0LL, min((long long)n_objects - 1, oi));
+        s_o[2 * slot] = center[(b * n_objects + oi) * 2 + 0];
+        s_o[2 * slot + 1] = center[(b * n_objects + oi) * 2 + 1];
+        if (abs(cy) > 20000 || abs(cx) > 20000) s_big = 1;
+      }
+      base += __popc(bal);
+    }
+    if (tid == 0) s_n = base;
+  }
+  __syncthreads();
+  const int n = s_n;
+  const bool big = s_big != 0 || H > 10000 || W > 10000;
+  const int y0 = band * rows_per_band;
+  const int y1 = min(H, y0 + rows_per_band);
+  const size_t hw = (size_t)H * W;
+  float* hp = heatmap + (size_t)plane * hw;
+  float* wp = weight + (size_t)plane * hw;
+  float* ay = affinity + (size_t)plane * 2 * hw;
+  float* ax = ay + hw;
+  const float fh = (float)H, fw = (float)W;
+
+  auto eval = [&](int y, int x, float& vh, float& vw, float& vay, float& vax) {
+    long long best = 0x7fffffffffffffffLL;
+    if (!big) {
+      int bi = 0x7fffffff;
+      for (int j = 0; j < n; ++j) {
+        const int dy = y - s_c[2 * j], dx = x - s_c[2 * j + 1];
+        bi = min(bi, dy * dy + dx * dx);
+      }
+      best = bi;
+    } else {
+      for (int j = 0; j < n; ++j) {
+        const long long dy = y - s_c[2 * j], dx = x - s_c[2 * j + 1];
+        best = min(best, dy * dy + dx * dx);
+      }
+    }
+    vh = gauss_from_d2(best, two_sh2);
+    vw = gauss_from_d2(best, two_sa2);
+    // affinity: unit vector from the owning object's centre, nearest object wins, first on ties
+    const float py = __fdiv_rn((float)y, fh), px = __fdiv_rn((float)x, fw);  // loss.py:114
+    float cur = __int_as_float(0x7f800000);
+    float a0 = 0.f, a1 = 0.f;
+    for (int j = 0; j < n; ++j) {
+      const float dy = nan_to_num(__fsub_rn(py, s_o[2 * j]), 0.f);
+      const float dx = nan_to_num(__fsub_rn(px, s_o[2 * j + 1]), 0.f);
+      const float dist = nan_to_num(__fsqrt_rn(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx))), 1.f);
+      if (dist < cur) {
+        a0 = __fdiv_rn(dy, dist);
+        a1 = __fdiv_rn(dx, dist);
+        cur = dist;
+      }
+    }
+    vay = nan_to_num(a0, 0.f);
+    vax = nan_to_num(a1, 0.f);
+  };
+
+  if (VEC) {
+    const int S = W >> 2;
+    const int total = (y1 - y0) * S;
+    const size_t o0 = (size_t)y0 * W;
+    float4* h4 = reinterpret_cast<float4*>(hp + o0);
+    float4* w4 = reinterpret_cast<float4*>(wp + o0);
+    float4* y4 = reinterpret_cast<float4*>(ay + o0);
+    float4* x4 = reinterpret_cast<float4*>(ax + o0);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = tid; t < total; t += kEncThreads) {
+      if (n == 0) {
+        h4[t] = z; w4[t] = z; y4[t] = z; x4[t] = z;
+        continue;
+      }
+      const int y = y0 + t / S;
+      const int x = (t % S) << 2;
+      float4 vh, vw, vy, vx;
+      eval(y, x, vh.x, vw.x, vy.x, vx.x);
+      eval(y, x + 1, vh.y, vw.y, vy.y, vx.y);
+      eval(y, x + 2, vh.z, vw.z, vy.z, vx.z);
+      eval(y, x + 3, vh.w, vw.w, vy.w, vx.w);
+      h4[t] = vh; w4[t] = vw; y4[t] = vy; x4[t] = vx;
+    }
+  } else {
+    const int total = (y1 - y0) * W;
+    const size_t o0 = (size_t)y0 * W;
+    for (int t = tid; t < total; t += kEncThreads) {
+      float vh = 0.f, vw = 0.f, vy = 0.f, vx = 0.f;
+      if (n) eval(y0 + t / W, t % W, vh, vw, vy, vx);
+      hp[o0 + t] = vh; wp[o0 + t] = vw; ay[o0 + t] = vy; ax[o0 + t] = vx;
+    }
+  }
+}
+
+__global__ void out_index_offset_kernel(const float* __restrict__ pos, long long n, float in_h, float in_w,
+                                        float ratio, long long iratio, int out_h, int out_w,
+                                        int64_t* __restrict__ index, float* __restrict__ offset) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= 2 * n) return;
+  const int ax = (int)(t & 1);
+  const float in_sz = ax ? in_w : in_h;
+  const int out_sz = ax ? out_w : out_h;
+  const float pix = __fmul_rn(pos[t], in_sz);
+  // .to(torch.long) truncates toward zero; out-of-range / NaN follow the x86 cvttss2si convention
+  const float q = __fdiv_rn(pix, ratio);
+  long long cell;
+  if (!(q > -9.2e18f && q < 9.2e18f)) cell = (long long)0x8000000000000000ULL;
+  else cell = (long long)q;
+  long long ci = cell < 0 ? 0 : (cell > out_sz - 1 ? out_sz - 1 : cell);
+  index[t] = ci;
+  if (offset) offset[t] = __fsub_rn(pix, (float)(iratio * cell));  // loss.py:263-264 (unclamped cell)
+}
+
+__global__ void gaussian_splat_kernel(int h, int w, int cy, int cx, float two_sigma2, float* __restrict__ out) {
+  const long long n = (long long)h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long y = i / w, x = i % w;
+    const long long dy = y - cy, dx = x - cx;
+    out[i] = gauss_from_d2(dy * dy + dx * dx, two_sigma2);
+  }
+}
+
+static void band_plan(int H, int W, long long planes, int* bands, int* rows) {
+  int r = kEncBandElems / W;
+  if (r < 1) r = 1;
+  if (r > H) r = H;
+  // enough CTAs to fill the machine a few times over even for tiny batches
+  const int sms = num_sms();
+  while (r > 1 && planes * ((H + r - 1) / r) < 4LL * sms) r = (r + 1) / 2;
+  *rows = r;
+  *bands = (H + r - 1) / r;
+}
+
+}  // namespace tauv
+
+using namespace tauv;
+
+static float two_sigma_sq(double sigma) {
+  if (sigma < 0.1) sigma = 0.1;  // loss.py:60-62 ("tiny sigma!")
+  return (float)(2.0 * (sigma * sigma));
+}
+
+extern "C" int tauv_gaussian_encode(const uint8_t* valid, const int64_t* label, const float* center, int B,
+                                    int n_objects, int C, int H, int W, int in_h, int in_w, int downsample_ratio,
+                                    double sigma, float* out, tauv_stream_t stream) {
+  TAUV_REQUIRE(out, TAUV_E_NULL, "out must not be NULL");
+  TAUV_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && n_objects >= 0, TAUV_E_SHAPE, "bad shape");
+  TAUV_REQUIRE(n_objects == 0 || (valid && label && center), TAUV_E_NULL, "valid/label/center must not be NULL");
+  TAUV_REQUIRE(in_h > 0 && in_w > 0 && downsample_ratio > 0, TAUV_E_SHAPE, "bad model geometry");
+  TAUV_REQUIRE(n_objects <= 4096, TAUV_E_UNSUPPORTED, "n_objects=%d exceeds the built-in limit 4096", n_objects);
+  const long long planes = (long long)B * C;
+  int bands, rows;
+  band_plan(H, W, planes, &bands, &rows);
+  const long long grid = planes * bands;
+  TAUV_REQUIRE(grid < (1LL << 31), TAUV_E_UNSUPPORTED, "grid too large");
+  const size_t smem = (size_t)(n_objects > 0 ? n_objects : 1) * 8;
+  const bool vec = (W % 4 == 0) && ((uintptr_t)out % 16 == 0);
+  const float ts = two_sigma_sq(sigma);
+  if (vec)
+    gaussian_encode_kernel<true><<<(unsigned)grid, kEncThreads, smem, (cudaStream_t)stream>>>(
+        valid, label, center, n_objects, C, H, W, (float)in_h, (float)in_w, (float)downsample_ratio, ts, bands, rows, out);
+  else
+    gaussian_encode_kernel<false><<<(unsigned)grid, kEncThreads, smem, (cudaStream_t)stream>>>(
+        valid, label, center, n_objects, C, H, W, (float)in_h, (float)in_w, (float)downsample_ratio, ts, bands, rows, out);
+  TAUV_LAUNCH_CHECK("gaussian_encode_kernel");
+  return 0;
+}
+
+extern "C" int tauv_keypoint_encode(const uint8_t* kp_valid, const int64_t* kp_label, const float* kp_center,
+                                    const int64_t* kp_object_index, const float* center, int B, int m, int n_objects,
+                                    int Kp, int H, int W, int in_h, int in_w, int downsample_ratio,
+                                    double sigma_heatmap, double sigma_affinity, float* heatmap, float* weight,
+                                    float* affinity, tauv_stream_t stream) {
+  TAUV_REQUIRE(heatmap && weight && affinity, TAUV_E_NULL, "outputs must not be NULL");
+  TAUV_REQUIRE(B > 0 && Kp > 0 && H > 0 && W > 0 && m >= 0 && n_objects >= 0, TAUV_E_SHAPE, "bad shape");
+  TAUV_REQUIRE(m == 0 || (kp_valid && kp_label && kp_center && kp_object_index && center && n_objects > 0), TAUV_E_NULL,
+               "keypoint inputs must not be NULL");
+  TAUV_REQUIRE(in_h > 0 && in_w > 0 && downsample_ratio > 0, TAUV_E_SHAPE, "bad model geometry");
+  TAUV_REQUIRE(m <= 4096, TAUV_E_UNSUPPORTED, "n_keypoint_instances=%d exceeds the built-in limit 4096", m);
+  const long long planes = (long long)B * Kp;
+  int bands, rows;
+  band_plan(H, W, planes, &bands, &rows);
+  const long long grid = planes * bands;
+  TAUV_REQUIRE(grid < (1LL << 31), TAUV_E_UNSUPPORTED, "grid too large");
+  const size_t smem = (size_t)(m > 0 ? m : 1) * 16;
+  const bool vec = (W % 4 == 0) && ((uintptr_t)heatmap % 16 == 0) && ((uintptr_t)weight % 16 == 0) &&
+                   ((uintptr_t)affinity % 16 == 0) && (((size_t)H * W) % 4 == 0);
+  // generate_keypoint_heatmap does not floor sigma (loss.py:101,109): plain 2*sigma**2
+  const float tsh = (float)(2.0 * (sigma_heatmap * sigma_heatmap));
+  const float tsa = (float)(2.0 * (sigma_affinity * sigma_affinity));
+  if (vec)
+    keypoint_encode_kernel<true><<<(unsigned)grid, kEncThreads, smem, (cudaStream_t)stream>>>(
+        kp_valid, kp_label, kp_center, kp_object_index, center, m, n_objects, Kp, H, W, (float)in_h, (float)in_w,
+        (float)downsample_ratio, tsh, tsa, bands, rows, heatmap, weight, affinity);
+  else
+    keypoint_encode_kernel<false><<<(unsigned)grid, kEncThreads, smem, (cudaStream_t)stream>>>(
+        kp_valid, kp_label, kp_center, kp_object_index, center, m, n_objects, Kp, H, W, (float)in_h, (float)in_w,
+        (float)downsample_ratio, tsh, tsa, bands, rows, heatmap, weight, affinity);
+  TAUV_LAUNCH_CHECK("keypoint_encode_kernel");
+  return 0;
+}
+
+extern "C" int tauv_out_index_offset(const float* position, int64_t n, int in_h, int in_w, int downsample_ratio,
+                                     int out_h, int out_w, int64_t* index, float* offset, tauv_stream_t stream) {
+  TAUV_REQUIRE(n >= 0, TAUV_E_SHAPE, "n must be >= 0");
+  if (n == 0) return 0;
+  TAUV_REQUIRE(position && index, TAUV_E_NULL, "position/index must not be NULL");
+  TAUV_REQUIRE(in_h > 0 && in_w > 0 && downsample_ratio > 0 && out_h > 0 && out_w > 0, TAUV_E_SHAPE, "bad model geometry");
+  const long long tot = 2 * (long long)n;
+  out_index_offset_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      position, n, (float)in_h, (float)in_w, (float)downsample_ratio, downsample_ratio, out_h, out_w, index, offset);
+  TAUV_LAUNCH_CHECK("out_index_offset_kernel");
+  return 0;
+}
+
+extern "C" int tauv_gaussian_splat(int h, int w, int cy, int cx, double sigma, float* out, tauv_stream_t stream) {
+  TAUV_REQUIRE(out, TAUV_E_NULL, "out must not be NULL");
+  TAUV_REQUIRE(h > 0 && w > 0, TAUV_E_SHAPE, "bad shape");
+  const long long n = (long long)h * w;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gaussian_splat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(h, w, cy, cx,
+                                                                            (float)(2.0 * (sigma * sigma)), out);
+  TAUV_LAUNCH_CHECK("gaussian_splat_kernel");
+  return 0;
+}

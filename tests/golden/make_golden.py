@@ -1,0 +1,272 @@
+"""Freeze golden vectors from the REAL reference (run in the build container only).
+
+    python tests/golden/make_golden.py            # needs /root/reference/src
+
+Imports the unmodified TAUV-Vision modules (matplotlib / spatialmath stubbed in sys.modules — both
+unused on the tensor path), runs them on CPU fp32 over the seeded inputs of
+tests/synth.py and stores inputs + outputs as small .npz files next to this script.  The GPU box has
+no /root/reference: tests only read the .npz files.
+
+Cases whose order the reference leaves to torch.topk / torch.sort use "separated" inputs (all scores
+distinct), so the frozen order is the only possible one.
+"""
+from __future__ import annotations
+
+import sys
+import types
+from math import pi
+from pathlib import Path
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE.parent.parent))
+sys.path.insert(0, "/root/reference/src")
+for _name in ("matplotlib", "matplotlib.pyplot", "spatialmath"):
+    sys.modules[_name] = types.ModuleType(_name)
+sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+sys.modules["spatialmath"].SE3 = sys.modules["spatialmath"].SO3 = object
+
+from tauv_vision.centernet.model import decode as ref_decode  # noqa: E402
+from tauv_vision.centernet.model import loss as ref_loss  # noqa: E402
+from tauv_vision.centernet.model.centernet import Prediction  # noqa: E402
+from tauv_vision.centernet.model.config import (AngleConfig, ModelConfig, ObjectConfig, ObjectConfigSet,  # noqa: E402
+                                                TrainConfig)
+from tauv_vision.datasets.load.pose_dataset import PoseSample  # noqa: E402
+from tauv_vision.yolact.model import anchors as ref_anchors  # noqa: E402
+from tauv_vision.yolact.model import boxes as ref_boxes  # noqa: E402
+from tauv_vision.yolact.model import masks as ref_masks  # noqa: E402
+from tauv_vision.yolact.model import nms as ref_nms  # noqa: E402
+from tauv_vision.yolact.model.config import ModelConfig as YolactModelConfig  # noqa: E402
+
+from oracle import ref_port  # noqa: E402  (only for gaussian_splat, which the reference snapshot lacks)
+from tests import synth  # noqa: E402
+
+torch.set_num_threads(1)  # reduction order independent of the machine
+
+
+def save(name, **arrays):
+    out = {}
+    for k, v in arrays.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    np.savez_compressed(HERE / f"{name}.npz", **out)
+    print(f"{name}: " + ", ".join(f"{k}{list(np.shape(v))}" for k, v in out.items()))
+
+
+def cn_model_config(in_hw=512, downsamples=2):
+    return ModelConfig(backbone_heights=[], backbone_channels=[], in_h=in_hw, in_w=in_hw, downsamples=downsamples,
+                       angle_bin_overlap=pi / 3)
+
+
+def train_config(sig_h=2.0, sig_a=3.0):
+    return TrainConfig(lr=0, batch_size=0, n_batches=0, n_epochs=0, heatmap_focal_loss_a=2, heatmap_focal_loss_b=4,
+                       heatmap_sigma_factor=0.1, keypoint_heatmap_sigma=sig_h, keypoint_affinity_sigma=sig_a,
+                       loss_lambda_keypoint_heatmap=1, loss_lambda_keypoint_affinity=1, loss_lambda_size=1,
+                       loss_lambda_offset=1, loss_lambda_angle=1, loss_lambda_depth=1, n_workers=0,
+                       weight_save_interval=1)
+
+
+def object_configs(n_labels, kp_per_object=0):
+    ang = AngleConfig(train=False, modulo=None)
+    cfgs = []
+    for i in range(n_labels):
+        kps = [(0.1 * j, 0.0, 0.05 * i) for j in range(kp_per_object)] if kp_per_object else None
+        cfgs.append(ObjectConfig(id=f"obj{i}", yaw=ang, pitch=ang, roll=ang, train_depth=True,
+                                 train_keypoints=kp_per_object > 0, keypoints=kps))
+    return ObjectConfigSet(cfgs)
+
+
+def prediction(heatmap, size, offset, depth=None, kp_heatmap=None, kp_affinity=None):
+    return Prediction(heatmap=heatmap, keypoint_heatmap=kp_heatmap, keypoint_affinity=kp_affinity, size=size,
+                      offset=offset, roll_bin=None, roll_offset=None, pitch_bin=None, pitch_offset=None,
+                      yaw_bin=None, yaw_offset=None, depth=depth)
+
+
+def detections_to_arrays(dets, k):
+    """[[Detection]] -> padded arrays + count."""
+    B = len(dets)
+    lab = np.full((B, k), -1, np.int64)
+    sc = np.zeros((B, k), np.float32)
+    yx = np.zeros((B, k, 2), np.float64)
+    hw = np.zeros((B, k, 2), np.float32)
+    dep = np.zeros((B, k), np.float32)
+    cnt = np.zeros((B,), np.int32)
+    for b, frame in enumerate(dets):
+        cnt[b] = len(frame)
+        for i, d in enumerate(frame):
+            lab[b, i], sc[b, i] = int(d.label), float(d.score)
+            yx[b, i] = (d.y, d.x)
+            hw[b, i] = (d.h, d.w)
+            dep[b, i] = d.depth if d.depth is not None else 0.0
+    return dict(label=lab, score=sc, yx=yx, hw=hw, depth_out=dep, count=cnt)
+
+
+def main():
+    # ---- KAT of decode.py:327-339 -----------------------------------------------------------------
+    hm = torch.cat((ref_port.gaussian_splat(512, 512, 100, 100, 50).unsqueeze(0).unsqueeze(1),
+                    ref_port.gaussian_splat(512, 512, 200, 200, 50).unsqueeze(0).unsqueeze(1)), dim=1)
+    sup = ref_decode.heatmap_nms(hm, 3)
+    idx, lab, sc = ref_decode.heatmap_detect(sup, 100)
+    assert idx[0, 0, 0] == 100 and idx[0, 0, 1] == 100
+    save("kat_decode", index=idx[:, :2], label=lab[:, :2], score=sc, n_nonzero=int((sup != 0).sum()))
+
+    # ---- heatmap_nms / heatmap_detect, small separated ------------------------------------------------
+    logits = synth.separated_logits(2, 3, 24, 28, seed=11)
+    sig = torch.sigmoid(logits)
+    sup = ref_decode.heatmap_nms(sig, 3)
+    idx, lab, sc = ref_decode.heatmap_detect(sup, 40)
+    save("cn_nms_detect", logits=logits, suppressed=sup, index=idx, label=lab, score=sc)
+    # plateau behaviour of heatmap_nms (ties survive) on a quantised map
+    q = torch.round(synth.natural_logits(1, 2, 16, 16, seed=12, n_peaks=(2, 4)) * 2) / 2
+    save("cn_nms_plateau", heatmap=q, suppressed=ref_decode.heatmap_nms(q, 3),
+         suppressed5=ref_decode.heatmap_nms(q, 5))
+
+    # ---- decode(), separated, permuted head views, depth --------------------------------------------
+    mc = cn_model_config(128, 2)  # 32x32 map
+    logits = synth.separated_logits(3, 4, 32, 32, seed=21)
+    size, offset, depth = synth.head_views(3, 32, 32, seed=22)
+    dets = ref_decode.decode(prediction(logits, size, offset, depth), mc, 30, 0.8)
+    save("cn_decode", logits=logits, size=size.contiguous(), offset=offset.contiguous(), depth=depth.contiguous(),
+         in_h=128, downsamples=2, k=30, thr=0.8, **detections_to_arrays(dets, 30))
+    dets0 = ref_decode.decode(prediction(logits, size, offset, None), mc, 30, 0.0)
+    save("cn_decode_thr0", **detections_to_arrays(dets0, 30))
+
+    # ---- BASELINE config #1: square-detection scenario, batch 1, 1x256x256, stride 2 ------------------
+    mc1 = cn_model_config(512, 1)
+    g = synth.gen(31)
+    cy, cx = (int(v) for v in torch.randint(50, 207, (2,), generator=g))
+    s = 50 + 100 * float(torch.rand((1,), generator=g))
+    splat = ref_port.gaussian_splat(256, 256, cy, cx, 0.05 * s).clamp(1e-6, 1 - 1e-6)
+    logit1 = torch.log(splat / (1 - splat)).reshape(1, 1, 256, 256)
+    size1, offset1, _ = synth.head_views(1, 256, 256, seed=32, with_depth=False)
+    dets1 = ref_decode.decode(prediction(logit1, size1, offset1), mc1, 100, 0.5)
+    save("cn_config1", cy=cy, cx=cx, sigma=0.05 * s, **detections_to_arrays(dets1, 100))
+
+    # ---- decode_keypoints (association on host), 2 objects x 3 keypoints ------------------------------
+    oc = object_configs(2, kp_per_object=3)
+    mck = cn_model_config(128, 2)
+    logits = synth.separated_logits(2, 2, 32, 32, seed=41)
+    kp_logits = synth.separated_logits(2, 6, 32, 32, seed=42)
+    g = synth.gen(43)
+    kp_aff = torch.randn((2, 6, 2, 32, 32), generator=g)
+    size, offset, depth = synth.head_views(2, 32, 32, seed=44)
+    kd = ref_decode.decode_keypoints(prediction(logits, size, offset, depth, kp_logits, kp_aff), mck, oc,
+                                     np.eye(3), 6, 20, 0.8, 0.8, 0.3)
+    flat = []
+    for b, frame in enumerate(kd):
+        for i, d in enumerate(frame):
+            row = [b, i, d.label, d.score, d.y, d.x, d.h, d.w, d.depth]
+            for j in range(3):
+                kp = d.keypoints[j]
+                row += [1.0, kp[0], kp[1], d.keypoint_scores[j], d.keypoint_affinities[j][0],
+                        d.keypoint_affinities[j][1]] if kp is not None else [0.0] * 6
+            flat.append(row)
+    save("cn_decode_keypoints", logits=logits, kp_logits=kp_logits, kp_aff=kp_aff, size=size.contiguous(),
+         offset=offset.contiguous(), depth=depth.contiguous(), rows=np.array(flat, np.float64),
+         counts=np.array([len(f) for f in kd]))
+
+    # ---- angle_decode / depth_decode -------------------------------------------------------------------
+    g = synth.gen(51)
+    pb, po = torch.randn((2, 9, 4), generator=g), torch.randn((2, 9, 4), generator=g)
+    save("cn_angle_depth", bin=pb, offset=po, angle=ref_decode.angle_decode(pb, po, 2 * pi, pi / 3),
+         angle_pi=ref_decode.angle_decode(pb, po, pi, pi / 3), depth_in=po, depth=ref_decode.depth_decode(po))
+
+    # ---- target encode -----------------------------------------------------------------------------------
+    mce = cn_model_config(96, 2)  # 24x24 map
+    tc = train_config(2.0, 3.0)
+    oce = object_configs(4, kp_per_object=2)  # 4 labels, 8 keypoint channels
+    t = synth.pose_truth(2, 7, 4, seed=61, n_kp_inst=9, Kp=8)
+    t.center[0, 0] = torch.tensor([0.999, 0.0])  # edges
+    t.center[0, 1] = t.center[0, 2]             # two objects on one cell
+    t.label[0, 1] = t.label[0, 2]
+    t.valid[0, :3] = True
+    truth = PoseSample(img=None, valid=t.valid, label=t.label, center=t.center, size=t.size, roll=None, pitch=None,
+                       yaw=None, depth=None, keypoint_valid=t.keypoint_valid, keypoint_label=t.keypoint_label,
+                       keypoint_center=t.keypoint_center, keypoint_object_index=t.keypoint_object_index)
+    hm = ref_loss.generate_heatmap(truth, mce, tc, oce)
+    khm, kw, ka = ref_loss.generate_keypoint_heatmap(truth, mce, tc, oce)
+    oi = ref_loss.out_index_for_position(truth.center, mce)
+    pix = truth.center * torch.Tensor((mce.in_h, mce.in_w)).unsqueeze(0).unsqueeze(1)
+    off = pix - mce.downsample_ratio * (pix / mce.downsample_ratio).to(torch.long)
+    save("cn_encode", valid=t.valid, label=t.label, center=t.center, kp_valid=t.keypoint_valid,
+         kp_label=t.keypoint_label, kp_center=t.keypoint_center, kp_obj=t.keypoint_object_index, heatmap=hm,
+         kp_heatmap=khm, kp_weight=kw, kp_affinity=ka, out_index=oi, offset=off, in_h=96, downsamples=2,
+         sigma_h=2.0, sigma_a=3.0)
+
+    # ---- YOLACT anchors ------------------------------------------------------------------------------------
+    ycfg = YolactModelConfig(in_w=550, in_h=550, feature_depth=0, n_classes=0, n_prototype_masks=0,
+                             n_masknet_layers_pre_upsample=0, n_masknet_layers_post_upsample=0,
+                             n_prediction_head_layers=0, n_classification_layers=0, n_box_layers=0, n_mask_layers=0,
+                             n_fpn_downsample_layers=0, anchor_scales=(24, 48, 96, 192, 384),
+                             anchor_aspect_ratios=(1 / 2, 1, 2), box_variances=(0.1, 0.2), iou_pos_threshold=0.4,
+                             iou_neg_threshold=0.3, negative_example_ratio=3, img_mean=(0, 0, 0), img_stddev=(1, 1, 1))
+    small = [(7, 5), (4, 3), (2, 2), (1, 1), (1, 1)]
+    anc_small = torch.cat([ref_anchors.get_anchor(i, s, ycfg) for i, s in enumerate(small)], dim=1)
+    full = synth.fpn_sizes(550, 550)
+    anc_full = torch.cat([ref_anchors.get_anchor(i, s, ycfg) for i, s in enumerate(full)], dim=1)
+    assert anc_full.shape[1] == 19248, anc_full.shape
+    sel = torch.tensor([0, 1, 68, 69, 4760, 4761, 9522, 14282, 14283, 17957, 18932, 19175, 19247])
+    save("yl_anchors", small_sizes=np.array(small), small=anc_small, full_sizes=np.array(full), full_sel=sel,
+         full_rows=anc_full[0, sel], full_sum=anc_full.double().sum(dim=1))
+
+    # ---- box_decode / box_encode / iou_matrix ----------------------------------------------------------
+    N = anc_small.shape[1]
+    g = synth.gen(71)
+    enc = torch.randn((3, N, 4), generator=g) * 0.5
+    dec = ref_boxes.box_decode(enc, anc_small, ycfg)
+    re_enc = ref_boxes.box_encode(dec, anc_small.expand(3, -1, -1), ycfg)
+    ba = torch.cat((torch.rand((2, 9, 2), generator=g), torch.rand((2, 9, 2), generator=g) * 0.5), -1)
+    bb = torch.cat((torch.rand((1, 5, 2), generator=g), torch.rand((1, 5, 2), generator=g) * 0.5), -1)
+    save("yl_boxes", anchor=anc_small, enc=enc, dec=dec, re_enc=re_enc, box_a=ba, box_b=bb,
+         iou_ab=ref_boxes.iou_matrix(ba, bb), iou_aa=ref_boxes.iou_matrix(ba, ba),
+         corners=ref_boxes.box_to_corners(ba), xy_swap=ref_boxes.box_xy_swap(ba),
+         back=ref_boxes.corners_to_box(ref_boxes.box_to_corners(ba)))
+
+    # ---- nms (frame 0 only; separated confidences) -------------------------------------------------------
+    N = 1500
+    g = synth.gen(81)
+    anchor = torch.cat((torch.rand((1, N, 2), generator=g), torch.rand((1, N, 2), generator=g) * 0.3 + 0.05), -1)
+    cls, enc = synth.yolact_heads(2, N, 6, seed=82, anchor=anchor, separated=True)
+    box = ref_boxes.box_decode(enc, anchor, ycfg)
+    keep = ref_nms.nms(cls, box, 120, 0.5, 0.05)
+    keep_b = ref_nms.nms(cls, box, 120, 0.3, 0.5)
+    keep_1 = ref_nms.nms(cls[1:], box[1:], 120, 0.5, 0.05)
+    save("yl_nms", cls=cls, enc=enc, anchor=anchor, box=box, keep=keep, keep_b=keep_b, keep_frame1=keep_1,
+         top_k=120)
+
+    # ---- assemble_mask / box_to_mask ----------------------------------------------------------------------
+    proto, coeff, mbox = synth.mask_inputs(8, 20, 24, 5, seed=91)
+    save("yl_mask", proto=proto, coeff=coeff, box=mbox, mask=ref_masks.assemble_mask(proto, coeff, mbox),
+         mask_nobox=ref_masks.assemble_mask(proto, coeff, None), crop0=ref_boxes.box_to_mask(mbox[0], (20, 24)))
+
+    # ---- anchor matching: yolact/model/loss.py:16-22 + :62-66, line by line with the reference's own ops ----
+    tb, tv = synth.truth_boxes(3, 6, seed=101)
+    g = synth.gen(102)
+    for b in range(3):  # half of the truths sit on (jittered) priors so that positives exist
+        pick = torch.randint(0, anc_small.shape[1], (3,), generator=g)
+        a = anc_small[0, pick]
+        jit = torch.randn((3, 4), generator=g)
+        tb[b, :3] = torch.cat((a[:, :2] + 0.15 * jit[:, :2] * a[:, 2:], a[:, 2:] * (1 + 0.15 * jit[:, 2:])), -1)
+    tb[1, 4] = tb[1, 0]  # duplicated truth: the first one must win the argmax tie
+    tv[0, :3] = True
+    tv[1, 0] = tv[1, 4] = True
+    tv[2] = False  # a frame without any valid truth
+    iou = ref_boxes.iou_matrix(anc_small, tb)
+    match_iou, match_index = torch.max(iou * tv.unsqueeze(1).float(), dim=2)
+    positive = match_iou >= 0.4
+    negative = match_iou <= 0.3
+    targets, counts = [], []
+    for b in range(3):
+        tg = ref_boxes.box_encode(tb[b, match_index[b, positive[b]]].unsqueeze(0),
+                                  anc_small[0, positive[b]].unsqueeze(0), ycfg).squeeze(0)
+        targets.append(tg)
+        counts.append(tg.shape[0])
+    save("yl_match", anchor=anc_small, truth_box=tb, truth_valid=tv, match_iou=match_iou, match_index=match_index,
+         positive=positive, negative=negative, targets=torch.cat(targets, 0), counts=np.array(counts))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,162 @@
+"""CPU: the oracle (oracle/ref_port.py) against the golden vectors frozen from the REAL reference
+(tests/golden/make_golden.py) and against the reference's two in-module KATs."""
+from math import pi
+
+import numpy as np
+import torch
+
+from oracle import ref_port as O
+from tests import synth
+from tests.helpers import assert_close, assert_equal, flat_index, golden, t
+
+
+def test_kat_decode_main_block():
+    """decode.py:327-339 — two sigma=50 splats; (100,100) on class 0 must rank first."""
+    g = golden("kat_decode")
+    hm = torch.cat((O.gaussian_splat(512, 512, 100, 100, 50)[None, None],
+                    O.gaussian_splat(512, 512, 200, 200, 50)[None, None]), dim=1)
+    sup = O.heatmap_nms(hm, 3)
+    assert int((sup != 0).sum()) == int(g["n_nonzero"]) == 2
+    idx, lab, sc = O.heatmap_detect(sup, 100)
+    assert idx[0, 0].tolist() == [100, 100] and int(lab[0, 0]) == 0
+    assert_equal(idx[:, :2], g["index"], "index")
+    assert_equal(lab[:, :2], g["label"], "label")
+    assert_equal(sc, g["score"], "score")
+    # canonical order among the 98 zero-score fillers: ascending flat index
+    assert flat_index(idx[0, 2:], lab[0, 2:], 512, 512).tolist() == list(range(98))
+
+
+def test_yolact_boxes_main_block():
+    """yolact boxes.py:106-117 round trips (with the config argument the stale block forgot)."""
+    g = synth.gen(5)
+    box, anchor = torch.rand((1, 1, 4), generator=g), torch.rand((1, 1, 4), generator=g)
+    assert torch.allclose(box, O.corners_to_box(O.box_to_corners(box)))
+    assert torch.allclose(box, O.box_decode(O.box_encode(box, anchor, (0.1, 0.2)), anchor, (0.1, 0.2)), atol=1e-6)
+
+
+def test_nms_detect_golden():
+    g = golden("cn_nms_detect")
+    sup = O.heatmap_nms(torch.sigmoid(t(g["logits"])), 3)
+    assert_equal(sup, g["suppressed"], "heatmap_nms")
+    idx, lab, sc = O.heatmap_detect(sup, 40)
+    assert_equal(idx, g["index"]), assert_equal(lab, g["label"]), assert_equal(sc, g["score"])
+
+
+def test_nms_plateau_golden():
+    g = golden("cn_nms_plateau")
+    assert_equal(O.heatmap_nms(t(g["heatmap"]), 3), g["suppressed"])
+    assert_equal(O.heatmap_nms(t(g["heatmap"]), 5), g["suppressed5"])
+
+
+def _decode_inputs(g):
+    B, H, W = g["size"].shape[:3]
+    size = t(g["size"]).permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)  # NHWC view of NCHW storage
+    offset = t(g["offset"]).permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
+    depth = t(g["depth"]).permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
+    return t(g["logits"]), size, offset, depth
+
+
+def _check_packed(p, g, with_depth=True):
+    cnt = g["count"]
+    assert_equal(p.count, cnt, "count")
+    for b in range(len(cnt)):
+        n = int(cnt[b])
+        assert_equal(p.label[b, :n], g["label"][b, :n], "label")
+        assert_equal(p.score[b, :n], g["score"][b, :n], "score")
+        assert_equal(p.yx[b, :n], g["yx"][b, :n], "yx (fp64, bit exact)")
+        assert_equal(p.hw[b, :n], g["hw"][b, :n], "hw")
+        if with_depth:
+            assert_equal(p.depth[b, :n], g["depth_out"][b, :n], "depth")
+
+
+def test_decode_golden():
+    g = golden("cn_decode")
+    logits, size, offset, depth = _decode_inputs(g)
+    p = O.decode_packed(logits, size, offset, depth, 4, 128, 128, 30, 0.8)
+    _check_packed(p, g)
+    g0 = golden("cn_decode_thr0")
+    p0 = O.decode_packed(logits, size, offset, None, 4, 128, 128, 30, 0.0)
+    _check_packed(p0, g0, with_depth=False)
+    assert (g0["count"] == 30).all()
+
+
+def test_config1_square_detection_golden():
+    """BASELINE.json configs[0]: batch 1, one Gaussian on a 1x256x256 map, stride 2, decode(.., 100, 0.5)."""
+    g = golden("cn_config1")
+    splat = O.gaussian_splat(256, 256, int(g["cy"]), int(g["cx"]), float(g["sigma"])).clamp(1e-6, 1 - 1e-6)
+    logits = torch.log(splat / (1 - splat)).reshape(1, 1, 256, 256)
+    size, offset, _ = synth.head_views(1, 256, 256, seed=32, with_depth=False)
+    p = O.decode_packed(logits, size, offset, None, 2, 512, 512, 100, 0.5)
+    _check_packed(p, g, with_depth=False)
+    assert int(p.count[0]) >= 1 and p.index[0, 0].tolist() == [int(g["cy"]), int(g["cx"])]
+
+
+def test_angle_depth_golden():
+    g = golden("cn_angle_depth")
+    assert_equal(O.angle_decode(t(g["bin"]), t(g["offset"]), 2 * pi, pi / 3), g["angle"])
+    assert_equal(O.angle_decode(t(g["bin"]), t(g["offset"]), pi, pi / 3), g["angle_pi"])
+    assert_equal(O.depth_decode(t(g["depth_in"])), g["depth"])
+
+
+def test_encode_golden():
+    g = golden("cn_encode")
+    args = dict(out_h=24, out_w=24, in_h=96, in_w=96, downsample_ratio=4)
+    hm = O.generate_heatmap(t(g["valid"]), t(g["label"]), t(g["center"]), 4, sigma=float(g["sigma_h"]), **args)
+    assert_equal(hm, g["heatmap"], "generate_heatmap")
+    khm, kw, ka = O.generate_keypoint_heatmap(t(g["kp_valid"]), t(g["kp_label"]), t(g["kp_center"]), t(g["kp_obj"]),
+                                              t(g["center"]), 8, sigma_heatmap=float(g["sigma_h"]),
+                                              sigma_affinity=float(g["sigma_a"]), **args)
+    assert_equal(khm, g["kp_heatmap"]), assert_equal(kw, g["kp_weight"]), assert_equal(ka, g["kp_affinity"])
+    assert_equal(O.out_index_for_position(t(g["center"]), 96, 96, 4, 24, 24), g["out_index"])
+    assert_equal(O.offset_target(t(g["center"]), 96, 96, 4), g["offset"])
+
+
+def test_anchors_golden():
+    g = golden("yl_anchors")
+    cfg = synth.yolact_config()
+    small = O.all_anchors([tuple(s) for s in g["small_sizes"]], cfg.anchor_scales, cfg.anchor_aspect_ratios, 550, 550)
+    assert_equal(small, g["small"])
+    sizes = synth.fpn_sizes(550, 550)
+    assert [list(s) for s in sizes] == g["full_sizes"].tolist() == [[69, 69], [35, 35], [18, 18], [9, 9], [5, 5]]
+    full = O.all_anchors(sizes, cfg.anchor_scales, cfg.anchor_aspect_ratios, 550, 550)
+    assert full.shape == (1, 19248, 4)
+    assert_equal(full[0, t(g["full_sel"])], g["full_rows"])
+    assert_equal(full.double().sum(dim=1), g["full_sum"])
+
+
+def test_boxes_golden():
+    g = golden("yl_boxes")
+    v = (0.1, 0.2)
+    assert_equal(O.box_decode(t(g["enc"]), t(g["anchor"]), v), g["dec"])
+    assert_equal(O.box_encode(t(g["dec"]), t(g["anchor"]).expand(3, -1, -1), v), g["re_enc"])
+    assert_equal(O.iou_matrix(t(g["box_a"]), t(g["box_b"])), g["iou_ab"])
+    assert_equal(O.iou_matrix(t(g["box_a"]), t(g["box_a"])), g["iou_aa"])
+    assert_equal(O.box_to_corners(t(g["box_a"])), g["corners"])
+    assert_equal(O.corners_to_box(O.box_to_corners(t(g["box_a"]))), g["back"])
+
+
+def test_nms_golden():
+    g = golden("yl_nms")
+    cls, box = t(g["cls"]), t(g["box"])
+    assert_equal(O.box_decode(t(g["enc"]), t(g["anchor"]), (0.1, 0.2)), g["box"])
+    assert_equal(O.nms(cls, box, 120, 0.5, 0.05), g["keep"])
+    assert_equal(O.nms(cls, box, 120, 0.3, 0.5), g["keep_b"])
+    assert_equal(O.nms(cls[1:], box[1:], 120, 0.5, 0.05), g["keep_frame1"])
+
+
+def test_mask_golden():
+    g = golden("yl_mask")
+    proto, coeff, box = t(g["proto"]), t(g["coeff"]), t(g["box"])
+    assert_equal(O.assemble_mask(proto, coeff, box), g["mask"])
+    assert_equal(O.assemble_mask(proto, coeff, None), g["mask_nobox"])
+    assert_equal(O.box_to_mask(box[0], (20, 24)), g["crop0"])
+
+
+def test_match_golden():
+    g = golden("yl_match")
+    mi, miou, pos, neg, tgt = O.match_anchors(t(g["anchor"]), t(g["truth_box"]), t(g["truth_valid"]), 0.4, 0.3,
+                                              (0.1, 0.2))
+    assert_equal(mi, g["match_index"]), assert_equal(miou, g["match_iou"])
+    assert_equal(pos, g["positive"]), assert_equal(neg, g["negative"])
+    assert_equal(tgt[pos], g["targets"], "box_encode targets of the positives")
+    assert [int(p.sum()) for p in pos] == g["counts"].tolist()
