@@ -112,6 +112,21 @@ int tauv_centernet_decode(const float* heatmap_logits, int B, int C, int H, int 
                           int32_t* count, void* workspace, size_t workspace_bytes,
                           tauv_stream_t stream);
 
+/* The two launches of tauv_centernet_decode as separate calls, so that a caller (bench.py) can put
+ * stream events between them.  stage1 fills the workspace with per-item candidates (reads the
+ * logits once); stage2 merges them per frame and does the box arithmetic.  Same workspace, same
+ * shapes, same stream for both. */
+int tauv_heatmap_topk_stage1(const float* heatmap, int B, int C, int H, int W, int k, int mode,
+                             void* workspace, size_t workspace_bytes, tauv_stream_t stream);
+int tauv_centernet_decode_stage2(int B, int C, int H, int W, int k, const float* size,
+                                 const int64_t size_strides[4], const float* offset,
+                                 const int64_t offset_strides[4], const float* depth,
+                                 const int64_t depth_strides[3], int mode, int downsample_ratio,
+                                 int in_h, int in_w, float score_threshold, int64_t* index,
+                                 int64_t* label, float* score, double* yx, float* hw,
+                                 float* depth_out, int32_t* count, void* workspace,
+                                 size_t workspace_bytes, tauv_stream_t stream);
+
 /* Gather `nch` channels at the ranked peak positions from a strided [B, ..., H, W] map:
  * out[b,j,c] = src[b*sb + sel(b,j)*ssel + c*sc + iy*sy + ix*sx], where sel is label[b,j]
  * (or 0 if label is NULL).  Used for keypoint_affinity[b,label,0:2,y,x] (decode.py:121-122). */

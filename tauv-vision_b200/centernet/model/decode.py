@@ -169,8 +169,12 @@ def _depth_view(depth: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return depth if depth.dtype == torch.float32 else depth.to(torch.float32)
 
 
-def decode_packed(prediction, model_config, n_detections: int, score_threshold: float) -> PackedDetections:
-    """Device part of ``decode``: two kernel launches, no synchronisation, permuted views taken as-is."""
+def decode_packed(prediction, model_config, n_detections: int, score_threshold: float,
+                  stage_events=None) -> PackedDetections:
+    """Device part of ``decode``: two kernel launches, no synchronisation, permuted views taken as-is.
+
+    ``stage_events`` (profiling hook): three ``torch.cuda.Event(enable_timing=True)`` recorded on the current
+    stream before the tile kernel, between the two kernels, and after the merge kernel."""
     hm = prediction.heatmap
     dev = _lib.require_cuda(hm, prediction.size, prediction.offset, prediction.depth)
     hm = _as_heatmap(hm)
@@ -192,15 +196,23 @@ def decode_packed(prediction, model_config, n_detections: int, score_threshold: 
     with torch.cuda.device(dev):
         nbytes = lib.tauv_heatmap_topk_workspace_bytes(B, C, H, W, k)
         ws = _lib.workspace(dev, nbytes)
-        _lib.check(lib.tauv_centernet_decode(
-            _lib.fptr(hm), B, C, H, W, k,
-            _lib.fptr(size), _lib.strides_arg(size, 4),
-            _lib.fptr(offset), _lib.strides_arg(offset, 4),
-            _lib.fptr(depth), _lib.strides_arg(depth, 3) if depth is not None else None,
-            BOX_DECODE, int(model_config.downsample_ratio), int(model_config.in_h), int(model_config.in_w),
-            float(score_threshold),
-            _lib.i64ptr(index), _lib.i64ptr(label), _lib.fptr(score), _lib.dptr(yx), _lib.fptr(hw),
-            _lib.fptr(depth_out), _lib.i32ptr(count), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)))
+        tail = (_lib.fptr(size), _lib.strides_arg(size, 4),
+                _lib.fptr(offset), _lib.strides_arg(offset, 4),
+                _lib.fptr(depth), _lib.strides_arg(depth, 3) if depth is not None else None,
+                BOX_DECODE, int(model_config.downsample_ratio), int(model_config.in_h), int(model_config.in_w),
+                float(score_threshold),
+                _lib.i64ptr(index), _lib.i64ptr(label), _lib.fptr(score), _lib.dptr(yx), _lib.fptr(hw),
+                _lib.fptr(depth_out), _lib.i32ptr(count), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+        if stage_events is None:
+            _lib.check(lib.tauv_centernet_decode(_lib.fptr(hm), B, C, H, W, k, *tail))
+        else:
+            e0, e1, e2 = stage_events
+            e0.record()
+            _lib.check(lib.tauv_heatmap_topk_stage1(_lib.fptr(hm), B, C, H, W, k, TOPK_SIGMOID_PEAK, ws.data_ptr(),
+                                                    ws.numel(), _lib.stream_ptr(dev)))
+            e1.record()
+            _lib.check(lib.tauv_centernet_decode_stage2(B, C, H, W, k, *tail))
+            e2.record()
     return PackedDetections(index, label, score, yx, hw, depth_out, count)
 
 

@@ -575,31 +575,45 @@ static int check_topk_shape(int B, int C, int H, int W, int k) {
   return 0;
 }
 
-static int run_topk(const float* hm, int B, int C, int H, int W, int k, int mode, int64_t* index,
-                    int64_t* label, float* score, const BoxArgs& box, void* ws, size_t ws_bytes,
-                    cudaStream_t st) {
-  TopkPlan p;
-  make_plan(B, C, H, W, k, hm, &p);
+static int plan_and_check(const float* hm, int B, int C, int H, int W, int k, void* ws, size_t ws_bytes, TopkPlan* p,
+                          TileArgs* a) {
+  make_plan(B, C, H, W, k, hm, p);
   TAUV_REQUIRE(ws != nullptr && (uintptr_t)ws % 256 == 0, TAUV_E_WORKSPACE, "workspace must be 256-byte aligned");
-  TAUV_REQUIRE(ws_bytes >= p.cand_bytes + p.count_bytes, TAUV_E_WORKSPACE, "workspace %zu < required %zu", ws_bytes,
-               p.cand_bytes + p.count_bytes);
-  TAUV_REQUIRE(p.smem_bytes <= 227 * 1024, TAUV_E_UNSUPPORTED, "tile needs %zu B shared memory", p.smem_bytes);
-  TileArgs a;
-  a.hm = hm; a.C = C; a.H = H; a.W = W; a.k = k;
-  a.R = p.rows_per_chunk; a.slot_elems = p.slot_elems; a.rows_per_item = p.rows_per_item;
-  a.items_per_plane = p.items_per_plane; a.cap = p.cap; a.soft = p.soft;
-  a.cand = reinterpret_cast<unsigned long long*>(ws);
-  a.cand_count = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws) + p.cand_bytes);
-  const long long items = (long long)B * p.items_per_frame;
+  TAUV_REQUIRE(ws_bytes >= p->cand_bytes + p->count_bytes, TAUV_E_WORKSPACE, "workspace %zu < required %zu", ws_bytes,
+               p->cand_bytes + p->count_bytes);
+  TAUV_REQUIRE(p->smem_bytes <= 227 * 1024, TAUV_E_UNSUPPORTED, "tile needs %zu B shared memory", p->smem_bytes);
+  a->hm = hm; a->C = C; a->H = H; a->W = W; a->k = k;
+  a->R = p->rows_per_chunk; a->slot_elems = p->slot_elems; a->rows_per_item = p->rows_per_item;
+  a->items_per_plane = p->items_per_plane; a->cap = p->cap; a->soft = p->soft;
+  a->cand = reinterpret_cast<unsigned long long*>(ws);
+  a->cand_count = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws) + p->cand_bytes);
+  const long long items = (long long)B * p->items_per_frame;
   TAUV_REQUIRE(items < (1LL << 31), TAUV_E_UNSUPPORTED, "too many items (%lld)", items);
+  return 0;
+}
 
+// stage 1: per-item candidates into the workspace
+static int run_stage1(const float* hm, int B, int C, int H, int W, int k, int mode, void* ws, size_t ws_bytes,
+                      cudaStream_t st) {
+  TopkPlan p;
+  TileArgs a;
+  if (int e = plan_and_check(hm, B, C, H, W, k, ws, ws_bytes, &p, &a)) return e;
+  const long long items = (long long)B * p.items_per_frame;
   void (*kern)(TileArgs) = nullptr;
   if (mode == TAUV_TOPK_SIGMOID_PEAK) kern = p.bulk ? tile_topk_kernel<1, true> : tile_topk_kernel<1, false>;
   else kern = p.bulk ? tile_topk_kernel<0, true> : tile_topk_kernel<0, false>;
   TAUV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
   kern<<<(unsigned)items, kTileThreads, p.smem_bytes, st>>>(a);
   TAUV_LAUNCH_CHECK("tile_topk_kernel");
+  return 0;
+}
 
+// stage 2: per-frame merge of the workspace candidates (+ boxes)
+static int run_stage2(int B, int C, int H, int W, int k, int mode, int64_t* index, int64_t* label, float* score,
+                      const BoxArgs& box, void* ws, size_t ws_bytes, cudaStream_t st) {
+  TopkPlan p;
+  TileArgs a;
+  if (int e = plan_and_check(nullptr, B, C, H, W, k, ws, ws_bytes, &p, &a)) return e;
   int p2 = 1;
   while (p2 < k) p2 <<= 1;
   const size_t msmem = (size_t)p2 * 8 + (size_t)(kRadixBins > k ? kRadixBins : k) * 4;
@@ -615,6 +629,12 @@ static int run_topk(const float* hm, int B, int C, int H, int W, int k, int mode
   }
   TAUV_LAUNCH_CHECK("merge_kernel");
   return 0;
+}
+
+static int run_topk(const float* hm, int B, int C, int H, int W, int k, int mode, int64_t* index, int64_t* label,
+                    float* score, const BoxArgs& box, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (int e = run_stage1(hm, B, C, H, W, k, mode, ws, ws_bytes, st)) return e;
+  return run_stage2(B, C, H, W, k, mode, index, label, score, box, ws, ws_bytes, st);
 }
 
 static int fill_box_args(BoxArgs* g, const float* size, const int64_t* ss, const float* offset, const int64_t* os,
@@ -724,4 +744,29 @@ extern "C" int tauv_gather_at(const float* src, int64_t sb, int64_t ssel, int64_
                                                                                     index, label, n, k, out);
   TAUV_LAUNCH_CHECK("gather_at_kernel");
   return 0;
+}
+
+extern "C" int tauv_heatmap_topk_stage1(const float* heatmap, int B, int C, int H, int W, int k, int mode,
+                                        void* workspace, size_t workspace_bytes, tauv_stream_t stream) {
+  TAUV_REQUIRE(heatmap, TAUV_E_NULL, "heatmap must not be NULL");
+  TAUV_REQUIRE(mode == TAUV_TOPK_RAW || mode == TAUV_TOPK_SIGMOID_PEAK, TAUV_E_SHAPE, "bad top-k mode %d", mode);
+  if (int e = check_topk_shape(B, C, H, W, k)) return e;
+  return run_stage1(heatmap, B, C, H, W, k, mode, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int tauv_centernet_decode_stage2(int B, int C, int H, int W, int k, const float* size,
+                                            const int64_t size_strides[4], const float* offset,
+                                            const int64_t offset_strides[4], const float* depth,
+                                            const int64_t depth_strides[3], int mode, int downsample_ratio, int in_h,
+                                            int in_w, float score_threshold, int64_t* index, int64_t* label,
+                                            float* score, double* yx, float* hw, float* depth_out, int32_t* count,
+                                            void* workspace, size_t workspace_bytes, tauv_stream_t stream) {
+  TAUV_REQUIRE(index && label && score, TAUV_E_NULL, "index/label/score must not be NULL");
+  if (int e = check_topk_shape(B, C, H, W, k)) return e;
+  BoxArgs g{};
+  if (int e = fill_box_args(&g, size, size_strides, offset, offset_strides, depth, depth_strides, mode,
+                            downsample_ratio, in_h, in_w, H, W, score_threshold, yx, hw, depth_out, count))
+    return e;
+  return run_stage2(B, C, H, W, k, TAUV_TOPK_SIGMOID_PEAK, index, label, score, g, workspace, workspace_bytes,
+                    (cudaStream_t)stream);
 }

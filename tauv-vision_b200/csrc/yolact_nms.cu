@@ -1,0 +1,350 @@
+// yolact_nms.cu — YOLACT confidence, top-k and Fast NMS on sm_100a.
+//
+// Replaces (reference file:line under src/tauv_vision/yolact/model/nms.py):
+//   :9-10   softmax(classification)[..., 1:].max(-1)       (full [B,N,C1] softmax materialised today)
+//   :12-17  full-N descending sort, first top_k of frame 0
+//   :19-22  iou_matrix of the top_k boxes, triu(1), column max
+//   :24-27  keep = (iou_max <= thr) & (conf >= thr); idx[keep]
+// and the decode of only the top_k priors (boxes.py:55-61) for the fused detect entry point.
+//
+// K1 scores_kernel   : one warp per class row, lanes across classes, coalesced 4-byte loads straight from
+//                      HBM (rows are 324 B, never 16-B aligned), shuffle max / sum.  Reads cls exactly once.
+// K2 nms_frame_kernel: one CTA per frame: radix-select the top_k (confidence desc, prior asc), bitonic
+//                      sort, boxes to shared memory, 32x32 IoU tiles -> per-column suppression bitmask
+//                      (__ballot + atomicOr), ordered compaction of the survivors.
+#include "common.cuh"
+#include "yolact_common.cuh"
+
+namespace tauv {
+
+constexpr int kNmsThreads = 1024;
+constexpr int kNmsMaxTopK = 4096;
+
+// ---- K1 ----------------------------------------------------------------------------------------
+// NCH = ceil(C1/32) register-resident chunks per lane (C1 <= 128); NCH = 0 -> generic two-pass loop.
+template <int NCH, bool ARGMAX>
+__global__ void __launch_bounds__(256) scores_kernel(const float* __restrict__ cls, long long rows, int C1,
+                                                     float* __restrict__ score, int32_t* __restrict__ argmax_all) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  // a warp owns blocks of 32 consecutive rows so that the results leave as one coalesced store
+  for (long long blk = warp; blk * 32 < rows; blk += nwarps) {
+    const long long row0 = blk * 32;
+    const int nrows = (int)min(32LL, rows - row0);
+    float my_score = 0.f;
+    int my_arg = 0;
+    for (int r = 0; r < nrows; ++r) {
+      const float* x = cls + (row0 + r) * C1;
+      float m = TAUV_NEG_INF, mfg = TAUV_NEG_INF;
+      float best_v = TAUV_NEG_INF;
+      int best_i = 0x7fffffff;
+      float sum = 0.f;
+      if (NCH > 0) {
+        float v[NCH > 0 ? NCH : 1];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int j = lane + 32 * c;
+          v[c] = (j < C1) ? __ldg(x + j) : TAUV_NEG_INF;
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int j = lane + 32 * c;
+          m = fmaxf(m, v[c]);
+          if (j >= 1) mfg = fmaxf(mfg, v[c]);
+          if (ARGMAX && j < C1 && v[c] > best_v) { best_v = v[c]; best_i = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          mfg = fmaxf(mfg, __shfl_xor_sync(0xffffffffu, mfg, o));
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int j = lane + 32 * c;
+          if (j < C1) sum = __fadd_rn(sum, expf(__fsub_rn(v[c], m)));
+        }
+      } else {
+        for (int j = lane; j < C1; j += 32) {
+          const float t = __ldg(x + j);
+          m = fmaxf(m, t);
+          if (j >= 1) mfg = fmaxf(mfg, t);
+          if (ARGMAX && t > best_v) { best_v = t; best_i = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          mfg = fmaxf(mfg, __shfl_xor_sync(0xffffffffu, mfg, o));
+        }
+        for (int j = lane; j < C1; j += 32) sum = __fadd_rn(sum, expf(__fsub_rn(__ldg(x + j), m)));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+      // softmax is monotone per row: max_j>=1 softmax_j = exp(max_fg - max) / sum
+      const float s = __fdiv_rn(expf(__fsub_rn(mfg, m)), sum);
+      if (ARGMAX) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+          if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
+        }
+      }
+      if (lane == r) {
+        my_score = s;
+        my_arg = best_i;
+      }
+    }
+    if (lane < nrows) {
+      score[row0 + lane] = my_score;
+      if (ARGMAX) argmax_all[row0 + lane] = my_arg;
+    }
+  }
+}
+
+// ---- K2 ----------------------------------------------------------------------------------------
+struct NmsArgs {
+  const float* score;      // [B,N]
+  const float4* box;       // decoded [B,N,4] or NULL
+  const float4* enc;       // [B,N,4] (when box == NULL)
+  const float4* anchor;    // [1 or B,N,4]
+  int anchor_batch;
+  float v0, v1;
+  int N, top_k;
+  float iou_thr, conf_thr;
+  int64_t* keep;           // [B,top_k]
+  int32_t* n_keep;         // [B]
+  float4* keep_box;        // [B,top_k,4] or NULL
+  float* keep_score;       // [B,top_k] or NULL
+};
+
+__global__ void __launch_bounds__(kNmsThreads) nms_frame_kernel(NmsArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const int N = a.N;
+  const int K = min(a.top_k, N);
+  int p2 = 1;
+  while (p2 < K) p2 <<= 1;
+  unsigned long long* sel = reinterpret_cast<unsigned long long*>(smem_raw);       // [p2]
+  float* cor = reinterpret_cast<float*>(smem_raw + (size_t)p2 * 8);                 // [5][p2] SoA corners+area
+  uint32_t* hist = reinterpret_cast<uint32_t*>(cor + 5 * (size_t)p2);               // [2048]
+  uint32_t* sup = hist;                                                              // reused: [p2/32]
+  __shared__ uint32_t ctl[8];
+  __shared__ int s_wsum[kNmsThreads / 32];
+  const float* sc = a.score + (size_t)b * N;
+
+  if (tid == 0) ctl[5] = 0;
+  for (int i = tid; i < p2; i += kNmsThreads) sel[i] = 0ull;
+  __syncthreads();
+  auto load = [&](int i) -> unsigned long long { return make_composite(float_to_key(sc[i]), (uint32_t)i); };
+  const unsigned long long T = block_kth_largest<kNmsThreads>(load, N, K, hist, ctl);
+  for (int i = tid; i < N; i += kNmsThreads) {
+    const unsigned long long c = load(i);
+    if (c >= T) sel[atomicAdd(&ctl[5], 1u)] = c;
+  }
+  __syncthreads();
+  block_bitonic_sort_desc<kNmsThreads>(sel, p2);  // (confidence desc, prior index asc)
+
+  // boxes of the ranked priors -> corners in shared memory (decoded on the fly in detect mode)
+  for (int r = tid; r < K; r += kNmsThreads) {
+    const uint32_t idx = composite_idx(sel[r]);
+    float4 bx;
+    if (a.box) {
+      bx = a.box[(size_t)b * N + idx];
+    } else {
+      const float4 an = a.anchor[(a.anchor_batch == 1 ? 0 : (size_t)b * N) + idx];
+      bx = decode_one(a.enc[(size_t)b * N + idx], an, a.v0, a.v1);
+    }
+    const Corners c = to_corners(bx);
+    cor[r] = c.y0; cor[p2 + r] = c.x0; cor[2 * p2 + r] = c.y1; cor[3 * p2 + r] = c.x1; cor[4 * p2 + r] = c.area;
+    if (a.keep_box) a.keep_box[(size_t)b * a.top_k + r] = bx;  // ranked order for now; compacted below
+  }
+  const int T32 = (K + 31) >> 5;
+  for (int i = tid; i < T32; i += kNmsThreads) sup[i] = 0u;
+  __syncthreads();
+
+  // Fast NMS: column j is suppressed iff some earlier-ranked i < j has iou(i,j) > thr (nms.py:19-24; a NaN
+  // IoU also suppresses because `NaN <= thr` is False).  Tiles (I <= J) of 32x32 pairs, one warp per tile.
+  const int ntiles = T32 * (T32 + 1) / 2;
+  for (int t = warp; t < ntiles; t += kNmsThreads / 32) {
+    // unrank t -> (J, I) with I <= J, tiles enumerated column by column
+    int J = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while ((J + 1) * (J + 2) / 2 <= t) ++J;
+    while (J * (J + 1) / 2 > t) --J;
+    const int I = t - J * (J + 1) / 2;
+    const int j = J * 32 + lane;
+    bool s = false;
+    if (j < K) {
+      Corners cj;
+      cj.y0 = cor[j]; cj.x0 = cor[p2 + j]; cj.y1 = cor[2 * p2 + j]; cj.x1 = cor[3 * p2 + j]; cj.area = cor[4 * p2 + j];
+      const int i_end = min(I * 32 + 32, j);  // strictly upper triangle
+      for (int i = I * 32; i < i_end; ++i) {
+        Corners ci;
+        ci.y0 = cor[i]; ci.x0 = cor[p2 + i]; ci.y1 = cor[2 * p2 + i]; ci.x1 = cor[3 * p2 + i]; ci.area = cor[4 * p2 + i];
+        const float iou = iou_pair(ci, cj);
+        s = s || !(iou <= a.iou_thr);
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, s);
+    if (lane == 0 && bal) atomicOr(&sup[J], bal);
+  }
+  __syncthreads();
+
+  // ordered compaction of the survivors
+  int base = 0;
+  const float conf_thr = a.conf_thr;
+  for (int start = 0; start < K; start += kNmsThreads) {
+    const int r = start + tid;
+    bool kp = false;
+    unsigned long long c = 0ull;
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < K) {
+      c = sel[r];
+      const float conf = key_to_float(composite_key(c));
+      kp = !((sup[r >> 5] >> (r & 31)) & 1u) && (conf >= conf_thr);
+      if (a.keep_box) bx = a.keep_box[(size_t)b * a.top_k + r];
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, kp);
+    if (lane == 0) s_wsum[warp] = __popc(bal);
+    __syncthreads();
+    int pos = base + __popc(bal & ((1u << lane) - 1u));
+    int tot = 0;
+    for (int w = 0; w < kNmsThreads / 32; ++w) {
+      if (w < warp) pos += s_wsum[w];
+      tot += s_wsum[w];
+    }
+    if (kp) {
+      a.keep[(size_t)b * a.top_k + pos] = (int64_t)composite_idx(c);
+      if (a.keep_score) a.keep_score[(size_t)b * a.top_k + pos] = key_to_float(composite_key(c));
+    }
+    __syncthreads();  // every thread has read its ranked box before anyone overwrites a slot
+    if (kp && a.keep_box) a.keep_box[(size_t)b * a.top_k + pos] = bx;
+    base += tot;
+    __syncthreads();
+  }
+  if (tid == 0) a.n_keep[b] = base;
+}
+
+// argmax over ALL classes for the kept priors (yolact_node.py:129 / evaluate_batch.py:93-95)
+__global__ void keep_class_kernel(const float* __restrict__ cls, const int64_t* __restrict__ keep,
+                                  const int32_t* __restrict__ n_keep, int N, int C1, int top_k,
+                                  int32_t* __restrict__ keep_class) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_keep[b]) return;
+  const float* x = cls + ((size_t)b * N + keep[(size_t)b * top_k + r]) * C1;
+  float best_v = TAUV_NEG_INF;
+  int best_i = 0x7fffffff;
+  for (int j = lane; j < C1; j += 32) {
+    const float t = x[j];
+    if (t > best_v) { best_v = t; best_i = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
+  }
+  if (lane == 0) keep_class[(size_t)b * top_k + r] = best_i == 0x7fffffff ? 0 : best_i;
+}
+
+static int launch_scores(const float* cls, long long rows, int C1, float* score, int32_t* argmax_all, cudaStream_t st) {
+  const long long blocks_needed = (rows + 32 * 8 - 1) / (32 * 8);  // 8 warps per CTA, 32 rows per warp
+  long long blocks = blocks_needed;
+  const long long cap = (long long)num_sms() * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const int nch = (C1 + 31) / 32;
+#define TAUV_SCORES(NCH)                                                                                       \
+  do {                                                                                                          \
+    if (argmax_all) scores_kernel<NCH, true><<<(unsigned)blocks, 256, 0, st>>>(cls, rows, C1, score, argmax_all); \
+    else scores_kernel<NCH, false><<<(unsigned)blocks, 256, 0, st>>>(cls, rows, C1, score, argmax_all);          \
+  } while (0)
+  switch (nch) {
+    case 1: TAUV_SCORES(1); break;
+    case 2: TAUV_SCORES(2); break;
+    case 3: TAUV_SCORES(3); break;
+    case 4: TAUV_SCORES(4); break;
+    default: TAUV_SCORES(0); break;
+  }
+#undef TAUV_SCORES
+  TAUV_LAUNCH_CHECK("scores_kernel");
+  return 0;
+}
+
+static size_t nms_smem(int K) {
+  int p2 = 1;
+  while (p2 < K) p2 <<= 1;
+  return (size_t)p2 * 8 + (size_t)p2 * 5 * 4 + kRadixBins * 4;
+}
+
+static int run_nms(const float* cls, const float* box, const float* enc, const float* anchor, int anchor_batch, float v0,
+                   float v1, int B, int N, int C1, int n_frames, int top_k, float iou_thr, float conf_thr,
+                   int64_t* keep, int32_t* n_keep, float* keep_box, float* keep_score, int32_t* keep_class, void* ws,
+                   size_t ws_bytes, cudaStream_t st) {
+  TAUV_REQUIRE(cls && keep && n_keep, TAUV_E_NULL, "cls/keep/n_keep must not be NULL");
+  TAUV_REQUIRE(B > 0 && N > 0 && C1 >= 2 && top_k > 0, TAUV_E_SHAPE, "bad shape B=%d N=%d C1=%d top_k=%d", B, N, C1, top_k);
+  TAUV_REQUIRE(n_frames > 0 && n_frames <= B, TAUV_E_SHAPE, "n_frames=%d must be in [1,%d]", n_frames, B);
+  TAUV_REQUIRE(top_k <= kNmsMaxTopK, TAUV_E_UNSUPPORTED, "top_k=%d exceeds the built-in limit %d", top_k, kNmsMaxTopK);
+  const size_t need = align_up((size_t)n_frames * N * 4, 256);
+  TAUV_REQUIRE(ws && (uintptr_t)ws % 256 == 0 && ws_bytes >= need, TAUV_E_WORKSPACE, "workspace %zu < required %zu", ws_bytes, need);
+  float* score = reinterpret_cast<float*>(ws);
+  if (int e = launch_scores(cls, (long long)n_frames * N, C1, score, nullptr, st)) return e;
+  NmsArgs a;
+  a.score = score; a.box = (const float4*)box; a.enc = (const float4*)enc; a.anchor = (const float4*)anchor;
+  a.anchor_batch = anchor_batch; a.v0 = v0; a.v1 = v1; a.N = N; a.top_k = top_k; a.iou_thr = iou_thr; a.conf_thr = conf_thr;
+  a.keep = keep; a.n_keep = n_keep; a.keep_box = (float4*)keep_box; a.keep_score = keep_score;
+  const size_t smem = nms_smem(top_k < N ? top_k : N);
+  TAUV_CUDA(cudaFuncSetAttribute(nms_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nms_frame_kernel<<<n_frames, kNmsThreads, smem, st>>>(a);
+  TAUV_LAUNCH_CHECK("nms_frame_kernel");
+  if (keep_class) {
+    dim3 grid((top_k * 32 + 255) / 256, n_frames);
+    keep_class_kernel<<<grid, 256, 0, st>>>(cls, keep, n_keep, N, C1, top_k, keep_class);
+    TAUV_LAUNCH_CHECK("keep_class_kernel");
+  }
+  return 0;
+}
+
+}  // namespace tauv
+
+using namespace tauv;
+
+extern "C" int tauv_yolact_scores(const float* cls, int B, int N, int C1, float* score, int32_t* argmax_all,
+                                  tauv_stream_t stream) {
+  TAUV_REQUIRE(cls && score, TAUV_E_NULL, "cls/score must not be NULL");
+  TAUV_REQUIRE(B > 0 && N > 0 && C1 >= 2, TAUV_E_SHAPE, "bad shape B=%d N=%d C1=%d", B, N, C1);
+  return launch_scores(cls, (long long)B * N, C1, score, argmax_all, (cudaStream_t)stream);
+}
+
+extern "C" size_t tauv_yolact_nms_workspace_bytes(int B, int N, int C1, int top_k) {
+  (void)C1; (void)top_k;
+  if (B <= 0 || N <= 0) return 0;
+  return align_up((size_t)B * N * 4, 256);
+}
+
+extern "C" int tauv_yolact_fast_nms(const float* cls, const float* box, int B, int N, int C1, int n_frames, int top_k,
+                                    float iou_threshold, float confidence_threshold, int64_t* keep, int32_t* n_keep,
+                                    void* workspace, size_t workspace_bytes, tauv_stream_t stream) {
+  TAUV_REQUIRE(box, TAUV_E_NULL, "box must not be NULL");
+  TAUV_REQUIRE((uintptr_t)box % 16 == 0, TAUV_E_ALIGN, "box must be 16-byte aligned");
+  return run_nms(cls, box, nullptr, nullptr, 1, 0.f, 0.f, B, N, C1, n_frames, top_k, iou_threshold,
+                 confidence_threshold, keep, n_keep, nullptr, nullptr, nullptr, workspace, workspace_bytes,
+                 (cudaStream_t)stream);
+}
+
+extern "C" int tauv_yolact_detect(const float* cls, const float* enc, const float* anchor, int B, int N, int C1,
+                                  int anchor_batch, float v0, float v1, int top_k, float iou_threshold,
+                                  float confidence_threshold, int64_t* keep, int32_t* n_keep, float* keep_box,
+                                  float* keep_score, int32_t* keep_class, void* workspace, size_t workspace_bytes,
+                                  tauv_stream_t stream) {
+  TAUV_REQUIRE(enc && anchor, TAUV_E_NULL, "enc/anchor must not be NULL");
+  TAUV_REQUIRE(anchor_batch == 1 || anchor_batch == B, TAUV_E_SHAPE, "anchor batch %d must be 1 or %d", anchor_batch, B);
+  TAUV_REQUIRE((uintptr_t)enc % 16 == 0 && (uintptr_t)anchor % 16 == 0 && (uintptr_t)keep_box % 16 == 0, TAUV_E_ALIGN,
+               "box tensors must be 16-byte aligned");
+  return run_nms(cls, nullptr, enc, anchor, anchor_batch, v0, v1, B, N, C1, B, top_k, iou_threshold,
+                 confidence_threshold, keep, n_keep, keep_box, keep_score, keep_class, workspace, workspace_bytes,
+                 (cudaStream_t)stream);
+}

@@ -1,0 +1,344 @@
+"""GPU parity: the CenterNet CUDA path (through the C ABI) against the golden vectors frozen from the real
+reference, and against the CPU oracle on seeded inputs.  Tolerances are the north star's: indices, labels
+and counts exact under the canonical tie order; fp32 values 1e-5 relative."""
+from math import pi
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_port as O
+from tests import synth
+from tests.helpers import (assert_close, assert_equal, assert_topk_tie_aware, flat_index, golden, t)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cn(cuda_device):
+    from tauv_vision_b200.centernet.model import decode as D
+    from tauv_vision_b200.centernet.model import loss as L
+    return SimpleNamespace(D=D, L=L, dev=cuda_device)
+
+
+def pred(heatmap, size, offset, depth=None, kp_heatmap=None, kp_affinity=None):
+    return SimpleNamespace(heatmap=heatmap, keypoint_heatmap=kp_heatmap, keypoint_affinity=kp_affinity, size=size,
+                           offset=offset, depth=depth, roll_bin=None, pitch_bin=None, yaw_bin=None)
+
+
+def nhwc_view(a, dev):
+    """[B,H,W,ch] numpy -> the permuted NCHW view Centernet.forward produces (centernet.py:81-89)."""
+    return t(a).permute(0, 3, 1, 2).contiguous().to(dev).permute(0, 2, 3, 1)
+
+
+# ---- the reference's own KAT ----------------------------------------------------------------------------
+
+def test_kat_decode_main_block(cn):
+    """decode.py:327-339 on the GPU: splats -> heatmap_nms(3) -> heatmap_detect(100)."""
+    g = golden("kat_decode")
+    hm = torch.cat((cn.L.gaussian_splat(512, 512, 100, 100, 50)[None, None],
+                    cn.L.gaussian_splat(512, 512, 200, 200, 50)[None, None]), dim=1)
+    assert_close(hm[0, 0], O.gaussian_splat(512, 512, 100, 100, 50), what="gaussian_splat")
+    sup = cn.D.heatmap_nms(hm, 3)
+    assert int((sup != 0).sum()) == 2
+    idx, lab, sc = cn.D.heatmap_detect(sup, 100)
+    assert idx[0, 0, 0] == 100 and idx[0, 0, 1] == 100  # the reference's assertion
+    assert_equal(idx[:, :2], g["index"]), assert_equal(lab[:, :2], g["label"]), assert_equal(sc, g["score"])
+    assert flat_index(idx[0, 2:].cpu(), lab[0, 2:].cpu(), 512, 512).tolist() == list(range(98))
+
+
+# ---- heatmap_nms / heatmap_detect -------------------------------------------------------------------------
+
+def test_heatmap_nms_golden(cn):
+    g = golden("cn_nms_detect")
+    sig = torch.sigmoid(t(g["logits"])).to(cn.dev)  # the reference's CPU sigmoid, so the comparison is exact
+    assert_equal(cn.D.heatmap_nms(sig, 3), g["suppressed"])
+    p = golden("cn_nms_plateau")
+    assert_equal(cn.D.heatmap_nms(t(p["heatmap"]).to(cn.dev), 3), p["suppressed"], "plateaus survive")
+    assert_equal(cn.D.heatmap_nms(t(p["heatmap"]).to(cn.dev), 5), p["suppressed5"], "kernel_size 5")
+    assert_equal(cn.D.heatmap_nms(t(p["heatmap"]).to(cn.dev), 1), p["heatmap"], "kernel_size 1 is the identity")
+
+
+def test_heatmap_detect_golden(cn):
+    g = golden("cn_nms_detect")
+    idx, lab, sc = cn.D.heatmap_detect(t(g["suppressed"]).to(cn.dev), 40)
+    assert_equal(idx, g["index"]), assert_equal(lab, g["label"]), assert_equal(sc, g["score"])
+    assert idx.dtype == torch.int64 and lab.dtype == torch.int64 and sc.dtype == torch.float32
+
+
+def test_fused_peaks_golden(cn):
+    """sigmoid + 3x3 suppression + top-k in one pass must give what the three reference calls give."""
+    g = golden("cn_nms_detect")
+    idx, lab, sc = cn.D.heatmap_peaks(t(g["logits"]).to(cn.dev), 40)
+    assert_equal(idx, g["index"]), assert_equal(lab, g["label"])
+    assert_close(sc, g["score"], what="score")
+
+
+def test_reference_error_behaviour(cn):
+    x = torch.zeros((1, 2, 4, 4), device=cn.dev)
+    with pytest.raises(AssertionError):
+        cn.D.heatmap_nms(x, 2)  # decode.py:243
+    with pytest.raises(AssertionError):
+        cn.D.heatmap_nms(x, 0)
+    with pytest.raises(RuntimeError):
+        cn.D.heatmap_detect(x, 33)  # torch.topk: selected index k out of range
+    with pytest.raises(RuntimeError):
+        cn.D.heatmap_detect(x.cpu(), 3)  # no CPU path
+    idx, lab, sc = cn.D.heatmap_detect(x, 32)  # k == C*H*W is legal
+    assert flat_index(idx[0].cpu(), lab[0].cpu(), 4, 4).tolist() == list(range(32))
+
+
+# ---- decode ---------------------------------------------------------------------------------------------------
+
+def _check_against_golden(p, g, with_depth):
+    h = p.to_host()
+    assert_equal(h["count"], g["count"], "count")
+    for b in range(len(g["count"])):
+        n = int(g["count"][b])
+        assert_equal(h["label"][b, :n], g["label"][b, :n], "label")
+        assert_close(h["score"][b, :n], g["score"][b, :n], what="score")
+        assert_equal(h["yx"][b, :n], g["yx"][b, :n], "yx: fp64 arithmetic on exact fp32 gathers is bit exact")
+        assert_equal(h["hw"][b, :n], g["hw"][b, :n], "hw")
+        if with_depth:
+            assert_close(h["depth"][b, :n], g["depth_out"][b, :n], what="depth")
+
+
+def test_decode_golden(cn):
+    g = golden("cn_decode")
+    mc = synth.centernet_model_config(128, 128, 2)
+    logits = t(g["logits"]).to(cn.dev)
+    size, offset, depth = nhwc_view(g["size"], cn.dev), nhwc_view(g["offset"], cn.dev), nhwc_view(g["depth"], cn.dev)
+    assert not size.is_contiguous()
+    p = cn.D.decode_packed(pred(logits, size, offset, depth), mc, 30, 0.8)
+    _check_against_golden(p, g, True)
+    dets = cn.D.decode(pred(logits, size, offset, depth), mc, 30, 0.8)
+    assert [len(f) for f in dets] == g["count"].tolist()
+    d0 = dets[0][0]
+    assert isinstance(d0, cn.D.Detection) and int(d0.label) == int(g["label"][0, 0]) and d0.y == g["yx"][0, 0, 0]
+    g0 = golden("cn_decode_thr0")  # threshold 0.0 keeps all k entries (first PR-curve point of evaluate.py:213)
+    p0 = cn.D.decode_packed(pred(logits, size, offset, None), mc, 30, 0.0)
+    _check_against_golden(p0, g0, False)
+
+
+def test_config1_square_detection(cn):
+    """BASELINE.json configs[0]: batch 1, one Gaussian on 1x256x256, stride 2, decode(.., 100, 0.5)."""
+    g = golden("cn_config1")
+    mc = synth.centernet_model_config(512, 512, 1)
+    splat = O.gaussian_splat(256, 256, int(g["cy"]), int(g["cx"]), float(g["sigma"])).clamp(1e-6, 1 - 1e-6)
+    logits = torch.log(splat / (1 - splat)).reshape(1, 1, 256, 256).to(cn.dev)
+    size, offset, _ = synth.head_views(1, 256, 256, seed=32, with_depth=False)
+    size = size.permute(0, 3, 1, 2).contiguous().to(cn.dev).permute(0, 2, 3, 1)
+    offset = offset.permute(0, 3, 1, 2).contiguous().to(cn.dev).permute(0, 2, 3, 1)
+    p = cn.D.decode_packed(pred(logits, size, offset), mc, 100, 0.5)
+    _check_against_golden(p, g, False)
+    assert p.index[0, 0].tolist() == [int(g["cy"]), int(g["cx"])]
+
+
+def test_decode_keypoints_golden(cn):
+    g = golden("cn_decode_keypoints")
+    mc = synth.centernet_model_config(128, 128, 2)
+    kps = lambda i: [(0.1 * j, 0.0, 0.05 * i) for j in range(3)]
+    configs = [SimpleNamespace(keypoints=kps(0)), SimpleNamespace(keypoints=kps(1))]
+    oc = SimpleNamespace(configs=configs, decode_keypoint_index=lambda k: (int(k) // 3, int(k) % 3))
+    p = pred(t(g["logits"]).to(cn.dev), nhwc_view(g["size"], cn.dev), nhwc_view(g["offset"], cn.dev),
+             nhwc_view(g["depth"], cn.dev), t(g["kp_logits"]).to(cn.dev), t(g["kp_aff"]).to(cn.dev))
+    out = cn.D.decode_keypoints(p, mc, oc, np.eye(3), 6, 20, 0.8, 0.8, 0.3)
+    assert [len(f) for f in out] == g["counts"].tolist()
+    rows = []
+    for b, frame in enumerate(out):
+        for i, d in enumerate(frame):
+            row = [b, i, d.label, d.score, d.y, d.x, d.h, d.w, d.depth]
+            for j in range(3):
+                kp = d.keypoints[j]
+                row += [1.0, kp[0], kp[1], d.keypoint_scores[j], d.keypoint_affinities[j][0],
+                        d.keypoint_affinities[j][1]] if kp is not None else [0.0] * 6
+            rows.append(row)
+    assert_close(np.array(rows), g["rows"], what="KeypointDetection fields")
+
+
+# ---- oracle comparisons on seeded inputs --------------------------------------------------------------------
+
+@pytest.mark.parametrize("B,C,H,W,k", [(2, 3, 13, 11, 17), (1, 1, 1, 5, 3), (3, 2, 40, 36, 64), (2, 5, 64, 128, 100),
+                                       (1, 2, 300, 256, 50), (2, 1, 8, 2052, 20)])
+def test_peaks_vs_oracle_shapes(cn, B, C, H, W, k):
+    """Scalar path (W % 4 != 0), single rows, multi-item planes, wide rows."""
+    logits = synth.separated_logits(B, C, H, W, seed=100 + H)
+    oi, ol, osc = O.heatmap_detect(O.heatmap_nms(torch.sigmoid(logits), 3), k)
+    idx, lab, sc = cn.D.heatmap_peaks(logits.to(cn.dev), k)
+    assert_equal(idx, oi), assert_equal(lab, ol), assert_close(sc, osc, what="score")
+    # RAW mode on arbitrary (negative too) values
+    oi, ol, osc = O.heatmap_detect(logits, k)
+    idx, lab, sc = cn.D.heatmap_detect(logits.to(cn.dev), k)
+    assert_equal(idx, oi), assert_equal(lab, ol), assert_equal(sc, osc)
+
+
+def test_unaligned_base_pointer(cn):
+    """A heatmap whose storage is offset by one float takes the plain-load path and must still be right."""
+    logits = synth.separated_logits(2, 3, 32, 32, seed=7)
+    buf = torch.empty(logits.numel() + 1, device=cn.dev)
+    buf[1:] = logits.flatten().to(cn.dev)
+    view = buf[1:].view(2, 3, 32, 32)
+    assert view.data_ptr() % 16 != 0
+    oi, ol, _ = O.heatmap_detect(O.heatmap_nms(torch.sigmoid(logits), 3), 25)
+    idx, lab, _ = cn.D.heatmap_peaks(view, 25)
+    assert_equal(idx, oi), assert_equal(lab, ol)
+
+
+def test_natural_frames_tie_aware(cn):
+    """N(-2.2,1.5) background + planted bumps: near-equal scores may swap by an ulp of expf; everything else exact."""
+    logits = synth.natural_logits(4, 8, 64, 64, seed=5)
+    oi, ol, osc = O.heatmap_detect(O.heatmap_nms(torch.sigmoid(logits), 3), 100)
+    idx, lab, sc = cn.D.heatmap_peaks(logits.to(cn.dev), 100)
+    swaps = assert_topk_tie_aware(flat_index(idx.cpu(), lab.cpu(), 64, 64), sc.cpu(), flat_index(oi, ol, 64, 64), osc,
+                                  what="natural", allow_swaps=2)
+    assert swaps <= 2
+
+
+def test_plateaus_and_fillers(cn):
+    dev = cn.dev
+    # constant logits: every cell is a peak with score 0.5 -> lowest flat indices win
+    idx, lab, sc = cn.D.heatmap_peaks(torch.zeros((2, 3, 16, 16), device=dev), 40)
+    assert flat_index(idx[1].cpu(), lab[1].cpu(), 16, 16).tolist() == list(range(40))
+    assert (sc == 0.5).all()
+    # saturated sigmoid: logits 20 and 30 both give exactly 1.0f -> a plateau in score space, as in the reference
+    x = torch.full((1, 1, 8, 8), -5.0)
+    x[0, 0, 2, 2], x[0, 0, 2, 3] = 20.0, 30.0
+    oi, ol, osc = O.heatmap_detect(O.heatmap_nms(torch.sigmoid(x), 3), 4)
+    idx, lab, sc = cn.D.heatmap_peaks(x.to(dev), 4)
+    assert osc[0, :2].tolist() == [1.0, 1.0]
+    assert_equal(idx, oi), assert_equal(sc, osc)
+    # fewer positive peaks than k: zero-score fillers in ascending flat index, skipping the peak cells
+    x = torch.full((1, 2, 6, 6), -200.0)  # sigmoid underflows to exactly 0
+    x[0, 0, 0, 1], x[0, 1, 3, 3] = 1.0, 2.0
+    oi, ol, osc = O.heatmap_detect(O.heatmap_nms(torch.sigmoid(x), 3), 10)
+    idx, lab, sc = cn.D.heatmap_peaks(x.to(dev), 10)
+    assert_equal(idx, oi), assert_equal(lab, ol), assert_close(sc, osc)
+    assert flat_index(idx[0, 2:].cpu(), lab[0, 2:].cpu(), 6, 6).tolist() == [0, 2, 3, 4, 5, 6, 7, 8]
+    # -inf everywhere
+    idx, lab, sc = cn.D.heatmap_peaks(torch.full((1, 1, 4, 4), float("-inf"), device=dev), 5)
+    assert (sc == 0).all() and flat_index(idx[0].cpu(), lab[0].cpu(), 4, 4).tolist() == [0, 1, 2, 3, 4]
+
+
+def test_large_k_and_pruning(cn):
+    """k = 1000 and a plateau-heavy map that overflows the per-item candidate list (exercises the prune path)."""
+    logits = synth.separated_logits(2, 4, 128, 128, seed=9)
+    oi, ol, osc = O.heatmap_detect(O.heatmap_nms(torch.sigmoid(logits), 3), 1000)
+    idx, lab, sc = cn.D.heatmap_peaks(logits.to(cn.dev), 1000)
+    assert_equal(idx, oi), assert_equal(lab, ol), assert_close(sc, osc)
+    q = (torch.round(synth.natural_logits(1, 2, 128, 128, seed=10) * 0.5) / 0.5)  # coarse quantisation: huge plateaus
+    oi, ol, osc = O.heatmap_detect(O.heatmap_nms(torch.sigmoid(q), 3), 300)
+    idx, lab, sc = cn.D.heatmap_peaks(q.to(cn.dev), 300)
+    assert_equal(idx, oi), assert_equal(lab, ol), assert_close(sc, osc)
+    oi, ol, osc = O.heatmap_detect(q, 300)  # RAW mode: every element is a candidate
+    idx, lab, sc = cn.D.heatmap_detect(q.to(cn.dev), 300)
+    assert_equal(idx, oi), assert_equal(lab, ol), assert_equal(sc, osc)
+
+
+def test_decode_full_size_vs_oracle(cn):
+    """BASELINE.json configs[1] shape per frame (C=80, 128x128, k=100, stride 4) on a few frames, plus the
+    other two strides of the multi-scale config at reduced batch."""
+    for (B, H, ds, seed) in [(4, 128, 2, 1), (2, 256, 1, 2), (4, 64, 3, 3)]:
+        logits = synth.separated_logits(B, 80, H, H, seed=seed, lo=-9.0, hi=4.0)
+        size, offset, depth = synth.head_views(B, H, H, seed=seed + 10)
+        o = O.decode_packed(logits, size, offset, depth, 2 ** ds, 512, 512, 100, 0.3)
+        mc = synth.centernet_model_config(512, 512, ds)
+        dv = lambda a: a.permute(0, 3, 1, 2).contiguous().to(cn.dev).permute(0, 2, 3, 1)
+        p = cn.D.decode_packed(pred(logits.to(cn.dev), dv(size), dv(offset), dv(depth)), mc, 100, 0.3)
+        assert_equal(p.index, o.index), assert_equal(p.label, o.label), assert_close(p.score, o.score)
+        assert_equal(p.yx, o.yx), assert_equal(p.hw, o.hw), assert_close(p.depth, o.depth), assert_equal(p.count, o.count)
+
+
+def test_full_batch_properties(cn):
+    """Size-independent properties at BASELINE.json's full size (B=64, C=80, 128x128, k=100): scores sorted,
+    every reported cell is a 3x3 maximum of its plane, the k-th score bounds every unreported peak, and the
+    result is idempotent under a second run."""
+    torch.manual_seed(0)
+    logits = torch.randn((64, 80, 128, 128), device=cn.dev) * 1.5 - 2.2
+    idx, lab, sc = cn.D.heatmap_peaks(logits, 100)
+    assert (sc[:, :-1] >= sc[:, 1:]).all()
+    sig = torch.sigmoid(logits)
+    pooled = torch.nn.functional.max_pool2d(sig, 3, 1, 1)
+    b = torch.arange(64, device=cn.dev)[:, None].expand(-1, 100)
+    assert (pooled[b, lab, idx[..., 0], idx[..., 1]] == sig[b, lab, idx[..., 0], idx[..., 1]]).all()
+    assert_close(sig[b, lab, idx[..., 0], idx[..., 1]], sc, what="reported score is the cell's sigmoid")
+    sup = torch.where(pooled == sig, sig, torch.zeros_like(sig)).reshape(64, -1)
+    kth = torch.topk(sup, 100).values[:, -1]
+    assert_close(sc[:, -1], kth, what="k-th score")
+    idx2, lab2, sc2 = cn.D.heatmap_peaks(logits, 100)
+    assert_equal(idx, idx2), assert_equal(lab, lab2), assert_equal(sc, sc2)
+
+
+# ---- target encode -----------------------------------------------------------------------------------------------
+
+def test_encode_golden(cn):
+    g = golden("cn_encode")
+    mc = synth.centernet_model_config(96, 96, 2)
+    tc = SimpleNamespace(keypoint_heatmap_sigma=float(g["sigma_h"]), keypoint_affinity_sigma=float(g["sigma_a"]))
+    oc = SimpleNamespace(n_labels=4, n_keypoints=8)
+    dev = cn.dev
+    truth = SimpleNamespace(valid=t(g["valid"]).to(dev), label=t(g["label"]).to(dev), center=t(g["center"]).to(dev),
+                            keypoint_valid=t(g["kp_valid"]).to(dev), keypoint_label=t(g["kp_label"]).to(dev),
+                            keypoint_center=t(g["kp_center"]).to(dev), keypoint_object_index=t(g["kp_obj"]).to(dev))
+    assert_close(cn.L.generate_heatmap(truth, mc, tc, oc), g["heatmap"], what="generate_heatmap")
+    hm, wt, aff = cn.L.generate_keypoint_heatmap(truth, mc, tc, oc)
+    assert_close(hm, g["kp_heatmap"], what="keypoint heatmap"), assert_close(wt, g["kp_weight"], what="affinity weight")
+    assert_equal(aff, g["kp_affinity"], "affinity field: IEEE ops only, bit exact")
+    assert_equal(cn.L.out_index_for_position(truth.center, mc), g["out_index"])
+    assert_equal(cn.L.offset_target(truth.center, mc), g["offset"])
+
+
+@pytest.mark.parametrize("B,n,C,H,W,ds", [(3, 5, 4, 13, 11, 1), (2, 16, 80, 128, 128, 2), (1, 0, 2, 8, 8, 2)])
+def test_encode_vs_oracle(cn, B, n, C, H, W, ds):
+    ratio = 2 ** ds
+    mc = SimpleNamespace(in_h=H * ratio, in_w=W * ratio, downsample_ratio=ratio, out_h=H, out_w=W)
+    tc = SimpleNamespace(keypoint_heatmap_sigma=1.7, keypoint_affinity_sigma=0.05)  # 0.05: no sigma floor in the keypoint path
+    tr = synth.pose_truth(B, max(n, 1), C, seed=H, n_kp_inst=max(n, 1), Kp=3)
+    if n == 0:
+        tr.valid[:] = False
+        tr.keypoint_valid[:] = False
+    oc = SimpleNamespace(n_labels=C, n_keypoints=3)
+    args = dict(out_h=H, out_w=W, in_h=mc.in_h, in_w=mc.in_w, downsample_ratio=ratio)
+    o = O.generate_heatmap(tr.valid, tr.label, tr.center, C, sigma=1.7, **args)
+    dtr = synth.truth_to(tr, cn.dev)
+    assert_close(cn.L.generate_heatmap(dtr, mc, tc, oc), o, what="generate_heatmap")
+    okh, okw, oka = O.generate_keypoint_heatmap(tr.keypoint_valid, tr.keypoint_label, tr.keypoint_center,
+                                                tr.keypoint_object_index, tr.center, 3, sigma_heatmap=1.7,
+                                                sigma_affinity=0.05, **args)
+    hm, wt, aff = cn.L.generate_keypoint_heatmap(dtr, mc, tc, oc)
+    assert_close(hm, okh), assert_close(wt, okw), assert_equal(aff, oka)
+
+
+def test_encode_sigma_floor_and_far_centres(cn):
+    mc = SimpleNamespace(in_h=64, in_w=64, downsample_ratio=4, out_h=16, out_w=16)
+    tc = SimpleNamespace(keypoint_heatmap_sigma=0.01, keypoint_affinity_sigma=1.0)  # floored to 0.1 (loss.py:60-62)
+    tr = SimpleNamespace(valid=torch.tensor([[True, True]]), label=torch.tensor([[0, 1]]),
+                         center=torch.tensor([[[0.5, 0.5], [40.0, -3.0]]]))  # second centre far outside, unclamped
+    o = O.generate_heatmap(tr.valid, tr.label, tr.center, 2, 16, 16, 64, 64, 4, 0.01)
+    got = cn.L.generate_heatmap(synth.truth_to(tr, cn.dev), mc, tc, SimpleNamespace(n_labels=2))
+    assert_close(got, o)
+    assert float(got[0, 0, 8, 8]) == 1.0 and float(got[0, 1].max()) == 0.0
+
+
+def test_encode_full_size_properties(cn):
+    """B=64, C=80, 128x128, 16 objects: every valid object's cell is exactly 1.0, planes without objects are 0."""
+    tr = synth.pose_truth(64, 16, 80, seed=3)
+    mc = synth.centernet_model_config(512, 512, 2)
+    hm = cn.L.generate_heatmap(synth.truth_to(tr, cn.dev), mc, SimpleNamespace(keypoint_heatmap_sigma=2.0),
+                               SimpleNamespace(n_labels=80))
+    cell = O.out_index_for_position(tr.center, 512, 512, 4, 128, 128)
+    b = torch.arange(64)[:, None].expand(-1, 16)
+    peak = hm.cpu()[b, tr.label, cell[..., 0], cell[..., 1]]
+    assert (peak[tr.valid] == 1.0).all()
+    has = torch.zeros((64, 80), dtype=torch.bool)
+    has[b[tr.valid], tr.label[tr.valid]] = True
+    assert (hm.cpu().amax(dim=(2, 3))[~has] == 0).all() and (hm.cpu().amax(dim=(2, 3))[has] == 1).all()
+
+
+def test_angle_depth_golden(cn):
+    g = golden("cn_angle_depth")
+    pb, po = t(g["bin"]).to(cn.dev), t(g["offset"]).to(cn.dev)
+    assert_close(cn.D.angle_decode(pb, po, 2 * pi, pi / 3), g["angle"], atol=1e-6, what="angle_decode")
+    assert_close(cn.D.angle_decode(pb, po, pi, pi / 3), g["angle_pi"], atol=1e-6, what="angle_decode(pi)")
+    assert_close(cn.D.depth_decode(t(g["depth_in"]).to(cn.dev)), g["depth"], what="depth_decode")
+    assert cn.D.angle_get_bins(pi / 3) == O.angle_get_bins(pi / 3)

@@ -1,0 +1,220 @@
+"""GPU parity: the YOLACT CUDA path (through the C ABI) against the golden vectors frozen from the real
+reference and against the CPU oracle.  Keep sets / indices / matches exact; boxes and scores 1e-5 relative;
+tensor-core mask logits 1e-2 absolute (north-star tolerances)."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_port as O
+from tests import synth
+from tests.helpers import assert_close, assert_equal, golden, t
+
+pytestmark = pytest.mark.gpu
+
+CFG = synth.yolact_config()
+
+
+@pytest.fixture(scope="module")
+def yl(cuda_device):
+    from tauv_vision_b200.yolact.model import anchors, boxes, loss, masks, nms
+    return SimpleNamespace(anchors=anchors, boxes=boxes, loss=loss, masks=masks, nms=nms, dev=cuda_device)
+
+
+def test_anchors_golden(yl):
+    g = golden("yl_anchors")
+    small = yl.anchors.all_anchors([tuple(s) for s in g["small_sizes"]], CFG, yl.dev)
+    assert_equal(small, g["small"], "aspect-major prior layout, bit exact")
+    lvl = yl.anchors.get_anchor(1, (4, 3), CFG, yl.dev)
+    assert_equal(lvl, O.get_anchor(1, (4, 3), CFG.anchor_scales, CFG.anchor_aspect_ratios, 550, 550))
+    full = yl.anchors.all_anchors(synth.fpn_sizes(550, 550), CFG, yl.dev)
+    assert full.shape == (1, 19248, 4)
+    assert_equal(full[0, t(g["full_sel"]).to(yl.dev)], g["full_rows"])
+    assert_equal(full.double().sum(dim=1), g["full_sum"])
+
+
+def test_boxes_golden(yl):
+    g = golden("yl_boxes")
+    d = yl.dev
+    anchor, enc = t(g["anchor"]).to(d), t(g["enc"]).to(d)
+    assert_close(yl.boxes.box_decode(enc, anchor, CFG), g["dec"], what="box_decode")
+    assert_close(yl.boxes.box_encode(t(g["dec"]).to(d), anchor.expand(3, -1, -1), CFG), g["re_enc"], atol=1e-6,
+                 what="box_encode")
+    ba, bb = t(g["box_a"]).to(d), t(g["box_b"]).to(d)
+    assert_equal(yl.boxes.iou_matrix(ba, bb), g["iou_ab"], "iou_matrix: IEEE ops only, bit exact")
+    assert_equal(yl.boxes.iou_matrix(ba, ba), g["iou_aa"])
+    assert_equal(yl.boxes.iou_matrix(bb, ba), np.swapaxes(g["iou_ab"], 1, 2), "broadcast on the first operand")
+    assert_equal(yl.boxes.box_to_corners(ba), g["corners"]), assert_equal(yl.boxes.box_xy_swap(ba), g["xy_swap"])
+    assert_equal(yl.boxes.corners_to_box(yl.boxes.box_to_corners(ba)), g["back"])
+
+
+def test_boxes_main_block_round_trip(yl):
+    """yolact boxes.py:106-117."""
+    box = torch.rand((1, 1, 4), device=yl.dev)
+    anchor = torch.rand((1, 1, 4), device=yl.dev) + 0.05
+    assert torch.allclose(box, yl.boxes.corners_to_box(yl.boxes.box_to_corners(box)))
+    assert torch.allclose(box, yl.boxes.box_decode(yl.boxes.box_encode(box, anchor, CFG), anchor, CFG), atol=1e-6)
+    iou = yl.boxes.iou_matrix(box, box)
+    assert iou.shape == (1, 1, 1) and abs(float(iou) - 1.0) < 1e-6
+    z = torch.zeros((1, 1, 4), device=yl.dev)
+    assert torch.isnan(yl.boxes.iou_matrix(z, z)).all()  # 0/0, as in the reference
+
+
+def test_nms_golden(yl):
+    g = golden("yl_nms")
+    cls, box = t(g["cls"]).to(yl.dev), t(g["box"]).to(yl.dev)
+    assert_equal(yl.nms.nms(cls, box, 120, 0.5, 0.05), g["keep"], "keep list (frame 0)")
+    assert_equal(yl.nms.nms(cls, box, 120, 0.3, 0.5), g["keep_b"], "other thresholds")
+    assert_equal(yl.nms.nms(cls[1:], box[1:], 120, 0.5, 0.05), g["keep_frame1"])
+    keep, n_keep = yl.nms.nms_batched(cls, box, 120, 0.5, 0.05)
+    assert n_keep.tolist() == [len(g["keep"]), len(g["keep_frame1"])]
+    assert_equal(keep[1, : int(n_keep[1])], g["keep_frame1"], "batched entry, frame 1")
+    assert yl.nms.nms(cls, box, 120, 0.5, 0.05).dtype == torch.int64
+
+
+def test_detect_fused_golden(yl):
+    """Decode only the ranked priors, NMS, class argmax: same keep sets as box_decode + nms of the reference."""
+    g = golden("yl_nms")
+    d = yl.dev
+    cls, enc, anchor = t(g["cls"]).to(d), t(g["enc"]).to(d), t(g["anchor"]).to(d)
+    det = yl.nms.detect(cls, enc, anchor, CFG, 120, 0.5, 0.05)
+    n0, n1 = int(det.n_keep[0]), int(det.n_keep[1])
+    assert_equal(det.keep[0, :n0], g["keep"]), assert_equal(det.keep[1, :n1], g["keep_frame1"])
+    assert_close(det.box[0, :n0], g["box"][0][g["keep"]], what="kept boxes")
+    ocls = t(g["cls"])
+    assert_equal(det.class_id[0, :n0], torch.argmax(ocls[0, t(g["keep"])], dim=-1).to(torch.int32), "class ids")
+    assert_close(det.score[0, :n0], O.nms_scores(ocls)[0, t(g["keep"])], what="confidences")
+
+
+def test_scores_vs_oracle(yl):
+    for C1 in (2, 6, 33, 81, 130):
+        g = synth.gen(C1)
+        cls = torch.randn((2, 700, C1), generator=g) * 3
+        s, a = yl.nms.max_foreground_confidence(cls.to(yl.dev), with_argmax=True)
+        assert_close(s, O.nms_scores(cls), what=f"scores C1={C1}")
+        assert_equal(a, torch.argmax(cls, dim=-1).to(torch.int32), f"argmax C1={C1}")
+
+
+def test_nms_edge_cases(yl):
+    d = yl.dev
+    g = synth.gen(3)
+    # fewer priors than top_k
+    cls = torch.randn((1, 7, 4), generator=g)
+    box = torch.cat((torch.rand((1, 7, 2), generator=g), torch.rand((1, 7, 2), generator=g) * 0.2 + 0.05), -1)
+    assert_equal(yl.nms.nms(cls.to(d), box.to(d), 50, 0.5, 0.0), O.nms(cls, box, 50, 0.5, 0.0))
+    # nothing passes the confidence threshold -> empty LongTensor (yolact_node.py:131-133 checks len == 0)
+    out = yl.nms.nms(cls.to(d), box.to(d), 50, 0.5, 2.0)
+    assert out.shape == (0,) and out.dtype == torch.int64
+    # identical boxes: only the most confident survives; equal confidences tie-break by prior index
+    cls = torch.zeros((1, 40, 3))
+    cls[0, :, 1] = 5.0
+    box = torch.tensor([0.5, 0.5, 0.2, 0.2]).repeat(1, 40, 1)
+    assert yl.nms.nms(cls.to(d), box.to(d), 40, 0.5, 0.1).tolist() == [0]
+    # low-confidence and already-suppressed boxes still suppress (Fast NMS), top_k = 1000
+    anchor = torch.cat((torch.rand((1, 3000, 2), generator=g), torch.rand((1, 3000, 2), generator=g) * 0.3 + 0.05), -1)
+    cls, enc = synth.yolact_heads(1, 3000, 9, seed=4, anchor=anchor, n_clusters=40, per_cluster=20, separated=True)
+    box = O.box_decode(enc, anchor, CFG.box_variances)
+    assert_equal(yl.nms.nms(cls.to(d), box.to(d), 1000, 0.4, 0.3), O.nms(cls, box, 1000, 0.4, 0.3), "top_k 1000")
+
+
+def test_full_size_vs_oracle(yl):
+    """BASELINE.json configs[2] geometry: 19 248 priors (550x550, 3 aspect ratios), 81 classes, top_k 200."""
+    d = yl.dev
+    anchor = O.all_anchors(synth.fpn_sizes(550, 550), CFG.anchor_scales, CFG.anchor_aspect_ratios, 550, 550)
+    cls, enc = synth.yolact_heads(3, 19248, 81, seed=6, anchor=anchor, n_clusters=15, per_cluster=12, separated=True)
+    box = O.box_decode(enc, anchor, CFG.box_variances)
+    scores = O.nms_scores(cls)
+    det = yl.nms.detect(cls.to(d), enc.to(d), anchor.to(d), CFG, 200, 0.5, 0.05)
+    for b in range(3):
+        keep, ranked, conf = O.nms_frame(scores[b], box[b], 200, 0.5, 0.05)
+        n = int(det.n_keep[b])
+        assert_equal(det.keep[b, :n], keep, f"frame {b} keep set")
+        assert 20 < n < 200
+    assert_close(yl.boxes.box_decode(enc.to(d), anchor.to(d), CFG), box, what="box_decode at N=19248")
+
+
+def _mask_check(yl, logits_atol):
+    g = golden("yl_mask")
+    d = yl.dev
+    proto, coeff, box = t(g["proto"]).to(d), t(g["coeff"]).to(d), t(g["box"]).to(d)
+    ref_logits = O.mask_logits(t(g["proto"]), t(g["coeff"]))
+    m, lg = yl.masks.assemble_mask(proto, coeff, box, return_logits=True)
+    assert_close(lg, ref_logits, rtol=0, atol=logits_atol, what="mask logits")
+    assert_close(m, g["mask"], rtol=0, atol=max(logits_atol / 4, 1e-6), what="assemble_mask with crop")
+    assert_equal(m == 0, g["mask"] == 0, "crop region (inclusive integer-pixel bounds) is exact")
+    assert_close(yl.masks.assemble_mask(proto, coeff, None), g["mask_nobox"], rtol=0,
+                 atol=max(logits_atol / 4, 1e-6), what="assemble_mask without box")
+    assert_equal(yl.boxes.box_to_mask(box[0], (20, 24)), g["crop0"], "box_to_mask")
+    assert yl.masks.assemble_mask(proto, coeff[:0], box[:0]).shape == (0, 20, 24)
+
+
+def test_mask_golden_simt(yl, monkeypatch):
+    monkeypatch.setenv("TAUV_MASK_SIMT", "1")
+    _mask_check(yl, 2e-6)
+
+
+def test_mask_golden_tensor_core(yl, monkeypatch):
+    monkeypatch.delenv("TAUV_MASK_SIMT", raising=False)
+    _mask_check(yl, 1e-2)
+
+
+@pytest.mark.parametrize("P,H,W,K", [(32, 138, 138, 100), (32, 276, 276, 37), (16, 64, 40, 130), (48, 30, 36, 5),
+                                      (32, 7, 9, 3), (24, 16, 16, 4)])
+def test_mask_vs_oracle_shapes(yl, monkeypatch, P, H, W, K):
+    """Tensor-core path where the shape fits (P % 16 == 0, H*W % 4 == 0), CUDA-core path otherwise; both against
+    the fp32 oracle.  n > 128 exercises several M tiles; odd sizes exercise ragged pixel tiles."""
+    monkeypatch.delenv("TAUV_MASK_SIMT", raising=False)
+    proto, coeff, box = synth.mask_inputs(P, H, W, K, seed=P + H)
+    ref = torch.sigmoid(proto.reshape(P, -1).T @ coeff.T).T.reshape(K, H, W)
+    crop = torch.stack([O.box_to_mask(box[i], (H, W)) for i in range(K)])
+    d = yl.dev
+    m = yl.masks.assemble_mask(proto.to(d), coeff.to(d), box.to(d))
+    assert_close(m, ref * crop, rtol=0, atol=2.5e-3, what="mask")
+    assert_equal(m == 0, (ref * crop) == 0, "crop exact")
+    m2 = yl.masks.assemble_mask(proto.to(d), coeff.to(d), None)
+    assert_close(m2, ref, rtol=0, atol=2.5e-3, what="mask, no crop")
+
+
+def test_mask_batched_matches_single(yl, monkeypatch):
+    monkeypatch.delenv("TAUV_MASK_SIMT", raising=False)
+    d = yl.dev
+    B, N, P, H, W, top_k = 3, 500, 32, 48, 52, 40
+    g = synth.gen(12)
+    anchor = torch.cat((torch.rand((1, N, 2), generator=g), torch.rand((1, N, 2), generator=g) * 0.3 + 0.05), -1)
+    cls, enc = synth.yolact_heads(B, N, 7, seed=13, anchor=anchor, separated=True)
+    proto = torch.nn.functional.leaky_relu(torch.randn((B, P, H, W), generator=g)).to(d)
+    coeff = torch.tanh(torch.randn((B, N, P), generator=g)).to(d)
+    det = yl.nms.detect(cls.to(d), enc.to(d), anchor.to(d), CFG, top_k, 0.5, 0.05)
+    out = yl.masks.assemble_mask_batched(proto, coeff, det)
+    for b in range(B):
+        n = int(det.n_keep[b])
+        assert n > 0
+        single = yl.masks.assemble_mask(proto[b], coeff[b, det.keep[b, :n]], det.box[b, :n])
+        assert_equal(out[b, :n], single, f"frame {b}: batched == per-frame call")
+
+
+def test_match_golden(yl):
+    g = golden("yl_match")
+    d = yl.dev
+    m = yl.loss.match_anchors(t(g["anchor"]).to(d), t(g["truth_box"]).to(d), t(g["truth_valid"]).to(d), CFG)
+    assert_equal(m.match_index, g["match_index"], "first max on ties"), assert_equal(m.match_iou, g["match_iou"])
+    assert_equal(m.positive_match, g["positive"]), assert_equal(m.negative_match, g["negative"])
+    assert_close(m.box_target[m.positive_match], g["targets"], atol=1e-6, what="regression targets of the positives")
+
+
+def test_match_full_size_vs_oracle(yl):
+    anchor = O.all_anchors(synth.fpn_sizes(550, 550), CFG.anchor_scales, CFG.anchor_aspect_ratios, 550, 550)
+    tb, tv = synth.truth_boxes(4, 16, seed=8)
+    g = synth.gen(9)
+    pick = torch.randint(0, 19248, (4, 8), generator=g)
+    tb[:, :8] = anchor[0, pick] * (1 + 0.05 * torch.randn((4, 8, 4), generator=g).clamp(-1, 1) * torch.tensor([0, 0, 1, 1]))
+    tv[:, :8] = True
+    mi, miou, pos, neg, tgt = O.match_anchors(anchor, tb, tv, 0.4, 0.3, CFG.box_variances)
+    d = yl.dev
+    m = yl.loss.match_anchors(anchor.to(d), tb.to(d), tv.to(d), CFG)
+    assert_equal(m.match_index, mi), assert_equal(m.match_iou, miou)
+    assert_equal(m.positive_match, pos), assert_equal(m.negative_match, neg)
+    assert int(pos.sum()) > 0
+    assert_close(m.box_target[m.positive_match], tgt[pos], atol=1e-6, what="targets")
