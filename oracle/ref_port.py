@@ -57,10 +57,15 @@ def stable_topk(scores: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tenso
     return vals, idxs
 
 
-def heatmap_detect(heatmap: torch.Tensor, n_detections: int):
-    """decode.py:255-279 — joint top-k over C*H*W; (index [B,k,2] (y,x), label [B,k], score [B,k])."""
+def heatmap_detect(heatmap: torch.Tensor, n_detections: int, canonical: bool = True):
+    """decode.py:255-279 — joint top-k over C*H*W; (index [B,k,2] (y,x), label [B,k], score [B,k]).
+    canonical=False uses a bare torch.topk exactly like the reference (arbitrary tie order) — that is the
+    variant bench.py times, so the CPU baseline carries no cost the reference does not have."""
     B, C, H, W = heatmap.shape
-    score, flat = stable_topk(heatmap.reshape(B, -1), n_detections)
+    if canonical:
+        score, flat = stable_topk(heatmap.reshape(B, -1), n_detections)
+    else:
+        score, flat = torch.topk(heatmap.reshape(B, -1), n_detections)
     label = torch.div(flat, H * W, rounding_mode="floor")
     rem = flat - label * (H * W)
     index = torch.stack((torch.div(rem, W, rounding_mode="floor"), rem % W), dim=-1)
@@ -107,12 +112,12 @@ def _gather_hw(t: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
 
 
 def decode_packed(heatmap_logits, size, offset, depth, downsample_ratio: int, in_h: int, in_w: int,
-                  n_detections: int, score_threshold: float) -> Packed:
+                  n_detections: int, score_threshold: float, canonical: bool = True) -> Packed:
     """decode.py:179-236 with the per-detection Python loop expressed as gathers.
     y = (ratio*iy + offset_y)/in_h in float64 (the reference computes these in Python floats, :214-215);
     count = entries before the first score < threshold (:208-209, fp32 compare)."""
     hm = heatmap_nms(torch.sigmoid(heatmap_logits), 3)
-    index, label, score = heatmap_detect(hm, n_detections)
+    index, label, score = heatmap_detect(hm, n_detections, canonical)
     off = _gather_hw(offset, index).to(torch.float64)
     yx = torch.stack(((downsample_ratio * index[..., 0].to(torch.float64) + off[..., 0]) / in_h,
                       (downsample_ratio * index[..., 1].to(torch.float64) + off[..., 1]) / in_w), dim=-1)
