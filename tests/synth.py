@@ -26,11 +26,16 @@ def centernet_model_config(in_h=512, in_w=512, downsamples=2):
 
 
 def separated_logits(B, C, H, W, seed, lo=-6.0, hi=3.0):
-    """Every frame is a random permutation of an evenly spaced ramp: all logits (and their sigmoids
-    near the top) are distinct and well separated, so top-k order is unambiguous."""
+    """Every frame is a random permutation of a strictly increasing ramp: all logits are distinct, and the
+    top of the ramp (the only part a top-k can reach) is spaced 1e-4 apart, i.e. tens of fp32 ulps apart even
+    after the sigmoid, so the ranked order is unambiguous whatever the last-ulp rounding of exp()."""
     g = gen(seed)
     n = C * H * W
-    ramp = torch.linspace(lo, hi, n, dtype=torch.float32)
+    m = min(n // 2, 20000)
+    top = hi - 1e-4 * torch.arange(m - 1, -1, -1, dtype=torch.float64)
+    rest = torch.linspace(lo, float(top[0]) - 1e-4, n - m, dtype=torch.float64) if n > m else top[:0]
+    ramp = torch.cat((rest, top)).to(torch.float32)
+    assert ramp.numel() == n
     out = torch.empty((B, n), dtype=torch.float32)
     for b in range(B):
         out[b] = ramp[torch.randperm(n, generator=g)]
@@ -115,25 +120,43 @@ def fpn_sizes(in_h, in_w):
 
 
 def yolact_heads(B, N, C1, seed, anchor, n_clusters=12, per_cluster=12, separated=False):
-    """cls ~ N(0, 2^2) with planted confident priors in overlapping clusters (so NMS has work to do);
-    enc ~ N(0, 0.5^2), with clustered priors pulled towards a shared box."""
+    """Class logits + box encodings with planted confident priors in clusters (so NMS has work to do).
+
+    separated=False: cls ~ N(0, 2^2), background-dominated, cluster members boosted — "natural" data whose
+    confidences can tie to within an ulp.
+    separated=True : every prior's max-foreground confidence is sigmoid(margin) for a distinct margin from a
+    shuffled ramp (all other foreground logits are -30, i.e. below fp32 resolution of the softmax sum), with
+    the largest margins given to the cluster members.  Ranked order is then unambiguous whatever the
+    last-ulp rounding of exp() / the softmax summation order."""
     g = gen(seed)
-    cls = torch.randn((B, N, C1), generator=g) * 2.0
-    cls[:, :, 0] += 4.0  # background-dominated like a trained head
     enc = torch.randn((B, N, 4), generator=g) * 0.5
+    if not separated:
+        cls = torch.randn((B, N, C1), generator=g) * 2.0
+        cls[:, :, 0] += 4.0  # background-dominated like a trained head
+    else:
+        cls = torch.full((B, N, C1), -30.0)
+        cls[:, :, 0] = 0.0
     for b in range(B):
+        members_all = []
         for c in range(n_clusters):
             centre = int(torch.randint(0, N, (1,), generator=g))
             members = (centre + torch.randperm(min(N, 64), generator=g)[:per_cluster]) % N
-            k = int(torch.randint(1, C1, (1,), generator=g))
-            boost = 8.0 + 4.0 * torch.rand((per_cluster,), generator=g)
-            cls[b, members, k] += boost
-            cls[b, members, 0] -= 4.0
             enc[b, members] *= 0.2
-    if separated:
-        # make every prior's max-fg confidence distinct by a deterministic ramp on one fg logit
-        ramp = torch.linspace(0, 0.5, N).unsqueeze(0)
-        cls[:, :, 1] += ramp
+            members_all.append(members)
+            if not separated:
+                k = int(torch.randint(1, C1, (1,), generator=g))
+                cls[b, members, k] += 8.0 + 4.0 * torch.rand((per_cluster,), generator=g)
+                cls[b, members, 0] -= 4.0
+        if separated:
+            ramp = torch.linspace(-8.0, 4.0, N)
+            members = torch.unique(torch.cat(members_all))
+            others = torch.tensor(sorted(set(range(N)) - set(members.tolist())), dtype=torch.int64)
+            order = torch.cat((others[torch.randperm(others.numel(), generator=g)],
+                               members[torch.randperm(members.numel(), generator=g)]))
+            margin = torch.empty(N)
+            margin[order] = ramp  # members receive the top of the ramp
+            k = torch.randint(1, C1, (N,), generator=g)
+            cls[b, torch.arange(N), k] = margin
     return cls, enc
 
 
