@@ -36,11 +36,10 @@ struct TopkPlan {
   int soft;             // prune when the list grows beyond this
   int bulk;             // 1: bulk-copy ring, 0: plain loads
   size_t smem_bytes;
-  size_t cand_bytes, count_bytes;
+  size_t cand_bytes, count_bytes, thr_bytes;
 };
 
 static int make_plan(int B, int C, int H, int W, int k, const void* ptr, TopkPlan* p) {
-  (void)B;
   p->bulk = (W % 4 == 0) && ((uintptr_t)ptr % 16 == 0);
   int R = kChunkElems / W;
   if (R < 1) R = 1;
@@ -61,16 +60,16 @@ static int make_plan(int B, int C, int H, int W, int k, const void* ptr, TopkPla
   p->rows_per_item = rows_item;
   p->items_per_plane = (H + rows_item - 1) / rows_item;
   p->items_per_frame = C * p->items_per_plane;
-  int chunk = p->slot_elems;
-  int cap = 2 * k + chunk;
-  if (cap < 3072 + chunk) cap = 3072 + chunk;
-  p->cap = cap;
-  p->soft = cap - chunk;
-  size_t smem = (size_t)kStages * p->slot_elems * sizeof(float);
-  smem = align_up(smem, 16) + (size_t)cap * 8 + kRadixBins * 4 + kStages * 8 + 64;
+  // The list is pruned to its top-k as soon as it holds more than 2k entries, which also gives the item (and,
+  // through the per-frame published threshold, every other item of the frame) a rejection threshold early.
+  p->soft = 2 * k;
+  p->cap = p->soft + p->slot_elems;
+  size_t smem = align_up((size_t)kStages * p->slot_elems * sizeof(float), 16);
+  smem += (size_t)p->cap * 8 + kRadixBins * 4 + kStages * 8 + 64 + (size_t)(R + 4) * 2 * sizeof(int);
   p->smem_bytes = smem;
   p->cand_bytes = align_up((size_t)B * p->items_per_frame * (size_t)k * 8, 256);
   p->count_bytes = align_up((size_t)B * p->items_per_frame * 4, 256);
+  p->thr_bytes = align_up((size_t)B * 4, 256);
   return 0;
 }
 
@@ -79,19 +78,31 @@ static int make_plan(int B, int C, int H, int W, int k, const void* ptr, TopkPla
 // ----------------------------------------------------------------------------------------------
 struct TileArgs {
   const float* hm;
-  int C, H, W, k;
+  int B, C, H, W, k;
   int R, slot_elems, rows_per_item, items_per_plane;
   int cap, soft;
   unsigned long long* cand;  // [B*items_per_frame][k]
   int* cand_count;           // [B*items_per_frame]
+  uint32_t* frame_thr;       // [B] published rejection threshold (order-preserving key of a logit / value), 0 = none
 };
 
-// list helpers ---------------------------------------------------------------------------------
-struct ListState {
-  unsigned long long* list;
-  int* count;                // shared counter
-  unsigned long long* thr;   // shared running threshold (composite); 0 = none
-};
+// x < m can still tie after the sigmoid (saturation, or a sub-ulp gap): the reference compares sigmoid values
+// (decode.py:252), so those rare cases are decided on the sigmoids themselves.
+__device__ __noinline__ bool sigmoid_tie(float x, float m) { return sigmoid_ref(x) == sigmoid_ref(m); }
+
+// A logit x_c such that every x < x_c has sigmoid(x) strictly below the score s_k (with a few-ulp guard for the
+// last-bit wobble of expf).  Returns the order-preserving key of x_c, or 0 when no such logit is found cheaply
+// (saturated scores) — then nothing is rejected up front and the exact prune alone bounds the list.
+__device__ uint32_t reject_key_for_score(float s_k) {
+  if (!(s_k > 0.0f) || !(s_k < 1.0f)) return 0u;
+  const float x0 = logf(__fdiv_rn(s_k, __fsub_rn(1.0f, s_k)));
+  float margin = 1e-3f * fmaxf(1.0f, fabsf(x0));
+  for (int t = 0; t < 4; ++t, margin *= 8.0f) {
+    const float xc = x0 - margin;
+    if (sigmoid_ref(xc) < s_k * (1.0f - 4e-6f)) return float_to_key(xc);
+  }
+  return 0u;
+}
 
 template <int MODE, bool BULK>
 __global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(TileArgs a) {
@@ -106,13 +117,21 @@ __global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(TileArgs a) {
   off += kRadixBins * 4;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + off);
   off += kStages * 8;
-  uint32_t* ctl = reinterpret_cast<uint32_t*>(smem_raw + off);  // [0..3] select ctl, [4] count, [5] emit
-  __shared__ unsigned long long s_thr;
+  uint32_t* ctl = reinterpret_cast<uint32_t*>(smem_raw + off);  // [0..3] select ctl, [4] count, [5] emit, [6] n_conv
+  off += 64;
+  int* rowtab = reinterpret_cast<int*>(smem_raw + off);          // [2][R+4] ring offsets of rows ra-1 .. rb
+  __shared__ unsigned long long s_thr;                           // push filter (see push())
+  __shared__ int s_wsum[kTileThreads / 32], s_base;
 
-  const int item = blockIdx.x;
-  const int ip = item % a.items_per_plane;
-  const long long plane = item / a.items_per_plane;  // b*C + c
-  const int c_in_frame = (int)(plane % a.C);
+  // Block -> item mapping interleaves the frames (consecutive blocks work on different frames), so that the
+  // first items of EVERY frame finish early and publish a threshold the frame's remaining items can use.
+  const int items_per_frame = a.C * a.items_per_plane;
+  const int frame = blockIdx.x % a.B;
+  const int item_in_frame = blockIdx.x / a.B;
+  const int item = frame * items_per_frame + item_in_frame;
+  const int ip = item_in_frame % a.items_per_plane;
+  const int c_in_frame = item_in_frame / a.items_per_plane;
+  const long long plane = (long long)frame * a.C + c_in_frame;
   const int r0 = ip * a.rows_per_item;
   const int r1 = min(H, r0 + a.rows_per_item);
   const int lo = max(r0 - 1, 0);
@@ -127,7 +146,8 @@ __global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(TileArgs a) {
       mbar_fence_init();
     }
     ctl[4] = 0;
-    s_thr = 0ull;
+    ctl[6] = 0;
+    s_thr = (unsigned long long)(*reinterpret_cast<volatile uint32_t*>(a.frame_thr + frame)) << 32;
   }
   __syncthreads();
 
@@ -139,33 +159,69 @@ __global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(TileArgs a) {
     mbar_expect_tx(bar, bytes);
     bulk_g2s(ring + (size_t)(j % kStages) * a.slot_elems, base + (size_t)row * W, bytes, bar);
   };
-  if (BULK) {
-    if (tid == 0) {
-      const int pre = min(nchunks, kStages);
-      for (int j = 0; j < pre; ++j) issue_chunk(j);
-    }
+  if (BULK && tid == 0) {
+    const int pre = min(nchunks, kStages);
+    for (int j = 0; j < pre; ++j) issue_chunk(j);
   }
 
-  auto row_ptr = [&](int r) -> const float* {  // r in [lo, hi)
+  auto row_off = [&](int r) -> int {  // ring offset (in floats) of plane row r, -1 when the row does not exist
+    if (r < 0 || r >= H) return -1;
     const int q = r - lo;
     const int ch = q / R;
-    return ring + (size_t)(ch % kStages) * a.slot_elems + (size_t)(q - ch * R) * W;
+    return (ch % kStages) * a.slot_elems + (q - ch * R) * W;
   };
+  auto fill_rowtab = [&](int j) {  // rows ra-1 .. rb of step j
+    const int ra = max(lo + j * R, r0);
+    const int rb = min(min(lo + (j + 1) * R, hi), r1);
+    int* tab = rowtab + (j & 1) * (R + 4);
+    for (int i = tid; i < rb - ra + 2; i += kTileThreads) tab[i] = row_off(ra - 1 + i);
+  };
+  fill_rowtab(0);
+  __syncthreads();  // table of step 0 visible to everyone (later tables ride on the end-of-step barrier)
 
   int* count_p = reinterpret_cast<int*>(&ctl[4]);
   int my_end = 0;  // highest (slot+1) this thread produced in the current step
   unsigned long long thr = 0ull;
+  float thr_f = TAUV_NEG_INF;
 
-  auto push = [&](float x, int r, int col) {
-    // x is a surviving logit (MODE 1) or a raw value (MODE 0)
-    float s = (MODE == TAUV_TOPK_SIGMOID_PEAK) ? sigmoid_ref(x) : x;
-    if (MODE == TAUV_TOPK_SIGMOID_PEAK && !(s > 0.0f)) return;  // zero-valued: handled by the merge filler
-    const uint32_t flat = plane_flat0 + (uint32_t)(r * W + col);
-    const unsigned long long c = make_composite(float_to_key(s), flat);
-    if (c < thr) return;
+  // A list entry is a 64-bit "pre-composite": order-preserving key of the VALUE in the high word, ~flat index in
+  // the low word.  In RAW mode that already is the final sort key.  In SIGMOID_PEAK mode the value is the logit;
+  // the sigmoid (and the final key) is applied later, densely, by convert().  Entries below `thr` are provably
+  // outside the frame's top-k and never enter the list.
+  auto push = [&](float x, uint32_t flat) {
+    const unsigned long long pre = make_composite(float_to_key(x), flat);
+    if (pre < thr) return;
     const int slot = atomicAdd(count_p, 1);
-    list[slot] = c;  // capacity is guaranteed by the prune policy (cap >= soft + chunk elems)
+    list[slot] = pre;  // capacity is guaranteed by the prune policy (cap = soft + chunk elements)
     my_end = max(my_end, slot + 1);
+  };
+
+  // logit pre-composites [n_conv, n) -> score composites (0 for a sigmoid that underflowed to 0: zero-valued cells
+  // are supplied by the merge kernel's filler, like non-peaks)
+  auto convert = [&](int n) {
+    if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
+      for (int i = (int)ctl[6] + tid; i < n; i += kTileThreads) {
+        const unsigned long long pre = list[i];
+        const float s = sigmoid_ref(key_to_float(composite_key(pre)));
+        list[i] = (s > 0.0f) ? (((unsigned long long)float_to_key(s) << 32) | (pre & 0xffffffffull)) : 0ull;
+      }
+      __syncthreads();
+    }
+  };
+  // after a select with threshold T over score composites: new push filter + publication
+  auto publish = [&](unsigned long long T, int n_kept) {  // thread 0 only
+    if (n_kept < a.k) return;
+    uint32_t key;
+    if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
+      key = reject_key_for_score(key_to_float(composite_key(T)));
+      if (key == 0u) return;
+      const unsigned long long t = (unsigned long long)key << 32;
+      if (t > s_thr) s_thr = t;
+    } else {
+      key = composite_key(T);
+      if (T > s_thr) s_thr = T;
+    }
+    atomicMax(a.frame_thr + frame, key);
   };
 
   for (int j = 0; j < nchunks; ++j) {
@@ -174,7 +230,6 @@ __global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(TileArgs a) {
       mbar_wait(&bars[j % kStages], (uint32_t)((j / kStages) & 1));
       if (j + 1 < nchunks) mbar_wait(&bars[(j + 1) % kStages], (uint32_t)(((j + 1) / kStages) & 1));
     } else {
-      // plain-load fallback: (re)load chunks j-1..j+1 synchronously
       __syncthreads();
       for (int jj = max(j - 1, 0); jj <= min(j + 1, nchunks - 1); ++jj) {
         const int row = lo + jj * R;
@@ -185,110 +240,124 @@ __global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(TileArgs a) {
       }
       __syncthreads();
     }
+    // what other items of this frame have published meanwhile: the load is issued here and consumed at the end
+    // of the step (folded into s_thr for the next step), so its L2 latency hides behind the step's work
+    uint32_t pub_key = 0u;
+    if (tid == 0) pub_key = *reinterpret_cast<volatile uint32_t*>(a.frame_thr + frame);
     thr = s_thr;
+    thr_f = key_to_float(composite_key(thr));
+    if (composite_key(thr) == 0u) thr_f = TAUV_NEG_INF;
     my_end = 0;
     const int ra = max(lo + j * R, r0);
     const int rb = min(min(lo + (j + 1) * R, hi), r1);
+    const int* tab = rowtab + (j & 1) * (R + 4);  // tab[i] = ring offset of row ra-1+i
 
     if (BULK) {
-      // ---- vector path: task = (pair of rows, strip of 4 columns) ----
+      // ---- vector path: one float4 strip per task; only strips holding a value >= thr are examined further ----
       const int S = W >> 2;
-      const int npairs = (rb - ra + 1) >> 1;
-      const int ntasks = npairs * S;
-      const int ntasks_pad = (ntasks + 31) & ~31;
-      const int lane = tid & 31;
-      for (int task = tid; task < ntasks_pad; task += kTileThreads) {
-        const bool active = task < ntasks;
-        const int pr = active ? task / S : 0;
-        const int cs = active ? task - pr * S : 0;
-        const int rt = ra + 2 * pr;  // first output row of this task
+      const int ntasks = (rb - ra) * S;
+      int ri = tid / S, cs = tid - ri * S;         // task = (row ra+ri, strip cs)
+      const int dr = kTileThreads / S, dc = kTileThreads - dr * S;
+#pragma unroll 1
+      for (int task = tid; task < ntasks; task += kTileThreads) {
+        const int o1 = tab[ri + 1];
         const int col = cs << 2;
-        float4 v[4];
-        float hm_[4][4];  // horizontal 3-max for rows rt-1 .. rt+2
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = rt - 1 + i;
-          const bool in = active && r >= 0 && r < H && r < hi;  // r >= lo holds by construction
-          float4 x = make_float4(TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF);
-          const float* rp = nullptr;
-          if (in) {
-            rp = row_ptr(r);
-            x = *reinterpret_cast<const float4*>(rp + col);
-          }
-          float l = __shfl_up_sync(0xffffffffu, x.w, 1);
-          float rr = __shfl_down_sync(0xffffffffu, x.x, 1);
-          if (cs == 0) l = TAUV_NEG_INF;
-          else if (lane == 0 && in) l = rp[col - 1];
-          if (cs == S - 1) rr = TAUV_NEG_INF;
-          else if (lane == 31 && in) rr = rp[col + 4];
-          if (!in) { l = TAUV_NEG_INF; rr = TAUV_NEG_INF; }
-          v[i] = x;
-          hm_[i][0] = fmaxf(fmaxf(l, x.x), x.y);
-          hm_[i][1] = fmaxf(fmaxf(x.x, x.y), x.z);
-          hm_[i][2] = fmaxf(fmaxf(x.y, x.z), x.w);
-          hm_[i][3] = fmaxf(fmaxf(x.z, x.w), rr);
-        }
-        if (!active) continue;
-#pragma unroll
-        for (int i = 1; i <= 2; ++i) {
-          const int r = rt - 1 + i;
-          if (r >= rb) break;
-          const float xs[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const float x = xs[cc];
-            if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
-              const float m = fmaxf(fmaxf(hm_[i - 1][cc], hm_[i][cc]), hm_[i + 1][cc]);
-              bool peak = (x >= m);
-              if (!peak) {
-                // x < m can still tie after the sigmoid (saturation, or a sub-ulp gap): the
-                // reference compares sigmoid values (decode.py:252).  Exact check, rarely taken.
-                if (x > 4.0f || m < -80.0f || (m - x) < 1e-3f) peak = (sigmoid_ref(x) == sigmoid_ref(m));
+        const float4 x = *reinterpret_cast<const float4*>(ring + o1 + col);
+        const float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+        if (mx >= thr_f) {
+          const uint32_t flat = plane_flat0 + (uint32_t)((ra + ri) * W + col);
+          if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
+            // 3x3 neighbourhood of the strip: columns col-1 .. col+4 of rows r-1, r, r+1 (-inf outside the plane)
+            const int o0 = tab[ri], o2 = tab[ri + 2];
+            float cm[6];  // column-wise max over the three rows
+            {
+              const bool hl = col > 0, hr = col + 4 < W;
+              float4 u = make_float4(TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF), d = u;
+              float ul = TAUV_NEG_INF, ur = TAUV_NEG_INF, dl = TAUV_NEG_INF, dright = TAUV_NEG_INF;
+              if (o0 >= 0) {
+                u = *reinterpret_cast<const float4*>(ring + o0 + col);
+                if (hl) ul = ring[o0 + col - 1];
+                if (hr) ur = ring[o0 + col + 4];
               }
-              if (peak) push(x, r, col + cc);
-            } else {
-              push(x, r, col + cc);
+              if (o2 >= 0) {
+                d = *reinterpret_cast<const float4*>(ring + o2 + col);
+                if (hl) dl = ring[o2 + col - 1];
+                if (hr) dright = ring[o2 + col + 4];
+              }
+              const float ml = hl ? ring[o1 + col - 1] : TAUV_NEG_INF;
+              const float mr = hr ? ring[o1 + col + 4] : TAUV_NEG_INF;
+              cm[0] = fmaxf(fmaxf(ul, ml), dl);
+              cm[1] = fmaxf(fmaxf(u.x, x.x), d.x);
+              cm[2] = fmaxf(fmaxf(u.y, x.y), d.y);
+              cm[3] = fmaxf(fmaxf(u.z, x.z), d.z);
+              cm[4] = fmaxf(fmaxf(u.w, x.w), d.w);
+              cm[5] = fmaxf(fmaxf(ur, mr), dright);
             }
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              const float xv = xs[cc];
+              if (xv >= thr_f) {
+                const float m = fmaxf(fmaxf(cm[cc], cm[cc + 1]), cm[cc + 2]);
+                bool peak = (xv >= m);
+                if (!peak && (xv > 4.0f || m < -80.0f || (m - xv) < 1e-3f)) peak = sigmoid_tie(xv, m);
+                if (peak) push(xv, flat + cc);
+              }
+            }
+          } else {
+            if (x.x >= thr_f) push(x.x, flat);
+            if (x.y >= thr_f) push(x.y, flat + 1);
+            if (x.z >= thr_f) push(x.z, flat + 2);
+            if (x.w >= thr_f) push(x.w, flat + 3);
           }
         }
+        ri += dr;
+        cs += dc;
+        if (cs >= S) { cs -= S; ++ri; }
       }
     } else {
       // ---- scalar path (any W / unaligned base): one element per task ----
       const int n = (rb - ra) * W;
       for (int t = tid; t < n; t += kTileThreads) {
-        const int r = ra + t / W;
-        const int col = t % W;
-        const float x = row_ptr(r)[col];
+        const int ri = t / W;
+        const int col = t - ri * W;
+        const int o1 = tab[ri + 1];
+        const float xv = ring[o1 + col];
+        if (!(xv >= thr_f)) continue;
+        const uint32_t flat = plane_flat0 + (uint32_t)((ra + ri) * W + col);
         if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
           float m = TAUV_NEG_INF;
-          for (int dr = -1; dr <= 1; ++dr) {
-            const int r2 = r + dr;
-            if (r2 < 0 || r2 >= H) continue;
-            const float* rp = row_ptr(r2);
-            for (int dc = -1; dc <= 1; ++dc) {
-              const int c2 = col + dc;
-              if (c2 < 0 || c2 >= W) continue;
-              m = fmaxf(m, rp[c2]);
+          for (int dy = 0; dy < 3; ++dy) {
+            const int o = tab[ri + dy];
+            if (o < 0) continue;
+            for (int dc2 = -1; dc2 <= 1; ++dc2) {
+              const int c2 = col + dc2;
+              if (c2 >= 0 && c2 < W) m = fmaxf(m, ring[o + c2]);
             }
           }
-          bool peak = (x >= m);
-          if (!peak && (x > 4.0f || m < -80.0f || (m - x) < 1e-3f)) peak = (sigmoid_ref(x) == sigmoid_ref(m));
-          if (peak) push(x, r, col);
+          bool peak = (xv >= m);
+          if (!peak && (xv > 4.0f || m < -80.0f || (m - xv) < 1e-3f)) peak = sigmoid_tie(xv, m);
+          if (peak) push(xv, flat);
         } else {
-          push(x, r, col);
+          push(xv, flat);
         }
       }
     }
 
     // ---- end of step: everyone is done with chunk j-1; prune if the list is getting full ----
+    if (j + 1 < nchunks) fill_rowtab(j + 1);
+    if (tid == 0) {
+      const unsigned long long pub = (unsigned long long)pub_key << 32;
+      if (pub > s_thr) s_thr = pub;
+    }
     const int over = __syncthreads_or(my_end > a.soft);
     if (BULK && tid == 0 && j >= 1 && j - 1 + kStages < nchunks) issue_chunk(j - 1 + kStages);
     if (over) {
       const int n = *count_p;
+      convert(n);
       const unsigned long long T =
           block_kth_largest<kTileThreads>([&](int i) { return list[i]; }, n, a.k, hist, ctl);
       // stable in-place compaction, kTileThreads entries per round (write index <= read index)
-      __shared__ int s_base, s_wsum[kTileThreads / 32];
       if (tid == 0) s_base = 0;
       __syncthreads();
       for (int start = 0; start < n; start += kTileThreads) {
@@ -297,7 +366,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(TileArgs a) {
         bool keep = false;
         if (i < n) {
           c = list[i];
-          keep = (c >= T);
+          keep = (c >= T) && (c != 0ull);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         const int lane = tid & 31, warp = tid >> 5;
@@ -316,7 +385,8 @@ __global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(TileArgs a) {
       }
       if (tid == 0) {
         *count_p = s_base;
-        s_thr = T;
+        ctl[6] = (uint32_t)s_base;  // everything kept is converted
+        publish(T, s_base);
       }
       __syncthreads();
     }
@@ -325,6 +395,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(TileArgs a) {
   // ---- emit the item's top-k ----
   __syncthreads();
   const int n = *count_p;
+  convert(n);
   const unsigned long long T =
       block_kth_largest<kTileThreads>([&](int i) { return list[i]; }, n, a.k, hist, ctl);
   if (tid == 0) ctl[5] = 0;
@@ -332,10 +403,13 @@ __global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(TileArgs a) {
   unsigned long long* out = a.cand + (size_t)item * a.k;
   for (int i = tid; i < n; i += kTileThreads) {
     const unsigned long long c = list[i];
-    if (c >= T) out[atomicAdd(&ctl[5], 1u)] = c;
+    if (c >= T && c != 0ull) out[atomicAdd(&ctl[5], 1u)] = c;
   }
   __syncthreads();
-  if (tid == 0) a.cand_count[item] = (int)ctl[5];
+  if (tid == 0) {
+    a.cand_count[item] = (int)ctl[5];
+    publish(T, (int)ctl[5]);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -378,18 +452,19 @@ __device__ __forceinline__ void box_one(const BoxArgs& g, int b, long long slot,
 template <int MODE>
 __global__ void __launch_bounds__(kMergeThreads) merge_kernel(
     const unsigned long long* __restrict__ cand, const int* __restrict__ cand_count,
-    int items_per_frame, int k, int H, int W, long long chw, int64_t* __restrict__ index,
+    int items_per_frame, int k, int H, int W, int pool_cap, int64_t* __restrict__ index,
     int64_t* __restrict__ label, float* __restrict__ score, BoxArgs g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   int p2 = 1;
   while (p2 < k) p2 <<= 1;
-  unsigned long long* sel = reinterpret_cast<unsigned long long*>(smem_raw);  // [p2]
-  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)p2 * 8);    // [2048]
-  uint32_t* flags = hist;                                                      // reused: [k]
+  unsigned long long* sel = reinterpret_cast<unsigned long long*>(smem_raw);                 // [p2]
+  unsigned long long* pool = sel + p2;                                                        // [pool_cap]
+  uint32_t* hist = reinterpret_cast<uint32_t*>(pool + pool_cap);                              // [max(2048,k)]
+  uint32_t* flags = hist;                                                                     // reused: [k]
   __shared__ uint32_t ctl[8];
-  __shared__ int s_total, s_first_below;
+  __shared__ int s_total, s_first_below, s_pool_n;
   __shared__ int s_wsum[kMergeThreads / 32];
 
   const unsigned long long* fc = cand + (size_t)b * items_per_frame * k;
@@ -399,6 +474,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(
   if (tid == 0) {
     s_total = 0;
     s_first_below = k;
+    s_pool_n = 0;
     ctl[5] = 0;
   }
   for (int i = tid; i < p2; i += kMergeThreads) sel[i] = 0ull;
@@ -409,16 +485,35 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(
   __syncthreads();
   const int total = s_total;
 
-  // candidates live in a padded [items][k] table: slot i is valid iff (i % k) < cnt[i / k].
-  auto load = [&](int i) -> unsigned long long {
-    const int it = i / k;
-    return (i - it * k) < cnt[it] ? fc[i] : 0ull;  // 0 never beats a real composite
-  };
-  const unsigned long long T =
-      (total > k) ? block_kth_largest<kMergeThreads>(load, nslots, k, hist, ctl) : 1ull;
-  for (int i = tid; i < nslots; i += kMergeThreads) {
-    const unsigned long long c = load(i);
-    if (c >= T && c != 0ull) sel[atomicAdd(&ctl[5], 1u)] = c;
+  unsigned long long T = 1ull;  // total <= k: everything valid (non-zero) is selected
+  if (total <= pool_cap) {
+    // usual case (items reject most of their candidates against the frame threshold): pull the frame's
+    // candidates into shared memory once, one warp per item, then select there
+    for (int it = warp; it < items_per_frame; it += kMergeThreads / 32) {
+      const int c = cnt[it];
+      if (c == 0) continue;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_pool_n, c);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (int i = lane; i < c; i += 32) pool[base + i] = fc[(size_t)it * k + i];
+    }
+    __syncthreads();
+    if (total > k) T = block_kth_largest<kMergeThreads>([&](int i) { return pool[i]; }, total, k, hist, ctl);
+    for (int i = tid; i < total; i += kMergeThreads) {
+      const unsigned long long c = pool[i];
+      if (c >= T && c != 0ull) sel[atomicAdd(&ctl[5], 1u)] = c;
+    }
+  } else {
+    // candidates live in a padded [items][k] table: slot i is valid iff (i % k) < cnt[i / k]
+    auto load = [&](int i) -> unsigned long long {
+      const int it = i / k;
+      return (i - it * k) < cnt[it] ? fc[i] : 0ull;  // 0 never beats a real composite
+    };
+    if (total > k) T = block_kth_largest<kMergeThreads>(load, nslots, k, hist, ctl);
+    for (int i = tid; i < nslots; i += kMergeThreads) {
+      const unsigned long long c = load(i);
+      if (c >= T && c != 0ull) sel[atomicAdd(&ctl[5], 1u)] = c;
+    }
   }
   __syncthreads();
   const int npos = (int)ctl[5];  // = min(k, total)
@@ -444,8 +539,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(
     }
   }
   if (MODE == TAUV_TOPK_SIGMOID_PEAK && npos < k) {
-    // Dense stable top-k semantics: the remaining slots are zero-valued cells in ascending flat
-    // index.  At most npos of the first k cells are positive peaks, so [0,k) always suffices.
+    // Dense stable top-k semantics: the remaining slots are zero-valued cells in ascending flat index.  At most
+    // npos of the first k cells are positive peaks, so [0,k) always suffices.
     __syncthreads();
     for (int i = tid; i < k; i += kMergeThreads) flags[i] = 0u;
     __syncthreads();
@@ -460,7 +555,6 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(
       const int i = start + tid;
       const bool freec = (i < k) && (flags[i] == 0u);
       const unsigned bal = __ballot_sync(0xffffffffu, freec);
-      const int lane = tid & 31, warp = tid >> 5;
       if (lane == 0) s_wsum[warp] = __popc(bal);
       __syncthreads();
       int pos = base + __popc(bal & ((1u << lane) - 1u));
@@ -488,7 +582,6 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(
       __syncthreads();
     }
   }
-  (void)chw;
   if (g.enabled) {
     __syncthreads();
     if (tid == 0) g.count[b] = s_first_below;
@@ -579,14 +672,15 @@ static int plan_and_check(const float* hm, int B, int C, int H, int W, int k, vo
                           TileArgs* a) {
   make_plan(B, C, H, W, k, hm, p);
   TAUV_REQUIRE(ws != nullptr && (uintptr_t)ws % 256 == 0, TAUV_E_WORKSPACE, "workspace must be 256-byte aligned");
-  TAUV_REQUIRE(ws_bytes >= p->cand_bytes + p->count_bytes, TAUV_E_WORKSPACE, "workspace %zu < required %zu", ws_bytes,
-               p->cand_bytes + p->count_bytes);
+  TAUV_REQUIRE(ws_bytes >= p->cand_bytes + p->count_bytes + p->thr_bytes, TAUV_E_WORKSPACE,
+               "workspace %zu < required %zu", ws_bytes, p->cand_bytes + p->count_bytes + p->thr_bytes);
   TAUV_REQUIRE(p->smem_bytes <= 227 * 1024, TAUV_E_UNSUPPORTED, "tile needs %zu B shared memory", p->smem_bytes);
-  a->hm = hm; a->C = C; a->H = H; a->W = W; a->k = k;
+  a->hm = hm; a->B = B; a->C = C; a->H = H; a->W = W; a->k = k;
   a->R = p->rows_per_chunk; a->slot_elems = p->slot_elems; a->rows_per_item = p->rows_per_item;
   a->items_per_plane = p->items_per_plane; a->cap = p->cap; a->soft = p->soft;
   a->cand = reinterpret_cast<unsigned long long*>(ws);
   a->cand_count = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws) + p->cand_bytes);
+  a->frame_thr = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(ws) + p->cand_bytes + p->count_bytes);
   const long long items = (long long)B * p->items_per_frame;
   TAUV_REQUIRE(items < (1LL << 31), TAUV_E_UNSUPPORTED, "too many items (%lld)", items);
   return 0;
@@ -603,6 +697,7 @@ static int run_stage1(const float* hm, int B, int C, int H, int W, int k, int mo
   if (mode == TAUV_TOPK_SIGMOID_PEAK) kern = p.bulk ? tile_topk_kernel<1, true> : tile_topk_kernel<1, false>;
   else kern = p.bulk ? tile_topk_kernel<0, true> : tile_topk_kernel<0, false>;
   TAUV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+  TAUV_CUDA(cudaMemsetAsync(a.frame_thr, 0, p.thr_bytes, st));  // key 0 = "no threshold published yet"
   kern<<<(unsigned)items, kTileThreads, p.smem_bytes, st>>>(a);
   TAUV_LAUNCH_CHECK("tile_topk_kernel");
   return 0;
@@ -616,16 +711,17 @@ static int run_stage2(int B, int C, int H, int W, int k, int mode, int64_t* inde
   if (int e = plan_and_check(nullptr, B, C, H, W, k, ws, ws_bytes, &p, &a)) return e;
   int p2 = 1;
   while (p2 < k) p2 <<= 1;
-  const size_t msmem = (size_t)p2 * 8 + (size_t)(kRadixBins > k ? kRadixBins : k) * 4;
-  const long long chw = (long long)C * H * W;
+  long long pool_cap = (long long)p.items_per_frame * k;
+  if (pool_cap > 12288) pool_cap = 12288;
+  const size_t msmem = (size_t)p2 * 8 + (size_t)pool_cap * 8 + (size_t)(kRadixBins > k ? kRadixBins : k) * 4;
   if (mode == TAUV_TOPK_SIGMOID_PEAK) {
     TAUV_CUDA(cudaFuncSetAttribute(merge_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-    merge_kernel<1><<<B, kMergeThreads, msmem, st>>>(a.cand, a.cand_count, p.items_per_frame, k, H, W, chw, index,
-                                                     label, score, box);
+    merge_kernel<1><<<B, kMergeThreads, msmem, st>>>(a.cand, a.cand_count, p.items_per_frame, k, H, W, (int)pool_cap,
+                                                     index, label, score, box);
   } else {
     TAUV_CUDA(cudaFuncSetAttribute(merge_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-    merge_kernel<0><<<B, kMergeThreads, msmem, st>>>(a.cand, a.cand_count, p.items_per_frame, k, H, W, chw, index,
-                                                     label, score, box);
+    merge_kernel<0><<<B, kMergeThreads, msmem, st>>>(a.cand, a.cand_count, p.items_per_frame, k, H, W, (int)pool_cap,
+                                                     index, label, score, box);
   }
   TAUV_LAUNCH_CHECK("merge_kernel");
   return 0;
@@ -666,7 +762,7 @@ extern "C" size_t tauv_heatmap_topk_workspace_bytes(int B, int C, int H, int W, 
   TopkPlan p;
   // alignment only affects the load path, never the sizes
   make_plan(B, C, H, W, k, nullptr, &p);
-  return p.cand_bytes + p.count_bytes;
+  return p.cand_bytes + p.count_bytes + p.thr_bytes;
 }
 
 extern "C" int tauv_heatmap_topk(const float* heatmap, int B, int C, int H, int W, int k, int mode, int64_t* index,

@@ -172,6 +172,36 @@ __device__ unsigned long long block_kth_largest(LoadFn load, int n, int k, uint3
   int hi = 64;                       // bits [hi,64) of the threshold are fixed in `prefix`
   int k_rem = k;
   __shared__ uint32_t warp_tot[32];
+  __shared__ unsigned long long s_and, s_or;
+  // Skip the leading bits every key shares (scores of one frame sit in one or two binades, so the
+  // first 11-bit digit would otherwise be wasted): one AND/OR sweep costs less than one radix pass.
+  {
+    if (tid == 0) {
+      s_and = ~0ull;
+      s_or = 0ull;
+    }
+    __syncthreads();
+    unsigned long long a = ~0ull, o = 0ull;
+    for (int i = tid; i < n; i += NT) {
+      const unsigned long long c = load(i);
+      a &= c;
+      o |= c;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      a &= __shfl_xor_sync(0xffffffffu, a, d);
+      o |= __shfl_xor_sync(0xffffffffu, o, d);
+    }
+    if ((tid & 31) == 0) {
+      atomicAnd(&s_and, a);
+      atomicOr(&s_or, o);
+    }
+    __syncthreads();
+    const unsigned long long diff = s_and ^ s_or;
+    hi = diff ? 64 - __clzll((long long)diff) : 0;  // highest differing bit + 1
+    prefix = hi < 64 ? (s_or >> hi) : 0ull;
+    if (hi == 0) return s_or;  // all keys equal (n == 1 after the k >= n test cannot happen; defensive)
+  }
   while (hi > 0) {
     const int bits = hi >= kRadixBits ? kRadixBits : hi;
     const int lo = hi - bits;
