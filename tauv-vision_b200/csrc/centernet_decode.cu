@@ -7,11 +7,14 @@
 //   decode.py:204-234  per-detection gather + box arithmetic
 //
 // Pipeline (2 launches for a whole batch):
-//   K1 tile_topk_kernel : one CTA per "item" (a band of rows of one (frame, class) plane).  The
-//      band streams HBM -> shared through a ring of 1-D bulk copies (cp.async.bulk + mbarrier);
-//      peaks are found on the logits (sigmoid is monotone), the sigmoid is evaluated only for
-//      survivors, and the item's top-k candidates (64-bit composite keys) go to a small global
-//      candidate table.  The logits are read from HBM exactly once; nothing dense is written.
+//   K1 tile_topk_kernel : one CTA per "item" (a band of rows of one (frame, class) plane).  Every
+//      thread streams 128-bit loads straight from HBM (measured on B200: 5.46 TB/s read-only for
+//      plain vector loads vs 4.9 TB/s for a cp.async.bulk shared-memory ring, tools/ring_bench.cu)
+//      and compares each strip with the frame's published rejection threshold; only strips that
+//      pass get the 3x3 peak test (on the logits: sigmoid is monotone), the sigmoid is evaluated
+//      only for survivors, and the item's top-k candidates (64-bit composite keys) go to a small
+//      global candidate table and into a per-frame histogram from which the threshold is
+//      republished.  The logits are read from HBM exactly once; nothing dense is written.
 //   K2 merge_kernel     : one CTA per frame selects the frame's top-k from its items' candidates
 //      (radix select + bitonic sort), fills zero-score slots like a dense stable top-k would,
 //      and (optionally) gathers size/offset/depth and does the box arithmetic.
@@ -20,56 +23,46 @@
 namespace tauv {
 
 constexpr int kTileThreads = 256;
-constexpr int kStages = 6;          // ring slots
-constexpr int kChunkElems = 2048;   // target elements per ring slot
-constexpr int kItemElems = 16384;   // target elements per item
+constexpr int kItemElems = 16384;   // target elements per item (one CTA, 16 float4 loads per thread)
 constexpr int kMergeThreads = 1024;
 constexpr int kMaxK = 4096;
+constexpr int kFrameBins = 4096;    // per-frame candidate histogram: top 12 bits of the order-preserving key
+constexpr int kFrameStateWords = kFrameBins + 4;  // [0] published reject key, [1] highest occupied bin, [2] candidates so far
 
 struct TopkPlan {
-  int rows_per_chunk;   // R
-  int slot_elems;       // R*W rounded up to a multiple of 4
   int rows_per_item;
   int items_per_plane;
   int items_per_frame;  // C * items_per_plane
   int cap;              // candidate-list capacity (entries)
-  int soft;             // prune when the list grows beyond this
-  int bulk;             // 1: bulk-copy ring, 0: plain loads
+  int soft;             // overflow-safe path: prune when the list grows beyond this
+  int sub_elems;        // overflow-safe path: elements per sub-step (cap - soft)
+  int vec;              // 1: 128-bit loads, 0: scalar loads (W % 4 != 0 or unaligned base)
   size_t smem_bytes;
-  size_t cand_bytes, count_bytes, thr_bytes;
+  size_t cand_bytes, count_bytes, state_bytes;
 };
 
 static int make_plan(int B, int C, int H, int W, int k, const void* ptr, TopkPlan* p) {
-  p->bulk = (W % 4 == 0) && ((uintptr_t)ptr % 16 == 0);
-  int R = kChunkElems / W;
-  if (R < 1) R = 1;
-  if (R > H) R = H;
-  p->rows_per_chunk = R;
-  p->slot_elems = (int)align_up((size_t)R * W, 4);
-  // item: whole chunks, about kItemElems elements, but enough items to fill the machine
-  int rows_item = (int)align_up((size_t)((kItemElems + W - 1) / W), (size_t)R);
-  if (rows_item < R) rows_item = R;
+  p->vec = (W % 4 == 0) && ((uintptr_t)ptr % 16 == 0);
+  // item: a band of rows of one (frame, class) plane, about kItemElems elements, but enough items to fill the machine
+  int rows_item = (kItemElems + W - 1) / W;
+  if (rows_item < 1) rows_item = 1;
   const long long planes = (long long)B * C;
   const int sms = num_sms();
-  while (rows_item > R && planes * ((H + rows_item - 1) / rows_item) < 3LL * sms) {
-    int next = (int)align_up((size_t)(rows_item / 2), (size_t)R);
-    if (next >= rows_item) break;
-    rows_item = next;
-  }
+  while (rows_item > 1 && planes * ((H + rows_item - 1) / rows_item) < 8LL * sms) rows_item = (rows_item + 1) / 2;
   if (rows_item > H) rows_item = H;
   p->rows_per_item = rows_item;
   p->items_per_plane = (H + rows_item - 1) / rows_item;
   p->items_per_frame = C * p->items_per_plane;
-  // The list is pruned to its top-k as soon as it holds more than 2k entries, which also gives the item (and,
-  // through the per-frame published threshold, every other item of the frame) a rejection threshold early.
+  // An item's peaks (about 1/9 of its cells on noise, far fewer once the frame has published a threshold) go to a
+  // shared-memory list.  If they do not fit (plateaus, dense data without a threshold) the item is redone in
+  // sub-steps of cap - soft elements with an exact prune to the top-k whenever the list passes soft = 2k.
   p->soft = 2 * k;
-  p->cap = p->soft + p->slot_elems;
-  size_t smem = align_up((size_t)kStages * p->slot_elems * sizeof(float), 16);
-  smem += (size_t)p->cap * 8 + kRadixBins * 4 + kStages * 8 + 64 + (size_t)(R + 4) * 2 * sizeof(int);
-  p->smem_bytes = smem;
+  p->cap = 4 * k > 2560 ? 4 * k : 2560;
+  p->sub_elems = ((p->cap - p->soft) / 4) * 4;
+  p->smem_bytes = (size_t)p->cap * 8 + kRadixBins * 4;
   p->cand_bytes = align_up((size_t)B * p->items_per_frame * (size_t)k * 8, 256);
   p->count_bytes = align_up((size_t)B * p->items_per_frame * 4, 256);
-  p->thr_bytes = align_up((size_t)B * 4, 256);
+  p->state_bytes = align_up((size_t)B * kFrameStateWords * 4, 256);
   return 0;
 }
 
@@ -79,337 +72,390 @@ static int make_plan(int B, int C, int H, int W, int k, const void* ptr, TopkPla
 struct TileArgs {
   const float* hm;
   int B, C, H, W, k;
-  int R, slot_elems, rows_per_item, items_per_plane;
-  int cap, soft;
+  int rows_per_item, items_per_plane;
+  int cap, soft, sub_elems;
   unsigned long long* cand;  // [B*items_per_frame][k]
   int* cand_count;           // [B*items_per_frame]
-  uint32_t* frame_thr;       // [B] published rejection threshold (order-preserving key of a logit / value), 0 = none
+  uint32_t* frame_state;     // [B][kFrameStateWords], zeroed before the launch
 };
 
 // x < m can still tie after the sigmoid (saturation, or a sub-ulp gap): the reference compares sigmoid values
 // (decode.py:252), so those rare cases are decided on the sigmoids themselves.
 __device__ __noinline__ bool sigmoid_tie(float x, float m) { return sigmoid_ref(x) == sigmoid_ref(m); }
 
-// A logit x_c such that every x < x_c has sigmoid(x) strictly below the score s_k (with a few-ulp guard for the
-// last-bit wobble of expf).  Returns the order-preserving key of x_c, or 0 when no such logit is found cheaply
-// (saturated scores) — then nothing is rejected up front and the exact prune alone bounds the list.
-__device__ uint32_t reject_key_for_score(float s_k) {
+// A logit x_c such that every x < x_c has sigmoid(x) strictly below the score s_k, with a relative guard band that
+// covers the last-bit wobble of expf / logf.  Returns the order-preserving key of x_c, or 0 when no such logit is
+// found cheaply (saturated scores) — then nothing is rejected up front and the exact selection alone decides.
+__device__ __noinline__ uint32_t reject_key_for_score(float s_k) {
   if (!(s_k > 0.0f) || !(s_k < 1.0f)) return 0u;
   const float x0 = logf(__fdiv_rn(s_k, __fsub_rn(1.0f, s_k)));
   float margin = 1e-3f * fmaxf(1.0f, fabsf(x0));
   for (int t = 0; t < 4; ++t, margin *= 8.0f) {
     const float xc = x0 - margin;
-    if (sigmoid_ref(xc) < s_k * (1.0f - 4e-6f)) return float_to_key(xc);
+    if (sigmoid_ref(xc) < s_k * (1.0f - 2e-5f)) return float_to_key(xc);
   }
   return 0u;
 }
 
-template <int MODE, bool BULK>
-__global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(TileArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tid = threadIdx.x;
-  const int W = a.W, H = a.H, R = a.R;
-  float* ring = reinterpret_cast<float*>(smem_raw);
-  size_t off = align_up((size_t)kStages * a.slot_elems * sizeof(float), 16);
-  unsigned long long* list = reinterpret_cast<unsigned long long*>(smem_raw + off);
-  off += (size_t)a.cap * 8;
-  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + off);
-  off += kRadixBins * 4;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + off);
-  off += kStages * 8;
-  uint32_t* ctl = reinterpret_cast<uint32_t*>(smem_raw + off);  // [0..3] select ctl, [4] count, [5] emit, [6] n_conv
-  off += 64;
-  int* rowtab = reinterpret_cast<int*>(smem_raw + off);          // [2][R+4] ring offsets of rows ra-1 .. rb
-  __shared__ unsigned long long s_thr;                           // push filter (see push())
-  __shared__ int s_wsum[kTileThreads / 32], s_base;
-
-  // Block -> item mapping interleaves the frames (consecutive blocks work on different frames), so that the
-  // first items of EVERY frame finish early and publish a threshold the frame's remaining items can use.
-  const int items_per_frame = a.C * a.items_per_plane;
-  const int frame = blockIdx.x % a.B;
-  const int item_in_frame = blockIdx.x / a.B;
-  const int item = frame * items_per_frame + item_in_frame;
-  const int ip = item_in_frame % a.items_per_plane;
-  const int c_in_frame = item_in_frame / a.items_per_plane;
-  const long long plane = (long long)frame * a.C + c_in_frame;
-  const int r0 = ip * a.rows_per_item;
-  const int r1 = min(H, r0 + a.rows_per_item);
-  const int lo = max(r0 - 1, 0);
-  const int hi = min(r1 + 1, H);
-  const int nchunks = (hi - lo + R - 1) / R;
-  const float* base = a.hm + (size_t)plane * H * W;
-  const uint32_t plane_flat0 = (uint32_t)c_in_frame * (uint32_t)(H * W);
-
-  if (tid == 0) {
-    if (BULK) {
-      for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
-      mbar_fence_init();
-    }
-    ctl[4] = 0;
-    ctl[6] = 0;
-    s_thr = (unsigned long long)(*reinterpret_cast<volatile uint32_t*>(a.frame_thr + frame)) << 32;
+// Histogram bin of a final sort key.  RAW: top bits of the value key.  SIGMOID_PEAK: top bits of the key of the
+// pseudo-logit log(s/(1-s)) — the score itself has no resolution left near 1.0, its logit does.
+template <int MODE>
+__device__ __forceinline__ uint32_t frame_bin(unsigned long long c) {
+  if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
+    const float s = key_to_float(composite_key(c));
+    return float_to_key(logf(__fdiv_rn(s, __fsub_rn(1.0f, s)))) >> 20;
   }
-  __syncthreads();
+  return composite_key(c) >> 20;
+}
 
-  auto issue_chunk = [&](int j) {  // thread 0 only
-    const int row = lo + j * R;
-    const int rows = min(R, hi - row);
-    const uint32_t bytes = (uint32_t)rows * W * 4u;
-    uint64_t* bar = &bars[j % kStages];
-    mbar_expect_tx(bar, bytes);
-    bulk_g2s(ring + (size_t)(j % kStages) * a.slot_elems, base + (size_t)row * W, bytes, bar);
-  };
-  if (BULK && tid == 0) {
-    const int pre = min(nchunks, kStages);
-    for (int j = 0; j < pre; ++j) issue_chunk(j);
-  }
+// Per-CTA state in shared memory.
+struct __align__(16) TileCtx {
+  unsigned long long thr;  // push filter (a pre-composite, see push_entry)
+  float thr_f;             // its value as a float (-inf: none)
+  int count;               // list entries
+  int n_conv;              // list[0, n_conv) already hold final sort keys (SIGMOID_PEAK)
+  uint32_t emit, maxbin;
+  int flags;               // bit 1 = the list overflowed
+  int base, wsum[kTileThreads / 32];
+  uint32_t sel[4];
+};
 
-  auto row_off = [&](int r) -> int {  // ring offset (in floats) of plane row r, -1 when the row does not exist
-    if (r < 0 || r >= H) return -1;
-    const int q = r - lo;
-    const int ch = q / R;
-    return (ch % kStages) * a.slot_elems + (q - ch * R) * W;
-  };
-  auto fill_rowtab = [&](int j) {  // rows ra-1 .. rb of step j
-    const int ra = max(lo + j * R, r0);
-    const int rb = min(min(lo + (j + 1) * R, hi), r1);
-    int* tab = rowtab + (j & 1) * (R + 4);
-    for (int i = tid; i < rb - ra + 2; i += kTileThreads) tab[i] = row_off(ra - 1 + i);
-  };
-  fill_rowtab(0);
-  __syncthreads();  // table of step 0 visible to everyone (later tables ride on the end-of-step barrier)
+// A list entry is a 64-bit "pre-composite": order-preserving key of the VALUE in the high word, ~flat index in the
+// low word.  In RAW mode that already is the final sort key.  In SIGMOID_PEAK mode the value is the logit; the
+// sigmoid (and the final key) is applied later, densely, by convert_entries().  Entries below ctx->thr are provably
+// outside the frame's top-k and never enter the list.  Returns 2 when the entry had to be dropped (list full).
+__device__ __forceinline__ int push_entry(const TileArgs& a, TileCtx* ctx, unsigned long long* list, float x,
+                                          uint32_t flat) {
+  const unsigned long long pre = make_composite(float_to_key(x), flat);
+  if (pre < ctx->thr) return 0;
+  const int slot = atomicAdd(&ctx->count, 1);
+  if (slot >= a.cap) return 2;
+  list[slot] = pre;
+  return 0;
+}
 
-  int* count_p = reinterpret_cast<int*>(&ctl[4]);
-  int my_end = 0;  // highest (slot+1) this thread produced in the current step
-  unsigned long long thr = 0ull;
-  float thr_f = TAUV_NEG_INF;
-
-  // A list entry is a 64-bit "pre-composite": order-preserving key of the VALUE in the high word, ~flat index in
-  // the low word.  In RAW mode that already is the final sort key.  In SIGMOID_PEAK mode the value is the logit;
-  // the sigmoid (and the final key) is applied later, densely, by convert().  Entries below `thr` are provably
-  // outside the frame's top-k and never enter the list.
-  auto push = [&](float x, uint32_t flat) {
-    const unsigned long long pre = make_composite(float_to_key(x), flat);
-    if (pre < thr) return;
-    const int slot = atomicAdd(count_p, 1);
-    list[slot] = pre;  // capacity is guaranteed by the prune policy (cap = soft + chunk elements)
-    my_end = max(my_end, slot + 1);
-  };
-
-  // logit pre-composites [n_conv, n) -> score composites (0 for a sigmoid that underflowed to 0: zero-valued cells
-  // are supplied by the merge kernel's filler, like non-peaks)
-  auto convert = [&](int n) {
+// Full test of one strip of 4 (VEC) / one element that passed the threshold scan.  `plane` points at the (frame,
+// class) plane in global memory, off is the float offset inside it; neighbours come from L1/L2.
+template <int MODE, bool VEC>
+__device__ __noinline__ int examine(const TileArgs& a, TileCtx* ctx, unsigned long long* list,
+                                    const float* __restrict__ plane, uint32_t plane_flat0, int off) {
+  const int W = a.W, H = a.H;
+  const float thr_f = ctx->thr_f;
+  const int r = off / W;
+  const int col = off - r * W;
+  const float* p1 = plane + off;
+  const uint32_t flat = plane_flat0 + (uint32_t)off;
+  int fl = 0;
+  if (VEC) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(p1));
     if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
-      for (int i = (int)ctl[6] + tid; i < n; i += kTileThreads) {
-        const unsigned long long pre = list[i];
-        const float s = sigmoid_ref(key_to_float(composite_key(pre)));
-        list[i] = (s > 0.0f) ? (((unsigned long long)float_to_key(s) << 32) | (pre & 0xffffffffull)) : 0ull;
-      }
-      __syncthreads();
-    }
-  };
-  // after a select with threshold T over score composites: new push filter + publication
-  auto publish = [&](unsigned long long T, int n_kept) {  // thread 0 only
-    if (n_kept < a.k) return;
-    uint32_t key;
-    if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
-      key = reject_key_for_score(key_to_float(composite_key(T)));
-      if (key == 0u) return;
-      const unsigned long long t = (unsigned long long)key << 32;
-      if (t > s_thr) s_thr = t;
-    } else {
-      key = composite_key(T);
-      if (T > s_thr) s_thr = T;
-    }
-    atomicMax(a.frame_thr + frame, key);
-  };
-
-  for (int j = 0; j < nchunks; ++j) {
-    // ---- make chunk j (and j+1: the row below the last row of j) resident ----
-    if (BULK) {
-      mbar_wait(&bars[j % kStages], (uint32_t)((j / kStages) & 1));
-      if (j + 1 < nchunks) mbar_wait(&bars[(j + 1) % kStages], (uint32_t)(((j + 1) / kStages) & 1));
-    } else {
-      __syncthreads();
-      for (int jj = max(j - 1, 0); jj <= min(j + 1, nchunks - 1); ++jj) {
-        const int row = lo + jj * R;
-        const int n = min(R, hi - row) * W;
-        float* dst = ring + (size_t)(jj % kStages) * a.slot_elems;
-        const float* src = base + (size_t)row * W;
-        for (int i = tid; i < n; i += kTileThreads) dst[i] = __ldg(src + i);
-      }
-      __syncthreads();
-    }
-    // what other items of this frame have published meanwhile: the load is issued here and consumed at the end
-    // of the step (folded into s_thr for the next step), so its L2 latency hides behind the step's work
-    uint32_t pub_key = 0u;
-    if (tid == 0) pub_key = *reinterpret_cast<volatile uint32_t*>(a.frame_thr + frame);
-    thr = s_thr;
-    thr_f = key_to_float(composite_key(thr));
-    if (composite_key(thr) == 0u) thr_f = TAUV_NEG_INF;
-    my_end = 0;
-    const int ra = max(lo + j * R, r0);
-    const int rb = min(min(lo + (j + 1) * R, hi), r1);
-    const int* tab = rowtab + (j & 1) * (R + 4);  // tab[i] = ring offset of row ra-1+i
-
-    if (BULK) {
-      // ---- vector path: one float4 strip per task; only strips holding a value >= thr are examined further ----
-      const int S = W >> 2;
-      const int ntasks = (rb - ra) * S;
-      int ri = tid / S, cs = tid - ri * S;         // task = (row ra+ri, strip cs)
-      const int dr = kTileThreads / S, dc = kTileThreads - dr * S;
-#pragma unroll 1
-      for (int task = tid; task < ntasks; task += kTileThreads) {
-        const int o1 = tab[ri + 1];
-        const int col = cs << 2;
-        const float4 x = *reinterpret_cast<const float4*>(ring + o1 + col);
-        const float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
-        if (mx >= thr_f) {
-          const uint32_t flat = plane_flat0 + (uint32_t)((ra + ri) * W + col);
-          if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
-            // 3x3 neighbourhood of the strip: columns col-1 .. col+4 of rows r-1, r, r+1 (-inf outside the plane)
-            const int o0 = tab[ri], o2 = tab[ri + 2];
-            float cm[6];  // column-wise max over the three rows
-            {
-              const bool hl = col > 0, hr = col + 4 < W;
-              float4 u = make_float4(TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF), d = u;
-              float ul = TAUV_NEG_INF, ur = TAUV_NEG_INF, dl = TAUV_NEG_INF, dright = TAUV_NEG_INF;
-              if (o0 >= 0) {
-                u = *reinterpret_cast<const float4*>(ring + o0 + col);
-                if (hl) ul = ring[o0 + col - 1];
-                if (hr) ur = ring[o0 + col + 4];
-              }
-              if (o2 >= 0) {
-                d = *reinterpret_cast<const float4*>(ring + o2 + col);
-                if (hl) dl = ring[o2 + col - 1];
-                if (hr) dright = ring[o2 + col + 4];
-              }
-              const float ml = hl ? ring[o1 + col - 1] : TAUV_NEG_INF;
-              const float mr = hr ? ring[o1 + col + 4] : TAUV_NEG_INF;
-              cm[0] = fmaxf(fmaxf(ul, ml), dl);
-              cm[1] = fmaxf(fmaxf(u.x, x.x), d.x);
-              cm[2] = fmaxf(fmaxf(u.y, x.y), d.y);
-              cm[3] = fmaxf(fmaxf(u.z, x.z), d.z);
-              cm[4] = fmaxf(fmaxf(u.w, x.w), d.w);
-              cm[5] = fmaxf(fmaxf(ur, mr), dright);
-            }
-            const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              const float xv = xs[cc];
-              if (xv >= thr_f) {
-                const float m = fmaxf(fmaxf(cm[cc], cm[cc + 1]), cm[cc + 2]);
-                bool peak = (xv >= m);
-                if (!peak && (xv > 4.0f || m < -80.0f || (m - xv) < 1e-3f)) peak = sigmoid_tie(xv, m);
-                if (peak) push(xv, flat + cc);
-              }
-            }
-          } else {
-            if (x.x >= thr_f) push(x.x, flat);
-            if (x.y >= thr_f) push(x.y, flat + 1);
-            if (x.z >= thr_f) push(x.z, flat + 2);
-            if (x.w >= thr_f) push(x.w, flat + 3);
-          }
+      // columns col-1 .. col+4 of rows r-1, r, r+1 (-inf outside the plane)
+      float cm[6];  // column-wise max over the three rows
+      {
+        const bool hl = col > 0, hr = col + 4 < W;
+        float4 u = make_float4(TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF), d = u;
+        float ul = TAUV_NEG_INF, ur = TAUV_NEG_INF, dl = TAUV_NEG_INF, dright = TAUV_NEG_INF;
+        if (r > 0) {
+          u = __ldg(reinterpret_cast<const float4*>(p1 - W));
+          if (hl) ul = __ldg(p1 - W - 1);
+          if (hr) ur = __ldg(p1 - W + 4);
         }
-        ri += dr;
-        cs += dc;
-        if (cs >= S) { cs -= S; ++ri; }
+        if (r + 1 < H) {
+          d = __ldg(reinterpret_cast<const float4*>(p1 + W));
+          if (hl) dl = __ldg(p1 + W - 1);
+          if (hr) dright = __ldg(p1 + W + 4);
+        }
+        const float ml = hl ? __ldg(p1 - 1) : TAUV_NEG_INF;
+        const float mr = hr ? __ldg(p1 + 4) : TAUV_NEG_INF;
+        cm[0] = fmaxf(fmaxf(ul, ml), dl);
+        cm[1] = fmaxf(fmaxf(u.x, x.x), d.x);
+        cm[2] = fmaxf(fmaxf(u.y, x.y), d.y);
+        cm[3] = fmaxf(fmaxf(u.z, x.z), d.z);
+        cm[4] = fmaxf(fmaxf(u.w, x.w), d.w);
+        cm[5] = fmaxf(fmaxf(ur, mr), dright);
       }
-    } else {
-      // ---- scalar path (any W / unaligned base): one element per task ----
-      const int n = (rb - ra) * W;
-      for (int t = tid; t < n; t += kTileThreads) {
-        const int ri = t / W;
-        const int col = t - ri * W;
-        const int o1 = tab[ri + 1];
-        const float xv = ring[o1 + col];
-        if (!(xv >= thr_f)) continue;
-        const uint32_t flat = plane_flat0 + (uint32_t)((ra + ri) * W + col);
-        if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
-          float m = TAUV_NEG_INF;
-          for (int dy = 0; dy < 3; ++dy) {
-            const int o = tab[ri + dy];
-            if (o < 0) continue;
-            for (int dc2 = -1; dc2 <= 1; ++dc2) {
-              const int c2 = col + dc2;
-              if (c2 >= 0 && c2 < W) m = fmaxf(m, ring[o + c2]);
-            }
-          }
+      const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const float xv = xs[cc];
+        if (xv >= thr_f) {
+          const float m = fmaxf(fmaxf(cm[cc], cm[cc + 1]), cm[cc + 2]);
           bool peak = (xv >= m);
           if (!peak && (xv > 4.0f || m < -80.0f || (m - xv) < 1e-3f)) peak = sigmoid_tie(xv, m);
-          if (peak) push(xv, flat);
-        } else {
-          push(xv, flat);
+          if (peak) fl |= push_entry(a, ctx, list, xv, flat + cc);
         }
       }
+    } else {
+      if (x.x >= thr_f) fl |= push_entry(a, ctx, list, x.x, flat);
+      if (x.y >= thr_f) fl |= push_entry(a, ctx, list, x.y, flat + 1);
+      if (x.z >= thr_f) fl |= push_entry(a, ctx, list, x.z, flat + 2);
+      if (x.w >= thr_f) fl |= push_entry(a, ctx, list, x.w, flat + 3);
     }
-
-    // ---- end of step: everyone is done with chunk j-1; prune if the list is getting full ----
-    if (j + 1 < nchunks) fill_rowtab(j + 1);
-    if (tid == 0) {
-      const unsigned long long pub = (unsigned long long)pub_key << 32;
-      if (pub > s_thr) s_thr = pub;
-    }
-    const int over = __syncthreads_or(my_end > a.soft);
-    if (BULK && tid == 0 && j >= 1 && j - 1 + kStages < nchunks) issue_chunk(j - 1 + kStages);
-    if (over) {
-      const int n = *count_p;
-      convert(n);
-      const unsigned long long T =
-          block_kth_largest<kTileThreads>([&](int i) { return list[i]; }, n, a.k, hist, ctl);
-      // stable in-place compaction, kTileThreads entries per round (write index <= read index)
-      if (tid == 0) s_base = 0;
-      __syncthreads();
-      for (int start = 0; start < n; start += kTileThreads) {
-        const int i = start + tid;
-        unsigned long long c = 0ull;
-        bool keep = false;
-        if (i < n) {
-          c = list[i];
-          keep = (c >= T) && (c != 0ull);
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        const int lane = tid & 31, warp = tid >> 5;
-        if (lane == 0) s_wsum[warp] = __popc(bal);
-        __syncthreads();
-        int pos = s_base + __popc(bal & ((1u << lane) - 1u));
-        for (int w = 0; w < warp; ++w) pos += s_wsum[w];
-        if (keep) list[pos] = c;
-        __syncthreads();
-        if (tid == 0) {
-          int tot = 0;
-          for (int w = 0; w < kTileThreads / 32; ++w) tot += s_wsum[w];
-          s_base += tot;
-        }
-        __syncthreads();
+  } else {
+    const float xv = __ldg(p1);
+    if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
+      float m = TAUV_NEG_INF;
+      for (int dy = -1; dy <= 1; ++dy) {
+        if (r + dy < 0 || r + dy >= H) continue;
+        for (int dx = -1; dx <= 1; ++dx)
+          if (col + dx >= 0 && col + dx < W) m = fmaxf(m, __ldg(p1 + dy * W + dx));
       }
-      if (tid == 0) {
-        *count_p = s_base;
-        ctl[6] = (uint32_t)s_base;  // everything kept is converted
-        publish(T, s_base);
-      }
-      __syncthreads();
+      bool peak = (xv >= m);
+      if (!peak && (xv > 4.0f || m < -80.0f || (m - xv) < 1e-3f)) peak = sigmoid_tie(xv, m);
+      if (peak) fl |= push_entry(a, ctx, list, xv, flat);
+    } else {
+      fl |= push_entry(a, ctx, list, xv, flat);
     }
   }
+  return fl;
+}
 
-  // ---- emit the item's top-k ----
+// Threshold scan of the elements [e0, e1) of a plane (both multiples of 4 on the VEC path): every thread streams
+// four 128-bit loads at a time straight from HBM (read-once data: no L1 allocation) and compares the strip maximum
+// with the threshold; only what passes is examined.  With a published frame threshold that is ~1 % of the strips.
+template <int MODE, bool VEC>
+__device__ __forceinline__ int scan_elems(const TileArgs& a, TileCtx* ctx, unsigned long long* list,
+                                          const float* __restrict__ plane, uint32_t plane_flat0, int e0, int e1) {
+  const float thr_f = ctx->thr_f;
+  const int tid = threadIdx.x;
+  int fl = 0;
+  if (VEC) {
+    const int t1 = e1 >> 2;
+#pragma unroll 1
+    for (int t0 = (e0 >> 2) + tid; t0 < t1; t0 += 4 * kTileThreads) {
+      float4 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u * kTileThreads;
+        x[u] = (t < t1) ? ldg_stream4(plane + ((size_t)t << 2))
+                        : make_float4(TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF);
+      }
+      uint32_t hot = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w)) >= thr_f && t0 + u * kTileThreads < t1) hot |= 1u << u;
+#pragma unroll 1
+      while (hot) {
+        const int u = __ffs(hot) - 1;
+        hot &= hot - 1;
+        fl |= examine<MODE, VEC>(a, ctx, list, plane, plane_flat0, (t0 + u * kTileThreads) << 2);
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int t = e0 + tid; t < e1; t += kTileThreads)
+      if (__ldg(plane + t) >= thr_f) fl |= examine<MODE, VEC>(a, ctx, list, plane, plane_flat0, t);
+  }
+  return fl;
+}
+
+__device__ __forceinline__ void set_thr(TileCtx* ctx, unsigned long long t) {  // one thread
+  if (t > ctx->thr) {
+    ctx->thr = t;
+    ctx->thr_f = composite_key(t) ? key_to_float(composite_key(t)) : TAUV_NEG_INF;
+  }
+}
+
+// logit pre-composites [n_conv, n) -> final sort keys (0 for a sigmoid that underflowed to 0: zero-valued cells are
+// supplied by the merge kernel's filler, like non-peaks)
+template <int MODE>
+__device__ void convert_entries(TileCtx* ctx, unsigned long long* list, int n) {
+  if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
+    for (int i = ctx->n_conv + (int)threadIdx.x; i < n; i += kTileThreads) {
+      const unsigned long long pre = list[i];
+      const float s = sigmoid_ref(key_to_float(composite_key(pre)));
+      list[i] = (s > 0.0f) ? (((unsigned long long)float_to_key(s) << 32) | (pre & 0xffffffffull)) : 0ull;
+    }
+    __syncthreads();
+  }
+}
+
+// stable in-place compaction of list[0,n) by a predicate; the new length lands in ctx->base
+template <class Keep>
+__device__ void compact_list(TileCtx* ctx, unsigned long long* list, int n, Keep keep_fn) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) ctx->base = 0;
   __syncthreads();
-  const int n = *count_p;
-  convert(n);
-  const unsigned long long T =
-      block_kth_largest<kTileThreads>([&](int i) { return list[i]; }, n, a.k, hist, ctl);
-  if (tid == 0) ctl[5] = 0;
+  for (int start = 0; start < n; start += kTileThreads) {
+    const int i = start + tid;
+    unsigned long long c = 0ull;
+    bool keep = false;
+    if (i < n) {
+      c = list[i];
+      keep = keep_fn(c);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) ctx->wsum[warp] = __popc(bal);
+    __syncthreads();
+    int pos = ctx->base + __popc(bal & ((1u << lane) - 1u));
+    for (int w = 0; w < warp; ++w) pos += ctx->wsum[w];
+    if (keep) list[pos] = c;  // write index <= read index, and every read of this round is already done
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < kTileThreads / 32; ++w) tot += ctx->wsum[w];
+      ctx->base += tot;
+    }
+    __syncthreads();
+  }
+}
+
+// exact prune of the list to its top-k, then tighten the item's own push filter from the k-th key
+template <int MODE>
+__device__ __noinline__ void prune_list(const TileArgs& a, TileCtx* ctx, unsigned long long* list, uint32_t* hist) {
+  const int n = ctx->count;
+  convert_entries<MODE>(ctx, list, n);
+  const unsigned long long T = block_kth_largest<kTileThreads>([&](int i) { return list[i]; }, n, a.k, hist, ctx->sel);
+  compact_list(ctx, list, n, [&](unsigned long long c) { return c >= T && c != 0ull; });
+  if (threadIdx.x == 0) {
+    ctx->count = ctx->base;
+    ctx->n_conv = ctx->base;
+    if (ctx->base >= a.k) {
+      if (MODE == TAUV_TOPK_SIGMOID_PEAK)
+        set_thr(ctx, (unsigned long long)reject_key_for_score(key_to_float(composite_key(T))) << 32);
+      else
+        set_thr(ctx, T);
+    }
+  }
+  __syncthreads();
+}
+
+// The list overflowed during the one-shot scan: start the item over in sub-steps that cannot overflow, pruning to
+// the exact top-k (which also raises the item's own threshold) whenever the list passes `soft`.
+template <int MODE, bool VEC>
+__device__ __noinline__ void rescan_item_safely(const TileArgs& a, TileCtx* ctx, unsigned long long* list,
+                                                uint32_t* hist, const float* __restrict__ plane,
+                                                uint32_t plane_flat0, int e0, int e1) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ctx->count = 0;
+    ctx->n_conv = 0;
+  }
+  __syncthreads();
+  for (int s0 = e0; s0 < e1; s0 += a.sub_elems) {
+    scan_elems<MODE, VEC>(a, ctx, list, plane, plane_flat0, s0, min(s0 + a.sub_elems, e1));
+    __syncthreads();
+    if (ctx->count > a.soft) prune_list<MODE>(a, ctx, list, hist);  // uniform: nobody pushes before the next barrier
+    __syncthreads();
+  }
+}
+
+// end of an item: emit its top-k into the candidate table, add them to the frame's histogram, and republish the
+// frame's rejection threshold (the lower edge of the highest bin b with at least k candidates of the whole frame in
+// bins >= b; counts only grow, so a published threshold stays valid)
+template <int MODE>
+__device__ __noinline__ void finish_item(const TileArgs& a, TileCtx* ctx, unsigned long long* list, uint32_t* hist,
+                                         int item, uint32_t* fstate) {
+  const int tid = threadIdx.x;
+  const int n = ctx->count;
+  convert_entries<MODE>(ctx, list, n);
+  const unsigned long long T = block_kth_largest<kTileThreads>([&](int i) { return list[i]; }, n, a.k, hist, ctx->sel);
+  if (tid == 0) {
+    ctx->emit = 0;
+    ctx->maxbin = 0;
+  }
   __syncthreads();
   unsigned long long* out = a.cand + (size_t)item * a.k;
+  uint32_t my_maxbin = 0;
   for (int i = tid; i < n; i += kTileThreads) {
     const unsigned long long c = list[i];
-    if (c >= T && c != 0ull) out[atomicAdd(&ctl[5], 1u)] = c;
+    if (c >= T && c != 0ull) {
+      out[atomicAdd(&ctx->emit, 1u)] = c;
+      const uint32_t bin = frame_bin<MODE>(c);
+      atomicAdd(fstate + 4 + bin, 1u);
+      my_maxbin = max(my_maxbin, bin);
+    }
+  }
+  if (my_maxbin) atomicMax(&ctx->maxbin, my_maxbin);
+  __syncthreads();
+  const int n_emit = (int)ctx->emit;
+  if (tid == 0) a.cand_count[item] = n_emit;
+  if (tid < 32 && n_emit > 0) {
+    const int lane = tid;
+    uint32_t before = 0, maxbin = 0;
+    if (lane == 0) {
+      maxbin = max(atomicMax(fstate + 1, ctx->maxbin), ctx->maxbin);
+      before = atomicAdd(fstate + 2, (uint32_t)n_emit);
+    }
+    before = __shfl_sync(0xffffffffu, before, 0);
+    maxbin = __shfl_sync(0xffffffffu, maxbin, 0);
+    // The bins are rescanned only when the frame's candidate count crosses k, 2k, 4k, ...: each doubling tightens
+    // the threshold noticeably, more often does not pay for the scan's round trips to L2.
+    const uint32_t k = (uint32_t)a.k, after = before + (uint32_t)n_emit;
+    const bool rescan = after >= k && (before < k || (31 - __clz(after / k)) != (31 - __clz(before / k)));
+    if (rescan) {
+      __threadfence();
+      uint32_t acc = 0;
+      int found = -1;
+      for (int it = 0; it < 8 && found < 0; ++it) {  // at most 256 bins below the top occupied one
+        const int bin = (int)maxbin - it * 32 - lane;
+        uint32_t v = bin >= 0 ? *reinterpret_cast<volatile uint32_t*>(fstate + 4 + bin) : 0u;
+        uint32_t pre = v;  // inclusive prefix over lanes (lane 0 = highest bin)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o);
+          if (lane >= o) pre += t;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, acc + pre >= k);
+        if (hit) found = (int)maxbin - it * 32 - (__ffs(hit) - 1);
+        acc += __shfl_sync(0xffffffffu, pre, 31);
+        if ((int)maxbin - (it + 1) * 32 < 0) break;
+      }
+      if (lane == 0 && found > 0) {
+        const float edge = key_to_float((uint32_t)found << 20);  // lowest value of the bin
+        uint32_t key;
+        if (MODE == TAUV_TOPK_SIGMOID_PEAK) key = reject_key_for_score(sigmoid_ref(edge));
+        else key = (uint32_t)found << 20;
+        if (key) atomicMax(fstate, key);
+      }
+    }
+  }
+}
+
+// One CTA per item.  Block index -> item interleaves the frames (consecutive blocks are different frames), so the
+// first items of EVERY frame finish early and publish a threshold for the frame's other items.
+template <int MODE, bool VEC>
+__global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(const __grid_constant__ TileArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* list = reinterpret_cast<unsigned long long*>(smem_raw);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)a.cap * 8);
+  __shared__ TileCtx s_ctx;
+  TileCtx* ctx = &s_ctx;
+  const int tid = threadIdx.x;
+
+  const int items_per_frame = a.C * a.items_per_plane;
+  const int item_in_frame = blockIdx.x / a.B;
+  const int frame = blockIdx.x - item_in_frame * a.B;
+  const int item = frame * items_per_frame + item_in_frame;
+  const int c_in_frame = item_in_frame / a.items_per_plane;
+  const int ip = item_in_frame - c_in_frame * a.items_per_plane;
+  const int r0 = ip * a.rows_per_item;
+  const int r1 = min(a.H, r0 + a.rows_per_item);
+  const float* plane = a.hm + ((size_t)frame * a.C + c_in_frame) * a.H * a.W;
+  const uint32_t plane_flat0 = (uint32_t)c_in_frame * (uint32_t)(a.H * a.W);
+  uint32_t* fstate = a.frame_state + (size_t)frame * kFrameStateWords;
+
+  if (tid == 0) {
+    const uint32_t key = *reinterpret_cast<volatile uint32_t*>(fstate);  // what the frame's finished items published
+    ctx->count = 0;
+    ctx->n_conv = 0;
+    ctx->flags = 0;
+    ctx->thr = (unsigned long long)key << 32;
+    ctx->thr_f = key ? key_to_float(key) : TAUV_NEG_INF;
   }
   __syncthreads();
-  if (tid == 0) {
-    a.cand_count[item] = (int)ctl[5];
-    publish(T, (int)ctl[5]);
+
+  const int e0 = r0 * a.W, e1 = r1 * a.W;
+  const int fl = scan_elems<MODE, VEC>(a, ctx, list, plane, plane_flat0, e0, e1);
+  if (fl) atomicOr(&ctx->flags, fl);
+  __syncthreads();
+  if (ctx->flags & 2) rescan_item_safely<MODE, VEC>(a, ctx, list, hist, plane, plane_flat0, e0, e1);
+
+  if (ctx->count == 0) {
+    if (tid == 0) a.cand_count[item] = 0;
+    return;
   }
+  finish_item<MODE>(a, ctx, list, hist, item, fstate);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -672,15 +718,15 @@ static int plan_and_check(const float* hm, int B, int C, int H, int W, int k, vo
                           TileArgs* a) {
   make_plan(B, C, H, W, k, hm, p);
   TAUV_REQUIRE(ws != nullptr && (uintptr_t)ws % 256 == 0, TAUV_E_WORKSPACE, "workspace must be 256-byte aligned");
-  TAUV_REQUIRE(ws_bytes >= p->cand_bytes + p->count_bytes + p->thr_bytes, TAUV_E_WORKSPACE,
-               "workspace %zu < required %zu", ws_bytes, p->cand_bytes + p->count_bytes + p->thr_bytes);
+  TAUV_REQUIRE(ws_bytes >= p->cand_bytes + p->count_bytes + p->state_bytes, TAUV_E_WORKSPACE,
+               "workspace %zu < required %zu", ws_bytes, p->cand_bytes + p->count_bytes + p->state_bytes);
   TAUV_REQUIRE(p->smem_bytes <= 227 * 1024, TAUV_E_UNSUPPORTED, "tile needs %zu B shared memory", p->smem_bytes);
   a->hm = hm; a->B = B; a->C = C; a->H = H; a->W = W; a->k = k;
-  a->R = p->rows_per_chunk; a->slot_elems = p->slot_elems; a->rows_per_item = p->rows_per_item;
-  a->items_per_plane = p->items_per_plane; a->cap = p->cap; a->soft = p->soft;
+  a->rows_per_item = p->rows_per_item; a->items_per_plane = p->items_per_plane;
+  a->cap = p->cap; a->soft = p->soft; a->sub_elems = p->sub_elems;
   a->cand = reinterpret_cast<unsigned long long*>(ws);
   a->cand_count = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws) + p->cand_bytes);
-  a->frame_thr = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(ws) + p->cand_bytes + p->count_bytes);
+  a->frame_state = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(ws) + p->cand_bytes + p->count_bytes);
   const long long items = (long long)B * p->items_per_frame;
   TAUV_REQUIRE(items < (1LL << 31), TAUV_E_UNSUPPORTED, "too many items (%lld)", items);
   return 0;
@@ -693,11 +739,15 @@ static int run_stage1(const float* hm, int B, int C, int H, int W, int k, int mo
   TileArgs a;
   if (int e = plan_and_check(hm, B, C, H, W, k, ws, ws_bytes, &p, &a)) return e;
   const long long items = (long long)B * p.items_per_frame;
-  void (*kern)(TileArgs) = nullptr;
-  if (mode == TAUV_TOPK_SIGMOID_PEAK) kern = p.bulk ? tile_topk_kernel<1, true> : tile_topk_kernel<1, false>;
-  else kern = p.bulk ? tile_topk_kernel<0, true> : tile_topk_kernel<0, false>;
+  void (*kern)(const TileArgs) = nullptr;
+  if (mode == TAUV_TOPK_SIGMOID_PEAK) kern = p.vec ? tile_topk_kernel<1, true> : tile_topk_kernel<1, false>;
+  else kern = p.vec ? tile_topk_kernel<0, true> : tile_topk_kernel<0, false>;
   TAUV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-  TAUV_CUDA(cudaMemsetAsync(a.frame_thr, 0, p.thr_bytes, st));  // key 0 = "no threshold published yet"
+  {
+    const char* dbg = getenv("TAUV_TILE_DEBUG");  // experiment hook: "keep" = reuse the previous call's thresholds
+    if (!(dbg && dbg[0] == 'k'))
+      TAUV_CUDA(cudaMemsetAsync(a.frame_state, 0, p.state_bytes, st));  // key 0 = "no threshold published yet"
+  }
   kern<<<(unsigned)items, kTileThreads, p.smem_bytes, st>>>(a);
   TAUV_LAUNCH_CHECK("tile_topk_kernel");
   return 0;
@@ -762,7 +812,7 @@ extern "C" size_t tauv_heatmap_topk_workspace_bytes(int B, int C, int H, int W, 
   TopkPlan p;
   // alignment only affects the load path, never the sizes
   make_plan(B, C, H, W, k, nullptr, &p);
-  return p.cand_bytes + p.count_bytes + p.thr_bytes;
+  return p.cand_bytes + p.count_bytes + p.state_bytes;
 }
 
 extern "C" int tauv_heatmap_topk(const float* heatmap, int B, int C, int H, int W, int k, int mode, int64_t* index,
