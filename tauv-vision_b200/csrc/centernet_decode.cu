@@ -37,6 +37,7 @@ struct TopkPlan {
   int soft;             // overflow-safe path: prune when the list grows beyond this
   int sub_elems;        // overflow-safe path: elements per sub-step (cap - soft)
   int vec;              // 1: 128-bit loads, 0: scalar loads (W % 4 != 0 or unaligned base)
+  int tile_floats;      // shared-memory staging tile of the bootstrap round (0: none)
   size_t smem_bytes;
   size_t cand_bytes, count_bytes, state_bytes;
 };
@@ -59,7 +60,10 @@ static int make_plan(int B, int C, int H, int W, int k, const void* ptr, TopkPla
   p->soft = 2 * k;
   p->cap = 4 * k > 2560 ? 4 * k : 2560;
   p->sub_elems = ((p->cap - p->soft) / 4) * 4;
-  p->smem_bytes = (size_t)p->cap * 8 + kRadixBins * 4;
+  // bootstrap tile: one round of rows plus halo, staged in shared memory (only for W <= 512; wider maps use the
+  // global-memory path for the bootstrap round too)
+  p->tile_floats = (p->vec && W <= 512) ? 16 * kTileThreads + 3 * W : 0;
+  p->smem_bytes = (size_t)p->cap * 8 + kRadixBins * 4 + (size_t)p->tile_floats * 4;
   p->cand_bytes = align_up((size_t)B * p->items_per_frame * (size_t)k * 8, 256);
   p->count_bytes = align_up((size_t)B * p->items_per_frame * 4, 256);
   p->state_bytes = align_up((size_t)B * kFrameStateWords * 4, 256);
@@ -73,10 +77,11 @@ struct TileArgs {
   const float* hm;
   int B, C, H, W, k;
   int rows_per_item, items_per_plane;
-  int cap, soft, sub_elems;
+  int cap, soft, sub_elems, tile_floats;
   unsigned long long* cand;  // [B*items_per_frame][k]
   int* cand_count;           // [B*items_per_frame]
   uint32_t* frame_state;     // [B][kFrameStateWords], zeroed before the launch
+  long long* trace;          // debug: per item {t_start, t_boot, t_scan, t_end, n_list, thr_key_at_start, 0, 0} or NULL
 };
 
 // x < m can still tie after the sigmoid (saturation, or a sub-ulp gap): the reference compares sigmoid values
@@ -114,10 +119,12 @@ struct __align__(16) TileCtx {
   float thr_f;             // its value as a float (-inf: none)
   int count;               // list entries
   int n_conv;              // list[0, n_conv) already hold final sort keys (SIGMOID_PEAK)
+  int n_boot;              // list[0, n_boot) are already counted in the frame histogram (-1: order lost, count nothing more)
   uint32_t emit, maxbin;
   int flags;               // bit 1 = the list overflowed
   int base, wsum[kTileThreads / 32];
   uint32_t sel[4];
+  __align__(16) uint32_t fs[4];  // cp.async snapshot of frame_state[0..3]; possibly stale, never waited on mid-scan
 };
 
 // A list entry is a 64-bit "pre-composite": order-preserving key of the VALUE in the high word, ~flat index in the
@@ -136,18 +143,26 @@ __device__ __forceinline__ int push_entry(const TileArgs& a, TileCtx* ctx, unsig
 
 // Full test of one strip of 4 (VEC) / one element that passed the threshold scan.  `plane` points at the (frame,
 // class) plane in global memory, off is the float offset inside it; neighbours come from L1/L2.
-template <int MODE, bool VEC>
+template <bool SMEM>
+__device__ __forceinline__ float ld1(const float* p) { return SMEM ? *p : __ldg(p); }
+template <bool SMEM>
+__device__ __forceinline__ float4 ld4(const float* p) {
+  return SMEM ? *reinterpret_cast<const float4*>(p) : __ldg(reinterpret_cast<const float4*>(p));
+}
+
+// (SMEM: `plane` is a shared-memory copy that starts at plane offset `origin`; off stays a plane offset.)
+template <int MODE, bool VEC, bool SMEM = false>
 __device__ __noinline__ int examine(const TileArgs& a, TileCtx* ctx, unsigned long long* list,
-                                    const float* __restrict__ plane, uint32_t plane_flat0, int off) {
+                                    const float* __restrict__ plane, uint32_t plane_flat0, int off, int origin = 0) {
   const int W = a.W, H = a.H;
   const float thr_f = ctx->thr_f;
   const int r = off / W;
   const int col = off - r * W;
-  const float* p1 = plane + off;
+  const float* p1 = plane + (off - origin);
   const uint32_t flat = plane_flat0 + (uint32_t)off;
   int fl = 0;
   if (VEC) {
-    const float4 x = __ldg(reinterpret_cast<const float4*>(p1));
+    const float4 x = ld4<SMEM>(p1);
     if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
       // columns col-1 .. col+4 of rows r-1, r, r+1 (-inf outside the plane)
       float cm[6];  // column-wise max over the three rows
@@ -156,17 +171,17 @@ __device__ __noinline__ int examine(const TileArgs& a, TileCtx* ctx, unsigned lo
         float4 u = make_float4(TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF), d = u;
         float ul = TAUV_NEG_INF, ur = TAUV_NEG_INF, dl = TAUV_NEG_INF, dright = TAUV_NEG_INF;
         if (r > 0) {
-          u = __ldg(reinterpret_cast<const float4*>(p1 - W));
-          if (hl) ul = __ldg(p1 - W - 1);
-          if (hr) ur = __ldg(p1 - W + 4);
+          u = ld4<SMEM>(p1 - W);
+          if (hl) ul = ld1<SMEM>(p1 - W - 1);
+          if (hr) ur = ld1<SMEM>(p1 - W + 4);
         }
         if (r + 1 < H) {
-          d = __ldg(reinterpret_cast<const float4*>(p1 + W));
-          if (hl) dl = __ldg(p1 + W - 1);
-          if (hr) dright = __ldg(p1 + W + 4);
+          d = ld4<SMEM>(p1 + W);
+          if (hl) dl = ld1<SMEM>(p1 + W - 1);
+          if (hr) dright = ld1<SMEM>(p1 + W + 4);
         }
-        const float ml = hl ? __ldg(p1 - 1) : TAUV_NEG_INF;
-        const float mr = hr ? __ldg(p1 + 4) : TAUV_NEG_INF;
+        const float ml = hl ? ld1<SMEM>(p1 - 1) : TAUV_NEG_INF;
+        const float mr = hr ? ld1<SMEM>(p1 + 4) : TAUV_NEG_INF;
         cm[0] = fmaxf(fmaxf(ul, ml), dl);
         cm[1] = fmaxf(fmaxf(u.x, x.x), d.x);
         cm[2] = fmaxf(fmaxf(u.y, x.y), d.y);
@@ -192,13 +207,13 @@ __device__ __noinline__ int examine(const TileArgs& a, TileCtx* ctx, unsigned lo
       if (x.w >= thr_f) fl |= push_entry(a, ctx, list, x.w, flat + 3);
     }
   } else {
-    const float xv = __ldg(p1);
+    const float xv = ld1<SMEM>(p1);
     if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
       float m = TAUV_NEG_INF;
       for (int dy = -1; dy <= 1; ++dy) {
         if (r + dy < 0 || r + dy >= H) continue;
         for (int dx = -1; dx <= 1; ++dx)
-          if (col + dx >= 0 && col + dx < W) m = fmaxf(m, __ldg(p1 + dy * W + dx));
+          if (col + dx >= 0 && col + dx < W) m = fmaxf(m, ld1<SMEM>(p1 + dy * W + dx));
       }
       bool peak = (xv >= m);
       if (!peak && (xv > 4.0f || m < -80.0f || (m - xv) < 1e-3f)) peak = sigmoid_tie(xv, m);
@@ -210,19 +225,37 @@ __device__ __noinline__ int examine(const TileArgs& a, TileCtx* ctx, unsigned lo
   return fl;
 }
 
+__device__ __forceinline__ void set_thr(TileCtx* ctx, unsigned long long t) {  // one thread
+  if (t > ctx->thr) {
+    ctx->thr = t;
+    ctx->thr_f = composite_key(t) ? key_to_float(composite_key(t)) : TAUV_NEG_INF;
+  }
+}
+
 // Threshold scan of the elements [e0, e1) of a plane (both multiples of 4 on the VEC path): every thread streams
 // four 128-bit loads at a time straight from HBM (read-once data: no L1 allocation) and compares the strip maximum
 // with the threshold; only what passes is examined.  With a published frame threshold that is ~1 % of the strips.
 template <int MODE, bool VEC>
 __device__ __forceinline__ int scan_elems(const TileArgs& a, TileCtx* ctx, unsigned long long* list,
-                                          const float* __restrict__ plane, uint32_t plane_flat0, int e0, int e1) {
-  const float thr_f = ctx->thr_f;
+                                          const float* __restrict__ plane, uint32_t plane_flat0, int e0, int e1,
+                                          const uint32_t* fstate = nullptr) {
+  float thr_f = ctx->thr_f;
   const int tid = threadIdx.x;
   int fl = 0;
   if (VEC) {
     const int t1 = e1 >> 2;
 #pragma unroll 1
     for (int t0 = (e0 >> 2) + tid; t0 < t1; t0 += 4 * kTileThreads) {
+      if (fstate) {
+        // Pick up what the frame's other items have published since this item started: thread 0 folds in the last
+        // snapshot and requests a fresh one (asynchronously; not in the last round, so nothing is pending at exit).
+        if (tid == 0) {
+          set_thr(ctx, (unsigned long long)ctx->fs[0] << 32);
+          if (t0 + 4 * kTileThreads < t1)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(ctx->fs)), "l"(fstate) : "memory");
+        }
+        thr_f = *reinterpret_cast<volatile float*>(&ctx->thr_f);
+      }
       float4 x[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -247,13 +280,6 @@ __device__ __forceinline__ int scan_elems(const TileArgs& a, TileCtx* ctx, unsig
       if (__ldg(plane + t) >= thr_f) fl |= examine<MODE, VEC>(a, ctx, list, plane, plane_flat0, t);
   }
   return fl;
-}
-
-__device__ __forceinline__ void set_thr(TileCtx* ctx, unsigned long long t) {  // one thread
-  if (t > ctx->thr) {
-    ctx->thr = t;
-    ctx->thr_f = composite_key(t) ? key_to_float(composite_key(t)) : TAUV_NEG_INF;
-  }
 }
 
 // logit pre-composites [n_conv, n) -> final sort keys (0 for a sigmoid that underflowed to 0: zero-valued cells are
@@ -310,6 +336,7 @@ __device__ __noinline__ void prune_list(const TileArgs& a, TileCtx* ctx, unsigne
   if (threadIdx.x == 0) {
     ctx->count = ctx->base;
     ctx->n_conv = ctx->base;
+    if (ctx->n_boot > 0) ctx->n_boot = -1;  // compaction moved entries: stop adding this item to the frame's bins
     if (ctx->base >= a.k) {
       if (MODE == TAUV_TOPK_SIGMOID_PEAK)
         set_thr(ctx, (unsigned long long)reject_key_for_score(key_to_float(composite_key(T))) << 32);
@@ -330,6 +357,7 @@ __device__ __noinline__ void rescan_item_safely(const TileArgs& a, TileCtx* ctx,
   if (threadIdx.x == 0) {
     ctx->count = 0;
     ctx->n_conv = 0;
+    if (ctx->n_boot > 0) ctx->n_boot = -1;
   }
   __syncthreads();
   for (int s0 = e0; s0 < e1; s0 += a.sub_elems) {
@@ -338,6 +366,53 @@ __device__ __noinline__ void rescan_item_safely(const TileArgs& a, TileCtx* ctx,
     if (ctx->count > a.soft) prune_list<MODE>(a, ctx, list, hist);  // uniform: nobody pushes before the next barrier
     __syncthreads();
   }
+}
+
+// Warp 0: account `n_added` new candidates of this CTA (already added to the bins; ctx->maxbin = their highest bin)
+// and, when worthwhile, rescan the frame's bins and publish the rejection key.  Returns the key the frame has
+// published after this call (0: none yet), broadcast to the warp.
+template <int MODE>
+__device__ __forceinline__ uint32_t frame_republish(const TileArgs& a, TileCtx* ctx, uint32_t* fstate,
+                                                    uint32_t n_added, bool force) {
+  const int lane = threadIdx.x & 31;
+  uint32_t before = 0, maxbin = 0;
+  if (lane == 0) {
+    maxbin = max(atomicMax(fstate + 1, ctx->maxbin), ctx->maxbin);
+    before = atomicAdd(fstate + 2, n_added);
+  }
+  before = __shfl_sync(0xffffffffu, before, 0);
+  maxbin = __shfl_sync(0xffffffffu, maxbin, 0);
+  // The bins are rescanned only when the frame's candidate count crosses k, 2k, 4k, ...: each doubling tightens
+  // the threshold noticeably, more often does not pay for the scan's round trips to L2.
+  const uint32_t k = (uint32_t)a.k, after = before + n_added;
+  const bool rescan = after >= k && (force || before < k || (31 - __clz(after / k)) != (31 - __clz(before / k)));
+  uint32_t key = 0;
+  if (rescan) {
+    __threadfence();
+    uint32_t acc = 0;
+    int found = -1;
+    for (int it = 0; it < 8 && found < 0; ++it) {  // at most 256 bins below the top occupied one
+      const int bin = (int)maxbin - it * 32 - lane;
+      uint32_t v = bin >= 0 ? *reinterpret_cast<volatile uint32_t*>(fstate + 4 + bin) : 0u;
+      uint32_t pre = v;  // inclusive prefix over lanes (lane 0 = highest bin)
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += t;
+      }
+      const unsigned hit = __ballot_sync(0xffffffffu, acc + pre >= k);
+      if (hit) found = (int)maxbin - it * 32 - (__ffs(hit) - 1);
+      acc += __shfl_sync(0xffffffffu, pre, 31);
+      if ((int)maxbin - (it + 1) * 32 < 0) break;
+    }
+    if (lane == 0 && found > 0) {
+      const float edge = key_to_float((uint32_t)found << 20);  // lowest value of the bin
+      if (MODE == TAUV_TOPK_SIGMOID_PEAK) key = reject_key_for_score(sigmoid_ref(edge));
+      else key = (uint32_t)found << 20;
+      if (key) key = max(atomicMax(fstate, key), key);
+    }
+  }
+  return __shfl_sync(0xffffffffu, key, 0);
 }
 
 // end of an item: emit its top-k into the candidate table, add them to the frame's histogram, and republish the
@@ -353,63 +428,29 @@ __device__ __noinline__ void finish_item(const TileArgs& a, TileCtx* ctx, unsign
   if (tid == 0) {
     ctx->emit = 0;
     ctx->maxbin = 0;
+    ctx->base = 0;  // candidates newly added to the frame's bins
   }
   __syncthreads();
   unsigned long long* out = a.cand + (size_t)item * a.k;
   uint32_t my_maxbin = 0;
+  const int n_boot = ctx->n_boot;  // list[0, n_boot) went into the frame's bins during the bootstrap round already
   for (int i = tid; i < n; i += kTileThreads) {
     const unsigned long long c = list[i];
     if (c >= T && c != 0ull) {
       out[atomicAdd(&ctx->emit, 1u)] = c;
-      const uint32_t bin = frame_bin<MODE>(c);
-      atomicAdd(fstate + 4 + bin, 1u);
-      my_maxbin = max(my_maxbin, bin);
+      if (n_boot >= 0 && i >= n_boot) {
+        const uint32_t bin = frame_bin<MODE>(c);
+        atomicAdd(fstate + 4 + bin, 1u);
+        atomicAdd(&ctx->base, 1);
+        my_maxbin = max(my_maxbin, bin);
+      }
     }
   }
   if (my_maxbin) atomicMax(&ctx->maxbin, my_maxbin);
   __syncthreads();
   const int n_emit = (int)ctx->emit;
   if (tid == 0) a.cand_count[item] = n_emit;
-  if (tid < 32 && n_emit > 0) {
-    const int lane = tid;
-    uint32_t before = 0, maxbin = 0;
-    if (lane == 0) {
-      maxbin = max(atomicMax(fstate + 1, ctx->maxbin), ctx->maxbin);
-      before = atomicAdd(fstate + 2, (uint32_t)n_emit);
-    }
-    before = __shfl_sync(0xffffffffu, before, 0);
-    maxbin = __shfl_sync(0xffffffffu, maxbin, 0);
-    // The bins are rescanned only when the frame's candidate count crosses k, 2k, 4k, ...: each doubling tightens
-    // the threshold noticeably, more often does not pay for the scan's round trips to L2.
-    const uint32_t k = (uint32_t)a.k, after = before + (uint32_t)n_emit;
-    const bool rescan = after >= k && (before < k || (31 - __clz(after / k)) != (31 - __clz(before / k)));
-    if (rescan) {
-      __threadfence();
-      uint32_t acc = 0;
-      int found = -1;
-      for (int it = 0; it < 8 && found < 0; ++it) {  // at most 256 bins below the top occupied one
-        const int bin = (int)maxbin - it * 32 - lane;
-        uint32_t v = bin >= 0 ? *reinterpret_cast<volatile uint32_t*>(fstate + 4 + bin) : 0u;
-        uint32_t pre = v;  // inclusive prefix over lanes (lane 0 = highest bin)
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o);
-          if (lane >= o) pre += t;
-        }
-        const unsigned hit = __ballot_sync(0xffffffffu, acc + pre >= k);
-        if (hit) found = (int)maxbin - it * 32 - (__ffs(hit) - 1);
-        acc += __shfl_sync(0xffffffffu, pre, 31);
-        if ((int)maxbin - (it + 1) * 32 < 0) break;
-      }
-      if (lane == 0 && found > 0) {
-        const float edge = key_to_float((uint32_t)found << 20);  // lowest value of the bin
-        uint32_t key;
-        if (MODE == TAUV_TOPK_SIGMOID_PEAK) key = reject_key_for_score(sigmoid_ref(edge));
-        else key = (uint32_t)found << 20;
-        if (key) atomicMax(fstate, key);
-      }
-    }
-  }
+  if (tid < 32 && ctx->base > 0) frame_republish<MODE>(a, ctx, fstate, (uint32_t)ctx->base, false);
 }
 
 // One CTA per item.  Block index -> item interleaves the frames (consecutive blocks are different frames), so the
@@ -435,27 +476,96 @@ __global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(const __grid_co
   const uint32_t plane_flat0 = (uint32_t)c_in_frame * (uint32_t)(a.H * a.W);
   uint32_t* fstate = a.frame_state + (size_t)frame * kFrameStateWords;
 
+  long long tr[4] = {0, 0, 0, 0};
+  auto now = []() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; };
+  if (a.trace && tid == 0) tr[0] = now();
   if (tid == 0) {
     const uint32_t key = *reinterpret_cast<volatile uint32_t*>(fstate);  // what the frame's finished items published
+    if (a.trace) a.trace[(size_t)blockIdx.x * 8 + 5] = key;
     ctx->count = 0;
     ctx->n_conv = 0;
+    ctx->n_boot = 0;
     ctx->flags = 0;
+    ctx->fs[0] = ctx->fs[1] = ctx->fs[2] = ctx->fs[3] = 0;
     ctx->thr = (unsigned long long)key << 32;
     ctx->thr_f = key ? key_to_float(key) : TAUV_NEG_INF;
   }
   __syncthreads();
 
   const int e0 = r0 * a.W, e1 = r1 * a.W;
-  const int fl = scan_elems<MODE, VEC>(a, ctx, list, plane, plane_flat0, e0, e1);
+  int es = e0;
+  constexpr int kRound = 16 * kTileThreads;  // elements per round of four 128-bit loads per thread
+  if (VEC && ctx->thr == 0ull && e1 - e0 > kRound) {
+    // Bootstrap: the frame has published nothing yet.  Every cell of the first round gets the full peak test —
+    // from a shared-memory copy of the rows when it fits, so the dependent neighbour loads cost tens of cycles
+    // instead of hundreds — and every peak found goes straight into the frame's bins.  All items that start
+    // without a threshold do this at the same time, so a few microseconds into the kernel the frame knows the
+    // k-th best of several thousand peaks and every item of the frame switches to streaming.
+    es = e0 + kRound;
+    // The bootstrap round is a chain of latencies (tile load, peak tests, atomics, bin scan) during which this
+    // CTA asks nothing of HBM: have the rest of the item pulled into L2 meanwhile, so the rounds that follow
+    // stream from L2 and the memory pipe stays busy.
+    for (int line = tid; line * 32 < e1 - es; line += kTileThreads)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(plane + es + line * 32));
+    int fl0 = 0;
+    if (a.tile_floats) {
+      float* tile = reinterpret_cast<float*>(smem_raw + (size_t)a.cap * 8 + kRadixBins * 4);
+      const int la = max(r0 - 1, 0), lb = min((es + a.W - 1) / a.W + 1, a.H);
+      const int n4 = ((lb - la) * a.W) >> 2;
+      const float* src = plane + (size_t)la * a.W;
+      for (int t = tid; t < n4; t += kTileThreads)
+        reinterpret_cast<float4*>(tile)[t] = ldg_stream4(src + ((size_t)t << 2));
+      __syncthreads();
+#pragma unroll 1
+      for (int t = (e0 >> 2) + tid; t < (es >> 2); t += kTileThreads)
+        fl0 |= examine<MODE, VEC, true>(a, ctx, list, tile, plane_flat0, t << 2, la * a.W);
+    } else {
+      fl0 = scan_elems<MODE, VEC>(a, ctx, list, plane, plane_flat0, e0, es);
+    }
+    if (fl0) atomicOr(&ctx->flags, fl0);
+    if (tid == 0) ctx->maxbin = 0;
+    __syncthreads();
+    if (!(ctx->flags & 2)) {
+      const int nb = ctx->count;
+      uint32_t my_maxbin = 0;
+      for (int i = tid; i < nb; i += kTileThreads) {
+        // (SIGMOID_PEAK: the entries still carry logit keys, which is the space the bins live in)
+        const uint32_t bin = composite_key(list[i]) >> 20;
+        atomicAdd(fstate + 4 + bin, 1u);
+        my_maxbin = max(my_maxbin, bin);
+      }
+      if (my_maxbin) atomicMax(&ctx->maxbin, my_maxbin);
+      __syncthreads();
+      if (tid < 32 && nb > 0) {
+        const uint32_t key = frame_republish<MODE>(a, ctx, fstate, (uint32_t)nb, true);
+        if (tid == 0) {
+          ctx->n_boot = nb;
+          set_thr(ctx, (unsigned long long)key << 32);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (a.trace && tid == 0) tr[1] = now();
+  const int fl = scan_elems<MODE, VEC>(a, ctx, list, plane, plane_flat0, es, e1, fstate);
   if (fl) atomicOr(&ctx->flags, fl);
+  if (tid == 0) asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   if (ctx->flags & 2) rescan_item_safely<MODE, VEC>(a, ctx, list, hist, plane, plane_flat0, e0, e1);
 
+  if (a.trace && tid == 0) {
+    tr[2] = now();
+    a.trace[(size_t)blockIdx.x * 8 + 4] = ctx->count;
+  }
   if (ctx->count == 0) {
     if (tid == 0) a.cand_count[item] = 0;
-    return;
+  } else {
+    finish_item<MODE>(a, ctx, list, hist, item, fstate);
   }
-  finish_item<MODE>(a, ctx, list, hist, item, fstate);
+  if (a.trace && tid == 0) {
+    tr[3] = now();
+    for (int i = 0; i < 4; ++i) a.trace[(size_t)blockIdx.x * 8 + i] = tr[i];
+  }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -714,6 +824,8 @@ static int check_topk_shape(int B, int C, int H, int W, int k) {
   return 0;
 }
 
+static long long* g_debug_trace = nullptr;  // experiment hook (tools/tile_trace.py); not part of the public ABI
+
 static int plan_and_check(const float* hm, int B, int C, int H, int W, int k, void* ws, size_t ws_bytes, TopkPlan* p,
                           TileArgs* a) {
   make_plan(B, C, H, W, k, hm, p);
@@ -723,10 +835,11 @@ static int plan_and_check(const float* hm, int B, int C, int H, int W, int k, vo
   TAUV_REQUIRE(p->smem_bytes <= 227 * 1024, TAUV_E_UNSUPPORTED, "tile needs %zu B shared memory", p->smem_bytes);
   a->hm = hm; a->B = B; a->C = C; a->H = H; a->W = W; a->k = k;
   a->rows_per_item = p->rows_per_item; a->items_per_plane = p->items_per_plane;
-  a->cap = p->cap; a->soft = p->soft; a->sub_elems = p->sub_elems;
+  a->cap = p->cap; a->soft = p->soft; a->sub_elems = p->sub_elems; a->tile_floats = p->tile_floats;
   a->cand = reinterpret_cast<unsigned long long*>(ws);
   a->cand_count = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws) + p->cand_bytes);
   a->frame_state = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(ws) + p->cand_bytes + p->count_bytes);
+  a->trace = g_debug_trace;
   const long long items = (long long)B * p->items_per_frame;
   TAUV_REQUIRE(items < (1LL << 31), TAUV_E_UNSUPPORTED, "too many items (%lld)", items);
   return 0;
@@ -916,3 +1029,7 @@ extern "C" int tauv_centernet_decode_stage2(int B, int C, int H, int W, int k, c
   return run_stage2(B, C, H, W, k, TAUV_TOPK_SIGMOID_PEAK, index, label, score, g, workspace, workspace_bytes,
                     (cudaStream_t)stream);
 }
+
+// Debug hook for tools/tile_trace.py: per-item timestamps of the next tile_topk launches land in `buf`
+// (8 int64 per item; NULL switches tracing off).  Process-global, not thread-safe, not in the public header.
+extern "C" void tauv_debug_tile_trace(long long* buf) { tauv::g_debug_trace = buf; }
