@@ -453,6 +453,148 @@ __device__ __noinline__ void finish_item(const TileArgs& a, TileCtx* ctx, unsign
   if (tid < 32 && ctx->base > 0) frame_republish<MODE>(a, ctx, fstate, (uint32_t)ctx->base, false);
 }
 
+// ----------------------------------------------------------------------------------------------
+// K0: seed the per-frame rejection threshold from a sample
+// ----------------------------------------------------------------------------------------------
+// One CTA per frame: the full peak test on a small sample of the frame (a few tiles of rows taken from planes spread
+// over the classes, 0.6 % of the batch at the headline shape, staged in shared memory with all loads in flight at
+// once), a histogram of the sampled peaks' keys, and the lower edge of the bin holding the k-th best becomes the
+// frame's first published threshold: at least k genuine peaks of the frame are known to lie at or above it, so
+// nothing below it can be in the frame's top-k.  With it every item of the main kernel streams from its first
+// cell instead of testing every cell until the first items have finished.
+constexpr int kSeedThreads = 256;
+constexpr int kSeedTileElems = 4096;
+
+// grid = (n_tiles, B): one CTA per sampled tile.  Peaks go into the frame's bins in global memory; the CTA that
+// finishes last for a frame (ticket in frame_state[3]) scans the bins, publishes the key and zeroes bins and ticket
+// again, so the main kernel starts from an empty histogram and never counts a cell twice.
+template <int MODE>
+__global__ void __launch_bounds__(kSeedThreads) seed_threshold_kernel(const __grid_constant__ TileArgs a, int tile_rows) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int W = a.W, H = a.H;
+  float* tile = reinterpret_cast<float*>(smem_raw);
+  uint32_t* lbins = reinterpret_cast<uint32_t*>(smem_raw + (size_t)(tile_rows + 2) * a.W * 4);  // CTA-local bins
+  __shared__ uint32_t warp_tot[kSeedThreads / 32];
+  __shared__ int s_found, s_last;
+  const int tid = threadIdx.x;
+  const int frame = blockIdx.y, s = blockIdx.x, n_tiles = gridDim.x;
+  for (int i = tid; i < kFrameBins; i += kSeedThreads) lbins[i] = 0;
+  uint32_t* fstate = a.frame_state + (size_t)frame * kFrameStateWords;
+  const float NI = TAUV_NEG_INF;
+
+  // tile s -> (class, row block): spread over the classes first, then over the row blocks
+  const int row_blocks = (H + tile_rows - 1) / tile_rows;
+  const int per_rb = (n_tiles + row_blocks - 1) / row_blocks;
+  const int rbk = s / per_rb, jj = s - rbk * per_rb;
+  const int c = (int)(((long long)jj * a.C) / per_rb);
+  const int ra = min(rbk, row_blocks - 1) * tile_rows, rb = min(ra + tile_rows, H);
+  const int la = max(ra - 1, 0), lb = min(rb + 1, H);
+  const float* src = a.hm + (((size_t)frame * a.C + c) * H + la) * W;
+  const int n4 = ((lb - la) * W) >> 2;
+  for (int t = tid; t < n4; t += kSeedThreads)
+    reinterpret_cast<float4*>(tile)[t] = ldg_stream4(src + ((size_t)t << 2));
+  if (tid == 0) s_found = -1;
+  __syncthreads();
+
+  const int S = W >> 2;
+  for (int t = tid; t < (rb - ra) * S; t += kSeedThreads) {
+    const int ri = t / S, col = (t - ri * S) << 2;
+    const int r = ra + ri;
+    const float* p1 = tile + (r - la) * W + col;
+    const float4 x = *reinterpret_cast<const float4*>(p1);
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+    if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
+      const bool hl = col > 0, hr = col + 4 < W;
+      float4 u = make_float4(NI, NI, NI, NI), d = u;
+      float ul = NI, ur = NI, dl = NI, dright = NI;
+      if (r > 0) {
+        u = *reinterpret_cast<const float4*>(p1 - W);
+        if (hl) ul = p1[-W - 1];
+        if (hr) ur = p1[-W + 4];
+      }
+      if (r + 1 < H) {
+        d = *reinterpret_cast<const float4*>(p1 + W);
+        if (hl) dl = p1[W - 1];
+        if (hr) dright = p1[W + 4];
+      }
+      const float ml = hl ? p1[-1] : NI, mr = hr ? p1[4] : NI;
+      float cm[6];
+      cm[0] = fmaxf(fmaxf(ul, ml), dl);
+      cm[1] = fmaxf(fmaxf(u.x, x.x), d.x);
+      cm[2] = fmaxf(fmaxf(u.y, x.y), d.y);
+      cm[3] = fmaxf(fmaxf(u.z, x.z), d.z);
+      cm[4] = fmaxf(fmaxf(u.w, x.w), d.w);
+      cm[5] = fmaxf(fmaxf(ur, mr), dright);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        // a logit >= its 3x3 neighbourhood is a peak of the suppressed map whatever the sigmoid's rounding; below
+        // -80 the sigmoid may underflow to a zero score, which is not a candidate: leave those out
+        const float m = fmaxf(fmaxf(cm[cc], cm[cc + 1]), cm[cc + 2]);
+        if (xs[cc] >= m && xs[cc] > -80.0f) atomicAdd(&lbins[float_to_key(xs[cc]) >> 20], 1u);
+      }
+    } else {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) atomicAdd(&lbins[float_to_key(xs[cc]) >> 20], 1u);
+    }
+  }
+  __syncthreads();
+  // one global atomic per occupied bin instead of one per peak (the peaks of a tile share a dozen bins)
+  for (int i = tid; i < kFrameBins; i += kSeedThreads)
+    if (lbins[i]) atomicAdd(fstate + 4 + i, lbins[i]);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(fstate + 3, 1u) == (uint32_t)n_tiles - 1u);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+
+  // the frame's last tile: highest bin b with count(bins >= b) >= k  (thread t owns bins [16t, 16t+16))
+  constexpr int BPT = kFrameBins / kSeedThreads;
+  uint32_t local[BPT], mine = 0;
+#pragma unroll
+  for (int j = 0; j < BPT; ++j) {
+    local[j] = *reinterpret_cast<volatile uint32_t*>(fstate + 4 + tid * BPT + j);
+    mine += local[j];
+  }
+  uint32_t suf = mine;
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_down_sync(0xffffffffu, suf, o);
+    if (lane + o < 32) suf += v;
+  }
+  if (lane == 0) warp_tot[warp] = suf;
+  __syncthreads();
+  for (int w = warp + 1; w < kSeedThreads / 32; ++w) suf += warp_tot[w];
+  const uint32_t above = suf - mine, k = (uint32_t)a.k;
+  if (above < k && suf >= k) {
+    uint32_t acc = above;
+#pragma unroll
+    for (int j = BPT - 1; j >= 0; --j) {
+      acc += local[j];
+      if (acc >= k) {
+        s_found = tid * BPT + j;
+        break;
+      }
+    }
+  }
+  // leave the bins and the ticket as the main kernel expects them: empty
+#pragma unroll
+  for (int j = 0; j < BPT; ++j)
+    if (local[j]) fstate[4 + tid * BPT + j] = 0u;
+  __syncthreads();
+  if (tid == 0) {
+    fstate[3] = 0u;
+    if (s_found > 0) {
+      const float edge = key_to_float((uint32_t)s_found << 20);  // lowest value of the bin
+      uint32_t key;
+      if (MODE == TAUV_TOPK_SIGMOID_PEAK) key = reject_key_for_score(sigmoid_ref(edge));
+      else key = (uint32_t)s_found << 20;
+      if (key) fstate[0] = key;
+    }
+  }
+}
+
 // One CTA per item.  Block index -> item interleaves the frames (consecutive blocks are different frames), so the
 // first items of EVERY frame finish early and publish a threshold for the frame's other items.
 template <int MODE, bool VEC>
@@ -860,6 +1002,19 @@ static int run_stage1(const float* hm, int B, int C, int H, int W, int k, int mo
     const char* dbg = getenv("TAUV_TILE_DEBUG");  // experiment hook: "keep" = reuse the previous call's thresholds
     if (!(dbg && dbg[0] == 'k'))
       TAUV_CUDA(cudaMemsetAsync(a.frame_state, 0, p.state_bytes, st));  // key 0 = "no threshold published yet"
+  }
+  // seed thresholds from a sample (only worth a launch when a frame is much larger than the sample)
+  if (p.vec && B <= 65535 && (long long)C * H * W >= 16LL * 8 * kSeedTileElems) {
+    int tile_rows = kSeedTileElems / W;
+    if (tile_rows < 1) tile_rows = 1;
+    if (tile_rows > H) tile_rows = H;
+    const int n_tiles = 8;
+    const size_t ssmem = (size_t)(tile_rows + 2) * W * 4 + kFrameBins * 4;
+    void (*seed)(const TileArgs, int) =
+        mode == TAUV_TOPK_SIGMOID_PEAK ? seed_threshold_kernel<1> : seed_threshold_kernel<0>;
+    TAUV_CUDA(cudaFuncSetAttribute(seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+    seed<<<dim3(n_tiles, B), kSeedThreads, ssmem, st>>>(a, tile_rows);
+    TAUV_LAUNCH_CHECK("seed_threshold_kernel");
   }
   kern<<<(unsigned)items, kTileThreads, p.smem_bytes, st>>>(a);
   TAUV_LAUNCH_CHECK("tile_topk_kernel");
