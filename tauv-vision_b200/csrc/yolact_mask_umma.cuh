@@ -1,12 +1,336 @@
 // yolact_mask_umma.cuh — tcgen05 / TMEM mask contraction (included by yolact_mask.cu).
+//
+//   mask[i, pix] = sigmoid( sum_p coeff[i,p] * proto[p,pix] ) * crop(box[i])      (masks.py:8-21)
+//
+// as D[M = 128 detections, N = 256 pixels] = A[128 x 32] * B[256 x 32]^T on the 5th-gen tensor cores:
+//   A = coefficients, bf16, K-major, SWIZZLE_64B canonical layout (a row is 32 bf16 = 64 B), written once per frame;
+//       every fp32 operand is split into a bf16 pair hi + lo and the product is formed as hi*hi + hi*lo + lo*hi
+//       (three MMAs into the same accumulator), so the logits are accurate to ~1e-5 instead of bf16's ~1e-2;
+//   B = prototype tile transposed to [pixel][p], bf16, same layout, converted from the fp32 [P][HW] map by the
+//       producer warps (coalesced 4-byte loads along the pixels, 16-byte swizzled stores), 2 stages;
+//   D = fp32 accumulator in tensor memory (2 x 256 columns, so the epilogue of one tile overlaps the MMA of the next).
+// Persistent, warp-specialised, one CTA per SM:
+//   warps 0-3  epilogue : tcgen05.ld -> shared-memory transpose -> sigmoid + crop -> coalesced 128-byte row stores
+//   warps 4-11 producer : fp32 -> bf16 conversion of the B tile (and of A / the crop bounds at a frame change)
+//   warp  12   MMA      : one elected thread issues tcgen05.mma (K = 16 per instruction, two per tile) + commits
+// All hand-offs are mbarriers; tcgen05.commit arrives on them when the tensor core is done with an operand.
+// The contraction depth is 32, i.e. ~12 flop per byte moved: the kernel is bound by the fp32 mask WRITE, the tensor
+// pipe idles most of the time by construction.
 #pragma once
 
 namespace tauv {
 
-static bool umma_shape_ok(const MaskArgs&) { return false; }
+constexpr int kUmmaP = 32;            // contraction depth this kernel is built for
+constexpr int kUmmaM = 128;           // detections per MMA tile (TMEM lanes)
+constexpr int kUmmaN = 256;           // pixels per MMA tile (TMEM columns per accumulator stage)
+constexpr int kUmmaMaxMTiles = 4;     // detections handled per launch = 512 (more: the host loops over groups)
+constexpr int kUmmaEpiWarps = 4, kUmmaProdWarps = 8;
+constexpr int kUmmaThreads = (kUmmaEpiWarps + kUmmaProdWarps + 1) * 32;  // 416
 
-static int launch_mask_umma(const MaskArgs&, int, int, cudaStream_t) {
-  return fail(TAUV_E_UNSUPPORTED, "tensor-core mask kernel not built");
+struct UmmaSmem {
+  // operands (each 512-byte aligned groups of 8 rows x 64 B)
+  // each operand is kept as a bf16 pair (hi, lo) with hi + lo == the fp32 value to ~2^-17: three MMAs
+  // (hi*hi + hi*lo + lo*hi) give fp32-class logits from bf16 tensor-core instructions
+  __align__(1024) unsigned char a[2][kUmmaMaxMTiles][kUmmaM * 64];  // [hi/lo] 2 x 4 x 8 KB
+  __align__(1024) unsigned char b[2][2][kUmmaN * 64];               // [stage][hi/lo] 2 x 2 x 16 KB
+  float bounds[kUmmaMaxMTiles * kUmmaM][4];                      // crop bounds (left, right, top, bottom) per detection
+  float stage[kUmmaEpiWarps][32][33];                            // per-warp transpose tile
+  uint64_t b_full[2], b_empty[2], acc_full[2], acc_empty[2], frame_done;
+  uint32_t tmem_base;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 columns of 32-bit: thread t of the warp gets columns [c, c+32) of TMEM lane (lane_base + t)
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
+      "[%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor for a K-major, SWIZZLE_64B operand whose rows are 64 bytes (32 bf16):
+// 8-row groups are 512 B apart (stride byte offset), start address in 16-byte units, descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(const void* smem, uint32_t byte_offset) {
+  const uint32_t addr = smem_u32(smem) + byte_offset;
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fffu);        // start address
+  d |= (uint64_t)1u << 16;                       // leading byte offset (unused for swizzled K-major; canonical 1)
+  d |= (uint64_t)(512u >> 4) << 32;              // stride byte offset: 8 rows x 64 B
+  d |= (uint64_t)1u << 46;                       // version
+  d |= (uint64_t)4u << 61;                       // layout type: SWIZZLE_64B
+  return d;
+}
+// Instruction descriptor: D = F32, A = B = BF16, both K-major, N = 256, M = 128, dense, no negate.
+__device__ __forceinline__ uint32_t umma_idesc_bf16_m128_n256() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kUmmaN >> 3) << 17) | ((uint32_t)(kUmmaM >> 4) << 24);
+}
+
+// Byte offset of the 16-byte chunk `c` (8 bf16: k = 8c..8c+7) of row `r` in the SWIZZLE_64B K-major layout:
+// Swizzle<2,4,3>: address bits [4,6) ^= address bits [7,9), i.e. chunk ^= (r >> 1) & 3 for 64-byte rows.
+__device__ __forceinline__ uint32_t sw64_offset(int r, int c) { return (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// fp32 -> (hi, lo) bf16 pairs of two values: hi = rn_bf16(x), lo = rn_bf16(x - hi)
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(x0, x1);
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  lo = pack_bf16x2(x0 - h0, x1 - h1);
+}
+
+struct UnitRange {
+  long long u0, u1;  // units = (frame, pixel tile); this CTA's contiguous share
+  int n_tiles_n;
+};
+
+// number of 128-row tiles of frame b handled by this launch (rows [m_base, m_base + 512))
+__device__ __forceinline__ int frame_mtiles(const MaskArgs& a, int b, int m_base) {
+  const int n = (a.n_keep ? a.n_keep[b] : a.n_host) - m_base;
+  if (n <= 0) return 0;
+  const int mt = (n + kUmmaM - 1) / kUmmaM;
+  return mt < kUmmaMaxMTiles ? mt : kUmmaMaxMTiles;
+}
+
+__global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid_constant__ MaskArgs a, int B,
+                                                                    int m_base) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  UmmaSmem* sm = reinterpret_cast<UmmaSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HW = a.H * a.W;
+  const int n_tiles_n = (HW + kUmmaN - 1) / kUmmaN;
+  const long long units = (long long)B * n_tiles_n;
+  const long long u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
+
+  if (tid == 0) {
+    mbar_init(&sm->b_full[0], kUmmaProdWarps * 32);
+    mbar_init(&sm->b_full[1], kUmmaProdWarps * 32);
+    mbar_init(&sm->b_empty[0], 1);
+    mbar_init(&sm->b_empty[1], 1);
+    mbar_init(&sm->acc_full[0], 1);
+    mbar_init(&sm->acc_full[1], 1);
+    mbar_init(&sm->acc_empty[0], kUmmaEpiWarps * 32);
+    mbar_init(&sm->acc_empty[1], kUmmaEpiWarps * 32);
+    mbar_init(&sm->frame_done, kUmmaEpiWarps * 32);
+    mbar_fence_init();
+  }
+  if (warp == kUmmaEpiWarps + kUmmaProdWarps) {  // the MMA warp owns the tensor memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+
+  if (warp < kUmmaEpiWarps) {
+    // ======================================= epilogue =======================================
+    uint32_t uses[2] = {0, 0};
+    int as = 0;
+    float(*st)[33] = sm->stage[warp];
+    for (long long u = u0; u < u1; ++u) {
+      const int b = (int)(u / n_tiles_n), nt = (int)(u - (long long)b * n_tiles_n);
+      const int mt = frame_mtiles(a, b, m_base);
+      if (mt == 0) continue;
+      const int n_rows = (a.n_keep ? a.n_keep[b] : a.n_host) - m_base;
+      const int pix0 = nt * kUmmaN;
+      for (int m = 0; m < mt; ++m) {
+        mbar_wait(&sm->acc_full[as], uses[as] & 1u);
+        tc_fence_after();
+        const int row0 = m * kUmmaM + warp * 32;  // first detection (relative to m_base) of this warp's TMEM lanes
+#pragma unroll 1
+        for (int cb = 0; cb < kUmmaN / 32; ++cb) {
+          if (pix0 + cb * 32 >= HW) break;
+          float v[32];
+          tc_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * kUmmaN + cb * 32), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) st[lane][j] = v[j];
+          __syncwarp();
+          const int pix = pix0 + cb * 32 + lane;
+          const float py = (float)(pix / a.W), px = (float)(pix - (pix / a.W) * a.W);
+          if (pix < HW) {
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+              const int row = row0 + rr;
+              if (row >= n_rows) break;
+              const float logit = st[rr][lane];
+              const float4 bd = *reinterpret_cast<const float4*>(sm->bounds[row]);
+              const bool inside = px >= bd.x && px <= bd.y && py >= bd.z && py <= bd.w;
+              const float val = inside ? __fdividef(1.0f, 1.0f + __expf(-logit)) : 0.0f;
+              const size_t o = ((size_t)b * a.top_k + m_base + row) * HW + pix;
+              a.out[o] = val;
+              if (a.logits) a.logits[o] = logit;
+            }
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        mbar_arrive(&sm->acc_empty[as]);
+        ++uses[as];
+        as ^= 1;
+      }
+      // end of this CTA's run of units of frame b: the producers may overwrite A / the crop bounds
+      if (u + 1 == u1 || (int)((u + 1) / n_tiles_n) != b) mbar_arrive(&sm->frame_done);
+    }
+  } else if (warp < kUmmaEpiWarps + kUmmaProdWarps) {
+    // ======================================= producers =======================================
+    const int pt = tid - kUmmaEpiWarps * 32;  // 0..255: the pixel row of the B tile this thread converts
+    uint32_t fills[2] = {0, 0}, frames = 0;
+    int bs = 0, cur_frame = -1;
+    for (long long u = u0; u < u1; ++u) {
+      const int b = (int)(u / n_tiles_n), nt = (int)(u - (long long)b * n_tiles_n);
+      const int mt = frame_mtiles(a, b, m_base);
+      if (mt == 0) continue;
+      if (b != cur_frame) {
+        // A (coefficients) and the crop bounds of the frame.  The epilogue must be done with the previous frame.
+        if (frames > 0) mbar_wait(&sm->frame_done, (frames - 1) & 1u);
+        const int n_rows = (a.n_keep ? a.n_keep[b] : a.n_host) - m_base;
+        for (int i = pt; i < mt * kUmmaM * 4; i += kUmmaProdWarps * 32) {
+          const int row = i >> 2, c = i & 3;  // 16-byte chunk c of detection `row`
+          uint4 qh = make_uint4(0, 0, 0, 0), ql = qh;
+          if (row < n_rows) {
+            const size_t src_row = a.keep ? ((size_t)b * a.N + (size_t)a.keep[(size_t)b * a.top_k + m_base + row])
+                                          : (size_t)(m_base + row);
+            const float4 f0 = *reinterpret_cast<const float4*>(a.coeff + src_row * kUmmaP + c * 8);
+            const float4 f1 = *reinterpret_cast<const float4*>(a.coeff + src_row * kUmmaP + c * 8 + 4);
+            split_bf16x2(f0.x, f0.y, qh.x, ql.x);
+            split_bf16x2(f0.z, f0.w, qh.y, ql.y);
+            split_bf16x2(f1.x, f1.y, qh.z, ql.z);
+            split_bf16x2(f1.z, f1.w, qh.w, ql.w);
+          }
+          *reinterpret_cast<uint4*>(sm->a[0][row / kUmmaM] + sw64_offset(row % kUmmaM, c)) = qh;
+          *reinterpret_cast<uint4*>(sm->a[1][row / kUmmaM] + sw64_offset(row % kUmmaM, c)) = ql;
+        }
+        for (int row = pt; row < mt * kUmmaM; row += kUmmaProdWarps * 32) {
+          float4 bd = make_float4(TAUV_NEG_INF, -TAUV_NEG_INF, TAUV_NEG_INF, -TAUV_NEG_INF);  // no crop
+          if (a.box && row < n_rows) {
+            const CropBounds cbd = crop_bounds(a.box[(size_t)b * a.top_k + m_base + row], a.H, a.W);
+            bd = make_float4(cbd.left, cbd.right, cbd.top, cbd.bottom);
+          }
+          *reinterpret_cast<float4*>(sm->bounds[row]) = bd;
+        }
+        cur_frame = b;
+        ++frames;
+        // (the bounds are read by the epilogue only after an acc_full that follows this unit's b_full; the named
+        //  barrier below orders the generic-proxy writes of all producer threads before any of them arrives)
+        asm volatile("bar.sync 1, %0;" ::"n"(kUmmaProdWarps * 32) : "memory");
+      }
+      if (fills[bs] > 0) mbar_wait(&sm->b_empty[bs], (fills[bs] - 1) & 1u);
+      // B tile: pixel row pt, 32 prototype values -> 4 chunks of 8 bf16
+      const int pix = nt * kUmmaN + pt;
+      const float* src = a.proto + (size_t)b * kUmmaP * HW + pix;
+      float f[kUmmaP];
+#pragma unroll
+      for (int p = 0; p < kUmmaP; ++p) f[p] = pix < HW ? __ldg(src + (size_t)p * HW) : 0.0f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 qh, ql;
+        split_bf16x2(f[8 * c], f[8 * c + 1], qh.x, ql.x);
+        split_bf16x2(f[8 * c + 2], f[8 * c + 3], qh.y, ql.y);
+        split_bf16x2(f[8 * c + 4], f[8 * c + 5], qh.z, ql.z);
+        split_bf16x2(f[8 * c + 6], f[8 * c + 7], qh.w, ql.w);
+        *reinterpret_cast<uint4*>(sm->b[bs][0] + sw64_offset(pt, c)) = qh;
+        *reinterpret_cast<uint4*>(sm->b[bs][1] + sw64_offset(pt, c)) = ql;
+      }
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
+      mbar_arrive(&sm->b_full[bs]);
+      ++fills[bs];
+      bs ^= 1;
+    }
+  } else if (lane == 0) {
+    // ======================================= MMA issuer =======================================
+    const uint32_t idesc = umma_idesc_bf16_m128_n256();
+    uint32_t fills[2] = {0, 0}, uses[2] = {0, 0};
+    int bs = 0, as = 0;
+    for (long long u = u0; u < u1; ++u) {
+      const int b = (int)(u / n_tiles_n);
+      const int mt = frame_mtiles(a, b, m_base);
+      if (mt == 0) continue;
+      mbar_wait(&sm->b_full[bs], fills[bs] & 1u);
+      tc_fence_after();
+      for (int m = 0; m < mt; ++m) {
+        if (uses[as] > 0) {
+          mbar_wait(&sm->acc_empty[as], (uses[as] - 1) & 1u);
+          tc_fence_after();
+        }
+        const uint32_t d = tmem + (uint32_t)(as * kUmmaN);
+#pragma unroll
+        for (int k = 0; k < kUmmaP / 16; ++k) {  // K = 16 bf16 = 32 bytes per instruction, inside the 64-byte rows
+          const uint64_t ah = umma_desc_k_sw64(sm->a[0][m], k * 32), al = umma_desc_k_sw64(sm->a[1][m], k * 32);
+          const uint64_t bh = umma_desc_k_sw64(sm->b[bs][0], k * 32), bl = umma_desc_k_sw64(sm->b[bs][1], k * 32);
+          tc_mma_bf16(d, al, bh, idesc, k > 0);  // small terms first
+          tc_mma_bf16(d, ah, bl, idesc, 1u);
+          tc_mma_bf16(d, ah, bh, idesc, 1u);
+        }
+        tc_commit(&sm->acc_full[as]);  // arrives when the MMAs above are complete
+        ++uses[as];
+        as ^= 1;
+      }
+      tc_commit(&sm->b_empty[bs]);  // ... and this one when the B stage (and A) are no longer being read
+      ++fills[bs];
+      bs ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kUmmaEpiWarps + kUmmaProdWarps) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+static bool umma_shape_ok(const MaskArgs& a) {
+  return a.P == kUmmaP && (uintptr_t)a.coeff % 16 == 0;
+}
+
+static int launch_mask_umma(const MaskArgs& a, int B, int max_rows, cudaStream_t st) {
+  const size_t smem = sizeof(UmmaSmem) + 1024;
+  TAUV_CUDA(cudaFuncSetAttribute(mask_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int HW = a.H * a.W;
+  const long long units = (long long)B * ((HW + kUmmaN - 1) / kUmmaN);
+  long long grid = num_sms();
+  if (grid > units) grid = units;
+  for (int m_base = 0; m_base < max_rows; m_base += kUmmaMaxMTiles * kUmmaM) {
+    mask_umma_kernel<<<(unsigned)grid, kUmmaThreads, smem, st>>>(a, B, m_base);
+    TAUV_LAUNCH_CHECK("mask_umma_kernel");
+  }
+  return 0;
 }
 
 }  // namespace tauv
