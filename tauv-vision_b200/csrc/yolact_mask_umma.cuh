@@ -2,17 +2,22 @@
 //
 //   mask[i, pix] = sigmoid( sum_p coeff[i,p] * proto[p,pix] ) * crop(box[i])      (masks.py:8-21)
 //
-// as D[M = 128 detections, N = 256 pixels] = A[128 x 32] * B[256 x 32]^T on the 5th-gen tensor cores:
-//   A = coefficients, bf16, K-major, SWIZZLE_64B canonical layout (a row is 32 bf16 = 64 B), written once per frame;
-//       every fp32 operand is split into a bf16 pair hi + lo and the product is formed as hi*hi + hi*lo + lo*hi
+// as D[M = 128 pixels, N = detections (<= 256)] = A[128 x 32] * B[N x 32]^T on the 5th-gen tensor cores:
+//   A = prototype tile transposed to [pixel][p], bf16, K-major, SWIZZLE_64B canonical layout (a row is 32 bf16 =
+//       64 B), converted from the fp32 [P][HW] map by the producer warps (coalesced 4-byte loads along the pixels,
+//       16-byte swizzled stores), 2 stages;
+//   B = the frame's coefficients [detection][p], same layout, written once per frame;
+//       every fp32 operand is split into a bf16 pair hi + lo and the product is formed as lo*hi + hi*lo + hi*hi
 //       (three MMAs into the same accumulator), so the logits are accurate to ~1e-5 instead of bf16's ~1e-2;
-//   B = prototype tile transposed to [pixel][p], bf16, same layout, converted from the fp32 [P][HW] map by the
-//       producer warps (coalesced 4-byte loads along the pixels, 16-byte swizzled stores), 2 stages;
-//   D = fp32 accumulator in tensor memory (2 x 256 columns, so the epilogue of one tile overlaps the MMA of the next).
+//   D = fp32 accumulator in tensor memory, TMEM lane = pixel, column = detection (2 x 256 columns, so the epilogue
+//       of one tile overlaps the MMA of the next).
+// Pixels on the TMEM lanes make the epilogue store-friendly: after tcgen05.ld a warp holds, for one detection, 32
+// consecutive pixels in its 32 lanes, i.e. one fully coalesced 128-byte store per detection and warp, straight from
+// registers (the mask write is >80 % of the bytes this kernel moves).
 // Persistent, warp-specialised, one CTA per SM:
-//   warps 0-3  epilogue : tcgen05.ld -> shared-memory transpose -> sigmoid + crop -> coalesced 128-byte row stores
-//   warps 4-11 producer : fp32 -> bf16 conversion of the B tile (and of A / the crop bounds at a frame change)
-//   warp  12   MMA      : one elected thread issues tcgen05.mma (K = 16 per instruction, two per tile) + commits
+//   warps 0-7  epilogue : tcgen05.ld -> sigmoid + crop -> coalesced row stores (2 warps per TMEM lane quadrant)
+//   warps 8-11 producer : fp32 -> bf16 hi/lo conversion of the A tile (and of B / the crop bounds at a frame change)
+//   warp  12   MMA      : one elected thread issues tcgen05.mma (K = 16 per instruction) + commits
 // All hand-offs are mbarriers; tcgen05.commit arrives on them when the tensor core is done with an operand.
 // The contraction depth is 32, i.e. ~12 flop per byte moved: the kernel is bound by the fp32 mask WRITE, the tensor
 // pipe idles most of the time by construction.
@@ -21,21 +26,18 @@
 namespace tauv {
 
 constexpr int kUmmaP = 32;            // contraction depth this kernel is built for
-constexpr int kUmmaM = 128;           // detections per MMA tile (TMEM lanes)
-constexpr int kUmmaN = 256;           // pixels per MMA tile (TMEM columns per accumulator stage)
-constexpr int kUmmaMaxMTiles = 4;     // detections handled per launch = 512 (more: the host loops over groups)
-constexpr int kUmmaEpiWarps = 4, kUmmaProdWarps = 8;
+constexpr int kUmmaM = 128;           // pixels per MMA tile (TMEM lanes)
+constexpr int kUmmaNMax = 256;        // detections per launch (TMEM columns per accumulator stage); more: host loops
+constexpr int kUmmaEpiWarps = 8, kUmmaProdWarps = 4;
 constexpr int kUmmaThreads = (kUmmaEpiWarps + kUmmaProdWarps + 1) * 32;  // 416
 
 struct UmmaSmem {
-  // operands (each 512-byte aligned groups of 8 rows x 64 B)
-  // each operand is kept as a bf16 pair (hi, lo) with hi + lo == the fp32 value to ~2^-17: three MMAs
-  // (hi*hi + hi*lo + lo*hi) give fp32-class logits from bf16 tensor-core instructions
-  __align__(1024) unsigned char a[2][kUmmaMaxMTiles][kUmmaM * 64];  // [hi/lo] 2 x 4 x 8 KB
-  __align__(1024) unsigned char b[2][2][kUmmaN * 64];               // [stage][hi/lo] 2 x 2 x 16 KB
-  float bounds[kUmmaMaxMTiles * kUmmaM][4];                      // crop bounds (left, right, top, bottom) per detection
-  float stage[kUmmaEpiWarps][32][33];                            // per-warp transpose tile
-  uint64_t b_full[2], b_empty[2], acc_full[2], acc_empty[2], frame_done;
+  // each operand is kept as a bf16 pair (hi, lo) with hi + lo == the fp32 value to ~2^-17
+  __align__(1024) unsigned char a[2][2][kUmmaM * 64];     // [stage][hi/lo] prototype tiles, 4 x 8 KB
+  __align__(1024) unsigned char b[2][kUmmaNMax * 64];     // [hi/lo] coefficients of the frame, 2 x 16 KB
+  float bounds[kUmmaNMax][4];                             // crop bounds (left, right, top, bottom) per detection
+  __align__(16) float zeros[kUmmaM];                      // source of the bulk zero-fill stores
+  uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], frame_done;
   uint32_t tmem_base;
 };
 
@@ -90,9 +92,9 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw64(const void* smem, uint32_t 
   d |= (uint64_t)4u << 61;                       // layout type: SWIZZLE_64B
   return d;
 }
-// Instruction descriptor: D = F32, A = B = BF16, both K-major, N = 256, M = 128, dense, no negate.
-__device__ __forceinline__ uint32_t umma_idesc_bf16_m128_n256() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kUmmaN >> 3) << 17) | ((uint32_t)(kUmmaM >> 4) << 24);
+// Instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = n (multiple of 16, <= 256), dense.
+__device__ __forceinline__ uint32_t umma_idesc_bf16_m128(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kUmmaM >> 4) << 24);
 }
 
 // Byte offset of the 16-byte chunk `c` (8 bf16: k = 8c..8c+7) of row `r` in the SWIZZLE_64B K-major layout:
@@ -112,17 +114,10 @@ __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, u
   lo = pack_bf16x2(x0 - h0, x1 - h1);
 }
 
-struct UnitRange {
-  long long u0, u1;  // units = (frame, pixel tile); this CTA's contiguous share
-  int n_tiles_n;
-};
-
-// number of 128-row tiles of frame b handled by this launch (rows [m_base, m_base + 512))
-__device__ __forceinline__ int frame_mtiles(const MaskArgs& a, int b, int m_base) {
+// detections of frame b handled by this launch (rows [m_base, m_base + 256))
+__device__ __forceinline__ int frame_rows(const MaskArgs& a, int b, int m_base) {
   const int n = (a.n_keep ? a.n_keep[b] : a.n_host) - m_base;
-  if (n <= 0) return 0;
-  const int mt = (n + kUmmaM - 1) / kUmmaM;
-  return mt < kUmmaMaxMTiles ? mt : kUmmaMaxMTiles;
+  return n <= 0 ? 0 : (n < kUmmaNMax ? n : kUmmaNMax);
 }
 
 __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid_constant__ MaskArgs a, int B,
@@ -131,22 +126,22 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
   UmmaSmem* sm = reinterpret_cast<UmmaSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HW = a.H * a.W;
-  const int n_tiles_n = (HW + kUmmaN - 1) / kUmmaN;
-  const long long units = (long long)B * n_tiles_n;
+  const int n_tiles = (HW + kUmmaM - 1) / kUmmaM;
+  const long long units = (long long)B * n_tiles;  // unit = (frame, tile of 128 pixels); contiguous share per CTA
   const long long u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
 
   if (tid == 0) {
-    mbar_init(&sm->b_full[0], kUmmaProdWarps * 32);
-    mbar_init(&sm->b_full[1], kUmmaProdWarps * 32);
-    mbar_init(&sm->b_empty[0], 1);
-    mbar_init(&sm->b_empty[1], 1);
-    mbar_init(&sm->acc_full[0], 1);
-    mbar_init(&sm->acc_full[1], 1);
-    mbar_init(&sm->acc_empty[0], kUmmaEpiWarps * 32);
-    mbar_init(&sm->acc_empty[1], kUmmaEpiWarps * 32);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sm->a_full[s], kUmmaProdWarps * 32);
+      mbar_init(&sm->a_empty[s], 1);
+      mbar_init(&sm->acc_full[s], 1);
+      mbar_init(&sm->acc_empty[s], kUmmaEpiWarps * 32);
+    }
     mbar_init(&sm->frame_done, kUmmaEpiWarps * 32);
     mbar_fence_init();
   }
+  if (tid < kUmmaM) sm->zeros[tid] = 0.0f;
+  fence_proxy_async();  // the zeros are read by the async proxy (bulk stores)
   if (warp == kUmmaEpiWarps + kUmmaProdWarps) {  // the MMA warp owns the tensor memory
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)),
                  "r"(512u)
@@ -160,67 +155,90 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
 
   if (warp < kUmmaEpiWarps) {
     // ======================================= epilogue =======================================
+    const int quad = warp & 3, half = warp >> 2;  // TMEM lane quadrant / which 32-detection chunks (even, odd)
+    // bulk stores need 16-byte aligned rows: H*W % 4 == 0 and an aligned output
+    const bool bulk_zero = (HW % 4 == 0) && ((uintptr_t)a.out % 16 == 0);
     uint32_t uses[2] = {0, 0};
-    int as = 0;
-    float(*st)[33] = sm->stage[warp];
+    int as = 0, rows_frame = -1, n_rows = 0;
     for (long long u = u0; u < u1; ++u) {
-      const int b = (int)(u / n_tiles_n), nt = (int)(u - (long long)b * n_tiles_n);
-      const int mt = frame_mtiles(a, b, m_base);
-      if (mt == 0) continue;
-      const int n_rows = (a.n_keep ? a.n_keep[b] : a.n_host) - m_base;
-      const int pix0 = nt * kUmmaN;
-      for (int m = 0; m < mt; ++m) {
-        mbar_wait(&sm->acc_full[as], uses[as] & 1u);
-        tc_fence_after();
-        const int row0 = m * kUmmaM + warp * 32;  // first detection (relative to m_base) of this warp's TMEM lanes
+      const int b = (int)(u / n_tiles), nt = (int)(u - (long long)b * n_tiles);
+      if (b != rows_frame) {  // one global read per frame, not per tile
+        n_rows = frame_rows(a, b, m_base);
+        rows_frame = b;
+      }
+      if (n_rows == 0) continue;
+      const int pix = nt * kUmmaM + quad * 32 + lane;
+      const int yy = pix / a.W;
+      const float py = (float)yy, px = (float)(pix - yy * a.W);
+      float* out_tile = a.out + ((size_t)b * a.top_k + m_base) * HW + nt * kUmmaM;
+      float* out_pix = out_tile + quad * 32 + lane;
+      float* lg_pix = a.logits ? a.logits + ((size_t)b * a.top_k + m_base) * HW + pix : nullptr;
+      // image rows the tile's pixels lie in: a mask whose box misses them is all zero on this tile
+      const int tile_px = min(kUmmaM, HW - nt * kUmmaM);
+      const float ty0 = (float)((nt * kUmmaM) / a.W), ty1 = (float)((nt * kUmmaM + tile_px - 1) / a.W);
+      mbar_wait(&sm->acc_full[as], uses[as] & 1u);
+      tc_fence_after();
 #pragma unroll 1
-        for (int cb = 0; cb < kUmmaN / 32; ++cb) {
-          if (pix0 + cb * 32 >= HW) break;
-          float v[32];
-          tc_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * kUmmaN + cb * 32), v);
+      for (int c = half; c * 32 < n_rows; c += 2) {
+        // lane j looks at detection c*32+j: does its box reach the tile at all?  If not, one bulk store of zeros
+        // (shared -> global, issued by a single lane of the quadrant-0 warp) replaces 4 warps x 1 store + tests.
+        bool live = false;
+        {
+          const int det = c * 32 + lane;
+          if (det < n_rows) {
+            const float4 bd = *reinterpret_cast<const float4*>(sm->bounds[det]);
+            live = lg_pix != nullptr || !bulk_zero || !(ty1 < bd.z || ty0 > bd.w);
+            if (!live && quad == 0) bulk_s2g(out_tile + (size_t)det * HW, sm->zeros, (uint32_t)tile_px * 4u);
+          }
+        }
+        const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+        if (live_mask == 0u) continue;
+        float v[32];
+        tc_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kUmmaNMax + c * 32), v);
+        float* op = out_pix + (size_t)(c * 32) * HW;
+        float* lp = lg_pix ? lg_pix + (size_t)(c * 32) * HW : nullptr;
+        const float4* bp = reinterpret_cast<const float4*>(sm->bounds[c * 32]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) st[lane][j] = v[j];
-          __syncwarp();
-          const int pix = pix0 + cb * 32 + lane;
-          const float py = (float)(pix / a.W), px = (float)(pix - (pix / a.W) * a.W);
-          if (pix < HW) {
-#pragma unroll 4
-            for (int rr = 0; rr < 32; ++rr) {
-              const int row = row0 + rr;
-              if (row >= n_rows) break;
-              const float logit = st[rr][lane];
-              const float4 bd = *reinterpret_cast<const float4*>(sm->bounds[row]);
-              const bool inside = px >= bd.x && px <= bd.y && py >= bd.z && py <= bd.w;
-              const float val = inside ? __fdividef(1.0f, 1.0f + __expf(-logit)) : 0.0f;
-              const size_t o = ((size_t)b * a.top_k + m_base + row) * HW + pix;
-              a.out[o] = val;
-              if (a.logits) a.logits[o] = logit;
+        for (int j = 0; j < 32; ++j, op += HW) {
+          if ((live_mask >> j) & 1u) {  // warp-uniform
+            const float4 bd = bp[j];  // same address for the whole warp: a broadcast
+            const bool inside = px >= bd.x && px <= bd.y && py >= bd.z && py <= bd.w;
+            float val = 0.0f;
+            if (__any_sync(0xffffffffu, inside)) val = inside ? __fdividef(1.0f, 1.0f + __expf(-v[j])) : 0.0f;
+            if (pix < HW) {
+              *op = val;  // 32 lanes = 32 consecutive pixels of one mask: one 128-byte store
+              if (lp) lp[(size_t)j * HW] = v[j];
             }
           }
-          __syncwarp();
         }
-        tc_fence_before();
-        mbar_arrive(&sm->acc_empty[as]);
-        ++uses[as];
-        as ^= 1;
       }
-      // end of this CTA's run of units of frame b: the producers may overwrite A / the crop bounds
-      if (u + 1 == u1 || (int)((u + 1) / n_tiles_n) != b) mbar_arrive(&sm->frame_done);
+      tc_fence_before();
+      mbar_arrive(&sm->acc_empty[as]);
+      ++uses[as];
+      as ^= 1;
+      // end of this CTA's run of units of frame b: the producers may overwrite B / the crop bounds
+      if (u + 1 == u1 || (int)((u + 1) / n_tiles) != b) mbar_arrive(&sm->frame_done);
     }
+    bulk_commit();
+    bulk_wait<0>();  // the zero-fill stores this thread issued have completed
   } else if (warp < kUmmaEpiWarps + kUmmaProdWarps) {
     // ======================================= producers =======================================
-    const int pt = tid - kUmmaEpiWarps * 32;  // 0..255: the pixel row of the B tile this thread converts
+    const int pt = tid - kUmmaEpiWarps * 32;  // 0..127: the pixel row of the A tile this thread converts
     uint32_t fills[2] = {0, 0}, frames = 0;
-    int bs = 0, cur_frame = -1;
+    int st = 0, cur_frame = -1, rows_frame = -1, n_rows = 0;
     for (long long u = u0; u < u1; ++u) {
-      const int b = (int)(u / n_tiles_n), nt = (int)(u - (long long)b * n_tiles_n);
-      const int mt = frame_mtiles(a, b, m_base);
-      if (mt == 0) continue;
+      const int b = (int)(u / n_tiles), nt = (int)(u - (long long)b * n_tiles);
+      if (b != rows_frame) {
+        n_rows = frame_rows(a, b, m_base);
+        rows_frame = b;
+      }
+      if (n_rows == 0) continue;
       if (b != cur_frame) {
-        // A (coefficients) and the crop bounds of the frame.  The epilogue must be done with the previous frame.
+        // B (coefficients) and the crop bounds of the frame.  The epilogue must be done with the previous frame
+        // (which also means every MMA that read the old B has completed).
         if (frames > 0) mbar_wait(&sm->frame_done, (frames - 1) & 1u);
-        const int n_rows = (a.n_keep ? a.n_keep[b] : a.n_host) - m_base;
-        for (int i = pt; i < mt * kUmmaM * 4; i += kUmmaProdWarps * 32) {
+        const int n_pad = (n_rows + 15) & ~15;
+        for (int i = pt; i < n_pad * 4; i += kUmmaProdWarps * 32) {
           const int row = i >> 2, c = i & 3;  // 16-byte chunk c of detection `row`
           uint4 qh = make_uint4(0, 0, 0, 0), ql = qh;
           if (row < n_rows) {
@@ -233,12 +251,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
             split_bf16x2(f1.x, f1.y, qh.z, ql.z);
             split_bf16x2(f1.z, f1.w, qh.w, ql.w);
           }
-          *reinterpret_cast<uint4*>(sm->a[0][row / kUmmaM] + sw64_offset(row % kUmmaM, c)) = qh;
-          *reinterpret_cast<uint4*>(sm->a[1][row / kUmmaM] + sw64_offset(row % kUmmaM, c)) = ql;
+          *reinterpret_cast<uint4*>(sm->b[0] + sw64_offset(row, c)) = qh;
+          *reinterpret_cast<uint4*>(sm->b[1] + sw64_offset(row, c)) = ql;
         }
-        for (int row = pt; row < mt * kUmmaM; row += kUmmaProdWarps * 32) {
+        for (int row = pt; row < n_rows; row += kUmmaProdWarps * 32) {
           float4 bd = make_float4(TAUV_NEG_INF, -TAUV_NEG_INF, TAUV_NEG_INF, -TAUV_NEG_INF);  // no crop
-          if (a.box && row < n_rows) {
+          if (a.box) {
             const CropBounds cbd = crop_bounds(a.box[(size_t)b * a.top_k + m_base + row], a.H, a.W);
             bd = make_float4(cbd.left, cbd.right, cbd.top, cbd.bottom);
           }
@@ -246,13 +264,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
         }
         cur_frame = b;
         ++frames;
-        // (the bounds are read by the epilogue only after an acc_full that follows this unit's b_full; the named
-        //  barrier below orders the generic-proxy writes of all producer threads before any of them arrives)
-        asm volatile("bar.sync 1, %0;" ::"n"(kUmmaProdWarps * 32) : "memory");
       }
-      if (fills[bs] > 0) mbar_wait(&sm->b_empty[bs], (fills[bs] - 1) & 1u);
-      // B tile: pixel row pt, 32 prototype values -> 4 chunks of 8 bf16
-      const int pix = nt * kUmmaN + pt;
+      if (fills[st] > 0) mbar_wait(&sm->a_empty[st], (fills[st] - 1) & 1u);
+      // A tile: pixel row pt, 32 prototype values -> 4 chunks of 8 bf16 (hi and lo)
+      const int pix = nt * kUmmaM + pt;
       const float* src = a.proto + (size_t)b * kUmmaP * HW + pix;
       float f[kUmmaP];
 #pragma unroll
@@ -264,46 +279,44 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
         split_bf16x2(f[8 * c + 2], f[8 * c + 3], qh.y, ql.y);
         split_bf16x2(f[8 * c + 4], f[8 * c + 5], qh.z, ql.z);
         split_bf16x2(f[8 * c + 6], f[8 * c + 7], qh.w, ql.w);
-        *reinterpret_cast<uint4*>(sm->b[bs][0] + sw64_offset(pt, c)) = qh;
-        *reinterpret_cast<uint4*>(sm->b[bs][1] + sw64_offset(pt, c)) = ql;
+        *reinterpret_cast<uint4*>(sm->a[st][0] + sw64_offset(pt, c)) = qh;
+        *reinterpret_cast<uint4*>(sm->a[st][1] + sw64_offset(pt, c)) = ql;
       }
-      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
-      mbar_arrive(&sm->b_full[bs]);
-      ++fills[bs];
-      bs ^= 1;
+      fence_proxy_async();  // generic-proxy writes (A, and B / bounds at a frame change) -> visible to the async proxy
+      mbar_arrive(&sm->a_full[st]);
+      ++fills[st];
+      st ^= 1;
     }
   } else if (lane == 0) {
     // ======================================= MMA issuer =======================================
-    const uint32_t idesc = umma_idesc_bf16_m128_n256();
     uint32_t fills[2] = {0, 0}, uses[2] = {0, 0};
-    int bs = 0, as = 0;
+    int st = 0, as = 0, rows_frame = -1, n_rows = 0;
     for (long long u = u0; u < u1; ++u) {
-      const int b = (int)(u / n_tiles_n);
-      const int mt = frame_mtiles(a, b, m_base);
-      if (mt == 0) continue;
-      mbar_wait(&sm->b_full[bs], fills[bs] & 1u);
-      tc_fence_after();
-      for (int m = 0; m < mt; ++m) {
-        if (uses[as] > 0) {
-          mbar_wait(&sm->acc_empty[as], (uses[as] - 1) & 1u);
-          tc_fence_after();
-        }
-        const uint32_t d = tmem + (uint32_t)(as * kUmmaN);
-#pragma unroll
-        for (int k = 0; k < kUmmaP / 16; ++k) {  // K = 16 bf16 = 32 bytes per instruction, inside the 64-byte rows
-          const uint64_t ah = umma_desc_k_sw64(sm->a[0][m], k * 32), al = umma_desc_k_sw64(sm->a[1][m], k * 32);
-          const uint64_t bh = umma_desc_k_sw64(sm->b[bs][0], k * 32), bl = umma_desc_k_sw64(sm->b[bs][1], k * 32);
-          tc_mma_bf16(d, al, bh, idesc, k > 0);  // small terms first
-          tc_mma_bf16(d, ah, bl, idesc, 1u);
-          tc_mma_bf16(d, ah, bh, idesc, 1u);
-        }
-        tc_commit(&sm->acc_full[as]);  // arrives when the MMAs above are complete
-        ++uses[as];
-        as ^= 1;
+      const int b = (int)(u / n_tiles);
+      if (b != rows_frame) {
+        n_rows = frame_rows(a, b, m_base);
+        rows_frame = b;
       }
-      tc_commit(&sm->b_empty[bs]);  // ... and this one when the B stage (and A) are no longer being read
-      ++fills[bs];
-      bs ^= 1;
+      if (n_rows == 0) continue;
+      const uint32_t idesc = umma_idesc_bf16_m128((n_rows + 15) & ~15);
+      mbar_wait(&sm->a_full[st], fills[st] & 1u);
+      if (uses[as] > 0) mbar_wait(&sm->acc_empty[as], (uses[as] - 1) & 1u);
+      tc_fence_after();
+      const uint32_t d = tmem + (uint32_t)(as * kUmmaNMax);
+#pragma unroll
+      for (int k = 0; k < kUmmaP / 16; ++k) {  // K = 16 bf16 = 32 bytes per instruction, inside the 64-byte rows
+        const uint64_t ah = umma_desc_k_sw64(sm->a[st][0], k * 32), al = umma_desc_k_sw64(sm->a[st][1], k * 32);
+        const uint64_t bh = umma_desc_k_sw64(sm->b[0], k * 32), bl = umma_desc_k_sw64(sm->b[1], k * 32);
+        tc_mma_bf16(d, al, bh, idesc, k > 0);  // small terms first
+        tc_mma_bf16(d, ah, bl, idesc, 1u);
+        tc_mma_bf16(d, ah, bh, idesc, 1u);
+      }
+      tc_commit(&sm->acc_full[as]);  // arrives when the MMAs above are complete ...
+      tc_commit(&sm->a_empty[st]);   // ... and so does this one: the A stage may be refilled
+      ++uses[as];
+      as ^= 1;
+      ++fills[st];
+      st ^= 1;
     }
   }
 
@@ -323,10 +336,10 @@ static int launch_mask_umma(const MaskArgs& a, int B, int max_rows, cudaStream_t
   const size_t smem = sizeof(UmmaSmem) + 1024;
   TAUV_CUDA(cudaFuncSetAttribute(mask_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int HW = a.H * a.W;
-  const long long units = (long long)B * ((HW + kUmmaN - 1) / kUmmaN);
+  const long long units = (long long)B * ((HW + kUmmaM - 1) / kUmmaM);
   long long grid = num_sms();
   if (grid > units) grid = units;
-  for (int m_base = 0; m_base < max_rows; m_base += kUmmaMaxMTiles * kUmmaM) {
+  for (int m_base = 0; m_base < max_rows; m_base += kUmmaNMax) {
     mask_umma_kernel<<<(unsigned)grid, kUmmaThreads, smem, st>>>(a, B, m_base);
     TAUV_LAUNCH_CHECK("mask_umma_kernel");
   }
