@@ -170,11 +170,12 @@ def _depth_view(depth: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 
 def decode_packed(prediction, model_config, n_detections: int, score_threshold: float,
-                  stage_events=None) -> PackedDetections:
+                  stage_events=None, out: Optional[PackedDetections] = None) -> PackedDetections:
     """Device part of ``decode``: two kernel launches, no synchronisation, permuted views taken as-is.
 
     ``stage_events`` (profiling hook): three ``torch.cuda.Event(enable_timing=True)`` recorded on the current
-    stream before the tile kernel, between the two kernels, and after the merge kernel."""
+    stream before the tile kernel, between the two kernels, and after the merge kernel.
+    ``out``: a PackedDetections from an earlier call with the same shapes, to be overwritten (no allocation)."""
     hm = prediction.heatmap
     dev = _lib.require_cuda(hm, prediction.size, prediction.offset, prediction.depth)
     hm = _as_heatmap(hm)
@@ -186,13 +187,19 @@ def decode_packed(prediction, model_config, n_detections: int, score_threshold: 
     if k > C * H * W:
         raise RuntimeError(f"selected index k out of range (k={k} > {C * H * W})")
     lib = _lib.load()
-    index = torch.empty((B, k, 2), dtype=torch.int64, device=dev)
-    label = torch.empty((B, k), dtype=torch.int64, device=dev)
-    score = torch.empty((B, k), dtype=torch.float32, device=dev)
-    yx = torch.empty((B, k, 2), dtype=torch.float64, device=dev)
-    hw = torch.empty((B, k, 2), dtype=torch.float32, device=dev)
-    depth_out = torch.empty((B, k), dtype=torch.float32, device=dev) if depth is not None else None
-    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    if out is not None:
+        index, label, score, yx, hw, depth_out, count = (out.index, out.label, out.score, out.yx, out.hw, out.depth,
+                                                         out.count)
+        if tuple(index.shape) != (B, k, 2) or (depth is not None) != (depth_out is not None):
+            raise ValueError("`out` does not match this call's shapes")
+    else:
+        index = torch.empty((B, k, 2), dtype=torch.int64, device=dev)
+        label = torch.empty((B, k), dtype=torch.int64, device=dev)
+        score = torch.empty((B, k), dtype=torch.float32, device=dev)
+        yx = torch.empty((B, k, 2), dtype=torch.float64, device=dev)
+        hw = torch.empty((B, k, 2), dtype=torch.float32, device=dev)
+        depth_out = torch.empty((B, k), dtype=torch.float32, device=dev) if depth is not None else None
+        count = torch.empty((B,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         nbytes = lib.tauv_heatmap_topk_workspace_bytes(B, C, H, W, k)
         ws = _lib.workspace(dev, nbytes)

@@ -25,13 +25,17 @@ def _i64(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous() if t.dtype == torch.int64 else t.to(torch.int64).contiguous()
 
 
-def generate_heatmap(truth, model_config, train_config, object_config) -> torch.Tensor:
-    """[B, n_labels, out_h, out_w] Gaussian class heatmap   — reference loss.py:31-72."""
+def generate_heatmap(truth, model_config, train_config, object_config, out: torch.Tensor = None) -> torch.Tensor:
+    """[B, n_labels, out_h, out_w] Gaussian class heatmap   — reference loss.py:31-72.
+    ``out`` (optional, beyond the reference signature): a contiguous fp32 tensor of that shape to overwrite."""
     dev = _lib.require_cuda(truth.valid, truth.label, truth.center)
     B, n = truth.valid.shape
     C = int(object_config.n_labels)
     H, W = int(model_config.out_h), int(model_config.out_w)
-    out = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (B, C, H, W) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("`out` must be a contiguous fp32 [B, n_labels, out_h, out_w] tensor")
     valid, label, center = _u8(truth.valid), _i64(truth.label), _lib.f32c(truth.center)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().tauv_gaussian_encode(

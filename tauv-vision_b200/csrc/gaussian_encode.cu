@@ -51,23 +51,48 @@ __global__ void __launch_bounds__(kEncThreads) gaussian_encode_kernel(
   const long long b = plane / C;
   if (tid == 0) { s_n = 0; s_big = 0; }
   __syncthreads();
-  for (int o = tid; o < n_objects; o += kEncThreads) {
+  // the frame's objects that render into this plane: the loads are issued now ...
+  bool mine = false;
+  int cy = 0, cx = 0;
+  if (tid < n_objects) {
+    const long long i = b * n_objects + tid;
+    if (valid[i] && label[i] == c) {
+      mine = true;
+      cy = grid_floor(center[i * 2 + 0], in_h, ratio);
+      cx = grid_floor(center[i * 2 + 1], in_w, ratio);
+    }
+  }
+  const int y0 = band * rows_per_band;
+  const int y1 = min(H, y0 + rows_per_band);
+  float* op = out + (size_t)plane * H * W;
+  // ... and while they are in flight the band is zero-filled unconditionally: four planes out of five hold no
+  // object at all, and for the rest the second write below lands on lines that are still in L2.
+  if (VEC) {
+    const int total = (y1 - y0) * (W >> 2);
+    float4* o4 = reinterpret_cast<float4*>(op + (size_t)y0 * W);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = tid; t < total; t += kEncThreads) o4[t] = z;
+  }
+  if (mine) {
+    const int slot = atomicAdd(&s_n, 1);
+    s_obj[2 * slot] = cy;
+    s_obj[2 * slot + 1] = cx;
+    if (abs(cy) > 20000 || abs(cx) > 20000) s_big = 1;
+  }
+  for (int o = tid + kEncThreads; o < n_objects; o += kEncThreads) {  // (more than 256 objects per frame: rare)
     const long long i = b * n_objects + o;
     if (valid[i] && label[i] == c) {
-      const int cy = grid_floor(center[i * 2 + 0], in_h, ratio);
-      const int cx = grid_floor(center[i * 2 + 1], in_w, ratio);
+      const int oy = grid_floor(center[i * 2 + 0], in_h, ratio);
+      const int ox = grid_floor(center[i * 2 + 1], in_w, ratio);
       const int slot = atomicAdd(&s_n, 1);
-      s_obj[2 * slot] = cy;
-      s_obj[2 * slot + 1] = cx;
-      if (abs(cy) > 20000 || abs(cx) > 20000) s_big = 1;
+      s_obj[2 * slot] = oy;
+      s_obj[2 * slot + 1] = ox;
+      if (abs(oy) > 20000 || abs(ox) > 20000) s_big = 1;
     }
   }
   __syncthreads();
   const int n = s_n;
   const bool big = s_big != 0 || H > 10000 || W > 10000;
-  const int y0 = band * rows_per_band;
-  const int y1 = min(H, y0 + rows_per_band);
-  float* op = out + (size_t)plane * H * W;
 
   auto value = [&](int y, int x) -> float {
     if (!big) {
@@ -91,10 +116,7 @@ __global__ void __launch_bounds__(kEncThreads) gaussian_encode_kernel(
     const int S = W >> 2;
     const int total = (y1 - y0) * S;
     float4* o4 = reinterpret_cast<float4*>(op + (size_t)y0 * W);
-    if (n == 0) {
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int t = tid; t < total; t += kEncThreads) o4[t] = z;
-    } else {
+    if (n != 0) {
       for (int t = tid; t < total; t += kEncThreads) {
         const int y = y0 + t / S;
         const int x = (t % S) << 2;
