@@ -70,7 +70,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(src: Path) -> Path:
         obj = OBJ_DIR / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("TAUV_EXTRA_NVCC", "").split(), "-I", str(INCLUDE), "-c", str(src),
+               "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

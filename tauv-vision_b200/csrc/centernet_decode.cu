@@ -20,6 +20,10 @@
 //      and (optionally) gathers size/offset/depth and does the box arithmetic.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
 namespace tauv {
 
 constexpr int kTileThreads = 256;
@@ -33,11 +37,11 @@ struct TopkPlan {
   int rows_per_item;
   int items_per_plane;
   int items_per_frame;  // C * items_per_plane
+  int rows_per_frame;   // rows of the candidate table per frame: max(items_per_frame, cluster size)
   int cap;              // candidate-list capacity (entries)
   int soft;             // overflow-safe path: prune when the list grows beyond this
   int sub_elems;        // overflow-safe path: elements per sub-step (cap - soft)
   int vec;              // 1: 128-bit loads, 0: scalar loads (W % 4 != 0 or unaligned base)
-  int tile_floats;      // shared-memory staging tile of the bootstrap round (0: none)
   size_t smem_bytes;
   size_t cand_bytes, count_bytes, state_bytes;
 };
@@ -60,12 +64,11 @@ static int make_plan(int B, int C, int H, int W, int k, const void* ptr, TopkPla
   p->soft = 2 * k;
   p->cap = 4 * k > 2560 ? 4 * k : 2560;
   p->sub_elems = ((p->cap - p->soft) / 4) * 4;
-  // bootstrap tile: one round of rows plus halo, staged in shared memory (only for W <= 512; wider maps use the
-  // global-memory path for the bootstrap round too)
-  p->tile_floats = (p->vec && W <= 512) ? 16 * kTileThreads + 3 * W : 0;
-  p->smem_bytes = (size_t)p->cap * 8 + kRadixBins * 4 + (size_t)p->tile_floats * 4;
-  p->cand_bytes = align_up((size_t)B * p->items_per_frame * (size_t)k * 8, 256);
-  p->count_bytes = align_up((size_t)B * p->items_per_frame * 4, 256);
+  p->smem_bytes = (size_t)p->cap * 8 + kRadixBins * 4;
+  // one row per item (scalar path) or per (unit, CTA) (cluster path: at most max(items, 8) per frame)
+  p->rows_per_frame = p->items_per_frame > 8 ? p->items_per_frame : 8;
+  p->cand_bytes = align_up((size_t)B * p->rows_per_frame * (size_t)k * 8, 256);
+  p->count_bytes = align_up((size_t)B * p->rows_per_frame * 4, 256);
   p->state_bytes = align_up((size_t)B * kFrameStateWords * 4, 256);
   return 0;
 }
@@ -76,8 +79,8 @@ static int make_plan(int B, int C, int H, int W, int k, const void* ptr, TopkPla
 struct TileArgs {
   const float* hm;
   int B, C, H, W, k;
-  int rows_per_item, items_per_plane;
-  int cap, soft, sub_elems, tile_floats;
+  int rows_per_item, items_per_plane, rows_per_frame;
+  int cap, soft, sub_elems;
   unsigned long long* cand;  // [B*items_per_frame][k]
   int* cand_count;           // [B*items_per_frame]
   uint32_t* frame_state;     // [B][kFrameStateWords], zeroed before the launch
@@ -121,6 +124,7 @@ struct __align__(16) TileCtx {
   int n_conv;              // list[0, n_conv) already hold final sort keys (SIGMOID_PEAK)
   int n_boot;              // list[0, n_boot) are already counted in the frame histogram (-1: order lost, count nothing more)
   uint32_t emit, maxbin;
+  int nhot;                // deferred peak tests queued in the hot list (cluster kernel)
   int flags;               // bit 1 = the list overflowed
   int base, wsum[kTileThreads / 32];
   uint32_t sel[4];
@@ -135,7 +139,15 @@ __device__ __forceinline__ int push_entry(const TileArgs& a, TileCtx* ctx, unsig
                                           uint32_t flat) {
   const unsigned long long pre = make_composite(float_to_key(x), flat);
   if (pre < ctx->thr) return 0;
-  const int slot = atomicAdd(&ctx->count, 1);
+  // one shared-memory atomic per warp instruction instead of one per lane (same-address atomics serialise: in the
+  // bootstrap round, where a ninth of all cells push, they were most of the round's time)
+  const unsigned active = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(active) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(&ctx->count, __popc(active));
+  base = __shfl_sync(active, base, leader);
+  const int slot = base + __popc(active & ((1u << lane) - 1u));
   if (slot >= a.cap) return 2;
   list[slot] = pre;
   return 0;
@@ -453,148 +465,6 @@ __device__ __noinline__ void finish_item(const TileArgs& a, TileCtx* ctx, unsign
   if (tid < 32 && ctx->base > 0) frame_republish<MODE>(a, ctx, fstate, (uint32_t)ctx->base, false);
 }
 
-// ----------------------------------------------------------------------------------------------
-// K0: seed the per-frame rejection threshold from a sample
-// ----------------------------------------------------------------------------------------------
-// One CTA per frame: the full peak test on a small sample of the frame (a few tiles of rows taken from planes spread
-// over the classes, 0.6 % of the batch at the headline shape, staged in shared memory with all loads in flight at
-// once), a histogram of the sampled peaks' keys, and the lower edge of the bin holding the k-th best becomes the
-// frame's first published threshold: at least k genuine peaks of the frame are known to lie at or above it, so
-// nothing below it can be in the frame's top-k.  With it every item of the main kernel streams from its first
-// cell instead of testing every cell until the first items have finished.
-constexpr int kSeedThreads = 256;
-constexpr int kSeedTileElems = 4096;
-
-// grid = (n_tiles, B): one CTA per sampled tile.  Peaks go into the frame's bins in global memory; the CTA that
-// finishes last for a frame (ticket in frame_state[3]) scans the bins, publishes the key and zeroes bins and ticket
-// again, so the main kernel starts from an empty histogram and never counts a cell twice.
-template <int MODE>
-__global__ void __launch_bounds__(kSeedThreads) seed_threshold_kernel(const __grid_constant__ TileArgs a, int tile_rows) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int W = a.W, H = a.H;
-  float* tile = reinterpret_cast<float*>(smem_raw);
-  uint32_t* lbins = reinterpret_cast<uint32_t*>(smem_raw + (size_t)(tile_rows + 2) * a.W * 4);  // CTA-local bins
-  __shared__ uint32_t warp_tot[kSeedThreads / 32];
-  __shared__ int s_found, s_last;
-  const int tid = threadIdx.x;
-  const int frame = blockIdx.y, s = blockIdx.x, n_tiles = gridDim.x;
-  for (int i = tid; i < kFrameBins; i += kSeedThreads) lbins[i] = 0;
-  uint32_t* fstate = a.frame_state + (size_t)frame * kFrameStateWords;
-  const float NI = TAUV_NEG_INF;
-
-  // tile s -> (class, row block): spread over the classes first, then over the row blocks
-  const int row_blocks = (H + tile_rows - 1) / tile_rows;
-  const int per_rb = (n_tiles + row_blocks - 1) / row_blocks;
-  const int rbk = s / per_rb, jj = s - rbk * per_rb;
-  const int c = (int)(((long long)jj * a.C) / per_rb);
-  const int ra = min(rbk, row_blocks - 1) * tile_rows, rb = min(ra + tile_rows, H);
-  const int la = max(ra - 1, 0), lb = min(rb + 1, H);
-  const float* src = a.hm + (((size_t)frame * a.C + c) * H + la) * W;
-  const int n4 = ((lb - la) * W) >> 2;
-  for (int t = tid; t < n4; t += kSeedThreads)
-    reinterpret_cast<float4*>(tile)[t] = ldg_stream4(src + ((size_t)t << 2));
-  if (tid == 0) s_found = -1;
-  __syncthreads();
-
-  const int S = W >> 2;
-  for (int t = tid; t < (rb - ra) * S; t += kSeedThreads) {
-    const int ri = t / S, col = (t - ri * S) << 2;
-    const int r = ra + ri;
-    const float* p1 = tile + (r - la) * W + col;
-    const float4 x = *reinterpret_cast<const float4*>(p1);
-    const float xs[4] = {x.x, x.y, x.z, x.w};
-    if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
-      const bool hl = col > 0, hr = col + 4 < W;
-      float4 u = make_float4(NI, NI, NI, NI), d = u;
-      float ul = NI, ur = NI, dl = NI, dright = NI;
-      if (r > 0) {
-        u = *reinterpret_cast<const float4*>(p1 - W);
-        if (hl) ul = p1[-W - 1];
-        if (hr) ur = p1[-W + 4];
-      }
-      if (r + 1 < H) {
-        d = *reinterpret_cast<const float4*>(p1 + W);
-        if (hl) dl = p1[W - 1];
-        if (hr) dright = p1[W + 4];
-      }
-      const float ml = hl ? p1[-1] : NI, mr = hr ? p1[4] : NI;
-      float cm[6];
-      cm[0] = fmaxf(fmaxf(ul, ml), dl);
-      cm[1] = fmaxf(fmaxf(u.x, x.x), d.x);
-      cm[2] = fmaxf(fmaxf(u.y, x.y), d.y);
-      cm[3] = fmaxf(fmaxf(u.z, x.z), d.z);
-      cm[4] = fmaxf(fmaxf(u.w, x.w), d.w);
-      cm[5] = fmaxf(fmaxf(ur, mr), dright);
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        // a logit >= its 3x3 neighbourhood is a peak of the suppressed map whatever the sigmoid's rounding; below
-        // -80 the sigmoid may underflow to a zero score, which is not a candidate: leave those out
-        const float m = fmaxf(fmaxf(cm[cc], cm[cc + 1]), cm[cc + 2]);
-        if (xs[cc] >= m && xs[cc] > -80.0f) atomicAdd(&lbins[float_to_key(xs[cc]) >> 20], 1u);
-      }
-    } else {
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) atomicAdd(&lbins[float_to_key(xs[cc]) >> 20], 1u);
-    }
-  }
-  __syncthreads();
-  // one global atomic per occupied bin instead of one per peak (the peaks of a tile share a dozen bins)
-  for (int i = tid; i < kFrameBins; i += kSeedThreads)
-    if (lbins[i]) atomicAdd(fstate + 4 + i, lbins[i]);
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(fstate + 3, 1u) == (uint32_t)n_tiles - 1u);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-
-  // the frame's last tile: highest bin b with count(bins >= b) >= k  (thread t owns bins [16t, 16t+16))
-  constexpr int BPT = kFrameBins / kSeedThreads;
-  uint32_t local[BPT], mine = 0;
-#pragma unroll
-  for (int j = 0; j < BPT; ++j) {
-    local[j] = *reinterpret_cast<volatile uint32_t*>(fstate + 4 + tid * BPT + j);
-    mine += local[j];
-  }
-  uint32_t suf = mine;
-  const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t v = __shfl_down_sync(0xffffffffu, suf, o);
-    if (lane + o < 32) suf += v;
-  }
-  if (lane == 0) warp_tot[warp] = suf;
-  __syncthreads();
-  for (int w = warp + 1; w < kSeedThreads / 32; ++w) suf += warp_tot[w];
-  const uint32_t above = suf - mine, k = (uint32_t)a.k;
-  if (above < k && suf >= k) {
-    uint32_t acc = above;
-#pragma unroll
-    for (int j = BPT - 1; j >= 0; --j) {
-      acc += local[j];
-      if (acc >= k) {
-        s_found = tid * BPT + j;
-        break;
-      }
-    }
-  }
-  // leave the bins and the ticket as the main kernel expects them: empty
-#pragma unroll
-  for (int j = 0; j < BPT; ++j)
-    if (local[j]) fstate[4 + tid * BPT + j] = 0u;
-  __syncthreads();
-  if (tid == 0) {
-    fstate[3] = 0u;
-    if (s_found > 0) {
-      const float edge = key_to_float((uint32_t)s_found << 20);  // lowest value of the bin
-      uint32_t key;
-      if (MODE == TAUV_TOPK_SIGMOID_PEAK) key = reject_key_for_score(sigmoid_ref(edge));
-      else key = (uint32_t)s_found << 20;
-      if (key) fstate[0] = key;
-    }
-  }
-}
-
 // One CTA per item.  Block index -> item interleaves the frames (consecutive blocks are different frames), so the
 // first items of EVERY frame finish early and publish a threshold for the frame's other items.
 template <int MODE, bool VEC>
@@ -609,7 +479,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(const __grid_co
   const int items_per_frame = a.C * a.items_per_plane;
   const int item_in_frame = blockIdx.x / a.B;
   const int frame = blockIdx.x - item_in_frame * a.B;
-  const int item = frame * items_per_frame + item_in_frame;
+  const int item = frame * a.rows_per_frame + item_in_frame;  // row of the candidate table
   const int c_in_frame = item_in_frame / a.items_per_plane;
   const int ip = item_in_frame - c_in_frame * a.items_per_plane;
   const int r0 = ip * a.rows_per_item;
@@ -635,61 +505,8 @@ __global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(const __grid_co
   __syncthreads();
 
   const int e0 = r0 * a.W, e1 = r1 * a.W;
-  int es = e0;
-  constexpr int kRound = 16 * kTileThreads;  // elements per round of four 128-bit loads per thread
-  if (VEC && ctx->thr == 0ull && e1 - e0 > kRound) {
-    // Bootstrap: the frame has published nothing yet.  Every cell of the first round gets the full peak test —
-    // from a shared-memory copy of the rows when it fits, so the dependent neighbour loads cost tens of cycles
-    // instead of hundreds — and every peak found goes straight into the frame's bins.  All items that start
-    // without a threshold do this at the same time, so a few microseconds into the kernel the frame knows the
-    // k-th best of several thousand peaks and every item of the frame switches to streaming.
-    es = e0 + kRound;
-    // The bootstrap round is a chain of latencies (tile load, peak tests, atomics, bin scan) during which this
-    // CTA asks nothing of HBM: have the rest of the item pulled into L2 meanwhile, so the rounds that follow
-    // stream from L2 and the memory pipe stays busy.
-    for (int line = tid; line * 32 < e1 - es; line += kTileThreads)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(plane + es + line * 32));
-    int fl0 = 0;
-    if (a.tile_floats) {
-      float* tile = reinterpret_cast<float*>(smem_raw + (size_t)a.cap * 8 + kRadixBins * 4);
-      const int la = max(r0 - 1, 0), lb = min((es + a.W - 1) / a.W + 1, a.H);
-      const int n4 = ((lb - la) * a.W) >> 2;
-      const float* src = plane + (size_t)la * a.W;
-      for (int t = tid; t < n4; t += kTileThreads)
-        reinterpret_cast<float4*>(tile)[t] = ldg_stream4(src + ((size_t)t << 2));
-      __syncthreads();
-#pragma unroll 1
-      for (int t = (e0 >> 2) + tid; t < (es >> 2); t += kTileThreads)
-        fl0 |= examine<MODE, VEC, true>(a, ctx, list, tile, plane_flat0, t << 2, la * a.W);
-    } else {
-      fl0 = scan_elems<MODE, VEC>(a, ctx, list, plane, plane_flat0, e0, es);
-    }
-    if (fl0) atomicOr(&ctx->flags, fl0);
-    if (tid == 0) ctx->maxbin = 0;
-    __syncthreads();
-    if (!(ctx->flags & 2)) {
-      const int nb = ctx->count;
-      uint32_t my_maxbin = 0;
-      for (int i = tid; i < nb; i += kTileThreads) {
-        // (SIGMOID_PEAK: the entries still carry logit keys, which is the space the bins live in)
-        const uint32_t bin = composite_key(list[i]) >> 20;
-        atomicAdd(fstate + 4 + bin, 1u);
-        my_maxbin = max(my_maxbin, bin);
-      }
-      if (my_maxbin) atomicMax(&ctx->maxbin, my_maxbin);
-      __syncthreads();
-      if (tid < 32 && nb > 0) {
-        const uint32_t key = frame_republish<MODE>(a, ctx, fstate, (uint32_t)nb, true);
-        if (tid == 0) {
-          ctx->n_boot = nb;
-          set_thr(ctx, (unsigned long long)key << 32);
-        }
-      }
-      __syncthreads();
-    }
-  }
   if (a.trace && tid == 0) tr[1] = now();
-  const int fl = scan_elems<MODE, VEC>(a, ctx, list, plane, plane_flat0, es, e1, fstate);
+  const int fl = scan_elems<MODE, VEC>(a, ctx, list, plane, plane_flat0, e0, e1, fstate);
   if (fl) atomicOr(&ctx->flags, fl);
   if (tid == 0) asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
@@ -707,6 +524,577 @@ __global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(const __grid_co
   if (a.trace && tid == 0) {
     tr[3] = now();
     for (int i = 0; i < 4; ++i) a.trace[(size_t)blockIdx.x * 8 + i] = tr[i];
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K1 (vectorised path): one thread-block cluster per "unit" (a frame, or a contiguous share of a frame's items)
+// ----------------------------------------------------------------------------------------------
+// The rejection threshold of a unit and the candidate histogram it is derived from live in the DISTRIBUTED SHARED
+// MEMORY of the cluster that owns the unit — no global state, no memset, no separate seed launch:
+//   * bins: 8192 counters over the top 13 bits of the order-preserving key, 1024 per CTA (bin b lives in CTA b>>10);
+//     every CTA adds its candidates with remote shared-memory atomics;
+//   * thr_key: every CTA holds its own copy of the published rejection key; a publisher raises all eight copies with
+//     remote atomicMax, so the streaming loop reads the threshold from local shared memory;
+//   * next_item (rank 0): the unit's dynamic work queue.
+// Timeline of a unit: all eight CTAs load round 0 of their first item (4096 cells each) plus its halo rows, run the
+// full 3x3 peak test on it from a shared-memory tile (the only place every cell is tested), bin the peaks, and after
+// one cluster barrier each CTA derives the first threshold from the 8 x 4096-cell sample: at least k genuine peaks
+// of the frame lie at or above it, so nothing below it can be in the frame's top-k.  From then on the CTAs stream:
+// the loads of the next round — of this item or of the CTA's next item — are issued before the current round is
+// compared against the threshold, only strips that pass get the peak test (neighbours from L1/L2), and at the end of
+// every item its candidates go to the global candidate table and into the bins, from which the threshold is
+// republished whenever the unit's candidate count crosses k, 2k, 4k, ...
+constexpr int kClSize = 8;                            // CTAs per cluster (portable maximum)
+constexpr int kClBinShift = 19;                       // fine bin = key >> 19: sign + 8 exponent + 4 mantissa bits
+constexpr int kClWin = 1024;                          // bins per window (64 binades at 16 bins each)
+constexpr int kClBins = 2 * kClWin;                   // negative window + positive window
+constexpr int kClNegBase = 1536;                      // fine bins [1536, 2560): -2^33 .. -2^-31
+constexpr int kClPosBase = 5632;                      // fine bins [5632, 6656): +2^-31 .. +2^33
+#ifndef TAUV_ROUND_W
+#define TAUV_ROUND_W 3
+#endif
+#ifndef TAUV_SVC_ITEMS
+#define TAUV_SVC_ITEMS 4
+#endif
+constexpr int kRoundW = TAUV_ROUND_W;                            // 128-bit strips per thread and round (2 x kRoundW live in registers)
+constexpr int kRoundF4 = kRoundW * kTileThreads;      // 128-bit strips per round per CTA
+constexpr int kRoundElems = 4 * kRoundF4;             // cells per round
+constexpr int kClMaxW = 1016;                         // halo rows are held in two 128-bit registers per thread
+
+struct __align__(16) ClusterCtx {
+  uint32_t bins[kClBins];  // THIS CTA's candidates by window bin; a scan sums the eight CTAs' copies with remote loads
+  uint32_t thr_key;        // this CTA's copy of the unit's published rejection key
+  uint32_t maxbin;         // this CTA's copy of the highest occupied window bin of the unit
+  int next_item;           // rank 0 only: next unclaimed item of the unit (index inside the frame)
+};
+
+// Window bin of an order-preserving key.  The map is monotone and only ever moves a value DOWN (values between or
+// above the windows go to the top bin of the window below them), so "at least k candidates in bins >= b" still
+// certifies that k candidates are >= the lower edge of b.  Values below the negative window are not counted (-1).
+__device__ __forceinline__ int cl_window_bin(uint32_t key) {
+  const int b = (int)(key >> kClBinShift);
+  if (b >= kClPosBase) return kClWin + min(b - kClPosBase, kClWin - 1);
+  if (b >= kClNegBase) return min(b - kClNegBase, kClWin - 1);
+  return -1;
+}
+__device__ __forceinline__ float cl_window_edge(int wbin) {  // lowest value that maps to the bin
+  const int b = wbin >= kClWin ? wbin - kClWin + kClPosBase : wbin + kClNegBase;
+  return key_to_float((uint32_t)b << kClBinShift);
+}
+
+// Shared-memory layout of the cluster kernel (all dynamic, so that device functions reach it without pointer
+// arguments): [ClusterCtx | TileCtx | list[cap] | radix histogram | bootstrap tile / queue of deferred peak tests]
+constexpr int kClOffCtx = (int)((sizeof(ClusterCtx) + 15) / 16 * 16);
+constexpr int kClOffList = kClOffCtx + (int)((sizeof(TileCtx) + 15) / 16 * 16);
+__device__ __forceinline__ unsigned char* cl_smem() {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  return smem_raw;
+}
+__device__ __forceinline__ ClusterCtx* cl_cc() { return reinterpret_cast<ClusterCtx*>(cl_smem()); }
+__device__ __forceinline__ TileCtx* cl_ctx() { return reinterpret_cast<TileCtx*>(cl_smem() + kClOffCtx); }
+__device__ __forceinline__ unsigned long long* cl_list() { return reinterpret_cast<unsigned long long*>(cl_smem() + kClOffList); }
+__device__ __forceinline__ uint32_t* cl_hist(const TileArgs& a) {
+  return reinterpret_cast<uint32_t*>(cl_smem() + kClOffList + (size_t)a.cap * 8);
+}
+__device__ __forceinline__ float* cl_tile(const TileArgs& a) {
+  return reinterpret_cast<float*>(cl_smem() + kClOffList + (size_t)a.cap * 8 + kRadixBins * 4);
+}
+__device__ __forceinline__ int cl_hot_cap(const TileArgs& a) { return (kRoundElems + 2 * a.W + 8) / 2; }
+
+struct ItemGeom {
+  const float* plane;
+  uint32_t plane_flat0;
+  int e0, e1;  // element range inside the plane
+  int item;    // global item number (row of the candidate table)
+};
+
+__device__ __forceinline__ ItemGeom item_geom(const TileArgs& a, int frame, int iif) {
+  ItemGeom g;
+  g.item = frame * (a.C * a.items_per_plane) + iif;
+  const int c = iif / a.items_per_plane;
+  const int ip = iif - c * a.items_per_plane;
+  const int r0 = ip * a.rows_per_item;
+  const int r1 = min(a.H, r0 + a.rows_per_item);
+  g.plane = a.hm + ((size_t)frame * a.C + c) * a.H * a.W;
+  g.plane_flat0 = (uint32_t)c * (uint32_t)(a.H * a.W);
+  g.e0 = r0 * a.W;
+  g.e1 = r1 * a.W;
+  return g;
+}
+
+__device__ __forceinline__ void load_round(const ItemGeom& g, int r, float4 (&x)[kRoundW]) {
+  const int t1 = g.e1 >> 2;
+  const int tb = (g.e0 >> 2) + r * kRoundF4 + (int)threadIdx.x;
+#pragma unroll
+  for (int u = 0; u < kRoundW; ++u) {
+    const int t = tb + u * kTileThreads;
+    x[u] = (t < t1) ? ldg_stream4(g.plane + ((size_t)t << 2))
+                    : make_float4(TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF);
+  }
+}
+
+// pull a round into L2 without tying up registers (used where a function call sits between issue and use)
+__device__ __forceinline__ void prefetch_round_l2(const ItemGeom& g, int r) {
+  const int t1 = g.e1 >> 2;
+  const int tb = (g.e0 >> 2) + r * kRoundF4;
+  for (int line = (int)threadIdx.x; line < kRoundF4 / 8; line += kTileThreads) {  // 8 strips per 128-byte line
+    const int t = tb + line * 8;
+    if (t < t1) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.plane + ((size_t)t << 2)));
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ int cl_bin(unsigned long long c) {  // window bin of a FINAL sort key
+  if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
+    const float s = key_to_float(composite_key(c));
+    return cl_window_bin(float_to_key(logf(__fdiv_rn(s, __fsub_rn(1.0f, s)))));
+  }
+  return cl_window_bin(composite_key(c));
+}
+
+// Warp 0: scan the unit's histogram (the sum of the eight CTAs' local copies, read through distributed shared memory)
+// from the highest occupied bin downwards, find the highest bin b with count(bins >= b) >= k, and return the
+// rejection key of its lower edge (0: fewer than k candidates so far).  At most 512 bins are visited.
+template <int MODE>
+__device__ __forceinline__ uint32_t cl_scan_threshold(cg::cluster_group& cluster, ClusterCtx* cc, int k) {
+  const int lane = threadIdx.x & 31;
+  const int maxbin = (int)*reinterpret_cast<volatile uint32_t*>(&cc->maxbin);
+  uint32_t acc = 0;
+  int found = -1;
+  for (int it = 0; it < 16 && found < 0; ++it) {
+    const int bin = maxbin - it * 32 - lane;
+    uint32_t v = 0;
+    if (bin >= 0) {
+#pragma unroll
+      for (int r = 0; r < kClSize; ++r) v += *reinterpret_cast<volatile uint32_t*>(&cluster.map_shared_rank(cc, r)->bins[bin]);
+    }
+    uint32_t pre = v;  // inclusive prefix over lanes (lane 0 = highest bin)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += t;
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, acc + pre >= (uint32_t)k);
+    if (hit) found = maxbin - it * 32 - (__ffs(hit) - 1);
+    acc += __shfl_sync(0xffffffffu, pre, 31);
+    if (maxbin - (it + 1) * 32 < 0) break;
+  }
+  uint32_t key = 0;
+  if (lane == 0 && found >= 0) {
+    const float edge = cl_window_edge(found);
+    key = MODE == TAUV_TOPK_SIGMOID_PEAK ? reject_key_for_score(sigmoid_ref(edge)) : float_to_key(edge);
+  }
+  return __shfl_sync(0xffffffffu, key, 0);
+}
+
+// lanes 0..7 of one warp: raise every CTA's copy of a cluster-wide maximum
+__device__ __forceinline__ void cl_raise_all(cg::cluster_group& cluster, uint32_t* local_word, uint32_t v) {
+  const int lane = threadIdx.x & 31;
+  if (v && lane < kClSize) atomicMax(cluster.map_shared_rank(local_word, lane), v);
+}
+
+// Service step of a CTA (all threads; the caller has just passed a __syncthreads): run the queued peak tests of the
+// last few items against the latest threshold, add what is new in the list to this CTA's bins, and (warp 0) rescan
+// and republish the unit's threshold once the CTA has binned k/8 candidates since its last scan.
+constexpr int kSvcItems = TAUV_SVC_ITEMS;  // items between two service steps (bounds what an overflow has to redo)
+
+template <int MODE>
+__device__ __noinline__ void cl_service(const TileArgs& a, TileCtx* ctx, unsigned long long* list, uint32_t* hist,
+                                        const int2* hotq, int hot_cap, int frame, cg::cluster_group& cluster,
+                                        ClusterCtx* cc, int* since_scan, long long* trow) {
+  const int tid = threadIdx.x;
+  auto now = []() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; };
+  const int nq = min(ctx->nhot, hot_cap);
+  if (trow && tid == 0) { trow[1] = now(); trow[4] = nq; }
+  if (tid == 0) set_thr(ctx, (unsigned long long)(*reinterpret_cast<volatile uint32_t*>(&cc->thr_key)) << 32);
+  __syncthreads();
+  int fl = 0;
+#pragma unroll 1
+  for (int i = tid; i < nq; i += kTileThreads) {
+    const int2 q = hotq[i];
+    const ItemGeom g = item_geom(a, frame, q.x);
+    fl |= examine<MODE, true>(a, ctx, list, g.plane, g.plane_flat0, q.y);
+  }
+  if (fl) atomicOr(&ctx->flags, fl);
+  if (tid == 0) {
+    ctx->maxbin = 0;
+    ctx->base = 0;
+  }
+  __syncthreads();
+  if (trow && tid == 0) trow[6] = now();
+  if (tid == 0) ctx->nhot = 0;
+  if (ctx->flags & 2) return;  // the list overflowed: the caller redoes the affected items
+  const int n = ctx->count, nb = ctx->n_boot;
+  if (nb >= 0 && n > nb) {
+    // list[nb, n) are new and still carry logit keys (SIGMOID_PEAK), the space the bins live in
+    uint32_t my_maxbin = 0, mine = 0;
+    for (int i = nb + tid; i < n; i += kTileThreads) {
+      const uint32_t key = composite_key(list[i]);
+      if (MODE == TAUV_TOPK_SIGMOID_PEAK && !(key_to_float(key) > -80.0f)) continue;  // may underflow to score 0
+      const int bin = cl_window_bin(key);
+      if (bin < 0) continue;
+      atomicAdd(&cc->bins[bin], 1u);
+      my_maxbin = max(my_maxbin, (uint32_t)bin);
+      ++mine;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      my_maxbin = max(my_maxbin, __shfl_xor_sync(0xffffffffu, my_maxbin, o));
+      mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    }
+    if ((tid & 31) == 0 && mine) {
+      atomicMax(&ctx->maxbin, my_maxbin);
+      atomicAdd(&ctx->base, (int)mine);
+    }
+    __syncthreads();
+    if (tid == 0) ctx->n_boot = n;
+    if (tid < 32) {
+      if (ctx->maxbin > *reinterpret_cast<volatile uint32_t*>(&cc->maxbin)) cl_raise_all(cluster, &cc->maxbin, ctx->maxbin);
+      *since_scan += ctx->base;
+      const int every = a.k >= 8 ? a.k / 8 : 1;
+      if (*since_scan >= every) {
+        *since_scan = 0;
+        cl_raise_all(cluster, &cc->thr_key, cl_scan_threshold<MODE>(cluster, cc, a.k));
+      }
+    }
+  }
+  if (trow && tid == 0) trow[7] = now();
+  // keep the list far from its capacity (uniform: count is stable here)
+  if (n > a.cap / 2) {
+    __syncthreads();
+    prune_list<MODE>(a, ctx, list, hist);
+    if (tid == 0) ctx->n_boot = -1;  // order lost: this CTA adds nothing more to the bins
+    __syncthreads();
+  }
+}
+
+// The list overflowed while the items [recent[0..n_recent)) were being collected (plateaus, or no usable threshold):
+// drop what they contributed, prune the rest to the exact top-k, and redo those items in sub-steps that cannot
+// overflow, pruning whenever the list passes `soft`.
+template <int MODE>
+__device__ __noinline__ void cl_redo_items_safely(const TileArgs& a, TileCtx* ctx, unsigned long long* list,
+                                                  uint32_t* hist, int frame, const int* recent, int n_recent) {
+  __syncthreads();
+  const int tid = threadIdx.x;
+  // entries of the affected items, recognised by their flat index
+  uint32_t lo[kSvcItems + 1], hi[kSvcItems + 1];
+  for (int j = 0; j < n_recent; ++j) {
+    const ItemGeom g = item_geom(a, frame, recent[j]);
+    lo[j] = g.plane_flat0 + (uint32_t)g.e0;
+    hi[j] = g.plane_flat0 + (uint32_t)g.e1;
+  }
+  auto keep = [&](unsigned long long c) {
+    const uint32_t flat = composite_idx(c);
+    bool mine = false;
+    for (int j = 0; j < n_recent; ++j) mine |= (flat >= lo[j] && flat < hi[j]);
+    return !mine;
+  };
+  const int n = min(ctx->count, a.cap);
+  // the compaction is stable, so the converted prefix [0, n_conv) stays a prefix; count what survives of it
+  if (tid == 0) ctx->emit = 0;
+  __syncthreads();
+  for (int i = tid; i < ctx->n_conv; i += kTileThreads)
+    if (keep(list[i])) atomicAdd(&ctx->emit, 1u);
+  __syncthreads();
+  const int new_conv = (int)ctx->emit;
+  compact_list(ctx, list, n, keep);
+  if (tid == 0) {
+    ctx->count = ctx->base;
+    ctx->n_conv = new_conv;
+    ctx->n_boot = -1;  // this CTA adds nothing more to the bins
+    ctx->flags = 0;
+    ctx->nhot = 0;
+  }
+  __syncthreads();
+  if (ctx->count > a.soft) prune_list<MODE>(a, ctx, list, hist);
+  __syncthreads();
+  for (int j = 0; j < n_recent; ++j) {
+    const ItemGeom g = item_geom(a, frame, recent[j]);
+    for (int s0 = g.e0; s0 < g.e1; s0 += a.sub_elems) {
+      scan_elems<MODE, true>(a, ctx, list, g.plane, g.plane_flat0, s0, min(s0 + a.sub_elems, g.e1));
+      __syncthreads();
+      if (ctx->count > a.soft) prune_list<MODE>(a, ctx, list, hist);  // uniform: nobody pushes before the next barrier
+      __syncthreads();
+    }
+  }
+}
+
+// A run of `n_run` items of this CTA (iif, iif + 8, ...), the first one starting at round r_begin.  No barrier and no
+// call in here, and nothing but the streaming state is live, so the next round's four 128-bit loads stay in registers:
+// they are requested before the current round is compared against the threshold (of the same item, or round 0 of the
+// next item of the run).  Strips that pass are only QUEUED (their peak tests wait on neighbour loads from L2; done in
+// line they would stall the warp's streaming once per strip).  The round that follows the run is pulled into L2.
+template <int MODE>
+__device__ __noinline__ int cl_stream_run(const TileArgs& a, int frame, int iif, int n_run, int r_begin, int i_hi) {
+  const int tid = threadIdx.x;
+  TileCtx* const ctx = cl_ctx();
+  ClusterCtx* const cc = cl_cc();
+  int2* const hotq = reinterpret_cast<int2*>(cl_tile(a));
+  const int hot_cap = cl_hot_cap(a);
+  int fl = 0;
+  ItemGeom g = item_geom(a, frame, iif);
+  float4 xn[kRoundW];
+  {
+    const int rounds0 = ((g.e1 >> 2) - (g.e0 >> 2) + kRoundF4 - 1) / kRoundF4;
+    if (r_begin < rounds0) load_round(g, r_begin, xn);
+    else if (n_run > 1) load_round(item_geom(a, frame, iif + kClSize), 0, xn);
+  }
+#pragma unroll 1
+  for (int j = 0; j < n_run; ++j) {
+    const bool more = j + 1 < n_run;
+    const int t1 = g.e1 >> 2;
+    const int rounds = (t1 - (g.e0 >> 2) + kRoundF4 - 1) / kRoundF4;
+    if (a.trace && tid == 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      a.trace[(size_t)g.item * 8 + 0] = t;
+      a.trace[(size_t)g.item * 8 + 5] = composite_key(ctx->thr);
+    }
+#pragma unroll 1
+    for (int r = r_begin; r < rounds; ++r) {
+      float4 x[kRoundW];
+#pragma unroll
+      for (int u = 0; u < kRoundW; ++u) x[u] = xn[u];
+      if (r + 1 < rounds) load_round(g, r + 1, xn);
+      else if (more) load_round(item_geom(a, frame, iif + kClSize), 0, xn);
+      else if (iif + kClSize < i_hi) prefetch_round_l2(item_geom(a, frame, iif + kClSize), 0);
+      // pick up what the unit's CTAs have published meanwhile (local shared memory)
+      if (tid == 0) set_thr(ctx, (unsigned long long)(*reinterpret_cast<volatile uint32_t*>(&cc->thr_key)) << 32);
+      const float thr_f = *reinterpret_cast<volatile float*>(&ctx->thr_f);
+      const int tb = (g.e0 >> 2) + r * kRoundF4 + tid;
+      uint32_t hot = 0;
+#pragma unroll
+      for (int u = 0; u < kRoundW; ++u)
+        if (fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w)) >= thr_f && tb + u * kTileThreads < t1) hot |= 1u << u;
+#pragma unroll 1
+      while (hot) {
+        const int u = __ffs(hot) - 1;
+        hot &= hot - 1;
+        const int slot = atomicAdd(&ctx->nhot, 1);
+        if (slot < hot_cap) hotq[slot] = make_int2(iif, (tb + u * kTileThreads) << 2);
+        else fl = 2;  // queue full: treated like a list overflow, the items are redone safely
+      }
+    }
+    if (a.trace && tid == 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      a.trace[(size_t)g.item * 8 + 2] = t;
+    }
+    iif += kClSize;
+    r_begin = 0;
+    if (more) g = item_geom(a, frame, iif);
+  }
+  return fl;
+}
+
+// Bootstrap round of a unit: the full test on round 0 of this CTA's first item, from the shared-memory tile
+// (tile[0] = plane cell `origin`; cells outside the plane are never read).  Peaks go to the list and into the bins.
+template <int MODE>
+__device__ __noinline__ void cl_bootstrap_round(const TileArgs& a, TileCtx* ctx, unsigned long long* list,
+                                                uint32_t* hist, const float* tile, int origin, const ItemGeom& g,
+                                                cg::cluster_group& cluster, ClusterCtx* cc) {
+  const int tid = threadIdx.x;
+  const int c_end = min(g.e1, g.e0 + kRoundElems);
+  int fl = 0;
+  if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
+#pragma unroll 1
+    for (int u = 0; u < kRoundW; ++u) {
+      const int off = g.e0 + ((u * kTileThreads + tid) << 2);
+      if (off < c_end) fl |= examine<MODE, true, true>(a, ctx, list, tile, g.plane_flat0, off, origin);
+    }
+  } else {
+    // RAW: every cell is a candidate; keep this round's k best (exact selection straight from the tile)
+    const int n = c_end - g.e0;
+    auto load = [&](int i) { return make_composite(float_to_key(tile[g.e0 - origin + i]), g.plane_flat0 + (uint32_t)(g.e0 + i)); };
+    const unsigned long long T = block_kth_largest<kTileThreads>(load, n, a.k, hist, ctx->sel);
+    for (int i = tid; i < n; i += kTileThreads)
+      if (load(i) >= T) fl |= push_entry(a, ctx, list, tile[g.e0 - origin + i], g.plane_flat0 + (uint32_t)(g.e0 + i));
+  }
+  if (fl) atomicOr(&ctx->flags, fl);
+  if (tid == 0) ctx->maxbin = 0;
+  __syncthreads();
+  if (ctx->flags & 2) return;  // the list overflowed (plateaus): the item is redone safely later; nothing is binned now
+  const int nb = ctx->count;
+  uint32_t my_maxbin = 0;
+  for (int i = tid; i < nb; i += kTileThreads) {
+    // (SIGMOID_PEAK: the entries still carry logit keys, which is the space the bins live in; a logit below -80 may
+    // underflow to a zero score, which is no candidate)
+    const uint32_t key = composite_key(list[i]);
+    if (MODE == TAUV_TOPK_SIGMOID_PEAK && !(key_to_float(key) > -80.0f)) continue;
+    const int bin = cl_window_bin(key);
+    if (bin < 0) continue;
+    atomicAdd(&cc->bins[bin], 1u);
+    my_maxbin = max(my_maxbin, (uint32_t)bin);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) my_maxbin = max(my_maxbin, __shfl_xor_sync(0xffffffffu, my_maxbin, o));
+  if ((tid & 31) == 0 && my_maxbin) atomicMax(&ctx->maxbin, my_maxbin);
+  __syncthreads();
+  if (tid < 32) cl_raise_all(cluster, &cc->maxbin, ctx->maxbin);
+  if (tid == 0) ctx->n_boot = nb;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __grid_constant__ TileArgs a, int n_units,
+                                                                       int parts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  unsigned long long* list = cl_list();
+  uint32_t* hist = cl_hist(a);
+  float* tile = cl_tile(a);                    // [kRoundElems + 2W + 8]
+  int2* hotq = reinterpret_cast<int2*>(tile);  // the same memory after the bootstrap round: queued peak tests
+  const int hot_cap = cl_hot_cap(a);
+  __shared__ int s_recent[kSvcItems];
+  TileCtx* ctx = cl_ctx();
+  ClusterCtx* cc = cl_cc();
+  const int tid = threadIdx.x;
+  const int rank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / kClSize, ncl = gridDim.x / kClSize;
+  const int ipf = a.C * a.items_per_plane;
+  const int W = a.W;
+  auto now = []() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; };
+
+#pragma unroll 1
+  for (int unit = cid; unit < n_units; unit += ncl) {
+    const int frame = unit / parts, part = unit - frame * parts;
+    const int i_lo = (int)((long long)ipf * part / parts), i_hi = (int)((long long)ipf * (part + 1) / parts);
+    // items of a unit are dealt round-robin to the cluster's CTAs: this CTA takes i_lo + rank, + 8, + 16, ...
+    int iif = i_lo + rank;
+    bool have = iif < i_hi;
+    ItemGeom g = item_geom(a, frame, have ? iif : i_lo);
+    float4 xn[kRoundW];
+    // halo of round 0: plane cells [e0 - W, e0) and [c_end, c_end + W + 4), two 128-bit strips per thread at most
+    const int c_end = min(g.e1, g.e0 + kRoundElems);
+    const int origin = g.e0 - W;                 // plane cell held in tile[0] (may be negative: never read then)
+    const int plane_cells = a.H * W;
+    const int nh = W >> 2;                        // strips per halo row
+    float4 halo[2];
+    if (have) {
+      load_round(g, 0, xn);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int h = tid + j * kTileThreads;     // [0, nh): row above; [nh, 2nh+1): row below (+1 strip)
+        int cell = -1;
+        if (h < nh) cell = g.e0 - W + (h << 2);
+        else if (h < 2 * nh + 1) cell = c_end + ((h - nh) << 2);
+        halo[j] = (cell >= 0 && cell < plane_cells) ? ldg_stream4(g.plane + cell) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    // reset the unit's state while the loads are in flight
+    for (int i = tid; i < kClBins / 4; i += kTileThreads) reinterpret_cast<uint4*>(cc->bins)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+      cc->thr_key = 0u;
+      cc->maxbin = 0u;
+      ctx->count = 0;
+      ctx->n_conv = 0;
+      ctx->n_boot = 0;
+      ctx->nhot = 0;
+      ctx->flags = 0;
+      ctx->thr = 0ull;
+      ctx->thr_f = TAUV_NEG_INF;
+    }
+    cluster.sync();  // (1) every CTA's bins and words are ready (and nobody is still reading the previous unit's)
+
+    long long tr0 = 0;
+    if (a.trace && tid == 0) tr0 = now();
+    int r_begin = 0;
+    if (have) {
+      // ---- bootstrap: round 0 of the first item, every cell tested, from shared memory
+#pragma unroll
+      for (int u = 0; u < kRoundW; ++u) {
+        const int off = g.e0 + ((u * kTileThreads + tid) << 2);
+        if (off < c_end) *reinterpret_cast<float4*>(tile + (off - origin)) = xn[u];
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int h = tid + j * kTileThreads;
+        int cell = -1;
+        if (h < nh) cell = g.e0 - W + (h << 2);
+        else if (h < 2 * nh + 1) cell = c_end + ((h - nh) << 2);
+        if (cell >= 0 && cell < plane_cells) *reinterpret_cast<float4*>(tile + (cell - origin)) = halo[j];
+      }
+      __syncthreads();
+      if (a.trace && tid == 0) a.trace[(size_t)g.item * 8 + 1] = now();
+      // keep HBM busy underneath the bootstrap (into L2 only: registers would not survive the calls below)
+      if (c_end < g.e1) prefetch_round_l2(g, 1);
+      else if (iif + kClSize < i_hi) prefetch_round_l2(item_geom(a, frame, iif + kClSize), 0);
+      cl_bootstrap_round<MODE>(a, ctx, list, hist, tile, origin, g, cluster, cc);
+      if (a.trace && tid == 0) a.trace[(size_t)g.item * 8 + 6] = now();
+      r_begin = 1;
+    }
+    cluster.sync();  // (2) the sample of all eight CTAs is in their bins, the highest occupied bin is known everywhere
+    // first threshold: every CTA derives it for itself (warp 0, remote loads only; nothing to publish)
+    if (tid < 32) {
+      const uint32_t key = cl_scan_threshold<MODE>(cluster, cc, a.k);
+      if (tid == 0 && key) {
+        atomicMax(&cc->thr_key, key);
+        set_thr(ctx, (unsigned long long)(*reinterpret_cast<volatile uint32_t*>(&cc->thr_key)) << 32);
+      }
+    }
+    __syncthreads();
+    if (have && !(ctx->flags & 2) && ctx->thr != 0ull) {
+      // the bootstrap collected every peak of round 0; keep only what the first threshold lets through
+      // (stable, and all survivors are already in the bins)
+      const unsigned long long thr = ctx->thr;
+      compact_list(ctx, list, ctx->count, [&](unsigned long long c) { return c >= thr; });
+      if (tid == 0) {
+        ctx->count = ctx->base;
+        ctx->n_boot = ctx->base;
+      }
+      __syncthreads();
+    }
+    if (a.trace && tid == 0 && have) a.trace[(size_t)g.item * 8 + 7] = now();
+    int since_scan = 0;  // (warp 0) candidates this CTA has binned since its last scan
+
+    // ---- stream: runs of up to kSvcItems items (no barrier, no call inside a run), a service step after each
+    while (have) {
+      int n_run = (i_hi - iif + kClSize - 1) / kClSize;  // items this CTA still has in the unit
+      if (n_run > kSvcItems) n_run = kSvcItems;
+      if (tid == 0)
+        for (int j = 0; j < n_run; ++j) s_recent[j] = iif + j * kClSize;
+      const int fl = cl_stream_run<MODE>(a, frame, iif, n_run, r_begin, i_hi);
+      if (fl) atomicOr(&ctx->flags, fl);
+      __syncthreads();
+      cl_service<MODE>(a, ctx, list, hist, hotq, hot_cap, frame, cluster, cc, &since_scan,
+                       a.trace ? a.trace + (size_t)item_geom(a, frame, iif + (n_run - 1) * kClSize).item * 8 : nullptr);
+      if (ctx->flags & 2) cl_redo_items_safely<MODE>(a, ctx, list, hist, frame, s_recent, n_run);
+      __syncthreads();
+      if (a.trace && tid == 0) {
+        tr0 = now();
+        for (int j = 0; j < n_run; ++j) {
+          const size_t row = (size_t)item_geom(a, frame, iif + j * kClSize).item * 8;
+          a.trace[row + 3] = tr0;
+        }
+      }
+      iif += n_run * kClSize;
+      have = iif < i_hi;
+      r_begin = 0;
+    }
+
+    // ---- the CTA's candidates of the whole unit: exact top-k, one row of the candidate table
+    {
+      const int row = frame * a.rows_per_frame + part * kClSize + rank;
+      if (part == 0 && rank == 0)  // rows of the frame that no CTA owns hold no candidates
+        for (int r = parts * kClSize + tid; r < a.rows_per_frame; r += kTileThreads) a.cand_count[frame * a.rows_per_frame + r] = 0;
+      const int n = ctx->count;
+      if (n == 0) {
+        if (tid == 0) a.cand_count[row] = 0;
+      } else {
+        convert_entries<MODE>(ctx, list, n);
+        const unsigned long long T = block_kth_largest<kTileThreads>([&](int i) { return list[i]; }, n, a.k, hist, ctx->sel);
+        if (tid == 0) ctx->emit = 0;
+        __syncthreads();
+        unsigned long long* out = a.cand + (size_t)row * a.k;
+        for (int i = tid; i < n; i += kTileThreads) {
+          const unsigned long long c = list[i];
+          if (c >= T && c != 0ull) out[atomicAdd(&ctx->emit, 1u)] = c;
+        }
+        __syncthreads();
+        if (tid == 0) a.cand_count[row] = (int)ctx->emit;
+      }
+    }
+    cluster.sync();  // (3) nobody touches this unit's distributed state any more
   }
 }
 
@@ -976,8 +1364,8 @@ static int plan_and_check(const float* hm, int B, int C, int H, int W, int k, vo
                "workspace %zu < required %zu", ws_bytes, p->cand_bytes + p->count_bytes + p->state_bytes);
   TAUV_REQUIRE(p->smem_bytes <= 227 * 1024, TAUV_E_UNSUPPORTED, "tile needs %zu B shared memory", p->smem_bytes);
   a->hm = hm; a->B = B; a->C = C; a->H = H; a->W = W; a->k = k;
-  a->rows_per_item = p->rows_per_item; a->items_per_plane = p->items_per_plane;
-  a->cap = p->cap; a->soft = p->soft; a->sub_elems = p->sub_elems; a->tile_floats = p->tile_floats;
+  a->rows_per_item = p->rows_per_item; a->items_per_plane = p->items_per_plane; a->rows_per_frame = p->rows_per_frame;
+  a->cap = p->cap; a->soft = p->soft; a->sub_elems = p->sub_elems;
   a->cand = reinterpret_cast<unsigned long long*>(ws);
   a->cand_count = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws) + p->cand_bytes);
   a->frame_state = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(ws) + p->cand_bytes + p->count_bytes);
@@ -994,30 +1382,51 @@ static int run_stage1(const float* hm, int B, int C, int H, int W, int k, int mo
   TileArgs a;
   if (int e = plan_and_check(hm, B, C, H, W, k, ws, ws_bytes, &p, &a)) return e;
   const long long items = (long long)B * p.items_per_frame;
-  void (*kern)(const TileArgs) = nullptr;
-  if (mode == TAUV_TOPK_SIGMOID_PEAK) kern = p.vec ? tile_topk_kernel<1, true> : tile_topk_kernel<1, false>;
-  else kern = p.vec ? tile_topk_kernel<0, true> : tile_topk_kernel<0, false>;
-  TAUV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-  {
-    const char* dbg = getenv("TAUV_TILE_DEBUG");  // experiment hook: "keep" = reuse the previous call's thresholds
-    if (!(dbg && dbg[0] == 'k'))
-      TAUV_CUDA(cudaMemsetAsync(a.frame_state, 0, p.state_bytes, st));  // key 0 = "no threshold published yet"
+  if (!(p.vec && W <= kClMaxW)) {
+    // scalar path (W % 4 != 0, unaligned base) and very wide maps: one CTA per item against per-frame state in the
+    // workspace, zeroed here (key 0 = "no threshold published yet")
+    void (*kern)(const TileArgs) = nullptr;
+    if (mode == TAUV_TOPK_SIGMOID_PEAK) kern = p.vec ? tile_topk_kernel<1, true> : tile_topk_kernel<1, false>;
+    else kern = p.vec ? tile_topk_kernel<0, true> : tile_topk_kernel<0, false>;
+    TAUV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+    TAUV_CUDA(cudaMemsetAsync(a.cand_count, 0, p.count_bytes + p.state_bytes, st));  // (adjacent in the workspace)
+    kern<<<(unsigned)items, kTileThreads, p.smem_bytes, st>>>(a);
+    TAUV_LAUNCH_CHECK("tile_topk_kernel");
+    return 0;
   }
-  // seed thresholds from a sample (only worth a launch when a frame is much larger than the sample)
-  if (p.vec && B <= 65535 && (long long)C * H * W >= 16LL * 8 * kSeedTileElems) {
-    int tile_rows = kSeedTileElems / W;
-    if (tile_rows < 1) tile_rows = 1;
-    if (tile_rows > H) tile_rows = H;
-    const int n_tiles = 8;
-    const size_t ssmem = (size_t)(tile_rows + 2) * W * 4 + kFrameBins * 4;
-    void (*seed)(const TileArgs, int) =
-        mode == TAUV_TOPK_SIGMOID_PEAK ? seed_threshold_kernel<1> : seed_threshold_kernel<0>;
-    TAUV_CUDA(cudaFuncSetAttribute(seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
-    seed<<<dim3(n_tiles, B), kSeedThreads, ssmem, st>>>(a, tile_rows);
-    TAUV_LAUNCH_CHECK("seed_threshold_kernel");
+  // vectorised path: persistent clusters of 8 CTAs, one unit (a frame, or a share of a frame's items) at a time
+  void (*ck)(const TileArgs, int, int) = mode == TAUV_TOPK_SIGMOID_PEAK ? tile_cluster_kernel<1> : tile_cluster_kernel<0>;
+  const size_t csmem = (size_t)kClOffList + p.smem_bytes + (size_t)(kRoundElems + 2 * W + 8) * 4;
+  TAUV_REQUIRE(csmem <= 227 * 1024, TAUV_E_UNSUPPORTED, "tile needs %zu B shared memory", csmem);
+  TAUV_CUDA(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(kClSize);
+  cfg.blockDim = dim3(kTileThreads);
+  cfg.dynamicSmemBytes = csmem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kClSize;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int ncl = 0;  // clusters that are resident at once
+  TAUV_CUDA(cudaOccupancyMaxActiveClusters(&ncl, ck, &cfg));
+  TAUV_REQUIRE(ncl >= 1, TAUV_E_UNSUPPORTED, "no cluster of %d CTAs fits the device with %zu B shared memory", kClSize, csmem);
+  // units: whole frames when there are at least as many frames as clusters, otherwise every frame is split into
+  // `parts` contiguous shares of its items (each share keeps its own threshold; the merge kernel joins them)
+  int parts = 1;
+  if (B < ncl) {
+    parts = ncl / B;
+    const int by_items = p.items_per_frame / kClSize;
+    if (parts > by_items) parts = by_items;
+    if (parts < 1) parts = 1;
   }
-  kern<<<(unsigned)items, kTileThreads, p.smem_bytes, st>>>(a);
-  TAUV_LAUNCH_CHECK("tile_topk_kernel");
+  const long long n_units = (long long)B * parts;
+  const long long ncl_used = n_units < ncl ? n_units : ncl;
+  cfg.gridDim = dim3((unsigned)(ncl_used * kClSize));
+  TAUV_CUDA(cudaLaunchKernelEx(&cfg, ck, a, (int)n_units, parts));
   return 0;
 }
 
@@ -1029,16 +1438,16 @@ static int run_stage2(int B, int C, int H, int W, int k, int mode, int64_t* inde
   if (int e = plan_and_check(nullptr, B, C, H, W, k, ws, ws_bytes, &p, &a)) return e;
   int p2 = 1;
   while (p2 < k) p2 <<= 1;
-  long long pool_cap = (long long)p.items_per_frame * k;
+  long long pool_cap = (long long)p.rows_per_frame * k;
   if (pool_cap > 12288) pool_cap = 12288;
   const size_t msmem = (size_t)p2 * 8 + (size_t)pool_cap * 8 + (size_t)(kRadixBins > k ? kRadixBins : k) * 4;
   if (mode == TAUV_TOPK_SIGMOID_PEAK) {
     TAUV_CUDA(cudaFuncSetAttribute(merge_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-    merge_kernel<1><<<B, kMergeThreads, msmem, st>>>(a.cand, a.cand_count, p.items_per_frame, k, H, W, (int)pool_cap,
+    merge_kernel<1><<<B, kMergeThreads, msmem, st>>>(a.cand, a.cand_count, p.rows_per_frame, k, H, W, (int)pool_cap,
                                                      index, label, score, box);
   } else {
     TAUV_CUDA(cudaFuncSetAttribute(merge_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-    merge_kernel<0><<<B, kMergeThreads, msmem, st>>>(a.cand, a.cand_count, p.items_per_frame, k, H, W, (int)pool_cap,
+    merge_kernel<0><<<B, kMergeThreads, msmem, st>>>(a.cand, a.cand_count, p.rows_per_frame, k, H, W, (int)pool_cap,
                                                      index, label, score, box);
   }
   TAUV_LAUNCH_CHECK("merge_kernel");

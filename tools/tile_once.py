@@ -1,4 +1,4 @@
-"""ncu target: one bootstrap run of stage 1, then runs that reuse the published thresholds (steady state)."""
+"""ncu target: four runs of stage 1 (seed + tile kernels)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -14,7 +14,5 @@ def run():
     rc = lib.tauv_heatmap_topk_stage1(_lib.fptr(logits), B, C, H, W, K, 1, ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
     assert rc == 0
     torch.cuda.synchronize()
-run(); run()
-os.environ["TAUV_TILE_DEBUG"] = "keep"
-run(); run()
+run(); run(); run(); run()
 print("done")

@@ -32,10 +32,7 @@ def run(n=20, label=""):
     gb = 4 * B * C * H * W / 1e9
     print(f"{label:28s} median {ts[len(ts)//2]:8.1f} us  min {ts[0]:8.1f} us  -> {gb / (ts[len(ts)//2] * 1e-6):7.0f} GB/s")
 
-run(label="normal (memset + bootstrap)")
-os.environ["TAUV_TILE_DEBUG"] = "keep"
-run(label="thresholds kept from last run")
-del os.environ["TAUV_TILE_DEBUG"]
+run(label="seed + stream kernel")
 # copy bandwidth reference
 a = torch.empty(335544320 // 4, device=dev); b = torch.empty_like(a)
 for _ in range(3): b.copy_(a)

@@ -20,15 +20,27 @@ lib.tauv_debug_tile_trace.argtypes = [ctypes.c_void_p]
 lib.tauv_debug_tile_trace(trace.data_ptr())
 run()
 lib.tauv_debug_tile_trace(None)
-t = trace.cpu().numpy().astype(np.float64)
-t0 = t[:, 0].min()
-start, boot, scan, end = [(t[:, i] - t0) / 1e3 for i in range(4)]
-print(f"kernel span {end.max():.1f} us; items {n_items}")
-print("blk   start    boot_dur scan_dur  fin_dur  n_list  thr_key")
-for b in list(range(0, 40, 4)) + list(range(560, 700, 20)) + list(range(1000, 5120, 400)):
-    print(f"{b:5d} {start[b]:8.1f} {boot[b]-start[b]:8.2f} {scan[b]-boot[b]:8.2f} {end[b]-scan[b]:8.2f} {int(t[b,4]):6d}  {int(t[b,5]):#x}")
-for lo, hi in [(0, 592), (592, 1184), (1184, 2368), (2368, 5120)]:
-    s = slice(lo, hi)
-    print(f"blocks [{lo},{hi}): start {start[s].min():6.1f}-{start[s].max():6.1f}  mean dur {np.mean(end[s]-start[s]):6.2f} "
-          f"(boot {np.mean(boot[s]-start[s]):5.2f} scan {np.mean(scan[s]-boot[s]):5.2f} fin {np.mean(end[s]-scan[s]):5.2f})  "
-          f"mean list {t[s,4].mean():7.1f}  no-thr {int((t[s,5]==0).sum())}")
+t = trace.cpu().numpy().astype(np.float64)[:n_items].reshape(B, C, 8)
+t0 = t[:, :, 0][t[:, :, 0] > 0].min()
+us = lambda x: (x - t0) / 1e3
+first = t[:, :8, :]                       # the bootstrap items (rank r takes item r of the frame)
+print("bootstrap items: tile stored at %.2f | tested+binned +%.2f | sync+threshold+filter +%.2f | first run starts +%.2f" % (
+    us(first[:, :, 1]).mean(), (first[:, :, 6] - first[:, :, 1]).mean() / 1e3, (first[:, :, 7] - first[:, :, 6]).mean() / 1e3,
+    (first[:, :, 0] - first[:, :, 7]).mean() / 1e3))
+rounds = (t[:, :, 2] - t[:, :, 0]) / 1e3
+print("rounds per item (us): first items %.2f | items 8-39 %.2f | items 40-79 %.2f" % (rounds[:, :8].mean(), rounds[:, 8:40].mean(), rounds[:, 40:].mean()))
+# a run = items r, r+8, r+16, r+24 (then service); service duration = t3 - t2 of the run's last item
+svc = (t[:, :, 3] - t[:, :, 2]) / 1e3
+last_of_run = [j for j in range(C) if ((j // 8) % 4 == 3) or j // 8 == (C - 1) // 8]
+print("service step (us): mean %.2f  max %.2f" % (svc[:, last_of_run].mean(), svc[:, last_of_run].max()))
+for name, js in (("1st service", list(range(24, 32))), ("2nd service", list(range(56, 64))), ("last service", list(range(72, 80)))):
+    r = t[:, js, :]
+    print("  %s: wait for all warps +%.2f | peak tests (%d queued) +%.2f | bin+scan +%.2f | rest +%.2f" % (
+        name, (r[:, :, 1] - r[:, :, 2]).mean() / 1e3, r[:, :, 4].mean(), (r[:, :, 6] - r[:, :, 1]).mean() / 1e3,
+        (r[:, :, 7] - r[:, :, 6]).mean() / 1e3, (r[:, :, 3] - r[:, :, 7]).mean() / 1e3))
+end = us(t[:, :, 3].max(axis=1))
+print("unit (frame) end: min %.1f median %.1f max %.1f ; per-CTA end spread inside a cluster: mean %.2f us" % (
+    end.min(), np.median(end), end.max(), np.mean([us(t[b, -8:, 3]).max() - us(t[b, -8:, 3]).min() for b in range(B)])))
+thr = t[:, :, 5].astype(np.int64)
+for j in (0, 8, 16, 32, 48, 72):
+    print(f"  item {j:2d}: start {us(t[:, j, 0]).mean():6.1f}  rounds {rounds[:, j].mean():5.2f}  thr_key {int(np.median(thr[:, j])):#x}")
