@@ -22,6 +22,9 @@
 
 #include <cooperative_groups.h>
 
+#include <atomic>
+#include <mutex>
+
 namespace cg = cooperative_groups;
 
 namespace tauv {
@@ -124,7 +127,9 @@ struct __align__(16) TileCtx {
   int n_conv;              // list[0, n_conv) already hold final sort keys (SIGMOID_PEAK)
   int n_boot;              // list[0, n_boot) are already counted in the frame histogram (-1: order lost, count nothing more)
   uint32_t emit, maxbin;
-  int nhot;                // deferred peak tests queued in the hot list (cluster kernel)
+  int nhot;                // cluster kernel: queue tail (entries ever queued by the streaming warps)
+  int qhead;               // cluster kernel: queue head (entries consumed by the service warp)
+  int done;                // cluster kernel: streaming warps that have finished the unit
   int flags;               // bit 1 = the list overflowed
   int base, wsum[kTileThreads / 32];
   uint32_t sel[4];
@@ -551,15 +556,13 @@ constexpr int kClWin = 1024;                          // bins per window (64 bin
 constexpr int kClBins = 2 * kClWin;                   // negative window + positive window
 constexpr int kClNegBase = 1536;                      // fine bins [1536, 2560): -2^33 .. -2^-31
 constexpr int kClPosBase = 5632;                      // fine bins [5632, 6656): +2^-31 .. +2^33
-#ifndef TAUV_ROUND_W
-#define TAUV_ROUND_W 3
-#endif
-#ifndef TAUV_SVC_ITEMS
-#define TAUV_SVC_ITEMS 4
-#endif
-constexpr int kRoundW = TAUV_ROUND_W;                            // 128-bit strips per thread and round (2 x kRoundW live in registers)
-constexpr int kRoundF4 = kRoundW * kTileThreads;      // 128-bit strips per round per CTA
-constexpr int kRoundElems = 4 * kRoundF4;             // cells per round
+// (measured on B200: 2 beats 3 and 4 — wider rounds spill a loaded register, and a spill right after the load waits for it)
+constexpr int kRoundW = 2;                            // 128-bit strips per thread and round (2 x kRoundW live in registers)
+constexpr int kStreamThreads = kTileThreads - 32;     // warps 1..7 stream, warp 0 serves
+constexpr int kRoundF4 = kRoundW * kStreamThreads;    // 128-bit strips per streaming round per CTA
+constexpr int kBootF4 = kRoundW * kTileThreads;       // strips of the bootstrap round (all eight warps)
+constexpr int kBootElems = 4 * kBootF4;               // cells of the bootstrap round
+constexpr int kHotCap = 1024;                         // ring of queued peak tests (entries of 8 bytes)
 constexpr int kClMaxW = 1016;                         // halo rows are held in two 128-bit registers per thread
 
 struct __align__(16) ClusterCtx {
@@ -600,7 +603,6 @@ __device__ __forceinline__ uint32_t* cl_hist(const TileArgs& a) {
 __device__ __forceinline__ float* cl_tile(const TileArgs& a) {
   return reinterpret_cast<float*>(cl_smem() + kClOffList + (size_t)a.cap * 8 + kRadixBins * 4);
 }
-__device__ __forceinline__ int cl_hot_cap(const TileArgs& a) { return (kRoundElems + 2 * a.W + 8) / 2; }
 
 struct ItemGeom {
   const float* plane;
@@ -623,24 +625,16 @@ __device__ __forceinline__ ItemGeom item_geom(const TileArgs& a, int frame, int 
   return g;
 }
 
-__device__ __forceinline__ void load_round(const ItemGeom& g, int r, float4 (&x)[kRoundW]) {
+// kRoundW 128-bit strips per thread: strips s0 + u*NT + t of the item (s0 relative to the item's first strip)
+template <int NT>
+__device__ __forceinline__ void load_strips(const ItemGeom& g, int s0, int t, float4 (&x)[kRoundW]) {
   const int t1 = g.e1 >> 2;
-  const int tb = (g.e0 >> 2) + r * kRoundF4 + (int)threadIdx.x;
+  const int tb = (g.e0 >> 2) + s0 + t;
 #pragma unroll
   for (int u = 0; u < kRoundW; ++u) {
-    const int t = tb + u * kTileThreads;
-    x[u] = (t < t1) ? ldg_stream4(g.plane + ((size_t)t << 2))
-                    : make_float4(TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF);
-  }
-}
-
-// pull a round into L2 without tying up registers (used where a function call sits between issue and use)
-__device__ __forceinline__ void prefetch_round_l2(const ItemGeom& g, int r) {
-  const int t1 = g.e1 >> 2;
-  const int tb = (g.e0 >> 2) + r * kRoundF4;
-  for (int line = (int)threadIdx.x; line < kRoundF4 / 8; line += kTileThreads) {  // 8 strips per 128-byte line
-    const int t = tb + line * 8;
-    if (t < t1) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.plane + ((size_t)t << 2)));
+    const int tt = tb + u * NT;
+    x[u] = (tt < t1) ? ldg_stream4(g.plane + ((size_t)tt << 2))
+                     : make_float4(TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF);
   }
 }
 
@@ -694,123 +688,165 @@ __device__ __forceinline__ void cl_raise_all(cg::cluster_group& cluster, uint32_
   if (v && lane < kClSize) atomicMax(cluster.map_shared_rank(local_word, lane), v);
 }
 
-// Service step of a CTA (all threads; the caller has just passed a __syncthreads): run the queued peak tests of the
-// last few items against the latest threshold, add what is new in the list to this CTA's bins, and (warp 0) rescan
-// and republish the unit's threshold once the CTA has binned k/8 candidates since its last scan.
-constexpr int kSvcItems = TAUV_SVC_ITEMS;  // items between two service steps (bounds what an overflow has to redo)
-
-template <int MODE>
-__device__ __noinline__ void cl_service(const TileArgs& a, TileCtx* ctx, unsigned long long* list, uint32_t* hist,
-                                        const int2* hotq, int hot_cap, int frame, cg::cluster_group& cluster,
-                                        ClusterCtx* cc, int* since_scan, long long* trow) {
-  const int tid = threadIdx.x;
-  auto now = []() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; };
-  const int nq = min(ctx->nhot, hot_cap);
-  if (trow && tid == 0) { trow[1] = now(); trow[4] = nq; }
-  if (tid == 0) set_thr(ctx, (unsigned long long)(*reinterpret_cast<volatile uint32_t*>(&cc->thr_key)) << 32);
-  __syncthreads();
-  int fl = 0;
+// ---- streaming warps (1..7) -------------------------------------------------------------------------------------
+// All items of this CTA in the unit (iif, iif + 8, ... < i_hi), the first one from strip s_begin on.  No barrier and no
+// call in here, and nothing but the streaming state is live, so the next round's loads stay in registers: they are
+// requested before the current round is compared against the threshold (of the same item, or the first round of the
+// next item).  Strips that pass are only QUEUED for the service warp: their peak tests wait on neighbour loads, and
+// done in line they would stall the streaming once per strip.
+__device__ __noinline__ void cl_stream_all(const TileArgs& a, int frame, int iif, int i_hi, int s_begin) {
+  const int st = (int)threadIdx.x - 32;  // thread index among the streaming threads
+  TileCtx* const ctx = cl_ctx();
+  int2* const hotq = reinterpret_cast<int2*>(cl_tile(a));
+  ItemGeom g = item_geom(a, frame, iif);
+  while (s_begin >= (g.e1 >> 2) - (g.e0 >> 2)) {  // the bootstrap round covered the whole first item
+    iif += kClSize;
+    s_begin = 0;
+    if (iif >= i_hi) {
+      iif = -1;
+      break;
+    }
+    g = item_geom(a, frame, iif);
+  }
+  float4 xn[kRoundW];
+  if (iif >= 0) load_strips<kStreamThreads>(g, s_begin, st, xn);
 #pragma unroll 1
-  for (int i = tid; i < nq; i += kTileThreads) {
-    const int2 q = hotq[i];
-    const ItemGeom g = item_geom(a, frame, q.x);
-    fl |= examine<MODE, true>(a, ctx, list, g.plane, g.plane_flat0, q.y);
-  }
-  if (fl) atomicOr(&ctx->flags, fl);
-  if (tid == 0) {
-    ctx->maxbin = 0;
-    ctx->base = 0;
-  }
-  __syncthreads();
-  if (trow && tid == 0) trow[6] = now();
-  if (tid == 0) ctx->nhot = 0;
-  if (ctx->flags & 2) return;  // the list overflowed: the caller redoes the affected items
-  const int n = ctx->count, nb = ctx->n_boot;
-  if (nb >= 0 && n > nb) {
-    // list[nb, n) are new and still carry logit keys (SIGMOID_PEAK), the space the bins live in
-    uint32_t my_maxbin = 0, mine = 0;
-    for (int i = nb + tid; i < n; i += kTileThreads) {
-      const uint32_t key = composite_key(list[i]);
-      if (MODE == TAUV_TOPK_SIGMOID_PEAK && !(key_to_float(key) > -80.0f)) continue;  // may underflow to score 0
-      const int bin = cl_window_bin(key);
-      if (bin < 0) continue;
-      atomicAdd(&cc->bins[bin], 1u);
-      my_maxbin = max(my_maxbin, (uint32_t)bin);
-      ++mine;
+  while (iif >= 0) {
+    const bool more = iif + kClSize < i_hi;
+    const int t1 = g.e1 >> 2;
+    const int n_strips = t1 - (g.e0 >> 2);
+    if (a.trace && st == 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      a.trace[(size_t)g.item * 8 + 0] = t;
+      a.trace[(size_t)g.item * 8 + 5] = composite_key(ctx->thr);
     }
+#pragma unroll 1
+    for (int s0 = s_begin; s0 < n_strips; s0 += kRoundF4) {
+      float4 x[kRoundW];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      my_maxbin = max(my_maxbin, __shfl_xor_sync(0xffffffffu, my_maxbin, o));
-      mine += __shfl_xor_sync(0xffffffffu, mine, o);
+      for (int u = 0; u < kRoundW; ++u) x[u] = xn[u];
+      if (s0 + kRoundF4 < n_strips) load_strips<kStreamThreads>(g, s0 + kRoundF4, st, xn);
+      else if (more) load_strips<kStreamThreads>(item_geom(a, frame, iif + kClSize), 0, st, xn);
+      const float thr_f = *reinterpret_cast<volatile float*>(&ctx->thr_f);  // kept current by the service warp
+      const int tb = (g.e0 >> 2) + s0 + st;
+      uint32_t hot = 0;
+#pragma unroll
+      for (int u = 0; u < kRoundW; ++u)
+        if (fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w)) >= thr_f && tb + u * kStreamThreads < t1) hot |= 1u << u;
+#pragma unroll 1
+      while (hot) {
+        const int u = __ffs(hot) - 1;
+        hot &= hot - 1;
+        const int slot = atomicAdd(&ctx->nhot, 1);
+        // ring full: wait for the service warp (it never waits for us, so this always ends)
+        while (slot - *reinterpret_cast<volatile int*>(&ctx->qhead) >= kHotCap) __nanosleep(64);
+        hotq[slot & (kHotCap - 1)] = make_int2(iif, (tb + u * kStreamThreads) << 2);
+      }
     }
-    if ((tid & 31) == 0 && mine) {
-      atomicMax(&ctx->maxbin, my_maxbin);
-      atomicAdd(&ctx->base, (int)mine);
+    if (a.trace && st == 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      a.trace[(size_t)g.item * 8 + 2] = t;
     }
-    __syncthreads();
-    if (tid == 0) ctx->n_boot = n;
-    if (tid < 32) {
-      if (ctx->maxbin > *reinterpret_cast<volatile uint32_t*>(&cc->maxbin)) cl_raise_all(cluster, &cc->maxbin, ctx->maxbin);
-      *since_scan += ctx->base;
-      const int every = a.k >= 8 ? a.k / 8 : 1;
-      if (*since_scan >= every) {
-        *since_scan = 0;
+    if (!more) break;
+    iif += kClSize;
+    s_begin = 0;
+    g = item_geom(a, frame, iif);
+  }
+  __syncwarp();
+  __threadfence_block();
+  if ((threadIdx.x & 31) == 0) atomicAdd(&ctx->done, 1);
+}
+
+// ---- service warp (0) ----------------------------------------------------------------------------------------------
+// Consumes the queue while the other warps stream: runs the peak tests (neighbours from L2/HBM; the latency is this
+// warp's alone), appends candidates to the CTA's list, adds them to this CTA's bins, and whenever it has binned k/8
+// new candidates rescans the unit's histogram (remote loads) and raises the rejection key in all eight CTAs.  It also
+// folds keys published by the other CTAs into this CTA's threshold, which the streaming warps read every round.
+template <int MODE>
+__device__ __noinline__ void cl_service_warp(const TileArgs& a, int frame, cg::cluster_group& cluster) {
+  const int lane = threadIdx.x & 31;
+  TileCtx* const ctx = cl_ctx();
+  ClusterCtx* const cc = cl_cc();
+  unsigned long long* const list = cl_list();
+  int2* const hotq = reinterpret_cast<int2*>(cl_tile(a));
+  const int every = a.k >= 8 ? a.k / 8 : 1;
+  int head = 0, since_scan = 0;
+  int n_binned = ctx->n_boot;  // list[0, n_binned) are in the bins already (bootstrap survivors); -1: stop binning
+  while (true) {
+    if (lane == 0) set_thr(ctx, (unsigned long long)(*reinterpret_cast<volatile uint32_t*>(&cc->thr_key)) << 32);
+    __syncwarp();
+    const int done = *reinterpret_cast<volatile int*>(&ctx->done);
+    const int avail = *reinterpret_cast<volatile int*>(&ctx->nhot) - head;
+    if (avail <= 0) {
+      if (done == kStreamThreads / 32) break;
+      __nanosleep(128);
+      continue;
+    }
+    const int n = avail < 32 ? avail : 32;
+    int2 q = make_int2(-1, 0);
+    if (lane < n) {
+      volatile int2* slot = reinterpret_cast<volatile int2*>(&hotq[(head + lane) & (kHotCap - 1)]);
+      while ((q.x = slot->x) < 0) {}  // (the producer is between its atomicAdd and its store)
+      q.y = slot->y;
+      slot->x = -1;                   // free the slot before the head moves past it
+    }
+    __syncwarp();
+    head += n;
+    if (lane == 0) *reinterpret_cast<volatile int*>(&ctx->qhead) = head;
+    int fl = 0;
+    if (lane < n) {
+      const ItemGeom g = item_geom(a, frame, q.x);
+      fl = examine<MODE, true>(a, ctx, list, g.plane, g.plane_flat0, q.y);
+    }
+    fl = __reduce_or_sync(0xffffffffu, (unsigned)fl);
+    if (fl & 2) {  // the list is full: everything is redone safely at the end of the unit; keep draining the queue
+      if (lane == 0) ctx->flags |= 2;
+      n_binned = -1;
+      continue;
+    }
+    __syncwarp();
+    const int cnt = *reinterpret_cast<volatile int*>(&ctx->count);
+    if (n_binned >= 0 && cnt > n_binned) {
+      // list[n_binned, cnt) are new and still carry logit keys (SIGMOID_PEAK), the space the bins live in
+      uint32_t my_maxbin = 0;
+      for (int i = n_binned + lane; i < cnt; i += 32) {
+        const uint32_t key = composite_key(list[i]);
+        if (MODE == TAUV_TOPK_SIGMOID_PEAK && !(key_to_float(key) > -80.0f)) continue;  // may underflow to score 0
+        const int bin = cl_window_bin(key);
+        if (bin < 0) continue;
+        atomicAdd(&cc->bins[bin], 1u);
+        my_maxbin = max(my_maxbin, (uint32_t)bin);
+      }
+      my_maxbin = __reduce_max_sync(0xffffffffu, my_maxbin);
+      since_scan += cnt - n_binned;
+      n_binned = cnt;
+      if (my_maxbin > *reinterpret_cast<volatile uint32_t*>(&cc->maxbin)) cl_raise_all(cluster, &cc->maxbin, my_maxbin);
+      if (since_scan >= every) {
+        since_scan = 0;
+        __threadfence_block();
         cl_raise_all(cluster, &cc->thr_key, cl_scan_threshold<MODE>(cluster, cc, a.k));
       }
     }
   }
-  if (trow && tid == 0) trow[7] = now();
-  // keep the list far from its capacity (uniform: count is stable here)
-  if (n > a.cap / 2) {
-    __syncthreads();
-    prune_list<MODE>(a, ctx, list, hist);
-    if (tid == 0) ctx->n_boot = -1;  // order lost: this CTA adds nothing more to the bins
-    __syncthreads();
-  }
 }
 
-// The list overflowed while the items [recent[0..n_recent)) were being collected (plateaus, or no usable threshold):
-// drop what they contributed, prune the rest to the exact top-k, and redo those items in sub-steps that cannot
-// overflow, pruning whenever the list passes `soft`.
+// The list overflowed somewhere in the unit (plateaus, or no usable threshold): start this CTA's share of the unit
+// over, in sub-steps that cannot overflow, pruning to the exact top-k whenever the list passes `soft`.
 template <int MODE>
-__device__ __noinline__ void cl_redo_items_safely(const TileArgs& a, TileCtx* ctx, unsigned long long* list,
-                                                  uint32_t* hist, int frame, const int* recent, int n_recent) {
+__device__ __noinline__ void cl_redo_all_safely(const TileArgs& a, TileCtx* ctx, unsigned long long* list, uint32_t* hist,
+                                                int frame, int iif0, int i_hi) {
   __syncthreads();
-  const int tid = threadIdx.x;
-  // entries of the affected items, recognised by their flat index
-  uint32_t lo[kSvcItems + 1], hi[kSvcItems + 1];
-  for (int j = 0; j < n_recent; ++j) {
-    const ItemGeom g = item_geom(a, frame, recent[j]);
-    lo[j] = g.plane_flat0 + (uint32_t)g.e0;
-    hi[j] = g.plane_flat0 + (uint32_t)g.e1;
-  }
-  auto keep = [&](unsigned long long c) {
-    const uint32_t flat = composite_idx(c);
-    bool mine = false;
-    for (int j = 0; j < n_recent; ++j) mine |= (flat >= lo[j] && flat < hi[j]);
-    return !mine;
-  };
-  const int n = min(ctx->count, a.cap);
-  // the compaction is stable, so the converted prefix [0, n_conv) stays a prefix; count what survives of it
-  if (tid == 0) ctx->emit = 0;
-  __syncthreads();
-  for (int i = tid; i < ctx->n_conv; i += kTileThreads)
-    if (keep(list[i])) atomicAdd(&ctx->emit, 1u);
-  __syncthreads();
-  const int new_conv = (int)ctx->emit;
-  compact_list(ctx, list, n, keep);
-  if (tid == 0) {
-    ctx->count = ctx->base;
-    ctx->n_conv = new_conv;
-    ctx->n_boot = -1;  // this CTA adds nothing more to the bins
+  if (threadIdx.x == 0) {
+    ctx->count = 0;
+    ctx->n_conv = 0;
+    ctx->n_boot = -1;
     ctx->flags = 0;
-    ctx->nhot = 0;
   }
   __syncthreads();
-  if (ctx->count > a.soft) prune_list<MODE>(a, ctx, list, hist);
-  __syncthreads();
-  for (int j = 0; j < n_recent; ++j) {
-    const ItemGeom g = item_geom(a, frame, recent[j]);
+  for (int iif = iif0; iif < i_hi; iif += kClSize) {
+    const ItemGeom g = item_geom(a, frame, iif);
     for (int s0 = g.e0; s0 < g.e1; s0 += a.sub_elems) {
       scan_elems<MODE, true>(a, ctx, list, g.plane, g.plane_flat0, s0, min(s0 + a.sub_elems, g.e1));
       __syncthreads();
@@ -820,74 +856,6 @@ __device__ __noinline__ void cl_redo_items_safely(const TileArgs& a, TileCtx* ct
   }
 }
 
-// A run of `n_run` items of this CTA (iif, iif + 8, ...), the first one starting at round r_begin.  No barrier and no
-// call in here, and nothing but the streaming state is live, so the next round's four 128-bit loads stay in registers:
-// they are requested before the current round is compared against the threshold (of the same item, or round 0 of the
-// next item of the run).  Strips that pass are only QUEUED (their peak tests wait on neighbour loads from L2; done in
-// line they would stall the warp's streaming once per strip).  The round that follows the run is pulled into L2.
-template <int MODE>
-__device__ __noinline__ int cl_stream_run(const TileArgs& a, int frame, int iif, int n_run, int r_begin, int i_hi) {
-  const int tid = threadIdx.x;
-  TileCtx* const ctx = cl_ctx();
-  ClusterCtx* const cc = cl_cc();
-  int2* const hotq = reinterpret_cast<int2*>(cl_tile(a));
-  const int hot_cap = cl_hot_cap(a);
-  int fl = 0;
-  ItemGeom g = item_geom(a, frame, iif);
-  float4 xn[kRoundW];
-  {
-    const int rounds0 = ((g.e1 >> 2) - (g.e0 >> 2) + kRoundF4 - 1) / kRoundF4;
-    if (r_begin < rounds0) load_round(g, r_begin, xn);
-    else if (n_run > 1) load_round(item_geom(a, frame, iif + kClSize), 0, xn);
-  }
-#pragma unroll 1
-  for (int j = 0; j < n_run; ++j) {
-    const bool more = j + 1 < n_run;
-    const int t1 = g.e1 >> 2;
-    const int rounds = (t1 - (g.e0 >> 2) + kRoundF4 - 1) / kRoundF4;
-    if (a.trace && tid == 0) {
-      long long t;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-      a.trace[(size_t)g.item * 8 + 0] = t;
-      a.trace[(size_t)g.item * 8 + 5] = composite_key(ctx->thr);
-    }
-#pragma unroll 1
-    for (int r = r_begin; r < rounds; ++r) {
-      float4 x[kRoundW];
-#pragma unroll
-      for (int u = 0; u < kRoundW; ++u) x[u] = xn[u];
-      if (r + 1 < rounds) load_round(g, r + 1, xn);
-      else if (more) load_round(item_geom(a, frame, iif + kClSize), 0, xn);
-      else if (iif + kClSize < i_hi) prefetch_round_l2(item_geom(a, frame, iif + kClSize), 0);
-      // pick up what the unit's CTAs have published meanwhile (local shared memory)
-      if (tid == 0) set_thr(ctx, (unsigned long long)(*reinterpret_cast<volatile uint32_t*>(&cc->thr_key)) << 32);
-      const float thr_f = *reinterpret_cast<volatile float*>(&ctx->thr_f);
-      const int tb = (g.e0 >> 2) + r * kRoundF4 + tid;
-      uint32_t hot = 0;
-#pragma unroll
-      for (int u = 0; u < kRoundW; ++u)
-        if (fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w)) >= thr_f && tb + u * kTileThreads < t1) hot |= 1u << u;
-#pragma unroll 1
-      while (hot) {
-        const int u = __ffs(hot) - 1;
-        hot &= hot - 1;
-        const int slot = atomicAdd(&ctx->nhot, 1);
-        if (slot < hot_cap) hotq[slot] = make_int2(iif, (tb + u * kTileThreads) << 2);
-        else fl = 2;  // queue full: treated like a list overflow, the items are redone safely
-      }
-    }
-    if (a.trace && tid == 0) {
-      long long t;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-      a.trace[(size_t)g.item * 8 + 2] = t;
-    }
-    iif += kClSize;
-    r_begin = 0;
-    if (more) g = item_geom(a, frame, iif);
-  }
-  return fl;
-}
-
 // Bootstrap round of a unit: the full test on round 0 of this CTA's first item, from the shared-memory tile
 // (tile[0] = plane cell `origin`; cells outside the plane are never read).  Peaks go to the list and into the bins.
 template <int MODE>
@@ -895,7 +863,7 @@ __device__ __noinline__ void cl_bootstrap_round(const TileArgs& a, TileCtx* ctx,
                                                 uint32_t* hist, const float* tile, int origin, const ItemGeom& g,
                                                 cg::cluster_group& cluster, ClusterCtx* cc) {
   const int tid = threadIdx.x;
-  const int c_end = min(g.e1, g.e0 + kRoundElems);
+  const int c_end = min(g.e1, g.e0 + kBootElems);
   int fl = 0;
   if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
 #pragma unroll 1
@@ -913,7 +881,9 @@ __device__ __noinline__ void cl_bootstrap_round(const TileArgs& a, TileCtx* ctx,
   }
   if (fl) atomicOr(&ctx->flags, fl);
   if (tid == 0) ctx->maxbin = 0;
+  if (a.trace && tid == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.trace[(size_t)g.item * 8 + 3] = t; }
   __syncthreads();
+  if (a.trace && tid == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.trace[(size_t)g.item * 8 + 4] = t; }
   if (ctx->flags & 2) return;  // the list overflowed (plateaus): the item is redone safely later; nothing is binned now
   const int nb = ctx->count;
   uint32_t my_maxbin = 0;
@@ -942,10 +912,8 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
   cg::cluster_group cluster = cg::this_cluster();
   unsigned long long* list = cl_list();
   uint32_t* hist = cl_hist(a);
-  float* tile = cl_tile(a);                    // [kRoundElems + 2W + 8]
-  int2* hotq = reinterpret_cast<int2*>(tile);  // the same memory after the bootstrap round: queued peak tests
-  const int hot_cap = cl_hot_cap(a);
-  __shared__ int s_recent[kSvcItems];
+  float* tile = cl_tile(a);                    // [kBootElems + 2W + 8]
+  int2* hotq = reinterpret_cast<int2*>(tile);  // the same memory after the bootstrap round: ring of queued peak tests
   TileCtx* ctx = cl_ctx();
   ClusterCtx* cc = cl_cc();
   const int tid = threadIdx.x;
@@ -954,6 +922,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
   const int ipf = a.C * a.items_per_plane;
   const int W = a.W;
   auto now = []() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; };
+  const long long t_kernel = a.trace ? now() : 0;
 
 #pragma unroll 1
   for (int unit = cid; unit < n_units; unit += ncl) {
@@ -965,13 +934,13 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
     ItemGeom g = item_geom(a, frame, have ? iif : i_lo);
     float4 xn[kRoundW];
     // halo of round 0: plane cells [e0 - W, e0) and [c_end, c_end + W + 4), two 128-bit strips per thread at most
-    const int c_end = min(g.e1, g.e0 + kRoundElems);
+    const int c_end = min(g.e1, g.e0 + kBootElems);
     const int origin = g.e0 - W;                 // plane cell held in tile[0] (may be negative: never read then)
     const int plane_cells = a.H * W;
     const int nh = W >> 2;                        // strips per halo row
     float4 halo[2];
     if (have) {
-      load_round(g, 0, xn);
+      load_strips<kTileThreads>(g, 0, tid, xn);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int h = tid + j * kTileThreads;     // [0, nh): row above; [nh, 2nh+1): row below (+1 strip)
@@ -990,6 +959,8 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
       ctx->n_conv = 0;
       ctx->n_boot = 0;
       ctx->nhot = 0;
+      ctx->qhead = 0;
+      ctx->done = 0;
       ctx->flags = 0;
       ctx->thr = 0ull;
       ctx->thr_f = TAUV_NEG_INF;
@@ -998,7 +969,6 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
 
     long long tr0 = 0;
     if (a.trace && tid == 0) tr0 = now();
-    int r_begin = 0;
     if (have) {
       // ---- bootstrap: round 0 of the first item, every cell tested, from shared memory
 #pragma unroll
@@ -1016,12 +986,8 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
       }
       __syncthreads();
       if (a.trace && tid == 0) a.trace[(size_t)g.item * 8 + 1] = now();
-      // keep HBM busy underneath the bootstrap (into L2 only: registers would not survive the calls below)
-      if (c_end < g.e1) prefetch_round_l2(g, 1);
-      else if (iif + kClSize < i_hi) prefetch_round_l2(item_geom(a, frame, iif + kClSize), 0);
       cl_bootstrap_round<MODE>(a, ctx, list, hist, tile, origin, g, cluster, cc);
       if (a.trace && tid == 0) a.trace[(size_t)g.item * 8 + 6] = now();
-      r_begin = 1;
     }
     cluster.sync();  // (2) the sample of all eight CTAs is in their bins, the highest occupied bin is known everywhere
     // first threshold: every CTA derives it for itself (warp 0, remote loads only; nothing to publish)
@@ -1045,31 +1011,31 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
       __syncthreads();
     }
     if (a.trace && tid == 0 && have) a.trace[(size_t)g.item * 8 + 7] = now();
-    int since_scan = 0;  // (warp 0) candidates this CTA has binned since its last scan
 
-    // ---- stream: runs of up to kSvcItems items (no barrier, no call inside a run), a service step after each
-    while (have) {
-      int n_run = (i_hi - iif + kClSize - 1) / kClSize;  // items this CTA still has in the unit
-      if (n_run > kSvcItems) n_run = kSvcItems;
-      if (tid == 0)
-        for (int j = 0; j < n_run; ++j) s_recent[j] = iif + j * kClSize;
-      const int fl = cl_stream_run<MODE>(a, frame, iif, n_run, r_begin, i_hi);
-      if (fl) atomicOr(&ctx->flags, fl);
+    // ---- stream: warps 1..7 stream every item of this CTA, warp 0 serves the queue; no barrier until both are done
+    if (have) {
+      for (int i = tid; i < kHotCap; i += kTileThreads) hotq[i] = make_int2(-1, 0);  // (the tile is free now)
       __syncthreads();
-      cl_service<MODE>(a, ctx, list, hist, hotq, hot_cap, frame, cluster, cc, &since_scan,
-                       a.trace ? a.trace + (size_t)item_geom(a, frame, iif + (n_run - 1) * kClSize).item * 8 : nullptr);
-      if (ctx->flags & 2) cl_redo_items_safely<MODE>(a, ctx, list, hist, frame, s_recent, n_run);
+      if (tid < 32) cl_service_warp<MODE>(a, frame, cluster);
+      else cl_stream_all(a, frame, iif, i_hi, kBootF4);
       __syncthreads();
+      if (ctx->flags & 2) cl_redo_all_safely<MODE>(a, ctx, list, hist, frame, iif, i_hi);
       if (a.trace && tid == 0) {
-        tr0 = now();
-        for (int j = 0; j < n_run; ++j) {
-          const size_t row = (size_t)item_geom(a, frame, iif + j * kClSize).item * 8;
-          a.trace[row + 3] = tr0;
+        const long long t = now();
+        int last = iif;
+        for (int j = iif; j < i_hi; j += kClSize) {
+          if (j != iif) a.trace[(size_t)item_geom(a, frame, j).item * 8 + 3] = t;
+          if (j != iif) a.trace[(size_t)item_geom(a, frame, j).item * 8 + 4] = ctx->count;
+          last = j;
+        }
+        if (last != iif) {
+          unsigned smid;
+          asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+          a.trace[(size_t)item_geom(a, frame, last).item * 8 + 7] = smid;
+          a.trace[(size_t)item_geom(a, frame, last).item * 8 + 6] = t_kernel;
+          a.trace[(size_t)item_geom(a, frame, last).item * 8 + 3] = t;
         }
       }
-      iif += n_run * kClSize;
-      have = iif < i_hi;
-      r_begin = 0;
     }
 
     // ---- the CTA's candidates of the whole unit: exact top-k, one row of the candidate table
@@ -1396,9 +1362,8 @@ static int run_stage1(const float* hm, int B, int C, int H, int W, int k, int mo
   }
   // vectorised path: persistent clusters of 8 CTAs, one unit (a frame, or a share of a frame's items) at a time
   void (*ck)(const TileArgs, int, int) = mode == TAUV_TOPK_SIGMOID_PEAK ? tile_cluster_kernel<1> : tile_cluster_kernel<0>;
-  const size_t csmem = (size_t)kClOffList + p.smem_bytes + (size_t)(kRoundElems + 2 * W + 8) * 4;
+  const size_t csmem = (size_t)kClOffList + p.smem_bytes + (size_t)(kBootElems + 2 * W + 8) * 4;
   TAUV_REQUIRE(csmem <= 227 * 1024, TAUV_E_UNSUPPORTED, "tile needs %zu B shared memory", csmem);
-  TAUV_CUDA(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(kClSize);
   cfg.blockDim = dim3(kTileThreads);
@@ -1411,8 +1376,30 @@ static int run_stage1(const float* hm, int B, int C, int H, int W, int k, int mo
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  int ncl = 0;  // clusters that are resident at once
-  TAUV_CUDA(cudaOccupancyMaxActiveClusters(&ncl, ck, &cfg));
+  int ncl = 0;  // clusters that are resident at once (the query costs tens of microseconds of host time: cached)
+  {
+    // per (mode, device): the largest dynamic shared-memory size the kernel has been opted in to (only ever raised,
+    // under a lock, so concurrent callers cannot lower it under each other), and the last occupancy answer
+    static std::mutex mu;
+    static std::atomic<unsigned long long> max_smem[2][64], occ[2][64];
+    int dev = 0;
+    TAUV_CUDA(cudaGetDevice(&dev));
+    const int m = mode == TAUV_TOPK_SIGMOID_PEAK, d = (dev >= 0 && dev < 64) ? dev : 63;
+    if (max_smem[m][d].load(std::memory_order_acquire) < csmem || dev != d) {
+      std::lock_guard<std::mutex> lock(mu);
+      if (max_smem[m][d].load(std::memory_order_relaxed) < csmem || dev != d) {
+        TAUV_CUDA(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+        if (dev == d) max_smem[m][d].store(csmem, std::memory_order_release);
+      }
+    }
+    const unsigned long long seen = occ[m][d].load(std::memory_order_relaxed);  // (csmem + 1) << 16 | ncl; idempotent
+    if (dev == d && (seen >> 16) == (unsigned long long)csmem + 1) {
+      ncl = (int)(seen & 0xffff);
+    } else {
+      TAUV_CUDA(cudaOccupancyMaxActiveClusters(&ncl, ck, &cfg));
+      occ[m][d].store((((unsigned long long)csmem + 1) << 16) | (unsigned long long)(ncl & 0xffff), std::memory_order_relaxed);
+    }
+  }
   TAUV_REQUIRE(ncl >= 1, TAUV_E_UNSUPPORTED, "no cluster of %d CTAs fits the device with %zu B shared memory", kClSize, csmem);
   // units: whole frames when there are at least as many frames as clusters, otherwise every frame is split into
   // `parts` contiguous shares of its items (each share keeps its own threshold; the merge kernel joins them)

@@ -27,20 +27,19 @@ first = t[:, :8, :]                       # the bootstrap items (rank r takes it
 print("bootstrap items: tile stored at %.2f | tested+binned +%.2f | sync+threshold+filter +%.2f | first run starts +%.2f" % (
     us(first[:, :, 1]).mean(), (first[:, :, 6] - first[:, :, 1]).mean() / 1e3, (first[:, :, 7] - first[:, :, 6]).mean() / 1e3,
     (first[:, :, 0] - first[:, :, 7]).mean() / 1e3))
-rounds = (t[:, :, 2] - t[:, :, 0]) / 1e3
-print("rounds per item (us): first items %.2f | items 8-39 %.2f | items 40-79 %.2f" % (rounds[:, :8].mean(), rounds[:, 8:40].mean(), rounds[:, 40:].mean()))
-# a run = items r, r+8, r+16, r+24 (then service); service duration = t3 - t2 of the run's last item
-svc = (t[:, :, 3] - t[:, :, 2]) / 1e3
-last_of_run = [j for j in range(C) if ((j // 8) % 4 == 3) or j // 8 == (C - 1) // 8]
-print("service step (us): mean %.2f  max %.2f" % (svc[:, last_of_run].mean(), svc[:, last_of_run].max()))
-for name, js in (("1st service", list(range(24, 32))), ("2nd service", list(range(56, 64))), ("last service", list(range(72, 80)))):
-    r = t[:, js, :]
-    print("  %s: wait for all warps +%.2f | peak tests (%d queued) +%.2f | bin+scan +%.2f | rest +%.2f" % (
-        name, (r[:, :, 1] - r[:, :, 2]).mean() / 1e3, r[:, :, 4].mean(), (r[:, :, 6] - r[:, :, 1]).mean() / 1e3,
-        (r[:, :, 7] - r[:, :, 6]).mean() / 1e3, (r[:, :, 3] - r[:, :, 7]).mean() / 1e3))
+print("bootstrap detail: peak tests +%.2f | barrier +%.2f | binning etc +%.2f" % ((first[:, :, 3] - first[:, :, 1]).mean() / 1e3, (first[:, :, 4] - first[:, :, 3]).mean() / 1e3, (first[:, :, 6] - first[:, :, 4]).mean() / 1e3))
+last = t[:, -8:, :]
+print("kernel start (CTA's first instruction) at %.2f .. %.2f; CTA end at %.1f .. %.1f" % (us(last[:, :, 6]).min(), us(last[:, :, 6]).max(), us(last[:, :, 3]).min(), us(last[:, :, 3]).max()))
+smid = last[:, :, 7].astype(int).ravel(); cend = us(last[:, :, 2]).ravel()
+per_sm = np.bincount(smid, minlength=148)
+print("CTAs per SM histogram:", np.bincount(per_sm), " mean stream end by CTAs-on-SM:", {int(c): round(float(cend[per_sm[smid] == c].mean()), 1) for c in np.unique(per_sm[smid])})
+rounds = (t[:, 8:, 2] - t[:, 8:, 0]) / 1e3
+rounds = np.concatenate([np.zeros((B, 8)), rounds], axis=1)
+print("rounds per item (us): items 8-39 %.2f | items 40-79 %.2f" % (rounds[:, 8:40].mean(), rounds[:, 40:].mean()))
 end = us(t[:, :, 3].max(axis=1))
-print("unit (frame) end: min %.1f median %.1f max %.1f ; per-CTA end spread inside a cluster: mean %.2f us" % (
-    end.min(), np.median(end), end.max(), np.mean([us(t[b, -8:, 3]).max() - us(t[b, -8:, 3]).min() for b in range(B)])))
+se = us(t[:, -8:, 2])  # end of streaming of each CTA (its last item)
+print("unit (frame) end: min %.1f median %.1f max %.1f ; streaming end per CTA: min %.1f max %.1f, spread inside a cluster mean %.2f us; drain after streaming mean %.2f us; list at end mean %.1f" % (
+    end.min(), np.median(end), end.max(), se.min(), se.max(), np.mean(se.max(axis=1) - se.min(axis=1)), np.mean(us(t[:, -8:, 3]) - se), t[:, -8:, 4].mean()))
 thr = t[:, :, 5].astype(np.int64)
-for j in (0, 8, 16, 32, 48, 72):
+for j in (8, 16, 32, 48, 72):
     print(f"  item {j:2d}: start {us(t[:, j, 0]).mean():6.1f}  rounds {rounds[:, j].mean():5.2f}  thr_key {int(np.median(thr[:, j])):#x}")
