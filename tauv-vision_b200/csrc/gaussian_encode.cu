@@ -31,107 +31,189 @@ __device__ __forceinline__ float gauss_from_d2(long long d2, float two_sigma2) {
   return expf(__fdiv_rn((float)(-d2), two_sigma2));
 }
 
-struct PlaneObjs {
-  int n;
-  bool big;
-};
+// One CTA per (frame, group of kEncGroup classes, row band).  The frame's truth is read ONCE per CTA (one latency for
+// up to kEncGroup * H * W * 4 bytes of stores instead of one per plane), bucketed by class in shared memory, and then
+// every plane of the group is written exactly once: zero planes (four out of five at 16 objects over 80 classes) as
+// plain 128-bit zero stores, planes with objects as one exp per pixel.
+constexpr int kEncGroup = 8;
 
 template <bool VEC>
 __global__ void __launch_bounds__(kEncThreads) gaussian_encode_kernel(
     const uint8_t* __restrict__ valid, const int64_t* __restrict__ label, const float* __restrict__ center,
-    int n_objects, int C, int H, int W, float in_h, float in_w, float ratio, float two_sigma2, int bands,
+    int n_objects, int C, int H, int W, float in_h, float in_w, float ratio, float two_sigma2, int groups, int bands,
     int rows_per_band, float* __restrict__ out) {
-  extern __shared__ int s_obj[];  // [2*n_objects] (cy, cx) of the objects rendered into this plane
-  __shared__ int s_n;
+  extern __shared__ int s_raw[];
+  int* s_obj = s_raw;                   // [2*n_objects] (cy, cx), bucketed by class: class g holds [s_start[g], s_start[g+1])
+  int* s_tmp = s_raw + 2 * n_objects;   // [3*n_objects] scratch: (class in group or -1, cy, cx) per object
+  __shared__ int s_cnt[kEncGroup], s_start[kEncGroup + 1], s_fill[kEncGroup];
   __shared__ int s_big;
   const int tid = threadIdx.x;
   const int band = blockIdx.x % bands;
-  const long long plane = blockIdx.x / bands;
-  const int c = (int)(plane % C);
-  const long long b = plane / C;
-  if (tid == 0) { s_n = 0; s_big = 0; }
+  const int grp = (blockIdx.x / bands) % groups;
+  const long long b = blockIdx.x / ((long long)bands * groups);
+  const int c0 = grp * kEncGroup;
+  const int nc = min(kEncGroup, C - c0);
+  if (tid < kEncGroup) { s_cnt[tid] = 0; s_fill[tid] = 0; }
+  if (tid == 0) s_big = 0;
   __syncthreads();
-  // the frame's objects that render into this plane: the loads are issued now ...
-  bool mine = false;
-  int cy = 0, cx = 0;
-  if (tid < n_objects) {
-    const long long i = b * n_objects + tid;
-    if (valid[i] && label[i] == c) {
-      mine = true;
-      cy = grid_floor(center[i * 2 + 0], in_h, ratio);
-      cx = grid_floor(center[i * 2 + 1], in_w, ratio);
+  for (int o = tid; o < n_objects; o += kEncThreads) {
+    const long long i = b * n_objects + o;
+    int g = -1, cy = 0, cx = 0;
+    if (valid[i]) {
+      const long long l = label[i] - c0;
+      if (l >= 0 && l < nc) {
+        g = (int)l;
+        cy = grid_floor(center[i * 2 + 0], in_h, ratio);
+        cx = grid_floor(center[i * 2 + 1], in_w, ratio);
+        atomicAdd(&s_cnt[g], 1);
+        if (abs(cy) > 20000 || abs(cx) > 20000) s_big = 1;
+      }
+    }
+    s_tmp[3 * o] = g;
+    s_tmp[3 * o + 1] = cy;
+    s_tmp[3 * o + 2] = cx;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int g = 0; g < kEncGroup; ++g) { s_start[g] = acc; acc += s_cnt[g]; }
+    s_start[kEncGroup] = acc;
+  }
+  __syncthreads();
+  for (int o = tid; o < n_objects; o += kEncThreads) {
+    const int g = s_tmp[3 * o];
+    if (g >= 0) {
+      const int slot = s_start[g] + atomicAdd(&s_fill[g], 1);  // (the order inside a class does not matter: max)
+      s_obj[2 * slot] = s_tmp[3 * o + 1];
+      s_obj[2 * slot + 1] = s_tmp[3 * o + 2];
     }
   }
+  __syncthreads();
+  const bool big = s_big != 0 || H > 10000 || W > 10000;
   const int y0 = band * rows_per_band;
   const int y1 = min(H, y0 + rows_per_band);
-  float* op = out + (size_t)plane * H * W;
-  // ... and while they are in flight the band is zero-filled unconditionally: four planes out of five hold no
-  // object at all, and for the rest the second write below lands on lines that are still in L2.
-  if (VEC) {
-    const int total = (y1 - y0) * (W >> 2);
-    float4* o4 = reinterpret_cast<float4*>(op + (size_t)y0 * W);
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = tid; t < total; t += kEncThreads) o4[t] = z;
-  }
-  if (mine) {
-    const int slot = atomicAdd(&s_n, 1);
-    s_obj[2 * slot] = cy;
-    s_obj[2 * slot + 1] = cx;
-    if (abs(cy) > 20000 || abs(cx) > 20000) s_big = 1;
-  }
-  for (int o = tid + kEncThreads; o < n_objects; o += kEncThreads) {  // (more than 256 objects per frame: rare)
-    const long long i = b * n_objects + o;
-    if (valid[i] && label[i] == c) {
-      const int oy = grid_floor(center[i * 2 + 0], in_h, ratio);
-      const int ox = grid_floor(center[i * 2 + 1], in_w, ratio);
-      const int slot = atomicAdd(&s_n, 1);
-      s_obj[2 * slot] = oy;
-      s_obj[2 * slot + 1] = ox;
-      if (abs(oy) > 20000 || abs(ox) > 20000) s_big = 1;
-    }
-  }
-  __syncthreads();
-  const int n = s_n;
-  const bool big = s_big != 0 || H > 10000 || W > 10000;
 
-  auto value = [&](int y, int x) -> float {
-    if (!big) {
-      int best = 0x7fffffff;
-      for (int j = 0; j < n; ++j) {
-        const int dy = y - s_obj[2 * j], dx = x - s_obj[2 * j + 1];
-        best = min(best, dy * dy + dx * dx);
+  for (int g = 0; g < nc; ++g) {
+    const int j0 = s_start[g], j1 = s_start[g + 1];
+    float* op = out + (((size_t)b * C + c0 + g) * H + y0) * W;
+    auto value = [&](int y, int x) -> float {
+      if (!big) {
+        int best = 0x7fffffff;
+        for (int j = j0; j < j1; ++j) {
+          const int dy = y - s_obj[2 * j], dx = x - s_obj[2 * j + 1];
+          best = min(best, dy * dy + dx * dx);
+        }
+        return gauss_from_d2((long long)best, two_sigma2);
+      } else {
+        long long best = 0x7fffffffffffffffLL;
+        for (int j = j0; j < j1; ++j) {
+          const long long dy = y - s_obj[2 * j], dx = x - s_obj[2 * j + 1];
+          best = min(best, dy * dy + dx * dx);
+        }
+        return gauss_from_d2(best, two_sigma2);
       }
-      return gauss_from_d2((long long)best, two_sigma2);
+    };
+    if (VEC) {
+      const int S = W >> 2;
+      const int total = (y1 - y0) * S;
+      float4* o4 = reinterpret_cast<float4*>(op);
+      if (j0 == j1) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int t = tid; t < total; t += kEncThreads) o4[t] = z;
+      } else {
+        for (int t = tid; t < total; t += kEncThreads) {
+          const int y = y0 + t / S;
+          const int x = (t % S) << 2;
+          float4 v;
+          v.x = value(y, x);
+          v.y = value(y, x + 1);
+          v.z = value(y, x + 2);
+          v.w = value(y, x + 3);
+          o4[t] = v;
+        }
+      }
     } else {
-      long long best = 0x7fffffffffffffffLL;
-      for (int j = 0; j < n; ++j) {
-        const long long dy = y - s_obj[2 * j], dx = x - s_obj[2 * j + 1];
-        best = min(best, dy * dy + dx * dx);
-      }
-      return gauss_from_d2(best, two_sigma2);
+      const int total = (y1 - y0) * W;
+      for (int t = tid; t < total; t += kEncThreads) op[t] = (j0 == j1) ? 0.f : value(y0 + t / W, t % W);
     }
-  };
+  }
+}
 
-  if (VEC) {
-    const int S = W >> 2;
-    const int total = (y1 - y0) * S;
-    float4* o4 = reinterpret_cast<float4*>(op + (size_t)y0 * W);
-    if (n != 0) {
-      for (int t = tid; t < total; t += kEncThreads) {
-        const int y = y0 + t / S;
-        const int x = (t % S) << 2;
-        float4 v;
-        v.x = value(y, x);
-        v.y = value(y, x + 1);
-        v.z = value(y, x + 2);
-        v.w = value(y, x + 3);
-        o4[t] = v;
-      }
+// Frames with at most 32 objects (the usual case): one WARP per 8 KB chunk of a plane, no shared memory and no block
+// barrier.  Lane l reads object l of the frame (the same few lines for every warp of the frame: L1/L2 hits), a
+// ballot says which objects render into this plane; if none do, the chunk is sixteen coalesced 128-bit zero stores per
+// lane, otherwise the matching centres are broadcast with shuffles.  Warps are laid out in memory order, so the CTAs
+// that are resident at any time write one contiguous window of the output, like a plain fill.
+constexpr int kEncWarpStrips = 512;  // 128-bit strips per warp (16 per lane)
+
+__global__ void __launch_bounds__(kEncThreads) gaussian_encode_warp_kernel(
+    const uint8_t* __restrict__ valid, const int64_t* __restrict__ label, const float* __restrict__ center,
+    int n_objects, int C, int H, int W, float in_h, float in_w, float ratio, float two_sigma2, int chunks_per_plane,
+    long long n_chunks, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long chunk_id = (long long)blockIdx.x * (kEncThreads / 32) + (threadIdx.x >> 5);
+  if (chunk_id >= n_chunks) return;
+  const long long plane = chunk_id / chunks_per_plane;
+  const int chunk = (int)(chunk_id - plane * chunks_per_plane);
+  const int c = (int)(plane % C);
+  const long long b = plane / C;
+  bool mine = false;
+  int cy = 0, cx = 0;
+  if (lane < n_objects) {
+    const long long i = b * n_objects + lane;
+    if (__ldg(valid + i) && __ldg(label + i) == c) {
+      mine = true;
+      cy = grid_floor(__ldg(center + i * 2 + 0), in_h, ratio);
+      cx = grid_floor(__ldg(center + i * 2 + 1), in_w, ratio);
     }
-  } else {
-    const int total = (y1 - y0) * W;
-    float* o = op + (size_t)y0 * W;
-    for (int t = tid; t < total; t += kEncThreads) o[t] = (n == 0) ? 0.f : value(y0 + t / W, t % W);
+  }
+  const unsigned mask = __ballot_sync(0xffffffffu, mine);
+  const int S = W >> 2;
+  const int plane_strips = H * S;
+  const int s0 = chunk * kEncWarpStrips;
+  const int s1 = min(plane_strips, s0 + kEncWarpStrips);
+  float4* o4 = reinterpret_cast<float4*>(out + (size_t)plane * H * W);
+  if (mask == 0u) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int t = s0 + lane; t < s1; t += 32) o4[t] = z;
+    return;
+  }
+  const bool big = __any_sync(0xffffffffu, mine && (abs(cy) > 20000 || abs(cx) > 20000)) || H > 10000 || W > 10000;
+  for (int t0 = s0; t0 < s1; t0 += 32) {  // (warp-uniform trip count: the shuffles below need every lane)
+    const int t = t0 + lane;
+    const int y = t / S;
+    const int x = (t - y * S) << 2;
+    float4 v;
+    if (!big) {
+      int b0 = 0x7fffffff, b1 = b0, b2 = b0, b3 = b0;
+      for (unsigned m = mask; m; m &= m - 1) {
+        const int j = __ffs(m) - 1;
+        const int dy = y - __shfl_sync(0xffffffffu, cy, j), dx = x - __shfl_sync(0xffffffffu, cx, j);
+        const int dy2 = dy * dy;
+        b0 = min(b0, dy2 + dx * dx);
+        b1 = min(b1, dy2 + (dx + 1) * (dx + 1));
+        b2 = min(b2, dy2 + (dx + 2) * (dx + 2));
+        b3 = min(b3, dy2 + (dx + 3) * (dx + 3));
+      }
+      v = make_float4(gauss_from_d2(b0, two_sigma2), gauss_from_d2(b1, two_sigma2), gauss_from_d2(b2, two_sigma2),
+                      gauss_from_d2(b3, two_sigma2));
+    } else {
+      long long b0 = 0x7fffffffffffffffLL, b1 = b0, b2 = b0, b3 = b0;
+      for (unsigned m = mask; m; m &= m - 1) {
+        const int j = __ffs(m) - 1;
+        const long long dy = y - __shfl_sync(0xffffffffu, cy, j), dx = x - __shfl_sync(0xffffffffu, cx, j);
+        const long long dy2 = dy * dy;
+        b0 = min(b0, dy2 + dx * dx);
+        b1 = min(b1, dy2 + (dx + 1) * (dx + 1));
+        b2 = min(b2, dy2 + (dx + 2) * (dx + 2));
+        b3 = min(b3, dy2 + (dx + 3) * (dx + 3));
+      }
+      v = make_float4(gauss_from_d2(b0, two_sigma2), gauss_from_d2(b1, two_sigma2), gauss_from_d2(b2, two_sigma2),
+                      gauss_from_d2(b3, two_sigma2));
+    }
+    if (t < s1) o4[t] = v;
   }
 }
 
@@ -326,20 +408,31 @@ extern "C" int tauv_gaussian_encode(const uint8_t* valid, const int64_t* label, 
   TAUV_REQUIRE(n_objects == 0 || (valid && label && center), TAUV_E_NULL, "valid/label/center must not be NULL");
   TAUV_REQUIRE(in_h > 0 && in_w > 0 && downsample_ratio > 0, TAUV_E_SHAPE, "bad model geometry");
   TAUV_REQUIRE(n_objects <= 4096, TAUV_E_UNSUPPORTED, "n_objects=%d exceeds the built-in limit 4096", n_objects);
-  const long long planes = (long long)B * C;
+  const int groups = (C + kEncGroup - 1) / kEncGroup;
   int bands, rows;
-  band_plan(H, W, planes, &bands, &rows);
-  const long long grid = planes * bands;
+  band_plan(H, W, (long long)B * groups, &bands, &rows);
+  const long long grid = (long long)B * groups * bands;
   TAUV_REQUIRE(grid < (1LL << 31), TAUV_E_UNSUPPORTED, "grid too large");
-  const size_t smem = (size_t)(n_objects > 0 ? n_objects : 1) * 8;
+  const size_t smem = (size_t)(n_objects > 0 ? n_objects : 1) * 20;
   const bool vec = (W % 4 == 0) && ((uintptr_t)out % 16 == 0);
   const float ts = two_sigma_sq(sigma);
-  if (vec)
+  if (vec && n_objects <= 32) {
+    const long long plane_strips = (long long)H * (W / 4);
+    const long long cpp = (plane_strips + kEncWarpStrips - 1) / kEncWarpStrips;
+    const long long n_chunks = (long long)B * C * cpp;
+    const long long wgrid = (n_chunks + kEncThreads / 32 - 1) / (kEncThreads / 32);
+    TAUV_REQUIRE(wgrid < (1LL << 31) && cpp < (1LL << 31), TAUV_E_UNSUPPORTED, "grid too large");
+    gaussian_encode_warp_kernel<<<(unsigned)wgrid, kEncThreads, 0, (cudaStream_t)stream>>>(
+        valid, label, center, n_objects, C, H, W, (float)in_h, (float)in_w, (float)downsample_ratio, ts, (int)cpp,
+        n_chunks, out);
+  } else if (vec)
     gaussian_encode_kernel<true><<<(unsigned)grid, kEncThreads, smem, (cudaStream_t)stream>>>(
-        valid, label, center, n_objects, C, H, W, (float)in_h, (float)in_w, (float)downsample_ratio, ts, bands, rows, out);
+        valid, label, center, n_objects, C, H, W, (float)in_h, (float)in_w, (float)downsample_ratio, ts, groups, bands,
+        rows, out);
   else
     gaussian_encode_kernel<false><<<(unsigned)grid, kEncThreads, smem, (cudaStream_t)stream>>>(
-        valid, label, center, n_objects, C, H, W, (float)in_h, (float)in_w, (float)downsample_ratio, ts, bands, rows, out);
+        valid, label, center, n_objects, C, H, W, (float)in_h, (float)in_w, (float)downsample_ratio, ts, groups, bands,
+        rows, out);
   TAUV_LAUNCH_CHECK("gaussian_encode_kernel");
   return 0;
 }

@@ -290,7 +290,8 @@ def test_encode_golden(cn):
     assert_equal(cn.L.offset_target(truth.center, mc), g["offset"])
 
 
-@pytest.mark.parametrize("B,n,C,H,W,ds", [(3, 5, 4, 13, 11, 1), (2, 16, 80, 128, 128, 2), (1, 0, 2, 8, 8, 2)])
+@pytest.mark.parametrize("B,n,C,H,W,ds", [(3, 5, 4, 13, 11, 1), (2, 16, 80, 128, 128, 2), (1, 0, 2, 8, 8, 2),
+                                              (2, 40, 19, 24, 36, 2), (1, 32, 3, 40, 20, 1), (2, 7, 9, 30, 44, 2)])
 def test_encode_vs_oracle(cn, B, n, C, H, W, ds):
     ratio = 2 ** ds
     mc = SimpleNamespace(in_h=H * ratio, in_w=W * ratio, downsample_ratio=ratio, out_h=H, out_w=W)
