@@ -6,14 +6,14 @@
 
 Workload (BASELINE.json configs[1]): CenterNet decode + Gaussian target encode of a batch of 64 synthetic
 512x512 frames per GPU (stride 4 -> 80 classes x 128x128 heatmaps, top-100, 16 objects per frame).
-One step = decode (2 kernels) + encode (1 kernel) over the batch.  Frames are independent, so N GPUs each
+One step = decode (1 kernel) + encode (1 kernel) over the batch.  Frames are independent, so N GPUs each
 take their own 64 frames (weak scaling, no collective on the data path; NCCL only carries the timing scalar).
 
 value     : frames/s with inputs resident in HBM, CUDA events around exactly K steps, max over ranks.
 e2e       : the same step through the public Python API with pinned HOST inputs copied in and the packed
             detections + a target checksum copied out inside the timed region.
-roofline  : the dominant kernel (tile_topk_kernel, reads the 335.5 MB of logits once), timed live with
-            events between the two decode launches, against MEASURED_PEAKS.json.
+roofline  : the dominant kernel (tile_cluster_kernel: the whole decode, reads the 335.5 MB of logits once), timed
+            live with events around its launch, against MEASURED_PEAKS.json.
 cpu_baseline / --impl reference : the CPU oracle port (oracle/ref_port.py, torch-CPU with all host threads)
             on a bounded sample of the same workload.
 """
@@ -47,9 +47,9 @@ def peaks():
     return 6650.0, "fallback"
 
 
-def algorithmic_bytes_decode_tile(B):
-    # read the logits once (+ the candidate table written by the tile kernel, negligible)
-    return 4 * B * C * H * W
+def algorithmic_bytes_decode(B):
+    # read the logits once + index/label/score (2*8+8+4) + size/offset gathers (16) + packed boxes (24)
+    return 4 * B * C * H * W + B * K_DET * (28 + 16 + 24)
 
 
 def algorithmic_bytes_encode(B):
@@ -223,7 +223,7 @@ def main():
         torch.cuda.synchronize()
 
     K = args.steps
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
 
     # outputs are allocated once and overwritten every step (a real pipeline re-uses its buffers too); the truth
     # tensors are already in the dtypes / layout the encoder takes, so a step is three kernel launches and nothing else
@@ -235,9 +235,11 @@ def main():
             det = D.decode_packed(pred, mc, K_DET, THR, out=det_buf)
             tgt = L.generate_heatmap(truth, mc, tc, oc, out=tgt_buf)
         else:
-            det = D.decode_packed(pred, mc, K_DET, THR, stage_events=events[:3], out=det_buf)
+            events[0].record()
+            det = D.decode_packed(pred, mc, K_DET, THR, out=det_buf)
+            events[1].record()
             tgt = L.generate_heatmap(truth, mc, tc, oc, out=tgt_buf)
-            events[3].record()
+            events[2].record()
         return det, tgt
 
     for _ in range(args.warmup):
@@ -251,9 +253,8 @@ def main():
         end.record()
         barrier()
     total_ms = start.elapsed_time(end)
-    t_tile = sum(e[0].elapsed_time(e[1]) for e in ev) / K
-    t_merge = sum(e[1].elapsed_time(e[2]) for e in ev) / K
-    t_enc = sum(e[2].elapsed_time(e[3]) for e in ev) / K
+    t_dec = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    t_enc = sum(e[1].elapsed_time(e[2]) for e in ev) / K
     n_keep_mean = float(det.count.float().mean())
 
     # ---- e2e: pinned host inputs in, packed detections + target checksum out, every step ----
@@ -298,21 +299,21 @@ def main():
     e2e_ms = es.elapsed_time(ee)  # device clock around the whole loop (each step ends with a blocking D2H)
 
     # ---- max over ranks ----
-    times = torch.tensor([total_ms, e2e_ms, t_tile, t_merge, t_enc], device=device, dtype=torch.float64)
+    times = torch.tensor([total_ms, e2e_ms, t_dec, t_enc], device=device, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, t_tile, t_merge, t_enc = times.tolist()
+    total_ms, e2e_ms, t_dec, t_enc = times.tolist()
 
     if rank == 0:
         hbm_gbs, peak_src = peaks()
         frames = B_PER_GPU * world
         value = frames * K / (total_ms * 1e-3)
         e2e_value = frames * args.e2e_steps / (e2e_ms * 1e-3)
-        achieved = algorithmic_bytes_decode_tile(B_PER_GPU) / (t_tile * 1e-3) / 1e9
+        achieved = algorithmic_bytes_decode(B_PER_GPU) / (t_dec * 1e-3) / 1e9
         traffic = None
         tp = ROOT / "profiles" / "traffic.json"
         if tp.exists():
-            traffic = json.loads(tp.read_text()).get("tile_topk_kernel_bytes_per_launch")
+            traffic = json.loads(tp.read_text()).get("tile_cluster_kernel_bytes_per_launch")
         cpu = None
         if not args.no_cpu_baseline:
             fps, per = cpu_reference_sample(B_PER_GPU, 5)
@@ -325,19 +326,19 @@ def main():
             "config": {"workload": WORKLOAD, "frames_per_gpu": B_PER_GPU, "global_batch": frames,
                        "l2": "inputs larger than L2 (335.5 MB logits + 335.5 MB targets per step vs 126 MB L2)",
                        "mean_detections_per_frame": n_keep_mean},
-            "roofline": {"bound": "hbm", "kernel": "tile_topk_kernel<SIGMOID_PEAK,bulk>", "achieved": achieved,
-                         "peak": hbm_gbs, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                         "traffic": traffic, "algorithmic_bytes": algorithmic_bytes_decode_tile(B_PER_GPU),
-                         "us_per_launch": t_tile * 1e3},
+            "roofline": {"bound": "hbm", "kernel": "tile_cluster_kernel<SIGMOID_PEAK> (whole decode: peaks, top-k, boxes)",
+                         "achieved": achieved, "peak": hbm_gbs, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": achieved / hbm_gbs, "traffic": traffic,
+                         "algorithmic_bytes": algorithmic_bytes_decode(B_PER_GPU), "us_per_launch": t_dec * 1e3},
             "kernels": {
-                "tile_topk_us": t_tile * 1e3, "merge_us": t_merge * 1e3, "gaussian_encode_us": t_enc * 1e3,
+                "decode_us": t_dec * 1e3, "gaussian_encode_us": t_enc * 1e3,
                 "gaussian_encode_gbs": algorithmic_bytes_encode(B_PER_GPU) / (t_enc * 1e-3) / 1e9,
                 "gaussian_encode_frac": algorithmic_bytes_encode(B_PER_GPU) / (t_enc * 1e-3) / 1e9 / hbm_gbs,
             },
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps},
-            "gpu_launches": 3 * K,
+            "gpu_launches": 2 * K,
             "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)

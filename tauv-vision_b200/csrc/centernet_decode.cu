@@ -79,6 +79,17 @@ static int make_plan(int B, int C, int H, int W, int k, const void* ptr, TopkPla
 // ----------------------------------------------------------------------------------------------
 // K1
 // ----------------------------------------------------------------------------------------------
+// per-detection gather + box arithmetic of decode()/decode_keypoints() (optional tail of the ranked output)
+struct BoxArgs {
+  int enabled;
+  const float* size; long long ss[4];
+  const float* offset; long long os[4];
+  const float* depth; long long ds[3];
+  int mode, ratio, in_h, in_w, out_h, out_w;
+  float thr;
+  double* yx; float* hw; float* depth_out; int* count;
+};
+
 struct TileArgs {
   const float* hm;
   int B, C, H, W, k;
@@ -87,6 +98,13 @@ struct TileArgs {
   unsigned long long* cand;  // [B*items_per_frame][k]
   int* cand_count;           // [B*items_per_frame]
   uint32_t* frame_state;     // [B][kFrameStateWords], zeroed before the launch
+  // fused tail (cluster kernel, whole-frame units): the cluster selects the frame's top-k itself and writes the ranked
+  // outputs, so no candidate table and no merge launch are needed
+  int fuse;
+  int64_t* out_index;
+  int64_t* out_label;
+  float* out_score;
+  BoxArgs box;
   long long* trace;          // debug: per item {t_start, t_boot, t_scan, t_end, n_list, thr_key_at_start, 0, 0} or NULL
 };
 
@@ -533,6 +551,132 @@ __global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(const __grid_co
 }
 
 // ----------------------------------------------------------------------------------------------
+// Frame-level selection and ranked output (shared by the merge kernel and the cluster kernel's fused tail)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void box_one(const BoxArgs& g, int b, long long slot, int iy, int ix) {
+  const float h = g.size[b * g.ss[0] + iy * g.ss[1] + ix * g.ss[2]];
+  const float w = g.size[b * g.ss[0] + iy * g.ss[1] + ix * g.ss[2] + g.ss[3]];
+  g.hw[slot * 2 + 0] = h;
+  g.hw[slot * 2 + 1] = w;
+  if (g.mode == TAUV_BOX_DECODE) {
+    // decode.py:214-215: Python doubles
+    const float oy = g.offset[b * g.os[0] + iy * g.os[1] + ix * g.os[2]];
+    const float ox = g.offset[b * g.os[0] + iy * g.os[1] + ix * g.os[2] + g.os[3]];
+    g.yx[slot * 2 + 0] = __ddiv_rn(__dadd_rn(__dmul_rn((double)g.ratio, (double)iy), (double)oy), (double)g.in_h);
+    g.yx[slot * 2 + 1] = __ddiv_rn(__dadd_rn(__dmul_rn((double)g.ratio, (double)ix), (double)ox), (double)g.in_w);
+  } else {
+    // decode.py:87-88: int64 tensor / int -> fp32 true divide, then float()
+    g.yx[slot * 2 + 0] = (double)__fdiv_rn((float)iy, (float)g.out_h);
+    g.yx[slot * 2 + 1] = (double)__fdiv_rn((float)ix, (float)g.out_w);
+  }
+  if (g.depth != nullptr && g.depth_out != nullptr) {
+    const float d = g.depth[b * g.ds[0] + iy * g.ds[1] + ix * g.ds[2]];
+    float inv = __fdiv_rn(1.0f, sigmoid_ref(d));
+    if (g.mode == TAUV_BOX_DECODE) inv = __fsub_rn(inv, 1.0f);  // decode.py:324
+    g.depth_out[slot] = inv;
+  }
+}
+
+// Select the k best of pool[0, total) (distinct composite keys, in shared memory) into sel[0, npos), npos = min(k, total),
+// unordered.  sel must hold p2 = next_pow2(k) entries and is zero-padded.  All NT threads of the CTA call this.
+template <int NT>
+__device__ int topk_select_pool(const unsigned long long* pool, int total, int k, int p2, unsigned long long* sel,
+                                uint32_t* hist, uint32_t* ctl) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < p2; i += NT) sel[i] = 0ull;
+  if (tid == 0) ctl[5] = 0;
+  __syncthreads();
+  unsigned long long T = 1ull;  // total <= k: everything valid (non-zero) is selected
+  if (total > k) T = block_kth_largest<NT>([&](int i) { return pool[i]; }, total, k, hist, ctl);
+  for (int i = tid; i < total; i += NT) {
+    const unsigned long long c = pool[i];
+    if (c >= T && c != 0ull) sel[atomicAdd(&ctl[5], 1u)] = c;
+  }
+  __syncthreads();
+  return (int)ctl[5];
+}
+
+// Sort sel[0, p2) descending and write the frame's ranked outputs: index/label/score for the npos selected peaks,
+// then (SIGMOID_PEAK) the zero-valued fillers a dense stable top-k would return, the box arithmetic, and the count of
+// leading entries at or above the score threshold.  flags: k words of shared memory (may alias the radix histogram).
+template <int MODE, int NT>
+__device__ void topk_emit_ranked(unsigned long long* sel, int p2, int npos, uint32_t* flags, int b, int k, int H, int W,
+                                 int64_t* __restrict__ index, int64_t* __restrict__ label, float* __restrict__ score,
+                                 const BoxArgs& g) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int s_first_below;
+  __shared__ int s_wsum[NT / 32];
+  if (tid == 0) s_first_below = k;
+  block_bitonic_sort_desc<NT>(sel, p2);
+  const long long hw_elems = (long long)H * W;
+  for (int r = tid; r < npos; r += NT) {
+    const unsigned long long c = sel[r];
+    const uint32_t flat = composite_idx(c);
+    const float s = key_to_float(composite_key(c));
+    const long long lab = flat / hw_elems;
+    const long long rem = flat - lab * hw_elems;
+    const int iy = (int)(rem / W), ix = (int)(rem - (long long)iy * W);
+    const long long slot = (long long)b * k + r;
+    index[slot * 2 + 0] = iy;
+    index[slot * 2 + 1] = ix;
+    label[slot] = lab;
+    score[slot] = s;
+    if (g.enabled) {
+      box_one(g, b, slot, iy, ix);
+      if (s < g.thr) atomicMin(&s_first_below, r);
+    }
+  }
+  if (MODE == TAUV_TOPK_SIGMOID_PEAK && npos < k) {
+    // Dense stable top-k semantics: the remaining slots are zero-valued cells in ascending flat index.  At most
+    // npos of the first k cells are positive peaks, so [0,k) always suffices.
+    __syncthreads();
+    for (int i = tid; i < k; i += NT) flags[i] = 0u;
+    __syncthreads();
+    for (int r = tid; r < npos; r += NT) {
+      const uint32_t flat = composite_idx(sel[r]);
+      if (flat < (uint32_t)k) flags[flat] = 1u;
+    }
+    __syncthreads();
+    const int need = k - npos;
+    int base = 0;
+    for (int start = 0; start < k && base < need; start += NT) {
+      const int i = start + tid;
+      const bool freec = (i < k) && (flags[i] == 0u);
+      const unsigned bal = __ballot_sync(0xffffffffu, freec);
+      if (lane == 0) s_wsum[warp] = __popc(bal);
+      __syncthreads();
+      int pos = base + __popc(bal & ((1u << lane) - 1u));
+      int tot = 0;
+      for (int w = 0; w < NT / 32; ++w) {
+        if (w < warp) pos += s_wsum[w];
+        tot += s_wsum[w];
+      }
+      if (freec && pos < need) {
+        const int r = npos + pos;
+        const long long lab = i / hw_elems;
+        const long long rem = i - lab * hw_elems;
+        const int iy = (int)(rem / W), ix = (int)(rem - (long long)iy * W);
+        const long long slot = (long long)b * k + r;
+        index[slot * 2 + 0] = iy;
+        index[slot * 2 + 1] = ix;
+        label[slot] = lab;
+        score[slot] = 0.0f;
+        if (g.enabled) {
+          box_one(g, b, slot, iy, ix);
+          if (0.0f < g.thr) atomicMin(&s_first_below, r);
+        }
+      }
+      base += tot;
+      __syncthreads();
+    }
+  }
+  if (g.enabled) {
+    __syncthreads();
+    if (tid == 0) g.count[b] = s_first_below;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // K1 (vectorised path): one thread-block cluster per "unit" (a frame, or a contiguous share of a frame's items)
 // ----------------------------------------------------------------------------------------------
 // The rejection threshold of a unit and the candidate histogram it is derived from live in the DISTRIBUTED SHARED
@@ -866,11 +1010,81 @@ __device__ __noinline__ void cl_bootstrap_round(const TileArgs& a, TileCtx* ctx,
   const int c_end = min(g.e1, g.e0 + kBootElems);
   int fl = 0;
   if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
-#pragma unroll 1
+    // Every cell of the round gets the 3x3 test from the tile.  A ninth of them are peaks: they are kept in registers
+    // and appended to the list at offsets from one block-wide scan — no atomics (pushed one by one through a
+    // shared-memory counter they serialise and cost several microseconds here).
+    const int W = a.W, H = a.H;
+    const float NI = TAUV_NEG_INF;
+    float pv[kRoundW * 4];
+    uint32_t pmask = 0;
+#pragma unroll
     for (int u = 0; u < kRoundW; ++u) {
       const int off = g.e0 + ((u * kTileThreads + tid) << 2);
-      if (off < c_end) fl |= examine<MODE, true, true>(a, ctx, list, tile, g.plane_flat0, off, origin);
+      if (off < c_end) {
+        const int r = off / W, col = off - r * W;
+        const float* p1 = tile + (off - origin);
+        const float4 x = *reinterpret_cast<const float4*>(p1);
+        const bool hl = col > 0, hr = col + 4 < W;
+        float4 up = make_float4(NI, NI, NI, NI), dn = up;
+        float ul = NI, ur = NI, dl = NI, dr = NI;
+        if (r > 0) {
+          up = *reinterpret_cast<const float4*>(p1 - W);
+          if (hl) ul = p1[-W - 1];
+          if (hr) ur = p1[-W + 4];
+        }
+        if (r + 1 < H) {
+          dn = *reinterpret_cast<const float4*>(p1 + W);
+          if (hl) dl = p1[W - 1];
+          if (hr) dr = p1[W + 4];
+        }
+        const float ml = hl ? p1[-1] : NI, mr = hr ? p1[4] : NI;
+        float cm[6];
+        cm[0] = fmaxf(fmaxf(ul, ml), dl);
+        cm[1] = fmaxf(fmaxf(up.x, x.x), dn.x);
+        cm[2] = fmaxf(fmaxf(up.y, x.y), dn.y);
+        cm[3] = fmaxf(fmaxf(up.z, x.z), dn.z);
+        cm[4] = fmaxf(fmaxf(up.w, x.w), dn.w);
+        cm[5] = fmaxf(fmaxf(ur, mr), dr);
+        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const float xv = xs[cc];
+          const float m = fmaxf(fmaxf(cm[cc], cm[cc + 1]), cm[cc + 2]);
+          bool peak = (xv >= m);
+          if (!peak && (xv > 4.0f || m < -80.0f || (m - xv) < 1e-3f)) peak = sigmoid_tie(xv, m);
+          pv[u * 4 + cc] = xv;
+          if (peak) pmask |= 1u << (u * 4 + cc);
+        }
+      }
     }
+    // block-wide exclusive scan of the per-thread peak counts
+    const int lane = tid & 31, warp = tid >> 5;
+    const int mine = __popc(pmask);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) ctx->wsum[warp] = incl;
+    __syncthreads();
+    int base = incl - mine, total = 0;
+    for (int w = 0; w < kTileThreads / 32; ++w) {
+      if (w < warp) base += ctx->wsum[w];
+      total += ctx->wsum[w];
+    }
+    if (total > a.cap) {
+      fl = 2;  // (plateaus) the whole unit is redone safely
+    } else {
+#pragma unroll
+      for (int i = 0; i < kRoundW * 4; ++i) {
+        if (pmask & (1u << i)) {
+          const int off = g.e0 + (((i >> 2) * kTileThreads + tid) << 2) + (i & 3);
+          list[base++] = make_composite(float_to_key(pv[i]), g.plane_flat0 + (uint32_t)off);
+        }
+      }
+    }
+    if (tid == 0) ctx->count = total > a.cap ? 0 : total;
   } else {
     // RAW: every cell is a candidate; keep this round's k best (exact selection straight from the tile)
     const int n = c_end - g.e0;
@@ -1038,6 +1252,40 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
       }
     }
 
+    if (a.fuse) {
+      // ---- fused tail (parts == 1): every CTA reduces its list to its exact top-k in place, rank 0 gathers the
+      // eight lists through distributed shared memory, and — once the others are released — selects the frame's
+      // top-k and writes the ranked outputs.
+      const int n = ctx->count;
+      convert_entries<MODE>(ctx, list, n);
+      const unsigned long long T = block_kth_largest<kTileThreads>([&](int i) { return list[i]; }, n, a.k, hist, ctx->sel);
+      compact_list(ctx, list, n, [&](unsigned long long c) { return c >= T && c != 0ull; });
+      if (tid == 0) ctx->emit = (uint32_t)ctx->base;
+      cluster.sync();  // (3a) all eight lists are final
+      __shared__ int s_total;
+      if (rank == 0) {
+        int off = (int)ctx->emit;
+        for (int r = 1; r < kClSize; ++r) {
+          const int cnt = (int)*cluster.map_shared_rank(&ctx->emit, r);
+          const unsigned long long* rl = cluster.map_shared_rank(list, r);
+          for (int i = tid; i < cnt; i += kTileThreads) list[off + i] = rl[i];
+          off += cnt;
+        }
+        if (tid == 0) s_total = off;
+      }
+      cluster.sync();  // (3) nobody touches this unit's distributed state any more
+      if (rank == 0) {
+        __shared__ uint32_t s_ctl[8];
+        int p2 = 1;
+        while (p2 < a.k) p2 <<= 1;
+        unsigned long long* sel = reinterpret_cast<unsigned long long*>(tile);
+        const int npos = topk_select_pool<kTileThreads>(list, s_total, a.k, p2, sel, hist, s_ctl);
+        topk_emit_ranked<MODE, kTileThreads>(sel, p2, npos, hist, frame, a.k, a.H, a.W, a.out_index, a.out_label,
+                                             a.out_score, a.box);
+        __syncthreads();
+      }
+      continue;
+    }
     // ---- the CTA's candidates of the whole unit: exact top-k, one row of the candidate table
     {
       const int row = frame * a.rows_per_frame + part * kClSize + rank;
@@ -1065,42 +1313,8 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
 }
 
 // ----------------------------------------------------------------------------------------------
-// K2: per-frame merge (+ optional box decode)
+// K2: per-frame merge (+ optional box decode) of the candidate table
 // ----------------------------------------------------------------------------------------------
-struct BoxArgs {
-  int enabled;
-  const float* size; long long ss[4];
-  const float* offset; long long os[4];
-  const float* depth; long long ds[3];
-  int mode, ratio, in_h, in_w, out_h, out_w;
-  float thr;
-  double* yx; float* hw; float* depth_out; int* count;
-};
-
-__device__ __forceinline__ void box_one(const BoxArgs& g, int b, long long slot, int iy, int ix) {
-  const float h = g.size[b * g.ss[0] + iy * g.ss[1] + ix * g.ss[2]];
-  const float w = g.size[b * g.ss[0] + iy * g.ss[1] + ix * g.ss[2] + g.ss[3]];
-  g.hw[slot * 2 + 0] = h;
-  g.hw[slot * 2 + 1] = w;
-  if (g.mode == TAUV_BOX_DECODE) {
-    // decode.py:214-215: Python doubles
-    const float oy = g.offset[b * g.os[0] + iy * g.os[1] + ix * g.os[2]];
-    const float ox = g.offset[b * g.os[0] + iy * g.os[1] + ix * g.os[2] + g.os[3]];
-    g.yx[slot * 2 + 0] = __ddiv_rn(__dadd_rn(__dmul_rn((double)g.ratio, (double)iy), (double)oy), (double)g.in_h);
-    g.yx[slot * 2 + 1] = __ddiv_rn(__dadd_rn(__dmul_rn((double)g.ratio, (double)ix), (double)ox), (double)g.in_w);
-  } else {
-    // decode.py:87-88: int64 tensor / int -> fp32 true divide, then float()
-    g.yx[slot * 2 + 0] = (double)__fdiv_rn((float)iy, (float)g.out_h);
-    g.yx[slot * 2 + 1] = (double)__fdiv_rn((float)ix, (float)g.out_w);
-  }
-  if (g.depth != nullptr && g.depth_out != nullptr) {
-    const float d = g.depth[b * g.ds[0] + iy * g.ds[1] + ix * g.ds[2]];
-    float inv = __fdiv_rn(1.0f, sigmoid_ref(d));
-    if (g.mode == TAUV_BOX_DECODE) inv = __fsub_rn(inv, 1.0f);  // decode.py:324
-    g.depth_out[slot] = inv;
-  }
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(kMergeThreads) merge_kernel(
     const unsigned long long* __restrict__ cand, const int* __restrict__ cand_count,
@@ -1114,10 +1328,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(
   unsigned long long* sel = reinterpret_cast<unsigned long long*>(smem_raw);                 // [p2]
   unsigned long long* pool = sel + p2;                                                        // [pool_cap]
   uint32_t* hist = reinterpret_cast<uint32_t*>(pool + pool_cap);                              // [max(2048,k)]
-  uint32_t* flags = hist;                                                                     // reused: [k]
   __shared__ uint32_t ctl[8];
-  __shared__ int s_total, s_first_below, s_pool_n;
-  __shared__ int s_wsum[kMergeThreads / 32];
+  __shared__ int s_total, s_pool_n;
 
   const unsigned long long* fc = cand + (size_t)b * items_per_frame * k;
   const int* cnt = cand_count + (size_t)b * items_per_frame;
@@ -1125,11 +1337,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(
 
   if (tid == 0) {
     s_total = 0;
-    s_first_below = k;
     s_pool_n = 0;
-    ctl[5] = 0;
   }
-  for (int i = tid; i < p2; i += kMergeThreads) sel[i] = 0ull;
   __syncthreads();
   int part = 0;
   for (int i = tid; i < items_per_frame; i += kMergeThreads) part += cnt[i];
@@ -1137,10 +1346,10 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(
   __syncthreads();
   const int total = s_total;
 
-  unsigned long long T = 1ull;  // total <= k: everything valid (non-zero) is selected
+  int npos;
   if (total <= pool_cap) {
     // usual case (items reject most of their candidates against the frame threshold): pull the frame's
-    // candidates into shared memory once, one warp per item, then select there
+    // candidates into shared memory once, one warp per row, then select there
     for (int it = warp; it < items_per_frame; it += kMergeThreads / 32) {
       const int c = cnt[it];
       if (c == 0) continue;
@@ -1150,94 +1359,26 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(
       for (int i = lane; i < c; i += 32) pool[base + i] = fc[(size_t)it * k + i];
     }
     __syncthreads();
-    if (total > k) T = block_kth_largest<kMergeThreads>([&](int i) { return pool[i]; }, total, k, hist, ctl);
-    for (int i = tid; i < total; i += kMergeThreads) {
-      const unsigned long long c = pool[i];
-      if (c >= T && c != 0ull) sel[atomicAdd(&ctl[5], 1u)] = c;
-    }
+    npos = topk_select_pool<kMergeThreads>(pool, total, k, p2, sel, hist, ctl);
   } else {
-    // candidates live in a padded [items][k] table: slot i is valid iff (i % k) < cnt[i / k]
+    // candidates live in a padded [rows][k] table: slot i is valid iff (i % k) < cnt[i / k]
     auto load = [&](int i) -> unsigned long long {
       const int it = i / k;
       return (i - it * k) < cnt[it] ? fc[i] : 0ull;  // 0 never beats a real composite
     };
+    for (int i = tid; i < p2; i += kMergeThreads) sel[i] = 0ull;
+    if (tid == 0) ctl[5] = 0;
+    __syncthreads();
+    unsigned long long T = 1ull;
     if (total > k) T = block_kth_largest<kMergeThreads>(load, nslots, k, hist, ctl);
     for (int i = tid; i < nslots; i += kMergeThreads) {
       const unsigned long long c = load(i);
       if (c >= T && c != 0ull) sel[atomicAdd(&ctl[5], 1u)] = c;
     }
-  }
-  __syncthreads();
-  const int npos = (int)ctl[5];  // = min(k, total)
-  block_bitonic_sort_desc<kMergeThreads>(sel, p2);
-
-  // ---- ranked outputs ----
-  const long long hw_elems = (long long)H * W;
-  for (int r = tid; r < npos; r += kMergeThreads) {
-    const unsigned long long c = sel[r];
-    const uint32_t flat = composite_idx(c);
-    const float s = key_to_float(composite_key(c));
-    const long long lab = flat / hw_elems;
-    const long long rem = flat - lab * hw_elems;
-    const int iy = (int)(rem / W), ix = (int)(rem - (long long)iy * W);
-    const long long slot = (long long)b * k + r;
-    index[slot * 2 + 0] = iy;
-    index[slot * 2 + 1] = ix;
-    label[slot] = lab;
-    score[slot] = s;
-    if (g.enabled) {
-      box_one(g, b, slot, iy, ix);
-      if (s < g.thr) atomicMin(&s_first_below, r);
-    }
-  }
-  if (MODE == TAUV_TOPK_SIGMOID_PEAK && npos < k) {
-    // Dense stable top-k semantics: the remaining slots are zero-valued cells in ascending flat index.  At most
-    // npos of the first k cells are positive peaks, so [0,k) always suffices.
     __syncthreads();
-    for (int i = tid; i < k; i += kMergeThreads) flags[i] = 0u;
-    __syncthreads();
-    for (int r = tid; r < npos; r += kMergeThreads) {
-      const uint32_t flat = composite_idx(sel[r]);
-      if (flat < (uint32_t)k) flags[flat] = 1u;
-    }
-    __syncthreads();
-    const int need = k - npos;
-    int base = 0;
-    for (int start = 0; start < k && base < need; start += kMergeThreads) {
-      const int i = start + tid;
-      const bool freec = (i < k) && (flags[i] == 0u);
-      const unsigned bal = __ballot_sync(0xffffffffu, freec);
-      if (lane == 0) s_wsum[warp] = __popc(bal);
-      __syncthreads();
-      int pos = base + __popc(bal & ((1u << lane) - 1u));
-      int tot = 0;
-      for (int w = 0; w < kMergeThreads / 32; ++w) {
-        if (w < warp) pos += s_wsum[w];
-        tot += s_wsum[w];
-      }
-      if (freec && pos < need) {
-        const int r = npos + pos;
-        const long long lab = i / hw_elems;
-        const long long rem = i - lab * hw_elems;
-        const int iy = (int)(rem / W), ix = (int)(rem - (long long)iy * W);
-        const long long slot = (long long)b * k + r;
-        index[slot * 2 + 0] = iy;
-        index[slot * 2 + 1] = ix;
-        label[slot] = lab;
-        score[slot] = 0.0f;
-        if (g.enabled) {
-          box_one(g, b, slot, iy, ix);
-          if (0.0f < g.thr) atomicMin(&s_first_below, r);
-        }
-      }
-      base += tot;
-      __syncthreads();
-    }
+    npos = (int)ctl[5];
   }
-  if (g.enabled) {
-    __syncthreads();
-    if (tid == 0) g.count[b] = s_first_below;
-  }
+  topk_emit_ranked<MODE, kMergeThreads>(sel, p2, npos, hist, b, k, H, W, index, label, score, g);
 }
 
 // Stand-alone box stage for callers that already hold index/score (tauv_centernet_boxes).
@@ -1336,14 +1477,26 @@ static int plan_and_check(const float* hm, int B, int C, int H, int W, int k, vo
   a->cand_count = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws) + p->cand_bytes);
   a->frame_state = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(ws) + p->cand_bytes + p->count_bytes);
   a->trace = g_debug_trace;
+  a->fuse = 0; a->out_index = nullptr; a->out_label = nullptr; a->out_score = nullptr;
+  a->box = BoxArgs{};
   const long long items = (long long)B * p->items_per_frame;
   TAUV_REQUIRE(items < (1LL << 31), TAUV_E_UNSUPPORTED, "too many items (%lld)", items);
   return 0;
 }
 
-// stage 1: per-item candidates into the workspace
+// What the fused tail of the cluster kernel writes (run_topk hands this in; the two-stage API never fuses).
+struct FuseOut {
+  int64_t* index;
+  int64_t* label;
+  float* score;
+  const BoxArgs* box;
+};
+
+// stage 1: per-item candidates into the workspace — or, when `fo` is given and the launch qualifies (whole-frame
+// units, 8k candidates fit the list), the complete ranked output (*fused = true: stage 2 must be skipped)
 static int run_stage1(const float* hm, int B, int C, int H, int W, int k, int mode, void* ws, size_t ws_bytes,
-                      cudaStream_t st) {
+                      cudaStream_t st, const FuseOut* fo = nullptr, bool* fused = nullptr) {
+  if (fused) *fused = false;
   TopkPlan p;
   TileArgs a;
   if (int e = plan_and_check(hm, B, C, H, W, k, ws, ws_bytes, &p, &a)) return e;
@@ -1412,6 +1565,17 @@ static int run_stage1(const float* hm, int B, int C, int H, int W, int k, int mo
   }
   const long long n_units = (long long)B * parts;
   const long long ncl_used = n_units < ncl ? n_units : ncl;
+  int p2 = 1;
+  while (p2 < k) p2 <<= 1;
+  if (fo && fused && parts == 1 && (long long)kClSize * k <= p.cap && (size_t)p2 * 8 <= (size_t)(kBootElems + 2 * W + 8) * 4 &&
+      k <= kRadixBins && !getenv("TAUV_NO_FUSE")) {
+    a.fuse = 1;
+    a.out_index = fo->index;
+    a.out_label = fo->label;
+    a.out_score = fo->score;
+    a.box = *fo->box;
+    *fused = true;
+  }
   cfg.gridDim = dim3((unsigned)(ncl_used * kClSize));
   TAUV_CUDA(cudaLaunchKernelEx(&cfg, ck, a, (int)n_units, parts));
   return 0;
@@ -1443,7 +1607,10 @@ static int run_stage2(int B, int C, int H, int W, int k, int mode, int64_t* inde
 
 static int run_topk(const float* hm, int B, int C, int H, int W, int k, int mode, int64_t* index, int64_t* label,
                     float* score, const BoxArgs& box, void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (int e = run_stage1(hm, B, C, H, W, k, mode, ws, ws_bytes, st)) return e;
+  const FuseOut fo{index, label, score, &box};
+  bool fused = false;
+  if (int e = run_stage1(hm, B, C, H, W, k, mode, ws, ws_bytes, st, &fo, &fused)) return e;
+  if (fused) return 0;
   return run_stage2(B, C, H, W, k, mode, index, label, score, box, ws, ws_bytes, st);
 }
 

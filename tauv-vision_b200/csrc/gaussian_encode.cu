@@ -161,11 +161,15 @@ __global__ void __launch_bounds__(kEncThreads) gaussian_encode_warp_kernel(
   bool mine = false;
   int cy = 0, cx = 0;
   if (lane < n_objects) {
+    // (all three loads are issued at once: one latency before the stores can start, not three)
     const long long i = b * n_objects + lane;
-    if (__ldg(valid + i) && __ldg(label + i) == c) {
+    const uint8_t v = __ldg(valid + i);
+    const long long l = __ldg(label + i);
+    const float2 yx = __ldg(reinterpret_cast<const float2*>(center) + i);
+    if (v && l == c) {
       mine = true;
-      cy = grid_floor(__ldg(center + i * 2 + 0), in_h, ratio);
-      cx = grid_floor(__ldg(center + i * 2 + 1), in_w, ratio);
+      cy = grid_floor(yx.x, in_h, ratio);
+      cx = grid_floor(yx.y, in_w, ratio);
     }
   }
   const unsigned mask = __ballot_sync(0xffffffffu, mine);
@@ -416,7 +420,7 @@ extern "C" int tauv_gaussian_encode(const uint8_t* valid, const int64_t* label, 
   const size_t smem = (size_t)(n_objects > 0 ? n_objects : 1) * 20;
   const bool vec = (W % 4 == 0) && ((uintptr_t)out % 16 == 0);
   const float ts = two_sigma_sq(sigma);
-  if (vec && n_objects <= 32) {
+  if (vec && n_objects <= 32 && (uintptr_t)center % 8 == 0) {
     const long long plane_strips = (long long)H * (W / 4);
     const long long cpp = (plane_strips + kEncWarpStrips - 1) / kEncWarpStrips;
     const long long n_chunks = (long long)B * C * cpp;
