@@ -27,6 +27,7 @@ struct MaskArgs {
   int top_k;                 // output rows per frame
   float* out;                // [B,top_k,HW]
   float* logits;             // optional, same shape
+  long long* trace;          // debug (tools/mask_trace.py): per-unit role timestamps of CTA 0, or NULL
 };
 
 constexpr int kSimtThreads = 256;
@@ -84,7 +85,11 @@ __global__ void __launch_bounds__(kSimtThreads) mask_simt_kernel(MaskArgs a) {
 
 namespace tauv {
 
-static int run_mask(const MaskArgs& a, int B, int max_rows, int force_simt, cudaStream_t st) {
+static long long* g_mask_trace = nullptr;  // experiment hook (tools/mask_trace.py); not part of the public ABI
+
+static int run_mask(const MaskArgs& a_in, int B, int max_rows, int force_simt, cudaStream_t st) {
+  MaskArgs a = a_in;
+  a.trace = g_mask_trace;
   const int HW = a.H * a.W;
   if (!force_simt && umma_shape_ok(a)) return launch_mask_umma(a, B, max_rows, st);
   const size_t smem = ((size_t)a.P * kSimtThreads + (size_t)kSimtDetChunk * a.P + kSimtDetChunk * 4) * sizeof(float);
@@ -131,3 +136,6 @@ extern "C" int tauv_yolact_assemble_mask_batched(const float* proto, const float
   a.n_host = 0; a.N = N; a.P = P; a.H = H; a.W = W; a.top_k = top_k; a.out = out; a.logits = nullptr;
   return run_mask(a, B, top_k, want_simt(), (cudaStream_t)stream);
 }
+
+// Debug hook for tools/mask_trace.py (process-global, not thread-safe, not in the public header).
+extern "C" void tauv_debug_mask_trace(long long* buf) { tauv::g_mask_trace = buf; }

@@ -23,6 +23,8 @@
 // pipe idles most of the time by construction.
 #pragma once
 
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
+
 namespace tauv {
 
 constexpr int kUmmaP = 32;            // contraction depth this kernel is built for
@@ -37,6 +39,11 @@ struct UmmaSmem {
   __align__(1024) unsigned char b[2][kUmmaNMax * 64];     // [hi/lo] coefficients of the frame, 2 x 16 KB
   float bounds[kUmmaNMax][4];                             // crop bounds (left, right, top, bottom) per detection
   __align__(16) float zeros[kUmmaM];                      // source of the bulk zero-fill stores
+  // Output staging: [epilogue group][buffer][detection of the chunk][pixel of the tile].  A warp can only read its own
+  // TMEM lane quadrant (32 pixels), and 128-byte segments scattered over ~160 masks that lie 305 KB apart run HBM at
+  // 1.6 TB/s (tools/store_bench.cu); 512-byte rows reach 3.9 TB/s.  So the four quadrant warps of a group assemble
+  // whole 512-byte rows here and one of them hands each row to the bulk-copy engine.
+  __align__(128) float stage[2][4][32][kUmmaM];           // 128 KB: four buffers per group (one barrier per chunk, two chunks of stores in flight)
   uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], frame_done;
   uint32_t tmem_base;
 };
@@ -114,6 +121,14 @@ __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, u
   lo = pack_bf16x2(x0 - h0, x1 - h1);
 }
 
+__device__ __forceinline__ void mask_stamp(const MaskArgs& a, long long u_rel, int col) {
+  if (a.trace && blockIdx.x == 0 && u_rel < 512) {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    a.trace[u_rel * 8 + col] = t;
+  }
+}
+
 // detections of frame b handled by this launch (rows [m_base, m_base + 256))
 __device__ __forceinline__ int frame_rows(const MaskArgs& a, int b, int m_base) {
   const int n = (a.n_keep ? a.n_keep[b] : a.n_host) - m_base;
@@ -121,9 +136,14 @@ __device__ __forceinline__ int frame_rows(const MaskArgs& a, int b, int m_base) 
 }
 
 __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid_constant__ MaskArgs a, int B,
-                                                                    int m_base) {
+                                                                    int m_base,
+                                                                    const __grid_constant__ CUtensorMap out_map,
+                                                                    int use_tma) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  UmmaSmem* sm = reinterpret_cast<UmmaSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // (round up INSIDE the shared window: pointer arithmetic on the __shared__ array keeps the address space, an integer
+  // round trip does not — the compiler then emits generic LD/ST for every shared access, which cost the epilogue ~150
+  // cycles per detection)
+  UmmaSmem* sm = reinterpret_cast<UmmaSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HW = a.H * a.W;
   const int n_tiles = (HW + kUmmaM - 1) / kUmmaM;
@@ -159,6 +179,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
     // bulk stores need 16-byte aligned rows: H*W % 4 == 0 and an aligned output
     const bool bulk_zero = (HW % 4 == 0) && ((uintptr_t)a.out % 16 == 0);
     uint32_t uses[2] = {0, 0};
+    uint32_t nbuf = 0;  // staged chunks so far (selects the staging buffer)
     int as = 0, rows_frame = -1, n_rows = 0;
     for (long long u = u0; u < u1; ++u) {
       const int b = (int)(u / n_tiles), nt = (int)(u - (long long)b * n_tiles);
@@ -178,6 +199,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
       const float ty0 = (float)((nt * kUmmaM) / a.W), ty1 = (float)((nt * kUmmaM + tile_px - 1) / a.W);
       mbar_wait(&sm->acc_full[as], uses[as] & 1u);
       tc_fence_after();
+      if (tid == 0) mask_stamp(a, u - u0, 5);
 #pragma unroll 1
       for (int c = half; c * 32 < n_rows; c += 2) {
         // lane j looks at detection c*32+j: does its box reach the tile at all?  If not, one bulk store of zeros
@@ -188,16 +210,82 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
           if (det < n_rows) {
             const float4 bd = *reinterpret_cast<const float4*>(sm->bounds[det]);
             live = lg_pix != nullptr || !bulk_zero || !(ty1 < bd.z || ty0 > bd.w);
-            if (!live && quad == 0) bulk_s2g(out_tile + (size_t)det * HW, sm->zeros, (uint32_t)tile_px * 4u);
+            // (TMA mode writes whole 32-row boxes: rows the box misses come out as zeros from the crop arithmetic)
+            if (!live && quad == 0 && !use_tma) bulk_s2g(out_tile + (size_t)det * HW, sm->zeros, (uint32_t)tile_px * 4u);
           }
         }
         const unsigned live_mask = __ballot_sync(0xffffffffu, live);
-        if (live_mask == 0u) continue;
+        // (uniform over the group's four warps: `live` does not depend on the quadrant)
+        if (live_mask == 0u && !use_tma) continue;
         float v[32];
         tc_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kUmmaNMax + c * 32), v);
         float* op = out_pix + (size_t)(c * 32) * HW;
         float* lp = lg_pix ? lg_pix + (size_t)(c * 32) * HW : nullptr;
         const float4* bp = reinterpret_cast<const float4*>(sm->bounds[c * 32]);
+        if (bulk_zero) {
+          // ---- staged path: rows of 128 pixels assembled in shared memory, one bulk store per (detection, tile)
+          float (*stg)[kUmmaM] = sm->stage[half][nbuf & 3u];
+          // Branch-free AND predicate-free on purpose.  With a vote and a branch per detection — or even just the
+          // chained FSETPs of the crop test and the range fix-ups of __expf / __fdividef, which all funnel through one
+          // predicate register — the 32 iterations ran strictly one after the other (~100-160 cycles each: 5-8 us of
+          // epilogue per tile against 2 us for everything else).  Here the crop test is sign-bit arithmetic
+          // (inclusive bounds; the "no crop" bounds are +-inf, which subtract to +inf) and the sigmoid is
+          // rcp.approx(1 + ex2.approx(-x*log2 e)) (2 ulp each; saturates correctly to 0 / 1), so eight detections at a
+          // time are independent straight-line code.  Rows that are not live are computed too and never stored.
+#pragma unroll
+          for (int j0 = 0; j0 < 32; j0 += 8) {
+            if (((live_mask >> j0) & 0xffu) == 0u) {  // warp-uniform: none of these eight boxes reaches the tile
+#pragma unroll
+              for (int i = 0; i < 8; ++i) stg[j0 + i][quad * 32 + lane] = 0.0f;
+              continue;
+            }
+            int keepm[8];
+            float sg[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 bd = bp[j0 + i];  // same address for the whole warp: a broadcast
+              const int neg = __float_as_int(px - bd.x) | __float_as_int(bd.y - px) | __float_as_int(py - bd.z) |
+                              __float_as_int(bd.w - py);
+              keepm[i] = ~(neg >> 31);  // all ones when the pixel is inside the box
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              // sigmoid(x) = 0.5 + 0.5*tanh(x/2): one MUFU op (tanh.approx, |error| <= ~5e-4 on the mask value against
+              // the 2.5e-3 the bf16 contraction is allowed) instead of ex2 + rcp
+              float t;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(v[j0 + i] * 0.5f));
+              sg[i] = fmaf(t, 0.5f, 0.5f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) stg[j0 + i][quad * 32 + lane] = __int_as_float(__float_as_int(sg[i]) & keepm[i]);
+          }
+          if (lp && pix < HW) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if ((live_mask >> j) & 1u) lp[(size_t)j * HW] = v[j];
+          }
+          fence_proxy_async();  // generic-proxy writes -> visible to the bulk-copy engine
+          // (before the barrier: the stores issued from the buffer the NEXT chunk will fill — three chunks ago — have read it)
+          if (quad == 0) bulk_wait_read<2>();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+          if (quad == 0) {
+            if (use_tma) {
+              // one tensor store for the whole chunk: box {128 pixels, 32 detections, 1 frame} of out[B][top_k][HW];
+              // the parts of the box beyond HW or top_k are clipped by the copy engine
+              if (lane == 0) {
+                asm volatile(
+                    "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&out_map),
+                    "r"(nt * kUmmaM), "r"(m_base + c * 32), "r"(b), "r"(smem_u32(&stg[0][0]))
+                    : "memory");
+              }
+            } else if ((live_mask >> lane) & 1u) {
+              bulk_s2g(out_tile + (size_t)(c * 32 + lane) * HW, stg[lane], (uint32_t)tile_px * 4u);
+            }
+            bulk_commit();
+          }
+          ++nbuf;
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j, op += HW) {
           if ((live_mask >> j) & 1u) {  // warp-uniform
@@ -212,6 +300,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
           }
         }
       }
+      if (tid == 0) mask_stamp(a, u - u0, 6);
       tc_fence_before();
       mbar_arrive(&sm->acc_empty[as]);
       ++uses[as];
@@ -254,9 +343,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
           *reinterpret_cast<uint4*>(sm->b[0] + sw64_offset(row, c)) = qh;
           *reinterpret_cast<uint4*>(sm->b[1] + sw64_offset(row, c)) = ql;
         }
-        for (int row = pt; row < n_rows; row += kUmmaProdWarps * 32) {
+        for (int row = pt; row < ((n_rows + 31) & ~31); row += kUmmaProdWarps * 32) {
           float4 bd = make_float4(TAUV_NEG_INF, -TAUV_NEG_INF, TAUV_NEG_INF, -TAUV_NEG_INF);  // no crop
-          if (a.box) {
+          if (row >= n_rows) {
+            bd = make_float4(-TAUV_NEG_INF, TAUV_NEG_INF, -TAUV_NEG_INF, TAUV_NEG_INF);  // padding row: empty box -> zeros
+          } else if (a.box) {
             const CropBounds cbd = crop_bounds(a.box[(size_t)b * a.top_k + m_base + row], a.H, a.W);
             bd = make_float4(cbd.left, cbd.right, cbd.top, cbd.bottom);
           }
@@ -266,6 +357,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
         ++frames;
       }
       if (fills[st] > 0) mbar_wait(&sm->a_empty[st], (fills[st] - 1) & 1u);
+      if (pt == 0) mask_stamp(a, u - u0, 0);
       // A tile: pixel row pt, 32 prototype values -> 4 chunks of 8 bf16 (hi and lo)
       const int pix = nt * kUmmaM + pt;
       const float* src = a.proto + (size_t)b * kUmmaP * HW + pix;
@@ -283,6 +375,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
         *reinterpret_cast<uint4*>(sm->a[st][1] + sw64_offset(pt, c)) = ql;
       }
       fence_proxy_async();  // generic-proxy writes (A, and B / bounds at a frame change) -> visible to the async proxy
+      if (pt == 0) mask_stamp(a, u - u0, 1);
       mbar_arrive(&sm->a_full[st]);
       ++fills[st];
       st ^= 1;
@@ -300,8 +393,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
       if (n_rows == 0) continue;
       const uint32_t idesc = umma_idesc_bf16_m128((n_rows + 15) & ~15);
       mbar_wait(&sm->a_full[st], fills[st] & 1u);
+      mask_stamp(a, u - u0, 2);
       if (uses[as] > 0) mbar_wait(&sm->acc_empty[as], (uses[as] - 1) & 1u);
       tc_fence_after();
+      mask_stamp(a, u - u0, 3);
       const uint32_t d = tmem + (uint32_t)(as * kUmmaNMax);
 #pragma unroll
       for (int k = 0; k < kUmmaP / 16; ++k) {  // K = 16 bf16 = 32 bytes per instruction, inside the 64-byte rows
@@ -313,6 +408,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
       }
       tc_commit(&sm->acc_full[as]);  // arrives when the MMAs above are complete ...
       tc_commit(&sm->a_empty[st]);   // ... and so does this one: the A stage may be refilled
+      mask_stamp(a, u - u0, 4);
       ++uses[as];
       as ^= 1;
       ++fills[st];
@@ -332,6 +428,35 @@ static bool umma_shape_ok(const MaskArgs& a) {
   return a.P == kUmmaP && (uintptr_t)a.coeff % 16 == 0;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// out[B][rows_per_frame][HW] fp32 as a 3-D tensor map with box {128, 32, 1}; false when the layout does not qualify
+// (HW*4 not a multiple of 16, unaligned base) or the driver entry point is unavailable: the kernel then stores rows
+// one by one.
+static bool make_out_map(const MaskArgs& a, int B, CUtensorMap* map) {
+  const long long HW = (long long)a.H * a.W;
+  if (HW % 4 != 0 || (uintptr_t)a.out % 16 != 0 || a.logits != nullptr) return false;
+  static EncodeTiledFn encode = nullptr;  // (idempotent lookup; benign race)
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+      (void)cudaGetLastError();
+      return false;
+    }
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)a.top_k, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)a.top_k * (cuuint64_t)HW * 4};  // bytes, dims 1 and 2
+  const cuuint32_t box[3] = {(cuuint32_t)kUmmaM, 32u, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int launch_mask_umma(const MaskArgs& a, int B, int max_rows, cudaStream_t st) {
   const size_t smem = sizeof(UmmaSmem) + 1024;
   TAUV_CUDA(cudaFuncSetAttribute(mask_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -339,8 +464,11 @@ static int launch_mask_umma(const MaskArgs& a, int B, int max_rows, cudaStream_t
   const long long units = (long long)B * ((HW + kUmmaM - 1) / kUmmaM);
   long long grid = num_sms();
   if (grid > units) grid = units;
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  const int use_tma = !getenv("TAUV_MASK_NO_TMA") && make_out_map(a, B, &map) ? 1 : 0;
   for (int m_base = 0; m_base < max_rows; m_base += kUmmaNMax) {
-    mask_umma_kernel<<<(unsigned)grid, kUmmaThreads, smem, st>>>(a, B, m_base);
+    mask_umma_kernel<<<(unsigned)grid, kUmmaThreads, smem, st>>>(a, B, m_base, map, use_tma);
     TAUV_LAUNCH_CHECK("mask_umma_kernel");
   }
   return 0;

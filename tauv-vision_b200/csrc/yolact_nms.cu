@@ -102,6 +102,77 @@ __global__ void __launch_bounds__(256) scores_kernel(const float* __restrict__ c
   }
 }
 
+// K1' scores_tile_kernel: the same result from a different mapping (C1 <= 256).  A warp pulls 32 consecutive class rows
+// (one contiguous 32*C1*4-byte block) into its own shared-memory tile with 4-byte cp.async (128 contiguous bytes per
+// warp instruction, no alignment requirement; rows of 81 floats are never 16-byte aligned), then LANE = ROW: every lane
+// walks its own row at an odd word stride (conflict-free), so the max / sum-of-exp reductions are plain sequential
+// loops with no shuffles — a third of the instructions of the lanes-across-classes version, which was issue-bound.
+constexpr int kScoreTileWarps = 4;
+
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool ARGMAX>
+__global__ void __launch_bounds__(kScoreTileWarps * 32) scores_tile_kernel(const float* __restrict__ cls, long long rows,
+                                                                            int C1, int stride,
+                                                                            float* __restrict__ score,
+                                                                            int32_t* __restrict__ argmax_all) {
+  extern __shared__ float s_tiles[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* tile = s_tiles + (size_t)wib * 32 * stride;
+  const long long warp = (long long)blockIdx.x * kScoreTileWarps + wib;
+  const long long nwarps = (long long)gridDim.x * kScoreTileWarps;
+  for (long long blk = warp; blk * 32 < rows; blk += nwarps) {
+    const long long row0 = blk * 32;
+    const int nrows = (int)min(32LL, rows - row0);
+    const int n_el = nrows * C1;
+    const float* src = cls + row0 * C1;
+    // element e of the block -> tile[(e / C1) * stride + e % C1], kept incrementally (e advances by 32)
+    int r = lane / C1, j = lane - r * C1;
+    const int dr = 32 / C1, dj = 32 - dr * C1;
+    for (int e = lane; e < n_el; e += 32) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(tile + r * stride + j)), "l"(src + e) : "memory");
+      r += dr;
+      j += dj;
+      if (j >= C1) { j -= C1; ++r; }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    if (lane < nrows) {
+      const float* x = tile + lane * stride;
+      float m = x[0], mfg = TAUV_NEG_INF;
+      int best_i = 0;
+      for (int c = 1; c < C1; ++c) {
+        const float v = x[c];
+        if (ARGMAX && v > m) best_i = c;  // first maximum wins, like torch.argmax
+        m = fmaxf(m, v);
+        mfg = fmaxf(mfg, v);
+      }
+      // sum of exp(x - m) in four independent chains.  ex2.approx on x*log2(e): <= 2 ulp, i.e. ~2e-7 relative on the
+      // score against the 1e-5 the parity tests allow (the reference's own softmax reduces in a different order too).
+      const float L2E = 1.4426950408889634f;
+      const float ml = m * L2E;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int c = 0;
+      for (; c + 4 <= C1; c += 4) {
+        s0 += ex2_fast(fmaf(x[c], L2E, -ml));
+        s1 += ex2_fast(fmaf(x[c + 1], L2E, -ml));
+        s2 += ex2_fast(fmaf(x[c + 2], L2E, -ml));
+        s3 += ex2_fast(fmaf(x[c + 3], L2E, -ml));
+      }
+      for (; c < C1; ++c) s0 += ex2_fast(fmaf(x[c], L2E, -ml));
+      const float sum = (s0 + s1) + (s2 + s3);
+      // softmax is monotone per row: max_j>=1 softmax_j = exp(max_fg - max) / sum
+      score[row0 + lane] = __fdiv_rn(ex2_fast(fmaf(mfg, L2E, -ml)), sum);
+      if (ARGMAX) argmax_all[row0 + lane] = best_i;
+    }
+    __syncwarp();  // the tile is overwritten by the next block
+  }
+}
+
 // ---- K2 ----------------------------------------------------------------------------------------
 struct NmsArgs {
   const float* score;      // [B,N]
@@ -251,6 +322,23 @@ __global__ void keep_class_kernel(const float* __restrict__ cls, const int64_t* 
 }
 
 static int launch_scores(const float* cls, long long rows, int C1, float* score, int32_t* argmax_all, cudaStream_t st) {
+  if (C1 <= 256 && !getenv("TAUV_SCORES_OLD")) {
+    const int stride = C1 | 1;
+    const size_t smem = (size_t)kScoreTileWarps * 32 * stride * 4;
+    long long blocks = (rows + 32 * kScoreTileWarps - 1) / (32 * kScoreTileWarps);
+    const long long cap = (long long)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (argmax_all) {
+      TAUV_CUDA(cudaFuncSetAttribute(scores_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      scores_tile_kernel<true><<<(unsigned)blocks, kScoreTileWarps * 32, smem, st>>>(cls, rows, C1, stride, score, argmax_all);
+    } else {
+      TAUV_CUDA(cudaFuncSetAttribute(scores_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      scores_tile_kernel<false><<<(unsigned)blocks, kScoreTileWarps * 32, smem, st>>>(cls, rows, C1, stride, score, argmax_all);
+    }
+    TAUV_LAUNCH_CHECK("scores_tile_kernel");
+    return 0;
+  }
   const long long blocks_needed = (rows + 32 * 8 - 1) / (32 * 8);  // 8 warps per CTA, 32 rows per warp
   long long blocks = blocks_needed;
   const long long cap = (long long)num_sms() * 8 * 4;

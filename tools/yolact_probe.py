@@ -53,7 +53,8 @@ del os.environ["TAUV_MASK_SIMT"]
 res["mask_simt_us"] = t
 t, _ = timeit(lambda: boxes.box_decode(enc, anchor, cfg)); res["box_decode_us"] = t; res["box_decode_gbs"] = 2 * B * N * 16 / t / 1e3
 tb, tvd = synth.truth_boxes(B, 16, seed=1)
-t, _ = timeit(lambda: loss.match_anchors(anchor, tb.to(dev), tvd.to(dev), cfg)); res["match_us"] = t
+tb, tvd = tb.to(dev), tvd.to(dev)
+t, _ = timeit(lambda: loss.match_anchors(anchor, tb, tvd, cfg)); res["match_us"] = t
 res["match_gbs"] = B * N * 30 / t / 1e3
 res["frames_per_s_full_postprocess"] = B / ((res["detect_us"] + res["mask_us"]) * 1e-6)
 print(json.dumps(res, indent=1))
