@@ -596,6 +596,46 @@ __device__ int topk_select_pool(const unsigned long long* pool, int total, int k
   return (int)ctl[5];
 }
 
+// The zero-score tail of a ranked list (SIGMOID_PEAK, fewer than k positive peaks): cells of value 0 in ascending flat
+// index, skipping the cells flagged as selected peaks (flags[i] != 0 for flat index i < k).  Slots [npos, k).
+template <int NT>
+__device__ void topk_emit_fillers(const uint32_t* flags, int npos, int b, int k, int H, int W,
+                                  int64_t* __restrict__ index, int64_t* __restrict__ label, float* __restrict__ score,
+                                  const BoxArgs& g) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int s_fsum[NT / 32];
+  const long long hw_elems = (long long)H * W;
+  const int need = k - npos;
+  int base = 0;
+  for (int start = 0; start < k && base < need; start += NT) {
+    const int i = start + tid;
+    const bool freec = (i < k) && (flags[i] == 0u);
+    const unsigned bal = __ballot_sync(0xffffffffu, freec);
+    if (lane == 0) s_fsum[warp] = __popc(bal);
+    __syncthreads();
+    int pos = base + __popc(bal & ((1u << lane) - 1u));
+    int tot = 0;
+    for (int w = 0; w < NT / 32; ++w) {
+      if (w < warp) pos += s_fsum[w];
+      tot += s_fsum[w];
+    }
+    if (freec && pos < need) {
+      const int r = npos + pos;
+      const long long lab = i / hw_elems;
+      const long long rem = i - lab * hw_elems;
+      const int iy = (int)(rem / W), ix = (int)(rem - (long long)iy * W);
+      const long long slot = (long long)b * k + r;
+      index[slot * 2 + 0] = iy;
+      index[slot * 2 + 1] = ix;
+      label[slot] = lab;
+      score[slot] = 0.0f;
+      if (g.enabled) box_one(g, b, slot, iy, ix);
+    }
+    base += tot;
+    __syncthreads();
+  }
+}
+
 // Sort sel[0, p2) descending and write the frame's ranked outputs: index/label/score for the npos selected peaks,
 // then (SIGMOID_PEAK) the zero-valued fillers a dense stable top-k would return, the box arithmetic, and the count of
 // leading entries at or above the score threshold.  flags: k words of shared memory (may alias the radix histogram).
@@ -637,37 +677,10 @@ __device__ void topk_emit_ranked(unsigned long long* sel, int p2, int npos, uint
       if (flat < (uint32_t)k) flags[flat] = 1u;
     }
     __syncthreads();
-    const int need = k - npos;
-    int base = 0;
-    for (int start = 0; start < k && base < need; start += NT) {
-      const int i = start + tid;
-      const bool freec = (i < k) && (flags[i] == 0u);
-      const unsigned bal = __ballot_sync(0xffffffffu, freec);
-      if (lane == 0) s_wsum[warp] = __popc(bal);
+    topk_emit_fillers<NT>(flags, npos, b, k, H, W, index, label, score, g);
+    if (g.enabled && 0.0f < g.thr) {
       __syncthreads();
-      int pos = base + __popc(bal & ((1u << lane) - 1u));
-      int tot = 0;
-      for (int w = 0; w < NT / 32; ++w) {
-        if (w < warp) pos += s_wsum[w];
-        tot += s_wsum[w];
-      }
-      if (freec && pos < need) {
-        const int r = npos + pos;
-        const long long lab = i / hw_elems;
-        const long long rem = i - lab * hw_elems;
-        const int iy = (int)(rem / W), ix = (int)(rem - (long long)iy * W);
-        const long long slot = (long long)b * k + r;
-        index[slot * 2 + 0] = iy;
-        index[slot * 2 + 1] = ix;
-        label[slot] = lab;
-        score[slot] = 0.0f;
-        if (g.enabled) {
-          box_one(g, b, slot, iy, ix);
-          if (0.0f < g.thr) atomicMin(&s_first_below, r);
-        }
-      }
-      base += tot;
-      __syncthreads();
+      if (tid == 0) atomicMin(&s_first_below, npos);
     }
   }
   if (g.enabled) {
@@ -706,6 +719,7 @@ constexpr int kStreamThreads = kTileThreads - 32;     // warps 1..7 stream, warp
 constexpr int kRoundF4 = kRoundW * kStreamThreads;    // 128-bit strips per streaming round per CTA
 constexpr int kBootF4 = kRoundW * kTileThreads;       // strips of the bootstrap round (all eight warps)
 constexpr int kBootElems = 4 * kBootF4;               // cells of the bootstrap round
+constexpr int kFuseMaxK = 256;                        // fused tail: flags / ranks for k output slots
 constexpr int kHotCap = 1024;                         // ring of queued peak tests (entries of 8 bytes)
 constexpr int kClMaxW = 1016;                         // halo rows are held in two 128-bit registers per thread
 
@@ -794,8 +808,8 @@ __device__ __forceinline__ int cl_bin(unsigned long long c) {  // window bin of 
 // Warp 0: scan the unit's histogram (the sum of the eight CTAs' local copies, read through distributed shared memory)
 // from the highest occupied bin downwards, find the highest bin b with count(bins >= b) >= k, and return the
 // rejection key of its lower edge (0: fewer than k candidates so far).  At most 512 bins are visited.
-template <int MODE>
-__device__ __forceinline__ uint32_t cl_scan_threshold(cg::cluster_group& cluster, ClusterCtx* cc, int k) {
+// (returns the bin, or -1 when fewer than k candidates have been binned; every lane gets the same value)
+__device__ __forceinline__ int cl_scan_bin(cg::cluster_group& cluster, ClusterCtx* cc, int k) {
   const int lane = threadIdx.x & 31;
   const int maxbin = (int)*reinterpret_cast<volatile uint32_t*>(&cc->maxbin);
   uint32_t acc = 0;
@@ -818,6 +832,13 @@ __device__ __forceinline__ uint32_t cl_scan_threshold(cg::cluster_group& cluster
     acc += __shfl_sync(0xffffffffu, pre, 31);
     if (maxbin - (it + 1) * 32 < 0) break;
   }
+  return found;
+}
+
+template <int MODE>
+__device__ __forceinline__ uint32_t cl_scan_threshold(cg::cluster_group& cluster, ClusterCtx* cc, int k) {
+  const int lane = threadIdx.x & 31;
+  const int found = cl_scan_bin(cluster, cc, k);
   uint32_t key = 0;
   if (lane == 0 && found >= 0) {
     const float edge = cl_window_edge(found);
@@ -1253,35 +1274,112 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
     }
 
     if (a.fuse) {
-      // ---- fused tail (parts == 1): every CTA reduces its list to its exact top-k in place, rank 0 gathers the
-      // eight lists through distributed shared memory, and — once the others are released — selects the frame's
-      // top-k and writes the ranked outputs.
+      // ---- fused tail (parts == 1).  The published threshold lags behind the final k-th best, so the eight lists
+      // together hold several times k candidates.  One last scan of the (now complete) histogram gives the bin that
+      // holds the k-th best; everything below its lower edge is dropped, which leaves k plus a handful.  Then the
+      // ranking is shared out: every CTA copies the eight pruned lists into its own shared memory and ranks ITS OWN
+      // entries against them with 16 threads per entry — the rank of a key among distinct keys is its output slot, so
+      // there is no selection pass and no sort, and only O(1) barriers.  Rank 0 adds the zero-score fillers and the
+      // threshold count.
+      __shared__ unsigned long long s_keyT;
+      __shared__ int s_total, s_nge;
+      __shared__ uint32_t s_flags[kFuseMaxK];  // rank 0: flat indices < k taken by a selected peak (for the fillers)
+      __shared__ int s_rank[kFuseMaxK];
       const int n = ctx->count;
       convert_entries<MODE>(ctx, list, n);
-      const unsigned long long T = block_kth_largest<kTileThreads>([&](int i) { return list[i]; }, n, a.k, hist, ctx->sel);
-      compact_list(ctx, list, n, [&](unsigned long long c) { return c >= T && c != 0ull; });
+      for (int i = tid; i < a.k; i += kTileThreads) s_flags[i] = 0u;
+      if (tid == 0) s_nge = 0;
+      cluster.sync();  // (3a) every CTA has finished streaming and binning; rank 0's flags are clear
+      if (tid < 32) {
+        const int bin = cl_scan_bin(cluster, cc, a.k);
+        if (tid == 0) {
+          unsigned long long kt = 1ull;  // fewer than k candidates binned: keep everything that is non-zero
+          if (bin >= 0) {
+            const float edge = cl_window_edge(bin);
+            // at least k candidates have values >= edge; in SIGMOID_PEAK mode the list holds their sigmoids, whose
+            // rounding (<= 2 ulp) the relative guard band covers
+            const float lowest = MODE == TAUV_TOPK_SIGMOID_PEAK ? sigmoid_ref(edge) * (1.0f - 4e-5f) : edge;
+            kt = (unsigned long long)float_to_key(lowest) << 32;
+            if (kt == 0ull) kt = 1ull;
+          }
+          s_keyT = kt;
+        }
+      }
+      __syncthreads();
+      {
+        const unsigned long long kt = s_keyT;
+        compact_list(ctx, list, n, [&](unsigned long long c) { return c >= kt && c != 0ull; });
+      }
+      if (ctx->base > a.k) {  // (ties / plateaus: more than k survive in this CTA alone; the pool holds 8k keys)
+        const int n2 = ctx->base;
+        const unsigned long long T = block_kth_largest<kTileThreads>([&](int i) { return list[i]; }, n2, a.k, hist, ctx->sel);
+        compact_list(ctx, list, n2, [&](unsigned long long c) { return c >= T; });
+      }
       if (tid == 0) ctx->emit = (uint32_t)ctx->base;
-      cluster.sync();  // (3a) all eight lists are final
-      __shared__ int s_total;
-      if (rank == 0) {
-        int off = (int)ctx->emit;
-        for (int r = 1; r < kClSize; ++r) {
+      cluster.sync();  // (3b) all eight pruned lists are final
+      unsigned long long* pool = reinterpret_cast<unsigned long long*>(hist);  // hist + tile: contiguous, >= 8k keys
+      {
+        int off = 0;
+        for (int r = 0; r < kClSize; ++r) {
           const int cnt = (int)*cluster.map_shared_rank(&ctx->emit, r);
           const unsigned long long* rl = cluster.map_shared_rank(list, r);
-          for (int i = tid; i < cnt; i += kTileThreads) list[off + i] = rl[i];
+          for (int i = tid; i < cnt; i += kTileThreads) pool[off + i] = rl[i];
           off += cnt;
         }
         if (tid == 0) s_total = off;
       }
-      cluster.sync();  // (3) nobody touches this unit's distributed state any more
+      const int n_own = (int)ctx->emit;
+      for (int i = tid; i < n_own; i += kTileThreads) s_rank[i] = 0;
+      __syncthreads();
+      {
+        // 16 threads per own entry, each over a sixteenth of the pool; partial ranks meet in shared memory
+        const int total = s_total;
+        const int part = tid & 15;
+        for (int e = tid >> 4; e < n_own; e += kTileThreads / 16) {
+          const unsigned long long c = list[e];
+          int r = 0;
+          for (int j = part; j < total; j += 16) r += (pool[j] > c);
+          if (r) atomicAdd(&s_rank[e], r);
+        }
+      }
+      __syncthreads();
+      {
+        const BoxArgs& g = a.box;
+        const long long hw_elems = (long long)a.H * a.W;
+        int my_ge = 0;
+        for (int i = tid; i < n_own; i += kTileThreads) {
+          const int r = s_rank[i];
+          if (r < a.k) {
+            const unsigned long long c = list[i];
+            const uint32_t flat = composite_idx(c);
+            const float sc = key_to_float(composite_key(c));
+            const long long lab = flat / hw_elems;
+            const long long rem = flat - lab * hw_elems;
+            const int iy = (int)(rem / a.W), ix = (int)(rem - (long long)iy * a.W);
+            const long long slot = (long long)frame * a.k + r;
+            a.out_index[slot * 2 + 0] = iy;
+            a.out_index[slot * 2 + 1] = ix;
+            a.out_label[slot] = lab;
+            a.out_score[slot] = sc;
+            if (g.enabled) {
+              box_one(g, frame, slot, iy, ix);
+              if (!(sc < g.thr)) ++my_ge;
+            }
+            if (flat < (uint32_t)a.k) *cluster.map_shared_rank(&s_flags[flat], 0) = 1u;
+          }
+        }
+        if (my_ge) atomicAdd(cluster.map_shared_rank(&s_nge, 0), my_ge);
+      }
+      cluster.sync();  // (3) nobody touches this unit's distributed state any more; rank 0 sees flags and count
       if (rank == 0) {
-        __shared__ uint32_t s_ctl[8];
-        int p2 = 1;
-        while (p2 < a.k) p2 <<= 1;
-        unsigned long long* sel = reinterpret_cast<unsigned long long*>(tile);
-        const int npos = topk_select_pool<kTileThreads>(list, s_total, a.k, p2, sel, hist, s_ctl);
-        topk_emit_ranked<MODE, kTileThreads>(sel, p2, npos, hist, frame, a.k, a.H, a.W, a.out_index, a.out_label,
-                                             a.out_score, a.box);
+        const int npos = min(a.k, s_total);
+        if (MODE == TAUV_TOPK_SIGMOID_PEAK && npos < a.k)
+          topk_emit_fillers<kTileThreads>(s_flags, npos, frame, a.k, a.H, a.W, a.out_index, a.out_label, a.out_score, a.box);
+        if (a.box.enabled && tid == 0) {  // entries before the first score < threshold (ranked scores descend; fillers score 0)
+          int cnt = s_nge;
+          if (MODE == TAUV_TOPK_SIGMOID_PEAK && npos < a.k && !(0.0f < a.box.thr)) cnt += a.k - npos;
+          a.box.count[frame] = cnt;
+        }
         __syncthreads();
       }
       continue;
@@ -1567,8 +1665,8 @@ static int run_stage1(const float* hm, int B, int C, int H, int W, int k, int mo
   const long long ncl_used = n_units < ncl ? n_units : ncl;
   int p2 = 1;
   while (p2 < k) p2 <<= 1;
-  if (fo && fused && parts == 1 && (long long)kClSize * k <= p.cap && (size_t)p2 * 8 <= (size_t)(kBootElems + 2 * W + 8) * 4 &&
-      k <= kRadixBins && !getenv("TAUV_NO_FUSE")) {
+  if (fo && fused && parts == 1 && k <= kFuseMaxK &&
+      (size_t)kClSize * k * 8 <= (size_t)kRadixBins * 4 + (size_t)(kBootElems + 2 * W + 8) * 4 && !getenv("TAUV_NO_FUSE")) {
     a.fuse = 1;
     a.out_index = fo->index;
     a.out_label = fo->label;
