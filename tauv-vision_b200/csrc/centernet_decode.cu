@@ -1089,11 +1089,13 @@ __device__ __noinline__ void cl_bootstrap_round(const TileArgs& a, TileCtx* ctx,
     }
     if (lane == 31) ctx->wsum[warp] = incl;
     __syncthreads();
-    int base = incl - mine, total = 0;
+    const int old_count = ctx->count;  // (entries of earlier bootstrap chunks)
+    int base = old_count + incl - mine, total = old_count;
     for (int w = 0; w < kTileThreads / 32; ++w) {
       if (w < warp) base += ctx->wsum[w];
       total += ctx->wsum[w];
     }
+    __syncthreads();  // everybody has read the old count
     if (total > a.cap) {
       fl = 2;  // (plateaus) the whole unit is redone safely
     } else {
@@ -1122,7 +1124,7 @@ __device__ __noinline__ void cl_bootstrap_round(const TileArgs& a, TileCtx* ctx,
   if (ctx->flags & 2) return;  // the list overflowed (plateaus): the item is redone safely later; nothing is binned now
   const int nb = ctx->count;
   uint32_t my_maxbin = 0;
-  for (int i = tid; i < nb; i += kTileThreads) {
+  for (int i = max(ctx->n_boot, 0) + tid; i < nb; i += kTileThreads) {  // (what this chunk added)
     // (SIGMOID_PEAK: the entries still carry logit keys, which is the space the bins live in; a logit below -80 may
     // underflow to a zero score, which is no candidate)
     const uint32_t key = composite_key(list[i]);
@@ -1158,6 +1160,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
   const int W = a.W;
   auto now = []() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; };
   const long long t_kernel = a.trace ? now() : 0;
+  const int n_boot_chunks = min(8, max(1, (a.k + 127) / 128));
 
 #pragma unroll 1
   for (int unit = cid; unit < n_units; unit += ncl) {
@@ -1222,6 +1225,32 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
       __syncthreads();
       if (a.trace && tid == 0) a.trace[(size_t)g.item * 8 + 1] = now();
       cl_bootstrap_round<MODE>(a, ctx, list, hist, tile, origin, g, cluster, cc);
+      // A large k needs a larger sample: the first threshold lets through about k / (sample fraction) cells, and with
+      // 2048 cells per CTA a k of 1000 would make every strip pass.  One more 2048-cell chunk per 128 of k.
+      for (int c = 1; c < n_boot_chunks; ++c) {
+        ItemGeom gb = g;
+        gb.e0 = g.e0 + c * kBootElems;
+        if (gb.e0 >= g.e1) break;
+        const int ce = min(gb.e1, gb.e0 + kBootElems), org = gb.e0 - W;
+        __syncthreads();  // the tile is re-used
+        float4 t4[kRoundW];
+        load_strips<kTileThreads>(gb, 0, tid, t4);
+#pragma unroll
+        for (int u = 0; u < kRoundW; ++u) {
+          const int off = gb.e0 + ((u * kTileThreads + tid) << 2);
+          if (off < ce) *reinterpret_cast<float4*>(tile + (off - org)) = t4[u];
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int h = tid + j * kTileThreads;
+          int cell = -1;
+          if (h < nh) cell = gb.e0 - W + (h << 2);
+          else if (h < 2 * nh + 1) cell = ce + ((h - nh) << 2);
+          if (cell >= 0 && cell < plane_cells) *reinterpret_cast<float4*>(tile + (cell - org)) = ldg_stream4(g.plane + cell);
+        }
+        __syncthreads();
+        cl_bootstrap_round<MODE>(a, ctx, list, hist, tile, org, gb, cluster, cc);
+      }
       if (a.trace && tid == 0) a.trace[(size_t)g.item * 8 + 6] = now();
     }
     cluster.sync();  // (2) the sample of all eight CTAs is in their bins, the highest occupied bin is known everywhere
@@ -1252,7 +1281,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
       for (int i = tid; i < kHotCap; i += kTileThreads) hotq[i] = make_int2(-1, 0);  // (the tile is free now)
       __syncthreads();
       if (tid < 32) cl_service_warp<MODE>(a, frame, cluster);
-      else cl_stream_all(a, frame, iif, i_hi, kBootF4);
+      else cl_stream_all(a, frame, iif, i_hi, n_boot_chunks * kBootF4);
       __syncthreads();
       if (ctx->flags & 2) cl_redo_all_safely<MODE>(a, ctx, list, hist, frame, iif, i_hi);
       if (a.trace && tid == 0) {
