@@ -1203,7 +1203,9 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
       ctx->thr = 0ull;
       ctx->thr_f = TAUV_NEG_INF;
     }
-    cluster.sync();  // (1) every CTA's bins and words are ready (and nobody is still reading the previous unit's)
+    // (1) every CTA's bins and words are ready (and nobody is still reading the previous unit's).  Split barrier: the
+    // wait sits after the tile has been filled, so its latency hides behind the sample loads.
+    cluster.barrier_arrive();
 
     long long tr0 = 0;
     if (a.trace && tid == 0) tr0 = now();
@@ -1224,6 +1226,9 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
       }
       __syncthreads();
       if (a.trace && tid == 0) a.trace[(size_t)g.item * 8 + 1] = now();
+    }
+    cluster.barrier_wait();  // (1)
+    if (have) {
       cl_bootstrap_round<MODE>(a, ctx, list, hist, tile, origin, g, cluster, cc);
       // A large k needs a larger sample: the first threshold lets through about k / (sample fraction) cells, and with
       // 2048 cells per CTA a k of 1000 would make every strip pass.  One more 2048-cell chunk per 128 of k.
@@ -1263,17 +1268,8 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
       }
     }
     __syncthreads();
-    if (have && !(ctx->flags & 2) && ctx->thr != 0ull) {
-      // the bootstrap collected every peak of round 0; keep only what the first threshold lets through
-      // (stable, and all survivors are already in the bins)
-      const unsigned long long thr = ctx->thr;
-      compact_list(ctx, list, ctx->count, [&](unsigned long long c) { return c >= thr; });
-      if (tid == 0) {
-        ctx->count = ctx->base;
-        ctx->n_boot = ctx->base;
-      }
-      __syncthreads();
-    }
+    // (the bootstrap collected every peak of its sample; those below the first threshold stay in the list — they are
+    // binned already and the tail's final prune drops them — rather than paying three barriers for a compaction here)
     if (a.trace && tid == 0 && have) a.trace[(size_t)g.item * 8 + 7] = now();
 
     // ---- stream: warps 1..7 stream every item of this CTA, warp 0 serves the queue; no barrier until both are done
