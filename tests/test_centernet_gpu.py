@@ -235,6 +235,23 @@ def test_large_k_and_pruning(cn):
     assert_equal(idx, oi), assert_equal(lab, ol), assert_equal(sc, osc)
 
 
+def test_many_frames_several_units_per_cluster(cn):
+    """More frames than resident clusters (a cluster works through several frames, the fused tail runs once per
+    frame), a frame count that is not a multiple of anything, and the threshold count of decode on top."""
+    B, C, H, W, k = 150, 8, 64, 64, 50
+    logits = synth.separated_logits(B, C, H, W, seed=77, lo=-8.0, hi=3.0)
+    size, offset, depth = synth.head_views(B, H, W, seed=78)
+    o = O.decode_packed(logits, size, offset, depth, 8, 512, 512, k, 0.6)
+    mc = synth.centernet_model_config(512, 512, 3)
+    dv = lambda a: a.permute(0, 3, 1, 2).contiguous().to(cn.dev).permute(0, 2, 3, 1)
+    p = cn.D.decode_packed(pred(logits.to(cn.dev), dv(size), dv(offset), dv(depth)), mc, k, 0.6)
+    assert_equal(p.index, o.index), assert_equal(p.label, o.label), assert_close(p.score, o.score)
+    assert_equal(p.yx, o.yx), assert_equal(p.hw, o.hw), assert_equal(p.count, o.count)
+    oi, ol, osc = O.heatmap_detect(logits, k)  # RAW mode through the same kernel
+    idx, lab, sc = cn.D.heatmap_detect(logits.to(cn.dev), k)
+    assert_equal(idx, oi), assert_equal(lab, ol), assert_equal(sc, osc)
+
+
 def test_decode_full_size_vs_oracle(cn):
     """BASELINE.json configs[1] shape per frame (C=80, 128x128, k=100, stride 4) on a few frames, plus the
     other two strides of the multi-scale config at reduced batch."""
