@@ -16,7 +16,9 @@
  *    (256-byte aligned).  Work is enqueued on `stream` (a cudaStream_t); no call synchronises.
  *  - Return value: 0 = OK; < 0 = argument error (TAUV_E_*); > 0 = a cudaError_t.
  *    tauv_last_error() returns a thread-local message for the last non-zero return.
- *  - Re-entrant: no mutable globals; concurrent calls on different streams/devices are safe.
+ *  - Re-entrant: no mutable state except an idempotent, lock-protected per-device cache of launch
+ *    configuration (occupancy, opted-in shared-memory size); concurrent calls on different
+ *    streams/devices are safe.
  *  - There is no CPU path: a device without sm_100 returns TAUV_E_ARCH.
  */
 #ifndef TAUV_B200_H
@@ -101,8 +103,9 @@ int tauv_centernet_boxes(const int64_t* index, const float* score, int B, int k,
                          int in_w, int out_h, int out_w, float score_threshold, double* yx,
                          float* hw, float* depth_out, int32_t* count, tauv_stream_t stream);
 
-/* decode(prediction, model_config, n_detections, score_threshold) — decode.py:179-236,
- * device part: tauv_heatmap_topk(SIGMOID_PEAK) followed by tauv_centernet_boxes. */
+/* decode(prediction, model_config, n_detections, score_threshold) — decode.py:179-236, device part:
+ * the result of tauv_heatmap_topk(SIGMOID_PEAK) followed by tauv_centernet_boxes, in ONE launch for
+ * k <= 256 (thread-block clusters; the workspace is then not touched), two launches otherwise. */
 int tauv_centernet_decode(const float* heatmap_logits, int B, int C, int H, int W, int k,
                           const float* size, const int64_t size_strides[4], const float* offset,
                           const int64_t offset_strides[4], const float* depth,
@@ -112,10 +115,9 @@ int tauv_centernet_decode(const float* heatmap_logits, int B, int C, int H, int 
                           int32_t* count, void* workspace, size_t workspace_bytes,
                           tauv_stream_t stream);
 
-/* The two launches of tauv_centernet_decode as separate calls, so that a caller (bench.py) can put
- * stream events between them.  stage1 fills the workspace with per-item candidates (reads the
- * logits once); stage2 merges them per frame and does the box arithmetic.  Same workspace, same
- * shapes, same stream for both. */
+/* The two-launch form of tauv_centernet_decode as separate calls (profiling tools put stream events
+ * between them).  stage1 fills the workspace with candidates (reads the logits once); stage2 merges
+ * them per frame and does the box arithmetic.  Same workspace, same shapes, same stream for both. */
 int tauv_heatmap_topk_stage1(const float* heatmap, int B, int C, int H, int W, int k, int mode,
                              void* workspace, size_t workspace_bytes, tauv_stream_t stream);
 int tauv_centernet_decode_stage2(int B, int C, int H, int W, int k, const float* size,
@@ -257,8 +259,8 @@ int tauv_box_to_mask(const float* box, int H, int W, float* out, tauv_stream_t s
  *   anchor [1,N,4], truth_box [B,M,4], truth_valid [B,M] u8 ->
  *   match_index [B,N] i64 (first max on ties), match_iou [B,N] f32,
  *   positive [B,N] u8 (iou >= pos_thr), negative [B,N] u8 (iou <= neg_thr),
- *   target [B,N,4] f32 = box_encode(truth_box[match_index], anchor) (meaningful where positive;
- *   may be NULL). */
+ *   target [B,N,4] f32 = box_encode(truth_box[match_index], anchor) where positive, zeros elsewhere
+ *   (may be NULL). */
 int tauv_yolact_match_anchors(const float* anchor, const float* truth_box,
                               const uint8_t* truth_valid, int B, int N, int M, float pos_thr,
                               float neg_thr, float v0, float v1, int64_t* match_index,

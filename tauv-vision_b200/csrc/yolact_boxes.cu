@@ -76,26 +76,42 @@ __global__ void __launch_bounds__(256) match_anchors_kernel(
     int N, int M, float pos_thr, float neg_thr, float v0, float v1, int64_t* __restrict__ match_index,
     float* __restrict__ match_iou, uint8_t* __restrict__ positive, uint8_t* __restrict__ negative,
     float4* __restrict__ target) {
-  extern __shared__ float s_truth[];  // [M][6]: y0,x0,y1,x1,area,valid
+  extern __shared__ float s_truth[];  // [M][8]: y0,x0,y1,x1,area,valid, "all five finite and not NaN" flag, pad
   const int b = blockIdx.y;
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
     const Corners c = to_corners(truth_box[(size_t)b * M + m]);
-    float* s = s_truth + 6 * m;
+    float* s = s_truth + 8 * m;
     s[0] = c.y0; s[1] = c.x0; s[2] = c.y1; s[3] = c.x1; s[4] = c.area;
     s[5] = truth_valid[(size_t)b * M + m] ? 1.0f : 0.0f;
+    const float sum = c.y0 + c.x0 + c.y1 + c.x1 + c.area;  // NaN or inf in any of them poisons the sum
+    s[6] = (fabsf(sum) <= 3.0e38f) ? 1.0f : 0.0f;
+    s[7] = 0.0f;
   }
   __syncthreads();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const float4 av = anchor[n];
   const Corners ca = to_corners(av);
+  const bool a_ok = fabsf(ca.y0 + ca.x0 + ca.y1 + ca.x1 + ca.area) <= 3.0e38f;
   float best = 0.f;
   int best_m = 0;
   for (int m = 0; m < M; ++m) {
-    const float* s = s_truth + 6 * m;
-    Corners cb;
-    cb.y0 = s[0]; cb.x0 = s[1]; cb.y1 = s[2]; cb.x1 = s[3]; cb.area = s[4];
-    const float v = __fmul_rn(iou_pair(ca, cb), s[5]);  // iou * truth_valid.float()
+    const float4 s0 = *reinterpret_cast<const float4*>(s_truth + 8 * m);      // y0 x0 y1 x1
+    const float4 s1 = *reinterpret_cast<const float4*>(s_truth + 8 * m + 4);  // area valid ok -
+    float v;
+    // Most (prior, truth) pairs do not overlap: the intersection is exactly 0 and, with a positive finite union, so is
+    // the IoU (0/u = +0, times valid = +0) — no NaN-propagating min/max, no IEEE divide.  Everything else takes the
+    // reference arithmetic.
+    const float ih = __fsub_rn(fminf(ca.y1, s0.z), fmaxf(ca.y0, s0.x));
+    const float iw = __fsub_rn(fminf(ca.x1, s0.w), fmaxf(ca.x0, s0.y));
+    const float uni0 = __fadd_rn(ca.area, s1.x);
+    if (a_ok && s1.z != 0.0f && (ih <= 0.0f || iw <= 0.0f) && uni0 > 0.0f && uni0 <= 3.0e38f) {
+      v = 0.0f;
+    } else {
+      Corners cb;
+      cb.y0 = s0.x; cb.x0 = s0.y; cb.y1 = s0.z; cb.x1 = s0.w; cb.area = s1.x;
+      v = __fmul_rn(iou_pair(ca, cb), s1.y);  // iou * truth_valid.float()
+    }
     // torch.max(dim): first maximum wins; a NaN wins over everything that came before it
     if (m == 0 || v > best || (v != v && best == best)) {
       best = v;
@@ -107,7 +123,9 @@ __global__ void __launch_bounds__(256) match_anchors_kernel(
   match_iou[o] = best;
   positive[o] = best >= pos_thr;
   negative[o] = best <= neg_thr;
-  if (target) target[o] = encode_one(truth_box[(size_t)b * M + best_m], av, v0, v1);
+  // the reference encodes the positives only (loss.py:62-66): everything else is written as zeros
+  if (target)
+    target[o] = (best >= pos_thr) ? encode_one(truth_box[(size_t)b * M + best_m], av, v0, v1) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 static unsigned grid_for(long long total, int threads) {
@@ -207,7 +225,7 @@ extern "C" int tauv_yolact_match_anchors(const float* anchor, const float* truth
   TAUV_REQUIRE((uintptr_t)anchor % 16 == 0 && (uintptr_t)truth_box % 16 == 0 && (uintptr_t)target % 16 == 0, TAUV_E_ALIGN,
                "box tensors must be 16-byte aligned");
   dim3 grid((N + 255) / 256, B);
-  const size_t smem = (size_t)M * 6 * sizeof(float);
+  const size_t smem = (size_t)M * 8 * sizeof(float);
   if (smem > 48 * 1024)
     TAUV_CUDA(cudaFuncSetAttribute(match_anchors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   match_anchors_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const float4*)anchor, (const float4*)truth_box,

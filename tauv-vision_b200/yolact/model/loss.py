@@ -18,7 +18,7 @@ class AnchorMatch:
     match_iou: torch.Tensor     # [B,N] f32
     positive_match: torch.Tensor  # [B,N] bool  (iou >= config.iou_pos_threshold)
     negative_match: torch.Tensor  # [B,N] bool  (iou <= config.iou_neg_threshold)
-    box_target: torch.Tensor    # [B,N,4] f32 — box_encode(truth_box[match_index], anchor); use where positive
+    box_target: torch.Tensor    # [B,N,4] f32 — box_encode(truth_box[match_index], anchor) where positive, 0 elsewhere
 
 
 def match_anchors(anchor: torch.Tensor, truth_box: torch.Tensor, truth_valid: torch.Tensor, config) -> AnchorMatch:
