@@ -714,7 +714,10 @@ constexpr int kClBins = 2 * kClWin;                   // negative window + posit
 constexpr int kClNegBase = 1536;                      // fine bins [1536, 2560): -2^33 .. -2^-31
 constexpr int kClPosBase = 5632;                      // fine bins [5632, 6656): +2^-31 .. +2^33
 // (measured on B200: 2 beats 3 and 4 — wider rounds spill a loaded register, and a spill right after the load waits for it)
-constexpr int kRoundW = 2;                            // 128-bit strips per thread and round (2 x kRoundW live in registers)
+#ifndef TAUV_ROUND_W
+#define TAUV_ROUND_W 2
+#endif
+constexpr int kRoundW = TAUV_ROUND_W;                            // 128-bit strips per thread and round (2 x kRoundW live in registers)
 constexpr int kStreamThreads = kTileThreads - 32;     // warps 1..7 stream, warp 0 serves
 constexpr int kRoundF4 = kRoundW * kStreamThreads;    // 128-bit strips per streaming round per CTA
 constexpr int kBootF4 = kRoundW * kTileThreads;       // strips of the bootstrap round (all eight warps)
