@@ -345,7 +345,7 @@ def main():
         if tp.exists():
             traffic = json.loads(tp.read_text()).get("tile_cluster_kernel_bytes_per_launch")
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # (the CPU leg is reported at N = 1 only)
             fps, per = cpu_reference_sample(B_PER_GPU, 5)
             cpu = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                    "sample": f"{B_PER_GPU} frames x 5 reps of decode+encode ({per:.2f} s per batch), torch-CPU oracle port"}
