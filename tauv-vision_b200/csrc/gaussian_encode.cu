@@ -356,6 +356,120 @@ __global__ void __launch_bounds__(kEncThreads) keypoint_encode_kernel(
   }
 }
 
+// Frames with at most 32*NCH keypoint instances: one WARP per 8 KB chunk of a keypoint plane, like
+// gaussian_encode_warp_kernel.  Lane l holds instances l, l+32, ... (chunk-major ballots walked in ascending bit order
+// ARE the instance order that decides affinity ties, loss.py:122); a plane without instances is four runs of coalesced zero stores (heatmap, weight,
+// affinity y and x), the others broadcast the matching instances with shuffles.  No shared memory, no block barrier.
+template <int NCH>
+__global__ void __launch_bounds__(kEncThreads) keypoint_encode_warp_kernel(
+    const uint8_t* __restrict__ kp_valid, const int64_t* __restrict__ kp_label, const float* __restrict__ kp_center,
+    const int64_t* __restrict__ kp_obj, const float* __restrict__ center, int m, int n_objects, int Kp, int H, int W,
+    float in_h, float in_w, float ratio, float two_sh2, float two_sa2, int chunks_per_plane, long long n_chunks,
+    float* __restrict__ heatmap, float* __restrict__ weight, float* __restrict__ affinity) {
+  const int lane = threadIdx.x & 31;
+  const long long chunk_id = (long long)blockIdx.x * (kEncThreads / 32) + (threadIdx.x >> 5);
+  if (chunk_id >= n_chunks) return;
+  const long long plane = chunk_id / chunks_per_plane;
+  const int chunk = (int)(chunk_id - plane * chunks_per_plane);
+  const int k = (int)(plane % Kp);
+  const long long b = plane / Kp;
+  int cy[NCH], cx[NCH];
+  float oy[NCH], ox[NCH];
+  unsigned mask[NCH];
+  unsigned any_mask = 0u;
+  bool far = false;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    bool mine = false;
+    cy[c] = cx[c] = 0;
+    oy[c] = ox[c] = 0.f;
+    const int inst = lane + 32 * c;
+    if (inst < m) {
+      const long long gi = b * m + inst;
+      const uint8_t v = __ldg(kp_valid + gi);
+      const long long l = __ldg(kp_label + gi);
+      const float c0 = __ldg(kp_center + gi * 2), c1 = __ldg(kp_center + gi * 2 + 1);
+      long long oi = __ldg(kp_obj + gi);
+      if (v && l == k) {
+        mine = true;
+        cy[c] = grid_floor(c0, in_h, ratio);
+        cx[c] = grid_floor(c1, in_w, ratio);
+        if (oi < 0) oi += n_objects;  // torch negative indexing
+        oi = max(0LL, min((long long)n_objects - 1, oi));
+        oy[c] = __ldg(center + (b * n_objects + oi) * 2 + 0);
+        ox[c] = __ldg(center + (b * n_objects + oi) * 2 + 1);
+        far |= abs(cy[c]) > 20000 || abs(cx[c]) > 20000;
+      }
+    }
+    mask[c] = __ballot_sync(0xffffffffu, mine);
+    any_mask |= mask[c];
+  }
+  const int S = W >> 2;
+  const int plane_strips = H * S;
+  const int s0 = chunk * kEncWarpStrips;
+  const int s1 = min(plane_strips, s0 + kEncWarpStrips);
+  const size_t hw = (size_t)H * W;
+  float4* h4 = reinterpret_cast<float4*>(heatmap + (size_t)plane * hw);
+  float4* w4 = reinterpret_cast<float4*>(weight + (size_t)plane * hw);
+  float4* y4 = reinterpret_cast<float4*>(affinity + (size_t)plane * 2 * hw);
+  float4* x4 = reinterpret_cast<float4*>(affinity + (size_t)plane * 2 * hw + hw);
+  if (any_mask == 0u) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int t = s0 + lane; t < s1; t += 32) { h4[t] = z; w4[t] = z; y4[t] = z; x4[t] = z; }
+    return;
+  }
+  const bool big = __any_sync(0xffffffffu, far) || H > 10000 || W > 10000;
+  const float fh = (float)H, fw = (float)W;
+  for (int t0 = s0; t0 < s1; t0 += 32) {  // (warp-uniform trip count: the shuffles below need every lane)
+    const int t = t0 + lane;
+    const int y = t / S;
+    const int xb = (t - y * S) << 2;
+    const float py = __fdiv_rn((float)y, fh);  // loss.py:114
+    long long best[4] = {0x7fffffffffffffffLL, 0x7fffffffffffffffLL, 0x7fffffffffffffffLL, 0x7fffffffffffffffLL};
+    float cur[4], a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, px[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      cur[i] = __int_as_float(0x7f800000);
+      px[i] = __fdiv_rn((float)(xb + i), fw);
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+    for (unsigned mm = mask[c]; mm; mm &= mm - 1) {  // chunk-major, ascending lane = instance order
+      const int j = __ffs(mm) - 1;
+      const int jcy = __shfl_sync(0xffffffffu, cy[c], j), jcx = __shfl_sync(0xffffffffu, cx[c], j);
+      const float joy = __shfl_sync(0xffffffffu, oy[c], j), jox = __shfl_sync(0xffffffffu, ox[c], j);
+      const float dyf = nan_to_num(__fsub_rn(py, joy), 0.f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (!big) {
+          const int dy = y - jcy, dx = xb + i - jcx;
+          best[i] = min(best[i], (long long)(dy * dy + dx * dx));
+        } else {
+          const long long dy = y - jcy, dx = xb + i - jcx;
+          best[i] = min(best[i], dy * dy + dx * dx);
+        }
+        // affinity: unit vector from the owning object's centre, nearest object wins, first on ties
+        const float dxf = nan_to_num(__fsub_rn(px[i], jox), 0.f);
+        const float dist = nan_to_num(__fsqrt_rn(__fadd_rn(__fmul_rn(dyf, dyf), __fmul_rn(dxf, dxf))), 1.f);
+        if (dist < cur[i]) {
+          a0[i] = __fdiv_rn(dyf, dist);
+          a1[i] = __fdiv_rn(dxf, dist);
+          cur[i] = dist;
+        }
+      }
+    }
+    if (t < s1) {
+      h4[t] = make_float4(gauss_from_d2(best[0], two_sh2), gauss_from_d2(best[1], two_sh2), gauss_from_d2(best[2], two_sh2),
+                          gauss_from_d2(best[3], two_sh2));
+      w4[t] = make_float4(gauss_from_d2(best[0], two_sa2), gauss_from_d2(best[1], two_sa2), gauss_from_d2(best[2], two_sa2),
+                          gauss_from_d2(best[3], two_sa2));
+      y4[t] = make_float4(nan_to_num(a0[0], 0.f), nan_to_num(a0[1], 0.f), nan_to_num(a0[2], 0.f), nan_to_num(a0[3], 0.f));
+      x4[t] = make_float4(nan_to_num(a1[0], 0.f), nan_to_num(a1[1], 0.f), nan_to_num(a1[2], 0.f), nan_to_num(a1[3], 0.f));
+    }
+  }
+}
+
 __global__ void out_index_offset_kernel(const float* __restrict__ pos, long long n, float in_h, float in_w,
                                         float ratio, long long iratio, int out_h, int out_w,
                                         int64_t* __restrict__ index, float* __restrict__ offset) {
@@ -463,7 +577,21 @@ extern "C" int tauv_keypoint_encode(const uint8_t* kp_valid, const int64_t* kp_l
   // generate_keypoint_heatmap does not floor sigma (loss.py:101,109): plain 2*sigma**2
   const float tsh = (float)(2.0 * (sigma_heatmap * sigma_heatmap));
   const float tsa = (float)(2.0 * (sigma_affinity * sigma_affinity));
-  if (vec)
+  if (vec && m <= 128 && m > 0) {
+    const long long plane_strips = (long long)H * (W / 4);
+    const long long cpp = (plane_strips + kEncWarpStrips - 1) / kEncWarpStrips;
+    const long long n_chunks = planes * cpp;
+    const long long wgrid = (n_chunks + kEncThreads / 32 - 1) / (kEncThreads / 32);
+    TAUV_REQUIRE(wgrid < (1LL << 31) && cpp < (1LL << 31), TAUV_E_UNSUPPORTED, "grid too large");
+#define TAUV_KP_WARP(NCH)                                                                                             \
+    keypoint_encode_warp_kernel<NCH><<<(unsigned)wgrid, kEncThreads, 0, (cudaStream_t)stream>>>(                       \
+        kp_valid, kp_label, kp_center, kp_object_index, center, m, n_objects, Kp, H, W, (float)in_h, (float)in_w,      \
+        (float)downsample_ratio, tsh, tsa, (int)cpp, n_chunks, heatmap, weight, affinity)
+    if (m <= 32) TAUV_KP_WARP(1);
+    else if (m <= 64) TAUV_KP_WARP(2);
+    else TAUV_KP_WARP(4);
+#undef TAUV_KP_WARP
+  } else if (vec)
     keypoint_encode_kernel<true><<<(unsigned)grid, kEncThreads, smem, (cudaStream_t)stream>>>(
         kp_valid, kp_label, kp_center, kp_object_index, center, m, n_objects, Kp, H, W, (float)in_h, (float)in_w,
         (float)downsample_ratio, tsh, tsa, bands, rows, heatmap, weight, affinity);

@@ -15,7 +15,7 @@ def timeit(fn, n=7):
         ts.append(e0.elapsed_time(e1) * 1e3)
     ts.sort(); return ts[len(ts) // 2]
 g = torch.Generator(device=dev); g.manual_seed(1)
-for (B, Kp, H, n, m) in [(64, 80, 128, 16, 16), (64, 24, 128, 16, 48)]:
+for (B, Kp, H, n, m) in [(64, 80, 128, 16, 16), (64, 32, 128, 16, 32), (64, 24, 128, 16, 48)]:
     truth = SimpleNamespace(valid=torch.rand((B, n), device=dev, generator=g) < 0.75,
                             label=torch.randint(0, 8, (B, n), device=dev, generator=g),
                             center=torch.rand((B, n, 2), device=dev, generator=g),
