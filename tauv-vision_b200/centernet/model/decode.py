@@ -23,6 +23,8 @@ import torch
 
 from ... import _lib
 
+_NP_DTYPE = {torch.int64: np.int64, torch.float64: np.float64, torch.float32: np.float32, torch.int32: np.int32}
+
 TOPK_RAW = 0
 TOPK_SIGMOID_PEAK = 1
 BOX_DECODE = 0
@@ -78,29 +80,51 @@ class PackedDetections:
     hw: torch.Tensor
     depth: Optional[torch.Tensor]
     count: torch.Tensor
+    _storage: Optional[torch.Tensor] = None  # one uint8 buffer all the tensors above are views of (if allocated here)
+    _layout: Optional[tuple] = None          # ((name, dtype, shape, byte offset, bytes), ...)
+
+    _FIELDS = (("index", torch.int64, 8, 2), ("label", torch.int64, 8, 1), ("yx", torch.float64, 8, 2),
+               ("score", torch.float32, 4, 1), ("hw", torch.float32, 4, 2), ("depth", torch.float32, 4, 1))
+
+    @classmethod
+    def allocate(cls, B: int, k: int, with_depth: bool, device) -> "PackedDetections":
+        """All outputs as typed views of ONE device buffer (8-byte fields first), so that ``to_host`` is one copy."""
+        layout, off = [], 0
+        for name, dtype, isz, per in cls._FIELDS:
+            if name == "depth" and not with_depth:
+                continue
+            layout.append((name, dtype, (B, k, per) if per > 1 else (B, k), off, B * k * per * isz))
+            off += (B * k * per * isz + 15) // 16 * 16
+        layout.append(("count", torch.int32, (B,), off, B * 4))
+        off += (B * 4 + 15) // 16 * 16
+        storage = torch.empty((off,), dtype=torch.uint8, device=device)
+        views = {name: storage[o:o + nb].view(dtype).view(shape) for name, dtype, shape, o, nb in layout}
+        return cls(views["index"], views["label"], views["score"], views["yx"], views["hw"], views.get("depth"),
+                   views["count"], storage, tuple(layout))
 
     def to_host(self) -> dict:
         """One synchronising device->host transfer of everything."""
+        if self._storage is not None:
+            raw = self._storage.cpu().numpy()
+            out = {"depth": None}
+            for name, dtype, shape, o, nb in self._layout:
+                out[name] = raw[o:o + nb].view(_NP_DTYPE[dtype]).reshape(shape)
+            return out
         out = {k: getattr(self, k).cpu().numpy() for k in ("index", "label", "score", "yx", "hw", "count")}
         out["depth"] = self.depth.cpu().numpy() if self.depth is not None else None
         return out
 
     def to_lists(self) -> List[List[Detection]]:
         h = self.to_host()
+        # (numpy -> Python scalars in bulk: .tolist() is several times faster than item-by-item conversion)
+        label, score, yx, hw = h["label"].tolist(), h["score"].tolist(), h["yx"].tolist(), h["hw"].tolist()
+        depth = h["depth"].tolist() if h["depth"] is not None else None
         frames = []
-        for b in range(h["count"].shape[0]):
-            dets = []
-            for i in range(int(h["count"][b])):
-                dets.append(Detection(
-                    label=int(h["label"][b, i]),
-                    score=float(h["score"][b, i]),
-                    y=float(h["yx"][b, i, 0]),
-                    x=float(h["yx"][b, i, 1]),
-                    h=float(h["hw"][b, i, 0]),
-                    w=float(h["hw"][b, i, 1]),
-                    depth=float(h["depth"][b, i]) if h["depth"] is not None else None,
-                ))
-            frames.append(dets)
+        for b, n in enumerate(h["count"].tolist()):
+            lb, sb, yb, hb = label[b], score[b], yx[b], hw[b]
+            db = depth[b] if depth is not None else None
+            frames.append([Detection(label=lb[i], score=sb[i], y=yb[i][0], x=yb[i][1], h=hb[i][0], w=hb[i][1],
+                                     depth=db[i] if db is not None else None) for i in range(n)])
         return frames
 
 
@@ -193,13 +217,9 @@ def decode_packed(prediction, model_config, n_detections: int, score_threshold: 
         if tuple(index.shape) != (B, k, 2) or (depth is not None) != (depth_out is not None):
             raise ValueError("`out` does not match this call's shapes")
     else:
-        index = torch.empty((B, k, 2), dtype=torch.int64, device=dev)
-        label = torch.empty((B, k), dtype=torch.int64, device=dev)
-        score = torch.empty((B, k), dtype=torch.float32, device=dev)
-        yx = torch.empty((B, k, 2), dtype=torch.float64, device=dev)
-        hw = torch.empty((B, k, 2), dtype=torch.float32, device=dev)
-        depth_out = torch.empty((B, k), dtype=torch.float32, device=dev) if depth is not None else None
-        count = torch.empty((B,), dtype=torch.int32, device=dev)
+        out = PackedDetections.allocate(B, k, depth is not None, dev)
+        index, label, score, yx, hw, depth_out, count = (out.index, out.label, out.score, out.yx, out.hw, out.depth,
+                                                         out.count)
     with torch.cuda.device(dev):
         nbytes = lib.tauv_heatmap_topk_workspace_bytes(B, C, H, W, k)
         ws = _lib.workspace(dev, nbytes)
@@ -220,7 +240,7 @@ def decode_packed(prediction, model_config, n_detections: int, score_threshold: 
             e1.record()
             _lib.check(lib.tauv_centernet_decode_stage2(B, C, H, W, k, *tail))
             e2.record()
-    return PackedDetections(index, label, score, yx, hw, depth_out, count)
+    return out
 
 
 def decode(prediction, model_config, n_detections: int, score_threshold: float) -> List[List[Detection]]:

@@ -56,7 +56,9 @@ static int make_plan(int B, int C, int H, int W, int k, const void* ptr, TopkPla
   if (rows_item < 1) rows_item = 1;
   const long long planes = (long long)B * C;
   const int sms = num_sms();
-  while (rows_item > 1 && planes * ((H + rows_item - 1) / rows_item) < 8LL * sms) rows_item = (rows_item + 1) / 2;
+  // (two items per SM are plenty: the cluster kernel deals a unit's items to 8 CTAs and wants several rounds per item —
+  // at batch 1 a finer split only made thousands of one-row items and a heavy merge)
+  while (rows_item > 1 && planes * ((H + rows_item - 1) / rows_item) < 2LL * sms) rows_item = (rows_item + 1) / 2;
   if (rows_item > H) rows_item = H;
   p->rows_per_item = rows_item;
   p->items_per_plane = (H + rows_item - 1) / rows_item;
@@ -1685,8 +1687,9 @@ static int run_stage1(const float* hm, int B, int C, int H, int W, int k, int mo
   int parts = 1;
   if (B < ncl) {
     parts = ncl / B;
-    const int by_items = p.items_per_frame / kClSize;
+    const int by_items = p.items_per_frame / (2 * kClSize);  // at least two items per CTA
     if (parts > by_items) parts = by_items;
+    if (parts > 8) parts = 8;  // (every part pays its own bootstrap and adds 8 rows to the merge; 64 CTAs per frame suffice)
     if (parts < 1) parts = 1;
   }
   const long long n_units = (long long)B * parts;
