@@ -15,9 +15,10 @@
 // consecutive pixels in its 32 lanes, i.e. one fully coalesced 128-byte store per detection and warp, straight from
 // registers (the mask write is >80 % of the bytes this kernel moves).
 // Persistent, warp-specialised, one CTA per SM:
-//   warps 0-7  epilogue : tcgen05.ld -> sigmoid + crop -> coalesced row stores (2 warps per TMEM lane quadrant)
-//   warps 8-11 producer : fp32 -> bf16 hi/lo conversion of the A tile (and of B / the crop bounds at a frame change)
-//   warp  12   MMA      : one elected thread issues tcgen05.mma (K = 16 per instruction) + commits
+//   warps 0-11  epilogue : tcgen05.ld -> sigmoid + crop -> rows staged in shared memory -> one TMA tensor store per
+//                          32 detections (three groups of four warps, one warp per TMEM lane quadrant)
+//   warps 12-15 producer : fp32 -> bf16 hi/lo conversion of the A tile (and of B / the crop bounds at a frame change)
+//   warp  16    MMA      : one elected thread issues tcgen05.mma (K = 16 per instruction) + commits
 // All hand-offs are mbarriers; tcgen05.commit arrives on them when the tensor core is done with an operand.
 // The contraction depth is 32, i.e. ~12 flop per byte moved: the kernel is bound by the fp32 mask WRITE, the tensor
 // pipe idles most of the time by construction.
@@ -30,12 +31,30 @@ namespace tauv {
 constexpr int kUmmaP = 32;            // contraction depth this kernel is built for
 constexpr int kUmmaM = 128;           // pixels per MMA tile (TMEM lanes)
 constexpr int kUmmaNMax = 256;        // detections per launch (TMEM columns per accumulator stage); more: host loops
-constexpr int kUmmaEpiWarps = 8, kUmmaProdWarps = 4;
-constexpr int kUmmaThreads = (kUmmaEpiWarps + kUmmaProdWarps + 1) * 32;  // 416
+#ifndef TAUV_MASK_EPI_WARPS
+#define TAUV_MASK_EPI_WARPS 12
+#endif
+#ifndef TAUV_MASK_PROD_WARPS
+#define TAUV_MASK_PROD_WARPS 4
+#endif
+// (measured with tools/mask_trace.py and tools/variants_mask.sh: 8 epilogue + 4 producer warps, 2 A stages: 1777 us per
+// 64 frames, epilogue-bound at 5 us per tile; 12 + 4 warps: 1279 us, now producer-bound (latency of the prototype loads);
+// 12 + 4 warps with 3 A stages and 2 staging buffers per group: 1008 us; 16 epilogue warps spill: 2756 us)
+constexpr int kUmmaEpiWarps = TAUV_MASK_EPI_WARPS, kUmmaProdWarps = TAUV_MASK_PROD_WARPS;
+#ifndef TAUV_MASK_A_STAGES
+#define TAUV_MASK_A_STAGES 3
+#endif
+#ifndef TAUV_MASK_STAGE_BUFS
+#define TAUV_MASK_STAGE_BUFS 2
+#endif
+constexpr int kUmmaGroups = kUmmaEpiWarps / 4;  // an epilogue group = four warps, one per TMEM lane quadrant
+constexpr int kUmmaAStages = TAUV_MASK_A_STAGES;      // prototype tiles in flight (the producers are latency-bound)
+constexpr int kUmmaStageBufs = TAUV_MASK_STAGE_BUFS;  // output staging buffers per epilogue group
+constexpr int kUmmaThreads = (kUmmaEpiWarps + kUmmaProdWarps + 1) * 32;
 
 struct UmmaSmem {
   // each operand is kept as a bf16 pair (hi, lo) with hi + lo == the fp32 value to ~2^-17
-  __align__(1024) unsigned char a[2][2][kUmmaM * 64];     // [stage][hi/lo] prototype tiles, 4 x 8 KB
+  __align__(1024) unsigned char a[kUmmaAStages][2][kUmmaM * 64];  // [stage][hi/lo] prototype tiles, 8 KB each
   __align__(1024) unsigned char b[2][kUmmaNMax * 64];     // [hi/lo] coefficients of the frame, 2 x 16 KB
   float bounds[kUmmaNMax][4];                             // crop bounds (left, right, top, bottom) per detection
   __align__(16) float zeros[kUmmaM];                      // source of the bulk zero-fill stores
@@ -43,8 +62,8 @@ struct UmmaSmem {
   // TMEM lane quadrant (32 pixels), and 128-byte segments scattered over ~160 masks that lie 305 KB apart run HBM at
   // 1.6 TB/s (tools/store_bench.cu); 512-byte rows reach 3.9 TB/s.  So the four quadrant warps of a group assemble
   // whole 512-byte rows here and one of them hands each row to the bulk-copy engine.
-  __align__(128) float stage[2][4][32][kUmmaM];           // 128 KB: four buffers per group (one barrier per chunk, two chunks of stores in flight)
-  uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], frame_done;
+  __align__(128) float stage[kUmmaGroups][kUmmaStageBufs][32][kUmmaM];  // 16 KB per buffer (one barrier per chunk)
+  uint64_t a_full[kUmmaAStages], a_empty[kUmmaAStages], acc_full[2], acc_empty[2], frame_done;
   uint32_t tmem_base;
 };
 
@@ -151,9 +170,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
   const long long u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kUmmaAStages; ++s) {
       mbar_init(&sm->a_full[s], kUmmaProdWarps * 32);
       mbar_init(&sm->a_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&sm->acc_full[s], 1);
       mbar_init(&sm->acc_empty[s], kUmmaEpiWarps * 32);
     }
@@ -175,7 +196,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
 
   if (warp < kUmmaEpiWarps) {
     // ======================================= epilogue =======================================
-    const int quad = warp & 3, half = warp >> 2;  // TMEM lane quadrant / which 32-detection chunks (even, odd)
+    const int quad = warp & 3, half = warp >> 2;  // TMEM lane quadrant / epilogue group (takes chunks half, half + groups, ...)
     // bulk stores need 16-byte aligned rows: H*W % 4 == 0 and an aligned output
     const bool bulk_zero = (HW % 4 == 0) && ((uintptr_t)a.out % 16 == 0);
     uint32_t uses[2] = {0, 0};
@@ -201,7 +222,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
       tc_fence_after();
       if (tid == 0) mask_stamp(a, u - u0, 5);
 #pragma unroll 1
-      for (int c = half; c * 32 < n_rows; c += 2) {
+      for (int c = half; c * 32 < n_rows; c += kUmmaGroups) {
         // lane j looks at detection c*32+j: does its box reach the tile at all?  If not, one bulk store of zeros
         // (shared -> global, issued by a single lane of the quadrant-0 warp) replaces 4 warps x 1 store + tests.
         bool live = false;
@@ -224,7 +245,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
         const float4* bp = reinterpret_cast<const float4*>(sm->bounds[c * 32]);
         if (bulk_zero) {
           // ---- staged path: rows of 128 pixels assembled in shared memory, one bulk store per (detection, tile)
-          float (*stg)[kUmmaM] = sm->stage[half][nbuf & 3u];
+          float (*stg)[kUmmaM] = sm->stage[half][nbuf % (uint32_t)kUmmaStageBufs];
           // Branch-free AND predicate-free on purpose.  With a vote and a branch per detection — or even just the
           // chained FSETPs of the crop test and the range fix-ups of __expf / __fdividef, which all funnel through one
           // predicate register — the 32 iterations ran strictly one after the other (~100-160 cycles each: 5-8 us of
@@ -265,8 +286,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
               if ((live_mask >> j) & 1u) lp[(size_t)j * HW] = v[j];
           }
           fence_proxy_async();  // generic-proxy writes -> visible to the bulk-copy engine
-          // (before the barrier: the stores issued from the buffer the NEXT chunk will fill — three chunks ago — have read it)
-          if (quad == 0) bulk_wait_read<2>();
+          // (before the barrier: the stores issued from the buffer the NEXT chunk will fill have read it)
+          if (quad == 0) bulk_wait_read<(kUmmaStageBufs >= 2 ? kUmmaStageBufs - 2 : 0)>();
           asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
           if (quad == 0) {
             if (use_tma) {
@@ -312,8 +333,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
     bulk_wait<0>();  // the zero-fill stores this thread issued have completed
   } else if (warp < kUmmaEpiWarps + kUmmaProdWarps) {
     // ======================================= producers =======================================
-    const int pt = tid - kUmmaEpiWarps * 32;  // 0..127: the pixel row of the A tile this thread converts
-    uint32_t fills[2] = {0, 0}, frames = 0;
+    const int pt = tid - kUmmaEpiWarps * 32;  // producer thread index: the pixel rows of the A tile this thread converts
+    uint32_t fills[kUmmaAStages] = {}, frames = 0;
     int st = 0, cur_frame = -1, rows_frame = -1, n_rows = 0;
     for (long long u = u0; u < u1; ++u) {
       const int b = (int)(u / n_tiles), nt = (int)(u - (long long)b * n_tiles);
@@ -358,31 +379,34 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
       }
       if (fills[st] > 0) mbar_wait(&sm->a_empty[st], (fills[st] - 1) & 1u);
       if (pt == 0) mask_stamp(a, u - u0, 0);
-      // A tile: pixel row pt, 32 prototype values -> 4 chunks of 8 bf16 (hi and lo)
-      const int pix = nt * kUmmaM + pt;
-      const float* src = a.proto + (size_t)b * kUmmaP * HW + pix;
-      float f[kUmmaP];
+      // A tile: pixel rows pt, pt + producers, ...; 32 prototype values each -> 4 chunks of 8 bf16 (hi and lo)
+#pragma unroll 1
+      for (int pr = pt; pr < kUmmaM; pr += kUmmaProdWarps * 32) {
+        const int pix = nt * kUmmaM + pr;
+        const float* src = a.proto + (size_t)b * kUmmaP * HW + pix;
+        float f[kUmmaP];
 #pragma unroll
-      for (int p = 0; p < kUmmaP; ++p) f[p] = pix < HW ? __ldg(src + (size_t)p * HW) : 0.0f;
+        for (int p = 0; p < kUmmaP; ++p) f[p] = pix < HW ? __ldg(src + (size_t)p * HW) : 0.0f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 qh, ql;
-        split_bf16x2(f[8 * c], f[8 * c + 1], qh.x, ql.x);
-        split_bf16x2(f[8 * c + 2], f[8 * c + 3], qh.y, ql.y);
-        split_bf16x2(f[8 * c + 4], f[8 * c + 5], qh.z, ql.z);
-        split_bf16x2(f[8 * c + 6], f[8 * c + 7], qh.w, ql.w);
-        *reinterpret_cast<uint4*>(sm->a[st][0] + sw64_offset(pt, c)) = qh;
-        *reinterpret_cast<uint4*>(sm->a[st][1] + sw64_offset(pt, c)) = ql;
+        for (int c = 0; c < 4; ++c) {
+          uint4 qh, ql;
+          split_bf16x2(f[8 * c], f[8 * c + 1], qh.x, ql.x);
+          split_bf16x2(f[8 * c + 2], f[8 * c + 3], qh.y, ql.y);
+          split_bf16x2(f[8 * c + 4], f[8 * c + 5], qh.z, ql.z);
+          split_bf16x2(f[8 * c + 6], f[8 * c + 7], qh.w, ql.w);
+          *reinterpret_cast<uint4*>(sm->a[st][0] + sw64_offset(pr, c)) = qh;
+          *reinterpret_cast<uint4*>(sm->a[st][1] + sw64_offset(pr, c)) = ql;
+        }
       }
       fence_proxy_async();  // generic-proxy writes (A, and B / bounds at a frame change) -> visible to the async proxy
       if (pt == 0) mask_stamp(a, u - u0, 1);
       mbar_arrive(&sm->a_full[st]);
       ++fills[st];
-      st ^= 1;
+      st = st + 1 == kUmmaAStages ? 0 : st + 1;
     }
   } else if (lane == 0) {
     // ======================================= MMA issuer =======================================
-    uint32_t fills[2] = {0, 0}, uses[2] = {0, 0};
+    uint32_t fills[kUmmaAStages] = {}, uses[2] = {0, 0};
     int st = 0, as = 0, rows_frame = -1, n_rows = 0;
     for (long long u = u0; u < u1; ++u) {
       const int b = (int)(u / n_tiles);
@@ -412,7 +436,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
       ++uses[as];
       as ^= 1;
       ++fills[st];
-      st ^= 1;
+      st = st + 1 == kUmmaAStages ? 0 : st + 1;
     }
   }
 
