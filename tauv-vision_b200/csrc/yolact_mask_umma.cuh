@@ -41,6 +41,9 @@ constexpr int kUmmaNMax = 256;        // detections per launch (TMEM columns per
 // 64 frames, epilogue-bound at 5 us per tile; 12 + 4 warps: 1279 us, now producer-bound (latency of the prototype loads);
 // 12 + 4 warps with 3 A stages and 2 staging buffers per group: 1008 us; 16 epilogue warps spill: 2756 us)
 constexpr int kUmmaEpiWarps = TAUV_MASK_EPI_WARPS, kUmmaProdWarps = TAUV_MASK_PROD_WARPS;
+#ifndef TAUV_MASK_PREFETCH
+#define TAUV_MASK_PREFETCH 1  // tiles ahead (measured: 0 -> 996 us, 1 -> 965, 2 -> 1035, 4 -> 1157 per 64 frames)
+#endif
 #ifndef TAUV_MASK_A_STAGES
 #define TAUV_MASK_A_STAGES 3
 #endif
@@ -377,25 +380,44 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
         cur_frame = b;
         ++frames;
       }
-      if (fills[st] > 0) mbar_wait(&sm->a_empty[st], (fills[st] - 1) & 1u);
-      if (pt == 0) mask_stamp(a, u - u0, 0);
-      // A tile: pixel rows pt, pt + producers, ...; 32 prototype values each -> 4 chunks of 8 bf16 (hi and lo)
+      if (TAUV_MASK_PREFETCH > 0 && u + TAUV_MASK_PREFETCH < u1) {
+        // The producers' cost is the latency of their 32 loads per pixel row (2.8 us per tile straight from HBM under
+        // the write stream).  Holding the next tile in registers spills (the kernel is capped at 96 registers by its
+        // 17 warps) and a spill waits for the load; an L2 prefetch of a later tile costs two instructions per thread:
+        // 32 planes x 512 bytes = 128 lines, one (+ the straddled one: plane bases are not 128-byte aligned) each.
+        const long long u2 = u + TAUV_MASK_PREFETCH;
+        const int b2 = (int)(u2 / n_tiles), nt2 = (int)(u2 - (long long)b2 * n_tiles);
+        for (int i = pt; i < kUmmaP * 4; i += kUmmaProdWarps * 32) {
+          const int p = i >> 2, q = i & 3;
+          const int pix = nt2 * kUmmaM + q * 32;
+          if (pix < HW) {
+            const float* src = a.proto + ((size_t)b2 * kUmmaP + p) * HW + pix;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+            if (pix + 31 < HW) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 31));
+          }
+        }
+      }
+      {
+        if (fills[st] > 0) mbar_wait(&sm->a_empty[st], (fills[st] - 1) & 1u);
+        if (pt == 0) mask_stamp(a, u - u0, 0);
+        // A tile: pixel rows pt, pt + producers, ...; 32 prototype values each -> 4 chunks of 8 bf16 (hi and lo)
 #pragma unroll 1
-      for (int pr = pt; pr < kUmmaM; pr += kUmmaProdWarps * 32) {
-        const int pix = nt * kUmmaM + pr;
-        const float* src = a.proto + (size_t)b * kUmmaP * HW + pix;
-        float f[kUmmaP];
+        for (int pr = pt; pr < kUmmaM; pr += kUmmaProdWarps * 32) {
+          const int pix = nt * kUmmaM + pr;
+          const float* src = a.proto + (size_t)b * kUmmaP * HW + pix;
+          float f[kUmmaP];
 #pragma unroll
-        for (int p = 0; p < kUmmaP; ++p) f[p] = pix < HW ? __ldg(src + (size_t)p * HW) : 0.0f;
+          for (int p = 0; p < kUmmaP; ++p) f[p] = pix < HW ? __ldg(src + (size_t)p * HW) : 0.0f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 qh, ql;
-          split_bf16x2(f[8 * c], f[8 * c + 1], qh.x, ql.x);
-          split_bf16x2(f[8 * c + 2], f[8 * c + 3], qh.y, ql.y);
-          split_bf16x2(f[8 * c + 4], f[8 * c + 5], qh.z, ql.z);
-          split_bf16x2(f[8 * c + 6], f[8 * c + 7], qh.w, ql.w);
-          *reinterpret_cast<uint4*>(sm->a[st][0] + sw64_offset(pr, c)) = qh;
-          *reinterpret_cast<uint4*>(sm->a[st][1] + sw64_offset(pr, c)) = ql;
+          for (int c = 0; c < 4; ++c) {
+            uint4 qh, ql;
+            split_bf16x2(f[8 * c], f[8 * c + 1], qh.x, ql.x);
+            split_bf16x2(f[8 * c + 2], f[8 * c + 3], qh.y, ql.y);
+            split_bf16x2(f[8 * c + 4], f[8 * c + 5], qh.z, ql.z);
+            split_bf16x2(f[8 * c + 6], f[8 * c + 7], qh.w, ql.w);
+            *reinterpret_cast<uint4*>(sm->a[st][0] + sw64_offset(pr, c)) = qh;
+            *reinterpret_cast<uint4*>(sm->a[st][1] + sw64_offset(pr, c)) = ql;
+          }
         }
       }
       fence_proxy_async();  // generic-proxy writes (A, and B / bounds at a frame change) -> visible to the async proxy
