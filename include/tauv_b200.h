@@ -252,6 +252,33 @@ int tauv_yolact_assemble_mask_batched(const float* proto, const float* coeff_all
                                       const float* keep_box, int B, int N, int P, int H, int W,
                                       int top_k, float* out, tauv_stream_t stream);
 
+/* Mask assembly fused with its consumer — yolact/node/yolact_node.py:102-103,130-131,178-183:
+ *     depth = where(depth_mm == 0, nan, depth_mm) / 1000                        (:102-103, float64)
+ *     mask  = F.interpolate(assemble_mask(proto, coeff, box)[None], (Hi, Wi))   (:130-131, 'nearest')
+ *     mean_depth[i] = nanmean(where(mask[i] > 0.5, depth, nan))                 (:178)
+ * computed without materialising any mask: the depth image is pooled onto the prototype grid with the inverse of
+ * the nearest-neighbour map (sum and count of the valid readings per prototype pixel, exact integers), and the
+ * tensor-core kernel's epilogue adds the pooled values of the pixels that are on (inside the box and logit > 0,
+ * i.e. sigmoid > 0.5) per detection.  Traffic per frame: the prototypes once (4*P*H*W) instead of 4*n*H*W of masks.
+ *   depth_mm [Hi,Wi] u16 (ROS mono16, 0 = no reading) ->
+ *   mean [n] f64 metres (NaN when no selected pixel has a reading), count [n] i64 readings averaged (may be NULL).
+ * Sums are integers: the result is deterministic; it differs from the reference only where a logit is within the
+ * bf16x2 contraction error (~2e-5) of zero.  workspace: tauv_yolact_mask_depth_workspace_bytes(1, H, W, n). */
+size_t tauv_yolact_mask_depth_workspace_bytes(int B, int H, int W, int top_k);
+int tauv_yolact_mask_depth(const float* proto, const float* coeff, const float* box, int n, int P,
+                           int H, int W, const uint16_t* depth_mm, int Hi, int Wi, double* mean,
+                           int64_t* count, void* workspace, size_t workspace_bytes,
+                           tauv_stream_t stream);
+
+/* The same for every frame of a batch, straight from the detect() outputs (one depth image per frame).
+ *   proto [B,P,H,W], coeff_all [B,N,P], keep [B,top_k], n_keep [B], keep_box [B,top_k,4] (NULL = no crop),
+ *   depth_mm [B,Hi,Wi] u16 -> mean [B,top_k] f64 (NaN for rows >= n_keep[b]), count [B,top_k] i64 (may be NULL). */
+int tauv_yolact_mask_depth_batched(const float* proto, const float* coeff_all, const int64_t* keep,
+                                   const int32_t* n_keep, const float* keep_box, int B, int N,
+                                   int P, int H, int W, int top_k, const uint16_t* depth_mm, int Hi,
+                                   int Wi, double* mean, int64_t* count, void* workspace,
+                                   size_t workspace_bytes, tauv_stream_t stream);
+
 /* box_to_mask(box, img_size) — yolact/model/boxes.py:88-103.  box [4] f32 -> out [H,W] {0,1}. */
 int tauv_box_to_mask(const float* box, int H, int W, float* out, tauv_stream_t stream);
 

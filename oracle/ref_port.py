@@ -340,6 +340,34 @@ def assemble_mask(mask_prototype, mask_coeff, box):
     return m
 
 
+def upsample_nearest_index(out_size: int, in_size: int) -> torch.Tensor:
+    """Source index of every output index for ``F.interpolate(x, size)`` in its default 'nearest' mode (the call at
+    yolact_node.py:131): min(floor(i * fp32(in/out)), in - 1), the product in fp32 (ATen UpSample.h,
+    nearest_neighbor_compute_source_index; checked against F.interpolate itself in tests/test_oracle_vs_golden.py)."""
+    scale = torch.tensor(in_size, dtype=torch.float32) / torch.tensor(out_size, dtype=torch.float32)
+    i = torch.arange(out_size, dtype=torch.float32)
+    return torch.clamp(torch.floor(i * scale).to(torch.int64), max=in_size - 1)
+
+
+def masked_depth_mean(mask_prototype, mask_coeff, box, depth_mm):
+    """yolact_node.py:102-103 (depth image: 0 -> NaN, millimetres -> metres in float64), :130-131 (assemble_mask, then
+    nearest-neighbour resize to the camera resolution), :178 (nanmean of the depth where the mask is > 0.5).
+    depth_mm: [Hi,Wi] integer tensor (mono16).  Returns (mean [n] float64 with NaN where nothing was averaged,
+    count [n] int64 = readings averaged)."""
+    hi, wi = depth_mm.shape
+    d = depth_mm.to(torch.float64)
+    d = torch.where(depth_mm == 0, torch.full_like(d, float("nan")), d) / 1000
+    mask = assemble_mask(mask_prototype, mask_coeff, box)
+    iy = upsample_nearest_index(hi, mask.shape[1])
+    ix = upsample_nearest_index(wi, mask.shape[2])
+    up = mask[:, iy][:, :, ix]
+    sel = (up > 0.5) & ~torch.isnan(d).unsqueeze(0)
+    count = sel.sum(dim=(1, 2))
+    total = torch.where(sel, d.unsqueeze(0).expand_as(up), torch.zeros((), dtype=torch.float64)).sum(dim=(1, 2))
+    mean = torch.where(count > 0, total / count.clamp(min=1), torch.full_like(total, float("nan")))
+    return mean, count
+
+
 def match_anchors(anchor, truth_box, truth_valid, pos_thr: float, neg_thr: float, variances):
     """yolact/model/loss.py:16-22 (+ :62-66 box_encode of the matched truth, here dense over all
     priors).  Returns (match_index [B,N], match_iou [B,N], positive, negative, target [B,N,4])."""

@@ -28,6 +28,10 @@ struct MaskArgs {
   float* out;                // [B,top_k,HW]
   float* logits;             // optional, same shape
   long long* trace;          // debug (tools/mask_trace.py): per-unit role timestamps of CTA 0, or NULL
+  // fused consumer (tauv_yolact_mask_depth*): when acc != NULL no mask is written; instead, per detection, the pooled
+  // camera depth of the pixels that are "on" (inside the box, sigmoid > 0.5) is added up
+  const uint2* pool;         // [B,HW] (sum of mm readings, number of valid readings) per prototype pixel
+  unsigned long long* acc;   // [B,top_k,2] (sum, count), zeroed by the caller
 };
 
 constexpr int kSimtThreads = 256;
@@ -62,7 +66,23 @@ __global__ void __launch_bounds__(kSimtThreads) mask_simt_kernel(MaskArgs a) {
       }
     }
     __syncthreads();
-    if (pix < HW) {
+    if (a.acc) {
+      // fused consumer: every lane takes part in the warp reductions (pixels beyond HW carry an empty pool entry)
+      const uint2 pw = pix < HW ? a.pool[(size_t)b * HW + pix] : make_uint2(0u, 0u);
+      for (int d = 0; d < nd; ++d) {
+        float acc = 0.f;
+        for (int p = 0; p < P; ++p) acc = __fadd_rn(acc, __fmul_rn(s_coeff[d * P + p], s_proto[p * kSimtThreads + tid]));
+        bool on = sigmoid_ref(acc) > 0.5f;  // the reference's own test on its own fp32 sigmoid (yolact_node.py:178)
+        if (a.box) on = on && px >= s_box[4 * d] && px <= s_box[4 * d + 1] && py >= s_box[4 * d + 2] && py <= s_box[4 * d + 3];
+        const unsigned s = __reduce_add_sync(0xffffffffu, on ? pw.x : 0u);
+        const unsigned c = __reduce_add_sync(0xffffffffu, on ? pw.y : 0u);
+        if ((tid & 31) == 0 && (s | c)) {
+          unsigned long long* dst = a.acc + ((size_t)b * a.top_k + d0 + d) * 2;
+          atomicAdd(dst, (unsigned long long)s);
+          atomicAdd(dst + 1, (unsigned long long)c);
+        }
+      }
+    } else if (pix < HW) {
       for (int d = 0; d < nd; ++d) {
         float acc = 0.f;
         for (int p = 0; p < P; ++p) acc = __fadd_rn(acc, __fmul_rn(s_coeff[d * P + p], s_proto[p * kSimtThreads + tid]));
@@ -85,6 +105,12 @@ __global__ void __launch_bounds__(kSimtThreads) mask_simt_kernel(MaskArgs a) {
 
 namespace tauv {
 
+// Test hook: TAUV_MASK_SIMT=1 in the environment forces the CUDA-core kernel (read per call; no global state).
+static int want_simt_env() {
+  const char* e = getenv("TAUV_MASK_SIMT");
+  return e && e[0] == '1';
+}
+
 static long long* g_mask_trace = nullptr;  // experiment hook (tools/mask_trace.py); not part of the public ABI
 
 static int run_mask(const MaskArgs& a_in, int B, int max_rows, int force_simt, cudaStream_t st) {
@@ -105,11 +131,7 @@ static int run_mask(const MaskArgs& a_in, int B, int max_rows, int force_simt, c
 
 using namespace tauv;
 
-// Test hook: TAUV_MASK_SIMT=1 in the environment forces the CUDA-core kernel (read per call; no global state).
-static int want_simt() {
-  const char* e = getenv("TAUV_MASK_SIMT");
-  return e && e[0] == '1';
-}
+static int want_simt() { return tauv::want_simt_env(); }
 
 extern "C" int tauv_yolact_assemble_mask(const float* proto, const float* coeff, const float* box, int n, int P, int H,
                                          int W, float* out, float* logits_out, tauv_stream_t stream) {
@@ -135,6 +157,121 @@ extern "C" int tauv_yolact_assemble_mask_batched(const float* proto, const float
   a.proto = proto; a.coeff = coeff_all; a.keep = keep; a.n_keep = n_keep; a.box = (const float4*)keep_box;
   a.n_host = 0; a.N = N; a.P = P; a.H = H; a.W = W; a.top_k = top_k; a.out = out; a.logits = nullptr;
   return run_mask(a, B, top_k, want_simt(), (cudaStream_t)stream);
+}
+
+// ---- fused consumer: masked depth mean ---------------------------------------------------------
+namespace tauv {
+
+// F.interpolate(..., size) in its default 'nearest' mode maps output index i to input index
+// min(floor(i * (float)in / out), in - 1), computed in fp32 (ATen UpSample.h: nearest_neighbor_compute_source_index).
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
+  return min((int)floorf((float)dst * scale), in_size - 1);
+}
+// first output index whose source index is >= r (the map is monotone): r / scale rounded up, then corrected by the
+// map itself, so the result is exact whatever the rounding of the guess
+__device__ __forceinline__ int nearest_first_dst(int r, float scale, int in_size, int out_size) {
+  int g = min(max((int)ceilf((float)r / scale), 0), out_size);
+  while (g > 0 && nearest_src(g - 1, scale, in_size) >= r) --g;
+  while (g < out_size && nearest_src(g, scale, in_size) < r) ++g;
+  return g;
+}
+
+// One thread per prototype pixel: the camera pixels whose nearest prototype pixel it is form a rectangle.
+__global__ void __launch_bounds__(256) depth_pool_kernel(const uint16_t* __restrict__ depth, int Hi, int Wi, int H, int W,
+                                                         uint2* __restrict__ pool) {
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  if (pix >= H * W) return;
+  const int r = pix / W, c = pix - r * W;
+  const float sy = (float)H / (float)Hi, sx = (float)W / (float)Wi;
+  const int y0 = nearest_first_dst(r, sy, H, Hi), y1 = r + 1 < H ? nearest_first_dst(r + 1, sy, H, Hi) : Hi;
+  const int x0 = nearest_first_dst(c, sx, W, Wi), x1 = c + 1 < W ? nearest_first_dst(c + 1, sx, W, Wi) : Wi;
+  const uint16_t* d = depth + (size_t)b * Hi * Wi;
+  unsigned sum = 0, cnt = 0;
+  for (int y = y0; y < y1; ++y)
+    for (int x = x0; x < x1; ++x) {
+      const unsigned v = d[(size_t)y * Wi + x];
+      sum += v;             // (a zero reading is "no reading": yolact_node.py:102; it adds nothing to the sum either)
+      cnt += v != 0u;
+    }
+  pool[(size_t)b * H * W + pix] = make_uint2(sum, cnt);
+}
+
+// mean = nanmean over the selected camera pixels of depth_mm / 1000 (yolact_node.py:103,178); NaN when none / row unused
+__global__ void depth_mean_kernel(const unsigned long long* __restrict__ acc, const int32_t* __restrict__ n_keep, int n_host,
+                                  int top_k, int total, double* __restrict__ mean, int64_t* __restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = i / top_k, d = i - b * top_k;
+  const int n = n_keep ? n_keep[b] : n_host;
+  const unsigned long long s = acc[2 * (size_t)i], c = acc[2 * (size_t)i + 1];
+  const bool used = d < n && c > 0;
+  mean[i] = used ? ((double)s / 1000.0) / (double)c : __longlong_as_double(0x7ff8000000000000LL);
+  if (count) count[i] = d < n ? (int64_t)c : 0;
+}
+
+static int run_mask_depth(MaskArgs a, int B, int max_rows, const uint16_t* depth, int Hi, int Wi, void* workspace,
+                          size_t workspace_bytes, double* mean, int64_t* count, cudaStream_t st) {
+  const size_t HW = (size_t)a.H * a.W;
+  const size_t pool_bytes = (B * HW * sizeof(uint2) + 255) & ~(size_t)255, acc_bytes = (size_t)B * a.top_k * 16;
+  TAUV_REQUIRE(workspace && workspace_bytes >= pool_bytes + acc_bytes, TAUV_E_WORKSPACE, "workspace too small: %zu < %zu",
+               workspace_bytes, pool_bytes + acc_bytes);
+  TAUV_REQUIRE((uintptr_t)workspace % 256 == 0, TAUV_E_ALIGN, "workspace must be 256-byte aligned");
+  // a warp adds up 32 pool entries in 32 bits: 32 x (camera pixels per prototype pixel) x 65535 must fit
+  const long long pre = (long long)((Hi + a.H - 1) / a.H + 1) * ((Wi + a.W - 1) / a.W + 1);
+  TAUV_REQUIRE(pre * 65535LL * 32LL < (1LL << 32), TAUV_E_UNSUPPORTED, "camera image %dx%d too large for a %dx%d prototype map",
+               Hi, Wi, a.H, a.W);
+  uint2* pool = reinterpret_cast<uint2*>(workspace);
+  unsigned long long* acc = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(workspace) + pool_bytes);
+  TAUV_CUDA(cudaMemsetAsync(acc, 0, acc_bytes, st));
+  depth_pool_kernel<<<dim3((unsigned)((HW + 255) / 256), B), 256, 0, st>>>(depth, Hi, Wi, a.H, a.W, pool);
+  TAUV_LAUNCH_CHECK("depth_pool_kernel");
+  a.pool = pool;
+  a.acc = acc;
+  a.out = nullptr;
+  a.logits = nullptr;
+  const int rc = run_mask(a, B, max_rows, want_simt_env(), st);
+  if (rc) return rc;
+  const int total = B * a.top_k;
+  depth_mean_kernel<<<(total + 255) / 256, 256, 0, st>>>(acc, a.n_keep, a.n_host, a.top_k, total, mean, count);
+  TAUV_LAUNCH_CHECK("depth_mean_kernel");
+  return 0;
+}
+
+}  // namespace tauv
+
+extern "C" size_t tauv_yolact_mask_depth_workspace_bytes(int B, int H, int W, int top_k) {
+  if (B <= 0 || H <= 0 || W <= 0 || top_k <= 0) return 0;
+  return (((size_t)B * H * W * sizeof(uint2) + 255) & ~(size_t)255) + (size_t)B * top_k * 16;
+}
+
+extern "C" int tauv_yolact_mask_depth(const float* proto, const float* coeff, const float* box, int n, int P, int H, int W,
+                                      const uint16_t* depth_mm, int Hi, int Wi, double* mean, int64_t* count,
+                                      void* workspace, size_t workspace_bytes, tauv_stream_t stream) {
+  TAUV_REQUIRE(n >= 0, TAUV_E_SHAPE, "n must be >= 0");
+  if (n == 0) return 0;
+  TAUV_REQUIRE(proto && coeff && depth_mm && mean, TAUV_E_NULL, "proto/coeff/depth_mm/mean must not be NULL");
+  TAUV_REQUIRE(P > 0 && H > 0 && W > 0 && Hi > 0 && Wi > 0, TAUV_E_SHAPE, "bad shape P=%d H=%d W=%d Hi=%d Wi=%d", P, H, W, Hi, Wi);
+  TAUV_REQUIRE((uintptr_t)box % 16 == 0, TAUV_E_ALIGN, "box must be 16-byte aligned");
+  MaskArgs a{};
+  a.proto = proto; a.coeff = coeff; a.keep = nullptr; a.n_keep = nullptr; a.box = (const float4*)box;
+  a.n_host = n; a.N = 0; a.P = P; a.H = H; a.W = W; a.top_k = n;
+  return run_mask_depth(a, 1, n, depth_mm, Hi, Wi, workspace, workspace_bytes, mean, count, (cudaStream_t)stream);
+}
+
+extern "C" int tauv_yolact_mask_depth_batched(const float* proto, const float* coeff_all, const int64_t* keep,
+                                              const int32_t* n_keep, const float* keep_box, int B, int N, int P, int H,
+                                              int W, int top_k, const uint16_t* depth_mm, int Hi, int Wi, double* mean,
+                                              int64_t* count, void* workspace, size_t workspace_bytes,
+                                              tauv_stream_t stream) {
+  TAUV_REQUIRE(proto && coeff_all && keep && n_keep && depth_mm && mean, TAUV_E_NULL, "pointers must not be NULL");
+  TAUV_REQUIRE(B > 0 && N > 0 && P > 0 && H > 0 && W > 0 && top_k > 0 && Hi > 0 && Wi > 0, TAUV_E_SHAPE, "bad shape");
+  TAUV_REQUIRE(B <= 65535, TAUV_E_UNSUPPORTED, "B=%d exceeds the built-in limit 65535", B);
+  TAUV_REQUIRE((uintptr_t)keep_box % 16 == 0, TAUV_E_ALIGN, "keep_box must be 16-byte aligned");
+  MaskArgs a{};
+  a.proto = proto; a.coeff = coeff_all; a.keep = keep; a.n_keep = n_keep; a.box = (const float4*)keep_box;
+  a.n_host = 0; a.N = N; a.P = P; a.H = H; a.W = W; a.top_k = top_k;
+  return run_mask_depth(a, B, top_k, depth_mm, Hi, Wi, workspace, workspace_bytes, mean, count, (cudaStream_t)stream);
 }
 
 // Debug hook for tools/mask_trace.py (process-global, not thread-safe, not in the public header).

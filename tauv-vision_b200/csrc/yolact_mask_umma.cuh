@@ -41,6 +41,14 @@ constexpr int kUmmaNMax = 256;        // detections per launch (TMEM columns per
 // 64 frames, epilogue-bound at 5 us per tile; 12 + 4 warps: 1279 us, now producer-bound (latency of the prototype loads);
 // 12 + 4 warps with 3 A stages and 2 staging buffers per group: 1008 us; 16 epilogue warps spill: 2756 us)
 constexpr int kUmmaEpiWarps = TAUV_MASK_EPI_WARPS, kUmmaProdWarps = TAUV_MASK_PROD_WARPS;
+#ifndef TAUV_EPI_BACKOFF
+#define TAUV_EPI_BACKOFF 0
+#endif
+#if TAUV_EPI_BACKOFF > 0
+#define TAUV_EPI_WAIT(bar, par) mbar_wait_relaxed(bar, par, TAUV_EPI_BACKOFF)
+#else
+#define TAUV_EPI_WAIT(bar, par) mbar_wait(bar, par)
+#endif
 #ifndef TAUV_MASK_PREFETCH
 #define TAUV_MASK_PREFETCH 1  // tiles ahead (measured: 0 -> 996 us, 1 -> 965, 2 -> 1035, 4 -> 1157 per 64 frames)
 #endif
@@ -53,6 +61,7 @@ constexpr int kUmmaEpiWarps = TAUV_MASK_EPI_WARPS, kUmmaProdWarps = TAUV_MASK_PR
 constexpr int kUmmaGroups = kUmmaEpiWarps / 4;  // an epilogue group = four warps, one per TMEM lane quadrant
 constexpr int kUmmaAStages = TAUV_MASK_A_STAGES;      // prototype tiles in flight (the producers are latency-bound)
 constexpr int kUmmaStageBufs = TAUV_MASK_STAGE_BUFS;  // output staging buffers per epilogue group
+constexpr int kUmmaDepthChunks = (kUmmaNMax / 32 + kUmmaGroups - 1) / kUmmaGroups;  // 32-detection chunks per group
 constexpr int kUmmaThreads = (kUmmaEpiWarps + kUmmaProdWarps + 1) * 32;
 
 struct UmmaSmem {
@@ -109,6 +118,17 @@ __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// One column: thread t of the warp gets column c of TMEM lane (lane_base + t).  Asynchronous: the register is valid
+// after tc_wait_ld, which names it as an operand so that the compiler cannot move a use above the wait.
+__device__ __forceinline__ float tc_ld_col(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tc_wait_ld(float& v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v)::"memory");
+}
+
 // Shared-memory matrix descriptor for a K-major, SWIZZLE_64B operand whose rows are 64 bytes (32 bf16):
 // 8-row groups are 512 B apart (stride byte offset), start address in 16-byte units, descriptor version 1 (sm_100).
 __device__ __forceinline__ uint64_t umma_desc_k_sw64(const void* smem, uint32_t byte_offset) {
@@ -157,6 +177,7 @@ __device__ __forceinline__ int frame_rows(const MaskArgs& a, int b, int m_base) 
   return n <= 0 ? 0 : (n < kUmmaNMax ? n : kUmmaNMax);
 }
 
+template <bool kDepth>
 __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid_constant__ MaskArgs a, int B,
                                                                     int m_base,
                                                                     const __grid_constant__ CUtensorMap out_map,
@@ -171,6 +192,13 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
   const int n_tiles = (HW + kUmmaM - 1) / kUmmaM;
   const long long units = (long long)B * n_tiles;  // unit = (frame, tile of 128 pixels); contiguous share per CTA
   const long long u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
+  // Per-tile index arithmetic without divisions: every role is a single dependent instruction stream per warp, and the
+  // 64-bit u / n_tiles plus the pixel -> (row, column) divisions cost ~1.3 us per tile (measured: the epilogue's
+  // "work" with its whole inner loop removed).  (frame, tile) advance incrementally; pix / W is a multiply-high.
+  const int b_first = (int)(u0 / n_tiles), nt_first = (int)(u0 - (long long)b_first * n_tiles);
+  const unsigned w_magic = (unsigned)((0x100000000ULL + (unsigned)a.W - 1) / (unsigned)a.W);   // ceil(2^32 / W)
+  const bool w_magic_ok = a.W > 1 && (unsigned long long)(HW + kUmmaM) * (unsigned)a.W < 0x100000000ULL;    // exact for pix < 2^32 / W
+  auto div_w = [&](int pix) { return w_magic_ok ? (int)__umulhi((unsigned)pix, w_magic) : pix / a.W; };
 
   if (tid == 0) {
     for (int s = 0; s < kUmmaAStages; ++s) {
@@ -204,26 +232,140 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
     const bool bulk_zero = (HW % 4 == 0) && ((uintptr_t)a.out % 16 == 0);
     uint32_t uses[2] = {0, 0};
     uint32_t nbuf = 0;  // staged chunks so far (selects the staging buffer)
+    unsigned long long dsum[kUmmaDepthChunks] = {}, dcnt[kUmmaDepthChunks] = {};  // (depth mode) lane j: detection c*32+j
+    uint2 pw_next = make_uint2(0u, 0u);  // (depth mode) the next tile's pooled depth of this thread's pixel
+    long long pw_u = -1;
     int as = 0, rows_frame = -1, n_rows = 0;
+    int b = b_first, nt = nt_first - 1;
     for (long long u = u0; u < u1; ++u) {
-      const int b = (int)(u / n_tiles), nt = (int)(u - (long long)b * n_tiles);
+      if (++nt == n_tiles) {
+        nt = 0;
+        ++b;
+      }
+      const bool frame_ends = u + 1 == u1 || nt + 1 == n_tiles;  // the last tile of this CTA's run of frame b
       if (b != rows_frame) {  // one global read per frame, not per tile
         n_rows = frame_rows(a, b, m_base);
         rows_frame = b;
       }
       if (n_rows == 0) continue;
       const int pix = nt * kUmmaM + quad * 32 + lane;
-      const int yy = pix / a.W;
+      const int yy = div_w(pix);
       const float py = (float)yy, px = (float)(pix - yy * a.W);
       float* out_tile = a.out + ((size_t)b * a.top_k + m_base) * HW + nt * kUmmaM;
       float* out_pix = out_tile + quad * 32 + lane;
       float* lg_pix = a.logits ? a.logits + ((size_t)b * a.top_k + m_base) * HW + pix : nullptr;
       // image rows the tile's pixels lie in: a mask whose box misses them is all zero on this tile
       const int tile_px = min(kUmmaM, HW - nt * kUmmaM);
-      const float ty0 = (float)((nt * kUmmaM) / a.W), ty1 = (float)((nt * kUmmaM + tile_px - 1) / a.W);
-      mbar_wait(&sm->acc_full[as], uses[as] & 1u);
+      const float ty0 = (float)div_w(nt * kUmmaM), ty1 = (float)div_w(nt * kUmmaM + tile_px - 1);
+      // (depth mode) this pixel's pooled camera depth: sum of the millimetre readings and number of valid readings
+      // among the camera pixels whose nearest prototype pixel it is
+      // (loaded one tile ahead: a load issued here would be waited for in full on every tile — 1.5 us of the 2.4 us
+      // tile period when the epilogue is the bottleneck and its accumulator is already waiting)
+      uint2 pw = make_uint2(0u, 0u);
+      if constexpr (kDepth) {
+        if (pw_u == u) pw = pw_next;
+        else if (pix < HW) pw = __ldg(a.pool + (size_t)b * HW + pix);
+        if (u + 1 < u1) {
+          const int b2 = nt + 1 == n_tiles ? b + 1 : b;
+          const int pix2 = (nt + 1 == n_tiles ? 0 : nt + 1) * kUmmaM + quad * 32 + lane;
+          pw_next = pix2 < HW ? __ldg(a.pool + (size_t)b2 * HW + pix2) : make_uint2(0u, 0u);
+          pw_u = u + 1;
+        }
+      }
+      TAUV_EPI_WAIT(&sm->acc_full[as], uses[as] & 1u);
       tc_fence_after();
       if (tid == 0) mask_stamp(a, u - u0, 5);
+      if constexpr (kDepth) {
+        // ---- fused consumer (yolact_node.py:131,178-183): no mask is written.  A detection's pixel is "on" when it
+        // lies inside the crop box and sigmoid(logit) > 0.5, i.e. logit > 0; the warp adds up the pooled depth of its
+        // 32 pixels with two integer warp reductions per detection, lane j keeps the running totals of detection
+        // c*32 + j, and they go to global memory once per frame.  Boxes that miss the tile's image rows are skipped.
+        // the image rows / columns this warp's 32 pixels lie in: a box that misses them selects nothing here (with the
+        // probe's boxes nine (warp, detection) pairs in ten are skipped; the kernel is bound by instruction issue)
+        const int wp0 = nt * kUmmaM + quad * 32, wp1 = min(wp0 + 31, HW - 1);
+        const int wr0 = div_w(wp0), wr1 = div_w(wp1);
+        const float wy0 = (float)wr0, wy1 = (float)wr1;
+        const float wx0 = wr0 == wr1 ? (float)(wp0 - wr0 * a.W) : 0.0f, wx1 = wr0 == wr1 ? (float)(wp1 - wr1 * a.W) : (float)a.W;
+#pragma unroll
+        for (int ci = 0; ci < kUmmaDepthChunks; ++ci) {
+          const int c = half + ci * kUmmaGroups;
+          if (c * 32 < n_rows && wp0 < HW) {  // warp-uniform
+            bool live = false;
+            const int det = c * 32 + lane;
+            if (det < n_rows) {
+              const float4 bd = *reinterpret_cast<const float4*>(sm->bounds[det]);
+              live = !(wy1 < bd.z || wy0 > bd.w || wx1 < bd.x || wx0 > bd.y);
+            }
+            const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+            if (live_mask != 0u) {
+              // Only the live detections are touched, one TMEM column each (a dynamic column address needs no register
+              // indexing; the next live column is in flight while this one is reduced).  Measured on the way here:
+              // testing all 32 detections of the chunk, with a branch or straight-line, costs 2 us per tile — a warp on
+              // its own issues a dependent instruction every ~5 cycles, so only the instruction COUNT matters.
+              const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kUmmaNMax + c * 32);
+              const float4* bp = reinterpret_cast<const float4*>(sm->bounds[c * 32]);
+              unsigned ts = 0u, tn = 0u;  // this lane's detection, this tile (fits 32 bits: checked by the host)
+              unsigned m = live_mask;
+              int j = __ffs(m) - 1;
+              m &= m - 1u;
+              float v_cur = tc_ld_col(tbase + (uint32_t)j), v_next = 0.0f;
+              tc_wait_ld(v_cur);
+              while (true) {
+                const bool more = m != 0u;
+                int jn = 0;
+                if (more) {
+                  jn = __ffs(m) - 1;
+                  m &= m - 1u;
+                  v_next = tc_ld_col(tbase + (uint32_t)jn);
+                }
+                const float4 bd = bp[j];  // a broadcast
+                const int neg = __float_as_int(px - bd.x) | __float_as_int(bd.y - px) | __float_as_int(py - bd.z) |
+                                __float_as_int(bd.w - py);
+                const bool on = neg >= 0 && v_cur > 0.0f;
+                const unsigned sx = __reduce_add_sync(0xffffffffu, on ? pw.x : 0u);
+                const unsigned sn = __reduce_add_sync(0xffffffffu, on ? pw.y : 0u);
+                if (lane == j) {
+                  ts = sx;
+                  tn = sn;
+                }
+                if (!more) break;
+                tc_wait_ld(v_next);
+                v_cur = v_next;
+                j = jn;
+              }
+              dsum[ci] += ts;
+              dcnt[ci] += tn;
+            }
+          }
+        }
+        if (tid == 0) mask_stamp(a, u - u0, 6);
+        if (a.trace && blockIdx.x == 0 && lane == 0 && u - u0 < 512) {  // the slowest epilogue warp of the tile: (time << 5) | warp
+          long long t;
+          asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+          atomicMax(reinterpret_cast<unsigned long long*>(a.trace + (u - u0) * 8 + 7), ((unsigned long long)t << 5) | (unsigned)warp);
+        }
+        tc_fence_before();
+        mbar_arrive(&sm->acc_empty[as]);
+        ++uses[as];
+        as ^= 1;
+        if (frame_ends) {
+          // end of this CTA's run of tiles of frame b: publish (integer sums: exact and order-independent)
+#pragma unroll
+          for (int ci = 0; ci < kUmmaDepthChunks; ++ci) {
+            const int det = (half + ci * kUmmaGroups) * 32 + lane;
+            if (det < n_rows && (dsum[ci] | dcnt[ci])) {
+              unsigned long long* dst = a.acc + ((size_t)b * a.top_k + m_base + det) * 2;
+              atomicAdd(dst, dsum[ci]);
+              atomicAdd(dst + 1, dcnt[ci]);
+            }
+            dsum[ci] = 0ull;
+            dcnt[ci] = 0ull;
+          }
+          mbar_arrive(&sm->frame_done);
+        }
+        continue;
+      }
+      if constexpr (!kDepth) {
 #pragma unroll 1
       for (int c = half; c * 32 < n_rows; c += kUmmaGroups) {
         // lane j looks at detection c*32+j: does its box reach the tile at all?  If not, one bulk store of zeros
@@ -330,7 +472,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
       ++uses[as];
       as ^= 1;
       // end of this CTA's run of units of frame b: the producers may overwrite B / the crop bounds
-      if (u + 1 == u1 || (int)((u + 1) / n_tiles) != b) mbar_arrive(&sm->frame_done);
+      if (frame_ends) mbar_arrive(&sm->frame_done);
+      }  // (!kDepth)
     }
     bulk_commit();
     bulk_wait<0>();  // the zero-fill stores this thread issued have completed
@@ -339,8 +482,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
     const int pt = tid - kUmmaEpiWarps * 32;  // producer thread index: the pixel rows of the A tile this thread converts
     uint32_t fills[kUmmaAStages] = {}, frames = 0;
     int st = 0, cur_frame = -1, rows_frame = -1, n_rows = 0;
+    int b = b_first, nt = nt_first - 1;
     for (long long u = u0; u < u1; ++u) {
-      const int b = (int)(u / n_tiles), nt = (int)(u - (long long)b * n_tiles);
+      if (++nt == n_tiles) {
+        nt = 0;
+        ++b;
+      }
       if (b != rows_frame) {
         n_rows = frame_rows(a, b, m_base);
         rows_frame = b;
@@ -385,8 +532,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
         // the write stream).  Holding the next tile in registers spills (the kernel is capped at 96 registers by its
         // 17 warps) and a spill waits for the load; an L2 prefetch of a later tile costs two instructions per thread:
         // 32 planes x 512 bytes = 128 lines, one (+ the straddled one: plane bases are not 128-byte aligned) each.
-        const long long u2 = u + TAUV_MASK_PREFETCH;
-        const int b2 = (int)(u2 / n_tiles), nt2 = (int)(u2 - (long long)b2 * n_tiles);
+        int b2 = b, nt2 = nt + TAUV_MASK_PREFETCH;
+        while (nt2 >= n_tiles) {
+          nt2 -= n_tiles;
+          ++b2;
+        }
         for (int i = pt; i < kUmmaP * 4; i += kUmmaProdWarps * 32) {
           const int p = i >> 2, q = i & 3;
           const int pix = nt2 * kUmmaM + q * 32;
@@ -430,8 +580,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
     // ======================================= MMA issuer =======================================
     uint32_t fills[kUmmaAStages] = {}, uses[2] = {0, 0};
     int st = 0, as = 0, rows_frame = -1, n_rows = 0;
+    int b = b_first, nt = nt_first - 1;
     for (long long u = u0; u < u1; ++u) {
-      const int b = (int)(u / n_tiles);
+      if (++nt == n_tiles) {
+        nt = 0;
+        ++b;
+      }
       if (b != rows_frame) {
         n_rows = frame_rows(a, b, m_base);
         rows_frame = b;
@@ -505,16 +659,19 @@ static bool make_out_map(const MaskArgs& a, int B, CUtensorMap* map) {
 
 static int launch_mask_umma(const MaskArgs& a, int B, int max_rows, cudaStream_t st) {
   const size_t smem = sizeof(UmmaSmem) + 1024;
-  TAUV_CUDA(cudaFuncSetAttribute(mask_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool depth = a.acc != nullptr;
+  TAUV_CUDA(cudaFuncSetAttribute(depth ? mask_umma_kernel<true> : mask_umma_kernel<false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int HW = a.H * a.W;
   const long long units = (long long)B * ((HW + kUmmaM - 1) / kUmmaM);
   long long grid = num_sms();
   if (grid > units) grid = units;
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
-  const int use_tma = !getenv("TAUV_MASK_NO_TMA") && make_out_map(a, B, &map) ? 1 : 0;
+  const int use_tma = !depth && !getenv("TAUV_MASK_NO_TMA") && make_out_map(a, B, &map) ? 1 : 0;
   for (int m_base = 0; m_base < max_rows; m_base += kUmmaNMax) {
-    mask_umma_kernel<<<(unsigned)grid, kUmmaThreads, smem, st>>>(a, B, m_base, map, use_tma);
+    if (depth) mask_umma_kernel<true><<<(unsigned)grid, kUmmaThreads, smem, st>>>(a, B, m_base, map, 0);
+    else mask_umma_kernel<false><<<(unsigned)grid, kUmmaThreads, smem, st>>>(a, B, m_base, map, use_tma);
     TAUV_LAUNCH_CHECK("mask_umma_kernel");
   }
   return 0;

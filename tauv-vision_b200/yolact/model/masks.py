@@ -54,3 +54,72 @@ def assemble_mask_batched(mask_prototype: torch.Tensor, mask_coeff: torch.Tensor
             _lib.fptr(proto), _lib.fptr(coeff), _lib.i64ptr(detections.keep), _lib.i32ptr(detections.n_keep),
             _lib.fptr(detections.box) if crop else None, B, N, P, H, W, top_k, _lib.fptr(out), _lib.stream_ptr(dev)))
     return out
+
+
+def _depth_u16(depth_mm: torch.Tensor, dev, dims: int) -> torch.Tensor:
+    """The ROS mono16 depth image as 16-bit words on the device (uint16, or int16 holding the same bits)."""
+    if depth_mm.dtype not in (torch.uint16, torch.int16):
+        raise TypeError(f"depth_mm must be uint16 (mono16 millimetres; int16 with the same bits is accepted); got {depth_mm.dtype}")
+    if depth_mm.dim() != dims:
+        raise ValueError(f"depth_mm must have {dims} dimensions; got {tuple(depth_mm.shape)}")
+    if depth_mm.device != dev:
+        raise RuntimeError(f"depth_mm is on {depth_mm.device}, the prototypes on {dev} (there is no CPU path)")
+    return depth_mm.contiguous()
+
+
+def masked_depth_mean(mask_prototype: torch.Tensor, mask_coeff: torch.Tensor, box: Optional[torch.Tensor],
+                      depth_mm: torch.Tensor, return_count: bool = False):
+    """Mean camera depth under each detection's mask, fused with the mask assembly — what the ROS node computes with
+    ``assemble_mask`` -> ``F.interpolate(mask[None], depth.shape)`` -> ``np.nanmean(np.where(mask > 0.5, depth, nan))``
+    (/root/reference/src/tauv_vision/yolact/node/yolact_node.py:102-103,130-131,178), without writing a mask.
+    mask_prototype [P,H,W], mask_coeff [n,P], box [n,4] or None, depth_mm [Hi,Wi] uint16 millimetres (0 = no reading)
+    -> mean [n] float64 metres (NaN where the node would ``continue``), optionally the number of readings averaged."""
+    dev = _lib.require_cuda(mask_prototype, mask_coeff, box)
+    proto, coeff = _lib.f32c(mask_prototype), _lib.f32c(mask_coeff)
+    if proto.dim() != 3 or coeff.dim() != 2 or coeff.shape[1] != proto.shape[0]:
+        raise ValueError(f"mask_prototype {tuple(proto.shape)} / mask_coeff {tuple(coeff.shape)} must be [P,H,W] / [n,P]")
+    P, H, W = proto.shape
+    n = coeff.shape[0]
+    bx = _lib.f32c(box) if box is not None else None
+    if bx is not None and tuple(bx.shape) != (n, 4):
+        raise ValueError(f"box must be [{n},4]; got {tuple(bx.shape)}")
+    depth = _depth_u16(depth_mm, dev, 2)
+    Hi, Wi = depth.shape
+    mean = torch.full((n,), float("nan"), dtype=torch.float64, device=dev)
+    count = torch.zeros((n,), dtype=torch.int64, device=dev)
+    if n:
+        lib = _lib.load()
+        ws = torch.empty(lib.tauv_yolact_mask_depth_workspace_bytes(1, H, W, n), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.tauv_yolact_mask_depth(_lib.fptr(proto), _lib.fptr(coeff), _lib.fptr(bx), n, P, H, W,
+                                                  depth.data_ptr(), Hi, Wi, _lib.dptr(mean), _lib.i64ptr(count),
+                                                  ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)))
+    return (mean, count) if return_count else mean
+
+
+def masked_depth_mean_batched(mask_prototype: torch.Tensor, mask_coeff: torch.Tensor, detections, depth_mm: torch.Tensor,
+                              crop: bool = True, workspace: Optional[torch.Tensor] = None):
+    """``masked_depth_mean`` for all frames at once from the fused detect() output.  mask_prototype [B,P,H,W],
+    mask_coeff [B,N,P], depth_mm [B,Hi,Wi] uint16 -> (mean [B,top_k] float64 with NaN for rows >= n_keep[b] or
+    without a reading, count [B,top_k] int64).  No synchronisation."""
+    dev = _lib.require_cuda(mask_prototype, mask_coeff, detections.keep)
+    proto, coeff = _lib.f32c(mask_prototype), _lib.f32c(mask_coeff)
+    B, P, H, W = proto.shape
+    N = coeff.shape[1]
+    top_k = detections.keep.shape[1]
+    depth = _depth_u16(depth_mm, dev, 3)
+    if depth.shape[0] != B:
+        raise ValueError(f"depth_mm must hold one image per frame: {tuple(depth.shape)} vs B={B}")
+    Hi, Wi = depth.shape[1:]
+    lib = _lib.load()
+    need = lib.tauv_yolact_mask_depth_workspace_bytes(B, H, W, top_k)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    mean = torch.empty((B, top_k), dtype=torch.float64, device=dev)
+    count = torch.empty((B, top_k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.tauv_yolact_mask_depth_batched(
+            _lib.fptr(proto), _lib.fptr(coeff), _lib.i64ptr(detections.keep), _lib.i32ptr(detections.n_keep),
+            _lib.fptr(detections.box) if crop else None, B, N, P, H, W, top_k, depth.data_ptr(), Hi, Wi,
+            _lib.dptr(mean), _lib.i64ptr(count), workspace.data_ptr(), workspace.numel(), _lib.stream_ptr(dev)))
+    return mean, count

@@ -242,6 +242,40 @@ def main():
     save("yl_mask", proto=proto, coeff=coeff, box=mbox, mask=ref_masks.assemble_mask(proto, coeff, mbox),
          mask_nobox=ref_masks.assemble_mask(proto, coeff, None), crop0=ref_boxes.box_to_mask(mbox[0], (20, 24)))
 
+    # ---- masked depth mean: the node's consumer of assemble_mask, with the reference's own calls --------------
+    # (yolact_node.py:102-103 depth image, :130-131 assemble_mask + F.interpolate, :178 nanmean)
+    import torch.nn.functional as F
+
+    def node_depth_mean(proto, coeff, box, depth_mm):
+        depth = depth_mm.numpy().astype(np.uint16)
+        depth = np.where(depth == 0, np.nan, depth)
+        depth = depth.astype(float) / 1000
+        mask = ref_masks.assemble_mask(proto, coeff, box)
+        mask = F.interpolate(mask.unsqueeze(0), (depth.shape[0], depth.shape[1])).squeeze(0)
+        means, counts = [], []
+        for i in range(mask.shape[0]):
+            mask_np = mask[i].detach().cpu().numpy()
+            sel = np.where(mask_np > 0.5, depth, np.nan)
+            counts.append(int(np.sum(~np.isnan(sel))))
+            with np.errstate(all="ignore"):
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    means.append(float(np.nanmean(sel)))
+        return np.array(means), np.array(counts)
+
+    arrays = {}
+    for tag, (P_, H_, W_, K_, exact) in {"a": (8, 20, 24, 5, False), "b": (32, 23, 31, 7, True)}.items():
+        proto, coeff, mbox = (synth.mask_inputs_exact if exact else synth.mask_inputs)(P_, H_, W_, K_, seed=95)
+        arrays.update({f"proto_{tag}": proto, f"coeff_{tag}": coeff, f"box_{tag}": mbox})
+        for j, (hi, wi) in enumerate([(45, 70), (2 * H_, 2 * W_), (H_, W_), (13, 17), (97, 64)]):
+            depth = synth.depth_image(hi, wi, seed=960 + j)
+            mean, count = node_depth_mean(proto, coeff, mbox, depth)
+            arrays.update({f"depth_{tag}{j}": depth.to(torch.int32), f"mean_{tag}{j}": mean, f"count_{tag}{j}": count})
+        mean, count = node_depth_mean(proto, coeff, None, synth.depth_image(45, 70, seed=960))
+        arrays.update({f"mean_{tag}_nobox": mean, f"count_{tag}_nobox": count})
+    save("yl_mask_depth", **arrays)
+
     # ---- anchor matching: yolact/model/loss.py:16-22 + :62-66, line by line with the reference's own ops ----
     tb, tv = synth.truth_boxes(3, 6, seed=101)
     g = synth.gen(102)

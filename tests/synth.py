@@ -168,6 +168,26 @@ def mask_inputs(P, H, W, K, seed):
     return proto, coeff, box
 
 
+def depth_image(hi, wi, seed, holes=0.2):
+    """A mono16 depth image (millimetres) with `holes` of the pixels carrying no reading (0), as int32 on the host
+    (torch has no CPU arithmetic on uint16); .to(torch.uint16) gives the device-side form."""
+    g = gen(seed)
+    d = torch.randint(300, 9000, (hi, wi), generator=g, dtype=torch.int32)
+    return torch.where(torch.rand((hi, wi), generator=g) < holes, torch.zeros((), dtype=torch.int32), d)
+
+
+def mask_inputs_exact(P, H, W, K, seed):
+    """Prototypes / coefficients that are small integers (exact in bf16, sums exact in fp32) with half-integer logits:
+    every implementation must select exactly the same pixels."""
+    g = gen(seed)
+    proto = torch.randint(-3, 4, (P, H, W), generator=g).float()
+    proto[0] = 1.0
+    coeff = torch.randint(-2, 3, (K, P), generator=g).float()
+    coeff[:, 0] = 0.5
+    box = torch.cat((torch.rand((K, 2), generator=g) * 0.8 + 0.1, torch.rand((K, 2), generator=g) * 0.7 + 0.1), dim=-1)
+    return proto, coeff, box
+
+
 def truth_boxes(B, M, seed):
     g = gen(seed)
     box = torch.cat((torch.rand((B, M, 2), generator=g) * 0.8 + 0.1, torch.rand((B, M, 2), generator=g) * 0.4 + 0.05),

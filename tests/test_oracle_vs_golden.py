@@ -152,6 +152,29 @@ def test_mask_golden():
     assert_equal(O.box_to_mask(box[0], (20, 24)), g["crop0"])
 
 
+def test_upsample_nearest_index_matches_interpolate():
+    """The oracle's index map is the one F.interpolate(x, size) (the call at yolact_node.py:131) uses."""
+    for in_size, out_size in [(276, 720), (276, 1280), (20, 45), (24, 70), (23, 46), (31, 31), (20, 13), (276, 277),
+                              (138, 480), (7, 1000), (1000, 7)]:
+        x = torch.arange(in_size, dtype=torch.float32).reshape(1, 1, 1, in_size)
+        up = torch.nn.functional.interpolate(x, (1, out_size)).reshape(-1).to(torch.int64)
+        assert_equal(O.upsample_nearest_index(out_size, in_size), up, f"{in_size} -> {out_size}")
+
+
+def test_mask_depth_golden():
+    """masked_depth_mean against the node's own sequence of calls (frozen by make_golden.py)."""
+    g = golden("yl_mask_depth")
+    for tag in "ab":
+        proto, coeff, box = t(g[f"proto_{tag}"]), t(g[f"coeff_{tag}"]), t(g[f"box_{tag}"])
+        for j in range(5):
+            mean, count = O.masked_depth_mean(proto, coeff, box, t(g[f"depth_{tag}{j}"]))
+            assert_equal(count, g[f"count_{tag}{j}"], f"count {tag}{j}")
+            assert_close(mean, g[f"mean_{tag}{j}"], rtol=1e-12, what=f"mean {tag}{j}")
+        mean, count = O.masked_depth_mean(proto, coeff, None, t(g[f"depth_{tag}0"]))
+        assert_equal(count, g[f"count_{tag}_nobox"]), assert_close(mean, g[f"mean_{tag}_nobox"], rtol=1e-12)
+    assert np.isnan(g["mean_a3"]).any() or (g["count_a3"] > 0).all()  # (NaN rows compare as equal in assert_close)
+
+
 def test_match_golden():
     g = golden("yl_match")
     mi, miou, pos, neg, tgt = O.match_anchors(t(g["anchor"]), t(g["truth_box"]), t(g["truth_valid"]), 0.4, 0.3,

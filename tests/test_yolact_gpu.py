@@ -212,6 +212,79 @@ def test_mask_batched_matches_single(yl, monkeypatch):
         assert_equal(out[b, :n], single, f"frame {b}: batched == per-frame call")
 
 
+def _u16(depth_i32, dev):
+    return depth_i32.to(torch.int32).to(dev).to(torch.uint16)
+
+
+@pytest.mark.parametrize("simt", [False, True])
+def test_mask_depth_golden(yl, monkeypatch, simt):
+    """masked_depth_mean against the node's own call sequence (assemble_mask -> F.interpolate -> nanmean of the
+    selected depth readings, yolact_node.py:102-103,130-131,178) frozen from the real reference.  Case b has
+    half-integer logits from bf16-exact operands and P = 32: the tensor-core epilogue must select exactly the same
+    pixels; case a (P = 8) goes through the CUDA-core kernel either way."""
+    if simt:
+        monkeypatch.setenv("TAUV_MASK_SIMT", "1")
+    else:
+        monkeypatch.delenv("TAUV_MASK_SIMT", raising=False)
+    g = golden("yl_mask_depth")
+    d = yl.dev
+    for tag in "ab":
+        proto, coeff, box = t(g[f"proto_{tag}"]).to(d), t(g[f"coeff_{tag}"]).to(d), t(g[f"box_{tag}"]).to(d)
+        for j in range(5):
+            mean, count = yl.masks.masked_depth_mean(proto, coeff, box, _u16(t(g[f"depth_{tag}{j}"]), d), return_count=True)
+            assert_equal(count, g[f"count_{tag}{j}"], f"count {tag}{j}")
+            assert_close(mean, g[f"mean_{tag}{j}"], rtol=1e-12, what=f"mean {tag}{j}")
+        mean, count = yl.masks.masked_depth_mean(proto, coeff, None, _u16(t(g[f"depth_{tag}0"]), d), return_count=True)
+        assert_equal(count, g[f"count_{tag}_nobox"]), assert_close(mean, g[f"mean_{tag}_nobox"], rtol=1e-12)
+    e = yl.masks.masked_depth_mean(proto, coeff[:0], box[:0], _u16(t(g["depth_b0"]), d))
+    assert e.shape == (0,) and e.dtype == torch.float64
+    with pytest.raises(TypeError):
+        yl.masks.masked_depth_mean(proto, coeff, box, t(g["depth_b0"]).to(d))  # int32 is not a mono16 image
+
+
+@pytest.mark.parametrize("H,W,K,hi,wi", [(138, 138, 100, 360, 640), (276, 276, 37, 720, 1280), (69, 69, 150, 69, 69),
+                                          (276, 276, 300, 240, 320)])
+def test_mask_depth_vs_oracle(yl, monkeypatch, H, W, K, hi, wi):
+    """Full-size prototype maps, several M tiles (K > 256 takes two launches), up- and down-sampling.  Real-valued
+    operands: a camera pixel may legitimately flip where its logit is within the bf16x2 contraction error of zero,
+    so counts may differ by the number of such readings (computed in float64) and the mean accordingly."""
+    monkeypatch.delenv("TAUV_MASK_SIMT", raising=False)
+    proto, coeff, box = synth.mask_inputs(32, H, W, K, seed=H + K)
+    depth = synth.depth_image(hi, wi, seed=hi)
+    ref_mean, ref_count = O.masked_depth_mean(proto, coeff, box, depth)
+    d = yl.dev
+    mean, count = yl.masks.masked_depth_mean(proto.to(d), coeff.to(d), box.to(d), _u16(depth, d), return_count=True)
+    lg = (coeff.double() @ proto.reshape(32, -1).double()).reshape(K, H, W)
+    iy, ix = O.upsample_nearest_index(hi, H), O.upsample_nearest_index(wi, W)
+    amb = ((lg.abs() < 1e-4)[:, iy][:, :, ix] & (depth != 0).unsqueeze(0)).sum(dim=(1, 2))
+    diff = (count.cpu() - ref_count).abs()
+    assert bool((diff <= amb).all()), f"count differs beyond the ambiguous readings: {diff.max().item()} vs {amb.max().item()}"
+    clean = (amb == 0).numpy()
+    assert_close(mean.cpu().numpy()[clean], ref_mean.numpy()[clean], rtol=1e-12, what="mean depth")
+    assert_close(mean.cpu().numpy()[~clean], ref_mean.numpy()[~clean], rtol=1e-2, what="mean depth (ambiguous readings)")
+
+
+def test_mask_depth_batched_matches_single(yl, monkeypatch):
+    monkeypatch.delenv("TAUV_MASK_SIMT", raising=False)
+    d = yl.dev
+    B, N, P, H, W, top_k, hi, wi = 3, 500, 32, 48, 52, 40, 120, 160
+    g = synth.gen(12)
+    anchor = torch.cat((torch.rand((1, N, 2), generator=g), torch.rand((1, N, 2), generator=g) * 0.3 + 0.05), -1)
+    cls, enc = synth.yolact_heads(B, N, 7, seed=13, anchor=anchor, separated=True)
+    proto = torch.nn.functional.leaky_relu(torch.randn((B, P, H, W), generator=g)).to(d)
+    coeff = torch.tanh(torch.randn((B, N, P), generator=g)).to(d)
+    depth = torch.stack([_u16(synth.depth_image(hi, wi, seed=70 + b), d) for b in range(B)])
+    det = yl.nms.detect(cls.to(d), enc.to(d), anchor.to(d), CFG, top_k, 0.5, 0.05)
+    mean, count = yl.masks.masked_depth_mean_batched(proto, coeff, det, depth)
+    for b in range(B):
+        n = int(det.n_keep[b])
+        assert n > 0
+        m1, c1 = yl.masks.masked_depth_mean(proto[b], coeff[b, det.keep[b, :n]], det.box[b, :n], depth[b], return_count=True)
+        assert_equal(count[b, :n], c1, f"frame {b}: count")
+        assert_close(mean[b, :n], m1, rtol=0, atol=0, what=f"frame {b}: batched == per-frame call")
+        assert bool(torch.isnan(mean[b, n:]).all()) and int(count[b, n:].abs().sum()) == 0
+
+
 def test_match_golden(yl):
     g = golden("yl_match")
     d = yl.dev

@@ -47,6 +47,16 @@ mask_bytes = proto.numel() * 4 + det.n_keep.sum().item() * (HP * HP * 4 + P * 4 
 mask_flops = 2.0 * det.n_keep.sum().item() * P * HP * HP
 res["mask_us"] = t; res["mask_gbs"] = mask_bytes / t / 1e3; res["mask_tflops_useful"] = mask_flops / t / 1e6
 res["mask_tflops_issued"] = 3 * 2.0 * B * ((HP * HP + 255) // 256) * 128 * 256 * P / t / 1e6
+# fused consumer: mask assembly + nearest resize to the camera + mean depth under each mask (no mask written)
+HI, WI = 720, 1280
+depth = torch.randint(300, 9000, (B, HI, WI), device=dev, dtype=torch.int32)
+depth = torch.where(torch.rand((B, HI, WI), device=dev) < 0.2, torch.zeros((), dtype=torch.int32, device=dev), depth).to(torch.uint16)
+ws_d = torch.empty(tv.load_library().tauv_yolact_mask_depth_workspace_bytes(B, HP, HP, TOPK), dtype=torch.uint8, device=dev)
+t, (dm, dc) = timeit(lambda: masks.masked_depth_mean_batched(proto, coeff, det, depth, workspace=ws_d), n=5)
+depth_bytes = proto.numel() * 4 + depth.numel() * 2 + 2 * B * HP * HP * 8 + det.n_keep.sum().item() * (P * 4 + 16 + 16)
+res["mask_depth_us"] = t; res["mask_depth_gbs"] = depth_bytes / t / 1e3
+res["mask_depth_camera"] = [HI, WI]; res["mask_depth_valid_rows"] = int((dc > 0).sum().item())
+res["frames_per_s_detect_plus_mask_depth"] = B / ((res["detect_us"] + t) * 1e-6)
 os.environ["TAUV_MASK_SIMT"] = "1"
 t, _ = timeit(lambda: masks.assemble_mask_batched(proto, coeff, det, out=out), n=3)
 del os.environ["TAUV_MASK_SIMT"]
