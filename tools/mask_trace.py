@@ -7,7 +7,7 @@ import tauv_vision_b200 as tv
 from tauv_vision_b200.yolact.model import masks
 lib = tv.load_library()
 dev = torch.device("cuda", 0)
-B, N, P, HP, TOPK, NK = 16, 19248, 32, 276, 200, 160
+B, N, P, HP, TOPK, NK = int(os.environ.get("B", 16)), 19248, 32, 276, 200, 160
 g = torch.Generator(device=dev); g.manual_seed(3)
 coeff = torch.tanh(torch.randn((B, N, P), device=dev, generator=g))
 proto = torch.nn.functional.leaky_relu(torch.randn((B, P, HP, HP), device=dev, generator=g))
