@@ -494,14 +494,13 @@ __device__ __noinline__ void finish_item(const TileArgs& a, TileCtx* ctx, unsign
 // first items of EVERY frame finish early and publish a threshold for the frame's other items.
 template <int MODE, bool VEC>
 __global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(const __grid_constant__ TileArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned long long* list = reinterpret_cast<unsigned long long*>(smem_raw);
   uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)a.cap * 8);
   __shared__ TileCtx s_ctx;
   TileCtx* ctx = &s_ctx;
   const int tid = threadIdx.x;
 
-  const int items_per_frame = a.C * a.items_per_plane;
   const int item_in_frame = blockIdx.x / a.B;
   const int frame = blockIdx.x - item_in_frame * a.B;
   const int item = frame * a.rows_per_frame + item_in_frame;  // row of the candidate table
@@ -645,9 +644,8 @@ template <int MODE, int NT>
 __device__ void topk_emit_ranked(unsigned long long* sel, int p2, int npos, uint32_t* flags, int b, int k, int H, int W,
                                  int64_t* __restrict__ index, int64_t* __restrict__ label, float* __restrict__ score,
                                  const BoxArgs& g) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   __shared__ int s_first_below;
-  __shared__ int s_wsum[NT / 32];
   if (tid == 0) s_first_below = k;
   block_bitonic_sort_desc<NT>(sel, p2);
   const long long hw_elems = (long long)H * W;
@@ -754,7 +752,7 @@ __device__ __forceinline__ float cl_window_edge(int wbin) {  // lowest value tha
 constexpr int kClOffCtx = (int)((sizeof(ClusterCtx) + 15) / 16 * 16);
 constexpr int kClOffList = kClOffCtx + (int)((sizeof(TileCtx) + 15) / 16 * 16);
 __device__ __forceinline__ unsigned char* cl_smem() {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   return smem_raw;
 }
 __device__ __forceinline__ ClusterCtx* cl_cc() { return reinterpret_cast<ClusterCtx*>(cl_smem()); }
@@ -1150,7 +1148,7 @@ __device__ __noinline__ void cl_bootstrap_round(const TileArgs& a, TileCtx* ctx,
 template <int MODE>
 __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __grid_constant__ TileArgs a, int n_units,
                                                                        int parts) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
   unsigned long long* list = cl_list();
   uint32_t* hist = cl_hist(a);

@@ -109,23 +109,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-// The same with a back-off between polls, for roles that may wait long (a warp that polls without pause takes issue
-// slots from the warps of its scheduler that everybody is waiting for).
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (!done) __nanosleep(ns);
-  } while (!done);
-}
 // global -> shared bulk copy, completion counted in bytes on `bar`.  16-byte aligned src/dst/size.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
                                          uint64_t* bar) {

@@ -41,19 +41,9 @@ constexpr int kUmmaNMax = 256;        // detections per launch (TMEM columns per
 // 64 frames, epilogue-bound at 5 us per tile; 12 + 4 warps: 1279 us, now producer-bound (latency of the prototype loads);
 // 12 + 4 warps with 3 A stages and 2 staging buffers per group: 1008 us; 16 epilogue warps spill: 2756 us)
 constexpr int kUmmaEpiWarps = TAUV_MASK_EPI_WARPS, kUmmaProdWarps = TAUV_MASK_PROD_WARPS;
-#ifndef TAUV_EPI_BACKOFF
-#define TAUV_EPI_BACKOFF 0
-#endif
-#if TAUV_EPI_BACKOFF > 0
-#define TAUV_EPI_WAIT(bar, par) mbar_wait_relaxed(bar, par, TAUV_EPI_BACKOFF)
-#else
-#define TAUV_EPI_WAIT(bar, par) mbar_wait(bar, par)
-#endif
-#ifndef TAUV_DEPTH_REGPF
-#define TAUV_DEPTH_REGPF 0
-#endif
 #ifndef TAUV_MASK_PREFETCH
-#define TAUV_MASK_PREFETCH 1  // tiles ahead (measured: 0 -> 996 us, 1 -> 965, 2 -> 1035, 4 -> 1157 per 64 frames)
+#define TAUV_MASK_PREFETCH 1  // tiles ahead (mask writer: 0 -> 996 us, 1 -> 965, 2 -> 1035, 4 -> 1157 per 64 frames; the reducing
+                              // kernel does not care: 1, 2, 3, 6 -> 808-810 us, and holding the next tile in registers: 814)
 #endif
 #ifndef TAUV_MASK_A_STAGES
 #define TAUV_MASK_A_STAGES 3
@@ -275,7 +265,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
           pw_u = u + 1;
         }
       }
-      TAUV_EPI_WAIT(&sm->acc_full[as], uses[as] & 1u);
+      mbar_wait(&sm->acc_full[as], uses[as] & 1u);
       tc_fence_after();
       if (tid == 0) mask_stamp(a, u - u0, 5);
       if constexpr (kDepth) {
@@ -486,8 +476,6 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
     uint32_t fills[kUmmaAStages] = {}, frames = 0;
     int st = 0, cur_frame = -1, rows_frame = -1, n_rows = 0;
     int b = b_first, nt = nt_first - 1;
-    float fn[kUmmaP];  // (depth mode) the next tile's pixel row, in flight
-    long long pf_u = -1;
     for (long long u = u0; u < u1; ++u) {
       if (++nt == n_tiles) {
         nt = 0;
@@ -552,40 +540,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
           }
         }
       }
-      if constexpr (TAUV_DEPTH_REGPF && kDepth && kUmmaProdWarps * 32 == kUmmaM) {
-        // The reducing kernel has registers to spare (no staging epilogue) and, with nothing to write, is bound by
-        // these loads: one pixel row per thread, the NEXT tile's 32 values in flight while this one is converted.
-        float f[kUmmaP];
-        if (pf_u == u) {
-#pragma unroll
-          for (int p = 0; p < kUmmaP; ++p) f[p] = fn[p];
-        } else {
-          const int pix = nt * kUmmaM + pt;
-          const float* src = a.proto + (size_t)b * kUmmaP * HW + pix;
-#pragma unroll
-          for (int p = 0; p < kUmmaP; ++p) f[p] = pix < HW ? __ldg(src + (size_t)p * HW) : 0.0f;
-        }
-        if (u + 1 < u1) {
-          const int b2 = nt + 1 == n_tiles ? b + 1 : b;
-          const int pix = (nt + 1 == n_tiles ? 0 : nt + 1) * kUmmaM + pt;
-          const float* src = a.proto + (size_t)b2 * kUmmaP * HW + pix;
-#pragma unroll
-          for (int p = 0; p < kUmmaP; ++p) fn[p] = pix < HW ? __ldg(src + (size_t)p * HW) : 0.0f;
-          pf_u = u + 1;
-        }
-        if (fills[st] > 0) mbar_wait(&sm->a_empty[st], (fills[st] - 1) & 1u);
-        if (pt == 0) mask_stamp(a, u - u0, 0);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 qh, ql;
-          split_bf16x2(f[8 * c], f[8 * c + 1], qh.x, ql.x);
-          split_bf16x2(f[8 * c + 2], f[8 * c + 3], qh.y, ql.y);
-          split_bf16x2(f[8 * c + 4], f[8 * c + 5], qh.z, ql.z);
-          split_bf16x2(f[8 * c + 6], f[8 * c + 7], qh.w, ql.w);
-          *reinterpret_cast<uint4*>(sm->a[st][0] + sw64_offset(pt, c)) = qh;
-          *reinterpret_cast<uint4*>(sm->a[st][1] + sw64_offset(pt, c)) = ql;
-        }
-      } else {
+      {
         if (fills[st] > 0) mbar_wait(&sm->a_empty[st], (fills[st] - 1) & 1u);
         if (pt == 0) mask_stamp(a, u - u0, 0);
         // A tile: pixel rows pt, pt + producers, ...; 32 prototype values each -> 4 chunks of 8 bf16 (hi and lo)
