@@ -219,12 +219,27 @@ __global__ void __launch_bounds__(kNmsThreads) nms_frame_kernel(NmsArgs a) {
   __syncthreads();
   auto load = [&](int i) -> unsigned long long { return make_composite(float_to_key(sc[i]), (uint32_t)i); };
   const unsigned long long T = block_kth_largest<kNmsThreads>(load, N, K, hist, ctl);
-  for (int i = tid; i < N; i += kNmsThreads) {
-    const unsigned long long c = load(i);
-    if (c >= T) sel[atomicAdd(&ctl[5], 1u)] = c;
+  for (int i0 = 0; i0 < N; i0 += 4 * kNmsThreads) {  // (four independent loads in flight; one atomic per warp and strip)
+    unsigned long long c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kNmsThreads + tid;
+      c[u] = i < N ? load(i) : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool take = i0 + u * kNmsThreads + tid < N && c[u] >= T;
+      const unsigned bal = __ballot_sync(0xffffffffu, take);
+      if (bal) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&ctl[5], (unsigned)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (take) sel[base + __popc(bal & ((1u << lane) - 1u))] = c[u];
+      }
+    }
   }
   __syncthreads();
-  block_bitonic_sort_desc<kNmsThreads>(sel, p2);  // (confidence desc, prior index asc)
+  block_bitonic_sort_desc_reg<kNmsThreads>(sel, p2);  // (confidence desc, prior index asc)
 
   // boxes of the ranked priors -> corners in shared memory (decoded on the fly in detect mode)
   for (int r = tid; r < K; r += kNmsThreads) {
@@ -262,6 +277,12 @@ __global__ void __launch_bounds__(kNmsThreads) nms_frame_kernel(NmsArgs a) {
       for (int i = I * 32; i < i_end; ++i) {
         Corners ci;
         ci.y0 = cor[i]; ci.x0 = cor[p2 + i]; ci.y1 = cor[2 * p2 + i]; ci.x1 = cor[3 * p2 + i]; ci.area = cor[4 * p2 + i];
+        // Disjoint boxes with a positive union have IoU exactly 0 — no NaN-propagating min/max, no IEEE divide
+        // (60 instructions per pair; this loop was a third of the kernel).  Anything with a NaN, an infinity-times-zero
+        // area or an empty union fails one of the comparisons and takes the exact path.
+        if ((ci.y1 <= cj.y0 || cj.y1 <= ci.y0 || ci.x1 <= cj.x0 || cj.x1 <= ci.x0) && (ci.area + cj.area) > 0.0f &&
+            0.0f <= a.iou_thr)
+          continue;
         const float iou = iou_pair(ci, cj);
         s = s || !(iou <= a.iou_thr);
       }

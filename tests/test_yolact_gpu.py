@@ -52,8 +52,11 @@ def test_boxes_golden(yl):
 
 def test_boxes_main_block_round_trip(yl):
     """yolact boxes.py:106-117."""
-    box = torch.rand((1, 1, 4), device=yl.dev)
-    anchor = torch.rand((1, 1, 4), device=yl.dev) + 0.05
+    # (seeded, and sizes bounded away from zero: the reference's own check draws an unseeded torch.rand box, and
+    # iou(box, box) == 1 only holds to ~eps * centre / size — a 1e-3-sized box fails it on the reference too)
+    g = torch.Generator(device="cpu").manual_seed(106)
+    box = torch.cat((torch.rand((1, 1, 2), generator=g), torch.rand((1, 1, 2), generator=g) * 0.5 + 0.25), -1).to(yl.dev)
+    anchor = (torch.rand((1, 1, 4), generator=g) + 0.05).to(yl.dev)
     assert torch.allclose(box, yl.boxes.corners_to_box(yl.boxes.box_to_corners(box)))
     assert torch.allclose(box, yl.boxes.box_decode(yl.boxes.box_encode(box, anchor, CFG), anchor, CFG), atol=1e-6)
     iou = yl.boxes.iou_matrix(box, box)
