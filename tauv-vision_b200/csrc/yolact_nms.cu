@@ -19,6 +19,8 @@ namespace tauv {
 
 constexpr int kNmsThreads = 1024;
 constexpr int kNmsMaxTopK = 4096;
+constexpr int kNmsRegs = 20;    // scores per thread held in registers by the one-pass ranking (N <= 20480)
+constexpr int kNmsCand = 1024;  // its candidate list (aliases the 8 KB radix histogram)
 
 // ---- K1 ----------------------------------------------------------------------------------------
 // NCH = ceil(C1/32) register-resident chunks per lane (C1 <= 128); NCH = 0 -> generic two-pass loop.
@@ -198,7 +200,7 @@ struct NmsArgs {
   float* keep_score;       // [B,top_k] or NULL
 };
 
-__global__ void __launch_bounds__(kNmsThreads) nms_frame_kernel(NmsArgs a) {
+__global__ void __launch_bounds__(kNmsThreads, 1) nms_frame_kernel(NmsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
@@ -218,28 +220,133 @@ __global__ void __launch_bounds__(kNmsThreads) nms_frame_kernel(NmsArgs a) {
   for (int i = tid; i < p2; i += kNmsThreads) sel[i] = 0ull;
   __syncthreads();
   auto load = [&](int i) -> unsigned long long { return make_composite(float_to_key(sc[i]), (uint32_t)i); };
-  const unsigned long long T = block_kth_largest<kNmsThreads>(load, N, K, hist, ctl);
-  for (int i0 = 0; i0 < N; i0 += 4 * kNmsThreads) {  // (four independent loads in flight; one atomic per warp and strip)
-    unsigned long long c[4];
+  // ---- top K of the frame's N confidences, ranked (confidence desc, prior index asc)
+  // Fast path (the shapes of the YOLACT head): every thread keeps its <= 20 scores in registers, ONE pass over the data.
+  //   threshold: thread maxima are sorted inside each warp (shuffles only); the ceil(K/32)-th largest maximum of a warp
+  //   has that many maxima above it, so the smallest of those 32 values has >= K scores at or above it — and, the
+  //   maxima being the top ~5 % of the scores, not many more (~2K);
+  //   the candidates at or above it go to a 1024-entry list and are ranked there.
+  // The exact radix select over all N scores (the general path below) needs five passes and was a third of the kernel.
+  bool ranked = false;
+  if (N >= kNmsThreads && N <= kNmsThreads * kNmsRegs && K <= kNmsCand / 2) {
+    unsigned long long* cand = reinterpret_cast<unsigned long long*>(hist);  // [kNmsCand] (the histogram is not in use)
+    __shared__ unsigned long long s_wthr[kNmsThreads / 32];
+    float v[kNmsRegs];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * kNmsThreads + tid;
-      c[u] = i < N ? load(i) : 0ull;
+    for (int u = 0; u < kNmsRegs; ++u) {
+      const int i = u * kNmsThreads + tid;
+      v[u] = __ldg(sc + min(i, N - 1));  // (unpredicated: there are only seven predicate registers)
     }
+    // All twenty loads are in flight before the first use: left to itself the compiler issues them in pairs between
+    // the key arithmetic (short live ranges), the warp stalls on the first use, and the pass costs 10 k cycles of
+    // serialised L2 latency.  One empty asm that names every value cannot be placed before the last load.
+    static_assert(kNmsRegs == 20, "the operand list below names twenty registers");
+    asm volatile(""
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                   "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]),
+                   "+f"(v[17]), "+f"(v[18]), "+f"(v[19]));
+    uint32_t mk = 0u, mi = 0u;  // the thread's best key and its (smallest) prior index
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const bool take = i0 + u * kNmsThreads + tid < N && c[u] >= T;
-      const unsigned bal = __ballot_sync(0xffffffffu, take);
-      if (bal) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&ctl[5], (unsigned)__popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (take) sel[base + __popc(bal & ((1u << lane) - 1u))] = c[u];
+    for (int u = 0; u < kNmsRegs; ++u) {
+      const int i = u * kNmsThreads + tid;
+      const uint32_t k = i < N ? float_to_key(v[u]) : 0u;
+      if (k > mk || u == 0) {
+        mk = k;
+        mi = (uint32_t)i;
       }
     }
+    unsigned long long mx = make_composite(mk, mi);
+    for (int i = tid; i < kNmsCand; i += kNmsThreads) cand[i] = 0ull;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {  // warp bitonic sort, descending: lane 0 ends with the largest
+      const bool desc = size == 32 || (lane & size) == 0;
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const unsigned long long y = __shfl_xor_sync(0xffffffffu, mx, stride);
+        const bool take_max = ((lane & stride) == 0) == desc;
+        mx = (take_max == (y > mx)) ? y : mx;
+      }
+    }
+    const unsigned long long wthr = __shfl_sync(0xffffffffu, mx, (K + 31) / 32 - 1);
+    if (lane == 0) s_wthr[warp] = wthr;
+    __syncthreads();
+    unsigned long long T = s_wthr[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long y = __shfl_xor_sync(0xffffffffu, T, o);
+      T = y < T ? y : T;
+    }
+    // append without atomics (640 warp-level adds to one shared counter serialise for ~13 k cycles) and without votes:
+    // every thread notes which of its scores qualify, one block-wide prefix over the counts gives it a private range
+    // of the list (the order inside the list does not matter: it is sorted next)
+    uint32_t tm = 0u;
+#pragma unroll
+    for (int u = 0; u < kNmsRegs; ++u) {
+      const int i = u * kNmsThreads + tid;
+      if (i < N && make_composite(float_to_key(v[u]), (uint32_t)i) >= T) tm |= 1u << u;
+    }
+    const unsigned my_cnt = (unsigned)__popc(tm);
+    unsigned incl = my_cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_wsum[warp] = (int)incl;
+    __syncthreads();
+    unsigned base = incl - my_cnt, n_cand = 0;
+    {
+      const unsigned w = (unsigned)s_wsum[lane];
+      unsigned wincl = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, wincl, o);
+        if (lane >= o) wincl += y;
+      }
+      n_cand = __shfl_sync(0xffffffffu, wincl, 31);
+      base += __shfl_sync(0xffffffffu, wincl - w, warp);
+    }
+    if (n_cand <= (unsigned)kNmsCand) {
+#pragma unroll
+      for (int u = 0; u < kNmsRegs; ++u)
+        if ((tm >> u) & 1u) cand[base++] = make_composite(float_to_key(v[u]), (uint32_t)(u * kNmsThreads + tid));
+    }
+    __syncthreads();
+    if (n_cand <= (unsigned)kNmsCand) {  // (a plateau of equal scores can overflow the list: general path)
+      int pc = p2;
+      while (pc < (int)n_cand) pc <<= 1;
+      block_bitonic_sort_desc_reg<kNmsThreads>(cand, pc);
+      for (int r = tid; r < K; r += kNmsThreads) sel[r] = cand[r];
+      ranked = true;
+    }
+    __syncthreads();  // (cand aliases hist / sup)
+    if (tid == 0) ctl[5] = 0;
+    __syncthreads();
   }
-  __syncthreads();
-  block_bitonic_sort_desc_reg<kNmsThreads>(sel, p2);  // (confidence desc, prior index asc)
+  if (!ranked) {
+    const unsigned long long T = block_kth_largest<kNmsThreads>(load, N, K, hist, ctl);
+    for (int i0 = 0; i0 < N; i0 += 4 * kNmsThreads) {  // (four independent loads in flight; one atomic per warp and strip)
+      unsigned long long c[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kNmsThreads + tid;
+        c[u] = i < N ? load(i) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool take = i0 + u * kNmsThreads + tid < N && c[u] >= T;
+        const unsigned bal = __ballot_sync(0xffffffffu, take);
+        if (bal) {
+          unsigned base = 0;
+          if (lane == 0) base = atomicAdd(&ctl[5], (unsigned)__popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (take) sel[base + __popc(bal & ((1u << lane) - 1u))] = c[u];
+        }
+      }
+    }
+    __syncthreads();
+    block_bitonic_sort_desc_reg<kNmsThreads>(sel, p2);
+  }
 
   // boxes of the ranked priors -> corners in shared memory (decoded on the fly in detect mode)
   for (int r = tid; r < K; r += kNmsThreads) {

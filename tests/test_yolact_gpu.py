@@ -122,6 +122,23 @@ def test_nms_edge_cases(yl):
     assert_equal(yl.nms.nms(cls.to(d), box.to(d), 1000, 0.4, 0.3), O.nms(cls, box, 1000, 0.4, 0.3), "top_k 1000")
 
 
+@pytest.mark.parametrize("N,top_k,plateau", [(3000, 100, False), (3000, 100, True), (1024, 512, False), (1023, 64, False),
+                                             (20480, 200, False), (20481, 200, False), (5000, 513, False), (2500, 37, True)])
+def test_nms_ranking_paths(yl, N, top_k, plateau):
+    """The one-pass ranking (1024 <= N <= 20480, top_k <= 512) and the general radix select must give the same keep set:
+    sizes on both sides of every limit, and a plateau of equal confidences (more candidates than the one-pass list
+    holds: it must fall back, and equal confidences tie-break by prior index)."""
+    d = yl.dev
+    g = synth.gen(N + top_k)
+    anchor = torch.cat((torch.rand((1, N, 2), generator=g), torch.rand((1, N, 2), generator=g) * 0.2 + 0.03), -1)
+    cls, enc = synth.yolact_heads(1, N, 5, seed=N, anchor=anchor, n_clusters=30, per_cluster=10, separated=True)
+    if plateau:
+        cls[0, : N // 2] = 0.0  # half of the priors share one, top, confidence exactly
+        cls[0, : N // 2, 1] = 9.0
+    box = O.box_decode(enc, anchor, CFG.box_variances)
+    assert_equal(yl.nms.nms(cls.to(d), box.to(d), top_k, 0.5, 0.05), O.nms(cls, box, top_k, 0.5, 0.05), f"N={N} top_k={top_k}")
+
+
 def test_full_size_vs_oracle(yl):
     """BASELINE.json configs[2] geometry: 19 248 priors (550x550, 3 aspect ratios), 81 classes, top_k 200."""
     d = yl.dev
