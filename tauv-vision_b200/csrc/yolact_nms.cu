@@ -194,6 +194,8 @@ struct NmsArgs {
   float v0, v1;
   int N, top_k;
   float iou_thr, conf_thr;
+  double iou_mid;          // midpoint between iou_thr and the next float up (exact in double); 0 = no division-free test
+  int iou_mid_inclusive;   // a quotient exactly at the midpoint rounds to iou_thr (even mantissa), i.e. does not suppress
   int64_t* keep;           // [B,top_k]
   int32_t* n_keep;         // [B]
   float4* keep_box;        // [B,top_k,4] or NULL
@@ -359,7 +361,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_frame_kernel(NmsArgs a) {
       bx = decode_one(a.enc[(size_t)b * N + idx], an, a.v0, a.v1);
     }
     const Corners c = to_corners(bx);
-    cor[r] = c.y0; cor[p2 + r] = c.x0; cor[2 * p2 + r] = c.y1; cor[3 * p2 + r] = c.x1; cor[4 * p2 + r] = c.area;
+    // (a NaN corner poisons the area: the pair test then takes the IEEE path, whose result is NaN either way)
+    const bool nan_corner = c.y0 != c.y0 || c.x0 != c.x0 || c.y1 != c.y1 || c.x1 != c.x1;
+    cor[r] = c.y0; cor[p2 + r] = c.x0; cor[2 * p2 + r] = c.y1; cor[3 * p2 + r] = c.x1;
+    cor[4 * p2 + r] = nan_corner ? __int_as_float(0x7fc00000) : c.area;
     if (a.keep_box) a.keep_box[(size_t)b * a.top_k + r] = bx;  // ranked order for now; compacted below
   }
   const int T32 = (K + 31) >> 5;
@@ -384,12 +389,23 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_frame_kernel(NmsArgs a) {
       for (int i = I * 32; i < i_end; ++i) {
         Corners ci;
         ci.y0 = cor[i]; ci.x0 = cor[p2 + i]; ci.y1 = cor[2 * p2 + i]; ci.x1 = cor[3 * p2 + i]; ci.area = cor[4 * p2 + i];
-        // Disjoint boxes with a positive union have IoU exactly 0 — no NaN-propagating min/max, no IEEE divide
-        // (60 instructions per pair; this loop was a third of the kernel).  Anything with a NaN, an infinity-times-zero
-        // area or an empty union fails one of the comparisons and takes the exact path.
-        if ((ci.y1 <= cj.y0 || cj.y1 <= ci.y0 || ci.x1 <= cj.x0 || cj.x1 <= ci.x0) && (ci.area + cj.area) > 0.0f &&
-            0.0f <= a.iou_thr)
-          continue;
+        // `fl(inter / union) <= thr` without the division: the rounded quotient is <= thr exactly when the real quotient
+        // is below the midpoint m between thr and the next float (at m itself: round-to-even decides), and
+        // inter <= m * union is exact in double (24 x 25 significant bits).  No NaN-propagating min/max either: boxes with
+        // a NaN corner carry a NaN area, which fails `uni > 0` like every other special case (empty or infinite union)
+        // and takes the IEEE path below.  (The divide path is ~60 instructions, and with 32 different columns per warp
+        // some lane needed it on almost every step: this loop was a third of the kernel.)
+        {
+          const float ih = fmaxf(__fsub_rn(fminf(ci.y1, cj.y1), fmaxf(ci.y0, cj.y0)), 0.0f);
+          const float iw = fmaxf(__fsub_rn(fminf(ci.x1, cj.x1), fmaxf(ci.x0, cj.x0)), 0.0f);
+          const float inter = __fmul_rn(ih, iw);
+          const float uni = __fsub_rn(__fadd_rn(ci.area, cj.area), inter);
+          if (a.iou_mid > 0.0 && uni > 0.0f && uni < __int_as_float(0x7f800000)) {
+            const double lhs = (double)inter, rhs = a.iou_mid * (double)uni;
+            s = s || !(a.iou_mid_inclusive ? lhs <= rhs : lhs < rhs);
+            continue;
+          }
+        }
         const float iou = iou_pair(ci, cj);
         s = s || !(iou <= a.iou_thr);
       }
@@ -520,6 +536,15 @@ static int run_nms(const float* cls, const float* box, const float* enc, const f
   NmsArgs a;
   a.score = score; a.box = (const float4*)box; a.enc = (const float4*)enc; a.anchor = (const float4*)anchor;
   a.anchor_batch = anchor_batch; a.v0 = v0; a.v1 = v1; a.N = N; a.top_k = top_k; a.iou_thr = iou_thr; a.conf_thr = conf_thr;
+  a.iou_mid = 0.0;
+  a.iou_mid_inclusive = 0;
+  if (iou_thr > 1e-30f && iou_thr < 1e30f) {  // (normal, positive: the midpoint construction below is exact)
+    const float up = nextafterf(iou_thr, INFINITY);
+    uint32_t bits;
+    memcpy(&bits, &iou_thr, sizeof(bits));
+    a.iou_mid = ((double)iou_thr + (double)up) * 0.5;
+    a.iou_mid_inclusive = (bits & 1u) == 0u;
+  }
   a.keep = keep; a.n_keep = n_keep; a.keep_box = (float4*)keep_box; a.keep_score = keep_score;
   const size_t smem = nms_smem(top_k < N ? top_k : N);
   TAUV_CUDA(cudaFuncSetAttribute(nms_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

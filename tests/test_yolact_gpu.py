@@ -139,6 +139,37 @@ def test_nms_ranking_paths(yl, N, top_k, plateau):
     assert_equal(yl.nms.nms(cls.to(d), box.to(d), top_k, 0.5, 0.05), O.nms(cls, box, top_k, 0.5, 0.05), f"N={N} top_k={top_k}")
 
 
+def test_nms_threshold_on_the_boundary(yl):
+    """The kernel decides `fl(inter / union) <= thr` without dividing (exact comparison against the rounding midpoint in
+    double).  Thresholds that ARE one of the pair IoUs, and their float neighbours, hit the equality / midpoint cases; the
+    keep set must equal the oracle's (IEEE division) every time.  Also boxes with NaN / infinite / zero sizes."""
+    d = yl.dev
+    g = synth.gen(77)
+    N = 96
+    box = torch.cat((torch.rand((1, N, 2), generator=g) * 0.5 + 0.25, torch.rand((1, N, 2), generator=g) * 0.3 + 0.1), -1)
+    cls = torch.zeros((1, N, 3))
+    cls[0, :, 1] = torch.linspace(6.0, 1.0, N)  # distinct, descending confidences: rank == prior index
+    iou = O.iou_matrix(box, box)[0]
+    vals = iou[torch.triu(torch.ones(N, N, dtype=torch.bool), 1)]
+    vals = vals[(vals > 0.05) & (vals < 0.95)]
+    picks = vals[torch.randperm(vals.numel(), generator=g)[:24]]
+    checked = 0
+    for v in picks.tolist():
+        f = np.float32(v)
+        for thr in (f, np.nextafter(f, np.float32(1)), np.nextafter(f, np.float32(0))):
+            assert_equal(yl.nms.nms(cls.to(d), box.to(d), N, float(thr), 0.0), O.nms(cls, box, N, float(thr), 0.0),
+                         f"iou_threshold {float(thr)!r}")
+            checked += 1
+    assert checked == 72
+    weird = box.clone()
+    weird[0, 3, 2] = float("nan")
+    weird[0, 7, 3] = float("inf")
+    weird[0, 11, 2:] = 0.0
+    weird[0, 12] = weird[0, 11]           # two empty boxes at the same place: 0/0 -> NaN suppresses
+    weird[0, 20, 0] = float("nan")
+    assert_equal(yl.nms.nms(cls.to(d), weird.to(d), N, 0.5, 0.0), O.nms(cls, weird, N, 0.5, 0.0), "NaN / inf / empty boxes")
+
+
 def test_full_size_vs_oracle(yl):
     """BASELINE.json configs[2] geometry: 19 248 priors (550x550, 3 aspect ratios), 81 classes, top_k 200."""
     d = yl.dev
