@@ -817,6 +817,9 @@ __device__ __forceinline__ int cl_scan_bin(cg::cluster_group& cluster, ClusterCt
   const int maxbin = (int)*reinterpret_cast<volatile uint32_t*>(&cc->maxbin);
   uint32_t acc = 0;
   int found = -1;
+  // (32 bins per step.  Four steps' worth of remote loads issued together were measured slower — 6.3 us instead of
+  // 2.7 for the final prune, and the streaming end slipped by 2 us: the k-th best usually lies within the first 32-64
+  // bins, and every extra remote load costs at the target CTA.)
   for (int it = 0; it < 16 && found < 0; ++it) {
     const int bin = maxbin - it * 32 - lane;
     uint32_t v = 0;
@@ -1314,10 +1317,16 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
       __shared__ uint32_t s_flags[kFuseMaxK];  // rank 0: flat indices < k taken by a selected peak (for the fillers)
       __shared__ int s_rank[kFuseMaxK];
       const int n = ctx->count;
+      // (debug trace, tools/tail_trace.py: tail stamps go to unused columns of the CTA's second and third item rows)
+      auto tail_stamp = [&](int which) {
+        if (a.trace && tid == 0 && iif + 2 * kClSize < i_hi)
+          a.trace[(size_t)item_geom(a, frame, iif + (which < 3 ? 1 : 2) * kClSize).item * 8 + (which % 3 == 0 ? 1 : 5 + which % 3)] = now();
+      };
       convert_entries<MODE>(ctx, list, n);
       for (int i = tid; i < a.k; i += kTileThreads) s_flags[i] = 0u;
       if (tid == 0) s_nge = 0;
       cluster.sync();  // (3a) every CTA has finished streaming and binning; rank 0's flags are clear
+      tail_stamp(0);
       if (tid < 32) {
         const int bin = cl_scan_bin(cluster, cc, a.k);
         if (tid == 0) {
@@ -1344,17 +1353,22 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
         compact_list(ctx, list, n2, [&](unsigned long long c) { return c >= T; });
       }
       if (tid == 0) ctx->emit = (uint32_t)ctx->base;
+      tail_stamp(1);
       cluster.sync();  // (3b) all eight pruned lists are final
+      tail_stamp(2);
       unsigned long long* pool = reinterpret_cast<unsigned long long*>(hist);  // hist + tile: contiguous, >= 8k keys
       {
-        int off = 0;
+        // the eight counts first (independent remote loads: one DSMEM round trip, not eight in a chain), then all lists
+        int cnt[kClSize], total_n = 0;
+#pragma unroll
+        for (int r = 0; r < kClSize; ++r) cnt[r] = (int)*cluster.map_shared_rank(&ctx->emit, r);
+#pragma unroll
         for (int r = 0; r < kClSize; ++r) {
-          const int cnt = (int)*cluster.map_shared_rank(&ctx->emit, r);
           const unsigned long long* rl = cluster.map_shared_rank(list, r);
-          for (int i = tid; i < cnt; i += kTileThreads) pool[off + i] = rl[i];
-          off += cnt;
+          for (int i = tid; i < cnt[r]; i += kTileThreads) pool[total_n + i] = rl[i];
+          total_n += cnt[r];
         }
-        if (tid == 0) s_total = off;
+        if (tid == 0) s_total = total_n;
       }
       const int n_own = (int)ctx->emit;
       for (int i = tid; i < n_own; i += kTileThreads) s_rank[i] = 0;
@@ -1371,9 +1385,10 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
         }
       }
       __syncthreads();
+      tail_stamp(3);
       {
         const BoxArgs& g = a.box;
-        const long long hw_elems = (long long)a.H * a.W;
+        const uint32_t hw_elems = (uint32_t)(a.H * a.W);  // (the cluster path requires W <= 1016 and C*H*W < 2^32)
         int my_ge = 0;
         for (int i = tid; i < n_own; i += kTileThreads) {
           const int r = s_rank[i];
@@ -1381,9 +1396,9 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
             const unsigned long long c = list[i];
             const uint32_t flat = composite_idx(c);
             const float sc = key_to_float(composite_key(c));
-            const long long lab = flat / hw_elems;
-            const long long rem = flat - lab * hw_elems;
-            const int iy = (int)(rem / a.W), ix = (int)(rem - (long long)iy * a.W);
+            const uint32_t lab = flat / hw_elems;  // 32-bit: a 64-bit divide is ~100 dependent instructions
+            const uint32_t rem = flat - lab * hw_elems;
+            const int iy = (int)(rem / (uint32_t)a.W), ix = (int)(rem - (uint32_t)iy * (uint32_t)a.W);
             const long long slot = (long long)frame * a.k + r;
             a.out_index[slot * 2 + 0] = iy;
             a.out_index[slot * 2 + 1] = ix;
@@ -1396,9 +1411,14 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
             if (flat < (uint32_t)a.k) *cluster.map_shared_rank(&s_flags[flat], 0) = 1u;
           }
         }
-        if (my_ge) atomicAdd(cluster.map_shared_rank(&s_nge, 0), my_ge);
+        // one remote add per warp, not per thread (remote shared-memory atomics cost ~8 ns each at the target)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_ge += __shfl_xor_sync(0xffffffffu, my_ge, o);
+        if ((tid & 31) == 0 && my_ge) atomicAdd(cluster.map_shared_rank(&s_nge, 0), my_ge);
       }
+      tail_stamp(4);
       cluster.sync();  // (3) nobody touches this unit's distributed state any more; rank 0 sees flags and count
+      tail_stamp(5);
       if (rank == 0) {
         const int npos = min(a.k, s_total);
         if (MODE == TAUV_TOPK_SIGMOID_PEAK && npos < a.k)
