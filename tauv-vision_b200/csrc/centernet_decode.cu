@@ -714,6 +714,9 @@ constexpr int kClBins = 2 * kClWin;                   // negative window + posit
 constexpr int kClNegBase = 1536;                      // fine bins [1536, 2560): -2^33 .. -2^-31
 constexpr int kClPosBase = 5632;                      // fine bins [5632, 6656): +2^-31 .. +2^33
 // (measured on B200: 2 beats 3 and 4 — wider rounds spill a loaded register, and a spill right after the load waits for it)
+#ifndef TAUV_STREAM_PF
+#define TAUV_STREAM_PF 3
+#endif
 #ifndef TAUV_ROUND_W
 #define TAUV_ROUND_W 2
 #endif
@@ -899,6 +902,19 @@ __device__ __noinline__ void cl_stream_all(const TileArgs& a, int frame, int iif
       for (int u = 0; u < kRoundW; ++u) x[u] = xn[u];
       if (s0 + kRoundF4 < n_strips) load_strips<kStreamThreads>(g, s0 + kRoundF4, st, xn);
       else if (more) load_strips<kStreamThreads>(item_geom(a, frame, iif + kClSize), 0, st, xn);
+#if TAUV_STREAM_PF > 0
+      // L2 prefetch of the round TAUV_STREAM_PF ahead (inside the item): the registers hold two
+      // rounds, ~28 KB per SM in flight, which covers ~0.8 us at 5 TB/s — HBM latency under this load is longer, an L2
+      // hit is not.  One lane in eight covers its warp's 128-byte line per strip row.  Measured: 109.6 us without,
+      // 104.7 / 104.5 / 106.0 us with 2 / 3 / 5 rounds ahead; carrying on into the CTA's next item: 105.5 (not kept).
+      if ((st & 7) == 0) {
+#pragma unroll
+        for (int u = 0; u < kRoundW; ++u) {
+          const int rel = s0 + TAUV_STREAM_PF * kRoundF4 + st + u * kStreamThreads;  // strip, relative to the item
+          if (rel < n_strips) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.plane + ((size_t)((g.e0 >> 2) + rel) << 2)));
+        }
+      }
+#endif
       const float thr_f = *reinterpret_cast<volatile float*>(&ctx->thr_f);  // kept current by the service warp
       const int tb = (g.e0 >> 2) + s0 + st;
       uint32_t hot = 0;
