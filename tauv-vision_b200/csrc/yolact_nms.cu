@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(kScoreTileWarps * 32) scores_tile_kernel(const
         if (j >= C1) { j -= C1; ++r; }
       }
     }
+    // (an L2 prefetch of the warp's next block here was measured: 81.9 -> 84.0 us, not kept — enough warps are in flight)
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     if (lane < nrows) {
