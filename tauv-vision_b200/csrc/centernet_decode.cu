@@ -723,10 +723,14 @@ constexpr int kClPosBase = 5632;                      // fine bins [5632, 6656):
 constexpr int kRoundW = TAUV_ROUND_W;                            // 128-bit strips per thread and round (2 x kRoundW live in registers)
 constexpr int kStreamThreads = kTileThreads - 32;     // warps 1..7 stream, warp 0 serves
 constexpr int kRoundF4 = kRoundW * kStreamThreads;    // 128-bit strips per streaming round per CTA
-constexpr int kBootF4 = kRoundW * kTileThreads;       // strips of the bootstrap round (all eight warps)
+#ifndef TAUV_BOOT_W
+#define TAUV_BOOT_W 2
+#endif
+constexpr int kBootW = TAUV_BOOT_W;                    // 128-bit strips per thread in a bootstrap chunk
+constexpr int kBootF4 = kBootW * kTileThreads;        // strips of a bootstrap chunk (all eight warps)
 constexpr int kBootElems = 4 * kBootF4;               // cells of the bootstrap round
 constexpr int kFuseMaxK = 256;                        // fused tail: flags / ranks for k output slots
-constexpr int kHotCap = 1024;                         // ring of queued peak tests (entries of 8 bytes)
+constexpr int kHotCap = kBootW >= 2 ? 1024 : 512;       // ring of queued peak tests (entries of 8 bytes; it lives in the bootstrap tile)
 constexpr int kClMaxW = 1016;                         // halo rows are held in two 128-bit registers per thread
 
 struct __align__(16) ClusterCtx {
@@ -790,12 +794,12 @@ __device__ __forceinline__ ItemGeom item_geom(const TileArgs& a, int frame, int 
 }
 
 // kRoundW 128-bit strips per thread: strips s0 + u*NT + t of the item (s0 relative to the item's first strip)
-template <int NT>
-__device__ __forceinline__ void load_strips(const ItemGeom& g, int s0, int t, float4 (&x)[kRoundW]) {
+template <int NT, int NW>
+__device__ __forceinline__ void load_strips(const ItemGeom& g, int s0, int t, float4 (&x)[NW]) {
   const int t1 = g.e1 >> 2;
   const int tb = (g.e0 >> 2) + s0 + t;
 #pragma unroll
-  for (int u = 0; u < kRoundW; ++u) {
+  for (int u = 0; u < NW; ++u) {
     const int tt = tb + u * NT;
     x[u] = (tt < t1) ? ldg_stream4(g.plane + ((size_t)tt << 2))
                      : make_float4(TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF);
@@ -883,7 +887,7 @@ __device__ __noinline__ void cl_stream_all(const TileArgs& a, int frame, int iif
     g = item_geom(a, frame, iif);
   }
   float4 xn[kRoundW];
-  if (iif >= 0) load_strips<kStreamThreads>(g, s_begin, st, xn);
+  if (iif >= 0) load_strips<kStreamThreads, kRoundW>(g, s_begin, st, xn);
 #pragma unroll 1
   while (iif >= 0) {
     const bool more = iif + kClSize < i_hi;
@@ -900,8 +904,8 @@ __device__ __noinline__ void cl_stream_all(const TileArgs& a, int frame, int iif
       float4 x[kRoundW];
 #pragma unroll
       for (int u = 0; u < kRoundW; ++u) x[u] = xn[u];
-      if (s0 + kRoundF4 < n_strips) load_strips<kStreamThreads>(g, s0 + kRoundF4, st, xn);
-      else if (more) load_strips<kStreamThreads>(item_geom(a, frame, iif + kClSize), 0, st, xn);
+      if (s0 + kRoundF4 < n_strips) load_strips<kStreamThreads, kRoundW>(g, s0 + kRoundF4, st, xn);
+      else if (more) load_strips<kStreamThreads, kRoundW>(item_geom(a, frame, iif + kClSize), 0, st, xn);
 #if TAUV_STREAM_PF > 0
       // L2 prefetch of the round TAUV_STREAM_PF ahead (inside the item): the registers hold two
       // rounds, ~28 KB per SM in flight, which covers ~0.8 us at 5 TB/s — HBM latency under this load is longer, an L2
@@ -1058,10 +1062,10 @@ __device__ __noinline__ void cl_bootstrap_round(const TileArgs& a, TileCtx* ctx,
     // shared-memory counter they serialise and cost several microseconds here).
     const int W = a.W, H = a.H;
     const float NI = TAUV_NEG_INF;
-    float pv[kRoundW * 4];
+    float pv[kBootW * 4];
     uint32_t pmask = 0;
 #pragma unroll
-    for (int u = 0; u < kRoundW; ++u) {
+    for (int u = 0; u < kBootW; ++u) {
       const int off = g.e0 + ((u * kTileThreads + tid) << 2);
       if (off < c_end) {
         const int r = off / W, col = off - r * W;
@@ -1122,7 +1126,7 @@ __device__ __noinline__ void cl_bootstrap_round(const TileArgs& a, TileCtx* ctx,
       fl = 2;  // (plateaus) the whole unit is redone safely
     } else {
 #pragma unroll
-      for (int i = 0; i < kRoundW * 4; ++i) {
+      for (int i = 0; i < kBootW * 4; ++i) {
         if (pmask & (1u << i)) {
           const int off = g.e0 + (((i >> 2) * kTileThreads + tid) << 2) + (i & 3);
           list[base++] = make_composite(float_to_key(pv[i]), g.plane_flat0 + (uint32_t)off);
@@ -1182,7 +1186,8 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
   const int W = a.W;
   auto now = []() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; };
   const long long t_kernel = a.trace ? now() : 0;
-  const int n_boot_chunks = min(8, max(1, (a.k + 127) / 128));
+  // one chunk (kBootElems cells per CTA) for k <= 128, then as many cells as 2048 per 128 of k, at most 16384
+  const int n_boot_chunks = a.k <= 128 ? 1 : min(8, (a.k + 127) / 128) * (2048 / kBootElems);
 
 #pragma unroll 1
   for (int unit = cid; unit < n_units; unit += ncl) {
@@ -1192,7 +1197,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
     int iif = i_lo + rank;
     bool have = iif < i_hi;
     ItemGeom g = item_geom(a, frame, have ? iif : i_lo);
-    float4 xn[kRoundW];
+    float4 xn[kBootW];
     // halo of round 0: plane cells [e0 - W, e0) and [c_end, c_end + W + 4), two 128-bit strips per thread at most
     const int c_end = min(g.e1, g.e0 + kBootElems);
     const int origin = g.e0 - W;                 // plane cell held in tile[0] (may be negative: never read then)
@@ -1200,7 +1205,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
     const int nh = W >> 2;                        // strips per halo row
     float4 halo[2];
     if (have) {
-      load_strips<kTileThreads>(g, 0, tid, xn);
+      load_strips<kTileThreads, kBootW>(g, 0, tid, xn);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int h = tid + j * kTileThreads;     // [0, nh): row above; [nh, 2nh+1): row below (+1 strip)
@@ -1234,7 +1239,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
     if (have) {
       // ---- bootstrap: round 0 of the first item, every cell tested, from shared memory
 #pragma unroll
-      for (int u = 0; u < kRoundW; ++u) {
+      for (int u = 0; u < kBootW; ++u) {
         const int off = g.e0 + ((u * kTileThreads + tid) << 2);
         if (off < c_end) *reinterpret_cast<float4*>(tile + (off - origin)) = xn[u];
       }
@@ -1260,10 +1265,10 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __g
         if (gb.e0 >= g.e1) break;
         const int ce = min(gb.e1, gb.e0 + kBootElems), org = gb.e0 - W;
         __syncthreads();  // the tile is re-used
-        float4 t4[kRoundW];
-        load_strips<kTileThreads>(gb, 0, tid, t4);
+        float4 t4[kBootW];
+        load_strips<kTileThreads, kBootW>(gb, 0, tid, t4);
 #pragma unroll
-        for (int u = 0; u < kRoundW; ++u) {
+        for (int u = 0; u < kBootW; ++u) {
           const int off = gb.e0 + ((u * kTileThreads + tid) << 2);
           if (off < ce) *reinterpret_cast<float4*>(tile + (off - org)) = t4[u];
         }
