@@ -121,6 +121,9 @@ __device__ __forceinline__ float tc_ld_col(uint32_t taddr) {
 __device__ __forceinline__ void tc_wait_ld(float& v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v)::"memory");
 }
+__device__ __forceinline__ void tc_wait_ld2(float& v0, float& v1) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v0), "+f"(v1)::"memory");
+}
 
 // Shared-memory matrix descriptor for a K-major, SWIZZLE_64B operand whose rows are 64 bytes (32 bf16):
 // 8-row groups are 512 B apart (stride byte offset), start address in 16-byte units, descriptor version 1 (sm_100).
@@ -298,33 +301,36 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
               const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kUmmaNMax + c * 32);
               const float4* bp = reinterpret_cast<const float4*>(sm->bounds[c * 32]);
               unsigned ts = 0u, tn = 0u;  // this lane's detection, this tile (fits 32 bits: checked by the host)
+              // two live detections per step: their two TMEM columns are loaded together and their four warp
+              // reductions issue back to back (each step is otherwise one chain of load -> test -> reduce -> select
+              // latencies); an odd one out is paired with itself
               unsigned m = live_mask;
-              int j = __ffs(m) - 1;
-              m &= m - 1u;
-              float v_cur = tc_ld_col(tbase + (uint32_t)j), v_next = 0.0f;
-              tc_wait_ld(v_cur);
-              while (true) {
-                const bool more = m != 0u;
-                int jn = 0;
-                if (more) {
-                  jn = __ffs(m) - 1;
-                  m &= m - 1u;
-                  v_next = tc_ld_col(tbase + (uint32_t)jn);
+              while (m) {
+                const int j0 = __ffs(m) - 1;
+                m &= m - 1u;
+                const bool two = m != 0u;
+                const int j1 = two ? __ffs(m) - 1 : j0;
+                m &= m - 1u;  // (0 & anything = 0)
+                float v0 = tc_ld_col(tbase + (uint32_t)j0), v1 = tc_ld_col(tbase + (uint32_t)j1);
+                tc_wait_ld2(v0, v1);
+                const float4 b0 = bp[j0], b1 = bp[j1];  // broadcasts
+                const int n0 = __float_as_int(px - b0.x) | __float_as_int(b0.y - px) | __float_as_int(py - b0.z) |
+                               __float_as_int(b0.w - py);
+                const int n1 = __float_as_int(px - b1.x) | __float_as_int(b1.y - px) | __float_as_int(py - b1.z) |
+                               __float_as_int(b1.w - py);
+                const bool on0 = n0 >= 0 && v0 > 0.0f, on1 = n1 >= 0 && v1 > 0.0f;
+                const unsigned sx0 = __reduce_add_sync(0xffffffffu, on0 ? pw.x : 0u);
+                const unsigned sn0 = __reduce_add_sync(0xffffffffu, on0 ? pw.y : 0u);
+                const unsigned sx1 = __reduce_add_sync(0xffffffffu, on1 ? pw.x : 0u);
+                const unsigned sn1 = __reduce_add_sync(0xffffffffu, on1 ? pw.y : 0u);
+                if (lane == j0) {
+                  ts = sx0;
+                  tn = sn0;
                 }
-                const float4 bd = bp[j];  // a broadcast
-                const int neg = __float_as_int(px - bd.x) | __float_as_int(bd.y - px) | __float_as_int(py - bd.z) |
-                                __float_as_int(bd.w - py);
-                const bool on = neg >= 0 && v_cur > 0.0f;
-                const unsigned sx = __reduce_add_sync(0xffffffffu, on ? pw.x : 0u);
-                const unsigned sn = __reduce_add_sync(0xffffffffu, on ? pw.y : 0u);
-                if (lane == j) {
-                  ts = sx;
-                  tn = sn;
+                if (lane == j1) {
+                  ts = sx1;
+                  tn = sn1;
                 }
-                if (!more) break;
-                tc_wait_ld(v_next);
-                v_cur = v_next;
-                j = jn;
               }
               dsum[ci] += ts;
               dcnt[ci] += tn;
