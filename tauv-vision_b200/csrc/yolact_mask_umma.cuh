@@ -56,6 +56,18 @@ constexpr int kUmmaAStages = TAUV_MASK_A_STAGES;      // prototype tiles in flig
 constexpr int kUmmaStageBufs = TAUV_MASK_STAGE_BUFS;  // output staging buffers per epilogue group
 constexpr int kUmmaDepthChunks = (kUmmaNMax / 32 + kUmmaGroups - 1) / kUmmaGroups;  // 32-detection chunks per group
 constexpr int kUmmaThreads = (kUmmaEpiWarps + kUmmaProdWarps + 1) * 32;
+// The reducing kernel (fused consumer) writes nothing and is bound by its producers: twice as many of them, each
+// thread converting half of a pixel row (16 of the 32 prototype planes).
+#ifndef TAUV_DEPTH_PROD_WARPS
+#define TAUV_DEPTH_PROD_WARPS 8
+#endif
+constexpr int kUmmaDepthProdWarps = TAUV_DEPTH_PROD_WARPS;
+constexpr int kUmmaDepthThreads = (kUmmaEpiWarps + kUmmaDepthProdWarps + 1) * 32;
+template <bool kDepth>
+struct UmmaRoles {
+  static constexpr int kProd = kDepth ? kUmmaDepthProdWarps : kUmmaProdWarps;
+  static constexpr int kThreads = kDepth ? kUmmaDepthThreads : kUmmaThreads;
+};
 
 struct UmmaSmem {
   // each operand is kept as a bf16 pair (hi, lo) with hi + lo == the fp32 value to ~2^-17
@@ -174,10 +186,11 @@ __device__ __forceinline__ int frame_rows(const MaskArgs& a, int b, int m_base) 
 }
 
 template <bool kDepth>
-__global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid_constant__ MaskArgs a, int B,
+__global__ void __launch_bounds__(UmmaRoles<kDepth>::kThreads, 1) mask_umma_kernel(const __grid_constant__ MaskArgs a, int B,
                                                                     int m_base,
                                                                     const __grid_constant__ CUtensorMap out_map,
                                                                     int use_tma) {
+  constexpr int kProd = UmmaRoles<kDepth>::kProd;  // producer warps of this mode
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // (round up INSIDE the shared window: pointer arithmetic on the __shared__ array keeps the address space, an integer
   // round trip does not — the compiler then emits generic LD/ST for every shared access, which cost the epilogue ~150
@@ -198,7 +211,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
 
   if (tid == 0) {
     for (int s = 0; s < kUmmaAStages; ++s) {
-      mbar_init(&sm->a_full[s], kUmmaProdWarps * 32);
+      mbar_init(&sm->a_full[s], kProd * 32);
       mbar_init(&sm->a_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -210,7 +223,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
   }
   if (tid < kUmmaM) sm->zeros[tid] = 0.0f;
   fence_proxy_async();  // the zeros are read by the async proxy (bulk stores)
-  if (warp == kUmmaEpiWarps + kUmmaProdWarps) {  // the MMA warp owns the tensor memory
+  if (warp == kUmmaEpiWarps + kProd) {  // the MMA warp owns the tensor memory
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)),
                  "r"(512u)
                  : "memory");
@@ -476,7 +489,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
     }
     bulk_commit();
     bulk_wait<0>();  // the zero-fill stores this thread issued have completed
-  } else if (warp < kUmmaEpiWarps + kUmmaProdWarps) {
+  } else if (warp < kUmmaEpiWarps + kProd) {
     // ======================================= producers =======================================
     const int pt = tid - kUmmaEpiWarps * 32;  // producer thread index: the pixel rows of the A tile this thread converts
     uint32_t fills[kUmmaAStages] = {}, frames = 0;
@@ -497,7 +510,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
         // (which also means every MMA that read the old B has completed).
         if (frames > 0) mbar_wait(&sm->frame_done, (frames - 1) & 1u);
         const int n_pad = (n_rows + 15) & ~15;
-        for (int i = pt; i < n_pad * 4; i += kUmmaProdWarps * 32) {
+        for (int i = pt; i < n_pad * 4; i += kProd * 32) {
           const int row = i >> 2, c = i & 3;  // 16-byte chunk c of detection `row`
           uint4 qh = make_uint4(0, 0, 0, 0), ql = qh;
           if (row < n_rows) {
@@ -513,7 +526,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
           *reinterpret_cast<uint4*>(sm->b[0] + sw64_offset(row, c)) = qh;
           *reinterpret_cast<uint4*>(sm->b[1] + sw64_offset(row, c)) = ql;
         }
-        for (int row = pt; row < ((n_rows + 31) & ~31); row += kUmmaProdWarps * 32) {
+        for (int row = pt; row < ((n_rows + 31) & ~31); row += kProd * 32) {
           float4 bd = make_float4(TAUV_NEG_INF, -TAUV_NEG_INF, TAUV_NEG_INF, -TAUV_NEG_INF);  // no crop
           if (row >= n_rows) {
             bd = make_float4(-TAUV_NEG_INF, TAUV_NEG_INF, -TAUV_NEG_INF, TAUV_NEG_INF);  // padding row: empty box -> zeros
@@ -536,7 +549,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
           nt2 -= n_tiles;
           ++b2;
         }
-        for (int i = pt; i < kUmmaP * 4; i += kUmmaProdWarps * 32) {
+        for (int i = pt; i < kUmmaP * 4; i += kProd * 32) {
           const int p = i >> 2, q = i & 3;
           const int pix = nt2 * kUmmaM + q * 32;
           if (pix < HW) {
@@ -550,8 +563,27 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
         if (fills[st] > 0) mbar_wait(&sm->a_empty[st], (fills[st] - 1) & 1u);
         if (pt == 0) mask_stamp(a, u - u0, 0);
         // A tile: pixel rows pt, pt + producers, ...; 32 prototype values each -> 4 chunks of 8 bf16 (hi and lo)
+        if constexpr (kProd * 32 == 2 * kUmmaM) {
+          // two threads per pixel row: planes [16h, 16h + 16) -> chunks 2h, 2h + 1
+          const int pr = pt & (kUmmaM - 1), h = pt >> 7;
+          const int pix = nt * kUmmaM + pr;
+          const float* src = a.proto + ((size_t)b * kUmmaP + 16 * h) * HW + pix;
+          float f[16];
+#pragma unroll
+          for (int p = 0; p < 16; ++p) f[p] = pix < HW ? __ldg(src + (size_t)p * HW) : 0.0f;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint4 qh, ql;
+            split_bf16x2(f[8 * c], f[8 * c + 1], qh.x, ql.x);
+            split_bf16x2(f[8 * c + 2], f[8 * c + 3], qh.y, ql.y);
+            split_bf16x2(f[8 * c + 4], f[8 * c + 5], qh.z, ql.z);
+            split_bf16x2(f[8 * c + 6], f[8 * c + 7], qh.w, ql.w);
+            *reinterpret_cast<uint4*>(sm->a[st][0] + sw64_offset(pr, 2 * h + c)) = qh;
+            *reinterpret_cast<uint4*>(sm->a[st][1] + sw64_offset(pr, 2 * h + c)) = ql;
+          }
+        } else
 #pragma unroll 1
-        for (int pr = pt; pr < kUmmaM; pr += kUmmaProdWarps * 32) {
+        for (int pr = pt; pr < kUmmaM; pr += kProd * 32) {
           const int pix = nt * kUmmaM + pr;
           const float* src = a.proto + (size_t)b * kUmmaP * HW + pix;
           float f[kUmmaP];
@@ -617,7 +649,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) mask_umma_kernel(const __grid
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kUmmaEpiWarps + kUmmaProdWarps) {
+  if (warp == kUmmaEpiWarps + kProd) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
@@ -669,7 +701,7 @@ static int launch_mask_umma(const MaskArgs& a, int B, int max_rows, cudaStream_t
   memset(&map, 0, sizeof(map));
   const int use_tma = !depth && !getenv("TAUV_MASK_NO_TMA") && make_out_map(a, B, &map) ? 1 : 0;
   for (int m_base = 0; m_base < max_rows; m_base += kUmmaNMax) {
-    if (depth) mask_umma_kernel<true><<<(unsigned)grid, kUmmaThreads, smem, st>>>(a, B, m_base, map, 0);
+    if (depth) mask_umma_kernel<true><<<(unsigned)grid, kUmmaDepthThreads, smem, st>>>(a, B, m_base, map, 0);
     else mask_umma_kernel<false><<<(unsigned)grid, kUmmaThreads, smem, st>>>(a, B, m_base, map, use_tma);
     TAUV_LAUNCH_CHECK("mask_umma_kernel");
   }
