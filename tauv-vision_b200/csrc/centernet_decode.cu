@@ -723,6 +723,10 @@ constexpr int kClPosBase = 5632;                      // fine bins [5632, 6656):
 constexpr int kRoundW = TAUV_ROUND_W;                            // 128-bit strips per thread and round (2 x kRoundW live in registers)
 constexpr int kStreamThreads = kTileThreads - 32;     // warps 1..7 stream, warp 0 serves
 constexpr int kRoundF4 = kRoundW * kStreamThreads;    // 128-bit strips per streaming round per CTA
+#ifndef TAUV_SERVE_W
+#define TAUV_SERVE_W 1
+#endif
+constexpr int kServeW = TAUV_SERVE_W;                  // queue entries per lane and service step
 #ifndef TAUV_BOOT_W
 #define TAUV_BOOT_W 2
 #endif
@@ -975,21 +979,30 @@ __device__ __noinline__ void cl_service_warp(const TileArgs& a, int frame, cg::c
       __nanosleep(128);
       continue;
     }
-    const int n = avail < 32 ? avail : 32;
-    int2 q = make_int2(-1, 0);
-    if (lane < n) {
-      volatile int2* slot = reinterpret_cast<volatile int2*>(&hotq[(head + lane) & (kHotCap - 1)]);
-      while ((q.x = slot->x) < 0) {}  // (the producer is between its atomicAdd and its store)
-      q.y = slot->y;
-      slot->x = -1;                   // free the slot before the head moves past it
+    // up to kServeW entries per lane and step (measured: two per lane — half as many fixed costs per entry — is slower,
+    // 104.9 -> 107.0 us: new candidates reach the bins, and with them the threshold, later)
+    const int n = avail < 32 * kServeW ? avail : 32 * kServeW;
+    int2 q[kServeW];
+#pragma unroll
+    for (int w = 0; w < kServeW; ++w) {
+      q[w] = make_int2(-1, 0);
+      if (lane + 32 * w < n) {
+        volatile int2* slot = reinterpret_cast<volatile int2*>(&hotq[(head + lane + 32 * w) & (kHotCap - 1)]);
+        while ((q[w].x = slot->x) < 0) {}  // (the producer is between its atomicAdd and its store)
+        q[w].y = slot->y;
+        slot->x = -1;                      // free the slot before the head moves past it
+      }
     }
     __syncwarp();
     head += n;
     if (lane == 0) *reinterpret_cast<volatile int*>(&ctx->qhead) = head;
     int fl = 0;
-    if (lane < n) {
-      const ItemGeom g = item_geom(a, frame, q.x);
-      fl = examine<MODE, true>(a, ctx, list, g.plane, g.plane_flat0, q.y);
+#pragma unroll
+    for (int w = 0; w < kServeW; ++w) {
+      if (lane + 32 * w < n) {
+        const ItemGeom g = item_geom(a, frame, q[w].x);
+        fl |= examine<MODE, true>(a, ctx, list, g.plane, g.plane_flat0, q[w].y);
+      }
     }
     fl = __reduce_or_sync(0xffffffffu, (unsigned)fl);
     if (fl & 2) {  // the list is full: everything is redone safely at the end of the unit; keep draining the queue
