@@ -723,6 +723,10 @@ constexpr int kClPosBase = 5632;                      // fine bins [5632, 6656):
 constexpr int kRoundW = TAUV_ROUND_W;                            // 128-bit strips per thread and round (2 x kRoundW live in registers)
 constexpr int kStreamThreads = kTileThreads - 32;     // warps 1..7 stream, warp 0 serves
 constexpr int kRoundF4 = kRoundW * kStreamThreads;    // 128-bit strips per streaming round per CTA
+#ifndef TAUV_SCAN_DIV
+#define TAUV_SCAN_DIV 8
+#endif
+constexpr int kScanDiv = TAUV_SCAN_DIV;
 #ifndef TAUV_SERVE_W
 #define TAUV_SERVE_W 1
 #endif
@@ -966,7 +970,7 @@ __device__ __noinline__ void cl_service_warp(const TileArgs& a, int frame, cg::c
   ClusterCtx* const cc = cl_cc();
   unsigned long long* const list = cl_list();
   int2* const hotq = reinterpret_cast<int2*>(cl_tile(a));
-  const int every = a.k >= 8 ? a.k / 8 : 1;
+  const int every = a.k >= kScanDiv ? a.k / kScanDiv : 1;  // new candidates between two rescans of the unit's histogram
   int head = 0, since_scan = 0;
   int n_binned = ctx->n_boot;  // list[0, n_binned) are in the bins already (bootstrap survivors); -1: stop binning
   while (true) {
