@@ -50,6 +50,7 @@ def _fingerprint() -> str:
             h.update(p.name.encode())
             h.update(p.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(os.environ.get("TAUV_EXTRA_NVCC", "").encode())  # e.g. -DTAUV_DEBUG (experiment hooks, tools/*_trace.py)
     return h.hexdigest()
 
 

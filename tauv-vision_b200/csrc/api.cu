@@ -1,6 +1,10 @@
 // api.cu — library-wide plumbing: version, thread-local error text, device checks.
 #include "common.cuh"
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace tauv {
 
 char* last_error_buf() {
@@ -19,6 +23,23 @@ int num_sms() {
     return 148;
   }
   return sms;
+}
+
+// Opt a kernel in to `bytes` of dynamic shared memory.  The limit is only ever RAISED, under a lock, per (kernel,
+// device): two host threads that need different sizes can never lower it under each other between one thread's
+// cudaFuncSetAttribute and its launch.  The fast path (limit already high enough) takes the lock but makes no CUDA call.
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> limit;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = limit[std::make_pair(func, dev)];
+  if (cur >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
 }
 
 }  // namespace tauv

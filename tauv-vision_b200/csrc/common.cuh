@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/tauv_b200.h"
 
@@ -48,6 +49,15 @@ inline int cuda_fail(cudaError_t e, const char* what) {
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int num_sms();  // cached per device (api.cu)
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes);  // thread-safe, only ever raises (api.cu)
+
+// Experiment switches (environment variables) exist only in -DTAUV_DEBUG builds: the default library reads no
+// environment on the call path and keeps no mutable process state.
+#ifdef TAUV_DEBUG
+inline bool debug_env(const char* name) { return getenv(name) != nullptr; }
+#else
+inline bool debug_env(const char*) { return false; }
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // Device helpers
@@ -155,13 +165,23 @@ __device__ __forceinline__ void stg_stream4(float* p, float4 v) {
 // Block-wide exact selection of the k-th largest of n DISTINCT 64-bit keys (MSB-first radix select,
 // 11-bit digits, early exit as soon as the chosen bin is wholly needed).
 //   load(i) -> key i (any memory);   hist: 2048 uint32 in shared;   ctl: 4 uint32 in shared.
-// Returns T such that exactly min(k,n) keys are >= T.  All threads of the block must call it
-// (uses __syncthreads) and all get the same T.  NT must be a multiple of 32 and <= 1024.
+// Returns T such that exactly min(k,n) keys are >= T.  All NT threads of the group must call it
+// (it synchronises through Sync) and all get the same T.  NT must be a multiple of 32 and <= 1024.
 // ----------------------------------------------------------------------------------------------
 constexpr int kRadixBits = 11;
 constexpr int kRadixBins = 1 << kRadixBits;
 
-template <int NT, class LoadFn>
+// Barrier policy: the whole CTA (default), or a named barrier over the first NT threads of a warp-specialised CTA
+// (the other warps — e.g. a TMA producer — never take part).
+struct SyncBlock {
+  __device__ static __forceinline__ void sync() { __syncthreads(); }
+};
+template <int ID, int NT>
+struct SyncNamed {
+  __device__ static __forceinline__ void sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NT) : "memory"); }
+};
+
+template <int NT, class LoadFn, class Sync = SyncBlock>
 __device__ unsigned long long block_kth_largest(LoadFn load, int n, int k, uint32_t* hist,
                                                 uint32_t* ctl) {
   if (k >= n) return 0ull;
@@ -180,7 +200,7 @@ __device__ unsigned long long block_kth_largest(LoadFn load, int n, int k, uint3
       s_and = ~0ull;
       s_or = 0ull;
     }
-    __syncthreads();
+    Sync::sync();
     unsigned long long a = ~0ull, o = 0ull;
     for (int i = tid; i < n; i += NT) {
       const unsigned long long c = load(i);
@@ -196,7 +216,7 @@ __device__ unsigned long long block_kth_largest(LoadFn load, int n, int k, uint3
       atomicAnd(&s_and, a);
       atomicOr(&s_or, o);
     }
-    __syncthreads();
+    Sync::sync();
     const unsigned long long diff = s_and ^ s_or;
     hi = diff ? 64 - __clzll((long long)diff) : 0;  // highest differing bit + 1
     prefix = hi < 64 ? (s_or >> hi) : 0ull;
@@ -206,13 +226,13 @@ __device__ unsigned long long block_kth_largest(LoadFn load, int n, int k, uint3
     const int bits = hi >= kRadixBits ? kRadixBits : hi;
     const int lo = hi - bits;
     for (int i = tid; i < kRadixBins; i += NT) hist[i] = 0;
-    __syncthreads();
+    Sync::sync();
     for (int i = tid; i < n; i += NT) {
       unsigned long long c = load(i);
       bool match = (hi == 64) ? true : ((c >> hi) == prefix);
       if (match) atomicAdd(&hist[(uint32_t)(c >> lo) & ((1u << bits) - 1u)], 1u);
     }
-    __syncthreads();
+    Sync::sync();
     // suffix scan: thread t owns bins [t*BPT, (t+1)*BPT); find the largest bin g with
     // count(bins >= g) >= k_rem.
     uint32_t local[BPT];
@@ -233,7 +253,7 @@ __device__ unsigned long long block_kth_largest(LoadFn load, int n, int k, uint3
       if (lane + o < 32) suf += v;
     }
     if (lane == 0) warp_tot[warp] = suf;
-    __syncthreads();
+    Sync::sync();
     uint32_t above_warps = 0;
     for (int w = warp + 1; w < NT / 32; ++w) above_warps += warp_tot[w];
     suf += above_warps;                 // count in bins >= my first bin
@@ -251,13 +271,13 @@ __device__ unsigned long long block_kth_largest(LoadFn load, int n, int k, uint3
         acc += local[j];
       }
     }
-    __syncthreads();
+    Sync::sync();
     const uint32_t digit = ctl[0];
     k_rem = (int)ctl[1];
     const uint32_t pop = ctl[2];
     prefix = (hi == 64) ? (unsigned long long)digit : ((prefix << bits) | digit);
     hi = lo;
-    __syncthreads();  // ctl / hist reused next round
+    Sync::sync();  // ctl / hist reused next round
     if ((uint32_t)k_rem == pop) break;  // every key in the bin is needed
   }
   return hi == 0 ? prefix : (prefix << hi);

@@ -227,7 +227,7 @@ extern "C" int tauv_yolact_match_anchors(const float* anchor, const float* truth
   dim3 grid((N + 255) / 256, B);
   const size_t smem = (size_t)M * 8 * sizeof(float);
   if (smem > 48 * 1024)
-    TAUV_CUDA(cudaFuncSetAttribute(match_anchors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TAUV_CUDA(ensure_dynamic_smem((const void*)(match_anchors_kernel), smem));
   match_anchors_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const float4*)anchor, (const float4*)truth_box,
                                                                   truth_valid, N, M, pos_thr, neg_thr, v0, v1, match_index,
                                                                   match_iou, positive, negative, (float4*)target);

@@ -105,22 +105,25 @@ __global__ void __launch_bounds__(kSimtThreads) mask_simt_kernel(MaskArgs a) {
 
 namespace tauv {
 
-// Test hook: TAUV_MASK_SIMT=1 in the environment forces the CUDA-core kernel (read per call; no global state).
-static int want_simt_env() {
-  const char* e = getenv("TAUV_MASK_SIMT");
-  return e && e[0] == '1';
-}
+// Test hook (only in -DTAUV_DEBUG builds): TAUV_MASK_SIMT in the environment forces the CUDA-core kernel.
+static int want_simt_env() { return debug_env("TAUV_MASK_SIMT") ? 1 : 0; }
 
-static long long* g_mask_trace = nullptr;  // experiment hook (tools/mask_trace.py); not part of the public ABI
+#ifdef TAUV_DEBUG
+static long long* g_mask_trace = nullptr;  // experiment hook (tools/mask_trace.py); only in -DTAUV_DEBUG builds
+#endif
 
 static int run_mask(const MaskArgs& a_in, int B, int max_rows, int force_simt, cudaStream_t st) {
   MaskArgs a = a_in;
+#ifdef TAUV_DEBUG
   a.trace = g_mask_trace;
+#else
+  a.trace = nullptr;
+#endif
   const int HW = a.H * a.W;
   if (!force_simt && umma_shape_ok(a)) return launch_mask_umma(a, B, max_rows, st);
   const size_t smem = ((size_t)a.P * kSimtThreads + (size_t)kSimtDetChunk * a.P + kSimtDetChunk * 4) * sizeof(float);
   TAUV_REQUIRE(smem <= 227 * 1024, TAUV_E_UNSUPPORTED, "P=%d needs %zu B shared memory", a.P, smem);
-  TAUV_CUDA(cudaFuncSetAttribute(mask_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TAUV_CUDA(ensure_dynamic_smem((const void*)(mask_simt_kernel), smem));
   dim3 grid((HW + kSimtThreads - 1) / kSimtThreads, B);
   mask_simt_kernel<<<grid, kSimtThreads, smem, st>>>(a);
   TAUV_LAUNCH_CHECK("mask_simt_kernel");
@@ -274,5 +277,7 @@ extern "C" int tauv_yolact_mask_depth_batched(const float* proto, const float* c
   return run_mask_depth(a, B, top_k, depth_mm, Hi, Wi, workspace, workspace_bytes, mean, count, (cudaStream_t)stream);
 }
 
-// Debug hook for tools/mask_trace.py (process-global, not thread-safe, not in the public header).
+#ifdef TAUV_DEBUG
+// Debug hook for tools/mask_trace.py (only in -DTAUV_DEBUG builds; process-global, not thread-safe).
 extern "C" void tauv_debug_mask_trace(long long* buf) { tauv::g_mask_trace = buf; }
+#endif

@@ -691,15 +691,14 @@ static bool make_out_map(const MaskArgs& a, int B, CUtensorMap* map) {
 static int launch_mask_umma(const MaskArgs& a, int B, int max_rows, cudaStream_t st) {
   const size_t smem = sizeof(UmmaSmem) + 1024;
   const bool depth = a.acc != nullptr;
-  TAUV_CUDA(cudaFuncSetAttribute(depth ? mask_umma_kernel<true> : mask_umma_kernel<false>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TAUV_CUDA(ensure_dynamic_smem((const void*)(depth ? mask_umma_kernel<true> : mask_umma_kernel<false>), smem));
   const int HW = a.H * a.W;
   const long long units = (long long)B * ((HW + kUmmaM - 1) / kUmmaM);
   long long grid = num_sms();
   if (grid > units) grid = units;
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
-  const int use_tma = !depth && !getenv("TAUV_MASK_NO_TMA") && make_out_map(a, B, &map) ? 1 : 0;
+  const int use_tma = !depth && !debug_env("TAUV_MASK_NO_TMA") && make_out_map(a, B, &map) ? 1 : 0;
   for (int m_base = 0; m_base < max_rows; m_base += kUmmaNMax) {
     if (depth) mask_umma_kernel<true><<<(unsigned)grid, kUmmaDepthThreads, smem, st>>>(a, B, m_base, map, 0);
     else mask_umma_kernel<false><<<(unsigned)grid, kUmmaThreads, smem, st>>>(a, B, m_base, map, use_tma);

@@ -476,7 +476,7 @@ __global__ void keep_class_kernel(const float* __restrict__ cls, const int64_t* 
 }
 
 static int launch_scores(const float* cls, long long rows, int C1, float* score, int32_t* argmax_all, cudaStream_t st) {
-  if (C1 <= 256 && !getenv("TAUV_SCORES_OLD")) {
+  if (C1 <= 256 && !debug_env("TAUV_SCORES_OLD")) {
     const int stride = C1 | 1;
     const size_t smem = (size_t)kScoreTileWarps * 32 * stride * 4;
     long long blocks = (rows + 32 * kScoreTileWarps - 1) / (32 * kScoreTileWarps);
@@ -484,10 +484,10 @@ static int launch_scores(const float* cls, long long rows, int C1, float* score,
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     if (argmax_all) {
-      TAUV_CUDA(cudaFuncSetAttribute(scores_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TAUV_CUDA(ensure_dynamic_smem((const void*)(scores_tile_kernel<true>), smem));
       scores_tile_kernel<true><<<(unsigned)blocks, kScoreTileWarps * 32, smem, st>>>(cls, rows, C1, stride, score, argmax_all);
     } else {
-      TAUV_CUDA(cudaFuncSetAttribute(scores_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TAUV_CUDA(ensure_dynamic_smem((const void*)(scores_tile_kernel<false>), smem));
       scores_tile_kernel<false><<<(unsigned)blocks, kScoreTileWarps * 32, smem, st>>>(cls, rows, C1, stride, score, argmax_all);
     }
     TAUV_LAUNCH_CHECK("scores_tile_kernel");
@@ -548,7 +548,7 @@ static int run_nms(const float* cls, const float* box, const float* enc, const f
   }
   a.keep = keep; a.n_keep = n_keep; a.keep_box = (float4*)keep_box; a.keep_score = keep_score;
   const size_t smem = nms_smem(top_k < N ? top_k : N);
-  TAUV_CUDA(cudaFuncSetAttribute(nms_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TAUV_CUDA(ensure_dynamic_smem((const void*)(nms_frame_kernel), smem));
   nms_frame_kernel<<<n_frames, kNmsThreads, smem, st>>>(a);
   TAUV_LAUNCH_CHECK("nms_frame_kernel");
   if (keep_class) {

@@ -19,21 +19,21 @@ def _boxes(t: torch.Tensor) -> torch.Tensor:
 
 
 def box_xy_swap(box: torch.Tensor) -> torch.Tensor:
-    """(y,x,h,w) <-> (x,y,w,h); pure layout, used by datasets/plots in the reference."""
-    _lib.require_cuda(box)
+    """(y,x,h,w) <-> (x,y,w,h); pure layout, any device: the reference's data loader, collate and plots call it
+    on CPU tensors (datasets/segmentation_dataset/segmentation_dataset.py:119, yolact/scripts/train.py:143-145,
+    utils/plot.py:49,65) — there is no kernel behind it, so nothing here insists on CUDA."""
     return box[:, :, [1, 0, 3, 2]]
 
 
 def box_to_corners(box: torch.Tensor) -> torch.Tensor:
     """(y,x,h,w) -> (min_y,min_x,max_y,max_x).  Layout helper off the hot path (the kernels form corners
-    in registers); kept as a thin torch expression with the reference's operation order."""
-    _lib.require_cuda(box)
+    in registers); kept as a thin torch expression with the reference's operation order, on any device."""
     half = box[:, :, 2:] / 2
     return torch.cat((box[:, :, :2] - half, box[:, :, :2] + half), dim=-1)
 
 
 def corners_to_box(corners: torch.Tensor) -> torch.Tensor:
-    _lib.require_cuda(corners)
+    """(min_y,min_x,max_y,max_x) -> (y,x,h,w); layout helper, any device (boxes.py:30-42)."""
     return torch.cat(((corners[:, :, :2] + corners[:, :, 2:]) / 2, corners[:, :, 2:] - corners[:, :, :2]), dim=-1)
 
 

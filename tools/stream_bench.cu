@@ -1,0 +1,150 @@
+// Micro-benchmark (round 2): read-only streaming ceiling of a B200 for the CenterNet decode shape (335 MB).
+//   ring : warp-specialised cp.async.bulk ring — one producer thread, NCW consumer warps, full/empty mbarriers per
+//          stage, no block barrier.  Sweep chunk size, ring depth, CTAs per SM, and the chunk->CTA map
+//          (interleaved: chunk c -> CTA c % grid; contiguous: CTA i owns chunks [i*n/grid, (i+1)*n/grid)).
+//   ldg  : plain 128-bit ld.global.nc loads (the round-1 structure), for reference.
+// Build on the box: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/stream_bench tools/stream_bench.cu
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdint.h>
+#include <vector>
+#include <algorithm>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(c)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t b) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(b) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* d, const void* s, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(d)), "l"(s), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ uint64_t policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ void bulk_g2s_hint(void* d, const void* s, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(d)), "l"(s), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
+// NCW consumer warps + 1 producer warp.  mode 0: interleaved chunks, 1: contiguous per CTA.
+template <int NCW, bool HINT = false>
+__global__ void __launch_bounds__(NCW * 32 + 32) ring_ws_kernel(const float* __restrict__ in, long long n_chunks, int chunk_floats, int stages, int mode, float thr, int* out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* ring = (float*)smem;
+  uint64_t* full = (uint64_t*)(smem + (size_t)stages * chunk_floats * 4);
+  uint64_t* empty = full + stages;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  long long c0, c1, step;
+  if (mode == 0) { c0 = blockIdx.x; c1 = n_chunks; step = gridDim.x; }
+  else { c0 = n_chunks * blockIdx.x / gridDim.x; c1 = n_chunks * (blockIdx.x + 1) / gridDim.x; step = 1; }
+  if (warp == NCW) {
+    if (lane == 0) {
+      int slot = 0; uint32_t phase = 0;
+      const uint64_t pol = policy_evict_first();
+      for (long long c = c0; c < c1; c += step) {
+        mbar_wait(&empty[slot], phase ^ 1);
+        mbar_expect_tx(&full[slot], chunk_floats * 4);
+        if (HINT) bulk_g2s_hint(ring + (size_t)slot * chunk_floats, in + c * chunk_floats, chunk_floats * 4, &full[slot], pol);
+        else bulk_g2s(ring + (size_t)slot * chunk_floats, in + c * chunk_floats, chunk_floats * 4, &full[slot]);
+        if (++slot == stages) { slot = 0; phase ^= 1; }
+      }
+    }
+    return;
+  }
+  int slot = 0; uint32_t phase = 0; int hits = 0;
+  for (long long c = c0; c < c1; c += step) {
+    mbar_wait(&full[slot], phase);
+    const float4* p4 = (const float4*)(ring + (size_t)slot * chunk_floats);
+#pragma unroll 4
+    for (int t = tid; t < chunk_floats / 4; t += NCW * 32) { float4 x = p4[t]; if (fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)) >= thr) ++hits; }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[slot]);
+    if (++slot == stages) { slot = 0; phase ^= 1; }
+  }
+  if (hits) atomicAdd(out, hits);
+}
+
+template <int NT, int U>
+__global__ void __launch_bounds__(NT) ldg_hint_kernel(const float4* __restrict__ in, long long n4, float thr, int* out) {
+  int hits = 0;
+  const uint64_t pol = policy_evict_first();
+  const long long stride = (long long)gridDim.x * NT;
+  long long i = blockIdx.x * (long long)NT + threadIdx.x;
+  for (; i + (U - 1) * stride < n4; i += U * stride) {
+    float4 x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w) : "l"(in + i + u * stride), "l"(pol));
+#pragma unroll
+    for (int u = 0; u < U; ++u) if (fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w)) >= thr) ++hits;
+  }
+  for (; i < n4; i += stride) { float4 x = in[i]; if (fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)) >= thr) ++hits; }
+  if (hits) atomicAdd(out, hits);
+}
+
+template <int NT, int U>
+__global__ void __launch_bounds__(NT) ldg_kernel(const float4* __restrict__ in, long long n4, float thr, int* out) {
+  int hits = 0;
+  const long long stride = (long long)gridDim.x * NT;
+  long long i = blockIdx.x * (long long)NT + threadIdx.x;
+  for (; i + (U - 1) * stride < n4; i += U * stride) {
+    float4 x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w) : "l"(in + i + u * stride));
+#pragma unroll
+    for (int u = 0; u < U; ++u) if (fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w)) >= thr) ++hits;
+  }
+  for (; i < n4; i += stride) { float4 x = in[i]; if (fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)) >= thr) ++hits; }
+  if (hits) atomicAdd(out, hits);
+}
+
+__global__ void empty_kernel(int* out) { if (threadIdx.x == 9999) *out = 1; }
+
+int main() {
+  const long long n = 64LL * 80 * 128 * 128;
+  float* d; int* out; float* flush;
+  cudaMalloc(&d, n * 4); cudaMalloc(&out, 4); cudaMalloc(&flush, 512 << 20);
+  cudaMemset(d, 0, n * 4); cudaMemset(out, 0, 4);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  auto timeit = [&](auto launch, const char* name, bool dirty) {
+    std::vector<float> ts;
+    for (int r = 0; r < 9; ++r) {
+      // dirty: the previous kernel wrote 512 MB (L2 full of dirty lines, like the encode before the decode);
+      // clean: the previous kernel only read
+      if (dirty) cudaMemsetAsync(flush, r, 512 << 20);
+      else ldg_kernel<256, 4><<<148 * 8, 256>>>((const float4*)flush, (512 << 20) / 16, 1e30f, out);
+      cudaEventRecord(e0); launch(); cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1); ts.push_back(ms);
+    }
+    cudaError_t e = cudaGetLastError(); std::sort(ts.begin(), ts.end());
+    printf("%-64s %s min %7.1f med %7.1f us  %6.0f GB/s (med) %s\n", name, dirty ? "dirtyL2" : "cleanL2", ts[0] * 1e3, ts[4] * 1e3, n * 4 / (ts[4] * 1e-3) / 1e9, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    fflush(stdout);
+  };
+  int sms = 148;
+  timeit([&]() { empty_kernel<<<148, 256>>>(out); }, "empty kernel (launch floor)", false);
+  for (int dirty = 0; dirty < 2; ++dirty) {
+    for (int hint = 0; hint < 2; ++hint)
+      for (int mode = 0; mode < 2; ++mode)
+        for (int cfg = 0; cfg < 5; ++cfg) {
+          const int chunk_kbs[5] = {32, 16, 16, 8, 32}, stgs[5] = {4, 8, 4, 8, 3}, per[5] = {1, 1, 2, 2, 2};
+          int chunk_kb = chunk_kbs[cfg], stages = stgs[cfg], per_sm = per[cfg];
+          int chunk_floats = chunk_kb * 256; size_t smem = (size_t)stages * chunk_kb * 1024 + stages * 16 + 64;
+          long long n_chunks = n / chunk_floats;
+          cudaFuncSetAttribute(ring_ws_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          cudaFuncSetAttribute(ring_ws_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          char name[160];
+          snprintf(name, 160, "ring8w %s %s chunk=%2dKB stages=%2d ctas/sm=%d (%3d KB/SM)", hint ? "evict1st" : "nohint  ", mode ? "contig" : "inter ", chunk_kb, stages, per_sm, stages * chunk_kb * per_sm);
+          if (hint) timeit([&]() { ring_ws_kernel<8, true><<<per_sm * sms, 288, smem>>>(d, n_chunks, chunk_floats, stages, mode, 1.0f, out); }, name, dirty);
+          else timeit([&]() { ring_ws_kernel<8, false><<<per_sm * sms, 288, smem>>>(d, n_chunks, chunk_floats, stages, mode, 1.0f, out); }, name, dirty);
+        }
+    timeit([&]() { ldg_kernel<256, 4><<<sms * 8, 256>>>((const float4*)d, n / 4, 1.0f, out); }, "ldg        256thr U=4 grid=8/SM", dirty);
+    timeit([&]() { ldg_hint_kernel<256, 4><<<sms * 8, 256>>>((const float4*)d, n / 4, 1.0f, out); }, "ldg evict1 256thr U=4 grid=8/SM", dirty);
+    timeit([&]() { ldg_kernel<256, 4><<<sms * 32, 256>>>((const float4*)d, n / 4, 1.0f, out); }, "ldg        256thr U=4 grid=32/SM", dirty);
+    timeit([&]() { ldg_hint_kernel<256, 4><<<sms * 32, 256>>>((const float4*)d, n / 4, 1.0f, out); }, "ldg evict1 256thr U=4 grid=32/SM", dirty);
+  }
+  return 0;
+}
