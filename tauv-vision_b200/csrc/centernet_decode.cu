@@ -916,12 +916,16 @@ static bool stream_shape_ok(const void* hm, int C, int H, int W, int k) {
 
 static void make_stream_plan(int B, int C, int H, int W, int k, StreamPlan* p) {
   const long long R = (long long)B * C * H;
-  // chunk: the largest power-of-two number of rows within 32 KB (measured: 4 x 32 KB per SM in flight streams at the
-  // rate of 8 x 16 KB and needs half the barrier traffic); ring: 4 slots
-  int cr = 1;
-  while ((size_t)cr * 2 * W * 4 <= 32768) cr *= 2;
+  // chunk: whole rows, about 16 KB (one filter iteration of the 16 warps); ring: as many chunks as fit beside the
+  // candidate lists (measured, profiles/r2_stream_bench_v*.txt: ~100 KB per SM in flight keeps HBM busy; a slot is only
+  // released one chunk late because the 3x3 test of a chunk's last row needs the next chunk's first)
+  int cr = 16384 / (W * 4);
+  if (cr < 1) cr = 1;
   p->chunk_rows = cr;
-  p->stages = 4;
+  const size_t fixed = sd_smem_bytes(0, 0, W);
+  int st = (int)((227 * 1024 - fixed) / ((size_t)cr * W * 4));
+  if (st > 12) st = 12;
+  p->stages = st;
   long long G = num_sms();          // one CTA per SM (the ring takes most of the shared memory)
   const long long min_rows = 8;     // tiny inputs: fewer CTAs rather than CTAs without rows
   if (G > R / min_rows) G = R / min_rows;
@@ -961,6 +965,10 @@ static int run_stream(const float* hm, int B, int C, int H, int W, int k, int mo
   a.rows_total = (long long)B * C * H;
   a.rows_frame = C * H;
   a.chunk_rows = p.chunk_rows; a.stages = p.stages;
+  {
+    const SdLayout l = sd_layout(p.chunk_rows, p.stages, W);
+    a.off_list = l.off_list; a.off_bins = l.off_bins; a.off_flags = l.off_flags; a.off_bars = l.off_bars; a.off_ctx = l.off_ctx;
+  }
   a.tbl_rows = p.tbl_rows; a.row_cap = p.row_cap;
   unsigned char* w = reinterpret_cast<unsigned char*>(ws);
   a.cand = reinterpret_cast<unsigned long long*>(w);

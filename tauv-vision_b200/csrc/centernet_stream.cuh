@@ -6,42 +6,59 @@
 //   :204-234 per-detection gather + box arithmetic (:87-88 / :65 for decode_keypoints).
 //
 // Why this shape (measured, profiles/r2_stream_bench_v*.txt): a B200 streams a read-once 335 MB tensor at
-// 6.2-6.4 TB/s through a cp.async.bulk (1-D TMA) shared-memory ring with one CTA per SM and 96-128 KB per SM in
+// 6.2-6.4 TB/s through a cp.async.bulk (1-D TMA) shared-memory ring with one CTA per SM and ~100 KB per SM in
 // flight — as fast as register loads, but the bytes in flight do not depend on what the consuming warps are doing,
 // the 3x3 neighbourhood of every cell is already in shared memory (no re-reads: DRAM traffic = algorithmic bytes),
 // and an L2 evict-first policy on the copies keeps the previous kernel's dirty lines from stalling the stream.
 //
-// Work split: the B*C*H rows of the batch are cut into G equal contiguous ranges, one per CTA (G = SMs x CTAs/SM):
-// every SM moves the same number of bytes whatever B is.  A range crosses at most a few frame boundaries; the part
-// of a range inside one frame is a RUN.  Per run the CTA keeps, in shared memory, a candidate list (64-bit composite
-// keys: score key << 32 | ~flat index, so plain descending order = score desc, index asc — the order the reference's
-// own KAT asserts, decode.py:327-339), a 2048-bin histogram of the candidates' logits, and a rejection threshold
-// derived from it (the k-th best candidate so far bounds the frame's k-th best from below).  Cells below the
-// threshold cost one max + compare per 128-bit strip; only strips that pass get the 3x3 test.  At the end of a run
-// the survivors (k + a handful) go to a small global table; the CTA that completes a frame's last run (an epoch-stamped
-// ticket per frame: no memset, no second launch) merges the frame's rows, ranks them, gathers size/offset/depth
-// through the strided views and writes the packed outputs.
+// Work split: the B*C*H rows of the batch are cut into G equal contiguous ranges, one per CTA (G = SMs): every SM
+// moves the same number of bytes whatever B is.  A range crosses at most a few frame boundaries; the part of a range
+// inside one frame is a RUN.
+//
+// Roles inside a CTA (18 warps):
+//   * producer (1 lane): keeps the ring of 4 x 32 KB chunks full; a slot is refilled when all filter warps released it.
+//   * 16 filter warps, INDEPENDENT of each other in steady state (no block barrier, no shared counters with return
+//     values): each takes every 16th group of 32 consecutive 128-bit strips of a chunk, compares the strip maximum
+//     with the run's rejection threshold (a handful of instructions per strip), and only for strips that pass runs
+//     the 3x3 test, evaluates the sigmoid of the peaks and appends their 64-bit composite keys (score key << 32 |
+//     ~flat index: plain descending order = score desc, index asc — the order the reference's own KAT asserts,
+//     decode.py:327-339) to the warp's PRIVATE sub-list; the peaks' logits are counted in a shared 2048-bin histogram
+//     with fire-and-forget shared-memory reductions.  (The first version of this kernel had 8 warps share one list
+//     and meet at four block barriers per chunk: every step was a chain of dependent instructions at ~5 cycles each
+//     with two warps per scheduler, 4.9 us per 32 KB chunk instead of the 0.73 us the HBM stream allows.)
+//   * manager warp: whenever enough new candidates were counted, rescans the histogram for the bin that holds the
+//     k-th best candidate of the run so far and raises the rejection threshold (the k-th best candidate so far bounds
+//     the frame's k-th best from below) — asynchronously, nobody waits for it.
+// At the end of a run the survivors (k + a handful) go to a small global table; the CTA that completes a frame's last
+// run (an epoch-stamped ticket per frame: no memset, no second launch) merges the frame's rows, sorts them, gathers
+// size/offset/depth through the strided views and writes the packed outputs.
 //
 // Exactness under ties: everything that decides order is done on the final keys (the sigmoid VALUES, like the
 // reference).  The cheap filter works on logits with a guard band (reject_key_for_score) so that it never rejects a
-// logit whose sigmoid could tie with the k-th score.  If the list overflows (plateaus, no usable threshold) the run
-// switches to a safe mode: sub-steps that cannot overflow, exact pruning to the top-k by radix select, and an exact
-// 64-bit composite threshold, so that an all-equal map costs time but never correctness.
+// logit whose sigmoid could tie with the k-th score.  A sub-list that fills up (plateaus, no usable threshold) is
+// pruned by its own warp — first below the histogram's floor, then exactly to its top-k by a bitwise search, which
+// also gives the warp an exact 64-bit composite threshold — so an all-equal map costs time but never correctness.
 #pragma once
 
 namespace tauv {
 
-constexpr int kSdCW = 8;                  // consumer warps
-constexpr int kSdNC = kSdCW * 32;         // consumer threads (threadIdx.x < kSdNC)
-constexpr int kSdThreads = kSdNC + 32;    // + one producer warp (one lane issues the bulk copies)
-constexpr int kSdCap = 4096;              // candidate-list capacity (entries)
-constexpr int kSdSoft = 2048;             // prune when the list grows beyond this
-constexpr int kSdMaxK = 1024;
+constexpr int kSdFW = 16;                      // filter warps
+constexpr int kSdNF = kSdFW * 32;              // filter threads (threadIdx.x < kSdNF)
+constexpr int kSdMgrWarp = kSdFW;              // warp 16: threshold manager
+constexpr int kSdProdWarp = kSdFW + 1;         // warp 17: one lane issues the bulk copies
+constexpr int kSdNA = (kSdFW + 1) * 32;        // filter + manager threads (joint barriers)
+constexpr int kSdThreads = (kSdFW + 2) * 32;
+constexpr int kSdListCap = 8192;               // candidate entries in shared memory, all sub-lists together
+constexpr int kSdSub = kSdListCap / kSdFW;     // private sub-list of a filter warp (512 entries)
+constexpr int kSdMaxK = kSdSub / 2;            // a warp can always prune its own sub-list to k and have room again
 constexpr int kSdMaxW = 1024;
-constexpr int kSdSlice = kSdCap / kSdNC;  // list entries per thread in a compaction
-constexpr int kSdMaxStages = 8;
+constexpr int kSdMaxStages = 16;
+constexpr int kSdU = 2;                        // 128-bit strips per thread and filter iteration
 
-using SdSync = SyncNamed<1, kSdNC>;       // named barrier over the consumer warps; the producer never joins
+using SdSyncAll = SyncNamed<1, kSdNA>;         // filter warps + manager
+using SdSyncF = SyncNamed<2, kSdNF>;           // filter warps only
+__device__ __forceinline__ void sd_sync_all() { SdSyncAll::sync(); }
+__device__ __forceinline__ void sd_sync_f() { SdSyncF::sync(); }
 
 struct SdArgs {
   const float* hm;
@@ -49,7 +66,8 @@ struct SdArgs {
   int G;                  // CTAs (every one owns rows [i*R/G, (i+1)*R/G))
   long long rows_total;   // R = B*C*H
   int rows_frame;         // C*H
-  int chunk_rows, stages; // rows per bulk copy (power of two), ring slots (power of two)
+  int chunk_rows, stages; // rows per bulk copy, ring slots
+  int off_list, off_bins, off_flags, off_bars, off_ctx;  // byte offsets of the shared-memory regions (host-computed)
   int tbl_rows, row_cap;  // candidate table: rows per frame, entries per row (2k)
   unsigned long long* cand;    // [B][tbl_rows][row_cap]
   int* cand_count;             // [B][tbl_rows]
@@ -62,221 +80,363 @@ struct SdArgs {
 };
 
 struct __align__(16) SdCtx {
-  unsigned long long T;     // exact composite threshold (0: none): entries <= T cannot be in the frame's top-k
-  unsigned long long keyT;  // scratch: broadcast of a prune threshold
-  long long load_row0;      // global row held at stream position 0
-  long long frame_row0;     // global row of the current frame's first row
-  float thr_f;              // cheap filter in logit (SIGMOID_PEAK) / value (RAW) space; -inf: none
-  int count;                // list entries
-  int flags;                // bit 1: a push found the list full
-  uint32_t maxbin;          // highest occupied window bin
-  int safe;                 // 1: overflow happened in this run; the bins are no longer trusted
-  int last_scan;            // list length at the last histogram scan
-  int found_bin;            // result of the last scan (-1: fewer than k binned)
-  int base;                 // scratch for compactions
+  unsigned long long floor_key;  // lowest final key that can still matter according to the histogram (0: none yet)
+  unsigned long long warpT[kSdFW]; // exact composite threshold of a filter warp (0: none): later entries <= T cannot matter
+  long long load_row0;           // global row held at stream position 0
+  long long frame_row0;          // global row of the current frame's first row
+  uint32_t thr_key;              // cheap filter: order-preserving key of a logit (SIGMOID_PEAK) / value (RAW); 0: none
+  uint32_t maxbin;               // highest occupied window bin
+  uint32_t pushed;               // candidates counted in the bins so far (this run)
+  int req;                       // run-end request: ordinal + 1 of the run the filter warps have finished
   int is_last;
   int total;
   int nge;
-  int wsum[kSdCW];
+  int base;
+  int wsum[kSdFW];
   uint32_t sel[8];
+  int scratch[kSdFW][32];        // per filter warp: strip indices of an iteration's hot strips, packed
 };
-
-__device__ __forceinline__ void sd_sync() { SdSync::sync(); }
 
 __device__ __forceinline__ uint64_t sd_policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
-__device__ __forceinline__ void sd_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+__device__ __forceinline__ void sd_bulk_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar,
                                             uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(dst_smem)),
-      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+      "l"(src_gmem), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void sd_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void sd_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity), "r"(100000u)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t sd_lds_u32_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 sd_lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float sd_lds1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
 
-// Shared-memory carve-up (dynamic): ring | list | bins | radix histogram | flags | mbarriers | ctx
-struct SdSmem {
-  float* ring;
-  unsigned long long* list;
-  uint32_t* bins;
-  uint32_t* hist;
-  uint32_t* flags;  // [kSdMaxK]
-  uint64_t* full;
-  uint64_t* empty;
-  SdCtx* ctx;
+// Shared-memory carve-up (dynamic): ring | sub-lists | bins (= radix histogram once a run's bins are dead) | flags |
+// mbarriers | ctx.  The host computes the byte offsets (SdArgs::off_*) so that device code reaches a region with one
+// constant-bank load and an add; a struct of pointers handed around by reference would live in local memory.
+struct SdLayout {
+  int off_list, off_bins, off_flags, off_bars, off_ctx;
+  size_t total;
 };
-__host__ __device__ inline size_t sd_smem_bytes(int chunk_rows, int stages, int W) {
-  return (size_t)stages * chunk_rows * W * 4 + (size_t)kSdCap * 8 + (size_t)kClBins * 4 + (size_t)kRadixBins * 4 +
-         (size_t)kSdMaxK * 4 + 2 * kSdMaxStages * 8 + sizeof(SdCtx) + 128;
+__host__ __device__ inline SdLayout sd_layout(int chunk_rows, int stages, int W) {
+  SdLayout l;
+  size_t o = (size_t)stages * chunk_rows * W * 4;
+  l.off_list = (int)o;
+  o += (size_t)kSdListCap * 8;
+  l.off_bins = (int)o;
+  o += (size_t)kClBins * 4;
+  l.off_flags = (int)o;
+  o += (size_t)kSdMaxK * 4;
+  l.off_bars = (int)o;
+  o += 2 * kSdMaxStages * 8;
+  l.off_ctx = (int)o;
+  o += sizeof(SdCtx);
+  l.total = o + 128;
+  return l;
 }
-__device__ __forceinline__ SdSmem sd_carve(const SdArgs& a) {
+__host__ __device__ inline size_t sd_smem_bytes(int chunk_rows, int stages, int W) { return sd_layout(chunk_rows, stages, W).total; }
+__device__ __forceinline__ unsigned char* sd_smem() {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  SdSmem s;
-  unsigned char* p = smem_raw;
-  s.ring = reinterpret_cast<float*>(p);
-  p += (size_t)a.stages * a.chunk_rows * a.W * 4;
-  s.list = reinterpret_cast<unsigned long long*>(p);
-  p += (size_t)kSdCap * 8;
-  s.bins = reinterpret_cast<uint32_t*>(p);
-  p += (size_t)kClBins * 4;
-  s.hist = reinterpret_cast<uint32_t*>(p);
-  p += (size_t)kRadixBins * 4;
-  s.flags = reinterpret_cast<uint32_t*>(p);
-  p += (size_t)kSdMaxK * 4;
-  s.full = reinterpret_cast<uint64_t*>(p);
-  s.empty = s.full + kSdMaxStages;
-  p += 2 * kSdMaxStages * 8;
-  s.ctx = reinterpret_cast<SdCtx*>(p);
-  return s;
+  return smem_raw;
+}
+__device__ __forceinline__ float* sd_ring() { return reinterpret_cast<float*>(sd_smem()); }
+__device__ __forceinline__ unsigned long long* sd_list(const SdArgs& a) { return reinterpret_cast<unsigned long long*>(sd_smem() + a.off_list); }
+__device__ __forceinline__ uint32_t* sd_bins(const SdArgs& a) { return reinterpret_cast<uint32_t*>(sd_smem() + a.off_bins); }
+__device__ __forceinline__ uint32_t* sd_flags(const SdArgs& a) { return reinterpret_cast<uint32_t*>(sd_smem() + a.off_flags); }
+__device__ __forceinline__ uint64_t* sd_full(const SdArgs& a) { return reinterpret_cast<uint64_t*>(sd_smem() + a.off_bars); }
+__device__ __forceinline__ uint64_t* sd_empty(const SdArgs& a) { return sd_full(a) + kSdMaxStages; }
+__device__ __forceinline__ SdCtx* sd_ctx(const SdArgs& a) { return reinterpret_cast<SdCtx*>(sd_smem() + a.off_ctx); }
+
+// Lowest FINAL key that a candidate counted in window bin `bin` or above can have (composite with index bits 0).
+template <int MODE>
+__device__ __forceinline__ unsigned long long sd_bin_floor(int bin) {
+  const float edge = cl_window_edge(bin);
+  // SIGMOID_PEAK: the bins count logits, the lists hold their sigmoids, whose last-bit wobble the guard band covers
+  const float lowest = MODE == TAUV_TOPK_SIGMOID_PEAK ? sigmoid_ref(edge) * (1.0f - 4e-5f) : edge;
+  const unsigned long long kt = (unsigned long long)float_to_key(lowest) << 32;
+  return kt == 0ull ? 1ull : kt;
 }
 
-// ---- candidates ----------------------------------------------------------------------------------------------------
-// x: logit (SIGMOID_PEAK, already known to be a 3x3 peak) or value (RAW); flat: index inside the frame.
-template <int MODE>
-__device__ __forceinline__ void sd_push(const SdSmem& sm, float x, uint32_t flat) {
-  SdCtx* const ctx = sm.ctx;
-  uint32_t key;
-  if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
-    const float s = sigmoid_ref(x);
-    if (!(s > 0.0f)) return;  // underflowed to 0: zero-valued cells are supplied by the filler, like non-peaks
-    key = float_to_key(s);
-  } else {
-    key = float_to_key(x);
-  }
-  const unsigned long long c = make_composite(key, flat);
-  if (c <= ctx->T) return;
-  // one shared-memory atomic per warp instruction (same-address atomics serialise)
-  const unsigned active = __activemask();
+// ---- a filter warp's own list housekeeping (warp-convergent) ----------------------------------------------------------
+// In-place compaction of the warp's sub-list by a predicate (single warp, in order: writes never pass unread entries).
+template <class Keep>
+__device__ __forceinline__ int sd_warp_compact(unsigned long long* sub, int n, Keep keep) {
   const int lane = threadIdx.x & 31;
-  const int leader = __ffs(active) - 1;
-  int base = 0;
-  if (lane == leader) base = atomicAdd(&ctx->count, __popc(active));
-  base = __shfl_sync(active, base, leader);
-  const int slot = base + __popc(active & ((1u << lane) - 1u));
-  if (slot >= kSdCap) {
-    ctx->flags = 2;
-    return;
+  int out = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    unsigned long long c = 0ull;
+    if (i < n) c = sub[i];
+    const bool kp = (i < n) && keep(c);
+    const unsigned bal = __ballot_sync(0xffffffffu, kp);
+    __syncwarp();
+    if (kp) sub[out + __popc(bal & ((1u << lane) - 1u))] = c;
+    out += __popc(bal);
+    __syncwarp();
   }
-  sm.list[slot] = c;
-  if (!ctx->safe) {
-    if (MODE == TAUV_TOPK_SIGMOID_PEAK && !(x > -80.0f)) return;
-    const int bin = cl_window_bin(float_to_key(x));
-    if (bin < 0) return;
-    atomicAdd(&sm.bins[bin], 1u);
-    if ((uint32_t)bin > *reinterpret_cast<volatile uint32_t*>(&ctx->maxbin)) atomicMax(&ctx->maxbin, (uint32_t)bin);
-  }
+  return out;
 }
 
-// Full test of one 128-bit strip that passed the threshold scan: stream position p (row), column col, values x.
-// The rows above and below come from the ring (the halo row of a range is loaded with it); rows outside the plane
-// do not exist (-inf padding, decode.py:245-250).
+// The sub-list is (nearly) full.  First drop what the histogram already rules out; if that does not free half of the
+// list, prune exactly to the warp's own top-k (the frame's top-k is a subset of the union of the warps' top-k's) by a
+// bitwise search for the k-th largest key, which also becomes this warp's exact push threshold.  Returns the new length.
 template <int MODE>
-__device__ __noinline__ void sd_examine(const SdArgs& a, const SdSmem& sm, int ring_mask, int p, int col, float4 x,
-                                        float thr_f) {
-  const SdCtx* const ctx = sm.ctx;
+__device__ __noinline__ int sd_warp_prune(const SdArgs& a, int cnt) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  SdCtx* const ctx = sd_ctx(a);
+  unsigned long long* sub = sd_list(a) + (size_t)warp * kSdSub;
+  const unsigned long long fl = *reinterpret_cast<volatile unsigned long long*>(&ctx->floor_key);
+  if (fl > 1ull) cnt = sd_warp_compact(sub, cnt, [&](unsigned long long c) { return c >= fl; });
+  if (cnt <= kSdSub / 2) return cnt;
+  // k-th largest of cnt (> kSdSub/2 >= k) distinct keys, one bit at a time from the top
+  unsigned long long T = 0ull;
+  for (int bit = 63; bit >= 0; --bit) {
+    const unsigned long long cand = T | (1ull << bit);
+    int n = 0;
+    for (int i = lane; i < cnt; i += 32) n += (sub[i] >= cand) ? 1 : 0;
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (n >= a.k) T = cand;
+  }
+  cnt = sd_warp_compact(sub, cnt, [&](unsigned long long c) { return c >= T; });
+  if (lane == 0) {
+    ctx->warpT[warp] = T;  // (T itself is in the list; keys are distinct, so nothing equal can come again)
+    // raise the shared cheap filter from this warp's k-th score
+    uint32_t key = 0;
+    if (MODE == TAUV_TOPK_SIGMOID_PEAK) key = reject_key_for_score(key_to_float(composite_key(T)));
+    else key = composite_key(T);
+    if (key) atomicMax(&ctx->thr_key, key);
+  }
+  __syncwarp();
+  return cnt;
+}
+
+// Full test of up to 32 strips that passed the threshold scan, one per lane (`mine`: this lane has one: stream row p,
+// column col), then the pushes.  Warp-convergent.  The rows above and below come from the ring (the halo rows of a
+// range are loaded with it); rows outside the plane do not exist (-inf padding, decode.py:245-250).  Peaks at or
+// above the threshold get their sigmoid, a composite key, a slot in the warp's private sub-list and a count in the
+// shared histogram (fire-and-forget shared-memory reductions).  Returns the sub-list's new length.
+template <int MODE>
+__device__ __noinline__ int sd_examine(const SdArgs& a, uint32_t ring_u32, int ring_rows, bool mine, int p, int rp, int col,
+                                       float thr_f, int cnt) {
+  SdCtx* const ctx = sd_ctx(a);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int W = a.W;
-  const int fr = (int)(ctx->load_row0 + p - ctx->frame_row0);  // row inside the frame
-  const uint32_t flat = (uint32_t)fr * (uint32_t)W + (uint32_t)col;
-  const float xs[4] = {x.x, x.y, x.z, x.w};
-  if (MODE != TAUV_TOPK_SIGMOID_PEAK) {
+  const uint32_t rowb = (uint32_t)W * 4u;
+  float xs[4] = {0.f, 0.f, 0.f, 0.f};
+  bool cand[4] = {false, false, false, false};
+  uint32_t flat = 0;
+  if (mine) {
+    const int fr = (int)(ctx->load_row0 + p - ctx->frame_row0);  // row inside the frame
+    flat = (uint32_t)fr * (uint32_t)W + (uint32_t)col;
+    const uint32_t mid = ring_u32 + (uint32_t)rp * rowb + (uint32_t)col * 4u;  // rp: the ring row that holds stream row p
+    const float4 x = sd_lds4(mid);
+    xs[0] = x.x; xs[1] = x.y; xs[2] = x.z; xs[3] = x.w;
+    if (MODE != TAUV_TOPK_SIGMOID_PEAK) {
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc)
-      if (xs[cc] >= thr_f) sd_push<MODE>(sm, xs[cc], flat + cc);
-    return;
+      for (int cc = 0; cc < 4; ++cc) cand[cc] = xs[cc] >= thr_f;
+    } else {
+      const int y = (a.H & (a.H - 1)) == 0 ? (fr & (a.H - 1)) : fr % a.H;
+      const float NI = TAUV_NEG_INF;
+      const bool hl = col > 0, hr = col + 4 < W;
+      float4 u = make_float4(NI, NI, NI, NI), d = u;
+      float ul = NI, ur = NI, dl = NI, dr = NI;
+      if (y > 0) {
+        const uint32_t up = ring_u32 + (uint32_t)(rp == 0 ? ring_rows - 1 : rp - 1) * rowb + (uint32_t)col * 4u;
+        u = sd_lds4(up);
+        if (hl) ul = sd_lds1(up - 4);
+        if (hr) ur = sd_lds1(up + 16);
+      }
+      if (y + 1 < a.H) {
+        const uint32_t dn = ring_u32 + (uint32_t)(rp + 1 == ring_rows ? 0 : rp + 1) * rowb + (uint32_t)col * 4u;
+        d = sd_lds4(dn);
+        if (hl) dl = sd_lds1(dn - 4);
+        if (hr) dr = sd_lds1(dn + 16);
+      }
+      const float ml = hl ? sd_lds1(mid - 4) : NI, mr = hr ? sd_lds1(mid + 16) : NI;
+      float cm[6];  // column-wise max over the three rows, columns col-1 .. col+4
+      cm[0] = fmaxf(fmaxf(ul, ml), dl);
+      cm[1] = fmaxf(fmaxf(u.x, x.x), d.x);
+      cm[2] = fmaxf(fmaxf(u.y, x.y), d.y);
+      cm[3] = fmaxf(fmaxf(u.z, x.z), d.z);
+      cm[4] = fmaxf(fmaxf(u.w, x.w), d.w);
+      cm[5] = fmaxf(fmaxf(ur, mr), dr);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const float xv = xs[cc];
+        if (xv >= thr_f) {
+          const float m = fmaxf(fmaxf(cm[cc], cm[cc + 1]), cm[cc + 2]);
+          bool peak = (xv >= m);
+          // x < m can still tie after the sigmoid (saturation, sub-ulp gap): the reference compares sigmoid values
+          if (!peak && (xv > 4.0f || m < -80.0f || (m - xv) < 1e-3f)) peak = sigmoid_tie(xv, m);
+          cand[cc] = peak;
+        }
+      }
+    }
   }
-  const int y = fr % a.H;
-  const float NI = TAUV_NEG_INF;
-  const float* mid = sm.ring + (size_t)(p & ring_mask) * W + col;
-  const bool hl = col > 0, hr = col + 4 < W;
-  float4 u = make_float4(NI, NI, NI, NI), d = u;
-  float ul = NI, ur = NI, dl = NI, dr = NI;
-  if (y > 0) {
-    const float* up = sm.ring + (size_t)((p - 1) & ring_mask) * W + col;
-    u = *reinterpret_cast<const float4*>(up);
-    if (hl) ul = up[-1];
-    if (hr) ur = up[4];
-  }
-  if (y + 1 < a.H) {
-    const float* dn = sm.ring + (size_t)((p + 1) & ring_mask) * W + col;
-    d = *reinterpret_cast<const float4*>(dn);
-    if (hl) dl = dn[-1];
-    if (hr) dr = dn[4];
-  }
-  const float ml = hl ? mid[-1] : NI, mr = hr ? mid[4] : NI;
-  float cm[6];  // column-wise max over the three rows, columns col-1 .. col+4
-  cm[0] = fmaxf(fmaxf(ul, ml), dl);
-  cm[1] = fmaxf(fmaxf(u.x, x.x), d.x);
-  cm[2] = fmaxf(fmaxf(u.y, x.y), d.y);
-  cm[3] = fmaxf(fmaxf(u.z, x.z), d.z);
-  cm[4] = fmaxf(fmaxf(u.w, x.w), d.w);
-  cm[5] = fmaxf(fmaxf(ur, mr), dr);
+  unsigned long long* const sub = sd_list(a) + (size_t)warp * kSdSub;
+  uint32_t* const bins = sd_bins(a);
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc) {
-    const float xv = xs[cc];
-    if (xv >= thr_f) {
-      const float m = fmaxf(fmaxf(cm[cc], cm[cc + 1]), cm[cc + 2]);
-      bool peak = (xv >= m);
-      // x < m can still tie after the sigmoid (saturation, sub-ulp gap): the reference compares sigmoid values
-      if (!peak && (xv > 4.0f || m < -80.0f || (m - xv) < 1e-3f)) peak = sigmoid_tie(xv, m);
-      if (peak) sd_push<MODE>(sm, xv, flat + cc);
+    if (!__any_sync(0xffffffffu, cand[cc])) continue;
+    const float x = xs[cc];
+    bool ok = cand[cc];
+    unsigned long long c = 0ull;
+    if (ok) {
+      uint32_t key;
+      if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
+        const float s = sigmoid_ref(x);
+        ok = s > 0.0f;  // underflowed to 0: zero-valued cells are supplied by the filler, like non-peaks
+        key = float_to_key(s);
+      } else {
+        key = float_to_key(x);
+      }
+      c = make_composite(key, flat + cc);
+      ok = ok && c > ctx->warpT[warp];
     }
+    unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (bal == 0u) continue;
+    if (cnt + __popc(bal) > kSdSub) {
+      cnt = sd_warp_prune<MODE>(a, cnt);
+      ok = ok && c > ctx->warpT[warp];
+      bal = __ballot_sync(0xffffffffu, ok);
+      if (bal == 0u) continue;
+    }
+    if (ok) {
+      sub[cnt + __popc(bal & ((1u << lane) - 1u))] = c;
+      // the histogram counts every candidate once, in logit / value space
+      if (MODE != TAUV_TOPK_SIGMOID_PEAK || x > -80.0f) {
+        const int bin = cl_window_bin(float_to_key(x));
+        if (bin >= 0) {
+          atomicAdd(&bins[bin], 1u);
+          if ((uint32_t)bin > *reinterpret_cast<volatile uint32_t*>(&ctx->maxbin)) atomicMax(&ctx->maxbin, (uint32_t)bin);
+        }
+      }
+    }
+    cnt += __popc(bal);
+    if (lane == 0) atomicAdd(&ctx->pushed, (uint32_t)__popc(bal));
   }
+  return cnt;
 }
 
-// Threshold scan of stream rows [p0, p1) (one frame): every consumer thread takes 128-bit strips from the ring,
-// four in flight; only strips whose maximum reaches the threshold are examined.
+// Threshold scan of this warp's share of the stream rows [p0, p1) (one frame; rp0 = ring row of p0; the rows are
+// contiguous in the ring): the warp takes every kSdFW-th group of 32 consecutive 128-bit strips, kSdU groups in flight.
+// Strips whose maximum reaches the threshold are packed — the j-th hot strip of the iteration goes to lane j, through
+// a 32-word scratch of the warp — and examined together.
 template <int MODE>
-__device__ __forceinline__ void sd_pass(const SdArgs& a, const SdSmem& sm, int ring_mask, int spr_shift, int p0, int p1) {
-  const int tid = threadIdx.x;
-  const int W = a.W, spr = W >> 2;
+__device__ __forceinline__ int sd_filter_part(const SdArgs& a, uint32_t ring_u32, int ring_rows, int spr_shift, int p0, int p1,
+                                              int rp0, int cnt) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int spr = a.W >> 2;
   const int n = (p1 - p0) * spr;
+  const uint32_t base = ring_u32 + (uint32_t)rp0 * (uint32_t)a.W * 4u;
+  const uint32_t thr_addr = smem_u32(&sd_ctx(a)->thr_key);
   const float NI = TAUV_NEG_INF;
 #pragma unroll 1
-  for (int base = 0; base < n; base += 4 * kSdNC) {
-    const float thr_f = *reinterpret_cast<volatile float*>(&sm.ctx->thr_f);
-    float4 v[4];
-    int pr[4], pc[4];
+  for (int s0 = 0; s0 < n; s0 += kSdU * kSdNF) {
+    const uint32_t tk = sd_lds_u32_volatile(thr_addr);
+    const float thr_f = tk ? key_to_float(tk) : NI;
+    float4 v[kSdU];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int s = base + u * kSdNC + tid;
-      const int r = spr_shift >= 0 ? (s >> spr_shift) : (s / spr);
-      pr[u] = p0 + r;
-      pc[u] = (s - r * spr) << 2;
-      v[u] = (s < n) ? *reinterpret_cast<const float4*>(sm.ring + (size_t)(pr[u] & ring_mask) * W + pc[u])
-                     : make_float4(NI, NI, NI, NI);
+    for (int u = 0; u < kSdU; ++u) {
+      const int s = s0 + u * kSdNF + tid;
+      v[u] = (s < n) ? sd_lds4(base + (uint32_t)s * 16u) : make_float4(NI, NI, NI, NI);
     }
+    unsigned bal[kSdU];
+    unsigned any = 0u;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kSdU; ++u) {
       const float m = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
-      if (m >= thr_f && base + u * kSdNC + tid < n) sd_examine<MODE>(a, sm, ring_mask, pr[u], pc[u], v[u], thr_f);
+      bal[u] = __ballot_sync(0xffffffffu, (m >= thr_f) && (s0 + u * kSdNF + tid < n));
+      any |= bal[u];
+    }
+    if (any == 0u) continue;
+    // pack: hot strip -> its rank among the iteration's hot strips -> scratch[rank] = strip index
+    int* scratch = sd_ctx(a)->scratch[tid >> 5];
+    int total = 0;
+#pragma unroll 1
+    for (int j0 = 0;; j0 += 32) {
+      __syncwarp();
+      int before = 0;
+#pragma unroll
+      for (int u = 0; u < kSdU; ++u) {
+        if (bal[u] & (1u << lane)) {
+          const int rank = before + __popc(bal[u] & ((1u << lane) - 1u)) - j0;
+          if (rank >= 0 && rank < 32) scratch[rank] = s0 + u * kSdNF + tid;
+        }
+        before += __popc(bal[u]);
+      }
+      total = before;
+      __syncwarp();
+      const bool mine = j0 + lane < total;
+      const int s = mine ? scratch[lane] : 0;
+      const int r = spr_shift >= 0 ? (s >> spr_shift) : (s / spr);
+      cnt = sd_examine<MODE>(a, ring_u32, ring_rows, mine, p0 + r, rp0 + r, (s - r * spr) << 2, thr_f, cnt);
+      if (j0 + 32 >= total) break;
     }
   }
+  return cnt;
 }
 
-// ---- threshold maintenance ------------------------------------------------------------------------------------------
-// Warp 0: highest window bin b with count(bins >= b) >= k (-1: fewer than k binned).  At most 32 x 32 bins below the
-// highest occupied one are visited; counts only grow, so a bin found from a slightly stale view is still valid.
-__device__ __forceinline__ int sd_scan_bin(const SdSmem& sm, int k) {
+// rows [p0, p1) of one frame; rp0 = ring row of p0
+template <int MODE>
+__device__ __forceinline__ int sd_filter_rows(const SdArgs& a, uint32_t ring_u32, int ring_rows, int spr_shift, int p0, int p1,
+                                              int rp0, int cnt) {
+  // split where the ring wraps so that each part is one contiguous run of strips in shared memory
+  const int n1 = ring_rows - rp0;
+  if (p1 - p0 <= n1) return sd_filter_part<MODE>(a, ring_u32, ring_rows, spr_shift, p0, p1, rp0, cnt);
+  cnt = sd_filter_part<MODE>(a, ring_u32, ring_rows, spr_shift, p0, p0 + n1, rp0, cnt);
+  return sd_filter_part<MODE>(a, ring_u32, ring_rows, spr_shift, p0 + n1, p1, 0, cnt);
+}
+
+// ---- manager warp ---------------------------------------------------------------------------------------------------
+// Highest window bin b with count(bins >= b) >= k (-1: fewer than k binned).  Counts only grow, so a bin found from a
+// slightly stale view is still valid.
+__device__ __forceinline__ int sd_scan_bin(const SdArgs& a) {
   const int lane = threadIdx.x & 31;
-  const int maxbin = (int)*reinterpret_cast<volatile uint32_t*>(&sm.ctx->maxbin);
+  const uint32_t* bins = sd_bins(a);
+  const int maxbin = (int)*reinterpret_cast<volatile uint32_t*>(&sd_ctx(a)->maxbin);
   uint32_t acc = 0;
   int found = -1;
   for (int it = 0; it < 64 && found < 0; ++it) {
     const int bin = maxbin - it * 32 - lane;
-    const uint32_t v = bin >= 0 ? *reinterpret_cast<volatile uint32_t*>(&sm.bins[bin]) : 0u;
+    const uint32_t v = bin >= 0 ? *reinterpret_cast<const volatile uint32_t*>(&bins[bin]) : 0u;
     uint32_t pre = v;  // inclusive prefix over lanes (lane 0 = highest bin)
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o);
       if (lane >= o) pre += t;
     }
-    const unsigned hit = __ballot_sync(0xffffffffu, acc + pre >= (uint32_t)k);
+    const unsigned hit = __ballot_sync(0xffffffffu, acc + pre >= (uint32_t)a.k);
     if (hit) found = maxbin - it * 32 - (__ffs(hit) - 1);
     acc += __shfl_sync(0xffffffffu, pre, 31);
     if (maxbin - (it + 1) * 32 < 0) break;
@@ -284,128 +444,42 @@ __device__ __forceinline__ int sd_scan_bin(const SdSmem& sm, int k) {
   return found;
 }
 
-// Lowest FINAL key that a candidate counted in window bin `bin` or above can have (composite with index bits 0).
+// Rescan the bins and raise the cheap filter and the prune floor.
 template <int MODE>
-__device__ __forceinline__ unsigned long long sd_bin_floor(int bin) {
-  const float edge = cl_window_edge(bin);
-  // SIGMOID_PEAK: the bins count logits, the list holds their sigmoids, whose last-bit wobble the guard band covers
-  const float lowest = MODE == TAUV_TOPK_SIGMOID_PEAK ? sigmoid_ref(edge) * (1.0f - 4e-5f) : edge;
-  const unsigned long long kt = (unsigned long long)float_to_key(lowest) << 32;
-  return kt == 0ull ? 1ull : kt;
-}
-
-// Warp 0 (after a pass barrier): rescan the bins when enough new candidates arrived and raise the cheap filter.
-template <int MODE>
-__device__ __forceinline__ void sd_rescan(const SdArgs& a, const SdSmem& sm, bool force) {
-  SdCtx* const ctx = sm.ctx;
-  if (ctx->safe) return;
-  const int cnt = ctx->count;
-  const int every = a.k >= 8 ? a.k / 8 : 1;
-  if (cnt < a.k || (!force && cnt - ctx->last_scan < every)) return;
-  const int found = sd_scan_bin(sm, a.k);
-  if ((threadIdx.x & 31) == 0) {
-    ctx->last_scan = cnt;
-    ctx->found_bin = found;
-    if (found >= 0) {
-      const float edge = cl_window_edge(found);  // at least k candidates of this frame have logit/value >= edge
-      float t = TAUV_NEG_INF;
-      if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
-        const uint32_t key = reject_key_for_score(sigmoid_ref(edge));
-        if (key) t = key_to_float(key);
-      } else {
-        t = edge;
-      }
-      if (t > ctx->thr_f) ctx->thr_f = t;
-    }
+__device__ __forceinline__ void sd_rescan(const SdArgs& a) {
+  SdCtx* const ctx = sd_ctx(a);
+  const int found = sd_scan_bin(a);
+  if ((threadIdx.x & 31) == 0 && found >= 0) {
+    const float edge = cl_window_edge(found);  // at least k candidates of this frame have logit/value >= edge
+    uint32_t key;
+    if (MODE == TAUV_TOPK_SIGMOID_PEAK) key = reject_key_for_score(sigmoid_ref(edge));
+    else key = float_to_key(edge);
+    if (key) atomicMax(&ctx->thr_key, key);
+    const unsigned long long fl = sd_bin_floor<MODE>(found);
+    if (fl > ctx->floor_key) *reinterpret_cast<volatile unsigned long long*>(&ctx->floor_key) = fl;
   }
   __syncwarp();
 }
 
-// All consumers: keep the list entries that satisfy `keep` (order not preserved across threads' slices, which is
-// fine: the keys carry their own order).  Every thread holds its slice in registers, so the in-place writes cannot
-// overtake unread entries.  New length -> ctx->count.
-template <class Keep>
-__device__ __forceinline__ void sd_compact(const SdSmem& sm, Keep keep) {
-  SdCtx* const ctx = sm.ctx;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = min(ctx->count, kSdCap);
-  unsigned long long mine[kSdSlice];
-  int nm = 0;
-#pragma unroll
-  for (int j = 0; j < kSdSlice; ++j) {
-    const int i = tid * kSdSlice + j;
-    unsigned long long c = 0ull;
-    if (i < n) c = sm.list[i];
-    const bool kp = (i < n) && keep(c);
-    mine[j] = kp ? c : 0ull;
-    nm += kp ? 1 : 0;
-  }
-  int incl = nm;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) ctx->wsum[warp] = incl;
-  sd_sync();  // every slice is in registers; warp sums are visible
-  int off = incl - nm, tot = 0;
-#pragma unroll
-  for (int w = 0; w < kSdCW; ++w) {
-    if (w < warp) off += ctx->wsum[w];
-    tot += ctx->wsum[w];
-  }
-#pragma unroll
-  for (int j = 0; j < kSdSlice; ++j)
-    if (mine[j] != 0ull) sm.list[off++] = mine[j];
-  sd_sync();
-  if (tid == 0) ctx->count = tot;
-  sd_sync();
-}
-
-// All consumers: exact prune of the list to its top-k (radix select) and, once k entries exist, an exact composite
-// threshold (the k-th key: later entries at or below it cannot be in the frame's top-k) plus the matching cheap filter.
-template <int MODE>
-__device__ __noinline__ void sd_prune_exact(const SdArgs& a, const SdSmem& sm) {
-  SdCtx* const ctx = sm.ctx;
-  const int n = min(ctx->count, kSdCap);
-  const unsigned long long* list = sm.list;
-  auto load = [&](int i) { return list[i]; };
-  const unsigned long long T = block_kth_largest<kSdNC, decltype(load), SdSync>(load, n, a.k, sm.hist, ctx->sel);
-  sd_compact(sm, [&](unsigned long long c) { return c >= T && c != 0ull; });
-  if (threadIdx.x == 0 && ctx->count >= a.k && T > ctx->T) {
-    ctx->T = T - 1ull;  // (push rejects c <= ctx->T; T itself is in the list already and cannot come again)
-    const float v = key_to_float(composite_key(T));
-    float t = TAUV_NEG_INF;
-    if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
-      const uint32_t key = reject_key_for_score(v);
-      if (key) t = key_to_float(key);
-    } else {
-      t = v;
-    }
-    if (t > ctx->thr_f) ctx->thr_f = t;
-  }
-  sd_sync();
-}
-
-// Descending bitonic sort of 256*E keys held E per thread (element e of thread t is index e*256 + t).  Strides >= 256
-// are exchanges inside a thread, strides < 32 shuffles; only strides 32..128 go through shared memory (buf: 256*E
-// keys) and the consumer barrier.
-template <int E>
+// Descending bitonic sort of NT*E keys held E per thread (element e of thread t is index e*NT + t).  Strides >= NT
+// are exchanges inside a thread, strides < 32 shuffles; only strides 32..NT/2 go through shared memory (buf: NT*E keys)
+// and the group's barrier.
+template <int NT, int E, class Sync>
 __device__ __forceinline__ void sd_sort_desc(unsigned long long (&x)[E], unsigned long long* buf) {
   const int t = threadIdx.x;
-  constexpr int N = kSdNC * E;
+  constexpr int N = NT * E;
 #pragma unroll 1
   for (int size = 2; size <= N; size <<= 1) {
 #pragma unroll 1
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (stride >= kSdNC) {
+      if (stride >= NT) {
 #pragma unroll
         for (int se = E / 2; se >= 1; se >>= 1) {  // stride in elements of one thread (compile-time after unrolling)
-          if (stride == se * kSdNC) {
+          if (stride == se * NT) {
 #pragma unroll
             for (int e = 0; e < E; ++e) {
               if ((e & se) == 0) {
-                const int i = e * kSdNC + t;
+                const int i = e * NT + t;
                 const bool desc = (i & size) == 0;
                 const unsigned long long lo = x[e], hi = x[e | se];
                 const bool sw = desc ? (lo < hi) : (lo > hi);
@@ -417,21 +491,21 @@ __device__ __forceinline__ void sd_sort_desc(unsigned long long (&x)[E], unsigne
         }
       } else if (stride >= 32) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) buf[e * kSdNC + t] = x[e];
-        sd_sync();
+        for (int e = 0; e < E; ++e) buf[e * NT + t] = x[e];
+        Sync::sync();
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-          const int i = e * kSdNC + t;
+          const int i = e * NT + t;
           const unsigned long long y = buf[i ^ stride];
           const bool desc = (i & size) == 0, lower = (i & stride) == 0;
           const bool take_max = lower == desc;
           x[e] = (take_max == (y > x[e])) ? y : x[e];
         }
-        sd_sync();
+        Sync::sync();
       } else {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-          const int i = e * kSdNC + t;
+          const int i = e * NT + t;
           const unsigned long long y = __shfl_xor_sync(0xffffffffu, x[e], stride);
           const bool desc = (i & size) == 0, lower = (i & stride) == 0;
           const bool take_max = lower == desc;
@@ -444,8 +518,9 @@ __device__ __forceinline__ void sd_sort_desc(unsigned long long (&x)[E], unsigne
 
 // One arrival at the frame's ticket; returns how many runs had arrived before.  The word carries the launch's epoch, so
 // whatever an earlier launch (or nobody) left in the workspace counts as zero: no memset in front of the kernel.
-__device__ __forceinline__ uint32_t sd_ticket_arrive(unsigned long long* w, uint32_t epoch) {
-  unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(w);
+// `guess`: the word as read earlier (saves the first round trip when nobody arrived in between).
+__device__ __forceinline__ uint32_t sd_ticket_arrive(unsigned long long* w, uint32_t epoch, unsigned long long guess) {
+  unsigned long long old = guess;
   while (true) {
     const unsigned long long neu = ((uint32_t)(old >> 32) == epoch) ? old + 1ull : (((unsigned long long)epoch << 32) | 1ull);
     const unsigned long long prev = atomicCAS(w, old, neu);
@@ -458,95 +533,114 @@ __device__ __forceinline__ int sd_owner(const SdArgs& a, long long row) {  // CT
   return (int)(((row + 1) * a.G + a.rows_total - 1) / a.rows_total) - 1;
 }
 
-// All consumers of the CTA that completed a frame: merge the frame's rows, rank, write the packed outputs.
+// Filter warps of the CTA that completed a frame: merge the frame's rows, sort, write the packed outputs.
 template <int MODE>
-__device__ __noinline__ void sd_merge_emit(const SdArgs& a, const SdSmem& sm, int frame, int n_runs) {
-  SdCtx* const ctx = sm.ctx;
+__device__ __noinline__ void sd_merge_emit(const SdArgs& a, int frame, int n_runs) {
+  SdCtx* const ctx = sd_ctx(a);
   const int tid = threadIdx.x;
   const int k = a.k;
-  unsigned long long* pool = sm.list;  // the run's list is in the table already
+  unsigned long long* pool = sd_list(a);  // the run's candidates are in the table already
+  uint32_t* flags = sd_flags(a);
+  uint32_t* hist = sd_bins(a);            // (the run's bins are dead)
   const unsigned long long* rows = a.cand + (size_t)frame * a.tbl_rows * a.row_cap;
   const int* cnts = a.cand_count + (size_t)frame * a.tbl_rows;
-  if (tid == 0) {
-    ctx->total = 0;
-    ctx->nge = 0;
-  }
-  for (int i = tid; i < k; i += kSdNC) sm.flags[i] = 0u;
-  sd_sync();
-  // (rows were written by other CTAs before their ticket arrival: read them through L2)
-  int part = 0;
-  for (int r = tid; r < n_runs; r += kSdNC) part += __ldcg(cnts + r);
-  if (part) atomicAdd(&ctx->total, part);
-  sd_sync();
-  const int total = ctx->total;
-  int npos;  // entries of the ranked output that are real candidates
-  if (total <= kSdCap) {
-    if (tid == 0) ctx->base = 0;
-    sd_sync();
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int r = warp; r < n_runs; r += kSdCW) {
-      const int c = __ldcg(cnts + r);
-      if (c == 0) continue;
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&ctx->base, c);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      for (int i = lane; i < c; i += 32) pool[base + i] = __ldcg(rows + (size_t)r * a.row_cap + i);
+  const int nslots = n_runs * a.row_cap;
+  int m;  // keys in the pool
+  if (nslots <= kSdListCap) {
+    // all rows at once, whatever their counts (one round trip through L2: the rows were written by other CTAs before
+    // their ticket arrival), invalid slots as 0; then squeeze the zeros out while sorting
+    for (int i = tid; i < nslots; i += kSdNF) {
+      const int r = i / a.row_cap;
+      const unsigned long long c = __ldcg(rows + (size_t)r * a.row_cap + (i - r * a.row_cap));
+      pool[i] = (i - r * a.row_cap) < __ldcg(cnts + r) ? c : 0ull;
     }
-    sd_sync();
-    if (total > 4 * kSdNC) {  // (many runs per frame: small batches) cut to the exact top-k first
-      if (tid == 0) ctx->count = total;
-      sd_sync();
+    for (int i = tid; i < k; i += kSdNF) flags[i] = 0u;
+    if (tid == 0) {
+      ctx->nge = 0;
+      ctx->base = 0;
+    }
+    sd_sync_f();
+    m = nslots;
+    if (nslots > 2 * kSdNF) {  // (many runs per frame: small batches) cut to the exact top-k first
       auto load = [&](int i) { return pool[i]; };
-      const unsigned long long T = block_kth_largest<kSdNC, decltype(load), SdSync>(load, total, k, sm.hist, ctx->sel);
-      sd_compact(sm, [&](unsigned long long c) { return c >= T; });
+      const unsigned long long T = block_kth_largest<kSdNF, decltype(load), SdSyncF>(load, nslots, k, hist, ctx->sel);
+      // survivors to the front: every thread holds its slice in registers, so in-place writes cannot pass unread entries
+      constexpr int SL = kSdListCap / kSdNF;
+      unsigned long long mine[SL];
+      int nm = 0;
+#pragma unroll
+      for (int j = 0; j < SL; ++j) {
+        const int i = tid * SL + j;
+        const unsigned long long c = i < nslots ? pool[i] : 0ull;
+        const bool kp = c >= T && c != 0ull;
+        mine[j] = kp ? c : 0ull;
+        nm += kp ? 1 : 0;
+      }
+      sd_sync_f();
+      int off = 0;
+      if (nm) off = atomicAdd(&ctx->base, nm);
+#pragma unroll
+      for (int j = 0; j < SL; ++j)
+        if (mine[j] != 0ull) pool[off++] = mine[j];
+      sd_sync_f();
+      m = ctx->base;
     }
   } else {
     // does not fit: exact k-th key straight from the table (slot i is valid iff (i % row_cap) < count of its row)
-    const int nslots = n_runs * a.row_cap;
+    for (int i = tid; i < k; i += kSdNF) flags[i] = 0u;
+    if (tid == 0) {
+      ctx->nge = 0;
+      ctx->base = 0;
+    }
+    sd_sync_f();
     auto load = [&](int i) -> unsigned long long {
       const int r = i / a.row_cap;
       return (i - r * a.row_cap) < __ldcg(cnts + r) ? __ldcg(rows + i) : 0ull;
     };
-    const unsigned long long T = block_kth_largest<kSdNC, decltype(load), SdSync>(load, nslots, k, sm.hist, ctx->sel);
-    if (tid == 0) ctx->base = 0;
-    sd_sync();
-    for (int i = tid; i < nslots; i += kSdNC) {
+    const unsigned long long T = block_kth_largest<kSdNF, decltype(load), SdSyncF>(load, nslots, k, hist, ctx->sel);
+    for (int i = tid; i < nslots; i += kSdNF) {
       const unsigned long long c = load(i);
       if (c >= T && c != 0ull) pool[atomicAdd(&ctx->base, 1)] = c;
     }
-    sd_sync();
+    sd_sync_f();
+    m = ctx->base;
   }
-  // (after a cut the pool holds min(k, total) keys)
-  int m = total;
-  if (total > kSdCap) m = ctx->base;
-  else if (total > 4 * kSdNC) m = ctx->count;
-  npos = min(m, k);
-  sd_sync();
-  // sort the pool (<= 1024 keys) descending in registers, ranked keys back to pool[0, m)
-  if (m <= 2 * kSdNC) {
+  // sort the pool (<= 1024 slots) descending in registers; zeros (invalid slots) sink to the end
+  int npos;
+  {
     unsigned long long x[2];
+    if (m <= kSdNF) {
+      unsigned long long y[1];
+      y[0] = tid < m ? pool[tid] : 0ull;
+      sd_sync_f();
+      sd_sort_desc<kSdNF, 1, SdSyncF>(y, pool);
+      x[0] = y[0];
+      x[1] = 0ull;
+    } else {
 #pragma unroll
-    for (int e = 0; e < 2; ++e) x[e] = (e * kSdNC + tid < m) ? pool[e * kSdNC + tid] : 0ull;
-    sd_sync();
-    sd_sort_desc<2>(x, pool);
+      for (int e = 0; e < 2; ++e) x[e] = (e * kSdNF + tid < m) ? pool[e * kSdNF + tid] : 0ull;
+      sd_sync_f();
+      sd_sort_desc<kSdNF, 2, SdSyncF>(x, pool);
+    }
 #pragma unroll
-    for (int e = 0; e < 2; ++e) pool[e * kSdNC + tid] = x[e];
-  } else {
-    unsigned long long x[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) x[e] = (e * kSdNC + tid < m) ? pool[e * kSdNC + tid] : 0ull;
-    sd_sync();
-    sd_sort_desc<4>(x, pool);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) pool[e * kSdNC + tid] = x[e];
+    for (int e = 0; e < 2; ++e) pool[e * kSdNF + tid] = x[e];
   }
-  sd_sync();
+  sd_sync_f();
+  {
+    // npos = number of non-zero keys among the first k of the sorted pool (they are a prefix)
+    int lo = 0, hi = min(k, 2 * kSdNF);
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (pool[mid] != 0ull) lo = mid + 1; else hi = mid;
+    }
+    npos = lo;
+  }
   // ranked outputs
   {
     const BoxArgs& g = a.box;
     const uint32_t hw_elems = (uint32_t)(a.H * a.W);
     int my_ge = 0;
-    for (int r = tid; r < npos; r += kSdNC) {
+    for (int r = tid; r < npos; r += kSdNF) {
       const unsigned long long c = pool[r];
       const uint32_t flat = composite_idx(c);
       const float sc = key_to_float(composite_key(c));
@@ -562,165 +656,141 @@ __device__ __noinline__ void sd_merge_emit(const SdArgs& a, const SdSmem& sm, in
         box_one(g, frame, slot, iy, ix);
         if (!(sc < g.thr)) ++my_ge;
       }
-      if (flat < (uint32_t)k) sm.flags[flat] = 1u;
+      if (flat < (uint32_t)k) flags[flat] = 1u;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) my_ge += __shfl_xor_sync(0xffffffffu, my_ge, o);
     if ((tid & 31) == 0 && my_ge) atomicAdd(&ctx->nge, my_ge);
   }
-  sd_sync();
+  sd_sync_f();
   if (MODE == TAUV_TOPK_SIGMOID_PEAK && npos < k) {
     // Dense stable top-k semantics: the remaining slots are zero-valued cells in ascending flat index, skipping the
-    // selected peaks.  At most npos of the first k cells are selected peaks, so cells [0, k) always suffice.
+    // selected peaks.  At most npos of the first k cells are selected peaks, so cells [0, k) always suffice (k <= 256
+    // <= the filter threads: one round).
     const BoxArgs& g = a.box;
     const int lane = tid & 31, warp = tid >> 5;
     const int need = k - npos;
     const long long hw_elems = (long long)a.H * a.W;
-    int base = 0;
-    for (int start = 0; start < k && base < need; start += kSdNC) {
-      const int i = start + tid;
-      const bool freec = (i < k) && (sm.flags[i] == 0u);
-      const unsigned bal = __ballot_sync(0xffffffffu, freec);
-      if (lane == 0) ctx->wsum[warp] = __popc(bal);
-      sd_sync();
-      int pos = base + __popc(bal & ((1u << lane) - 1u));
-      int tot = 0;
-      for (int w = 0; w < kSdCW; ++w) {
-        if (w < warp) pos += ctx->wsum[w];
-        tot += ctx->wsum[w];
-      }
-      if (freec && pos < need) {
-        const int r = npos + pos;
-        const long long lab = i / hw_elems;
-        const long long rem = i - lab * hw_elems;
-        const int iy = (int)(rem / a.W), ix = (int)(rem - (long long)iy * a.W);
-        const long long slot = (long long)frame * k + r;
-        a.out_index[slot * 2 + 0] = iy;
-        a.out_index[slot * 2 + 1] = ix;
-        a.out_label[slot] = lab;
-        a.out_score[slot] = 0.0f;
-        if (g.enabled) box_one(g, frame, slot, iy, ix);
-      }
-      base += tot;
-      sd_sync();
+    const int i = tid;
+    const bool freec = (i < k) && (flags[i] == 0u);
+    const unsigned bal = __ballot_sync(0xffffffffu, freec);
+    if (lane == 0) ctx->wsum[warp] = __popc(bal);
+    sd_sync_f();
+    int pos = __popc(bal & ((1u << lane) - 1u));
+    for (int ww = 0; ww < warp; ++ww) pos += ctx->wsum[ww];
+    if (freec && pos < need) {
+      const int r = npos + pos;
+      const long long lab = i / hw_elems;
+      const long long rem = i - lab * hw_elems;
+      const int iy = (int)(rem / a.W), ix = (int)(rem - (long long)iy * a.W);
+      const long long slot = (long long)frame * k + r;
+      a.out_index[slot * 2 + 0] = iy;
+      a.out_index[slot * 2 + 1] = ix;
+      a.out_label[slot] = lab;
+      a.out_score[slot] = 0.0f;
+      if (g.enabled) box_one(g, frame, slot, iy, ix);
     }
+    sd_sync_f();
   }
   if (a.box.enabled && tid == 0) {  // entries before the first score < threshold (ranked scores descend; fillers score 0)
     int cnt = ctx->nge;
     if (MODE == TAUV_TOPK_SIGMOID_PEAK && npos < k && !(0.0f < a.box.thr)) cnt += k - npos;
     a.box.count[frame] = cnt;
   }
-  sd_sync();
+  sd_sync_f();
 }
 
-// All consumers, end of a run: prune to k + a handful, hand the survivors to the table, arrive at the frame's ticket,
-// and — for the run that completes the frame — merge and emit.
+// Filter warps, end of a run: prune every sub-list to what can still matter (the manager's latest floor), hand the
+// survivors to the table, arrive at the frame's ticket, and — for the run that completes the frame — merge and emit.
 template <int MODE>
-__device__ __noinline__ void sd_run_end(const SdArgs& a, const SdSmem& sm, int frame) {
-  SdCtx* const ctx = sm.ctx;
-  const int tid = threadIdx.x;
-  if (!ctx->safe) {
-    // one last scan of the (complete) histogram: the bin that holds the run's k-th best; drop what lies below its edge
-    if (tid < 32) {
-      const int bin = sd_scan_bin(sm, a.k);
-      if (tid == 0) ctx->keyT = bin >= 0 ? sd_bin_floor<MODE>(bin) : 1ull;  // fewer than k binned: keep every key
-    }
-    sd_sync();
-    const unsigned long long kt = ctx->keyT;
-    sd_compact(sm, [&](unsigned long long c) { return c >= kt; });
+__device__ __noinline__ void sd_run_end(const SdArgs& a, int frame, int cnt) {
+  SdCtx* const ctx = sd_ctx(a);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned long long* sub = sd_list(a) + (size_t)warp * kSdSub;
+  unsigned long long kt = ctx->floor_key;  // floor of the bin that holds the run's k-th best (0: fewer than k binned)
+  if (kt == 0ull) kt = 1ull;
+  auto count_ge = [&](unsigned long long t) {
+    int n = 0;
+    for (int i = lane; i < cnt; i += 32) n += (sub[i] >= t) ? 1 : 0;
+    return __reduce_add_sync(0xffffffffu, n);
+  };
+  int mine = count_ge(kt);
+  if (lane == 0) ctx->wsum[warp] = mine;
+  sd_sync_f();
+  int total = 0;
+  for (int ww = 0; ww < kSdFW; ++ww) total += ctx->wsum[ww];
+  if (total > a.row_cap) {
+    // (ties / plateaus / a stale floor) exact k-th key over the union of the sub-lists (a padded [warp][kSdSub] table)
+    sd_sync_f();
+    if (lane == 0) ctx->wsum[warp] = cnt;
+    sd_sync_f();
+    const unsigned long long* list = sd_list(a);
+    const int* wc = ctx->wsum;
+    auto load = [&](int i) -> unsigned long long { return (i & (kSdSub - 1)) < wc[i / kSdSub] ? list[i] : 0ull; };
+    const unsigned long long T = block_kth_largest<kSdNF, decltype(load), SdSyncF>(load, kSdListCap, a.k, sd_bins(a), ctx->sel);
+    kt = T > kt ? T : kt;
+    mine = count_ge(kt);
+    sd_sync_f();
+    if (lane == 0) ctx->wsum[warp] = mine;
+    sd_sync_f();
+    total = 0;
+    for (int ww = 0; ww < kSdFW; ++ww) total += ctx->wsum[ww];
   }
-  if (ctx->safe || ctx->count > a.row_cap) sd_prune_exact<MODE>(a, sm);  // (ties / plateaus / safe mode: exactly <= k)
+  int off = 0;
+  for (int ww = 0; ww < warp; ++ww) off += ctx->wsum[ww];
   // the run's row of the candidate table
   const long long f0 = (long long)frame * a.rows_frame;
   const int first = sd_owner(a, f0), last = sd_owner(a, f0 + a.rows_frame - 1);
   const int n_runs = last - first + 1;
   const int row = (int)blockIdx.x - first;
-  const int n = ctx->count;
   unsigned long long* out = a.cand + ((size_t)frame * a.tbl_rows + row) * a.row_cap;
-  for (int i = tid; i < n; i += kSdNC) out[i] = sm.list[i];
-  if (tid == 0) a.cand_count[(size_t)frame * a.tbl_rows + row] = n;
+  for (int i0 = 0; i0 < cnt; i0 += 32) {
+    const int i = i0 + lane;
+    unsigned long long c = 0ull;
+    if (i < cnt) c = sub[i];
+    const bool kp = (i < cnt) && c >= kt;
+    const unsigned bal = __ballot_sync(0xffffffffu, kp);
+    if (kp) out[off + __popc(bal & ((1u << lane) - 1u))] = c;
+    off += __popc(bal);
+  }
+  if (tid == 0) a.cand_count[(size_t)frame * a.tbl_rows + row] = total;
   __threadfence();
-  sd_sync();
+  sd_sync_f();
   if (tid == 0) {
-    const uint32_t before = sd_ticket_arrive(a.ticket + frame, a.epoch);
+    const uint32_t before =
+        sd_ticket_arrive(a.ticket + frame, a.epoch, *reinterpret_cast<volatile unsigned long long*>(a.ticket + frame));
     __threadfence();
     ctx->is_last = (before == (uint32_t)(n_runs - 1));
   }
-  sd_sync();
-  if (ctx->is_last) sd_merge_emit<MODE>(a, sm, frame, n_runs);
+  sd_sync_f();
+  if (ctx->is_last) sd_merge_emit<MODE>(a, frame, n_runs);
 }
 
-// All consumers: start of a run
-__device__ __forceinline__ void sd_run_begin(const SdArgs& a, const SdSmem& sm, long long frame_row0) {
-  SdCtx* const ctx = sm.ctx;
+// Filter warps: the shared state of the next run (the manager is parked at the run-begin barrier)
+__device__ __forceinline__ void sd_run_reset(const SdArgs& a, int frame) {
+  SdCtx* const ctx = sd_ctx(a);
   const int tid = threadIdx.x;
-  for (int i = tid; i < kClBins / 4; i += kSdNC) reinterpret_cast<uint4*>(sm.bins)[i] = make_uint4(0, 0, 0, 0);
+  uint32_t* bins = sd_bins(a);
+  for (int i = tid; i < kClBins / 4; i += kSdNF) reinterpret_cast<uint4*>(bins)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < kSdFW) ctx->warpT[tid] = 0ull;
   if (tid == 0) {
-    ctx->T = 0ull;
-    ctx->thr_f = TAUV_NEG_INF;
-    ctx->count = 0;
-    ctx->flags = 0;
+    ctx->floor_key = 0ull;
+    ctx->thr_key = 0u;
     ctx->maxbin = 0u;
-    ctx->safe = 0;
-    ctx->last_scan = 0;
-    ctx->found_bin = -1;
-    ctx->frame_row0 = frame_row0;
-  }
-  sd_sync();
-}
-
-// All consumers: stream rows [p0, p1) of the current run through the filter, in passes that end with a barrier and
-// the list housekeeping.  While no threshold exists (and always in safe mode) a pass is short enough that it cannot
-// overflow the list.
-template <int MODE>
-__device__ __forceinline__ void sd_rows(const SdArgs& a, const SdSmem& sm, int ring_mask, int spr_shift, int p0, int p1) {
-  SdCtx* const ctx = sm.ctx;
-  const int tid = threadIdx.x;
-  int p = p0;
-  while (p < p1) {
-    const int count0 = ctx->count;
-    const bool bounded = ctx->safe || (ctx->thr_f == TAUV_NEG_INF && ctx->T == 0ull);
-    int rows = p1 - p;
-    if (bounded) rows = min(rows, max(1, (kSdCap - count0) / a.W));
-    sd_sync();  // (everybody has read the pass geometry before anybody pushes)
-    sd_pass<MODE>(a, sm, ring_mask, spr_shift, p, p + rows);
-    sd_sync();
-    if (ctx->flags & 2) {
-      // The list overflowed (plateaus, or a threshold that lets too much through).  Drop this pass's pushes, switch the
-      // run to safe mode (the bins have counted the dropped pushes: they are not read again), prune exactly, redo.
-      sd_sync();
-      if (tid == 0) {
-        ctx->count = count0;
-        ctx->flags = 0;
-        ctx->safe = 1;
-      }
-      sd_sync();
-      sd_prune_exact<MODE>(a, sm);
-      continue;
-    }
-    if (tid < 32) sd_rescan<MODE>(a, sm, false);
-    sd_sync();
-    if (ctx->count > kSdSoft) {
-      if (!ctx->safe && ctx->found_bin >= 0) {
-        // cheap prune: below the lower edge of the bin that holds the k-th best nothing can matter
-        if (tid < 32) sd_rescan<MODE>(a, sm, true);
-        sd_sync();
-        const unsigned long long kt = sd_bin_floor<MODE>(ctx->found_bin);
-        sd_compact(sm, [&](unsigned long long c) { return c >= kt; });
-      }
-      if (ctx->count > kSdSoft) sd_prune_exact<MODE>(a, sm);
-    }
-    p += rows;
+    ctx->pushed = 0u;
+    ctx->frame_row0 = (long long)frame * a.rows_frame;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ticket + frame));  // (the run's arrival will want the word near)
   }
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(kSdThreads, 1) stream_decode_kernel(const __grid_constant__ SdArgs a) {
-  const SdSmem sm = sd_carve(a);
-  SdCtx* const ctx = sm.ctx;
-  const int tid = threadIdx.x;
+  SdCtx* const ctx = sd_ctx(a);
+  uint64_t* const full = sd_full(a);
+  uint64_t* const empty = sd_empty(a);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int W = a.W, CR = a.chunk_rows, S = a.stages;
-  const int ring_mask = CR * S - 1;
+  const int ring_rows = CR * S;
 
   // this CTA's rows and what it loads: one halo row on either side unless the range starts / ends on a plane edge
   const long long own0 = a.rows_total * blockIdx.x / a.G, own1 = a.rows_total * (blockIdx.x + 1) / a.G;
@@ -730,68 +800,146 @@ __global__ void __launch_bounds__(kSdThreads, 1) stream_decode_kernel(const __gr
   const int n_own = (int)(own1 - own0);
   const int n_load = n_own + lead + trail;
   const int n_chunks = (n_load + CR - 1) / CR;
+  const int frame0 = (int)(own0 / a.rows_frame);
+  const int n_runs_cta = n_own > 0 ? (int)((own1 - 1) / a.rows_frame) - frame0 + 1 : 0;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 1);
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kSdFW);
     }
     mbar_fence_init();
     ctx->load_row0 = load_row0;
+    ctx->req = 0;
   }
   __syncthreads();
+  if (n_own <= 0) return;
 
-  if (tid >= kSdNC) {
-    // ---- producer: one lane keeps the ring full; a slot is refilled as soon as the consumers release it
-    if (tid == kSdNC) {
+  if (warp == kSdProdWarp) {
+    // ---- producer: one lane keeps the ring full; a slot is refilled as soon as all filter warps released it
+    if (lane == 0) {
       const uint64_t pol = sd_policy_evict_first();
+      const uint32_t ring_u32 = smem_u32(sd_ring());
+      int slot = 0;
+      uint32_t round = 0;
       for (int c = 0; c < n_chunks; ++c) {
-        const int slot = c & (S - 1);
-        if (c >= S) mbar_wait(&sm.empty[slot], (uint32_t)((c / S - 1) & 1));
+        if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
         const int rows = min(CR, n_load - c * CR);
         const uint32_t bytes = (uint32_t)rows * (uint32_t)W * 4u;
-        mbar_expect_tx(&sm.full[slot], bytes);
-        sd_bulk_g2s(sm.ring + (size_t)slot * CR * W, a.hm + (size_t)(load_row0 + (long long)c * CR) * W, bytes,
-                    &sm.full[slot], pol);
+        mbar_expect_tx(&full[slot], bytes);
+        sd_bulk_g2s(ring_u32 + (uint32_t)slot * (uint32_t)CR * (uint32_t)W * 4u,
+                    a.hm + (size_t)(load_row0 + (long long)c * CR) * W, bytes, smem_u32(&full[slot]), pol);
+        if (++slot == S) {
+          slot = 0;
+          ++round;
+        }
       }
     }
     return;
   }
 
-  // ---- consumers
+  if (warp == kSdMgrWarp) {
+    // ---- manager: while the filter warps stream a run, rescan the histogram whenever enough new candidates were
+    // counted and raise the rejection threshold and the prune floor.  Nobody waits for it.
+    const int every = a.k >= 8 ? a.k / 8 : 1;
+    for (int run = 0; run < n_runs_cta; ++run) {
+      sd_sync_all();  // run begin (the filter warps have reset the shared state)
+      uint32_t last_scan = 0;
+      while (*reinterpret_cast<volatile int*>(&ctx->req) != run + 1) {
+        const uint32_t pushed = *reinterpret_cast<volatile uint32_t*>(&ctx->pushed);
+        if (pushed >= (uint32_t)a.k && (last_scan == 0 || pushed - last_scan >= (uint32_t)every)) {
+          sd_rescan<MODE>(a);
+          last_scan = pushed;
+        } else if (last_scan != 0) {
+          __nanosleep(200);
+        }
+      }
+      sd_rescan<MODE>(a);  // (whatever arrived since the last scan)
+      sd_sync_all();        // every filter warp has finished the run's rows; the floor is final
+    }
+    return;
+  }
+
+  // ---- filter warps
+  const uint32_t ring_u32 = smem_u32(sd_ring());
+  const uint32_t full_u32 = smem_u32(full);
   int spr_shift = -1;
   {
     const int spr = W >> 2;
     if ((spr & (spr - 1)) == 0) spr_shift = 31 - __clz(spr);
   }
-  if (n_own <= 0) return;
-  int done = lead;                  // stream positions [lead, lead + n_own) are this CTA's rows
+  int cnt = 0;       // entries in this warp's sub-list
+  int done = lead;   // stream positions [lead, lead + n_own) are this CTA's rows
+  int rdone = lead;  // ring row of stream row `done`
   const int own_end = lead + n_own;
-  int frame = (int)(own0 / a.rows_frame);
-  sd_run_begin(a, sm, (long long)frame * a.rows_frame);
+  int frame = frame0, run = 0;
+  int frame_end = (int)((long long)(frame + 1) * a.rows_frame - load_row0);  // stream position of the next frame's first row
+  sd_run_reset(a, frame);
+  sd_sync_all();  // run begin
+#ifdef TAUV_SD_DEBUG
+  long long t_wait = 0, t_work = 0, t_end_run = 0, t0 = 0, t1 = 0, t_first = 0;
+  auto now = []() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+  t_first = now();
+#endif
+  int slot = 0, avail = 0;
+  uint32_t round = 0;
 #pragma unroll 1
   for (int c = 0; c < n_chunks; ++c) {
-    mbar_wait(&sm.full[c & (S - 1)], (uint32_t)((c / S) & 1));
-    const int avail = min((c + 1) * CR, n_load);
+#ifdef TAUV_SD_DEBUG
+    t0 = now();
+#endif
+    sd_mbar_wait(full_u32 + (uint32_t)slot * 8u, round & 1);
+#ifdef TAUV_SD_DEBUG
+    t1 = now();
+    t_wait += t1 - t0;
+#endif
+    avail += CR;
     // a row can be tested once the row below it has landed (or does not exist)
-    const int limit = (avail == n_load) ? own_end : min(own_end, avail - 1);
+    const int limit = (c == n_chunks - 1) ? own_end : min(own_end, avail - 1);
     while (done < limit) {
-      const long long frame_end = (long long)(frame + 1) * a.rows_frame - load_row0;  // stream position of the next frame
-      const int seg_end = (int)min((long long)limit, frame_end);
-      sd_rows<MODE>(a, sm, ring_mask, spr_shift, done, seg_end);
+      const int seg_end = min(limit, frame_end);
+      cnt = sd_filter_rows<MODE>(a, ring_u32, ring_rows, spr_shift, done, seg_end, rdone, cnt);
+      rdone += seg_end - done;
+      if (rdone >= ring_rows) rdone -= ring_rows;
       done = seg_end;
-      if ((long long)done == frame_end || done == own_end) {
-        sd_run_end<MODE>(a, sm, frame);
+      if (done == frame_end || done == own_end) {
+        // ---- end of a run
+#ifdef TAUV_SD_DEBUG
+        const long long tr0 = now();
+#endif
+        if (lane == 0) *reinterpret_cast<volatile int*>(&ctx->req) = run + 1;
+        sd_sync_all();  // all rows of the run are filtered and the manager's last scan is published
+        sd_run_end<MODE>(a, frame, cnt);
+        cnt = 0;
         if (done < own_end) {
           ++frame;
-          sd_run_begin(a, sm, (long long)frame * a.rows_frame);
+          ++run;
+          frame_end += a.rows_frame;
+          sd_run_reset(a, frame);
+          sd_sync_all();  // run begin
         }
+#ifdef TAUV_SD_DEBUG
+        t_end_run += now() - tr0;
+#endif
       }
     }
-    // rows of chunk c-1 are no longer needed once every row up to the last-but-one of chunk c is done
-    sd_sync();
-    if (tid == 0 && c >= 1) sd_mbar_arrive(&sm.empty[(c - 1) & (S - 1)]);
+#ifdef TAUV_SD_DEBUG
+    t_work += now() - t1;
+#endif
+    // the rows of the previous chunk are no longer needed by this warp once every row up to the last-but-one of this
+    // chunk is done
+    __syncwarp();
+    if (lane == 0 && c >= 1) sd_mbar_arrive(&empty[slot == 0 ? S - 1 : slot - 1]);
+    if (++slot == S) {
+      slot = 0;
+      ++round;
+    }
   }
+#ifdef TAUV_SD_DEBUG
+  if (lane == 0 && (blockIdx.x % 37) == 0 && (warp % 5) == 0)
+    printf("[sd] cta %d warp %d: chunks %d total %lld ns = wait %lld + work %lld (of which run ends %lld)\n", blockIdx.x, warp,
+           n_chunks, now() - t_first, t_wait, t_work, t_end_run);
+#endif
 }
 
 }  // namespace tauv
