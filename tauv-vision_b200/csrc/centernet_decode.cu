@@ -905,7 +905,7 @@ static int run_stage1(const float* hm, int B, int C, int H, int W, int k, int mo
 
 // ---- the one-launch streaming path (centernet_stream.cuh) ----------------------------------------------------------
 struct StreamPlan {
-  int G, chunk_rows, stages, tbl_rows, row_cap;
+  int G, chunk_rows, stages, tbl_rows, row_cap, sub_cap;
   size_t smem_bytes;
   size_t cand_bytes, count_bytes, ticket_bytes;
 };
@@ -916,15 +916,17 @@ static bool stream_shape_ok(const void* hm, int C, int H, int W, int k) {
 
 static void make_stream_plan(int B, int C, int H, int W, int k, StreamPlan* p) {
   const long long R = (long long)B * C * H;
-  // chunk: whole rows, about 16 KB (one filter iteration of the 16 warps); ring: as many chunks as fit beside the
-  // candidate lists (measured, profiles/r2_stream_bench_v*.txt: ~100 KB per SM in flight keeps HBM busy; a slot is only
-  // released one chunk late because the 3x3 test of a chunk's last row needs the next chunk's first)
-  int cr = 16384 / (W * 4);
+  // chunk: whole rows, about 32 KB (one filter iteration of the 16 warps); private sub-lists of 256 entries per
+  // filter warp for k <= 128, 512 for k <= 256; ring: as many chunks as fit beside them (measured,
+  // profiles/r2_stream_bench_v*.txt: ~100 KB per SM in flight keeps HBM busy, and a slot is only released one chunk late
+  // because the 3x3 test of a chunk's last row needs the next chunk's first)
+  int cr = 32768 / (W * 4);
   if (cr < 1) cr = 1;
   p->chunk_rows = cr;
-  const size_t fixed = sd_smem_bytes(0, 0, W);
+  p->sub_cap = k <= 128 ? 256 : 512;
+  const size_t fixed = sd_smem_bytes(0, 0, W, p->sub_cap);
   int st = (int)((227 * 1024 - fixed) / ((size_t)cr * W * 4));
-  if (st > 12) st = 12;
+  if (st > 8) st = 8;
   p->stages = st;
   long long G = num_sms();          // one CTA per SM (the ring takes most of the shared memory)
   const long long min_rows = 8;     // tiny inputs: fewer CTAs rather than CTAs without rows
@@ -936,7 +938,7 @@ static void make_stream_plan(int B, int C, int H, int W, int k, StreamPlan* p) {
   if (tr > G) tr = G;
   p->tbl_rows = (int)tr;
   p->row_cap = 2 * k;
-  p->smem_bytes = sd_smem_bytes(p->chunk_rows, p->stages, W);
+  p->smem_bytes = sd_smem_bytes(p->chunk_rows, p->stages, W, p->sub_cap);
   p->cand_bytes = align_up((size_t)B * p->tbl_rows * (size_t)p->row_cap * 8, 256);
   p->count_bytes = align_up((size_t)B * p->tbl_rows * 4, 256);
   p->ticket_bytes = align_up((size_t)B * 8, 256);
@@ -966,8 +968,10 @@ static int run_stream(const float* hm, int B, int C, int H, int W, int k, int mo
   a.rows_frame = C * H;
   a.chunk_rows = p.chunk_rows; a.stages = p.stages;
   {
-    const SdLayout l = sd_layout(p.chunk_rows, p.stages, W);
-    a.off_list = l.off_list; a.off_bins = l.off_bins; a.off_flags = l.off_flags; a.off_bars = l.off_bars; a.off_ctx = l.off_ctx;
+    const SdLayout l = sd_layout(p.chunk_rows, p.stages, W, p.sub_cap);
+    a.off_list = l.off_list; a.off_bins = l.off_bins; a.off_flags = l.off_flags; a.off_pend = l.off_pend;
+    a.off_bars = l.off_bars; a.off_ctx = l.off_ctx;
+    a.sub_cap = p.sub_cap;
   }
   a.tbl_rows = p.tbl_rows; a.row_cap = p.row_cap;
   unsigned char* w = reinterpret_cast<unsigned char*>(ws);

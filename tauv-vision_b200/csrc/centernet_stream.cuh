@@ -48,12 +48,13 @@ constexpr int kSdMgrWarp = kSdFW;              // warp 16: threshold manager
 constexpr int kSdProdWarp = kSdFW + 1;         // warp 17: one lane issues the bulk copies
 constexpr int kSdNA = (kSdFW + 1) * 32;        // filter + manager threads (joint barriers)
 constexpr int kSdThreads = (kSdFW + 2) * 32;
-constexpr int kSdListCap = 8192;               // candidate entries in shared memory, all sub-lists together
-constexpr int kSdSub = kSdListCap / kSdFW;     // private sub-list of a filter warp (512 entries)
-constexpr int kSdMaxK = kSdSub / 2;            // a warp can always prune its own sub-list to k and have room again
+constexpr int kSdListCap = 8192;               // candidate entries in shared memory, all sub-lists together (at most)
+constexpr int kSdSubMax = kSdListCap / kSdFW;  // private sub-list of a filter warp: 512 entries (k <= 256) or 256 (k <= 128)
+constexpr int kSdMaxK = kSdSubMax / 2;         // a warp can always prune its own sub-list to k and have room again
 constexpr int kSdMaxW = 1024;
 constexpr int kSdMaxStages = 16;
-constexpr int kSdU = 2;                        // 128-bit strips per thread and filter iteration
+constexpr int kSdU = 4;                        // 128-bit strips per thread and filter iteration
+constexpr int kSdPend = 64;                    // per filter warp: peaks waiting for their sigmoid + push (flushed 32 at a time)
 
 using SdSyncAll = SyncNamed<1, kSdNA>;         // filter warps + manager
 using SdSyncF = SyncNamed<2, kSdNF>;           // filter warps only
@@ -67,7 +68,8 @@ struct SdArgs {
   long long rows_total;   // R = B*C*H
   int rows_frame;         // C*H
   int chunk_rows, stages; // rows per bulk copy, ring slots
-  int off_list, off_bins, off_flags, off_bars, off_ctx;  // byte offsets of the shared-memory regions (host-computed)
+  int off_list, off_bins, off_flags, off_pend, off_bars, off_ctx;  // byte offsets of the shared-memory regions (host-computed)
+  int sub_cap;            // entries of a filter warp's private sub-list (>= 2k; a power of two)
   int tbl_rows, row_cap;  // candidate table: rows per frame, entries per row (2k)
   unsigned long long* cand;    // [B][tbl_rows][row_cap]
   int* cand_count;             // [B][tbl_rows]
@@ -80,7 +82,8 @@ struct SdArgs {
 };
 
 struct __align__(16) SdCtx {
-  unsigned long long floor_key;  // lowest final key that can still matter according to the histogram (0: none yet)
+  int found_bin;                 // window bin that holds the k-th best candidate counted so far (-1: fewer than k)
+  int pad0;
   unsigned long long warpT[kSdFW]; // exact composite threshold of a filter warp (0: none): later entries <= T cannot matter
   long long load_row0;           // global row held at stream position 0
   long long frame_row0;          // global row of the current frame's first row
@@ -94,7 +97,10 @@ struct __align__(16) SdCtx {
   int base;
   int wsum[kSdFW];
   uint32_t sel[8];
-  int scratch[kSdFW][32];        // per filter warp: strip indices of an iteration's hot strips, packed
+  // geometry of this CTA's range (written once) and where each filter warp stands in it (kept here between runs so that
+  // the streaming loop — a function of its own — starts from a clean register file)
+  int n_chunks, n_load, own_end;
+  struct { int c, slot, round, done, rdone, pad[3]; } st[kSdFW];
 };
 
 __device__ __forceinline__ uint64_t sd_policy_evict_first() {
@@ -145,18 +151,20 @@ __device__ __forceinline__ float sd_lds1(uint32_t addr) {
 // mbarriers | ctx.  The host computes the byte offsets (SdArgs::off_*) so that device code reaches a region with one
 // constant-bank load and an add; a struct of pointers handed around by reference would live in local memory.
 struct SdLayout {
-  int off_list, off_bins, off_flags, off_bars, off_ctx;
+  int off_list, off_bins, off_flags, off_pend, off_bars, off_ctx;
   size_t total;
 };
-__host__ __device__ inline SdLayout sd_layout(int chunk_rows, int stages, int W) {
+__host__ __device__ inline SdLayout sd_layout(int chunk_rows, int stages, int W, int sub_cap) {
   SdLayout l;
   size_t o = (size_t)stages * chunk_rows * W * 4;
   l.off_list = (int)o;
-  o += (size_t)kSdListCap * 8;
+  o += (size_t)kSdFW * sub_cap * 8;
   l.off_bins = (int)o;
   o += (size_t)kClBins * 4;
   l.off_flags = (int)o;
   o += (size_t)kSdMaxK * 4;
+  l.off_pend = (int)o;
+  o += (size_t)kSdFW * kSdPend * 8;
   l.off_bars = (int)o;
   o += 2 * kSdMaxStages * 8;
   l.off_ctx = (int)o;
@@ -164,7 +172,9 @@ __host__ __device__ inline SdLayout sd_layout(int chunk_rows, int stages, int W)
   l.total = o + 128;
   return l;
 }
-__host__ __device__ inline size_t sd_smem_bytes(int chunk_rows, int stages, int W) { return sd_layout(chunk_rows, stages, W).total; }
+__host__ __device__ inline size_t sd_smem_bytes(int chunk_rows, int stages, int W, int sub_cap) {
+  return sd_layout(chunk_rows, stages, W, sub_cap).total;
+}
 __device__ __forceinline__ unsigned char* sd_smem() {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   return smem_raw;
@@ -173,6 +183,7 @@ __device__ __forceinline__ float* sd_ring() { return reinterpret_cast<float*>(sd
 __device__ __forceinline__ unsigned long long* sd_list(const SdArgs& a) { return reinterpret_cast<unsigned long long*>(sd_smem() + a.off_list); }
 __device__ __forceinline__ uint32_t* sd_bins(const SdArgs& a) { return reinterpret_cast<uint32_t*>(sd_smem() + a.off_bins); }
 __device__ __forceinline__ uint32_t* sd_flags(const SdArgs& a) { return reinterpret_cast<uint32_t*>(sd_smem() + a.off_flags); }
+__device__ __forceinline__ uint2* sd_pend(const SdArgs& a) { return reinterpret_cast<uint2*>(sd_smem() + a.off_pend); }
 __device__ __forceinline__ uint64_t* sd_full(const SdArgs& a) { return reinterpret_cast<uint64_t*>(sd_smem() + a.off_bars); }
 __device__ __forceinline__ uint64_t* sd_empty(const SdArgs& a) { return sd_full(a) + kSdMaxStages; }
 __device__ __forceinline__ SdCtx* sd_ctx(const SdArgs& a) { return reinterpret_cast<SdCtx*>(sd_smem() + a.off_ctx); }
@@ -214,11 +225,14 @@ template <int MODE>
 __device__ __noinline__ int sd_warp_prune(const SdArgs& a, int cnt) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   SdCtx* const ctx = sd_ctx(a);
-  unsigned long long* sub = sd_list(a) + (size_t)warp * kSdSub;
-  const unsigned long long fl = *reinterpret_cast<volatile unsigned long long*>(&ctx->floor_key);
-  if (fl > 1ull) cnt = sd_warp_compact(sub, cnt, [&](unsigned long long c) { return c >= fl; });
-  if (cnt <= kSdSub / 2) return cnt;
-  // k-th largest of cnt (> kSdSub/2 >= k) distinct keys, one bit at a time from the top
+  unsigned long long* sub = sd_list(a) + (size_t)warp * a.sub_cap;
+  const int fb = *reinterpret_cast<volatile int*>(&ctx->found_bin);
+  if (fb >= 0) {  // nothing below the lower edge of the bin that holds the k-th best candidate can matter
+    const unsigned long long fl = sd_bin_floor<MODE>(fb);
+    cnt = sd_warp_compact(sub, cnt, [&](unsigned long long c) { return c >= fl; });
+  }
+  if (cnt <= a.sub_cap / 2) return cnt;
+  // k-th largest of cnt (> sub_cap/2 >= k) distinct keys, one bit at a time from the top
   unsigned long long T = 0ull;
   for (int bit = 63; bit >= 0; --bit) {
     const unsigned long long cand = T | (1ull << bit);
@@ -240,182 +254,276 @@ __device__ __noinline__ int sd_warp_prune(const SdArgs& a, int cnt) {
   return cnt;
 }
 
-// Full test of up to 32 strips that passed the threshold scan, one per lane (`mine`: this lane has one: stream row p,
-// column col), then the pushes.  Warp-convergent.  The rows above and below come from the ring (the halo rows of a
-// range are loaded with it); rows outside the plane do not exist (-inf padding, decode.py:245-250).  Peaks at or
-// above the threshold get their sigmoid, a composite key, a slot in the warp's private sub-list and a count in the
-// shared histogram (fire-and-forget shared-memory reductions).  Returns the sub-list's new length.
+// 3x3 test of one 128-bit strip that passed the threshold scan (called by the hot lanes only): stream row p held in
+// ring row rp, column col, values x.  The rows above and below come from the ring (the halo rows of a range are
+// loaded with it); rows outside the plane do not exist (-inf padding, decode.py:245-250).  Returns the flat index of
+// the strip's first cell << 8 | a 4-bit mask of the cells that are candidates (3x3 peaks at or above the threshold;
+// RAW: cells at or above the threshold).
 template <int MODE>
-__device__ __noinline__ int sd_examine(const SdArgs& a, uint32_t ring_u32, int ring_rows, bool mine, int p, int rp, int col,
-                                       float thr_f, int cnt) {
+__device__ __forceinline__ unsigned long long sd_peaks(const SdArgs& a, uint32_t ring_u32, int ring_rows, int fr_base, int p, int rp,
+                                                    int col, float thr_f) {
+  const int W = a.W;
+  const int fr = fr_base + p;  // row inside the frame
+  const uint32_t flat = (uint32_t)fr * (uint32_t)W + (uint32_t)col;
+  const float4 x = sd_lds4(ring_u32 + (uint32_t)rp * (uint32_t)W * 4u + (uint32_t)col * 4u);
+  const float xs[4] = {x.x, x.y, x.z, x.w};
+  unsigned mask = 0u;
+  if (MODE != TAUV_TOPK_SIGMOID_PEAK) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) mask |= (xs[cc] >= thr_f) ? (1u << cc) : 0u;
+  } else {
+    const uint32_t rowb = (uint32_t)W * 4u;
+    const uint32_t mid = ring_u32 + (uint32_t)rp * rowb + (uint32_t)col * 4u;
+    const int y = (a.H & (a.H - 1)) == 0 ? (fr & (a.H - 1)) : fr % a.H;
+    const float NI = TAUV_NEG_INF;
+    const bool hl = col > 0, hr = col + 4 < W;
+    float4 u = make_float4(NI, NI, NI, NI), d = u;
+    float ul = NI, ur = NI, dl = NI, dr = NI;
+    if (y > 0) {
+      const uint32_t up = ring_u32 + (uint32_t)(rp == 0 ? ring_rows - 1 : rp - 1) * rowb + (uint32_t)col * 4u;
+      u = sd_lds4(up);
+      if (hl) ul = sd_lds1(up - 4);
+      if (hr) ur = sd_lds1(up + 16);
+    }
+    if (y + 1 < a.H) {
+      const uint32_t dn = ring_u32 + (uint32_t)(rp + 1 == ring_rows ? 0 : rp + 1) * rowb + (uint32_t)col * 4u;
+      d = sd_lds4(dn);
+      if (hl) dl = sd_lds1(dn - 4);
+      if (hr) dr = sd_lds1(dn + 16);
+    }
+    const float ml = hl ? sd_lds1(mid - 4) : NI, mr = hr ? sd_lds1(mid + 16) : NI;
+    float cm[6];  // column-wise max over the three rows, columns col-1 .. col+4
+    cm[0] = fmaxf(fmaxf(ul, ml), dl);
+    cm[1] = fmaxf(fmaxf(u.x, x.x), d.x);
+    cm[2] = fmaxf(fmaxf(u.y, x.y), d.y);
+    cm[3] = fmaxf(fmaxf(u.z, x.z), d.z);
+    cm[4] = fmaxf(fmaxf(u.w, x.w), d.w);
+    cm[5] = fmaxf(fmaxf(ur, mr), dr);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const float xv = xs[cc];
+      if (xv >= thr_f) {
+        const float m = fmaxf(fmaxf(cm[cc], cm[cc + 1]), cm[cc + 2]);
+        bool peak = (xv >= m);
+        // x < m can still tie after the sigmoid (saturation, sub-ulp gap): the reference compares sigmoid values
+        if (!peak && (xv > 4.0f || m < -80.0f || (m - xv) < 1e-3f)) peak = sigmoid_tie(xv, m);
+        if (peak) mask |= 1u << cc;
+      }
+    }
+  }
+  return ((unsigned long long)flat << 8) | mask;
+}
+
+// Push the first n (<= 32) waiting peaks of this warp, all lanes at once: sigmoid, composite key, a slot in the warp's
+// private sub-list; then move the rest of the waiting list (npend - n entries) to its front.  Warp-convergent.
+// Returns the sub-list's new length.
+template <int MODE>
+__device__ __forceinline__ int sd_flush(const SdArgs& a, int n, int npend, int cnt) {
   SdCtx* const ctx = sd_ctx(a);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int W = a.W;
-  const uint32_t rowb = (uint32_t)W * 4u;
-  float xs[4] = {0.f, 0.f, 0.f, 0.f};
-  bool cand[4] = {false, false, false, false};
-  uint32_t flat = 0;
-  if (mine) {
-    const int fr = (int)(ctx->load_row0 + p - ctx->frame_row0);  // row inside the frame
-    flat = (uint32_t)fr * (uint32_t)W + (uint32_t)col;
-    const uint32_t mid = ring_u32 + (uint32_t)rp * rowb + (uint32_t)col * 4u;  // rp: the ring row that holds stream row p
-    const float4 x = sd_lds4(mid);
-    xs[0] = x.x; xs[1] = x.y; xs[2] = x.z; xs[3] = x.w;
-    if (MODE != TAUV_TOPK_SIGMOID_PEAK) {
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) cand[cc] = xs[cc] >= thr_f;
+  uint2* const pend = sd_pend(a) + warp * kSdPend;
+  unsigned long long* const sub = sd_list(a) + (size_t)warp * a.sub_cap;
+  bool ok = lane < n;
+  unsigned long long c = 0ull;
+  if (ok) {
+    const uint2 e = pend[lane];
+    const float x = __uint_as_float(e.x);
+    uint32_t key;
+    if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
+      const float s = sigmoid_ref(x);
+      ok = s > 0.0f;  // underflowed to 0: zero-valued cells are supplied by the filler, like non-peaks
+      key = float_to_key(s);
     } else {
-      const int y = (a.H & (a.H - 1)) == 0 ? (fr & (a.H - 1)) : fr % a.H;
-      const float NI = TAUV_NEG_INF;
-      const bool hl = col > 0, hr = col + 4 < W;
-      float4 u = make_float4(NI, NI, NI, NI), d = u;
-      float ul = NI, ur = NI, dl = NI, dr = NI;
-      if (y > 0) {
-        const uint32_t up = ring_u32 + (uint32_t)(rp == 0 ? ring_rows - 1 : rp - 1) * rowb + (uint32_t)col * 4u;
-        u = sd_lds4(up);
-        if (hl) ul = sd_lds1(up - 4);
-        if (hr) ur = sd_lds1(up + 16);
-      }
-      if (y + 1 < a.H) {
-        const uint32_t dn = ring_u32 + (uint32_t)(rp + 1 == ring_rows ? 0 : rp + 1) * rowb + (uint32_t)col * 4u;
-        d = sd_lds4(dn);
-        if (hl) dl = sd_lds1(dn - 4);
-        if (hr) dr = sd_lds1(dn + 16);
-      }
-      const float ml = hl ? sd_lds1(mid - 4) : NI, mr = hr ? sd_lds1(mid + 16) : NI;
-      float cm[6];  // column-wise max over the three rows, columns col-1 .. col+4
-      cm[0] = fmaxf(fmaxf(ul, ml), dl);
-      cm[1] = fmaxf(fmaxf(u.x, x.x), d.x);
-      cm[2] = fmaxf(fmaxf(u.y, x.y), d.y);
-      cm[3] = fmaxf(fmaxf(u.z, x.z), d.z);
-      cm[4] = fmaxf(fmaxf(u.w, x.w), d.w);
-      cm[5] = fmaxf(fmaxf(ur, mr), dr);
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const float xv = xs[cc];
-        if (xv >= thr_f) {
-          const float m = fmaxf(fmaxf(cm[cc], cm[cc + 1]), cm[cc + 2]);
-          bool peak = (xv >= m);
-          // x < m can still tie after the sigmoid (saturation, sub-ulp gap): the reference compares sigmoid values
-          if (!peak && (xv > 4.0f || m < -80.0f || (m - xv) < 1e-3f)) peak = sigmoid_tie(xv, m);
-          cand[cc] = peak;
-        }
-      }
+      key = float_to_key(x);
     }
+    c = make_composite(key, e.y);
+    ok = ok && c > ctx->warpT[warp];
   }
-  unsigned long long* const sub = sd_list(a) + (size_t)warp * kSdSub;
+  const uint2 tail = (lane + 32 < npend) ? pend[lane + 32] : make_uint2(0u, 0u);
+  __syncwarp();
+  if (lane + 32 < npend) pend[lane] = tail;
+  unsigned bal = __ballot_sync(0xffffffffu, ok);
+  if (bal == 0u) return cnt;
+  if (cnt + __popc(bal) > a.sub_cap) {
+    cnt = sd_warp_prune<MODE>(a, cnt);
+    ok = ok && c > ctx->warpT[warp];
+    bal = __ballot_sync(0xffffffffu, ok);
+    if (bal == 0u) return cnt;
+  }
+  if (ok) sub[cnt + __popc(bal & ((1u << lane) - 1u))] = c;
+  return cnt + __popc(bal);
+}
+
+// What a filter warp carries through the stream (all warp-uniform)
+struct SdWarpState {
+  int cnt;    // entries in the warp's private sub-list
+  int npend;  // peaks waiting in the warp's pending buffer (< 32 between iterations)
+};
+__device__ __forceinline__ int sd_pack(const SdWarpState& w) { return w.cnt | (w.npend << 16); }
+__device__ __forceinline__ SdWarpState sd_unpack(int v) { return SdWarpState{v & 0xffff, v >> 16}; }
+
+// The rare part of a filter iteration: lanes whose strip s (relative to the part that starts at stream row p0 / ring
+// row rp0) is hot run the 3x3 test; the peaks they find are appended to the warp's pending buffer, which is flushed
+// 32 at a time.  Warp-convergent; written for few registers and little code (runtime loops, one call site each).
+template <int MODE>
+__device__ __forceinline__ int sd_hot(const SdArgs& a, uint32_t ring_u32, int ring_rows, int spr_shift, int fr_base, int p0, int rp0,
+                                   int s_first, unsigned hotmask, float thr_f, int wstate) {
+  SdWarpState w = sd_unpack(wstate);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int spr = a.W >> 2;
+  uint2* const pend = sd_pend(a) + (tid >> 5) * kSdPend;
   uint32_t* const bins = sd_bins(a);
-#pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    if (!__any_sync(0xffffffffu, cand[cc])) continue;
-    const float x = xs[cc];
-    bool ok = cand[cc];
-    unsigned long long c = 0ull;
-    if (ok) {
-      uint32_t key;
-      if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
-        const float s = sigmoid_ref(x);
-        ok = s > 0.0f;  // underflowed to 0: zero-valued cells are supplied by the filler, like non-peaks
-        key = float_to_key(s);
-      } else {
-        key = float_to_key(x);
-      }
-      c = make_composite(key, flat + cc);
-      ok = ok && c > ctx->warpT[warp];
+  SdCtx* const ctx = sd_ctx(a);
+#pragma unroll 1
+  for (int u = 0; u < kSdU; ++u) {
+    const bool h = (hotmask >> u) & 1u;
+    if (!__any_sync(0xffffffffu, h)) continue;
+    unsigned long long pk = 0ull;
+    uint32_t xaddr = 0;
+    if (h) {
+      const int s = s_first + u * kSdNF;
+      const int r = spr_shift >= 0 ? (s >> spr_shift) : (s / spr);
+      const int col = (s - r * spr) << 2;
+      pk = sd_peaks<MODE>(a, ring_u32, ring_rows, fr_base, p0 + r, rp0 + r, col, thr_f);
+      xaddr = ring_u32 + (uint32_t)(rp0 + r) * (uint32_t)a.W * 4u + (uint32_t)col * 4u;
     }
-    unsigned bal = __ballot_sync(0xffffffffu, ok);
-    if (bal == 0u) continue;
-    if (cnt + __popc(bal) > kSdSub) {
-      cnt = sd_warp_prune<MODE>(a, cnt);
-      ok = ok && c > ctx->warpT[warp];
-      bal = __ballot_sync(0xffffffffu, ok);
+    if (!__any_sync(0xffffffffu, (pk & 15ull) != 0ull)) continue;
+    const uint32_t flat = (uint32_t)(pk >> 8);
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      const bool cand = (pk >> cc) & 1ull;
+      const unsigned bal = __ballot_sync(0xffffffffu, cand);
       if (bal == 0u) continue;
-    }
-    if (ok) {
-      sub[cnt + __popc(bal & ((1u << lane) - 1u))] = c;
-      // the histogram counts every candidate once, in logit / value space
-      if (MODE != TAUV_TOPK_SIGMOID_PEAK || x > -80.0f) {
-        const int bin = cl_window_bin(float_to_key(x));
-        if (bin >= 0) {
-          atomicAdd(&bins[bin], 1u);
-          if ((uint32_t)bin > *reinterpret_cast<volatile uint32_t*>(&ctx->maxbin)) atomicMax(&ctx->maxbin, (uint32_t)bin);
+      if (cand) {
+        const float x = sd_lds1(xaddr + 4u * cc);
+        pend[w.npend + __popc(bal & ((1u << lane) - 1u))] = make_uint2(__float_as_uint(x), flat + cc);
+        // the histogram counts every candidate once, at once (the threshold must not lag behind what waits here), in
+        // logit / value space, with fire-and-forget shared-memory reductions
+        if (MODE != TAUV_TOPK_SIGMOID_PEAK || x > -80.0f) {
+          const int bin = cl_window_bin(float_to_key(x));
+          if (bin >= 0) {
+            atomicAdd(&bins[bin], 1u);
+            if ((uint32_t)bin > *reinterpret_cast<volatile uint32_t*>(&ctx->maxbin)) atomicMax(&ctx->maxbin, (uint32_t)bin);
+          }
         }
       }
+      if (lane == 0) atomicAdd(&ctx->pushed, (uint32_t)__popc(bal));
+      w.npend += __popc(bal);
+      __syncwarp();
+      if (w.npend >= 32) {
+        w.cnt = sd_flush<MODE>(a, 32, w.npend, w.cnt);
+        w.npend -= 32;
+      }
     }
-    cnt += __popc(bal);
-    if (lane == 0) atomicAdd(&ctx->pushed, (uint32_t)__popc(bal));
   }
-  return cnt;
+  return sd_pack(w);
 }
 
 // Threshold scan of this warp's share of the stream rows [p0, p1) (one frame; rp0 = ring row of p0; the rows are
 // contiguous in the ring): the warp takes every kSdFW-th group of 32 consecutive 128-bit strips, kSdU groups in flight.
-// Strips whose maximum reaches the threshold are packed — the j-th hot strip of the iteration goes to lane j, through
-// a 32-word scratch of the warp — and examined together.
+// Only lanes whose strip maximum reaches the threshold run the 3x3 test; the peaks they find wait in the warp's pending
+// buffer until 32 are there, so that the expensive part (sigmoid, keys, list, histogram) always runs on full warps.
 template <int MODE>
-__device__ __forceinline__ int sd_filter_part(const SdArgs& a, uint32_t ring_u32, int ring_rows, int spr_shift, int p0, int p1,
-                                              int rp0, int cnt) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int spr = a.W >> 2;
-  const int n = (p1 - p0) * spr;
-  const uint32_t base = ring_u32 + (uint32_t)rp0 * (uint32_t)a.W * 4u;
-  const uint32_t thr_addr = smem_u32(&sd_ctx(a)->thr_key);
+__device__ __forceinline__ int sd_filter_part(const SdArgs& a, uint32_t ring_u32, int ring_rows, int spr_shift, int fr_base,
+                                              int p0, int p1, int rp0, int wstate) {
+  const int tid = threadIdx.x;
+  const int n = (p1 - p0) * (a.W >> 2);
+  const uint32_t base = ring_u32 + (uint32_t)rp0 * (uint32_t)a.W * 4u + (uint32_t)tid * 16u;
+  const uint32_t thr_addr = ring_u32 + (uint32_t)a.off_ctx + (uint32_t)offsetof(SdCtx, thr_key);
   const float NI = TAUV_NEG_INF;
 #pragma unroll 1
-  for (int s0 = 0; s0 < n; s0 += kSdU * kSdNF) {
+  for (int sb = 0; sb < n; sb += kSdU * kSdNF) {  // (warp-uniform trip count: the body votes)
+    const int s0 = sb + tid;
     const uint32_t tk = sd_lds_u32_volatile(thr_addr);
     const float thr_f = tk ? key_to_float(tk) : NI;
-    float4 v[kSdU];
+    unsigned hotmask = 0u;
 #pragma unroll
     for (int u = 0; u < kSdU; ++u) {
-      const int s = s0 + u * kSdNF + tid;
-      v[u] = (s < n) ? sd_lds4(base + (uint32_t)s * 16u) : make_float4(NI, NI, NI, NI);
-    }
-    unsigned bal[kSdU];
-    unsigned any = 0u;
-#pragma unroll
-    for (int u = 0; u < kSdU; ++u) {
-      const float m = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
-      bal[u] = __ballot_sync(0xffffffffu, (m >= thr_f) && (s0 + u * kSdNF + tid < n));
-      any |= bal[u];
-    }
-    if (any == 0u) continue;
-    // pack: hot strip -> its rank among the iteration's hot strips -> scratch[rank] = strip index
-    int* scratch = sd_ctx(a)->scratch[tid >> 5];
-    int total = 0;
-#pragma unroll 1
-    for (int j0 = 0;; j0 += 32) {
-      __syncwarp();
-      int before = 0;
-#pragma unroll
-      for (int u = 0; u < kSdU; ++u) {
-        if (bal[u] & (1u << lane)) {
-          const int rank = before + __popc(bal[u] & ((1u << lane) - 1u)) - j0;
-          if (rank >= 0 && rank < 32) scratch[rank] = s0 + u * kSdNF + tid;
-        }
-        before += __popc(bal[u]);
+      const int s = s0 + u * kSdNF;
+      if (s < n) {
+        const float4 v = sd_lds4(base + (uint32_t)(s - tid) * 16u);
+        const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        hotmask |= (m >= thr_f) ? (1u << u) : 0u;
       }
-      total = before;
-      __syncwarp();
-      const bool mine = j0 + lane < total;
-      const int s = mine ? scratch[lane] : 0;
-      const int r = spr_shift >= 0 ? (s >> spr_shift) : (s / spr);
-      cnt = sd_examine<MODE>(a, ring_u32, ring_rows, mine, p0 + r, rp0 + r, (s - r * spr) << 2, thr_f, cnt);
-      if (j0 + 32 >= total) break;
     }
+#if defined(TAUV_SD_EXP) && TAUV_SD_EXP == 1
+    if (false)
+#elif defined(TAUV_SD_EXP) && TAUV_SD_EXP == 2
+    if (__any_sync(0xffffffffu, hotmask != 0u) && tk == 0u)
+#else
+    if (__any_sync(0xffffffffu, hotmask != 0u))
+#endif
+      wstate = sd_hot<MODE>(a, ring_u32, ring_rows, spr_shift, fr_base, p0, rp0, s0, hotmask, thr_f, wstate);
   }
-  return cnt;
+  return wstate;
 }
 
 // rows [p0, p1) of one frame; rp0 = ring row of p0
 template <int MODE>
-__device__ __forceinline__ int sd_filter_rows(const SdArgs& a, uint32_t ring_u32, int ring_rows, int spr_shift, int p0, int p1,
-                                              int rp0, int cnt) {
+__device__ __forceinline__ int sd_filter_rows(const SdArgs& a, uint32_t ring_u32, int ring_rows, int spr_shift, int fr_base,
+                                              int p0, int p1, int rp0, int wstate) {
   // split where the ring wraps so that each part is one contiguous run of strips in shared memory
   const int n1 = ring_rows - rp0;
-  if (p1 - p0 <= n1) return sd_filter_part<MODE>(a, ring_u32, ring_rows, spr_shift, p0, p1, rp0, cnt);
-  cnt = sd_filter_part<MODE>(a, ring_u32, ring_rows, spr_shift, p0, p0 + n1, rp0, cnt);
-  return sd_filter_part<MODE>(a, ring_u32, ring_rows, spr_shift, p0 + n1, p1, 0, cnt);
+  if (p1 - p0 <= n1) return sd_filter_part<MODE>(a, ring_u32, ring_rows, spr_shift, fr_base, p0, p1, rp0, wstate);
+  wstate = sd_filter_part<MODE>(a, ring_u32, ring_rows, spr_shift, fr_base, p0, p0 + n1, rp0, wstate);
+  return sd_filter_part<MODE>(a, ring_u32, ring_rows, spr_shift, fr_base, p0 + n1, p1, 0, wstate);
+}
+
+// A filter warp streams its share of one run: from where it stands (ctx->st) to the end of the frame or of the CTA's
+// range, chunk by chunk as they land.  A function of its own so that the hot loop is compiled with nothing else live.
+// frame_end: stream position of the next frame's first row; fr_base: row inside the frame of stream position 0.
+// Returns the length of the warp's sub-list (the pending peaks are flushed before it returns).
+template <int MODE>
+__device__ __forceinline__ int sd_stream_run(const SdArgs& a, int frame_end, int fr_base) {
+  SdCtx* const ctx = sd_ctx(a);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int CR = a.chunk_rows, S = a.stages, ring_rows = CR * S;
+  const uint32_t ring_u32 = smem_u32(sd_ring());
+  const uint32_t full_u32 = ring_u32 + (uint32_t)a.off_bars;
+  const int n_chunks = ctx->n_chunks, n_load = ctx->n_load, own_end = ctx->own_end;
+  int spr_shift = -1;
+  {
+    const int spr = a.W >> 2;
+    if ((spr & (spr - 1)) == 0) spr_shift = 31 - __clz(spr);
+  }
+  int c = ctx->st[warp].c, slot = ctx->st[warp].slot, round = ctx->st[warp].round;
+  int done = ctx->st[warp].done, rdone = ctx->st[warp].rdone;
+  int wstate = 0;
+#pragma unroll 1
+  while (c < n_chunks) {
+    sd_mbar_wait(full_u32 + (uint32_t)slot * 8u, (uint32_t)round & 1u);
+    const int avail = min((c + 1) * CR, n_load);
+    // a row can be tested once the row below it has landed (or does not exist)
+    const int limit = (c == n_chunks - 1) ? own_end : min(own_end, avail - 1);
+    const int seg_end = min(limit, frame_end);
+    if (done < seg_end) {
+      wstate = sd_filter_rows<MODE>(a, ring_u32, ring_rows, spr_shift, fr_base, done, seg_end, rdone, wstate);
+      rdone += seg_end - done;
+      if (rdone >= ring_rows) rdone -= ring_rows;
+      done = seg_end;
+    }
+    if (done == frame_end || done == own_end) break;  // the run ends here (possibly in the middle of this chunk)
+    // the rows of the previous chunk are no longer needed by this warp once every row up to the last-but-one of this
+    // chunk is done
+    __syncwarp();
+    if (lane == 0 && c >= 1) sd_mbar_arrive(sd_empty(a) + (slot == 0 ? S - 1 : slot - 1));
+    ++c;
+    if (++slot == S) {
+      slot = 0;
+      ++round;
+    }
+  }
+  if (lane == 0) {
+    ctx->st[warp].c = c;
+    ctx->st[warp].slot = slot;
+    ctx->st[warp].round = round;
+    ctx->st[warp].done = done;
+    ctx->st[warp].rdone = rdone;
+  }
+  SdWarpState w = sd_unpack(wstate);
+  if (w.npend > 0) w.cnt = sd_flush<MODE>(a, w.npend, w.npend, w.cnt);
+  __syncwarp();
+  return w.cnt;
 }
 
 // ---- manager warp ---------------------------------------------------------------------------------------------------
@@ -444,19 +552,28 @@ __device__ __forceinline__ int sd_scan_bin(const SdArgs& a) {
   return found;
 }
 
-// Rescan the bins and raise the cheap filter and the prune floor.
+// Key of a logit (value) x_c below which nothing can reach the k-th best score, given that at least k candidates have
+// logits (values) >= edge.  SIGMOID_PEAK: every x < x_c must have sigmoid(x) strictly below sigmoid(edge) by a relative
+// 2e-5 (the guard band reject_key_for_score keeps against the last-bit wobble of expf and against ties after the
+// sigmoid); since d sigmoid / sigmoid = (1 - s) dx, a margin of 5e-5 (1 + e^x) does it, and 1e-3 max(1, |x|) as well
+// for x <= 0.  Far out (saturation, denormal scores) the exact routine decides.
+template <int MODE>
+__device__ __forceinline__ uint32_t sd_reject_key(float edge) {
+  if (MODE != TAUV_TOPK_SIGMOID_PEAK) return float_to_key(edge);
+  if (!(edge < 12.0f) || !(edge > -60.0f)) return reject_key_for_score(sigmoid_ref(edge));
+  const float margin = fmaxf(1e-3f * fmaxf(1.0f, fabsf(edge)), 5e-5f * (1.0f + __expf(edge) * 1.01f));
+  return float_to_key(edge - margin);
+}
+
+// Rescan the bins and raise the cheap filter; remember the bin (the prune floor is derived from it when needed).
 template <int MODE>
 __device__ __forceinline__ void sd_rescan(const SdArgs& a) {
   SdCtx* const ctx = sd_ctx(a);
   const int found = sd_scan_bin(a);
-  if ((threadIdx.x & 31) == 0 && found >= 0) {
-    const float edge = cl_window_edge(found);  // at least k candidates of this frame have logit/value >= edge
-    uint32_t key;
-    if (MODE == TAUV_TOPK_SIGMOID_PEAK) key = reject_key_for_score(sigmoid_ref(edge));
-    else key = float_to_key(edge);
+  if ((threadIdx.x & 31) == 0 && found > ctx->found_bin) {
+    const uint32_t key = sd_reject_key<MODE>(cl_window_edge(found));  // at least k candidates have logit/value >= edge
     if (key) atomicMax(&ctx->thr_key, key);
-    const unsigned long long fl = sd_bin_floor<MODE>(found);
-    if (fl > ctx->floor_key) *reinterpret_cast<volatile unsigned long long*>(&ctx->floor_key) = fl;
+    *reinterpret_cast<volatile int*>(&ctx->found_bin) = found;
   }
   __syncwarp();
 }
@@ -545,8 +662,9 @@ __device__ __noinline__ void sd_merge_emit(const SdArgs& a, int frame, int n_run
   const unsigned long long* rows = a.cand + (size_t)frame * a.tbl_rows * a.row_cap;
   const int* cnts = a.cand_count + (size_t)frame * a.tbl_rows;
   const int nslots = n_runs * a.row_cap;
+  const int pool_cap = kSdFW * a.sub_cap;
   int m;  // keys in the pool
-  if (nslots <= kSdListCap) {
+  if (nslots <= pool_cap) {
     // all rows at once, whatever their counts (one round trip through L2: the rows were written by other CTAs before
     // their ticket arrival), invalid slots as 0; then squeeze the zeros out while sorting
     for (int i = tid; i < nslots; i += kSdNF) {
@@ -565,7 +683,7 @@ __device__ __noinline__ void sd_merge_emit(const SdArgs& a, int frame, int n_run
       auto load = [&](int i) { return pool[i]; };
       const unsigned long long T = block_kth_largest<kSdNF, decltype(load), SdSyncF>(load, nslots, k, hist, ctx->sel);
       // survivors to the front: every thread holds its slice in registers, so in-place writes cannot pass unread entries
-      constexpr int SL = kSdListCap / kSdNF;
+      constexpr int SL = kSdListCap / kSdNF;  // (pool_cap <= kSdListCap)
       unsigned long long mine[SL];
       int nm = 0;
 #pragma unroll
@@ -706,9 +824,9 @@ template <int MODE>
 __device__ __noinline__ void sd_run_end(const SdArgs& a, int frame, int cnt) {
   SdCtx* const ctx = sd_ctx(a);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned long long* sub = sd_list(a) + (size_t)warp * kSdSub;
-  unsigned long long kt = ctx->floor_key;  // floor of the bin that holds the run's k-th best (0: fewer than k binned)
-  if (kt == 0ull) kt = 1ull;
+  unsigned long long* sub = sd_list(a) + (size_t)warp * a.sub_cap;
+  // floor of the bin that holds the run's k-th best (fewer than k binned: keep everything)
+  unsigned long long kt = ctx->found_bin >= 0 ? sd_bin_floor<MODE>(ctx->found_bin) : 1ull;
   auto count_ge = [&](unsigned long long t) {
     int n = 0;
     for (int i = lane; i < cnt; i += 32) n += (sub[i] >= t) ? 1 : 0;
@@ -720,14 +838,15 @@ __device__ __noinline__ void sd_run_end(const SdArgs& a, int frame, int cnt) {
   int total = 0;
   for (int ww = 0; ww < kSdFW; ++ww) total += ctx->wsum[ww];
   if (total > a.row_cap) {
-    // (ties / plateaus / a stale floor) exact k-th key over the union of the sub-lists (a padded [warp][kSdSub] table)
+    // (ties / plateaus / a stale floor) exact k-th key over the union of the sub-lists (a padded [warp][sub_cap] table)
     sd_sync_f();
     if (lane == 0) ctx->wsum[warp] = cnt;
     sd_sync_f();
     const unsigned long long* list = sd_list(a);
     const int* wc = ctx->wsum;
-    auto load = [&](int i) -> unsigned long long { return (i & (kSdSub - 1)) < wc[i / kSdSub] ? list[i] : 0ull; };
-    const unsigned long long T = block_kth_largest<kSdNF, decltype(load), SdSyncF>(load, kSdListCap, a.k, sd_bins(a), ctx->sel);
+    const int sc = a.sub_cap;
+    auto load = [&](int i) -> unsigned long long { return (i & (sc - 1)) < wc[i / sc] ? list[i] : 0ull; };
+    const unsigned long long T = block_kth_largest<kSdNF, decltype(load), SdSyncF>(load, kSdFW * sc, a.k, sd_bins(a), ctx->sel);
     kt = T > kt ? T : kt;
     mine = count_ge(kt);
     sd_sync_f();
@@ -774,7 +893,7 @@ __device__ __forceinline__ void sd_run_reset(const SdArgs& a, int frame) {
   for (int i = tid; i < kClBins / 4; i += kSdNF) reinterpret_cast<uint4*>(bins)[i] = make_uint4(0, 0, 0, 0);
   if (tid < kSdFW) ctx->warpT[tid] = 0ull;
   if (tid == 0) {
-    ctx->floor_key = 0ull;
+    ctx->found_bin = -1;
     ctx->thr_key = 0u;
     ctx->maxbin = 0u;
     ctx->pushed = 0u;
@@ -811,6 +930,9 @@ __global__ void __launch_bounds__(kSdThreads, 1) stream_decode_kernel(const __gr
     mbar_fence_init();
     ctx->load_row0 = load_row0;
     ctx->req = 0;
+    ctx->n_chunks = n_chunks;
+    ctx->n_load = n_load;
+    ctx->own_end = lead + n_own;
   }
   __syncthreads();
   if (n_own <= 0) return;
@@ -841,7 +963,7 @@ __global__ void __launch_bounds__(kSdThreads, 1) stream_decode_kernel(const __gr
   if (warp == kSdMgrWarp) {
     // ---- manager: while the filter warps stream a run, rescan the histogram whenever enough new candidates were
     // counted and raise the rejection threshold and the prune floor.  Nobody waits for it.
-    const int every = a.k >= 8 ? a.k / 8 : 1;
+    const int every = a.k >= 32 ? a.k / 16 : 2;
     for (int run = 0; run < n_runs_cta; ++run) {
       sd_sync_all();  // run begin (the filter warps have reset the shared state)
       uint32_t last_scan = 0;
@@ -851,7 +973,7 @@ __global__ void __launch_bounds__(kSdThreads, 1) stream_decode_kernel(const __gr
           sd_rescan<MODE>(a);
           last_scan = pushed;
         } else if (last_scan != 0) {
-          __nanosleep(200);
+          __nanosleep(64);
         }
       }
       sd_rescan<MODE>(a);  // (whatever arrived since the last scan)
@@ -860,86 +982,31 @@ __global__ void __launch_bounds__(kSdThreads, 1) stream_decode_kernel(const __gr
     return;
   }
 
-  // ---- filter warps
-  const uint32_t ring_u32 = smem_u32(sd_ring());
-  const uint32_t full_u32 = smem_u32(full);
-  int spr_shift = -1;
-  {
-    const int spr = W >> 2;
-    if ((spr & (spr - 1)) == 0) spr_shift = 31 - __clz(spr);
+  // ---- filter warps: per run — reset the shared state, stream, hand over
+  if (lane == 0) {
+    ctx->st[warp].c = 0;
+    ctx->st[warp].slot = 0;
+    ctx->st[warp].round = 0;
+    ctx->st[warp].done = lead;   // stream positions [lead, lead + n_own) are this CTA's rows
+    ctx->st[warp].rdone = lead;  // ring row of stream row `done`
   }
-  int cnt = 0;       // entries in this warp's sub-list
-  int done = lead;   // stream positions [lead, lead + n_own) are this CTA's rows
-  int rdone = lead;  // ring row of stream row `done`
-  const int own_end = lead + n_own;
-  int frame = frame0, run = 0;
-  int frame_end = (int)((long long)(frame + 1) * a.rows_frame - load_row0);  // stream position of the next frame's first row
-  sd_run_reset(a, frame);
-  sd_sync_all();  // run begin
-#ifdef TAUV_SD_DEBUG
-  long long t_wait = 0, t_work = 0, t_end_run = 0, t0 = 0, t1 = 0, t_first = 0;
-  auto now = []() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
-  t_first = now();
-#endif
-  int slot = 0, avail = 0;
-  uint32_t round = 0;
 #pragma unroll 1
-  for (int c = 0; c < n_chunks; ++c) {
+  for (int run = 0; run < n_runs_cta; ++run) {
+    const int frame = frame0 + run;
+    sd_run_reset(a, frame);
+    sd_sync_all();  // run begin
+    const int frame_end = (int)((long long)(frame + 1) * a.rows_frame - load_row0);  // stream position of the next frame
+    const int fr_base = (int)(load_row0 - (long long)frame * a.rows_frame);          // frame row of stream position 0
+    const int cnt = sd_stream_run<MODE>(a, frame_end, fr_base);
+    if (lane == 0) *reinterpret_cast<volatile int*>(&ctx->req) = run + 1;
+    sd_sync_all();  // all rows of the run are filtered and the manager's last scan is published
 #ifdef TAUV_SD_DEBUG
-    t0 = now();
+    if (tid == 0 && (blockIdx.x % 29) == 0)
+      printf("[sd] cta %d run %d: pushed %u, sub-list of warp 0: %d, thr %g\n", blockIdx.x, run, ctx->pushed, cnt,
+             ctx->thr_key ? key_to_float(ctx->thr_key) : -1e30f);
 #endif
-    sd_mbar_wait(full_u32 + (uint32_t)slot * 8u, round & 1);
-#ifdef TAUV_SD_DEBUG
-    t1 = now();
-    t_wait += t1 - t0;
-#endif
-    avail += CR;
-    // a row can be tested once the row below it has landed (or does not exist)
-    const int limit = (c == n_chunks - 1) ? own_end : min(own_end, avail - 1);
-    while (done < limit) {
-      const int seg_end = min(limit, frame_end);
-      cnt = sd_filter_rows<MODE>(a, ring_u32, ring_rows, spr_shift, done, seg_end, rdone, cnt);
-      rdone += seg_end - done;
-      if (rdone >= ring_rows) rdone -= ring_rows;
-      done = seg_end;
-      if (done == frame_end || done == own_end) {
-        // ---- end of a run
-#ifdef TAUV_SD_DEBUG
-        const long long tr0 = now();
-#endif
-        if (lane == 0) *reinterpret_cast<volatile int*>(&ctx->req) = run + 1;
-        sd_sync_all();  // all rows of the run are filtered and the manager's last scan is published
-        sd_run_end<MODE>(a, frame, cnt);
-        cnt = 0;
-        if (done < own_end) {
-          ++frame;
-          ++run;
-          frame_end += a.rows_frame;
-          sd_run_reset(a, frame);
-          sd_sync_all();  // run begin
-        }
-#ifdef TAUV_SD_DEBUG
-        t_end_run += now() - tr0;
-#endif
-      }
-    }
-#ifdef TAUV_SD_DEBUG
-    t_work += now() - t1;
-#endif
-    // the rows of the previous chunk are no longer needed by this warp once every row up to the last-but-one of this
-    // chunk is done
-    __syncwarp();
-    if (lane == 0 && c >= 1) sd_mbar_arrive(&empty[slot == 0 ? S - 1 : slot - 1]);
-    if (++slot == S) {
-      slot = 0;
-      ++round;
-    }
+    sd_run_end<MODE>(a, frame, cnt);
   }
-#ifdef TAUV_SD_DEBUG
-  if (lane == 0 && (blockIdx.x % 37) == 0 && (warp % 5) == 0)
-    printf("[sd] cta %d warp %d: chunks %d total %lld ns = wait %lld + work %lld (of which run ends %lld)\n", blockIdx.x, warp,
-           n_chunks, now() - t_first, t_wait, t_work, t_end_run);
-#endif
 }
 
 }  // namespace tauv
