@@ -925,7 +925,7 @@ static void make_stream_plan(int B, int C, int H, int W, int k, StreamPlan* p) {
   p->chunk_rows = cr;
   p->sub_cap = k <= 128 ? 256 : 512;
   const size_t fixed = sd_smem_bytes(0, 0, W, p->sub_cap);
-  int st = (int)((227 * 1024 - fixed) / ((size_t)cr * W * 4));
+  int st = (int)((226 * 1024 - fixed) / ((size_t)(cr + 2) * W * 4));  // (227 KB opt-in limit minus the static shared memory)
   if (st > 8) st = 8;
   p->stages = st;
   long long G = num_sms();          // one CTA per SM (the ring takes most of the shared memory)

@@ -54,7 +54,8 @@ constexpr int kSdMaxK = kSdSubMax / 2;         // a warp can always prune its ow
 constexpr int kSdMaxW = 1024;
 constexpr int kSdMaxStages = 16;
 constexpr int kSdU = 4;                        // 128-bit strips per thread and filter iteration
-constexpr int kSdPend = 64;                    // per filter warp: peaks waiting for their sigmoid + push (flushed 32 at a time)
+constexpr int kSdPend = 160;                   // per filter warp: peaks waiting for their sigmoid + push (flushed 32 at a time;
+                                               // one group of 32 strips can add 128 to the 31 left over)
 
 using SdSyncAll = SyncNamed<1, kSdNA>;         // filter warps + manager
 using SdSyncF = SyncNamed<2, kSdNF>;           // filter warps only
@@ -97,10 +98,9 @@ struct __align__(16) SdCtx {
   int base;
   int wsum[kSdFW];
   uint32_t sel[8];
-  // geometry of this CTA's range (written once) and where each filter warp stands in it (kept here between runs so that
-  // the streaming loop — a function of its own — starts from a clean register file)
-  int n_chunks, n_load, own_end;
-  struct { int c, slot, round, done, rdone, pad[3]; } st[kSdFW];
+  int npend[kSdFW];              // peaks waiting in a filter warp's pending buffer
+  // where each filter warp stands in the CTA's range (kept here between runs)
+  struct { int c, slot, round, done; } st[kSdFW];
 };
 
 __device__ __forceinline__ uint64_t sd_policy_evict_first() {
@@ -156,7 +156,7 @@ struct SdLayout {
 };
 __host__ __device__ inline SdLayout sd_layout(int chunk_rows, int stages, int W, int sub_cap) {
   SdLayout l;
-  size_t o = (size_t)stages * chunk_rows * W * 4;
+  size_t o = (size_t)stages * (chunk_rows + 2) * W * 4;  // every slot holds its chunk plus one halo row on either side
   l.off_list = (int)o;
   o += (size_t)kSdFW * sub_cap * 8;
   l.off_bins = (int)o;
@@ -254,66 +254,6 @@ __device__ __noinline__ int sd_warp_prune(const SdArgs& a, int cnt) {
   return cnt;
 }
 
-// 3x3 test of one 128-bit strip that passed the threshold scan (called by the hot lanes only): stream row p held in
-// ring row rp, column col, values x.  The rows above and below come from the ring (the halo rows of a range are
-// loaded with it); rows outside the plane do not exist (-inf padding, decode.py:245-250).  Returns the flat index of
-// the strip's first cell << 8 | a 4-bit mask of the cells that are candidates (3x3 peaks at or above the threshold;
-// RAW: cells at or above the threshold).
-template <int MODE>
-__device__ __forceinline__ unsigned long long sd_peaks(const SdArgs& a, uint32_t ring_u32, int ring_rows, int fr_base, int p, int rp,
-                                                    int col, float thr_f) {
-  const int W = a.W;
-  const int fr = fr_base + p;  // row inside the frame
-  const uint32_t flat = (uint32_t)fr * (uint32_t)W + (uint32_t)col;
-  const float4 x = sd_lds4(ring_u32 + (uint32_t)rp * (uint32_t)W * 4u + (uint32_t)col * 4u);
-  const float xs[4] = {x.x, x.y, x.z, x.w};
-  unsigned mask = 0u;
-  if (MODE != TAUV_TOPK_SIGMOID_PEAK) {
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) mask |= (xs[cc] >= thr_f) ? (1u << cc) : 0u;
-  } else {
-    const uint32_t rowb = (uint32_t)W * 4u;
-    const uint32_t mid = ring_u32 + (uint32_t)rp * rowb + (uint32_t)col * 4u;
-    const int y = (a.H & (a.H - 1)) == 0 ? (fr & (a.H - 1)) : fr % a.H;
-    const float NI = TAUV_NEG_INF;
-    const bool hl = col > 0, hr = col + 4 < W;
-    float4 u = make_float4(NI, NI, NI, NI), d = u;
-    float ul = NI, ur = NI, dl = NI, dr = NI;
-    if (y > 0) {
-      const uint32_t up = ring_u32 + (uint32_t)(rp == 0 ? ring_rows - 1 : rp - 1) * rowb + (uint32_t)col * 4u;
-      u = sd_lds4(up);
-      if (hl) ul = sd_lds1(up - 4);
-      if (hr) ur = sd_lds1(up + 16);
-    }
-    if (y + 1 < a.H) {
-      const uint32_t dn = ring_u32 + (uint32_t)(rp + 1 == ring_rows ? 0 : rp + 1) * rowb + (uint32_t)col * 4u;
-      d = sd_lds4(dn);
-      if (hl) dl = sd_lds1(dn - 4);
-      if (hr) dr = sd_lds1(dn + 16);
-    }
-    const float ml = hl ? sd_lds1(mid - 4) : NI, mr = hr ? sd_lds1(mid + 16) : NI;
-    float cm[6];  // column-wise max over the three rows, columns col-1 .. col+4
-    cm[0] = fmaxf(fmaxf(ul, ml), dl);
-    cm[1] = fmaxf(fmaxf(u.x, x.x), d.x);
-    cm[2] = fmaxf(fmaxf(u.y, x.y), d.y);
-    cm[3] = fmaxf(fmaxf(u.z, x.z), d.z);
-    cm[4] = fmaxf(fmaxf(u.w, x.w), d.w);
-    cm[5] = fmaxf(fmaxf(ur, mr), dr);
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const float xv = xs[cc];
-      if (xv >= thr_f) {
-        const float m = fmaxf(fmaxf(cm[cc], cm[cc + 1]), cm[cc + 2]);
-        bool peak = (xv >= m);
-        // x < m can still tie after the sigmoid (saturation, sub-ulp gap): the reference compares sigmoid values
-        if (!peak && (xv > 4.0f || m < -80.0f || (m - xv) < 1e-3f)) peak = sigmoid_tie(xv, m);
-        if (peak) mask |= 1u << cc;
-      }
-    }
-  }
-  return ((unsigned long long)flat << 8) | mask;
-}
-
 // Push the first n (<= 32) waiting peaks of this warp, all lanes at once: sigmoid, composite key, a slot in the warp's
 // private sub-list; then move the rest of the waiting list (npend - n entries) to its front.  Warp-convergent.
 // Returns the sub-list's new length.
@@ -339,9 +279,15 @@ __device__ __forceinline__ int sd_flush(const SdArgs& a, int n, int npend, int c
     c = make_composite(key, e.y);
     ok = ok && c > ctx->warpT[warp];
   }
-  const uint2 tail = (lane + 32 < npend) ? pend[lane + 32] : make_uint2(0u, 0u);
-  __syncwarp();
-  if (lane + 32 < npend) pend[lane] = tail;
+  // the rest of the waiting list moves down by n
+  for (int i0 = 0; i0 < npend - n; i0 += 32) {  // (warp-uniform trip count)
+    const int i = i0 + lane;
+    uint2 t = make_uint2(0u, 0u);
+    if (i < npend - n) t = pend[i + n];
+    __syncwarp();
+    if (i < npend - n) pend[i] = t;
+    __syncwarp();
+  }
   unsigned bal = __ballot_sync(0xffffffffu, ok);
   if (bal == 0u) return cnt;
   if (cnt + __popc(bal) > a.sub_cap) {
@@ -354,176 +300,204 @@ __device__ __forceinline__ int sd_flush(const SdArgs& a, int n, int npend, int c
   return cnt + __popc(bal);
 }
 
-// What a filter warp carries through the stream (all warp-uniform)
-struct SdWarpState {
-  int cnt;    // entries in the warp's private sub-list
-  int npend;  // peaks waiting in the warp's pending buffer (< 32 between iterations)
-};
-__device__ __forceinline__ int sd_pack(const SdWarpState& w) { return w.cnt | (w.npend << 16); }
-__device__ __forceinline__ SdWarpState sd_unpack(int v) { return SdWarpState{v & 0xffff, v >> 16}; }
-
-// The rare part of a filter iteration: lanes whose strip s (relative to the part that starts at stream row p0 / ring
-// row rp0) is hot run the 3x3 test; the peaks they find are appended to the warp's pending buffer, which is flushed
-// 32 at a time.  Warp-convergent; written for few registers and little code (runtime loops, one call site each).
+// The rare part of a filter iteration, for one group of 32 strips (warp-convergent call; `hot`: this lane's strip
+// passed the threshold scan).  Hot lanes run the 3x3 test on their strip — slot row `srow` (1-based: row 0 and the
+// last row of a slot are the halo rows loaded with the chunk, so the rows above and below are always in the slot; rows
+// outside the plane do not exist: -inf padding, decode.py:245-250) — and append the peaks at or above the threshold
+// to the warp's pending buffer, counting them in the shared histogram at once (the threshold must not lag behind what
+// waits here).  The expensive part (sigmoid, keys, list) runs later on full warps (sd_flush).  RAW: every cell at or
+// above the threshold is a candidate.  Returns the warp's sub-list length.
 template <int MODE>
-__device__ __forceinline__ int sd_hot(const SdArgs& a, uint32_t ring_u32, int ring_rows, int spr_shift, int fr_base, int p0, int rp0,
-                                   int s_first, unsigned hotmask, float thr_f, int wstate) {
-  SdWarpState w = sd_unpack(wstate);
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int spr = a.W >> 2;
-  uint2* const pend = sd_pend(a) + (tid >> 5) * kSdPend;
-  uint32_t* const bins = sd_bins(a);
+__device__ __forceinline__ int sd_hot(const SdArgs& a, uint32_t slot_u32, bool hot, int srow, int col, int fr, float thr_f,
+                                      int cnt) {
   SdCtx* const ctx = sd_ctx(a);
-#pragma unroll 1
-  for (int u = 0; u < kSdU; ++u) {
-    const bool h = (hotmask >> u) & 1u;
-    if (!__any_sync(0xffffffffu, h)) continue;
-    unsigned long long pk = 0ull;
-    uint32_t xaddr = 0;
-    if (h) {
-      const int s = s_first + u * kSdNF;
-      const int r = spr_shift >= 0 ? (s >> spr_shift) : (s / spr);
-      const int col = (s - r * spr) << 2;
-      pk = sd_peaks<MODE>(a, ring_u32, ring_rows, fr_base, p0 + r, rp0 + r, col, thr_f);
-      xaddr = ring_u32 + (uint32_t)(rp0 + r) * (uint32_t)a.W * 4u + (uint32_t)col * 4u;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint2* const pend = sd_pend(a) + warp * kSdPend;
+  if (hot) {
+    const int W = a.W;
+    const float4 x = sd_lds4(slot_u32 + (uint32_t)srow * (uint32_t)W * 4u + (uint32_t)col * 4u);
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+    unsigned mask = 0u;
+    if (MODE != TAUV_TOPK_SIGMOID_PEAK) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) mask |= (xs[cc] >= thr_f) ? (1u << cc) : 0u;
+    } else {
+      const uint32_t rowb = (uint32_t)W * 4u;
+      const uint32_t mid = slot_u32 + (uint32_t)srow * rowb + (uint32_t)col * 4u;
+      const int y = (a.H & (a.H - 1)) == 0 ? (fr & (a.H - 1)) : fr % a.H;
+      const float NI = TAUV_NEG_INF;
+      const bool hl = col > 0, hr = col + 4 < W;
+      float4 u = make_float4(NI, NI, NI, NI), d = u;
+      float ul = NI, ur = NI, dl = NI, dr = NI;
+      if (y > 0) {
+        u = sd_lds4(mid - rowb);
+        if (hl) ul = sd_lds1(mid - rowb - 4);
+        if (hr) ur = sd_lds1(mid - rowb + 16);
+      }
+      if (y + 1 < a.H) {
+        d = sd_lds4(mid + rowb);
+        if (hl) dl = sd_lds1(mid + rowb - 4);
+        if (hr) dr = sd_lds1(mid + rowb + 16);
+      }
+      const float ml = hl ? sd_lds1(mid - 4) : NI, mr = hr ? sd_lds1(mid + 16) : NI;
+      float cm[6];  // column-wise max over the three rows, columns col-1 .. col+4
+      cm[0] = fmaxf(fmaxf(ul, ml), dl);
+      cm[1] = fmaxf(fmaxf(u.x, x.x), d.x);
+      cm[2] = fmaxf(fmaxf(u.y, x.y), d.y);
+      cm[3] = fmaxf(fmaxf(u.z, x.z), d.z);
+      cm[4] = fmaxf(fmaxf(u.w, x.w), d.w);
+      cm[5] = fmaxf(fmaxf(ur, mr), dr);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const float xv = xs[cc];
+        if (xv >= thr_f) {
+          const float m = fmaxf(fmaxf(cm[cc], cm[cc + 1]), cm[cc + 2]);
+          bool peak = (xv >= m);
+          // x < m can still tie after the sigmoid (saturation, sub-ulp gap): the reference compares sigmoid values
+          if (!peak && (xv > 4.0f || m < -80.0f || (m - xv) < 1e-3f)) peak = sigmoid_tie(xv, m);
+          if (peak) mask |= 1u << cc;
+        }
+      }
     }
-    if (!__any_sync(0xffffffffu, (pk & 15ull) != 0ull)) continue;
-    const uint32_t flat = (uint32_t)(pk >> 8);
-#pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
-      const bool cand = (pk >> cc) & 1ull;
-      const unsigned bal = __ballot_sync(0xffffffffu, cand);
-      if (bal == 0u) continue;
-      if (cand) {
-        const float x = sd_lds1(xaddr + 4u * cc);
-        pend[w.npend + __popc(bal & ((1u << lane) - 1u))] = make_uint2(__float_as_uint(x), flat + cc);
-        // the histogram counts every candidate once, at once (the threshold must not lag behind what waits here), in
-        // logit / value space, with fire-and-forget shared-memory reductions
-        if (MODE != TAUV_TOPK_SIGMOID_PEAK || x > -80.0f) {
-          const int bin = cl_window_bin(float_to_key(x));
-          if (bin >= 0) {
-            atomicAdd(&bins[bin], 1u);
-            if ((uint32_t)bin > *reinterpret_cast<volatile uint32_t*>(&ctx->maxbin)) atomicMax(&ctx->maxbin, (uint32_t)bin);
+    if (mask) {
+      // (one shared-memory atomic per lane that found something: candidates are rare once a threshold exists, and the
+      // warp's counter is nobody else's)
+      const int n = __popc(mask);
+      int slot = atomicAdd(&ctx->npend[warp], n);
+      atomicAdd(&ctx->pushed, (uint32_t)n);
+      const uint32_t flat = (uint32_t)fr * (uint32_t)W + (uint32_t)col;
+      uint32_t* const bins = sd_bins(a);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        if (mask & (1u << cc)) {
+          const float xv = xs[cc];
+          pend[slot++] = make_uint2(__float_as_uint(xv), flat + cc);
+          if (MODE != TAUV_TOPK_SIGMOID_PEAK || xv > -80.0f) {
+            const int bin = cl_window_bin(float_to_key(xv));
+            if (bin >= 0) {
+              atomicAdd(&bins[bin], 1u);
+              if ((uint32_t)bin > *reinterpret_cast<volatile uint32_t*>(&ctx->maxbin)) atomicMax(&ctx->maxbin, (uint32_t)bin);
+            }
           }
         }
       }
-      if (lane == 0) atomicAdd(&ctx->pushed, (uint32_t)__popc(bal));
-      w.npend += __popc(bal);
-      __syncwarp();
-      if (w.npend >= 32) {
-        w.cnt = sd_flush<MODE>(a, 32, w.npend, w.cnt);
-        w.npend -= 32;
-      }
     }
   }
-  return sd_pack(w);
+  __syncwarp();
+  int np = *reinterpret_cast<volatile int*>(&ctx->npend[warp]);
+  while (np >= 32) {
+    cnt = sd_flush<MODE>(a, 32, np, cnt);
+    np -= 32;
+    if (lane == 0) ctx->npend[warp] = np;
+    __syncwarp();
+  }
+  return cnt;
 }
 
-// Threshold scan of this warp's share of the stream rows [p0, p1) (one frame; rp0 = ring row of p0; the rows are
-// contiguous in the ring): the warp takes every kSdFW-th group of 32 consecutive 128-bit strips, kSdU groups in flight.
-// Only lanes whose strip maximum reaches the threshold run the 3x3 test; the peaks they find wait in the warp's pending
-// buffer until 32 are there, so that the expensive part (sigmoid, keys, list, histogram) always runs on full warps.
+// Threshold scan of this warp's share of n consecutive 128-bit strips that start at shared-memory address `base`
+// (rows of one frame in one slot; strip 0 = column 0 of slot row srow0 = frame row fr0): the warp takes every kSdFW-th
+// group of 32 strips, kSdU groups in flight; while no threshold exists (bootstrap) only one, so that the first threshold
+// is used as early as possible.
 template <int MODE>
-__device__ __forceinline__ int sd_filter_part(const SdArgs& a, uint32_t ring_u32, int ring_rows, int spr_shift, int fr_base,
-                                              int p0, int p1, int rp0, int wstate) {
+__device__ __forceinline__ int sd_filter(const SdArgs& a, uint32_t slot_u32, uint32_t base, int n, int srow0, int fr0,
+                                         int spr_shift, int cnt) {
   const int tid = threadIdx.x;
-  const int n = (p1 - p0) * (a.W >> 2);
-  const uint32_t base = ring_u32 + (uint32_t)rp0 * (uint32_t)a.W * 4u + (uint32_t)tid * 16u;
-  const uint32_t thr_addr = ring_u32 + (uint32_t)a.off_ctx + (uint32_t)offsetof(SdCtx, thr_key);
+  const uint32_t thr_addr = smem_u32(sd_smem()) + (uint32_t)a.off_ctx + (uint32_t)offsetof(SdCtx, thr_key);
   const float NI = TAUV_NEG_INF;
+  int sb = 0;
 #pragma unroll 1
-  for (int sb = 0; sb < n; sb += kSdU * kSdNF) {  // (warp-uniform trip count: the body votes)
-    const int s0 = sb + tid;
+  while (sb < n) {  // (warp-uniform trip count: the body votes)
     const uint32_t tk = sd_lds_u32_volatile(thr_addr);
     const float thr_f = tk ? key_to_float(tk) : NI;
+    const int nu = tk ? kSdU : 1;
+    const int s0 = sb + tid;
     unsigned hotmask = 0u;
 #pragma unroll
     for (int u = 0; u < kSdU; ++u) {
       const int s = s0 + u * kSdNF;
-      if (s < n) {
-        const float4 v = sd_lds4(base + (uint32_t)(s - tid) * 16u);
+      if (u < nu && s < n) {
+        const float4 v = sd_lds4(base + (uint32_t)s * 16u);
         const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
         hotmask |= (m >= thr_f) ? (1u << u) : 0u;
       }
     }
 #if defined(TAUV_SD_EXP) && TAUV_SD_EXP == 1
-    if (false)
+    if (false) {
 #elif defined(TAUV_SD_EXP) && TAUV_SD_EXP == 2
-    if (__any_sync(0xffffffffu, hotmask != 0u) && tk == 0u)
+    if (__any_sync(0xffffffffu, hotmask != 0u) && tk == 0u) {
 #else
-    if (__any_sync(0xffffffffu, hotmask != 0u))
+    if (__any_sync(0xffffffffu, hotmask != 0u)) {
 #endif
-      wstate = sd_hot<MODE>(a, ring_u32, ring_rows, spr_shift, fr_base, p0, rp0, s0, hotmask, thr_f, wstate);
+      const int spr = a.W >> 2;
+#pragma unroll 1
+      for (int u = 0; u < kSdU; ++u) {  // (a runtime loop: one copy of the 3x3 test, nothing of the scan live in it)
+        const bool h = (hotmask >> u) & 1u;
+        if (!__any_sync(0xffffffffu, h)) continue;
+        const int s = s0 + u * kSdNF;
+        const int r = spr_shift >= 0 ? (s >> spr_shift) : (s / spr);
+        cnt = sd_hot<MODE>(a, slot_u32, h, srow0 + r, (s - r * spr) << 2, fr0 + r, thr_f, cnt);
+      }
+    }
+    sb += nu * kSdNF;
   }
-  return wstate;
-}
-
-// rows [p0, p1) of one frame; rp0 = ring row of p0
-template <int MODE>
-__device__ __forceinline__ int sd_filter_rows(const SdArgs& a, uint32_t ring_u32, int ring_rows, int spr_shift, int fr_base,
-                                              int p0, int p1, int rp0, int wstate) {
-  // split where the ring wraps so that each part is one contiguous run of strips in shared memory
-  const int n1 = ring_rows - rp0;
-  if (p1 - p0 <= n1) return sd_filter_part<MODE>(a, ring_u32, ring_rows, spr_shift, fr_base, p0, p1, rp0, wstate);
-  wstate = sd_filter_part<MODE>(a, ring_u32, ring_rows, spr_shift, fr_base, p0, p0 + n1, rp0, wstate);
-  return sd_filter_part<MODE>(a, ring_u32, ring_rows, spr_shift, fr_base, p0 + n1, p1, 0, wstate);
+  return cnt;
 }
 
 // A filter warp streams its share of one run: from where it stands (ctx->st) to the end of the frame or of the CTA's
-// range, chunk by chunk as they land.  A function of its own so that the hot loop is compiled with nothing else live.
-// frame_end: stream position of the next frame's first row; fr_base: row inside the frame of stream position 0.
-// Returns the length of the warp's sub-list (the pending peaks are flushed before it returns).
+// range, chunk by chunk as they land.  Chunk c holds the CTA's rows [c*CR, (c+1)*CR) in slot rows 1.., with the row
+// before in slot row 0 and the row after behind them, so every chunk is tested on its own and its slot is released as
+// soon as this warp is through with it.  run_end: position (row of the CTA's range) where the run ends; fr_off: frame
+// row of position 0.  Returns the length of the warp's sub-list (the pending peaks are flushed before it returns).
 template <int MODE>
-__device__ __forceinline__ int sd_stream_run(const SdArgs& a, int frame_end, int fr_base) {
+__device__ __forceinline__ int sd_stream_run(const SdArgs& a, int n_own, int run_end, int fr_off) {
   SdCtx* const ctx = sd_ctx(a);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int CR = a.chunk_rows, S = a.stages, ring_rows = CR * S;
-  const uint32_t ring_u32 = smem_u32(sd_ring());
-  const uint32_t full_u32 = ring_u32 + (uint32_t)a.off_bars;
-  const int n_chunks = ctx->n_chunks, n_load = ctx->n_load, own_end = ctx->own_end;
+  const int CR = a.chunk_rows, S = a.stages, W = a.W;
+  const uint32_t smem0 = smem_u32(sd_smem());
+  const uint32_t full_u32 = smem0 + (uint32_t)a.off_bars;
+  const uint32_t slot_bytes = (uint32_t)(CR + 2) * (uint32_t)W * 4u;
+  const int n_chunks = (n_own + CR - 1) / CR;
   int spr_shift = -1;
   {
-    const int spr = a.W >> 2;
+    const int spr = W >> 2;
     if ((spr & (spr - 1)) == 0) spr_shift = 31 - __clz(spr);
   }
-  int c = ctx->st[warp].c, slot = ctx->st[warp].slot, round = ctx->st[warp].round;
-  int done = ctx->st[warp].done, rdone = ctx->st[warp].rdone;
-  int wstate = 0;
+  int c = ctx->st[warp].c, slot = ctx->st[warp].slot, round = ctx->st[warp].round, done = ctx->st[warp].done;
+  int cnt = 0;
 #pragma unroll 1
   while (c < n_chunks) {
     sd_mbar_wait(full_u32 + (uint32_t)slot * 8u, (uint32_t)round & 1u);
-    const int avail = min((c + 1) * CR, n_load);
-    // a row can be tested once the row below it has landed (or does not exist)
-    const int limit = (c == n_chunks - 1) ? own_end : min(own_end, avail - 1);
-    const int seg_end = min(limit, frame_end);
+    const int chunk_end = min((c + 1) * CR, n_own);
+    const int seg_end = min(chunk_end, run_end);
     if (done < seg_end) {
-      wstate = sd_filter_rows<MODE>(a, ring_u32, ring_rows, spr_shift, fr_base, done, seg_end, rdone, wstate);
-      rdone += seg_end - done;
-      if (rdone >= ring_rows) rdone -= ring_rows;
+      const uint32_t slot_u32 = smem0 + (uint32_t)slot * slot_bytes;
+      const int srow0 = done - c * CR + 1;
+      cnt = sd_filter<MODE>(a, slot_u32, slot_u32 + (uint32_t)srow0 * (uint32_t)W * 4u, (seg_end - done) * (W >> 2), srow0,
+                            fr_off + done, spr_shift, cnt);
       done = seg_end;
     }
-    if (done == frame_end || done == own_end) break;  // the run ends here (possibly in the middle of this chunk)
-    // the rows of the previous chunk are no longer needed by this warp once every row up to the last-but-one of this
-    // chunk is done
+    if (done < chunk_end) break;  // the run ends in the middle of this chunk: the next run carries on from here
     __syncwarp();
-    if (lane == 0 && c >= 1) sd_mbar_arrive(sd_empty(a) + (slot == 0 ? S - 1 : slot - 1));
+    if (lane == 0) sd_mbar_arrive(sd_empty(a) + slot);  // this warp is through with the slot
     ++c;
     if (++slot == S) {
       slot = 0;
       ++round;
     }
+    if (done == run_end) break;
   }
   if (lane == 0) {
     ctx->st[warp].c = c;
     ctx->st[warp].slot = slot;
     ctx->st[warp].round = round;
     ctx->st[warp].done = done;
-    ctx->st[warp].rdone = rdone;
   }
-  SdWarpState w = sd_unpack(wstate);
-  if (w.npend > 0) w.cnt = sd_flush<MODE>(a, w.npend, w.npend, w.cnt);
+  const int np = *reinterpret_cast<volatile int*>(&ctx->npend[warp]);
+  if (np > 0) cnt = sd_flush<MODE>(a, np, np, cnt);
   __syncwarp();
-  return w.cnt;
+  if (lane == 0) ctx->npend[warp] = 0;
+  __syncwarp();
+  return cnt;
 }
 
 // ---- manager warp ---------------------------------------------------------------------------------------------------
@@ -909,16 +883,11 @@ __global__ void __launch_bounds__(kSdThreads, 1) stream_decode_kernel(const __gr
   uint64_t* const empty = sd_empty(a);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int W = a.W, CR = a.chunk_rows, S = a.stages;
-  const int ring_rows = CR * S;
 
-  // this CTA's rows and what it loads: one halo row on either side unless the range starts / ends on a plane edge
+  // this CTA's rows
   const long long own0 = a.rows_total * blockIdx.x / a.G, own1 = a.rows_total * (blockIdx.x + 1) / a.G;
-  const int lead = (own0 > 0 && own0 % a.H != 0) ? 1 : 0;
-  const int trail = (own1 < a.rows_total && own1 % a.H != 0) ? 1 : 0;
-  const long long load_row0 = own0 - lead;
   const int n_own = (int)(own1 - own0);
-  const int n_load = n_own + lead + trail;
-  const int n_chunks = (n_load + CR - 1) / CR;
+  const int n_chunks = (n_own + CR - 1) / CR;
   const int frame0 = (int)(own0 / a.rows_frame);
   const int n_runs_cta = n_own > 0 ? (int)((own1 - 1) / a.rows_frame) - frame0 + 1 : 0;
 
@@ -928,29 +897,37 @@ __global__ void __launch_bounds__(kSdThreads, 1) stream_decode_kernel(const __gr
       mbar_init(&empty[s], kSdFW);
     }
     mbar_fence_init();
-    ctx->load_row0 = load_row0;
     ctx->req = 0;
-    ctx->n_chunks = n_chunks;
-    ctx->n_load = n_load;
-    ctx->own_end = lead + n_own;
+  }
+  if (tid < kSdFW) {
+    ctx->npend[tid] = 0;
+    ctx->st[tid].c = 0;
+    ctx->st[tid].slot = 0;
+    ctx->st[tid].round = 0;
+    ctx->st[tid].done = 0;
   }
   __syncthreads();
   if (n_own <= 0) return;
 
   if (warp == kSdProdWarp) {
-    // ---- producer: one lane keeps the ring full; a slot is refilled as soon as all filter warps released it
+    // ---- producer: one lane keeps the ring full; a slot is refilled as soon as all filter warps released it.  A chunk
+    // is loaded with the row before and the row after it (where the tensor has them), so neighbouring chunks overlap by
+    // two rows: the second read of a row comes from L2, and no slot ever depends on another
     if (lane == 0) {
       const uint64_t pol = sd_policy_evict_first();
       const uint32_t ring_u32 = smem_u32(sd_ring());
+      const uint32_t rowb = (uint32_t)W * 4u;
       int slot = 0;
       uint32_t round = 0;
       for (int c = 0; c < n_chunks; ++c) {
         if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
-        const int rows = min(CR, n_load - c * CR);
-        const uint32_t bytes = (uint32_t)rows * (uint32_t)W * 4u;
+        const long long g0 = own0 + (long long)c * CR;                            // first row of the chunk
+        const long long g1 = own0 + min((long long)(c + 1) * CR, (long long)n_own);  // one past its last row
+        const long long l0 = g0 > 0 ? g0 - 1 : g0, l1 = g1 < a.rows_total ? g1 + 1 : g1;
+        const uint32_t bytes = (uint32_t)(l1 - l0) * rowb;
         mbar_expect_tx(&full[slot], bytes);
-        sd_bulk_g2s(ring_u32 + (uint32_t)slot * (uint32_t)CR * (uint32_t)W * 4u,
-                    a.hm + (size_t)(load_row0 + (long long)c * CR) * W, bytes, smem_u32(&full[slot]), pol);
+        sd_bulk_g2s(ring_u32 + (uint32_t)slot * (uint32_t)(CR + 2) * rowb + (uint32_t)(l0 - (g0 - 1)) * rowb,
+                    a.hm + (size_t)l0 * W, bytes, smem_u32(&full[slot]), pol);
         if (++slot == S) {
           slot = 0;
           ++round;
@@ -983,21 +960,14 @@ __global__ void __launch_bounds__(kSdThreads, 1) stream_decode_kernel(const __gr
   }
 
   // ---- filter warps: per run — reset the shared state, stream, hand over
-  if (lane == 0) {
-    ctx->st[warp].c = 0;
-    ctx->st[warp].slot = 0;
-    ctx->st[warp].round = 0;
-    ctx->st[warp].done = lead;   // stream positions [lead, lead + n_own) are this CTA's rows
-    ctx->st[warp].rdone = lead;  // ring row of stream row `done`
-  }
 #pragma unroll 1
   for (int run = 0; run < n_runs_cta; ++run) {
     const int frame = frame0 + run;
     sd_run_reset(a, frame);
     sd_sync_all();  // run begin
-    const int frame_end = (int)((long long)(frame + 1) * a.rows_frame - load_row0);  // stream position of the next frame
-    const int fr_base = (int)(load_row0 - (long long)frame * a.rows_frame);          // frame row of stream position 0
-    const int cnt = sd_stream_run<MODE>(a, frame_end, fr_base);
+    const long long f0 = (long long)frame * a.rows_frame;
+    const int run_end = (int)min((long long)n_own, f0 + a.rows_frame - own0);  // position where the run ends
+    const int cnt = sd_stream_run<MODE>(a, n_own, run_end, (int)(own0 - f0));
     if (lane == 0) *reinterpret_cast<volatile int*>(&ctx->req) = run + 1;
     sd_sync_all();  // all rows of the run are filtered and the manager's last scan is published
 #ifdef TAUV_SD_DEBUG
