@@ -928,6 +928,16 @@ static void make_stream_plan(int B, int C, int H, int W, int k, StreamPlan* p) {
   int st = (int)((226 * 1024 - fixed) / ((size_t)(cr + 2) * W * 4));  // (227 KB opt-in limit minus the static shared memory)
   if (st > 8) st = 8;
   p->stages = st;
+#ifdef TAUV_DEBUG
+  if (const char* e = getenv("TAUV_SD_CR")) {  // experiment: rows per chunk / ring slots
+    cr = atoi(e);
+    p->chunk_rows = cr;
+    st = (int)((226 * 1024 - fixed) / ((size_t)(cr + 2) * W * 4));
+    if (st > kSdMaxStages) st = kSdMaxStages;
+    p->stages = st;
+  }
+  if (const char* e = getenv("TAUV_SD_S")) p->stages = atoi(e) < p->stages ? atoi(e) : p->stages;
+#endif
   long long G = num_sms();          // one CTA per SM (the ring takes most of the shared memory)
   const long long min_rows = 8;     // tiny inputs: fewer CTAs rather than CTAs without rows
   if (G > R / min_rows) G = R / min_rows;
@@ -937,7 +947,10 @@ static void make_stream_plan(int B, int C, int H, int W, int k, StreamPlan* p) {
   long long tr = (long long)C * H / per + 2;
   if (tr > G) tr = G;
   p->tbl_rows = (int)tr;
-  p->row_cap = 2 * k;
+  p->row_cap = 2 * k;  // the survivors of a run: k plus the rest of the bin that holds the k-th (more: exact prune first)
+#ifdef TAUV_DEBUG
+  if (const char* e = getenv("TAUV_SD_ROWCAP")) p->row_cap = atoi(e);
+#endif
   p->smem_bytes = sd_smem_bytes(p->chunk_rows, p->stages, W, p->sub_cap);
   p->cand_bytes = align_up((size_t)B * p->tbl_rows * (size_t)p->row_cap * 8, 256);
   p->count_bytes = align_up((size_t)B * p->tbl_rows * 4, 256);

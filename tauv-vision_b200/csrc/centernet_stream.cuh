@@ -53,6 +53,7 @@ constexpr int kSdSubMax = kSdListCap / kSdFW;  // private sub-list of a filter w
 constexpr int kSdMaxK = kSdSubMax / 2;         // a warp can always prune its own sub-list to k and have room again
 constexpr int kSdMaxW = 1024;
 constexpr int kSdMaxStages = 16;
+constexpr int kSdRingPad = 128;
 constexpr int kSdU = 4;                        // 128-bit strips per thread and filter iteration
 constexpr int kSdPend = 160;                   // per filter warp: peaks waiting for their sigmoid + push (flushed 32 at a time;
                                                // one group of 32 strips can add 128 to the 31 left over)
@@ -156,7 +157,9 @@ struct SdLayout {
 };
 __host__ __device__ inline SdLayout sd_layout(int chunk_rows, int stages, int W, int sub_cap) {
   SdLayout l;
-  size_t o = (size_t)stages * (chunk_rows + 2) * W * 4;  // every slot holds its chunk plus one halo row on either side
+  // every slot holds its chunk plus one halo row on either side; kSdRingPad bytes in front so that the word left of the
+  // first slot's first cell is addressable (the 3x3 test loads its neighbourhood unconditionally)
+  size_t o = kSdRingPad + (size_t)stages * (chunk_rows + 2) * W * 4;
   l.off_list = (int)o;
   o += (size_t)kSdFW * sub_cap * 8;
   l.off_bins = (int)o;
@@ -470,7 +473,7 @@ __device__ __forceinline__ int sd_stream_run(const SdArgs& a, int n_own, int run
     const int chunk_end = min((c + 1) * CR, n_own);
     const int seg_end = min(chunk_end, run_end);
     if (done < seg_end) {
-      const uint32_t slot_u32 = smem0 + (uint32_t)slot * slot_bytes;
+      const uint32_t slot_u32 = smem0 + (uint32_t)kSdRingPad + (uint32_t)slot * slot_bytes;
       const int srow0 = done - c * CR + 1;
       cnt = sd_filter<MODE>(a, slot_u32, slot_u32 + (uint32_t)srow0 * (uint32_t)W * 4u, (seg_end - done) * (W >> 2), srow0,
                             fr_off + done, spr_shift, cnt);
@@ -926,7 +929,7 @@ __global__ void __launch_bounds__(kSdThreads, 1) stream_decode_kernel(const __gr
         const long long l0 = g0 > 0 ? g0 - 1 : g0, l1 = g1 < a.rows_total ? g1 + 1 : g1;
         const uint32_t bytes = (uint32_t)(l1 - l0) * rowb;
         mbar_expect_tx(&full[slot], bytes);
-        sd_bulk_g2s(ring_u32 + (uint32_t)slot * (uint32_t)(CR + 2) * rowb + (uint32_t)(l0 - (g0 - 1)) * rowb,
+        sd_bulk_g2s(ring_u32 + (uint32_t)kSdRingPad + (uint32_t)slot * (uint32_t)(CR + 2) * rowb + (uint32_t)(l0 - (g0 - 1)) * rowb,
                     a.hm + (size_t)l0 * W, bytes, smem_u32(&full[slot]), pol);
         if (++slot == S) {
           slot = 0;

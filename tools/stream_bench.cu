@@ -69,6 +69,52 @@ __global__ void __launch_bounds__(NCW * 32 + 32) ring_ws_kernel(const float* __r
   if (hits) atomicAdd(out, hits);
 }
 
+// As ring_ws_kernel (contiguous map, evict-first), but every chunk is copied with `halo_floats` extra floats before and
+// after it (neighbouring chunks overlap, like the decode's self-contained slots) and the whole tensor is read from
+// `in + off_floats` (chunk starts that are only 512-byte aligned).
+template <int NCW>
+__global__ void __launch_bounds__(NCW * 32 + 32) ring_halo_kernel(const float* __restrict__ in, long long n_chunks, int chunk_floats, int halo_floats, int stages, float thr, int* out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int slot_floats = chunk_floats + 2 * halo_floats;
+  float* ring = (float*)smem;
+  uint64_t* full = (uint64_t*)(smem + (size_t)stages * slot_floats * 4);
+  uint64_t* empty = full + stages;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long c0 = n_chunks * blockIdx.x / gridDim.x, c1 = n_chunks * (blockIdx.x + 1) / gridDim.x;
+  if (warp == NCW) {
+    if (lane == 0) {
+      int slot = 0; uint32_t phase = 0;
+      const uint64_t pol = policy_evict_first();
+      for (long long c = c0; c < c1; ++c) {
+        mbar_wait(&empty[slot], phase ^ 1);
+        long long f0 = c * chunk_floats - halo_floats, f1 = (c + 1) * chunk_floats + halo_floats;
+        if (f0 < 0) f0 = 0;
+        if (f1 > n_chunks * chunk_floats) f1 = n_chunks * chunk_floats;
+        mbar_expect_tx(&full[slot], (uint32_t)(f1 - f0) * 4);
+        bulk_g2s_hint(ring + (size_t)slot * slot_floats, in + f0, (uint32_t)(f1 - f0) * 4, &full[slot], pol);
+        if (++slot == stages) { slot = 0; phase ^= 1; }
+      }
+    }
+    return;
+  }
+  int slot = 0; uint32_t phase = 0; int hits = 0;
+  for (long long c = c0; c < c1; ++c) {
+    mbar_wait(&full[slot], phase);
+    const float4* p4 = (const float4*)(ring + (size_t)slot * slot_floats + halo_floats);
+#pragma unroll 4
+    for (int t = tid; t < chunk_floats / 4; t += NCW * 32) { float4 x = p4[t]; if (fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)) >= thr) ++hits; }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[slot]);
+    if (++slot == stages) { slot = 0; phase ^= 1; }
+  }
+  if (hits) atomicAdd(out, hits);
+}
+
 template <int NT, int U>
 __global__ void __launch_bounds__(NT) ldg_hint_kernel(const float4* __restrict__ in, long long n4, float thr, int* out) {
   int hits = 0;
@@ -127,24 +173,24 @@ int main() {
   int sms = 148;
   timeit([&]() { empty_kernel<<<148, 256>>>(out); }, "empty kernel (launch floor)", false);
   for (int dirty = 0; dirty < 2; ++dirty) {
-    for (int hint = 0; hint < 2; ++hint)
-      for (int mode = 0; mode < 2; ++mode)
-        for (int cfg = 0; cfg < 5; ++cfg) {
-          const int chunk_kbs[5] = {32, 16, 16, 8, 32}, stgs[5] = {4, 8, 4, 8, 3}, per[5] = {1, 1, 2, 2, 2};
-          int chunk_kb = chunk_kbs[cfg], stages = stgs[cfg], per_sm = per[cfg];
-          int chunk_floats = chunk_kb * 256; size_t smem = (size_t)stages * chunk_kb * 1024 + stages * 16 + 64;
-          long long n_chunks = n / chunk_floats;
-          cudaFuncSetAttribute(ring_ws_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          cudaFuncSetAttribute(ring_ws_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          char name[160];
-          snprintf(name, 160, "ring8w %s %s chunk=%2dKB stages=%2d ctas/sm=%d (%3d KB/SM)", hint ? "evict1st" : "nohint  ", mode ? "contig" : "inter ", chunk_kb, stages, per_sm, stages * chunk_kb * per_sm);
-          if (hint) timeit([&]() { ring_ws_kernel<8, true><<<per_sm * sms, 288, smem>>>(d, n_chunks, chunk_floats, stages, mode, 1.0f, out); }, name, dirty);
-          else timeit([&]() { ring_ws_kernel<8, false><<<per_sm * sms, 288, smem>>>(d, n_chunks, chunk_floats, stages, mode, 1.0f, out); }, name, dirty);
-        }
-    timeit([&]() { ldg_kernel<256, 4><<<sms * 8, 256>>>((const float4*)d, n / 4, 1.0f, out); }, "ldg        256thr U=4 grid=8/SM", dirty);
-    timeit([&]() { ldg_hint_kernel<256, 4><<<sms * 8, 256>>>((const float4*)d, n / 4, 1.0f, out); }, "ldg evict1 256thr U=4 grid=8/SM", dirty);
-    timeit([&]() { ldg_kernel<256, 4><<<sms * 32, 256>>>((const float4*)d, n / 4, 1.0f, out); }, "ldg        256thr U=4 grid=32/SM", dirty);
-    timeit([&]() { ldg_hint_kernel<256, 4><<<sms * 32, 256>>>((const float4*)d, n / 4, 1.0f, out); }, "ldg evict1 256thr U=4 grid=32/SM", dirty);
+    for (int variant = 0; variant < 6; ++variant) {
+      // variant: 0 = 8 warps aligned no halo, 1 = 16 warps aligned no halo, 2 = 16 warps + halo 128 floats (one row),
+      //          3 = 16 warps + halo + 512 B x 37 offset, 4 = 8 warps + halo + offset, 5 = 16 warps, offset only
+      const int halo = (variant == 2 || variant == 3 || variant == 4) ? 128 : 0;
+      const long long off = (variant == 3 || variant == 4 || variant == 5) ? 128 * 37 : 0;
+      const int chunk_floats = 8192, stages = 4;
+      const size_t smem = (size_t)stages * (chunk_floats + 2 * halo) * 4 + stages * 16 + 64;
+      const long long n_chunks = (n - off) / chunk_floats;
+      char name[160];
+      snprintf(name, 160, "ring-halo contig %2d warps halo=%3d off=%5lld B 4x32KB", (variant == 0 || variant == 4) ? 8 : 16, halo, off * 4);
+      if (variant == 0 || variant == 4) {
+        cudaFuncSetAttribute(ring_halo_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        timeit([&]() { ring_halo_kernel<8><<<sms, 288, smem>>>(d + off, n_chunks, chunk_floats, halo, stages, 1.0f, out); }, name, dirty);
+      } else {
+        cudaFuncSetAttribute(ring_halo_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        timeit([&]() { ring_halo_kernel<16><<<sms, 544, smem>>>(d + off, n_chunks, chunk_floats, halo, stages, 1.0f, out); }, name, dirty);
+      }
+    }
   }
   return 0;
 }
