@@ -20,8 +20,12 @@
 //      and (optionally) gathers size/offset/depth and does the box arithmetic.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 #include <atomic>
 #include <mutex>
+
+namespace cg = cooperative_groups;
 
 namespace tauv {
 
@@ -96,6 +100,13 @@ struct TileArgs {
   unsigned long long* cand;  // [B*items_per_frame][k]
   int* cand_count;           // [B*items_per_frame]
   uint32_t* frame_state;     // [B][kFrameStateWords], zeroed before the launch
+  // fused tail (cluster kernel, whole-frame units): the cluster selects the frame's top-k itself and writes the ranked
+  // outputs, so no candidate table and no merge launch are needed
+  int fuse;
+  int64_t* out_index;
+  int64_t* out_label;
+  float* out_score;
+  BoxArgs box;
   long long* trace;          // debug: per item {t_start, t_boot, t_scan, t_end, n_list, thr_key_at_start, 0, 0} or NULL
 };
 
@@ -679,15 +690,63 @@ __device__ void topk_emit_ranked(unsigned long long* sel, int p2, int npos, uint
 }
 
 // ----------------------------------------------------------------------------------------------
-// Candidate histogram bins shared by the streaming kernel (centernet_stream.cuh)
+// K1 (vectorised path): one thread-block cluster per "unit" (a frame, or a contiguous share of a frame's items)
 // ----------------------------------------------------------------------------------------------
-// 2048 counters over the top 13 bits of the order-preserving key, in two 1024-bin windows that cover the magnitudes
-// 2^-31 .. 2^33 of either sign at 16 bins per binade.
+// The rejection threshold of a unit and the candidate histogram it is derived from live in the DISTRIBUTED SHARED
+// MEMORY of the cluster that owns the unit — no global state, no memset, no separate seed launch:
+//   * bins: 8192 counters over the top 13 bits of the order-preserving key, 1024 per CTA (bin b lives in CTA b>>10);
+//     every CTA adds its candidates with remote shared-memory atomics;
+//   * thr_key: every CTA holds its own copy of the published rejection key; a publisher raises all eight copies with
+//     remote atomicMax, so the streaming loop reads the threshold from local shared memory;
+//   * next_item (rank 0): the unit's dynamic work queue.
+// Timeline of a unit: all eight CTAs load round 0 of their first item (4096 cells each) plus its halo rows, run the
+// full 3x3 peak test on it from a shared-memory tile (the only place every cell is tested), bin the peaks, and after
+// one cluster barrier each CTA derives the first threshold from the 8 x 4096-cell sample: at least k genuine peaks
+// of the frame lie at or above it, so nothing below it can be in the frame's top-k.  From then on the CTAs stream:
+// the loads of the next round — of this item or of the CTA's next item — are issued before the current round is
+// compared against the threshold, only strips that pass get the peak test (neighbours from L1/L2), and at the end of
+// every item its candidates go to the global candidate table and into the bins, from which the threshold is
+// republished whenever the unit's candidate count crosses k, 2k, 4k, ...
+constexpr int kClSize = 8;                            // CTAs per cluster (portable maximum)
 constexpr int kClBinShift = 19;                       // fine bin = key >> 19: sign + 8 exponent + 4 mantissa bits
 constexpr int kClWin = 1024;                          // bins per window (64 binades at 16 bins each)
 constexpr int kClBins = 2 * kClWin;                   // negative window + positive window
 constexpr int kClNegBase = 1536;                      // fine bins [1536, 2560): -2^33 .. -2^-31
 constexpr int kClPosBase = 5632;                      // fine bins [5632, 6656): +2^-31 .. +2^33
+// (measured on B200: 2 beats 3 and 4 — wider rounds spill a loaded register, and a spill right after the load waits for it)
+#ifndef TAUV_STREAM_PF
+#define TAUV_STREAM_PF 3
+#endif
+#ifndef TAUV_ROUND_W
+#define TAUV_ROUND_W 2
+#endif
+constexpr int kRoundW = TAUV_ROUND_W;                            // 128-bit strips per thread and round (2 x kRoundW live in registers)
+constexpr int kStreamThreads = kTileThreads - 32;     // warps 1..7 stream, warp 0 serves
+constexpr int kRoundF4 = kRoundW * kStreamThreads;    // 128-bit strips per streaming round per CTA
+#ifndef TAUV_SCAN_DIV
+#define TAUV_SCAN_DIV 8
+#endif
+constexpr int kScanDiv = TAUV_SCAN_DIV;
+#ifndef TAUV_SERVE_W
+#define TAUV_SERVE_W 1
+#endif
+constexpr int kServeW = TAUV_SERVE_W;                  // queue entries per lane and service step
+#ifndef TAUV_BOOT_W
+#define TAUV_BOOT_W 2
+#endif
+constexpr int kBootW = TAUV_BOOT_W;                    // 128-bit strips per thread in a bootstrap chunk
+constexpr int kBootF4 = kBootW * kTileThreads;        // strips of a bootstrap chunk (all eight warps)
+constexpr int kBootElems = 4 * kBootF4;               // cells of the bootstrap round
+constexpr int kFuseMaxK = 256;                        // fused tail: flags / ranks for k output slots
+constexpr int kHotCap = kBootW >= 2 ? 1024 : 512;       // ring of queued peak tests (entries of 8 bytes; it lives in the bootstrap tile)
+constexpr int kClMaxW = 1016;                         // halo rows are held in two 128-bit registers per thread
+
+struct __align__(16) ClusterCtx {
+  uint32_t bins[kClBins];  // THIS CTA's candidates by window bin; a scan sums the eight CTAs' copies with remote loads
+  uint32_t thr_key;        // this CTA's copy of the unit's published rejection key
+  uint32_t maxbin;         // this CTA's copy of the highest occupied window bin of the unit
+  int next_item;           // rank 0 only: next unclaimed item of the unit (index inside the frame)
+};
 
 // Window bin of an order-preserving key.  The map is monotone and only ever moves a value DOWN (values between or
 // above the windows go to the top bin of the window below them), so "at least k candidates in bins >= b" still
@@ -703,11 +762,739 @@ __device__ __forceinline__ float cl_window_edge(int wbin) {  // lowest value tha
   return key_to_float((uint32_t)b << kClBinShift);
 }
 
-}  // namespace tauv
+// Shared-memory layout of the cluster kernel (all dynamic, so that device functions reach it without pointer
+// arguments): [ClusterCtx | TileCtx | list[cap] | radix histogram | bootstrap tile / queue of deferred peak tests]
+constexpr int kClOffCtx = (int)((sizeof(ClusterCtx) + 15) / 16 * 16);
+constexpr int kClOffList = kClOffCtx + (int)((sizeof(TileCtx) + 15) / 16 * 16);
+__device__ __forceinline__ unsigned char* cl_smem() {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  return smem_raw;
+}
+__device__ __forceinline__ ClusterCtx* cl_cc() { return reinterpret_cast<ClusterCtx*>(cl_smem()); }
+__device__ __forceinline__ TileCtx* cl_ctx() { return reinterpret_cast<TileCtx*>(cl_smem() + kClOffCtx); }
+__device__ __forceinline__ unsigned long long* cl_list() { return reinterpret_cast<unsigned long long*>(cl_smem() + kClOffList); }
+__device__ __forceinline__ uint32_t* cl_hist(const TileArgs& a) {
+  return reinterpret_cast<uint32_t*>(cl_smem() + kClOffList + (size_t)a.cap * 8);
+}
+__device__ __forceinline__ float* cl_tile(const TileArgs& a) {
+  return reinterpret_cast<float*>(cl_smem() + kClOffList + (size_t)a.cap * 8 + kRadixBins * 4);
+}
 
-#include "centernet_stream.cuh"
+struct ItemGeom {
+  const float* plane;
+  uint32_t plane_flat0;
+  int e0, e1;  // element range inside the plane
+  int item;    // global item number (row of the candidate table)
+};
 
-namespace tauv {
+__device__ __forceinline__ ItemGeom item_geom(const TileArgs& a, int frame, int iif) {
+  ItemGeom g;
+  g.item = frame * (a.C * a.items_per_plane) + iif;
+  const int c = iif / a.items_per_plane;
+  const int ip = iif - c * a.items_per_plane;
+  const int r0 = ip * a.rows_per_item;
+  const int r1 = min(a.H, r0 + a.rows_per_item);
+  g.plane = a.hm + ((size_t)frame * a.C + c) * a.H * a.W;
+  g.plane_flat0 = (uint32_t)c * (uint32_t)(a.H * a.W);
+  g.e0 = r0 * a.W;
+  g.e1 = r1 * a.W;
+  return g;
+}
+
+// kRoundW 128-bit strips per thread: strips s0 + u*NT + t of the item (s0 relative to the item's first strip)
+template <int NT, int NW>
+__device__ __forceinline__ void load_strips(const ItemGeom& g, int s0, int t, float4 (&x)[NW]) {
+  const int t1 = g.e1 >> 2;
+  const int tb = (g.e0 >> 2) + s0 + t;
+#pragma unroll
+  for (int u = 0; u < NW; ++u) {
+    const int tt = tb + u * NT;
+    x[u] = (tt < t1) ? ldg_stream4(g.plane + ((size_t)tt << 2))
+                     : make_float4(TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF);
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ int cl_bin(unsigned long long c) {  // window bin of a FINAL sort key
+  if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
+    const float s = key_to_float(composite_key(c));
+    return cl_window_bin(float_to_key(logf(__fdiv_rn(s, __fsub_rn(1.0f, s)))));
+  }
+  return cl_window_bin(composite_key(c));
+}
+
+// Warp 0: scan the unit's histogram (the sum of the eight CTAs' local copies, read through distributed shared memory)
+// from the highest occupied bin downwards, find the highest bin b with count(bins >= b) >= k, and return the
+// rejection key of its lower edge (0: fewer than k candidates so far).  At most 512 bins are visited.
+// (returns the bin, or -1 when fewer than k candidates have been binned; every lane gets the same value)
+__device__ __forceinline__ int cl_scan_bin(cg::cluster_group& cluster, ClusterCtx* cc, int k) {
+  const int lane = threadIdx.x & 31;
+  const int maxbin = (int)*reinterpret_cast<volatile uint32_t*>(&cc->maxbin);
+  uint32_t acc = 0;
+  int found = -1;
+  // (32 bins per step.  Four steps' worth of remote loads issued together were measured slower — 6.3 us instead of
+  // 2.7 for the final prune, and the streaming end slipped by 2 us: the k-th best usually lies within the first 32-64
+  // bins, and every extra remote load costs at the target CTA.)
+  for (int it = 0; it < 16 && found < 0; ++it) {
+    const int bin = maxbin - it * 32 - lane;
+    uint32_t v = 0;
+    if (bin >= 0) {
+#pragma unroll
+      for (int r = 0; r < kClSize; ++r) v += *reinterpret_cast<volatile uint32_t*>(&cluster.map_shared_rank(cc, r)->bins[bin]);
+    }
+    uint32_t pre = v;  // inclusive prefix over lanes (lane 0 = highest bin)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += t;
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, acc + pre >= (uint32_t)k);
+    if (hit) found = maxbin - it * 32 - (__ffs(hit) - 1);
+    acc += __shfl_sync(0xffffffffu, pre, 31);
+    if (maxbin - (it + 1) * 32 < 0) break;
+  }
+  return found;
+}
+
+template <int MODE>
+__device__ __forceinline__ uint32_t cl_scan_threshold(cg::cluster_group& cluster, ClusterCtx* cc, int k) {
+  const int lane = threadIdx.x & 31;
+  const int found = cl_scan_bin(cluster, cc, k);
+  uint32_t key = 0;
+  if (lane == 0 && found >= 0) {
+    const float edge = cl_window_edge(found);
+    key = MODE == TAUV_TOPK_SIGMOID_PEAK ? reject_key_for_score(sigmoid_ref(edge)) : float_to_key(edge);
+  }
+  return __shfl_sync(0xffffffffu, key, 0);
+}
+
+// lanes 0..7 of one warp: raise every CTA's copy of a cluster-wide maximum
+__device__ __forceinline__ void cl_raise_all(cg::cluster_group& cluster, uint32_t* local_word, uint32_t v) {
+  const int lane = threadIdx.x & 31;
+  if (v && lane < kClSize) atomicMax(cluster.map_shared_rank(local_word, lane), v);
+}
+
+// ---- streaming warps (1..7) -------------------------------------------------------------------------------------
+// All items of this CTA in the unit (iif, iif + 8, ... < i_hi), the first one from strip s_begin on.  No barrier and no
+// call in here, and nothing but the streaming state is live, so the next round's loads stay in registers: they are
+// requested before the current round is compared against the threshold (of the same item, or the first round of the
+// next item).  Strips that pass are only QUEUED for the service warp: their peak tests wait on neighbour loads, and
+// done in line they would stall the streaming once per strip.
+__device__ __noinline__ void cl_stream_all(const TileArgs& a, int frame, int iif, int i_hi, int s_begin) {
+  const int st = (int)threadIdx.x - 32;  // thread index among the streaming threads
+  TileCtx* const ctx = cl_ctx();
+  int2* const hotq = reinterpret_cast<int2*>(cl_tile(a));
+  ItemGeom g = item_geom(a, frame, iif);
+  while (s_begin >= (g.e1 >> 2) - (g.e0 >> 2)) {  // the bootstrap round covered the whole first item
+    iif += kClSize;
+    s_begin = 0;
+    if (iif >= i_hi) {
+      iif = -1;
+      break;
+    }
+    g = item_geom(a, frame, iif);
+  }
+  float4 xn[kRoundW];
+  if (iif >= 0) load_strips<kStreamThreads, kRoundW>(g, s_begin, st, xn);
+#pragma unroll 1
+  while (iif >= 0) {
+    const bool more = iif + kClSize < i_hi;
+    const int t1 = g.e1 >> 2;
+    const int n_strips = t1 - (g.e0 >> 2);
+    if (a.trace && st == 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      a.trace[(size_t)g.item * 8 + 0] = t;
+      a.trace[(size_t)g.item * 8 + 5] = composite_key(ctx->thr);
+    }
+#pragma unroll 1
+    for (int s0 = s_begin; s0 < n_strips; s0 += kRoundF4) {
+      float4 x[kRoundW];
+#pragma unroll
+      for (int u = 0; u < kRoundW; ++u) x[u] = xn[u];
+      if (s0 + kRoundF4 < n_strips) load_strips<kStreamThreads, kRoundW>(g, s0 + kRoundF4, st, xn);
+      else if (more) load_strips<kStreamThreads, kRoundW>(item_geom(a, frame, iif + kClSize), 0, st, xn);
+#if TAUV_STREAM_PF > 0
+      // L2 prefetch of the round TAUV_STREAM_PF ahead (inside the item): the registers hold two
+      // rounds, ~28 KB per SM in flight, which covers ~0.8 us at 5 TB/s — HBM latency under this load is longer, an L2
+      // hit is not.  One lane in eight covers its warp's 128-byte line per strip row.  Measured: 109.6 us without,
+      // 104.7 / 104.5 / 106.0 us with 2 / 3 / 5 rounds ahead; carrying on into the CTA's next item: 105.5 (not kept).
+      if ((st & 7) == 0) {
+#pragma unroll
+        for (int u = 0; u < kRoundW; ++u) {
+          const int rel = s0 + TAUV_STREAM_PF * kRoundF4 + st + u * kStreamThreads;  // strip, relative to the item
+          if (rel < n_strips) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.plane + ((size_t)((g.e0 >> 2) + rel) << 2)));
+        }
+      }
+#endif
+      const float thr_f = *reinterpret_cast<volatile float*>(&ctx->thr_f);  // kept current by the service warp
+      const int tb = (g.e0 >> 2) + s0 + st;
+      uint32_t hot = 0;
+#pragma unroll
+      for (int u = 0; u < kRoundW; ++u)
+        if (fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w)) >= thr_f && tb + u * kStreamThreads < t1) hot |= 1u << u;
+#pragma unroll 1
+      while (hot) {
+        const int u = __ffs(hot) - 1;
+        hot &= hot - 1;
+        const int slot = atomicAdd(&ctx->nhot, 1);
+        // ring full: wait for the service warp (it never waits for us, so this always ends)
+        while (slot - *reinterpret_cast<volatile int*>(&ctx->qhead) >= kHotCap) __nanosleep(64);
+        hotq[slot & (kHotCap - 1)] = make_int2(iif, (tb + u * kStreamThreads) << 2);
+      }
+    }
+    if (a.trace && st == 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      a.trace[(size_t)g.item * 8 + 2] = t;
+    }
+    if (!more) break;
+    iif += kClSize;
+    s_begin = 0;
+    g = item_geom(a, frame, iif);
+  }
+  __syncwarp();
+  __threadfence_block();
+  if ((threadIdx.x & 31) == 0) atomicAdd(&ctx->done, 1);
+}
+
+// ---- service warp (0) ----------------------------------------------------------------------------------------------
+// Consumes the queue while the other warps stream: runs the peak tests (neighbours from L2/HBM; the latency is this
+// warp's alone), appends candidates to the CTA's list, adds them to this CTA's bins, and whenever it has binned k/8
+// new candidates rescans the unit's histogram (remote loads) and raises the rejection key in all eight CTAs.  It also
+// folds keys published by the other CTAs into this CTA's threshold, which the streaming warps read every round.
+template <int MODE>
+__device__ __noinline__ void cl_service_warp(const TileArgs& a, int frame, cg::cluster_group& cluster) {
+  const int lane = threadIdx.x & 31;
+  TileCtx* const ctx = cl_ctx();
+  ClusterCtx* const cc = cl_cc();
+  unsigned long long* const list = cl_list();
+  int2* const hotq = reinterpret_cast<int2*>(cl_tile(a));
+  const int every = a.k >= kScanDiv ? a.k / kScanDiv : 1;  // new candidates between two rescans of the unit's histogram
+  int head = 0, since_scan = 0;
+  int n_binned = ctx->n_boot;  // list[0, n_binned) are in the bins already (bootstrap survivors); -1: stop binning
+  while (true) {
+    if (lane == 0) set_thr(ctx, (unsigned long long)(*reinterpret_cast<volatile uint32_t*>(&cc->thr_key)) << 32);
+    __syncwarp();
+    const int done = *reinterpret_cast<volatile int*>(&ctx->done);
+    const int avail = *reinterpret_cast<volatile int*>(&ctx->nhot) - head;
+    if (avail <= 0) {
+      if (done == kStreamThreads / 32) break;
+      __nanosleep(128);
+      continue;
+    }
+    // up to kServeW entries per lane and step (measured: two per lane — half as many fixed costs per entry — is slower,
+    // 104.9 -> 107.0 us: new candidates reach the bins, and with them the threshold, later)
+    const int n = avail < 32 * kServeW ? avail : 32 * kServeW;
+    int2 q[kServeW];
+#pragma unroll
+    for (int w = 0; w < kServeW; ++w) {
+      q[w] = make_int2(-1, 0);
+      if (lane + 32 * w < n) {
+        volatile int2* slot = reinterpret_cast<volatile int2*>(&hotq[(head + lane + 32 * w) & (kHotCap - 1)]);
+        while ((q[w].x = slot->x) < 0) {}  // (the producer is between its atomicAdd and its store)
+        q[w].y = slot->y;
+        slot->x = -1;                      // free the slot before the head moves past it
+      }
+    }
+    __syncwarp();
+    head += n;
+    if (lane == 0) *reinterpret_cast<volatile int*>(&ctx->qhead) = head;
+    int fl = 0;
+#pragma unroll
+    for (int w = 0; w < kServeW; ++w) {
+      if (lane + 32 * w < n) {
+        const ItemGeom g = item_geom(a, frame, q[w].x);
+        fl |= examine<MODE, true>(a, ctx, list, g.plane, g.plane_flat0, q[w].y);
+      }
+    }
+    fl = __reduce_or_sync(0xffffffffu, (unsigned)fl);
+    if (fl & 2) {  // the list is full: everything is redone safely at the end of the unit; keep draining the queue
+      if (lane == 0) ctx->flags |= 2;
+      n_binned = -1;
+      continue;
+    }
+    __syncwarp();
+    const int cnt = *reinterpret_cast<volatile int*>(&ctx->count);
+    if (n_binned >= 0 && cnt > n_binned) {
+      // list[n_binned, cnt) are new and still carry logit keys (SIGMOID_PEAK), the space the bins live in
+      uint32_t my_maxbin = 0;
+      for (int i = n_binned + lane; i < cnt; i += 32) {
+        const uint32_t key = composite_key(list[i]);
+        if (MODE == TAUV_TOPK_SIGMOID_PEAK && !(key_to_float(key) > -80.0f)) continue;  // may underflow to score 0
+        const int bin = cl_window_bin(key);
+        if (bin < 0) continue;
+        atomicAdd(&cc->bins[bin], 1u);
+        my_maxbin = max(my_maxbin, (uint32_t)bin);
+      }
+      my_maxbin = __reduce_max_sync(0xffffffffu, my_maxbin);
+      since_scan += cnt - n_binned;
+      n_binned = cnt;
+      if (my_maxbin > *reinterpret_cast<volatile uint32_t*>(&cc->maxbin)) cl_raise_all(cluster, &cc->maxbin, my_maxbin);
+      if (since_scan >= every) {
+        since_scan = 0;
+        __threadfence_block();
+        cl_raise_all(cluster, &cc->thr_key, cl_scan_threshold<MODE>(cluster, cc, a.k));
+      }
+    }
+  }
+}
+
+// The list overflowed somewhere in the unit (plateaus, or no usable threshold): start this CTA's share of the unit
+// over, in sub-steps that cannot overflow, pruning to the exact top-k whenever the list passes `soft`.
+template <int MODE>
+__device__ __noinline__ void cl_redo_all_safely(const TileArgs& a, TileCtx* ctx, unsigned long long* list, uint32_t* hist,
+                                                int frame, int iif0, int i_hi) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ctx->count = 0;
+    ctx->n_conv = 0;
+    ctx->n_boot = -1;
+    ctx->flags = 0;
+  }
+  __syncthreads();
+  for (int iif = iif0; iif < i_hi; iif += kClSize) {
+    const ItemGeom g = item_geom(a, frame, iif);
+    for (int s0 = g.e0; s0 < g.e1; s0 += a.sub_elems) {
+      scan_elems<MODE, true>(a, ctx, list, g.plane, g.plane_flat0, s0, min(s0 + a.sub_elems, g.e1));
+      __syncthreads();
+      if (ctx->count > a.soft) prune_list<MODE>(a, ctx, list, hist);  // uniform: nobody pushes before the next barrier
+      __syncthreads();
+    }
+  }
+}
+
+// Bootstrap round of a unit: the full test on round 0 of this CTA's first item, from the shared-memory tile
+// (tile[0] = plane cell `origin`; cells outside the plane are never read).  Peaks go to the list and into the bins.
+template <int MODE>
+__device__ __noinline__ void cl_bootstrap_round(const TileArgs& a, TileCtx* ctx, unsigned long long* list,
+                                                uint32_t* hist, const float* tile, int origin, const ItemGeom& g,
+                                                cg::cluster_group& cluster, ClusterCtx* cc) {
+  const int tid = threadIdx.x;
+  const int c_end = min(g.e1, g.e0 + kBootElems);
+  int fl = 0;
+  if (MODE == TAUV_TOPK_SIGMOID_PEAK) {
+    // Every cell of the round gets the 3x3 test from the tile.  A ninth of them are peaks: they are kept in registers
+    // and appended to the list at offsets from one block-wide scan — no atomics (pushed one by one through a
+    // shared-memory counter they serialise and cost several microseconds here).
+    const int W = a.W, H = a.H;
+    const float NI = TAUV_NEG_INF;
+    float pv[kBootW * 4];
+    uint32_t pmask = 0;
+#pragma unroll
+    for (int u = 0; u < kBootW; ++u) {
+      const int off = g.e0 + ((u * kTileThreads + tid) << 2);
+      if (off < c_end) {
+        const int r = off / W, col = off - r * W;
+        const float* p1 = tile + (off - origin);
+        const float4 x = *reinterpret_cast<const float4*>(p1);
+        const bool hl = col > 0, hr = col + 4 < W;
+        float4 up = make_float4(NI, NI, NI, NI), dn = up;
+        float ul = NI, ur = NI, dl = NI, dr = NI;
+        if (r > 0) {
+          up = *reinterpret_cast<const float4*>(p1 - W);
+          if (hl) ul = p1[-W - 1];
+          if (hr) ur = p1[-W + 4];
+        }
+        if (r + 1 < H) {
+          dn = *reinterpret_cast<const float4*>(p1 + W);
+          if (hl) dl = p1[W - 1];
+          if (hr) dr = p1[W + 4];
+        }
+        const float ml = hl ? p1[-1] : NI, mr = hr ? p1[4] : NI;
+        float cm[6];
+        cm[0] = fmaxf(fmaxf(ul, ml), dl);
+        cm[1] = fmaxf(fmaxf(up.x, x.x), dn.x);
+        cm[2] = fmaxf(fmaxf(up.y, x.y), dn.y);
+        cm[3] = fmaxf(fmaxf(up.z, x.z), dn.z);
+        cm[4] = fmaxf(fmaxf(up.w, x.w), dn.w);
+        cm[5] = fmaxf(fmaxf(ur, mr), dr);
+        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const float xv = xs[cc];
+          const float m = fmaxf(fmaxf(cm[cc], cm[cc + 1]), cm[cc + 2]);
+          bool peak = (xv >= m);
+          if (!peak && (xv > 4.0f || m < -80.0f || (m - xv) < 1e-3f)) peak = sigmoid_tie(xv, m);
+          pv[u * 4 + cc] = xv;
+          if (peak) pmask |= 1u << (u * 4 + cc);
+        }
+      }
+    }
+    // block-wide exclusive scan of the per-thread peak counts
+    const int lane = tid & 31, warp = tid >> 5;
+    const int mine = __popc(pmask);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) ctx->wsum[warp] = incl;
+    __syncthreads();
+    const int old_count = ctx->count;  // (entries of earlier bootstrap chunks)
+    int base = old_count + incl - mine, total = old_count;
+    for (int w = 0; w < kTileThreads / 32; ++w) {
+      if (w < warp) base += ctx->wsum[w];
+      total += ctx->wsum[w];
+    }
+    __syncthreads();  // everybody has read the old count
+    if (total > a.cap) {
+      fl = 2;  // (plateaus) the whole unit is redone safely
+    } else {
+#pragma unroll
+      for (int i = 0; i < kBootW * 4; ++i) {
+        if (pmask & (1u << i)) {
+          const int off = g.e0 + (((i >> 2) * kTileThreads + tid) << 2) + (i & 3);
+          list[base++] = make_composite(float_to_key(pv[i]), g.plane_flat0 + (uint32_t)off);
+        }
+      }
+    }
+    if (tid == 0) ctx->count = total > a.cap ? 0 : total;
+  } else {
+    // RAW: every cell is a candidate; keep this round's k best (exact selection straight from the tile)
+    const int n = c_end - g.e0;
+    auto load = [&](int i) { return make_composite(float_to_key(tile[g.e0 - origin + i]), g.plane_flat0 + (uint32_t)(g.e0 + i)); };
+    const unsigned long long T = block_kth_largest<kTileThreads>(load, n, a.k, hist, ctx->sel);
+    for (int i = tid; i < n; i += kTileThreads)
+      if (load(i) >= T) fl |= push_entry(a, ctx, list, tile[g.e0 - origin + i], g.plane_flat0 + (uint32_t)(g.e0 + i));
+  }
+  if (fl) atomicOr(&ctx->flags, fl);
+  if (tid == 0) ctx->maxbin = 0;
+  if (a.trace && tid == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.trace[(size_t)g.item * 8 + 3] = t; }
+  __syncthreads();
+  if (a.trace && tid == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.trace[(size_t)g.item * 8 + 4] = t; }
+  if (ctx->flags & 2) return;  // the list overflowed (plateaus): the item is redone safely later; nothing is binned now
+  const int nb = ctx->count;
+  uint32_t my_maxbin = 0;
+  for (int i = max(ctx->n_boot, 0) + tid; i < nb; i += kTileThreads) {  // (what this chunk added)
+    // (SIGMOID_PEAK: the entries still carry logit keys, which is the space the bins live in; a logit below -80 may
+    // underflow to a zero score, which is no candidate)
+    const uint32_t key = composite_key(list[i]);
+    if (MODE == TAUV_TOPK_SIGMOID_PEAK && !(key_to_float(key) > -80.0f)) continue;
+    const int bin = cl_window_bin(key);
+    if (bin < 0) continue;
+    atomicAdd(&cc->bins[bin], 1u);
+    my_maxbin = max(my_maxbin, (uint32_t)bin);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) my_maxbin = max(my_maxbin, __shfl_xor_sync(0xffffffffu, my_maxbin, o));
+  if ((tid & 31) == 0 && my_maxbin) atomicMax(&ctx->maxbin, my_maxbin);
+  __syncthreads();
+  if (tid < 32) cl_raise_all(cluster, &cc->maxbin, ctx->maxbin);
+  if (tid == 0) ctx->n_boot = nb;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTileThreads, 4) tile_cluster_kernel(const __grid_constant__ TileArgs a, int n_units,
+                                                                       int parts) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  unsigned long long* list = cl_list();
+  uint32_t* hist = cl_hist(a);
+  float* tile = cl_tile(a);                    // [kBootElems + 2W + 8]
+  int2* hotq = reinterpret_cast<int2*>(tile);  // the same memory after the bootstrap round: ring of queued peak tests
+  TileCtx* ctx = cl_ctx();
+  ClusterCtx* cc = cl_cc();
+  const int tid = threadIdx.x;
+  const int rank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / kClSize, ncl = gridDim.x / kClSize;
+  const int ipf = a.C * a.items_per_plane;
+  const int W = a.W;
+  auto now = []() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; };
+  const long long t_kernel = a.trace ? now() : 0;
+  // one chunk (kBootElems cells per CTA) for k <= 128, then as many cells as 2048 per 128 of k, at most 16384
+  const int n_boot_chunks = a.k <= 128 ? 1 : min(8, (a.k + 127) / 128) * (2048 / kBootElems);
+
+#pragma unroll 1
+  for (int unit = cid; unit < n_units; unit += ncl) {
+    const int frame = unit / parts, part = unit - frame * parts;
+    const int i_lo = (int)((long long)ipf * part / parts), i_hi = (int)((long long)ipf * (part + 1) / parts);
+    // items of a unit are dealt round-robin to the cluster's CTAs: this CTA takes i_lo + rank, + 8, + 16, ...
+    int iif = i_lo + rank;
+    bool have = iif < i_hi;
+    ItemGeom g = item_geom(a, frame, have ? iif : i_lo);
+    float4 xn[kBootW];
+    // halo of round 0: plane cells [e0 - W, e0) and [c_end, c_end + W + 4), two 128-bit strips per thread at most
+    const int c_end = min(g.e1, g.e0 + kBootElems);
+    const int origin = g.e0 - W;                 // plane cell held in tile[0] (may be negative: never read then)
+    const int plane_cells = a.H * W;
+    const int nh = W >> 2;                        // strips per halo row
+    float4 halo[2];
+    if (have) {
+      load_strips<kTileThreads, kBootW>(g, 0, tid, xn);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int h = tid + j * kTileThreads;     // [0, nh): row above; [nh, 2nh+1): row below (+1 strip)
+        int cell = -1;
+        if (h < nh) cell = g.e0 - W + (h << 2);
+        else if (h < 2 * nh + 1) cell = c_end + ((h - nh) << 2);
+        halo[j] = (cell >= 0 && cell < plane_cells) ? ldg_stream4(g.plane + cell) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    // reset the unit's state while the loads are in flight
+    for (int i = tid; i < kClBins / 4; i += kTileThreads) reinterpret_cast<uint4*>(cc->bins)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+      cc->thr_key = 0u;
+      cc->maxbin = 0u;
+      ctx->count = 0;
+      ctx->n_conv = 0;
+      ctx->n_boot = 0;
+      ctx->nhot = 0;
+      ctx->qhead = 0;
+      ctx->done = 0;
+      ctx->flags = 0;
+      ctx->thr = 0ull;
+      ctx->thr_f = TAUV_NEG_INF;
+    }
+    // (1) every CTA's bins and words are ready (and nobody is still reading the previous unit's).  Split barrier: the
+    // wait sits after the tile has been filled, so its latency hides behind the sample loads.
+    cluster.barrier_arrive();
+
+    long long tr0 = 0;
+    if (a.trace && tid == 0) tr0 = now();
+    if (have) {
+      // ---- bootstrap: round 0 of the first item, every cell tested, from shared memory
+#pragma unroll
+      for (int u = 0; u < kBootW; ++u) {
+        const int off = g.e0 + ((u * kTileThreads + tid) << 2);
+        if (off < c_end) *reinterpret_cast<float4*>(tile + (off - origin)) = xn[u];
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int h = tid + j * kTileThreads;
+        int cell = -1;
+        if (h < nh) cell = g.e0 - W + (h << 2);
+        else if (h < 2 * nh + 1) cell = c_end + ((h - nh) << 2);
+        if (cell >= 0 && cell < plane_cells) *reinterpret_cast<float4*>(tile + (cell - origin)) = halo[j];
+      }
+      __syncthreads();
+      if (a.trace && tid == 0) a.trace[(size_t)g.item * 8 + 1] = now();
+    }
+    cluster.barrier_wait();  // (1)
+    if (have) {
+      cl_bootstrap_round<MODE>(a, ctx, list, hist, tile, origin, g, cluster, cc);
+      // A large k needs a larger sample: the first threshold lets through about k / (sample fraction) cells, and with
+      // 2048 cells per CTA a k of 1000 would make every strip pass.  One more 2048-cell chunk per 128 of k.
+      for (int c = 1; c < n_boot_chunks; ++c) {
+        ItemGeom gb = g;
+        gb.e0 = g.e0 + c * kBootElems;
+        if (gb.e0 >= g.e1) break;
+        const int ce = min(gb.e1, gb.e0 + kBootElems), org = gb.e0 - W;
+        __syncthreads();  // the tile is re-used
+        float4 t4[kBootW];
+        load_strips<kTileThreads, kBootW>(gb, 0, tid, t4);
+#pragma unroll
+        for (int u = 0; u < kBootW; ++u) {
+          const int off = gb.e0 + ((u * kTileThreads + tid) << 2);
+          if (off < ce) *reinterpret_cast<float4*>(tile + (off - org)) = t4[u];
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int h = tid + j * kTileThreads;
+          int cell = -1;
+          if (h < nh) cell = gb.e0 - W + (h << 2);
+          else if (h < 2 * nh + 1) cell = ce + ((h - nh) << 2);
+          if (cell >= 0 && cell < plane_cells) *reinterpret_cast<float4*>(tile + (cell - org)) = ldg_stream4(g.plane + cell);
+        }
+        __syncthreads();
+        cl_bootstrap_round<MODE>(a, ctx, list, hist, tile, org, gb, cluster, cc);
+      }
+      if (a.trace && tid == 0) a.trace[(size_t)g.item * 8 + 6] = now();
+    }
+    cluster.sync();  // (2) the sample of all eight CTAs is in their bins, the highest occupied bin is known everywhere
+    // first threshold: every CTA derives it for itself (warp 0, remote loads only; nothing to publish)
+    if (tid < 32) {
+      const uint32_t key = cl_scan_threshold<MODE>(cluster, cc, a.k);
+      if (tid == 0 && key) {
+        atomicMax(&cc->thr_key, key);
+        set_thr(ctx, (unsigned long long)(*reinterpret_cast<volatile uint32_t*>(&cc->thr_key)) << 32);
+      }
+    }
+    __syncthreads();
+    // (the bootstrap collected every peak of its sample; those below the first threshold stay in the list — they are
+    // binned already and the tail's final prune drops them — rather than paying three barriers for a compaction here)
+    if (a.trace && tid == 0 && have) a.trace[(size_t)g.item * 8 + 7] = now();
+
+    // ---- stream: warps 1..7 stream every item of this CTA, warp 0 serves the queue; no barrier until both are done
+    if (have) {
+      for (int i = tid; i < kHotCap; i += kTileThreads) hotq[i] = make_int2(-1, 0);  // (the tile is free now)
+      __syncthreads();
+      if (tid < 32) cl_service_warp<MODE>(a, frame, cluster);
+      else cl_stream_all(a, frame, iif, i_hi, n_boot_chunks * kBootF4);
+      __syncthreads();
+      if (ctx->flags & 2) cl_redo_all_safely<MODE>(a, ctx, list, hist, frame, iif, i_hi);
+      if (a.trace && tid == 0) {
+        const long long t = now();
+        int last = iif;
+        for (int j = iif; j < i_hi; j += kClSize) {
+          if (j != iif) a.trace[(size_t)item_geom(a, frame, j).item * 8 + 3] = t;
+          if (j != iif) a.trace[(size_t)item_geom(a, frame, j).item * 8 + 4] = ctx->count;
+          last = j;
+        }
+        if (last != iif) {
+          unsigned smid;
+          asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+          a.trace[(size_t)item_geom(a, frame, last).item * 8 + 7] = smid;
+          a.trace[(size_t)item_geom(a, frame, last).item * 8 + 6] = t_kernel;
+          a.trace[(size_t)item_geom(a, frame, last).item * 8 + 3] = t;
+        }
+      }
+    }
+
+    if (a.fuse) {
+      // ---- fused tail (parts == 1).  The published threshold lags behind the final k-th best, so the eight lists
+      // together hold several times k candidates.  One last scan of the (now complete) histogram gives the bin that
+      // holds the k-th best; everything below its lower edge is dropped, which leaves k plus a handful.  Then the
+      // ranking is shared out: every CTA copies the eight pruned lists into its own shared memory and ranks ITS OWN
+      // entries against them with 16 threads per entry — the rank of a key among distinct keys is its output slot, so
+      // there is no selection pass and no sort, and only O(1) barriers.  Rank 0 adds the zero-score fillers and the
+      // threshold count.
+      __shared__ unsigned long long s_keyT;
+      __shared__ int s_total, s_nge;
+      __shared__ uint32_t s_flags[kFuseMaxK];  // rank 0: flat indices < k taken by a selected peak (for the fillers)
+      __shared__ int s_rank[kFuseMaxK];
+      const int n = ctx->count;
+      // (debug trace, tools/tail_trace.py: tail stamps go to unused columns of the CTA's second and third item rows)
+      auto tail_stamp = [&](int which) {
+        if (a.trace && tid == 0 && iif + 2 * kClSize < i_hi)
+          a.trace[(size_t)item_geom(a, frame, iif + (which < 3 ? 1 : 2) * kClSize).item * 8 + (which % 3 == 0 ? 1 : 5 + which % 3)] = now();
+      };
+      convert_entries<MODE>(ctx, list, n);
+      for (int i = tid; i < a.k; i += kTileThreads) s_flags[i] = 0u;
+      if (tid == 0) s_nge = 0;
+      cluster.sync();  // (3a) every CTA has finished streaming and binning; rank 0's flags are clear
+      tail_stamp(0);
+      if (tid < 32) {
+        const int bin = cl_scan_bin(cluster, cc, a.k);
+        if (tid == 0) {
+          unsigned long long kt = 1ull;  // fewer than k candidates binned: keep everything that is non-zero
+          if (bin >= 0) {
+            const float edge = cl_window_edge(bin);
+            // at least k candidates have values >= edge; in SIGMOID_PEAK mode the list holds their sigmoids, whose
+            // rounding (<= 2 ulp) the relative guard band covers
+            const float lowest = MODE == TAUV_TOPK_SIGMOID_PEAK ? sigmoid_ref(edge) * (1.0f - 4e-5f) : edge;
+            kt = (unsigned long long)float_to_key(lowest) << 32;
+            if (kt == 0ull) kt = 1ull;
+          }
+          s_keyT = kt;
+        }
+      }
+      __syncthreads();
+      {
+        const unsigned long long kt = s_keyT;
+        compact_list(ctx, list, n, [&](unsigned long long c) { return c >= kt && c != 0ull; });
+      }
+      if (ctx->base > a.k) {  // (ties / plateaus: more than k survive in this CTA alone; the pool holds 8k keys)
+        const int n2 = ctx->base;
+        const unsigned long long T = block_kth_largest<kTileThreads>([&](int i) { return list[i]; }, n2, a.k, hist, ctx->sel);
+        compact_list(ctx, list, n2, [&](unsigned long long c) { return c >= T; });
+      }
+      if (tid == 0) ctx->emit = (uint32_t)ctx->base;
+      tail_stamp(1);
+      cluster.sync();  // (3b) all eight pruned lists are final
+      tail_stamp(2);
+      unsigned long long* pool = reinterpret_cast<unsigned long long*>(hist);  // hist + tile: contiguous, >= 8k keys
+      {
+        // the eight counts first (independent remote loads: one DSMEM round trip, not eight in a chain), then all lists
+        int cnt[kClSize], total_n = 0;
+#pragma unroll
+        for (int r = 0; r < kClSize; ++r) cnt[r] = (int)*cluster.map_shared_rank(&ctx->emit, r);
+#pragma unroll
+        for (int r = 0; r < kClSize; ++r) {
+          const unsigned long long* rl = cluster.map_shared_rank(list, r);
+          for (int i = tid; i < cnt[r]; i += kTileThreads) pool[total_n + i] = rl[i];
+          total_n += cnt[r];
+        }
+        if (tid == 0) s_total = total_n;
+      }
+      const int n_own = (int)ctx->emit;
+      for (int i = tid; i < n_own; i += kTileThreads) s_rank[i] = 0;
+      __syncthreads();
+      {
+        // 16 threads per own entry, each over a sixteenth of the pool; partial ranks meet in shared memory
+        const int total = s_total;
+        const int part = tid & 15;
+        for (int e = tid >> 4; e < n_own; e += kTileThreads / 16) {
+          const unsigned long long c = list[e];
+          int r = 0;
+          for (int j = part; j < total; j += 16) r += (pool[j] > c);
+          if (r) atomicAdd(&s_rank[e], r);
+        }
+      }
+      __syncthreads();
+      tail_stamp(3);
+      {
+        const BoxArgs& g = a.box;
+        const uint32_t hw_elems = (uint32_t)(a.H * a.W);  // (the cluster path requires W <= 1016 and C*H*W < 2^32)
+        int my_ge = 0;
+        for (int i = tid; i < n_own; i += kTileThreads) {
+          const int r = s_rank[i];
+          if (r < a.k) {
+            const unsigned long long c = list[i];
+            const uint32_t flat = composite_idx(c);
+            const float sc = key_to_float(composite_key(c));
+            const uint32_t lab = flat / hw_elems;  // 32-bit: a 64-bit divide is ~100 dependent instructions
+            const uint32_t rem = flat - lab * hw_elems;
+            const int iy = (int)(rem / (uint32_t)a.W), ix = (int)(rem - (uint32_t)iy * (uint32_t)a.W);
+            const long long slot = (long long)frame * a.k + r;
+            a.out_index[slot * 2 + 0] = iy;
+            a.out_index[slot * 2 + 1] = ix;
+            a.out_label[slot] = lab;
+            a.out_score[slot] = sc;
+            if (g.enabled) {
+              box_one(g, frame, slot, iy, ix);
+              if (!(sc < g.thr)) ++my_ge;
+            }
+            if (flat < (uint32_t)a.k) *cluster.map_shared_rank(&s_flags[flat], 0) = 1u;
+          }
+        }
+        // one remote add per warp, not per thread (remote shared-memory atomics cost ~8 ns each at the target)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_ge += __shfl_xor_sync(0xffffffffu, my_ge, o);
+        if ((tid & 31) == 0 && my_ge) atomicAdd(cluster.map_shared_rank(&s_nge, 0), my_ge);
+      }
+      tail_stamp(4);
+      cluster.sync();  // (3) nobody touches this unit's distributed state any more; rank 0 sees flags and count
+      tail_stamp(5);
+      if (rank == 0) {
+        const int npos = min(a.k, s_total);
+        if (MODE == TAUV_TOPK_SIGMOID_PEAK && npos < a.k)
+          topk_emit_fillers<kTileThreads>(s_flags, npos, frame, a.k, a.H, a.W, a.out_index, a.out_label, a.out_score, a.box);
+        if (a.box.enabled && tid == 0) {  // entries before the first score < threshold (ranked scores descend; fillers score 0)
+          int cnt = s_nge;
+          if (MODE == TAUV_TOPK_SIGMOID_PEAK && npos < a.k && !(0.0f < a.box.thr)) cnt += a.k - npos;
+          a.box.count[frame] = cnt;
+        }
+        __syncthreads();
+      }
+      continue;
+    }
+    // ---- the CTA's candidates of the whole unit: exact top-k, one row of the candidate table
+    {
+      const int row = frame * a.rows_per_frame + part * kClSize + rank;
+      if (part == 0 && rank == 0)  // rows of the frame that no CTA owns hold no candidates
+        for (int r = parts * kClSize + tid; r < a.rows_per_frame; r += kTileThreads) a.cand_count[frame * a.rows_per_frame + r] = 0;
+      const int n = ctx->count;
+      if (n == 0) {
+        if (tid == 0) a.cand_count[row] = 0;
+      } else {
+        convert_entries<MODE>(ctx, list, n);
+        const unsigned long long T = block_kth_largest<kTileThreads>([&](int i) { return list[i]; }, n, a.k, hist, ctx->sel);
+        if (tid == 0) ctx->emit = 0;
+        __syncthreads();
+        unsigned long long* out = a.cand + (size_t)row * a.k;
+        for (int i = tid; i < n; i += kTileThreads) {
+          const unsigned long long c = list[i];
+          if (c >= T && c != 0ull) out[atomicAdd(&ctx->emit, 1u)] = c;
+        }
+        __syncthreads();
+        if (tid == 0) a.cand_count[row] = (int)ctx->emit;
+      }
+    }
+    cluster.sync();  // (3) nobody touches this unit's distributed state any more
+  }
+}
 
 // ----------------------------------------------------------------------------------------------
 // K2: per-frame merge (+ optional box decode) of the candidate table
@@ -880,124 +1667,108 @@ static int plan_and_check(const float* hm, int B, int C, int H, int W, int k, vo
 #else
   a->trace = nullptr;
 #endif
+  a->fuse = 0; a->out_index = nullptr; a->out_label = nullptr; a->out_score = nullptr;
+  a->box = BoxArgs{};
   const long long items = (long long)B * p->items_per_frame;
   TAUV_REQUIRE(items < (1LL << 31), TAUV_E_UNSUPPORTED, "too many items (%lld)", items);
   return 0;
 }
 
-// stage 1 of the two-stage path (scalar loads for W % 4 != 0 or an unaligned base, very wide maps, k > 1024, and the
-// two-stage API): one CTA per item against per-frame state in the workspace, zeroed here (key 0 = "no threshold yet")
+// What the fused tail of the cluster kernel writes (run_topk hands this in; the two-stage API never fuses).
+struct FuseOut {
+  int64_t* index;
+  int64_t* label;
+  float* score;
+  const BoxArgs* box;
+};
+
+// stage 1: per-item candidates into the workspace — or, when `fo` is given and the launch qualifies (whole-frame
+// units, 8k candidates fit the list), the complete ranked output (*fused = true: stage 2 must be skipped)
 static int run_stage1(const float* hm, int B, int C, int H, int W, int k, int mode, void* ws, size_t ws_bytes,
-                      cudaStream_t st) {
+                      cudaStream_t st, const FuseOut* fo = nullptr, bool* fused = nullptr) {
+  if (fused) *fused = false;
   TopkPlan p;
   TileArgs a;
   if (int e = plan_and_check(hm, B, C, H, W, k, ws, ws_bytes, &p, &a)) return e;
   const long long items = (long long)B * p.items_per_frame;
-  void (*kern)(const TileArgs) = nullptr;
-  if (mode == TAUV_TOPK_SIGMOID_PEAK) kern = p.vec ? tile_topk_kernel<1, true> : tile_topk_kernel<1, false>;
-  else kern = p.vec ? tile_topk_kernel<0, true> : tile_topk_kernel<0, false>;
-  TAUV_CUDA(ensure_dynamic_smem((const void*)kern, p.smem_bytes));
-  TAUV_CUDA(cudaMemsetAsync(a.cand_count, 0, p.count_bytes + p.state_bytes, st));  // (adjacent in the workspace)
-  kern<<<(unsigned)items, kTileThreads, p.smem_bytes, st>>>(a);
-  TAUV_LAUNCH_CHECK("tile_topk_kernel");
-  return 0;
-}
-
-// ---- the one-launch streaming path (centernet_stream.cuh) ----------------------------------------------------------
-struct StreamPlan {
-  int G, chunk_rows, stages, tbl_rows, row_cap, sub_cap;
-  size_t smem_bytes;
-  size_t cand_bytes, count_bytes, ticket_bytes;
-};
-
-static bool stream_shape_ok(const void* hm, int C, int H, int W, int k) {
-  return (W % 4 == 0) && ((uintptr_t)hm % 16 == 0) && W <= kSdMaxW && k <= kSdMaxK && (long long)C * H < (1LL << 30);
-}
-
-static void make_stream_plan(int B, int C, int H, int W, int k, StreamPlan* p) {
-  const long long R = (long long)B * C * H;
-  // chunk: whole rows, about 32 KB (one filter iteration of the 16 warps); private sub-lists of 256 entries per
-  // filter warp for k <= 128, 512 for k <= 256; ring: as many chunks as fit beside them (measured,
-  // profiles/r2_stream_bench_v*.txt: ~100 KB per SM in flight keeps HBM busy, and a slot is only released one chunk late
-  // because the 3x3 test of a chunk's last row needs the next chunk's first)
-  int cr = 32768 / (W * 4);
-  if (cr < 1) cr = 1;
-  p->chunk_rows = cr;
-  p->sub_cap = k <= 128 ? 256 : 512;
-  const size_t fixed = sd_smem_bytes(0, 0, W, p->sub_cap);
-  int st = (int)((226 * 1024 - fixed) / ((size_t)(cr + 2) * W * 4));  // (227 KB opt-in limit minus the static shared memory)
-  if (st > 8) st = 8;
-  p->stages = st;
-#ifdef TAUV_DEBUG
-  if (const char* e = getenv("TAUV_SD_CR")) {  // experiment: rows per chunk / ring slots
-    cr = atoi(e);
-    p->chunk_rows = cr;
-    st = (int)((226 * 1024 - fixed) / ((size_t)(cr + 2) * W * 4));
-    if (st > kSdMaxStages) st = kSdMaxStages;
-    p->stages = st;
+  if (!(p.vec && W <= kClMaxW)) {
+    // scalar path (W % 4 != 0, unaligned base) and very wide maps: one CTA per item against per-frame state in the
+    // workspace, zeroed here (key 0 = "no threshold published yet")
+    void (*kern)(const TileArgs) = nullptr;
+    if (mode == TAUV_TOPK_SIGMOID_PEAK) kern = p.vec ? tile_topk_kernel<1, true> : tile_topk_kernel<1, false>;
+    else kern = p.vec ? tile_topk_kernel<0, true> : tile_topk_kernel<0, false>;
+    TAUV_CUDA(ensure_dynamic_smem((const void*)kern, p.smem_bytes));
+    TAUV_CUDA(cudaMemsetAsync(a.cand_count, 0, p.count_bytes + p.state_bytes, st));  // (adjacent in the workspace)
+    kern<<<(unsigned)items, kTileThreads, p.smem_bytes, st>>>(a);
+    TAUV_LAUNCH_CHECK("tile_topk_kernel");
+    return 0;
   }
-  if (const char* e = getenv("TAUV_SD_S")) p->stages = atoi(e) < p->stages ? atoi(e) : p->stages;
-#endif
-  long long G = num_sms();          // one CTA per SM (the ring takes most of the shared memory)
-  const long long min_rows = 8;     // tiny inputs: fewer CTAs rather than CTAs without rows
-  if (G > R / min_rows) G = R / min_rows;
-  if (G < 1) G = 1;
-  p->G = (int)G;
-  const long long per = R / G;      // every CTA owns at least this many rows
-  long long tr = (long long)C * H / per + 2;
-  if (tr > G) tr = G;
-  p->tbl_rows = (int)tr;
-  p->row_cap = 2 * k;  // the survivors of a run: k plus the rest of the bin that holds the k-th (more: exact prune first)
-#ifdef TAUV_DEBUG
-  if (const char* e = getenv("TAUV_SD_ROWCAP")) p->row_cap = atoi(e);
-#endif
-  p->smem_bytes = sd_smem_bytes(p->chunk_rows, p->stages, W, p->sub_cap);
-  p->cand_bytes = align_up((size_t)B * p->tbl_rows * (size_t)p->row_cap * 8, 256);
-  p->count_bytes = align_up((size_t)B * p->tbl_rows * 4, 256);
-  p->ticket_bytes = align_up((size_t)B * 8, 256);
-}
-
-static uint32_t next_epoch() {
-  // Unique per launch within the process, never 0.  (A ticket word left by another launch carries another epoch and
-  // counts as zero; the words of one workspace are only ever written by launches on that workspace.)
-  static std::atomic<uint32_t> ctr{0x9E3779B9u ^ (uint32_t)((uintptr_t)&ctr >> 4)};
-  uint32_t e = ctr.fetch_add(1, std::memory_order_relaxed) + 1;
-  if (e == 0) e = ctr.fetch_add(1, std::memory_order_relaxed) + 1;
-  return e;
-}
-
-static int run_stream(const float* hm, int B, int C, int H, int W, int k, int mode, int64_t* index, int64_t* label,
-                      float* score, const BoxArgs& box, void* ws, size_t ws_bytes, cudaStream_t st) {
-  StreamPlan p;
-  make_stream_plan(B, C, H, W, k, &p);
-  TAUV_REQUIRE(ws != nullptr && (uintptr_t)ws % 256 == 0, TAUV_E_WORKSPACE, "workspace must be 256-byte aligned");
-  TAUV_REQUIRE(ws_bytes >= p.cand_bytes + p.count_bytes + p.ticket_bytes, TAUV_E_WORKSPACE,
-               "workspace %zu < required %zu", ws_bytes, p.cand_bytes + p.count_bytes + p.ticket_bytes);
-  TAUV_REQUIRE(p.smem_bytes <= 227 * 1024, TAUV_E_UNSUPPORTED, "stream kernel needs %zu B shared memory", p.smem_bytes);
-  SdArgs a{};
-  a.hm = hm; a.B = B; a.C = C; a.H = H; a.W = W; a.k = k;
-  a.G = p.G;
-  a.rows_total = (long long)B * C * H;
-  a.rows_frame = C * H;
-  a.chunk_rows = p.chunk_rows; a.stages = p.stages;
+  // vectorised path: persistent clusters of 8 CTAs, one unit (a frame, or a share of a frame's items) at a time
+  void (*ck)(const TileArgs, int, int) = mode == TAUV_TOPK_SIGMOID_PEAK ? tile_cluster_kernel<1> : tile_cluster_kernel<0>;
+  const size_t csmem = (size_t)kClOffList + p.smem_bytes + (size_t)(kBootElems + 2 * W + 8) * 4;
+  TAUV_REQUIRE(csmem <= 227 * 1024, TAUV_E_UNSUPPORTED, "tile needs %zu B shared memory", csmem);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(kClSize);
+  cfg.blockDim = dim3(kTileThreads);
+  cfg.dynamicSmemBytes = csmem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kClSize;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int ncl = 0;  // clusters that are resident at once (the query costs tens of microseconds of host time: cached)
   {
-    const SdLayout l = sd_layout(p.chunk_rows, p.stages, W, p.sub_cap);
-    a.off_list = l.off_list; a.off_bins = l.off_bins; a.off_flags = l.off_flags; a.off_pend = l.off_pend;
-    a.off_bars = l.off_bars; a.off_ctx = l.off_ctx;
-    a.sub_cap = p.sub_cap;
+    // per (mode, device): the largest dynamic shared-memory size the kernel has been opted in to (only ever raised,
+    // under a lock, so concurrent callers cannot lower it under each other), and the last occupancy answer
+    static std::mutex mu;
+    static std::atomic<unsigned long long> max_smem[2][64], occ[2][64];
+    int dev = 0;
+    TAUV_CUDA(cudaGetDevice(&dev));
+    const int m = mode == TAUV_TOPK_SIGMOID_PEAK, d = (dev >= 0 && dev < 64) ? dev : 63;
+    if (max_smem[m][d].load(std::memory_order_acquire) < csmem || dev != d) {
+      std::lock_guard<std::mutex> lock(mu);
+      if (max_smem[m][d].load(std::memory_order_relaxed) < csmem || dev != d) {
+        TAUV_CUDA(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+        if (dev == d) max_smem[m][d].store(csmem, std::memory_order_release);
+      }
+    }
+    const unsigned long long seen = occ[m][d].load(std::memory_order_relaxed);  // (csmem + 1) << 16 | ncl; idempotent
+    if (dev == d && (seen >> 16) == (unsigned long long)csmem + 1) {
+      ncl = (int)(seen & 0xffff);
+    } else {
+      TAUV_CUDA(cudaOccupancyMaxActiveClusters(&ncl, ck, &cfg));
+      occ[m][d].store((((unsigned long long)csmem + 1) << 16) | (unsigned long long)(ncl & 0xffff), std::memory_order_relaxed);
+    }
   }
-  a.tbl_rows = p.tbl_rows; a.row_cap = p.row_cap;
-  unsigned char* w = reinterpret_cast<unsigned char*>(ws);
-  a.cand = reinterpret_cast<unsigned long long*>(w);
-  a.cand_count = reinterpret_cast<int*>(w + p.cand_bytes);
-  a.ticket = reinterpret_cast<unsigned long long*>(w + p.cand_bytes + p.count_bytes);
-  a.epoch = next_epoch();
-  a.out_index = index; a.out_label = label; a.out_score = score;
-  a.box = box;
-  void (*kern)(const SdArgs) = mode == TAUV_TOPK_SIGMOID_PEAK ? stream_decode_kernel<1> : stream_decode_kernel<0>;
-  TAUV_CUDA(ensure_dynamic_smem((const void*)kern, p.smem_bytes));
-  kern<<<(unsigned)p.G, kSdThreads, p.smem_bytes, st>>>(a);
-  TAUV_LAUNCH_CHECK("stream_decode_kernel");
+  TAUV_REQUIRE(ncl >= 1, TAUV_E_UNSUPPORTED, "no cluster of %d CTAs fits the device with %zu B shared memory", kClSize, csmem);
+  // units: whole frames when there are at least as many frames as clusters, otherwise every frame is split into
+  // `parts` contiguous shares of its items (each share keeps its own threshold; the merge kernel joins them)
+  int parts = 1;
+  if (B < ncl) {
+    parts = ncl / B;
+    const int by_items = p.items_per_frame / (2 * kClSize);  // at least two items per CTA
+    if (parts > by_items) parts = by_items;
+    if (parts > 8) parts = 8;  // (every part pays its own bootstrap and adds 8 rows to the merge; 64 CTAs per frame suffice)
+    if (parts < 1) parts = 1;
+  }
+  const long long n_units = (long long)B * parts;
+  const long long ncl_used = n_units < ncl ? n_units : ncl;
+  int p2 = 1;
+  while (p2 < k) p2 <<= 1;
+  if (fo && fused && parts == 1 && k <= kFuseMaxK &&
+      (size_t)kClSize * k * 8 <= (size_t)kRadixBins * 4 + (size_t)(kBootElems + 2 * W + 8) * 4 && !debug_env("TAUV_NO_FUSE")) {
+    a.fuse = 1;
+    a.out_index = fo->index;
+    a.out_label = fo->label;
+    a.out_score = fo->score;
+    a.box = *fo->box;
+    *fused = true;
+  }
+  cfg.gridDim = dim3((unsigned)(ncl_used * kClSize));
+  TAUV_CUDA(cudaLaunchKernelEx(&cfg, ck, a, (int)n_units, parts));
   return 0;
 }
 
@@ -1027,9 +1798,10 @@ static int run_stage2(int B, int C, int H, int W, int k, int mode, int64_t* inde
 
 static int run_topk(const float* hm, int B, int C, int H, int W, int k, int mode, int64_t* index, int64_t* label,
                     float* score, const BoxArgs& box, void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (stream_shape_ok(hm, C, H, W, k) && !debug_env("TAUV_NO_STREAM"))
-    return run_stream(hm, B, C, H, W, k, mode, index, label, score, box, ws, ws_bytes, st);
-  if (int e = run_stage1(hm, B, C, H, W, k, mode, ws, ws_bytes, st)) return e;
+  const FuseOut fo{index, label, score, &box};
+  bool fused = false;
+  if (int e = run_stage1(hm, B, C, H, W, k, mode, ws, ws_bytes, st, &fo, &fused)) return e;
+  if (fused) return 0;
   return run_stage2(B, C, H, W, k, mode, index, label, score, box, ws, ws_bytes, st);
 }
 
@@ -1062,14 +1834,7 @@ extern "C" size_t tauv_heatmap_topk_workspace_bytes(int B, int C, int H, int W, 
   TopkPlan p;
   // alignment only affects the load path, never the sizes
   make_plan(B, C, H, W, k, nullptr, &p);
-  size_t n = p.cand_bytes + p.count_bytes + p.state_bytes;
-  if (W % 4 == 0 && W <= kSdMaxW && k <= kSdMaxK) {  // the streaming path's table + tickets
-    StreamPlan sp;
-    make_stream_plan(B, C, H, W, k, &sp);
-    const size_t m = sp.cand_bytes + sp.count_bytes + sp.ticket_bytes;
-    if (m > n) n = m;
-  }
-  return n;
+  return p.cand_bytes + p.count_bytes + p.state_bytes;
 }
 
 extern "C" int tauv_heatmap_topk(const float* heatmap, int B, int C, int H, int W, int k, int mode, int64_t* index,
