@@ -136,6 +136,26 @@ int tauv_gather_at(const float* src, int64_t sb, int64_t ssel, int64_t sc, int64
                    int64_t sx, int nch, const int64_t* index, const int64_t* label, int B, int k,
                    float* out, tauv_stream_t stream);
 
+/* The greedy keypoint -> object association of decode_keypoints — decode.py:98-135, on the device
+ * (one warp per frame).  Inputs: the ranked objects of tauv_centernet_decode(mode KEYPOINTS)
+ * (label [B,k] i64, yx [B,k,2] f64, count [B] i32) and the ranked keypoint peaks of
+ * tauv_heatmap_topk(SIGMOID_PEAK) on the keypoint heatmap (kp_index [B,kk,2], kp_label [B,kk],
+ * kp_score [B,kk]); affinity: the [B,Kp,2,H,W] head tensor with its five element strides;
+ * kp_map [Kp][2] i32 = object_config.decode_keypoint_index(channel) = (object label, keypoint slot).
+ * Keypoints are taken in rank order until the first with (double)score < keypoint_score_threshold
+ * (the reference compares Python floats, :100-102); each goes to the free candidate with the
+ * smallest |atan2(a_y,a_x) - atan2(k_y-d_y, k_x-d_x)| in doubles, first minimum wins.
+ * Outputs per (frame, object rank, keypoint slot): kp_set [B,k,max_kp] u8, kp_yx [B,k,max_kp,2]
+ * f32 (index / out_h, index / out_w in fp32, :115-118), kp_score_out [B,k,max_kp] f32,
+ * kp_aff_out [B,k,max_kp,2] f32 (a_y, a_x).  k * max_kp <= 4096. */
+int tauv_centernet_keypoint_assoc(const int64_t* label, const double* yx, const int32_t* count,
+                                  int B, int k, const int64_t* kp_index, const int64_t* kp_label,
+                                  const float* kp_score, int kk, const float* affinity,
+                                  const int64_t affinity_strides[5], const int32_t* kp_map, int Kp,
+                                  int max_kp, int out_h, int out_w,
+                                  double keypoint_score_threshold, uint8_t* kp_set, float* kp_yx,
+                                  float* kp_score_out, float* kp_aff_out, tauv_stream_t stream);
+
 /* angle_decode(predicted_bin, predicted_offset, theta_range, bin_overlap) — decode.py:291-316
  * Two-bin angle decode over n rows of 4: softmax-select the bin, centre +- pi/2 plus atan2 of the
  * (sin, cos) offset pair, wrapped to [0, 2*pi) and rescaled by theta_range/(2*pi).

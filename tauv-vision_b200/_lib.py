@@ -7,6 +7,7 @@ infrastructure and is never imported from here.)
 from __future__ import annotations
 
 import ctypes
+import os
 import re
 import threading
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_void_p
@@ -48,6 +49,8 @@ _SIGNATURES = {
                                              c_size_t, c_void_p]),
     "tauv_gather_at": (c_int, [_F, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, _I64, _I64, c_int, c_int, _F,
                                c_void_p]),
+    "tauv_centernet_keypoint_assoc": (c_int, [_I64, _D, _I32, c_int, c_int, _I64, _I64, _F, c_int, _F, _I64, _I32, c_int,
+                                              c_int, c_int, c_int, c_double, _U8, _F, _F, _F, c_void_p]),
     "tauv_angle_decode": (c_int, [_F, _F, c_int64, c_double, _F, c_void_p]),
     "tauv_depth_decode": (c_int, [_F, c_int64, _F, c_void_p]),
     "tauv_gaussian_encode": (c_int, [_U8, _I64, _F, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double,
@@ -100,9 +103,11 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
         if _LIB is not None:
             return _LIB
         path = _build.LIB_PATH
-        if not path.exists():
+        if not _build.is_fresh() and os.environ.get("TAUV_SKIP_BUILD_CHECK") != "1":
+            # a missing library, or one built from other sources / flags than those in the tree (the stamp next to it
+            # records what it was built from): stale kernels must never pass for the current ones
             if not build_if_missing:
-                raise RuntimeError(f"{path} is missing and building was disabled; there is no fallback path")
+                raise RuntimeError(f"{path} is missing or stale and building was disabled; there is no fallback path")
             _build.build()
         lib = ctypes.CDLL(str(path))
         missing = []

@@ -23,7 +23,8 @@ import torch
 
 from ... import _lib
 
-_NP_DTYPE = {torch.int64: np.int64, torch.float64: np.float64, torch.float32: np.float32, torch.int32: np.int32}
+_NP_DTYPE = {torch.int64: np.int64, torch.float64: np.float64, torch.float32: np.float32, torch.int32: np.int32,
+             torch.uint8: np.uint8}
 
 TOPK_RAW = 0
 TOPK_SIGMOID_PEAK = 1
@@ -80,6 +81,7 @@ class PackedDetections:
     hw: torch.Tensor
     depth: Optional[torch.Tensor]
     count: torch.Tensor
+    extra: Optional[dict] = None             # further tensors carved from the same buffer (decode_keypoints)
     _storage: Optional[torch.Tensor] = None  # one uint8 buffer all the tensors above are views of (if allocated here)
     _layout: Optional[tuple] = None          # ((name, dtype, shape, byte offset, bytes), ...)
 
@@ -87,8 +89,9 @@ class PackedDetections:
                ("score", torch.float32, 4, 1), ("hw", torch.float32, 4, 2), ("depth", torch.float32, 4, 1))
 
     @classmethod
-    def allocate(cls, B: int, k: int, with_depth: bool, device) -> "PackedDetections":
-        """All outputs as typed views of ONE device buffer (8-byte fields first), so that ``to_host`` is one copy."""
+    def allocate(cls, B: int, k: int, with_depth: bool, device, extra=()) -> "PackedDetections":
+        """All outputs as typed views of ONE device buffer (8-byte fields first), so that ``to_host`` is one copy.
+        ``extra``: further (name, dtype, shape) tensors to carve from the same buffer (``self.extra[name]``)."""
         layout, off = [], 0
         for name, dtype, isz, per in cls._FIELDS:
             if name == "depth" and not with_depth:
@@ -97,10 +100,16 @@ class PackedDetections:
             off += (B * k * per * isz + 15) // 16 * 16
         layout.append(("count", torch.int32, (B,), off, B * 4))
         off += (B * 4 + 15) // 16 * 16
+        for name, dtype, shape in extra:
+            nb = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+            layout.append((name, dtype, tuple(shape), off, nb))
+            off += (nb + 15) // 16 * 16
         storage = torch.empty((off,), dtype=torch.uint8, device=device)
         views = {name: storage[o:o + nb].view(dtype).view(shape) for name, dtype, shape, o, nb in layout}
-        return cls(views["index"], views["label"], views["score"], views["yx"], views["hw"], views.get("depth"),
-                   views["count"], storage, tuple(layout))
+        out = cls(views["index"], views["label"], views["score"], views["yx"], views["hw"], views.get("depth"),
+                  views["count"], storage, tuple(layout))
+        out.extra = {name: views[name] for name, _, _ in extra}
+        return out
 
     def to_host(self) -> dict:
         """One synchronising device->host transfer of everything."""
@@ -252,93 +261,108 @@ def decode(prediction, model_config, n_detections: int, score_threshold: float) 
 # decode_keypoints
 # ------------------------------------------------------------------------------------------------
 
+def _keypoint_map(object_config, n_channels: int):
+    """(object label, keypoint slot) of every keypoint-heatmap channel, as the reference looks them up one by one
+    (``object_config.decode_keypoint_index``, decode.py:104-106), and the largest keypoint count of any object."""
+    table = np.empty((n_channels, 2), dtype=np.int32)
+    for ch in range(n_channels):
+        try:
+            obj, slot = object_config.decode_keypoint_index(ch)
+        except Exception:  # noqa: BLE001 - a channel no object owns can never be matched
+            obj, slot = -1, -1
+        table[ch] = (int(obj), int(slot))
+    max_kp = max([len(c.keypoints) for c in object_config.configs] + [1])
+    return table, max_kp
+
+
+def decode_keypoints_packed(prediction, model_config, object_config, n_detections: int, keypoint_n_detections: int,
+                            score_threshold: float, keypoint_score_threshold: float):
+    """Device part of ``decode_keypoints``: three launches (objects: peaks + top-k + boxes; keypoints: peaks + top-k;
+    the greedy association, csrc/centernet_keypoints.cu), nothing synchronises.  Returns (PackedDetections whose one
+    storage buffer also holds kp_set / kp_yx / kp_score / kp_aff [B,k,max_kp,...], max_kp)."""
+    dev = _lib.require_cuda(prediction.heatmap, prediction.keypoint_heatmap, prediction.keypoint_affinity,
+                            prediction.size, prediction.depth)
+    lib = _lib.load()
+    hm = _as_heatmap(prediction.heatmap)
+    kp_hm = _as_heatmap(prediction.keypoint_heatmap)
+    B, C, H, W = hm.shape
+    Kp = kp_hm.shape[1]
+    k, kk = int(n_detections), int(keypoint_n_detections)
+    if k > C * H * W or kk > Kp * H * W:
+        raise RuntimeError("selected index k out of range")
+    table, max_kp = _keypoint_map(object_config, Kp)
+    size = prediction.size if prediction.size.dtype == torch.float32 else prediction.size.float()
+    depth = _depth_view(prediction.depth)
+    aff = prediction.keypoint_affinity
+    aff = aff if aff.dtype == torch.float32 else aff.float()
+    out = PackedDetections.allocate(B, k, depth is not None, dev, extra=(
+        ("kp_yx", torch.float32, (B, k, max_kp, 2)), ("kp_score", torch.float32, (B, k, max_kp)),
+        ("kp_aff", torch.float32, (B, k, max_kp, 2)), ("kp_set", torch.uint8, (B, k, max_kp))))
+    x = out.extra
+    with torch.cuda.device(dev):
+        ws = _lib.workspace(dev, max(lib.tauv_heatmap_topk_workspace_bytes(B, C, H, W, k),
+                                     lib.tauv_heatmap_topk_workspace_bytes(B, Kp, H, W, kk)))
+        st = _lib.stream_ptr(dev)
+        _lib.check(lib.tauv_centernet_decode(
+            _lib.fptr(hm), B, C, H, W, k, _lib.fptr(size), _lib.strides_arg(size, 4), None, None,
+            _lib.fptr(depth), _lib.strides_arg(depth, 3) if depth is not None else None,
+            BOX_KEYPOINTS, int(model_config.downsample_ratio), int(model_config.in_h), int(model_config.in_w),
+            float(score_threshold), _lib.i64ptr(out.index), _lib.i64ptr(out.label), _lib.fptr(out.score),
+            _lib.dptr(out.yx), _lib.fptr(out.hw), _lib.fptr(out.depth), _lib.i32ptr(out.count), ws.data_ptr(), ws.numel(), st))
+        kp_index = torch.empty((B, kk, 2), dtype=torch.int64, device=dev)
+        kp_label = torch.empty((B, kk), dtype=torch.int64, device=dev)
+        kp_score = torch.empty((B, kk), dtype=torch.float32, device=dev)
+        _lib.check(lib.tauv_heatmap_topk(_lib.fptr(kp_hm), B, Kp, H, W, kk, TOPK_SIGMOID_PEAK, _lib.i64ptr(kp_index),
+                                         _lib.i64ptr(kp_label), _lib.fptr(kp_score), ws.data_ptr(), ws.numel(), st))
+        d_table = torch.from_numpy(table).to(dev, non_blocking=True)
+        _lib.check(lib.tauv_centernet_keypoint_assoc(
+            _lib.i64ptr(out.label), _lib.dptr(out.yx), _lib.i32ptr(out.count), B, k, _lib.i64ptr(kp_index),
+            _lib.i64ptr(kp_label), _lib.fptr(kp_score), kk, _lib.fptr(aff), _lib.strides_arg(aff, 5),
+            _lib.i32ptr(d_table), Kp, max_kp, int(model_config.out_h), int(model_config.out_w),
+            float(keypoint_score_threshold), _lib.u8ptr(x["kp_set"]), _lib.fptr(x["kp_yx"]), _lib.fptr(x["kp_score"]),
+            _lib.fptr(x["kp_aff"]), st))
+    return out, max_kp
+
+
 def decode_keypoints(prediction, model_config, object_config, M_projection: np.ndarray,
                      n_detections: int, keypoint_n_detections: int,
                      score_threshold: float, keypoint_score_threshold: float,
                      keypoint_angle_threshold: float) -> List[List[KeypointDetection]]:
     """Reference signature (decode.py:51-176).
 
-    Device: both fused peak/top-k passes, the object box gather and the affinity gather.
-    Host (as in the reference, on <= n_detections x keypoint_n_detections scalars): the greedy
-    keypoint->object association and the optional PnP tail.  ``keypoint_angle_threshold`` is
-    accepted and unused, exactly like the reference.
+    Device: both fused peak/top-k passes, the object box gather and the greedy keypoint->object association
+    (``decode_keypoints_packed``); ONE device->host copy of the packed result.  Host: building the
+    ``KeypointDetection`` records and the optional PnP tail (``cv2.solvePnP``, host-side in the reference too).
+    ``keypoint_angle_threshold`` is accepted and unused, exactly like the reference.
     """
-    dev = _lib.require_cuda(prediction.heatmap, prediction.keypoint_heatmap, prediction.keypoint_affinity,
-                            prediction.size, prediction.depth)
-    lib = _lib.load()
-    hm = _as_heatmap(prediction.heatmap)
-    B, C, H, W = hm.shape
-    k = int(n_detections)
-    kk = int(keypoint_n_detections)
-    index, label, score = _topk(hm, k, TOPK_SIGMOID_PEAK)
-    kp_hm = _as_heatmap(prediction.keypoint_heatmap)
-    kp_index, kp_label, kp_score = _topk(kp_hm, kk, TOPK_SIGMOID_PEAK)
-
-    size = prediction.size if prediction.size.dtype == torch.float32 else prediction.size.float()
-    depth = _depth_view(prediction.depth)
-    yx = torch.empty((B, k, 2), dtype=torch.float64, device=dev)
-    hw = torch.empty((B, k, 2), dtype=torch.float32, device=dev)
-    depth_out = torch.empty((B, k), dtype=torch.float32, device=dev) if depth is not None else None
-    count = torch.empty((B,), dtype=torch.int32, device=dev)
-    aff = prediction.keypoint_affinity
-    aff = aff if aff.dtype == torch.float32 else aff.float()
-    kp_aff = torch.empty((B, kk, 2), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        _lib.check(lib.tauv_centernet_boxes(
-            _lib.i64ptr(index), _lib.fptr(score), B, k, H, W,
-            _lib.fptr(size), _lib.strides_arg(size, 4), None, None,
-            _lib.fptr(depth), _lib.strides_arg(depth, 3) if depth is not None else None,
-            BOX_KEYPOINTS, int(model_config.downsample_ratio), int(model_config.in_h), int(model_config.in_w),
-            int(model_config.out_h), int(model_config.out_w), float(score_threshold),
-            _lib.dptr(yx), _lib.fptr(hw), _lib.fptr(depth_out), _lib.i32ptr(count), _lib.stream_ptr(dev)))
-        sb, sk, sc, sy, sx = aff.stride()
-        _lib.check(lib.tauv_gather_at(_lib.fptr(aff), sb, sk, sc, sy, sx, 2, _lib.i64ptr(kp_index),
-                                      _lib.i64ptr(kp_label), B, kk, _lib.fptr(kp_aff), _lib.stream_ptr(dev)))
-
-    # one synchronising transfer of everything the host loop needs
-    h_label, h_score, h_yx, h_hw = label.cpu().numpy(), score.cpu().numpy(), yx.cpu().numpy(), hw.cpu().numpy()
-    h_count = count.cpu().numpy()
-    h_depth = depth_out.cpu().numpy() if depth_out is not None else None
-    h_kp_index, h_kp_label = kp_index.cpu().numpy(), kp_label.cpu().numpy()
-    h_kp_score, h_kp_aff = kp_score.cpu().numpy(), kp_aff.cpu().numpy()
-    kp_thr = np.float32(keypoint_score_threshold)
-    out_h, out_w = np.float32(model_config.out_h), np.float32(model_config.out_w)
-
+    packed, max_kp = decode_keypoints_packed(prediction, model_config, object_config, n_detections,
+                                             keypoint_n_detections, score_threshold, keypoint_score_threshold)
+    h = packed.to_host()
     detections = []
-    for b in range(B):
+    for b in range(h["label"].shape[0]):
         sample = []
-        for i in range(int(h_count[b])):
-            lab = int(h_label[b, i])
+        last_match, last_rank = None, -1
+        for i in range(int(h["count"][b])):
+            lab = int(h["label"][b, i])
             n_kp = len(object_config.configs[lab].keypoints)
-            sample.append(KeypointDetection(
-                label=lab, score=float(h_score[b, i]),
-                y=float(h_yx[b, i, 0]), x=float(h_yx[b, i, 1]),
-                h=float(h_hw[b, i, 0]), w=float(h_hw[b, i, 1]),
-                depth=float(h_depth[b, i]) if h_depth is not None else None,
+            d = KeypointDetection(
+                label=lab, score=float(h["score"][b, i]),
+                y=float(h["yx"][b, i, 0]), x=float(h["yx"][b, i, 1]),
+                h=float(h["hw"][b, i, 0]), w=float(h["hw"][b, i, 1]),
+                depth=float(h["depth"][b, i]) if h["depth"] is not None else None,
                 keypoints=[None] * n_kp, keypoint_scores=[None] * n_kp, keypoint_affinities=[None] * n_kp,
-                cam_t_object=None))
-
-        match_detection = None
-        for j in range(kk):
-            if h_kp_score[b, j] < kp_thr:  # decode.py:99-100 (fp32 compare)
-                break
-            kp_score_f = float(h_kp_score[b, j])
-            kl = int(h_kp_label[b, j])
-            obj_i, obj_kp_i = object_config.decode_keypoint_index(kl)
-            cands = [d for d in sample if d.label == obj_i and d.keypoints[obj_kp_i] is None]
-            if not cands:
-                continue
-            ky = float(np.float32(h_kp_index[b, j, 0]) / out_h)  # int64 tensor / int -> fp32 divide
-            kx = float(np.float32(h_kp_index[b, j, 1]) / out_w)
-            ay, ax = float(h_kp_aff[b, j, 0]), float(h_kp_aff[b, j, 1])
-            ang = atan2(ay, ax)
-            errs = [abs(ang - atan2(ky - d.y, kx - d.x)) for d in cands]
-            match_detection = cands[errs.index(min(errs))]
-            match_detection.keypoints[obj_kp_i] = (ky, kx)
-            match_detection.keypoint_affinities[obj_kp_i] = (ay, ax)
-            match_detection.keypoint_scores[obj_kp_i] = kp_score_f
-
-        _pnp_tail(sample, match_detection, model_config, object_config, M_projection)
+                cam_t_object=None)
+            for j in range(min(n_kp, max_kp)):
+                if h["kp_set"][b, i, j]:
+                    d.keypoints[j] = (float(h["kp_yx"][b, i, j, 0]), float(h["kp_yx"][b, i, j, 1]))
+                    d.keypoint_affinities[j] = (float(h["kp_aff"][b, i, j, 0]), float(h["kp_aff"][b, i, j, 1]))
+                    d.keypoint_scores[j] = float(h["kp_score"][b, i, j])
+                    # the reference's PnP tail writes to the LAST matched detection (its stale `match_detection`,
+                    # decode.py:172): keypoints are matched in descending score, so that is the lowest matched score
+                    if last_match is None or h["kp_score"][b, i, j] < last_rank:
+                        last_match, last_rank = d, h["kp_score"][b, i, j]
+            sample.append(d)
+        _pnp_tail(sample, last_match, model_config, object_config, M_projection)
         detections.append(sample)
     return detections
 

@@ -168,6 +168,33 @@ def main():
          offset=offset.contiguous(), depth=depth.contiguous(), rows=np.array(flat, np.float64),
          counts=np.array([len(f) for f in kd]))
 
+    # ---- decode_keypoints, keypoint threshold boundary: a keypoint whose score is exactly float32(0.7) with
+    # keypoint_score_threshold = 0.7.  The reference compares Python floats (decode.py:100-102):
+    # float(float32(0.7)) = 0.699999988... < 0.7, so the loop stops AT that keypoint (an fp32 compare would keep it).
+    x_star = None
+    for cand in np.nextafter(np.float32(0.8472978), np.float32(1.0)) + np.arange(-40, 40) * np.float32(5.9604645e-08):
+        if torch.sigmoid(torch.tensor(np.float32(cand))).item() == float(np.float32(0.7)):
+            x_star = float(np.float32(cand))
+            break
+    assert x_star is not None
+    kp_logits2 = synth.separated_logits(2, 6, 32, 32, seed=45, lo=-6.0, hi=x_star + 9.5e-4)
+    flat0 = kp_logits2[0].reshape(-1)
+    order = torch.argsort(flat0, descending=True)
+    flat0[order[10]] = x_star  # the 11th best keypoint peak of frame 0 (its neighbours in rank are 0.5e-4 away)
+    kd2 = ref_decode.decode_keypoints(prediction(logits, size, offset, depth, kp_logits2, kp_aff), mck, oc,
+                                      np.eye(3), 6, 20, 0.8, 0.7, 0.3)
+    flat2 = []
+    for b, frame in enumerate(kd2):
+        for i, d in enumerate(frame):
+            row = [b, i, d.label, d.score, d.y, d.x, d.h, d.w, d.depth]
+            for j in range(3):
+                kp = d.keypoints[j]
+                row += [1.0, kp[0], kp[1], d.keypoint_scores[j], d.keypoint_affinities[j][0],
+                        d.keypoint_affinities[j][1]] if kp is not None else [0.0] * 6
+            flat2.append(row)
+    save("cn_decode_keypoints_thr", kp_logits=kp_logits2, rows=np.array(flat2, np.float64),
+         counts=np.array([len(f) for f in kd2]), x_star=np.float32(x_star))
+
     # ---- angle_decode / depth_decode -------------------------------------------------------------------
     g = synth.gen(51)
     pb, po = torch.randn((2, 9, 4), generator=g), torch.randn((2, 9, 4), generator=g)

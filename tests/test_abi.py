@@ -30,6 +30,17 @@ def test_exports_every_header_symbol(lib):
         assert getattr(lib, n) is not None
 
 
+def test_exports_nothing_the_header_does_not_declare():
+    """The default build has no debug hooks and no undeclared entry points (they exist only with -DTAUV_DEBUG)."""
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_build.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line and line.split()[-1].startswith("tauv_")}
+    assert exported, "nm found no tauv_ symbols"
+    assert exported == set(_lib.header_symbols()), sorted(exported ^ set(_lib.header_symbols()))
+    strings = subprocess.run(["strings", str(_build.LIB_PATH)], capture_output=True, text=True).stdout
+    for knob in ("TAUV_NO_FUSE", "TAUV_MASK_SIMT", "TAUV_SCORES_OLD", "TAUV_MASK_NO_TMA"):
+        assert knob not in strings, f"the default library still reads {knob} from the environment"
+
+
 def test_version_and_error_text(lib):
     assert lib.tauv_version() == 100
     assert isinstance(lib.tauv_last_error(), bytes)
@@ -69,6 +80,11 @@ def test_no_cpu_fallback():
         D.heatmap_nms(torch.zeros((1, 1, 4, 4)), 3)
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
         Bx.iou_matrix(torch.zeros((1, 1, 4)), torch.zeros((1, 1, 4)))
+    # the three pure layout helpers have no kernel behind them and work wherever the tensor lives: the reference's data
+    # loader, collate and plots call them on CPU tensors (segmentation_dataset.py:119, yolact/scripts/train.py:143-145)
+    b = torch.tensor([[[0.5, 0.4, 0.2, 0.1]]])
+    assert torch.equal(Bx.box_xy_swap(b), torch.tensor([[[0.4, 0.5, 0.1, 0.2]]]))
+    assert torch.allclose(Bx.corners_to_box(Bx.box_to_corners(b)), b)
 
 
 def test_product_never_imports_the_oracle():

@@ -157,6 +157,48 @@ def test_decode_keypoints_golden(cn):
     assert_close(np.array(rows), g["rows"], what="KeypointDetection fields")
 
 
+def test_decode_keypoints_threshold_is_a_double_compare(cn):
+    """decode.py:100-102 compares Python floats: a keypoint whose score is exactly float32(0.7) is BELOW a threshold of
+    0.7 (0.699999988 < 0.7) and ends the loop; an fp32 compare would keep it.  Golden from the real reference."""
+    g0, g = golden("cn_decode_keypoints"), golden("cn_decode_keypoints_thr")
+    mc = synth.centernet_model_config(128, 128, 2)
+    kps = lambda i: [(0.1 * j, 0.0, 0.05 * i) for j in range(3)]
+    oc = SimpleNamespace(configs=[SimpleNamespace(keypoints=kps(0)), SimpleNamespace(keypoints=kps(1))],
+                         decode_keypoint_index=lambda k: (int(k) // 3, int(k) % 3))
+    kp_logits = t(g["kp_logits"])
+    assert float(torch.sigmoid(torch.tensor(float(g["x_star"]), dtype=torch.float32))) == float(np.float32(0.7))
+    p = pred(t(g0["logits"]).to(cn.dev), nhwc_view(g0["size"], cn.dev), nhwc_view(g0["offset"], cn.dev),
+             nhwc_view(g0["depth"], cn.dev), kp_logits.to(cn.dev), t(g0["kp_aff"]).to(cn.dev))
+    out = cn.D.decode_keypoints(p, mc, oc, np.eye(3), 6, 20, 0.8, 0.7, 0.3)
+    assert [len(f) for f in out] == g["counts"].tolist()
+    rows = []
+    for b, frame in enumerate(out):
+        for i, d in enumerate(frame):
+            row = [b, i, d.label, d.score, d.y, d.x, d.h, d.w, d.depth]
+            for j in range(3):
+                kp = d.keypoints[j]
+                row += [1.0, kp[0], kp[1], d.keypoint_scores[j], d.keypoint_affinities[j][0],
+                        d.keypoint_affinities[j][1]] if kp is not None else [0.0] * 6
+            rows.append(row)
+    assert_close(np.array(rows), g["rows"], what="KeypointDetection fields at the threshold boundary")
+
+
+def test_decode_keypoints_is_one_transfer(cn):
+    """The packed result (objects + associated keypoints) lives in ONE device buffer: one device->host copy."""
+    g = golden("cn_decode_keypoints")
+    mc = synth.centernet_model_config(128, 128, 2)
+    oc = SimpleNamespace(configs=[SimpleNamespace(keypoints=[0] * 3), SimpleNamespace(keypoints=[0] * 3)],
+                         decode_keypoint_index=lambda k: (int(k) // 3, int(k) % 3))
+    p = pred(t(g["logits"]).to(cn.dev), nhwc_view(g["size"], cn.dev), nhwc_view(g["offset"], cn.dev),
+             nhwc_view(g["depth"], cn.dev), t(g["kp_logits"]).to(cn.dev), t(g["kp_aff"]).to(cn.dev))
+    packed, max_kp = cn.D.decode_keypoints_packed(p, mc, oc, 6, 20, 0.8, 0.8)
+    assert max_kp == 3 and packed._storage is not None
+    lo, hi = packed._storage.data_ptr(), packed._storage.data_ptr() + packed._storage.numel()
+    for x in (packed.index, packed.label, packed.score, packed.yx, packed.hw, packed.depth, packed.count,
+              *packed.extra.values()):
+        assert lo <= x.data_ptr() < hi
+
+
 # ---- oracle comparisons on seeded inputs --------------------------------------------------------------------
 
 @pytest.mark.parametrize("B,C,H,W,k", [(2, 3, 13, 11, 17), (1, 1, 1, 5, 3), (3, 2, 40, 36, 64), (2, 5, 64, 128, 100),

@@ -7,6 +7,8 @@ import textwrap
 import types
 
 import numpy as np
+from pathlib import Path
+
 import pytest
 import torch
 
@@ -182,3 +184,32 @@ def test_patched_signatures_match_reference_positional_order():
         # anything beyond the reference's parameters must be optional
         extra = list(inspect.signature(fn).parameters.values())[len(names):]
         assert all(p.default is not inspect.Parameter.empty for p in extra), fn.__name__
+
+
+REFERENCE_SRC = Path("/root/reference/src")
+
+
+@pytest.mark.skipif(not REFERENCE_SRC.exists(), reason="the reference tree only exists in the build container")
+def test_patch_reference_on_the_real_tree_keeps_cpu_callers_working(monkeypatch):
+    """patch_reference() against the unmodified reference: the layout helpers it re-binds are called on CPU tensors by
+    the reference's own data path (datasets/segmentation_dataset/segmentation_dataset.py:119, utils/plot.py:49,65,
+    yolact/scripts/train.py:143-145) and must keep working there; the kernels-backed functions refuse CPU tensors."""
+    import importlib
+    import sys
+    import torch
+    monkeypatch.syspath_prepend(str(REFERENCE_SRC))
+    for name in [m for m in sys.modules if m == "tauv_vision" or m.startswith("tauv_vision.")]:
+        monkeypatch.delitem(sys.modules, name)
+    ref_boxes = importlib.import_module("tauv_vision.yolact.model.boxes")
+    original = ref_boxes.box_to_corners
+    box = torch.tensor([[[0.5, 0.4, 0.2, 0.1], [0.25, 0.75, 0.5, 0.5]]])
+    want_corners, want_swap = ref_boxes.box_to_corners(box), ref_boxes.box_xy_swap(box)
+    with patch_reference(modules=["tauv_vision.yolact.model.boxes", "tauv_vision.yolact.model.nms"]) as handle:
+        assert not handle.skipped
+        assert ref_boxes.box_to_corners is not original
+        assert torch.equal(ref_boxes.box_to_corners(box), want_corners)      # CPU in, CPU out, same numbers
+        assert torch.equal(ref_boxes.box_xy_swap(box), want_swap)
+        assert torch.equal(ref_boxes.corners_to_box(ref_boxes.box_to_corners(box)), ref_boxes.corners_to_box(want_corners))
+        with pytest.raises(RuntimeError, match="CUDA"):
+            ref_boxes.iou_matrix(box, box)                                    # a kernel: no CPU path
+    assert ref_boxes.box_to_corners is original
