@@ -106,10 +106,9 @@ class PackedDetections:
             off += (nb + 15) // 16 * 16
         storage = torch.empty((off,), dtype=torch.uint8, device=device)
         views = {name: storage[o:o + nb].view(dtype).view(shape) for name, dtype, shape, o, nb in layout}
-        out = cls(views["index"], views["label"], views["score"], views["yx"], views["hw"], views.get("depth"),
-                  views["count"], storage, tuple(layout))
-        out.extra = {name: views[name] for name, _, _ in extra}
-        return out
+        return cls(index=views["index"], label=views["label"], score=views["score"], yx=views["yx"], hw=views["hw"],
+                   depth=views.get("depth"), count=views["count"], extra={name: views[name] for name, _, _ in extra},
+                   _storage=storage, _layout=tuple(layout))
 
     def to_host(self) -> dict:
         """One synchronising device->host transfer of everything."""
