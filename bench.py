@@ -1,22 +1,34 @@
 #!/usr/bin/env python
 """bench.py — decoded frames/s of the detection-head hot path on N B200s, one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload centernet|mixed]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): CenterNet decode + Gaussian target encode of a batch of 64 synthetic
-512x512 frames per GPU (stride 4 -> 80 classes x 128x128 heatmaps, top-100, 16 objects per frame).
-One step = decode (1 kernel) + encode (1 kernel) over the batch.  Frames are independent, so N GPUs each
-take their own 64 frames (weak scaling, no collective on the data path; NCCL only carries the timing scalar).
+Workloads
+  centernet (default; BASELINE.json configs[1], the line's `value`): CenterNet decode + Gaussian target encode of a
+      batch of 64 synthetic 512x512 frames per GPU (stride 4 -> 80 classes x 128x128 heatmaps, top-100, 16 objects per
+      frame).  One step = decode (1 kernel) + encode (1 kernel).  Weak scaling: every GPU takes its own 64 frames, no
+      collective on the data path (NCCL only carries the timing scalars).  In the same run, on every rank, the YOLACT
+      post-process kernels of configs[2] (B = 64, 19 248 priors, 81 classes, top_k 200, 32 prototypes 276x276) are
+      timed as well and reported under `kernels` with their algorithmic bytes.
+  mixed (configs[3]): 256 frames, each with a CenterNet head and a YOLACT head, sharded over the N GPUs
+      (`shard.frame_range`, strong scaling).  One step = CenterNet decode + YOLACT detect + fused mask/depth consumer of
+      the rank's frames; `e2e` additionally copies the packed results to the host and gathers them on rank 0 in frame
+      order (`shard.gather_host`) inside the timed region — the "final host gather" of SURVEY.md section 8e.
 
-value     : frames/s with inputs resident in HBM, CUDA events around exactly K steps, max over ranks.
-e2e       : the same step through the public Python API with pinned HOST inputs copied in and the packed
-            detections + a target checksum copied out inside the timed region, double-buffered over two streams
-            (the H2D copy of step i+1 overlaps step i's kernels and D2H); PCIe-bound: 352 MB in per step.
-roofline  : the dominant kernel (tile_cluster_kernel: the whole decode, reads the 335.5 MB of logits once), timed
-            live with events around its launch, against MEASURED_PEAKS.json.
-cpu_baseline / --impl reference : the CPU oracle port (oracle/ref_port.py, torch-CPU with all host threads)
-            on a bounded sample of the same workload.
+value     : frames/s with inputs resident in HBM; the K-step block is timed `--blocks` (>= 5) times with CUDA events on
+            the launching stream and the MEDIAN block is reported (`block_ms` lists them all); max over ranks.
+e2e       : the same step through the public Python API with pinned HOST inputs copied in (ONE staging buffer per
+            step and direction) and the packed results copied out inside the timed region, double-buffered over two
+            streams; PCIe-bound.  Each rank pins itself and its staging memory to its GPU's NUMA node; the per-rank
+            host->device rate is reported (`h2d_gbs_per_rank`).
+roofline  : the dominant kernel (tile_cluster_kernel: the whole decode, reads the 335.5 MB of logits once), timed live
+            with events around its launch inside the timed steps, against MEASURED_PEAKS.json.  In the steps the decode
+            runs right after the target encode, whose dirty L2 lines are written back while it streams
+            (profiles/r2_stream_bench_v*.txt); `us_per_launch_isolated` is the same launch timed back to back with itself.
+cpu_baseline / --impl reference : the CPU oracle port (oracle/ref_port.py, torch-CPU with all host threads) on the
+            FULL 64-frame batch per step.  (It times the tensor part of decode without the reference's per-detection
+            Python loop, decode.py:204-234, which flatters the CPU.)
 """
 from __future__ import annotations
 
@@ -36,16 +48,21 @@ import torch  # noqa: E402
 
 B_PER_GPU, C, H, W, K_DET, N_OBJ = 64, 80, 128, 128, 100, 16
 IN_HW, DOWNSAMPLES, SIGMA, THR = 512, 2, 2.0, 0.3
+YL_N, YL_C1, YL_P, YL_HP, YL_TOPK, YL_IOU, YL_CONF = 19248, 81, 32, 276, 200, 0.5, 0.05
+CAM_H, CAM_W = 720, 1280
+MIXED_FRAMES = 256
 METRIC, UNIT = "decoded_frames_per_sec", "frames/s"
 WORKLOAD = "centernet_decode_topk100+gaussian_target_encode, batch 64 x [80,128,128] per GPU (BASELINE configs[1], stride 4)"
+WORKLOAD_MIXED = ("mixed CenterNet (80x128x128, top-100) + YOLACT (19248 priors, 81 classes, top_k 200, 32 protos 276x276, "
+                  "depth 720x1280) head decode, 256 frames sharded over the GPUs (BASELINE configs[3])")
 
 
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return float(d["hbm_gbs"]), "measured"
-    return 6650.0, "fallback"
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))), "measured"
+    return 6650.0, 1400.0, "fallback"
 
 
 def algorithmic_bytes_decode(B):
@@ -55,6 +72,21 @@ def algorithmic_bytes_decode(B):
 
 def algorithmic_bytes_encode(B):
     return 4 * B * C * H * W
+
+
+def algorithmic_bytes_yolact_detect(B, n_keep_total):
+    # class logits once + box encodings + anchors once per batch + kept indices
+    return B * (4 * YL_N * YL_C1 + 16 * YL_N) + 16 * YL_N + 8 * n_keep_total
+
+
+def algorithmic_bytes_mask(B, n_keep_total):
+    # prototypes once + per kept mask: coefficients, box, the fp32 mask itself
+    return B * 4 * YL_P * YL_HP * YL_HP + n_keep_total * (YL_P * 4 + 16 + 4 * YL_HP * YL_HP)
+
+
+def algorithmic_bytes_mask_depth(B, n_keep_total):
+    # prototypes once + the mono16 depth image once + per kept mask: coefficients, box, (mean, count)
+    return B * (4 * YL_P * YL_HP * YL_HP + 2 * CAM_H * CAM_W) + n_keep_total * (YL_P * 4 + 16 + 16)
 
 
 class ClockSampler:
@@ -115,20 +147,76 @@ class ClockSampler:
                 "samples": len(s)}
 
 
-def make_inputs(device, seed):
-    """Synthetic head tensors generated on the device (N(-2.2,1.5) logits = the reference's heatmap bias init)."""
+def pin_to_gpu_numa_node(device_index: int):
+    """Pin this process (and, by first touch, the pinned staging memory it allocates afterwards) to the cores of the
+    GPU's NUMA node.  Returns (node, n_cores) or (None, n_cores) when the topology cannot be read."""
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = Path(f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node")
+        node = int(path.read_text().strip())
+        if node < 0:
+            return None, len(os.sched_getaffinity(0))
+        cpus = Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip()
+        cores = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            cores.update(range(int(lo), int(hi or lo) + 1))
+        cores &= os.sched_getaffinity(0)
+        if cores:
+            os.sched_setaffinity(0, cores)
+        return node, len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        return None, len(os.sched_getaffinity(0))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# synthetic inputs
+# ---------------------------------------------------------------------------------------------------------------------
+def make_inputs(device, seed, B=B_PER_GPU):
+    """Synthetic CenterNet head tensors generated on the device (N(-2.2,1.5) logits = the reference's heatmap bias init)."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    logits = torch.randn((B_PER_GPU, C, H, W), device=device, generator=g) * 1.5 - 2.2
-    size = (torch.rand((B_PER_GPU, 2, H, W), device=device, generator=g) * 0.3).permute(0, 2, 3, 1)
-    offset = (torch.rand((B_PER_GPU, 2, H, W), device=device, generator=g) * 4).permute(0, 2, 3, 1)
-    truth = SimpleNamespace(valid=torch.rand((B_PER_GPU, N_OBJ), device=device, generator=g) < 0.75,
-                            label=torch.randint(0, C, (B_PER_GPU, N_OBJ), device=device, generator=g),
-                            center=torch.rand((B_PER_GPU, N_OBJ, 2), device=device, generator=g))
+    logits = torch.randn((B, C, H, W), device=device, generator=g) * 1.5 - 2.2
+    size = (torch.rand((B, 2, H, W), device=device, generator=g) * 0.3).permute(0, 2, 3, 1)
+    offset = (torch.rand((B, 2, H, W), device=device, generator=g) * 4).permute(0, 2, 3, 1)
+    truth = SimpleNamespace(valid=torch.rand((B, N_OBJ), device=device, generator=g) < 0.75,
+                            label=torch.randint(0, C, (B, N_OBJ), device=device, generator=g),
+                            center=torch.rand((B, N_OBJ, 2), device=device, generator=g))
     return logits, size, offset, truth
 
 
-def cpu_reference_sample(n_frames: int, reps: int):
+def make_yolact_inputs(device, seed, B):
+    """Synthetic YOLACT head tensors (configs[2]): N(0,2) class logits with a background bias and ~150 planted confident
+    priors per frame in overlapping clusters (so NMS keeps ~100-160), N(0,0.3) box encodings, tanh coefficients,
+    leaky-relu prototypes, mono16 depth with 20 % holes; anchors from get_anchor at 550x550."""
+    from tauv_vision_b200.yolact.model import anchors
+    from tests import synth
+    cfg = synth.yolact_config()
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    anchor = anchors.all_anchors(synth.fpn_sizes(550, 550), cfg, device)
+    cls = torch.randn((B, YL_N, YL_C1), device=device, generator=g) * 2
+    cls[:, :, 0] += 4
+    idx = torch.randint(0, YL_N - 16, (B, 12), device=device, generator=g)
+    rows = torch.arange(B, device=device)
+    for j in range(12):
+        for o in range(12):
+            cls[rows, idx[:, j] + o, 1 + (j % (YL_C1 - 1))] += 10 + torch.rand((B,), device=device, generator=g) * 4
+    enc = torch.randn((B, YL_N, 4), device=device, generator=g) * 0.3
+    coeff = torch.tanh(torch.randn((B, YL_N, YL_P), device=device, generator=g))
+    proto = torch.nn.functional.leaky_relu(torch.randn((B, YL_P, YL_HP, YL_HP), device=device, generator=g))
+    depth = torch.randint(300, 9000, (B, CAM_H, CAM_W), device=device, dtype=torch.int32, generator=g)
+    holes = torch.rand((B, CAM_H, CAM_W), device=device, generator=g) < 0.2
+    depth = torch.where(holes, torch.zeros((), dtype=torch.int32, device=device), depth).to(torch.uint16)
+    return SimpleNamespace(cfg=cfg, anchor=anchor, cls=cls, enc=enc, coeff=coeff, proto=proto, depth=depth)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the CPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(n_frames: int, reps: int, warmup: int = 1):
     """The oracle port on the host cores: decode + encode of n_frames frames, `reps` times; returns frames/s."""
     from oracle import ref_port as O
     torch.set_num_threads(os.cpu_count() or 1)
@@ -144,7 +232,42 @@ def cpu_reference_sample(n_frames: int, reps: int):
         O.decode_packed(logits, size, offset, None, 2 ** DOWNSAMPLES, IN_HW, IN_HW, K_DET, THR, canonical=False)
         O.generate_heatmap(valid, label, center, C, H, W, IN_HW, IN_HW, 2 ** DOWNSAMPLES, SIGMA)
 
-    step()  # warm-up
+    for _ in range(max(1, warmup)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    dt = time.perf_counter() - t0
+    return n_frames * reps / dt, dt / reps
+
+
+def cpu_reference_mixed(n_frames: int, reps: int):
+    """The oracle port of one mixed step on a bounded sample of frames: CenterNet decode of the sample + per frame
+    box_decode -> nms -> assemble_mask -> nearest resize -> masked depth mean (yolact_node.py:127-135,178)."""
+    from oracle import ref_port as O
+    from tests import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(2)
+    logits = torch.randn((n_frames, C, H, W), generator=g) * 1.5 - 2.2
+    size = (torch.rand((n_frames, 2, H, W), generator=g) * 0.3).permute(0, 2, 3, 1)
+    offset = (torch.rand((n_frames, 2, H, W), generator=g) * 4).permute(0, 2, 3, 1)
+    cfg = synth.yolact_config()
+    anchor = torch.cat([O.get_anchor(i, s, cfg.anchor_scales, cfg.anchor_aspect_ratios, cfg.in_h, cfg.in_w)
+                        for i, s in enumerate(synth.fpn_sizes(550, 550))], dim=1)
+    cls, enc = synth.yolact_heads(n_frames, YL_N, YL_C1, seed=5, anchor=anchor)
+    coeff = torch.tanh(torch.randn((n_frames, YL_N, YL_P), generator=g))
+    proto = torch.nn.functional.leaky_relu(torch.randn((n_frames, YL_P, YL_HP, YL_HP), generator=g))
+    depth = torch.stack([synth.depth_image(CAM_H, CAM_W, seed=7 + i) for i in range(n_frames)])
+
+    def step():
+        O.decode_packed(logits, size, offset, None, 2 ** DOWNSAMPLES, IN_HW, IN_HW, K_DET, THR, canonical=False)
+        for b in range(n_frames):
+            box = O.box_decode(enc[b:b + 1], anchor, cfg.box_variances)
+            keep = O.nms(cls[b:b + 1], box, YL_TOPK, YL_IOU, YL_CONF)
+            if keep.numel():
+                O.masked_depth_mean(proto[b], coeff[b, keep], box[0, keep], depth[b])
+
+    step()
     t0 = time.perf_counter()
     for _ in range(reps):
         step()
@@ -154,38 +277,74 @@ def cpu_reference_sample(n_frames: int, reps: int):
 
 def run_reference(args, rank):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference is pure
-    Python/torch and cannot travel to the GPU box) on the host cores.  Rank 0 only."""
+    Python/torch and cannot travel to the GPU box) on the host cores, on the FULL batch per step.  Rank 0 only."""
     if rank != 0:
         return
-    # bounded sample: 8 frames per step (~0.2 s on 8 cores; per-frame cost matches the 64-frame batch), fewer if
-    # the requested number of steps would otherwise run for many minutes
-    n_frames = 8 if args.steps <= 400 else 2
-    fps, per_step = cpu_reference_sample(n_frames, max(1, args.steps))
+    if args.workload == "mixed":
+        n_frames, steps = 4, max(1, min(args.steps, 3))  # (a 256-frame step would take minutes on the CPU)
+        fps, per_step = cpu_reference_mixed(n_frames, steps)
+        sample = (f"{n_frames} of the 256 frames x {steps} steps (CenterNet decode + per-frame box_decode/nms/"
+                  "assemble_mask/masked depth mean), torch-CPU oracle port")
+        workload = WORKLOAD_MIXED
+    else:
+        n_frames, steps = B_PER_GPU, max(1, args.steps)
+        fps, per_step = cpu_reference_sample(n_frames, steps, warmup=max(1, min(args.warmup, 3)))
+        sample = (f"{n_frames} frames x {steps} steps of decode+encode (the full batch), torch-CPU oracle port; the "
+                  "decode leg is the tensor part only (no per-detection Python loop), which flatters the CPU")
+        workload = WORKLOAD
     cores = torch.get_num_threads()
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.workload == "mixed" else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{n_frames} frames per step"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n_frames} frames x {max(1, args.steps)} steps of decode+encode, torch-CPU oracle port"},
+        "config": {"workload": workload, "frames_per_step": n_frames},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------------------------------
+def median(xs):
+    s = sorted(xs)
+    return s[len(s) // 2]
+
+
+def time_kernel(fn, reps=7, warmup=3):
+    """Median device time (us) of fn() over `reps` launches, CUDA events on the current stream.  The YOLACT inputs are
+    several times larger than the 126 MB L2, so every launch streams from HBM."""
+    for _ in range(warmup):
+        r = fn()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    return median(ts), r
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--blocks", type=int, default=5, help="the K-step block is timed this many times; the median is reported")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="centernet", choices=["centernet", "mixed"])
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-yolact", action="store_true", help="skip the configs[2] kernel timings")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    args.blocks = max(5, args.blocks)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -199,6 +358,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
+    numa_node, n_cores = pin_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -207,174 +367,362 @@ def main():
         dist = dist_mod
 
     import tauv_vision_b200 as tv
-    from tauv_vision_b200.centernet.model import decode as D
-    from tauv_vision_b200.centernet.model import loss as L
     lib = tv.load_library()
     assert lib.tauv_check_device() == 0, lib.tauv_last_error()
-
-    mc = SimpleNamespace(in_h=IN_HW, in_w=IN_HW, downsample_ratio=2 ** DOWNSAMPLES, out_h=H, out_w=W)
-    tc = SimpleNamespace(keypoint_heatmap_sigma=SIGMA)
-    oc = SimpleNamespace(n_labels=C)
-    logits, size, offset, truth = make_inputs(device, 1234 + rank)
-    pred = SimpleNamespace(heatmap=logits, size=size, offset=offset, depth=None)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    K = args.steps
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    ctx = SimpleNamespace(args=args, rank=rank, local_rank=local_rank, world=world, device=device, dist=dist,
+                          barrier=barrier, numa_node=numa_node, n_cores=n_cores)
+    if args.workload == "mixed":
+        run_mixed(ctx)
+    else:
+        run_centernet(ctx)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# configs[1] (+ configs[2] kernels)
+# ---------------------------------------------------------------------------------------------------------------------
+def run_centernet(ctx):
+    from tauv_vision_b200.centernet.model import decode as D
+    from tauv_vision_b200.centernet.model import loss as L
+    args, device, dist, world, rank = ctx.args, ctx.device, ctx.dist, ctx.world, ctx.rank
+    mc = SimpleNamespace(in_h=IN_HW, in_w=IN_HW, downsample_ratio=2 ** DOWNSAMPLES, out_h=H, out_w=W)
+    tc = SimpleNamespace(keypoint_heatmap_sigma=SIGMA)
+    oc = SimpleNamespace(n_labels=C)
+    logits, size, offset, truth = make_inputs(device, 1234 + rank)
+    pred = SimpleNamespace(heatmap=logits, size=size, offset=offset, depth=None)
+    K, NB = args.steps, args.blocks
 
     # outputs are allocated once and overwritten every step (a real pipeline re-uses its buffers too); the truth
-    # tensors are already in the dtypes / layout the encoder takes, so a step is three kernel launches and nothing else
+    # tensors are already in the dtypes / layout the encoder takes, so a step is two kernel launches and nothing else
     det_buf = D.decode_packed(pred, mc, K_DET, THR)
     tgt_buf = torch.empty((B_PER_GPU, C, H, W), dtype=torch.float32, device=device)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K * NB)]
 
     def step(events=None):
         if events is None:
             det = D.decode_packed(pred, mc, K_DET, THR, out=det_buf)
-            tgt = L.generate_heatmap(truth, mc, tc, oc, out=tgt_buf)
+            L.generate_heatmap(truth, mc, tc, oc, out=tgt_buf)
         else:
             events[0].record()
             det = D.decode_packed(pred, mc, K_DET, THR, out=det_buf)
             events[1].record()
-            tgt = L.generate_heatmap(truth, mc, tc, oc, out=tgt_buf)
+            L.generate_heatmap(truth, mc, tc, oc, out=tgt_buf)
             events[2].record()
-        return det, tgt
+        return det
 
     for _ in range(args.warmup):
         step()
-    barrier()
-    with ClockSampler(local_rank) as clocks:
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        start.record()
-        for i in range(K):
-            det, tgt = step(ev[i])
-        end.record()
-        barrier()
-    total_ms = start.elapsed_time(end)
-    t_dec = sum(e[0].elapsed_time(e[1]) for e in ev) / K
-    t_enc = sum(e[1].elapsed_time(e[2]) for e in ev) / K
-    n_keep_mean = float(det.count.float().mean())
+    ctx.barrier()
+    block_ms = []
+    with ClockSampler(ctx.local_rank) as clocks:
+        for blk in range(NB):
+            ctx.barrier()
+            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record()
+            for i in range(K):
+                det = step(ev[blk * K + i])
+            end.record()
+            ctx.barrier()
+            block_ms.append(start.elapsed_time(end))
+    t_dec = sum(e[0].elapsed_time(e[1]) for e in ev) / len(ev)
+    t_enc = sum(e[1].elapsed_time(e[2]) for e in ev) / len(ev)
+    n_det_mean = float(det.count.float().mean())
 
-    # ---- e2e: pinned host inputs in, packed detections + target checksum out, every step ----
-    h_logits = logits.cpu().pin_memory()
-    h_size = size.permute(0, 3, 1, 2).contiguous().cpu().pin_memory()      # NCHW storage as the model emits it
-    h_offset = offset.permute(0, 3, 1, 2).contiguous().cpu().pin_memory()
-    h_valid, h_label, h_center = (truth.valid.cpu().pin_memory(), truth.label.cpu().pin_memory(),
-                                  truth.center.cpu().pin_memory())
-    # Two device buffer sets and two streams: the H2D copy of step i+1 runs while step i computes and its results go
-    # back (double buffering).  Every step still copies its own inputs in and its own results out, and the host reads
-    # step i's results (detections + target checksum) from pinned memory before it launches step i+2.
-    h2d = sum(t.numel() * t.element_size() for t in (h_logits, h_size, h_offset, h_valid, h_label, h_center))
+    # the decode back to back with itself (the launch before it only reads: no dirty L2 lines to write back)
+    for _ in range(3):
+        D.decode_packed(pred, mc, K_DET, THR, out=det_buf)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(K):
+        D.decode_packed(pred, mc, K_DET, THR, out=det_buf)
+    e1.record()
+    torch.cuda.synchronize()
+    t_dec_iso = e0.elapsed_time(e1) / K
+
+    # ---- configs[2]: the YOLACT post-process kernels, same run, every rank ----
+    yl = None
+    if not args.no_yolact:
+        yl = time_yolact(device, 4321 + rank)
+
+    # ---- e2e: pinned host inputs in (one staging buffer), packed detections + target checksum out, every step ----
+    e2e = e2e_centernet(ctx, logits, size, offset, truth, mc, tc, oc)
+
+    # ---- max over ranks ----
+    vals = [median(block_ms), e2e["ms"], t_dec, t_enc, t_dec_iso] + block_ms
+    if yl is not None:
+        vals += [yl["detect_us"], yl["mask_us"], yl["mask_depth_us"], yl["scores_us"]]
+    times = torch.tensor(vals, device=device, dtype=torch.float64)
+    h2d_rate = torch.tensor([e2e["h2d_gbs"]], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(h2d_rate, op=dist.ReduceOp.MIN)
+    vals = times.tolist()
+    med_ms, e2e_ms, t_dec, t_enc, t_dec_iso = vals[:5]
+    block_ms = vals[5:5 + NB]
+    if rank != 0:
+        return
+    hbm_gbs, tf_peak, peak_src = peaks()
+    frames = B_PER_GPU * world
+    value = frames * K / (med_ms * 1e-3)
+    e2e_value = frames * args.e2e_steps / (e2e_ms * 1e-3)
+    achieved = algorithmic_bytes_decode(B_PER_GPU) / (t_dec * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        traffic = json.loads(tp.read_text()).get("tile_cluster_kernel_bytes_per_launch")
+    kernels = {
+        "decode_us": t_dec * 1e3, "decode_isolated_us": t_dec_iso * 1e3,
+        "gaussian_encode_us": t_enc * 1e3,
+        "gaussian_encode_gbs": algorithmic_bytes_encode(B_PER_GPU) / (t_enc * 1e-3) / 1e9,
+        "gaussian_encode_frac": algorithmic_bytes_encode(B_PER_GPU) / (t_enc * 1e-3) / 1e9 / hbm_gbs,
+    }
+    launches = 2 * K * NB + K + 3
+    if yl is not None:
+        det_us, mask_us, md_us, sc_us = vals[5 + NB:5 + NB + 4]
+        nk = yl["n_keep_total"]
+        kernels.update({
+            "yolact_config": f"BASELINE configs[2]: B={B_PER_GPU}, {YL_N} priors, {YL_C1} classes, top_k {YL_TOPK}, "
+                             f"{YL_P} protos {YL_HP}x{YL_HP}, depth {CAM_H}x{CAM_W}; mean n_keep {nk / B_PER_GPU:.1f}",
+            "yolact_scores_us": sc_us,
+            "yolact_scores_frac": B_PER_GPU * 4 * YL_N * YL_C1 / (sc_us * 1e-6) / 1e9 / hbm_gbs,
+            "yolact_detect_us": det_us,
+            "yolact_detect_bytes": algorithmic_bytes_yolact_detect(B_PER_GPU, nk),
+            "yolact_detect_frac": algorithmic_bytes_yolact_detect(B_PER_GPU, nk) / (det_us * 1e-6) / 1e9 / hbm_gbs,
+            "mask_us": mask_us,
+            "mask_bytes": algorithmic_bytes_mask(B_PER_GPU, nk),
+            "mask_hbm_frac": algorithmic_bytes_mask(B_PER_GPU, nk) / (mask_us * 1e-6) / 1e9 / hbm_gbs,
+            "mask_tflops_useful": 2.0 * nk * YL_P * YL_HP * YL_HP / (mask_us * 1e-6) / 1e12,
+            "mask_tensor_pct": 100.0 * (2.0 * nk * YL_P * YL_HP * YL_HP / (mask_us * 1e-6) / 1e12) / tf_peak,
+            "mask_depth_us": md_us,
+            "mask_depth_bytes": algorithmic_bytes_mask_depth(B_PER_GPU, nk),
+            "mask_depth_hbm_frac": algorithmic_bytes_mask_depth(B_PER_GPU, nk) / (md_us * 1e-6) / 1e9 / hbm_gbs,
+            "yolact_frames_per_s_detect_plus_mask_depth": B_PER_GPU / ((det_us + md_us) * 1e-6),
+        })
+        launches += yl["launches"]
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:  # (the CPU leg is reported at N = 1 only)
+        fps, per = cpu_reference_sample(B_PER_GPU, 5)
+        cpu = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{B_PER_GPU} frames x 5 reps of decode+encode ({per:.2f} s per batch), torch-CPU oracle port "
+                         "(tensor part of decode only: no per-detection Python loop, which flatters the CPU)"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": med_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_gpu": B_PER_GPU, "global_batch": frames,
+                   "l2": "inputs larger than L2 (335.5 MB logits + 335.5 MB targets per step vs 126 MB L2)",
+                   "timing": f"median of {NB} blocks of {K} steps (CUDA events, max over ranks)",
+                   "mean_detections_per_frame": n_det_mean},
+        "block_ms": block_ms,
+        "roofline": {"bound": "hbm", "kernel": "tile_cluster_kernel<SIGMOID_PEAK> (whole decode: peaks, top-k, boxes)",
+                     "achieved": achieved, "peak": hbm_gbs, "peak_source": peak_src, "unit": "GB/s",
+                     "frac": achieved / hbm_gbs, "traffic": traffic,
+                     "algorithmic_bytes": algorithmic_bytes_decode(B_PER_GPU), "us_per_launch": t_dec * 1e3,
+                     "us_per_launch_isolated": t_dec_iso * 1e3,
+                     "frac_isolated": algorithmic_bytes_decode(B_PER_GPU) / (t_dec_iso * 1e-3) / 1e9 / hbm_gbs,
+                     "note": "in the steps the decode follows the target encode and streams while that kernel's dirty "
+                             "L2 lines (up to 126 MB) are written back; isolated = back to back with itself"},
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps,
+                "h2d_gbs_per_rank_min": float(h2d_rate[0]), "copies_per_step": "1 H2D + 2 D2H",
+                "numa_node": ctx.numa_node, "host_cores_pinned": ctx.n_cores},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def time_yolact(device, seed, B=B_PER_GPU):
+    from tauv_vision_b200.yolact.model import masks, nms
+    y = make_yolact_inputs(device, seed, B)
+    out = torch.empty((B, YL_TOPK, YL_HP, YL_HP), dtype=torch.float32, device=device)
+    lib = __import__("tauv_vision_b200").load_library()
+    ws_d = torch.empty(lib.tauv_yolact_mask_depth_workspace_bytes(B, YL_HP, YL_HP, YL_TOPK), dtype=torch.uint8, device=device)
+    sc_us, _ = time_kernel(lambda: nms.max_foreground_confidence(y.cls))
+    det_us, det = time_kernel(lambda: nms.detect(y.cls, y.enc, y.anchor, y.cfg, YL_TOPK, YL_IOU, YL_CONF))
+    mask_us, _ = time_kernel(lambda: masks.assemble_mask_batched(y.proto, y.coeff, det, out=out), reps=5, warmup=2)
+    md_us, _ = time_kernel(lambda: masks.masked_depth_mean_batched(y.proto, y.coeff, det, y.depth, workspace=ws_d), reps=5, warmup=2)
+    nk = int(det.n_keep.sum().item())
+    del out
+    return {"scores_us": sc_us, "detect_us": det_us, "mask_us": mask_us, "mask_depth_us": md_us, "n_keep_total": nk,
+            "launches": 10 * 1 + 10 * 3 + 7 * 1 + 7 * 3}
+
+
+def e2e_centernet(ctx, logits, size, offset, truth, mc, tc, oc):
+    """The step through the public API from pinned host memory: every step copies its inputs in as ONE staging buffer
+    and its results out (the packed detections: one buffer; the target checksum: 4 bytes), double-buffered over a copy
+    and a compute stream (the H2D of step i+1 overlaps step i).  Returns ms for args.e2e_steps steps on the device
+    clock, the bytes per step and the host->device rate this rank reached."""
+    from tauv_vision_b200.centernet.model import decode as D
+    from tauv_vision_b200.centernet.model import loss as L
+    args, device = ctx.args, ctx.device
+    # one host staging buffer: [logits | size (NCHW) | offset (NCHW) | center | label | valid], 256-byte aligned parts
+    parts = [("logits", logits), ("size", size.permute(0, 3, 1, 2).contiguous()),
+             ("offset", offset.permute(0, 3, 1, 2).contiguous()), ("center", truth.center), ("label", truth.label),
+             ("valid", truth.valid)]
+    layout, off = [], 0
+    for name, tns in parts:
+        nb = tns.numel() * tns.element_size()
+        layout.append((name, tns.dtype, tuple(tns.shape), off, nb))
+        off += (nb + 255) // 256 * 256
+    h_stage = torch.empty((off,), dtype=torch.uint8).pin_memory()
+    for (name, dtype, shape, o, nb), (_, tns) in zip(layout, parts):
+        h_stage[o:o + nb].view(dtype).view(shape).copy_(tns.cpu())
+    h2d = sum(nb for *_, nb in layout)
     copy_stream, comp_stream = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
     sets = []
     for _ in range(2):
-        d = SimpleNamespace(
-            logits=torch.empty_like(logits), size=torch.empty_like(h_size, device=device),
-            offset=torch.empty_like(h_offset, device=device),
-            truth=SimpleNamespace(valid=torch.empty_like(truth.valid), label=torch.empty_like(truth.label),
-                                  center=torch.empty_like(truth.center)),
-            det=None, tgt=torch.empty((B_PER_GPU, C, H, W), dtype=torch.float32, device=device),
-            host=None, h_chk=torch.empty((), dtype=torch.float32).pin_memory(),
-            copied=torch.cuda.Event(), done=torch.cuda.Event())
-        sets.append(d)
+        d_stage = torch.empty((off,), dtype=torch.uint8, device=device)
+        v = {name: d_stage[o:o + nb].view(dtype).view(shape) for name, dtype, shape, o, nb in layout}
+        sets.append(SimpleNamespace(
+            stage=d_stage, v=v, det=None, tgt=torch.empty((B_PER_GPU, C, H, W), dtype=torch.float32, device=device),
+            h_det=None, h_chk=torch.empty((), dtype=torch.float32).pin_memory(),
+            copied=torch.cuda.Event(enable_timing=True), copy_start=torch.cuda.Event(enable_timing=True),
+            done=torch.cuda.Event()))
     d2h = 0
 
-    def e2e_launch(d):
+    def launch(d):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(d.done)   # the previous user of this buffer set has finished
-            d.logits.copy_(h_logits, non_blocking=True)
-            d.size.copy_(h_size, non_blocking=True)
-            d.offset.copy_(h_offset, non_blocking=True)
-            d.truth.valid.copy_(h_valid, non_blocking=True)
-            d.truth.label.copy_(h_label, non_blocking=True)
-            d.truth.center.copy_(h_center, non_blocking=True)
+            d.copy_start.record(copy_stream)
+            d.stage.copy_(h_stage, non_blocking=True)
             d.copied.record(copy_stream)
         with torch.cuda.stream(comp_stream):
             comp_stream.wait_event(d.copied)
-            p = SimpleNamespace(heatmap=d.logits, size=d.size.permute(0, 2, 3, 1), offset=d.offset.permute(0, 2, 3, 1),
-                                depth=None)
+            p = SimpleNamespace(heatmap=d.v["logits"], size=d.v["size"].permute(0, 2, 3, 1),
+                                offset=d.v["offset"].permute(0, 2, 3, 1), depth=None)
+            tr = SimpleNamespace(valid=d.v["valid"], label=d.v["label"], center=d.v["center"])
             d.det = D.decode_packed(p, mc, K_DET, THR, out=d.det)
-            L.generate_heatmap(d.truth, mc, tc, oc, out=d.tgt)
-            if d.host is None:
-                d.host = {k: torch.empty(getattr(d.det, k).shape, dtype=getattr(d.det, k).dtype).pin_memory()
-                          for k in ("index", "label", "score", "yx", "hw", "count")}
-            for k, hbuf in d.host.items():
-                hbuf.copy_(getattr(d.det, k), non_blocking=True)      # D2H of the packed detections
-            d.h_chk.copy_(d.tgt.sum(), non_blocking=True)            # D2H of the encode's result scalar
+            L.generate_heatmap(tr, mc, tc, oc, out=d.tgt)
+            if d.h_det is None:
+                d.h_det = torch.empty(d.det._storage.shape, dtype=torch.uint8).pin_memory()
+            d.h_det.copy_(d.det._storage, non_blocking=True)     # D2H of the packed detections (one buffer)
+            d.h_chk.copy_(d.tgt.sum(), non_blocking=True)        # D2H of the encode's result scalar
             d.done.record(comp_stream)
 
-    def e2e_read(d):
+    def read(d):
         nonlocal d2h
         d.done.synchronize()
-        d2h = sum(v.numel() * v.element_size() for v in d.host.values()) + 4
-        return int(d.host["count"].sum()), float(d.h_chk)
+        d2h = d.h_det.numel() + 4
+        return int(d.h_det[-16:].sum()), float(d.h_chk)
 
-    def e2e_run(n):
+    def run(n):
         for i in range(n):
-            e2e_launch(sets[i & 1])
+            launch(sets[i & 1])
             if i >= 1:
-                e2e_read(sets[(i - 1) & 1])
-        return e2e_read(sets[(n - 1) & 1])
+                read(sets[(i - 1) & 1])
+        return read(sets[(n - 1) & 1])
 
-    e2e_run(4)
-    barrier()
+    run(4)
+    ctx.barrier()
     es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     es.record(copy_stream)
-    e2e_run(args.e2e_steps)
+    run(args.e2e_steps)
     ee.record(comp_stream)
-    barrier()
-    e2e_ms = es.elapsed_time(ee)  # device clock from before the first H2D to after the last D2H
+    ctx.barrier()
+    ms = es.elapsed_time(ee)  # device clock from before the first H2D to after the last D2H
+    copy_ms = min(s.copy_start.elapsed_time(s.copied) for s in sets)
+    return {"ms": ms, "h2d": h2d, "d2h": d2h, "h2d_gbs": h2d / (copy_ms * 1e-3) / 1e9}
 
-    # ---- max over ranks ----
-    times = torch.tensor([total_ms, e2e_ms, t_dec, t_enc], device=device, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, t_dec, t_enc = times.tolist()
 
+# ---------------------------------------------------------------------------------------------------------------------
+# configs[3]: mixed CenterNet + YOLACT, 256 frames sharded over the GPUs
+# ---------------------------------------------------------------------------------------------------------------------
+def run_mixed(ctx):
+    from tauv_vision_b200 import shard
+    from tauv_vision_b200.centernet.model import decode as D
+    from tauv_vision_b200.yolact.model import masks, nms
+    args, device, dist, world, rank = ctx.args, ctx.device, ctx.dist, ctx.world, ctx.rank
+    lo, hi = shard.frame_range(rank, world, MIXED_FRAMES)
+    nf = hi - lo
+    mc = SimpleNamespace(in_h=IN_HW, in_w=IN_HW, downsample_ratio=2 ** DOWNSAMPLES, out_h=H, out_w=W)
+    logits, size, offset, _ = make_inputs(device, 1000 + lo, B=nf)
+    pred = SimpleNamespace(heatmap=logits, size=size, offset=offset, depth=None)
+    y = make_yolact_inputs(device, 2000 + lo, nf)
+    lib = __import__("tauv_vision_b200").load_library()
+    ws_d = torch.empty(lib.tauv_yolact_mask_depth_workspace_bytes(nf, YL_HP, YL_HP, YL_TOPK), dtype=torch.uint8, device=device)
+    det_buf = D.decode_packed(pred, mc, K_DET, THR)
+    K, NB = args.steps, args.blocks
+
+    def step():
+        cn = D.decode_packed(pred, mc, K_DET, THR, out=det_buf)
+        yd = nms.detect(y.cls, y.enc, y.anchor, y.cfg, YL_TOPK, YL_IOU, YL_CONF)
+        mean, cnt = masks.masked_depth_mean_batched(y.proto, y.coeff, yd, y.depth, workspace=ws_d)
+        return cn, yd, mean, cnt
+
+    for _ in range(args.warmup):
+        out = step()
+    ctx.barrier()
+    block_ms = []
+    with ClockSampler(ctx.local_rank) as clocks:
+        for _ in range(NB):
+            ctx.barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(K):
+                out = step()
+            e.record()
+            ctx.barrier()
+            block_ms.append(s.elapsed_time(e))
+
+    # e2e: the same step + device->host copies of the packed results + the host gather on rank 0, in frame order
+    def e2e_step():
+        cn, yd, mean, cnt = step()
+        local = cn.to_host()                                   # one D2H of the CenterNet detections (synchronises)
+        local.update({"yl_keep": yd.keep.cpu().numpy(), "yl_n_keep": yd.n_keep.cpu().numpy(),
+                      "yl_box": yd.box.cpu().numpy(), "yl_score": yd.score.cpu().numpy(),
+                      "yl_class": yd.class_id.cpu().numpy(), "yl_depth_mean": mean.cpu().numpy()})
+        return shard.gather_host(local), sum(v.nbytes for v in local.values() if v is not None)
+
+    e2e_step()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        gathered, d2h = e2e_step()
+    ctx.barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
     if rank == 0:
-        hbm_gbs, peak_src = peaks()
-        frames = B_PER_GPU * world
-        value = frames * K / (total_ms * 1e-3)
-        e2e_value = frames * args.e2e_steps / (e2e_ms * 1e-3)
-        achieved = algorithmic_bytes_decode(B_PER_GPU) / (t_dec * 1e-3) / 1e9
-        traffic = None
-        tp = ROOT / "profiles" / "traffic.json"
-        if tp.exists():
-            traffic = json.loads(tp.read_text()).get("tile_cluster_kernel_bytes_per_launch")
-        cpu = None
-        if not args.no_cpu_baseline and world == 1:  # (the CPU leg is reported at N = 1 only)
-            fps, per = cpu_reference_sample(B_PER_GPU, 5)
-            cpu = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": f"{B_PER_GPU} frames x 5 reps of decode+encode ({per:.2f} s per batch), torch-CPU oracle port"}
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": B_PER_GPU, "global_batch": frames,
-                       "l2": "inputs larger than L2 (335.5 MB logits + 335.5 MB targets per step vs 126 MB L2)",
-                       "mean_detections_per_frame": n_keep_mean},
-            "roofline": {"bound": "hbm", "kernel": "tile_cluster_kernel<SIGMOID_PEAK> (whole decode: peaks, top-k, boxes)",
-                         "achieved": achieved, "peak": hbm_gbs, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": achieved / hbm_gbs, "traffic": traffic,
-                         "algorithmic_bytes": algorithmic_bytes_decode(B_PER_GPU), "us_per_launch": t_dec * 1e3},
-            "kernels": {
-                "decode_us": t_dec * 1e3, "gaussian_encode_us": t_enc * 1e3,
-                "gaussian_encode_gbs": algorithmic_bytes_encode(B_PER_GPU) / (t_enc * 1e-3) / 1e9,
-                "gaussian_encode_frac": algorithmic_bytes_encode(B_PER_GPU) / (t_enc * 1e-3) / 1e9 / hbm_gbs,
-            },
-            "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps},
-            "gpu_launches": 2 * K,
-            "clocks": clocks.summary(),
-        }
-        print(json.dumps(line), flush=True)
+        assert gathered["label"].shape[0] == MIXED_FRAMES and gathered["yl_keep"].shape[0] == MIXED_FRAMES, \
+            "the host gather must return all 256 frames in frame order"
+
+    vals = torch.tensor([median(block_ms), e2e_ms] + block_ms, device=device, dtype=torch.float64)
     if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    vals = vals.tolist()
+    if rank != 0:
+        return
+    med_ms, e2e_ms = vals[:2]
+    nk = float(out[1].n_keep.float().mean())
+    line = {
+        "metric": METRIC, "value": MIXED_FRAMES * K / (med_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": args.warmup, "ms_per_step": med_ms / K, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_MIXED, "frames_total": MIXED_FRAMES, "frames_per_gpu": nf,
+                   "l2": "inputs larger than L2 (per GPU at N = 8: 168 MB logits + 200 MB class logits + 312 MB prototypes)",
+                   "timing": f"median of {NB} blocks of {K} steps (CUDA events, max over ranks)",
+                   "mean_n_keep_rank0": nk},
+        "block_ms": vals[2:],
+        "cpu_baseline": None,
+        "e2e": {"value": MIXED_FRAMES * args.e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps,
+                "note": "inputs resident (the heads are produced on the owning GPU); every step copies the packed "
+                        "CenterNet + YOLACT results to the host and gathers them on rank 0 in frame order "
+                        "(shard.gather_host) inside the timed region, wall clock between barriers"},
+        "gpu_launches": (1 + 3 + 3) * K * NB,
+        "clocks": clocks.summary(),
+    }
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
