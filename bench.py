@@ -459,7 +459,7 @@ def run_centernet(ctx):
     # ---- max over ranks ----
     vals = [median(block_ms), e2e["ms"], t_dec, t_enc, t_dec_iso] + block_ms
     if yl is not None:
-        vals += [yl["detect_us"], yl["mask_us"], yl["mask_depth_us"], yl["scores_us"]]
+        vals += [yl["detect_us"], yl["mask_us"], yl["mask_depth_us"], yl["scores_us"], yl["match_us"]]
     times = torch.tensor(vals, device=device, dtype=torch.float64)
     h2d_rate = torch.tensor([e2e["h2d_gbs"]], device=device, dtype=torch.float64)
     if dist is not None:
@@ -487,7 +487,7 @@ def run_centernet(ctx):
     }
     launches = 2 * K * NB + K + 3
     if yl is not None:
-        det_us, mask_us, md_us, sc_us = vals[5 + NB:5 + NB + 4]
+        det_us, mask_us, md_us, sc_us, match_us = vals[5 + NB:5 + NB + 5]
         nk = yl["n_keep_total"]
         kernels.update({
             "yolact_config": f"BASELINE configs[2]: B={B_PER_GPU}, {YL_N} priors, {YL_C1} classes, top_k {YL_TOPK}, "
@@ -506,6 +506,9 @@ def run_centernet(ctx):
             "mask_depth_bytes": algorithmic_bytes_mask_depth(B_PER_GPU, nk),
             "mask_depth_hbm_frac": algorithmic_bytes_mask_depth(B_PER_GPU, nk) / (md_us * 1e-6) / 1e9 / hbm_gbs,
             "yolact_frames_per_s_detect_plus_mask_depth": B_PER_GPU / ((det_us + md_us) * 1e-6),
+            "match_anchors_us": match_us,
+            "match_anchors_bytes": 16 * YL_N + 16 * B_PER_GPU * 16 + B_PER_GPU * YL_N * 30,
+            "match_anchors_frac": (16 * YL_N + 16 * B_PER_GPU * 16 + B_PER_GPU * YL_N * 30) / (match_us * 1e-6) / 1e9 / hbm_gbs,
         })
         launches += yl["launches"]
     cpu = None
@@ -555,8 +558,23 @@ def time_yolact(device, seed, B=B_PER_GPU):
     md_us, _ = time_kernel(lambda: masks.masked_depth_mean_batched(y.proto, y.coeff, det, y.depth, workspace=ws_d), reps=5, warmup=2)
     nk = int(det.n_keep.sum().item())
     del out
+    # anchor matching (training-side target encode, loss.py:16-22,62-66): 16 truths per frame.  Its outputs (37 MB) fit in
+    # L2, so a large READ between the launches evicts them without leaving dirty lines behind (a memset would)
+    from tauv_vision_b200.yolact.model import loss as yl_loss
+    from tests import synth
+    tb, tvd = synth.truth_boxes(B, 16, seed=1)
+    tb, tvd = tb.to(device), tvd.to(device)
+    ts = []
+    for _ in range(7):
+        y.proto.sum()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        yl_loss.match_anchors(y.anchor, tb, tvd, y.cfg)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
     return {"scores_us": sc_us, "detect_us": det_us, "mask_us": mask_us, "mask_depth_us": md_us, "n_keep_total": nk,
-            "launches": 10 * 1 + 10 * 3 + 7 * 1 + 7 * 3}
+            "match_us": median(ts[2:]), "launches": 10 * 1 + 10 * 3 + 7 * 1 + 7 * 3 + 7}
 
 
 def e2e_centernet(ctx, logits, size, offset, truth, mc, tc, oc):

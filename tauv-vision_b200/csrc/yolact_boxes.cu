@@ -71,6 +71,7 @@ __global__ void box_to_mask_kernel(const float* __restrict__ box, int H, int W, 
 }
 
 // loss.py:16-22 + :62-66.  One thread per (frame, prior); the frame's M truths sit in shared memory.
+constexpr int kMatchTiles = 1;  // (measured: 4 tiles per CTA — truths staged once per 1024 priors — is slower, 34.8 -> 40.9 us: the kernel wants CTAs in flight, not fewer prologues)
 __global__ void __launch_bounds__(256) match_anchors_kernel(
     const float4* __restrict__ anchor, const float4* __restrict__ truth_box, const uint8_t* __restrict__ truth_valid,
     int N, int M, float pos_thr, float neg_thr, float v0, float v1, int64_t* __restrict__ match_index,
@@ -88,36 +89,77 @@ __global__ void __launch_bounds__(256) match_anchors_kernel(
     s[7] = 0.0f;
   }
   __syncthreads();
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  const float4 av = anchor[n];
+  // (every CTA takes kMatchTiles tiles of 256 priors of its frame: the truths are staged once per CTA, and 64 frames x
+  // 19 CTAs are one wave on 148 SMs)
+#pragma unroll 1
+  for (int tile = 0; tile < kMatchTiles; ++tile) {
+  const int n = (blockIdx.x * kMatchTiles + tile) * blockDim.x + threadIdx.x;
+  if ((n & ~31) >= N) break;    // (warp-uniform: the whole warp is past the end)
+  const bool in_range = n < N;  // (no early return for single lanes: the warp votes below)
+  const float4 av = anchor[in_range ? n : N - 1];
   const Corners ca = to_corners(av);
   const bool a_ok = fabsf(ca.y0 + ca.x0 + ca.y1 + ca.x1 + ca.area) <= 3.0e38f;
+  // ---- cull per warp before computing.  A warp holds 32 consecutive priors — neighbours on one row of one FPN level —
+  // so their hull is small and most truths miss it altogether.  Lane m tests truth m against the hull: if the hull's
+  // intersection height or width with the truth is <= 0 then so is every lane's (rounded subtraction is monotone in
+  // both operands), the unions of all lanes are positive and finite (checked with the smallest and largest prior
+  // area), and every (prior, truth) pair of the warp is the exact zero the per-pair fast path would produce.  Only the
+  // truths that survive — typically one or two of 16 — are looped over; a truth or a prior with a NaN / infinite
+  // coordinate is never culled.
+  const int lane = threadIdx.x & 31;
+  float hy0 = ca.y0, hx0 = ca.x0, hy1 = ca.y1, hx1 = ca.x1, amin = ca.area, amax = ca.area;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    hy0 = fminf(hy0, __shfl_xor_sync(0xffffffffu, hy0, o));
+    hx0 = fminf(hx0, __shfl_xor_sync(0xffffffffu, hx0, o));
+    hy1 = fmaxf(hy1, __shfl_xor_sync(0xffffffffu, hy1, o));
+    hx1 = fmaxf(hx1, __shfl_xor_sync(0xffffffffu, hx1, o));
+    amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, o));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  }
+  const bool warp_ok = __all_sync(0xffffffffu, a_ok);
   float best = 0.f;
   int best_m = 0;
-  for (int m = 0; m < M; ++m) {
-    const float4 s0 = *reinterpret_cast<const float4*>(s_truth + 8 * m);      // y0 x0 y1 x1
-    const float4 s1 = *reinterpret_cast<const float4*>(s_truth + 8 * m + 4);  // area valid ok -
-    float v;
-    // Most (prior, truth) pairs do not overlap: the intersection is exactly 0 and, with a positive finite union, so is
-    // the IoU (0/u = +0, times valid = +0) — no NaN-propagating min/max, no IEEE divide.  Everything else takes the
-    // reference arithmetic.
-    const float ih = __fsub_rn(fminf(ca.y1, s0.z), fmaxf(ca.y0, s0.x));
-    const float iw = __fsub_rn(fminf(ca.x1, s0.w), fmaxf(ca.x0, s0.y));
-    const float uni0 = __fadd_rn(ca.area, s1.x);
-    if (a_ok && s1.z != 0.0f && (ih <= 0.0f || iw <= 0.0f) && uni0 > 0.0f && uni0 <= 3.0e38f) {
-      v = 0.0f;
-    } else {
-      Corners cb;
-      cb.y0 = s0.x; cb.x0 = s0.y; cb.y1 = s0.z; cb.x1 = s0.w; cb.area = s1.x;
-      v = __fmul_rn(iou_pair(ca, cb), s1.y);  // iou * truth_valid.float()
+  for (int m0 = 0; m0 < M; m0 += 32) {
+    bool cand = false;
+    if (m0 + lane < M) {
+      const float4 s0 = *reinterpret_cast<const float4*>(s_truth + 8 * (m0 + lane));      // y0 x0 y1 x1
+      const float4 s1 = *reinterpret_cast<const float4*>(s_truth + 8 * (m0 + lane) + 4);  // area valid ok -
+      const float ih = __fsub_rn(fminf(hy1, s0.z), fmaxf(hy0, s0.x));
+      const float iw = __fsub_rn(fminf(hx1, s0.w), fmaxf(hx0, s0.y));
+      const float ulo = __fadd_rn(amin, s1.x), uhi = __fadd_rn(amax, s1.x);
+      const bool culled = warp_ok && s1.z != 0.0f && (ih <= 0.0f || iw <= 0.0f) && ulo > 0.0f && uhi <= 3.0e38f;
+      cand = !culled;
     }
-    // torch.max(dim): first maximum wins; a NaN wins over everything that came before it
-    if (m == 0 || v > best || (v != v && best == best)) {
-      best = v;
-      best_m = m;
+    unsigned todo = __ballot_sync(0xffffffffu, cand);
+    while (todo) {
+      const int m = m0 + __ffs(todo) - 1;
+      todo &= todo - 1;
+      const float4 s0 = *reinterpret_cast<const float4*>(s_truth + 8 * m);      // y0 x0 y1 x1
+      const float4 s1 = *reinterpret_cast<const float4*>(s_truth + 8 * m + 4);  // area valid ok -
+      float v;
+      // Most remaining (prior, truth) pairs do not overlap either: the intersection is exactly 0 and, with a positive
+      // finite union, so is the IoU (0/u = +0, times valid = +0) — no NaN-propagating min/max, no IEEE divide.
+      // Everything else takes the reference arithmetic.
+      const float ih = __fsub_rn(fminf(ca.y1, s0.z), fmaxf(ca.y0, s0.x));
+      const float iw = __fsub_rn(fminf(ca.x1, s0.w), fmaxf(ca.x0, s0.y));
+      const float uni0 = __fadd_rn(ca.area, s1.x);
+      if (a_ok && s1.z != 0.0f && (ih <= 0.0f || iw <= 0.0f) && uni0 > 0.0f && uni0 <= 3.0e38f) {
+        v = 0.0f;
+      } else {
+        Corners cb;
+        cb.y0 = s0.x; cb.x0 = s0.y; cb.y1 = s0.z; cb.x1 = s0.w; cb.area = s1.x;
+        v = __fmul_rn(iou_pair(ca, cb), s1.y);  // iou * truth_valid.float()
+      }
+      // torch.max(dim): first maximum wins; a NaN wins over everything that came before it.  (A culled truth is an
+      // exact +0: it can only ever be the maximum as truth 0, which is what best / best_m start from.)
+      if (m == 0 || v > best || (v != v && best == best)) {
+        best = v;
+        best_m = m;
+      }
     }
   }
+  if (!in_range) continue;
   const size_t o = (size_t)b * N + n;
   match_index[o] = best_m;
   match_iou[o] = best;
@@ -126,6 +168,7 @@ __global__ void __launch_bounds__(256) match_anchors_kernel(
   // the reference encodes the positives only (loss.py:62-66): everything else is written as zeros
   if (target)
     target[o] = (best >= pos_thr) ? encode_one(truth_box[(size_t)b * M + best_m], av, v0, v1) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 }
 
 static unsigned grid_for(long long total, int threads) {
@@ -224,7 +267,7 @@ extern "C" int tauv_yolact_match_anchors(const float* anchor, const float* truth
   TAUV_REQUIRE(B <= 65535, TAUV_E_UNSUPPORTED, "B=%d exceeds the built-in limit 65535", B);
   TAUV_REQUIRE((uintptr_t)anchor % 16 == 0 && (uintptr_t)truth_box % 16 == 0 && (uintptr_t)target % 16 == 0, TAUV_E_ALIGN,
                "box tensors must be 16-byte aligned");
-  dim3 grid((N + 255) / 256, B);
+  dim3 grid((N + 256 * kMatchTiles - 1) / (256 * kMatchTiles), B);
   const size_t smem = (size_t)M * 8 * sizeof(float);
   if (smem > 48 * 1024)
     TAUV_CUDA(ensure_dynamic_smem((const void*)(match_anchors_kernel), smem));

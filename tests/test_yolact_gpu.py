@@ -345,6 +345,33 @@ def test_match_golden(yl):
     assert_close(m.box_target[m.positive_match], g["targets"], atol=1e-6, what="regression targets of the positives")
 
 
+@pytest.mark.parametrize("N,M", [(1000, 16), (77, 3), (4000, 40), (19248, 1)])
+def test_match_culling_edge_cases_vs_oracle(yl, N, M):
+    """The kernel culls, per warp of 32 consecutive priors, the truths that miss the warp's hull.  Truths / priors with
+    NaN, infinite, zero-area or negative-size boxes must never be culled wrongly: index and IoU exact against the
+    oracle (torch.max: first maximum wins, a NaN wins over what came before), N not a multiple of 32, M > 32."""
+    g = synth.gen(100 + N + M)
+    anchor = torch.cat((torch.rand((1, N, 2), generator=g), torch.rand((1, N, 2), generator=g) * 0.2 + 0.01), -1)
+    tb, tv = synth.truth_boxes(3, M, seed=N)
+    if M >= 3:
+        tb[0, 1] = torch.tensor([float("nan"), 0.5, 0.1, 0.1])
+        tb[1, 2] = torch.tensor([0.5, 0.5, 0.0, 0.0])              # zero area: 0/0 -> NaN only against ...
+        tb[2, 0] = torch.tensor([0.5, float("inf"), 0.2, 0.2])
+        tv[:, :3] = True
+    if N >= 1000:
+        anchor[0, 5] = torch.tensor([0.5, 0.5, 0.0, 0.0])          # ... a zero-area prior at the same spot
+        anchor[0, 40] = torch.tensor([float("nan"), 0.2, 0.1, 0.1])
+        anchor[0, 70, 2:] = torch.tensor([-0.1, 0.3])              # negative height
+    mi, miou, pos, neg, _ = O.match_anchors(anchor, tb, tv, 0.4, 0.3, CFG.box_variances)
+    d = yl.dev
+    m = yl.loss.match_anchors(anchor.to(d), tb.to(d), tv.to(d), CFG)
+    assert_equal(torch.isnan(m.match_iou.cpu()), torch.isnan(miou), "NaN positions of match_iou")
+    assert_equal(torch.nan_to_num(m.match_iou.cpu(), nan=-7.0), torch.nan_to_num(miou, nan=-7.0), "match_iou")
+    ok = ~torch.isnan(miou)   # (where the maximum is NaN its index is whichever NaN came first: compare those too)
+    assert_equal(m.match_index.cpu()[ok], mi[ok]), assert_equal(m.match_index.cpu()[~ok], mi[~ok])
+    assert_equal(m.positive_match, pos), assert_equal(m.negative_match, neg)
+
+
 def test_match_full_size_vs_oracle(yl):
     anchor = O.all_anchors(synth.fpn_sizes(550, 550), CFG.anchor_scales, CFG.anchor_aspect_ratios, 550, 550)
     tb, tv = synth.truth_boxes(4, 16, seed=8)
