@@ -89,6 +89,11 @@ def algorithmic_bytes_mask_depth(B, n_keep_total):
     return B * (4 * YL_P * YL_HP * YL_HP + 2 * CAM_H * CAM_W) + n_keep_total * (YL_P * 4 + 16 + 16)
 
 
+def algorithmic_bytes_mask_binary(B, n_keep_total):
+    # prototypes once + per kept mask: coefficients, box, ONE byte per camera pixel (the binarised upsampled mask)
+    return B * 4 * YL_P * YL_HP * YL_HP + n_keep_total * (YL_P * 4 + 16 + CAM_H * CAM_W)
+
+
 class ClockSampler:
     """nvidia-smi-equivalent clock / throttle-reason sampling through NVML during the timed region."""
 
@@ -459,7 +464,8 @@ def run_centernet(ctx):
     # ---- max over ranks ----
     vals = [median(block_ms), e2e["ms"], t_dec, t_enc, t_dec_iso] + block_ms
     if yl is not None:
-        vals += [yl["detect_us"], yl["mask_us"], yl["mask_depth_us"], yl["scores_us"], yl["match_us"]]
+        vals += [yl["detect_us"], yl["mask_us"], yl["mask_depth_us"], yl["scores_us"], yl["match_us"],
+                 yl["mask_binary_nearest_us"], yl["mask_binary_bilinear_us"]]
     times = torch.tensor(vals, device=device, dtype=torch.float64)
     h2d_rate = torch.tensor([e2e["h2d_gbs"]], device=device, dtype=torch.float64)
     if dist is not None:
@@ -487,7 +493,7 @@ def run_centernet(ctx):
     }
     launches = 2 * K * NB + K + 3
     if yl is not None:
-        det_us, mask_us, md_us, sc_us, match_us = vals[5 + NB:5 + NB + 5]
+        det_us, mask_us, md_us, sc_us, match_us, mbn_us, mbb_us = vals[5 + NB:5 + NB + 7]
         nk = yl["n_keep_total"]
         kernels.update({
             "yolact_config": f"BASELINE configs[2]: B={B_PER_GPU}, {YL_N} priors, {YL_C1} classes, top_k {YL_TOPK}, "
@@ -506,6 +512,10 @@ def run_centernet(ctx):
             "mask_depth_bytes": algorithmic_bytes_mask_depth(B_PER_GPU, nk),
             "mask_depth_hbm_frac": algorithmic_bytes_mask_depth(B_PER_GPU, nk) / (md_us * 1e-6) / 1e9 / hbm_gbs,
             "yolact_frames_per_s_detect_plus_mask_depth": B_PER_GPU / ((det_us + md_us) * 1e-6),
+            "mask_binary_nearest_us": mbn_us, "mask_binary_bilinear_us": mbb_us,
+            "mask_binary_bytes": algorithmic_bytes_mask_binary(B_PER_GPU, nk),
+            "mask_binary_nearest_frac": algorithmic_bytes_mask_binary(B_PER_GPU, nk) / (mbn_us * 1e-6) / 1e9 / hbm_gbs,
+            "mask_binary_bilinear_frac": algorithmic_bytes_mask_binary(B_PER_GPU, nk) / (mbb_us * 1e-6) / 1e9 / hbm_gbs,
             "match_anchors_us": match_us,
             "match_anchors_bytes": 16 * YL_N + 16 * B_PER_GPU * 16 + B_PER_GPU * YL_N * 30,
             "match_anchors_frac": (16 * YL_N + 16 * B_PER_GPU * 16 + B_PER_GPU * YL_N * 30) / (match_us * 1e-6) / 1e9 / hbm_gbs,
@@ -558,6 +568,14 @@ def time_yolact(device, seed, B=B_PER_GPU):
     md_us, _ = time_kernel(lambda: masks.masked_depth_mean_batched(y.proto, y.coeff, det, y.depth, workspace=ws_d), reps=5, warmup=2)
     nk = int(det.n_keep.sum().item())
     del out
+    # binarised masks at the camera resolution (yolact_node.py:135 + :178): one byte per camera pixel and kept mask
+    out_b = torch.empty((B, YL_TOPK, CAM_H, CAM_W), dtype=torch.uint8, device=device)
+    ws_b = torch.empty(lib.tauv_yolact_mask_binary_workspace_bytes(B, YL_HP, YL_HP, YL_TOPK), dtype=torch.uint8, device=device)
+    mb_us = {}
+    for mode in ("nearest", "bilinear"):
+        mb_us[mode], _ = time_kernel(lambda: masks.assemble_mask_binary_batched(
+            y.proto, y.coeff, det, (CAM_H, CAM_W), mode=mode, out=out_b, workspace=ws_b), reps=5, warmup=2)
+    del out_b, ws_b
     # anchor matching (training-side target encode, loss.py:16-22,62-66): 16 truths per frame.  Its outputs (37 MB) fit in
     # L2, so a large READ between the launches evicts them without leaving dirty lines behind (a memset would)
     from tauv_vision_b200.yolact.model import loss as yl_loss
@@ -574,7 +592,8 @@ def time_yolact(device, seed, B=B_PER_GPU):
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
     return {"scores_us": sc_us, "detect_us": det_us, "mask_us": mask_us, "mask_depth_us": md_us, "n_keep_total": nk,
-            "match_us": median(ts[2:]), "launches": 10 * 1 + 10 * 3 + 7 * 1 + 7 * 3 + 7}
+            "match_us": median(ts[2:]), "mask_binary_nearest_us": mb_us["nearest"],
+            "mask_binary_bilinear_us": mb_us["bilinear"], "launches": 10 * 1 + 10 * 3 + 7 * 1 + 7 * 3 + 7 + 2 * 7 * 2}
 
 
 def e2e_centernet(ctx, logits, size, offset, truth, mc, tc, oc):

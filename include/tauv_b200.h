@@ -299,6 +299,34 @@ int tauv_yolact_mask_depth_batched(const float* proto, const float* coeff_all, c
                                    int Wi, double* mean, int64_t* count, void* workspace,
                                    size_t workspace_bytes, tauv_stream_t stream);
 
+/* Binarised masks at the camera / network-input resolution: what the reference's callers make of
+ * assemble_mask before anything else looks at it —
+ *     mask = F.interpolate(assemble_mask(proto, coeff, box)[None], (out_h, out_w))[0];  mask_np > 0.5
+ *                                   yolact/node/yolact_node.py:135, :178           (mode TAUV_RESIZE_NEAREST)
+ *     mask = F.interpolate(assemble_mask(...)[None], (out_h, out_w), mode="bilinear")[0];  mask = mask > 0.5
+ *                                   yolact/scripts/evaluate_batch.py:101-102       (mode TAUV_RESIZE_BILINEAR)
+ * as one byte per pixel (1 = on): a quarter of the bytes of the fp32 mask the reference upsamples, and the only
+ * full-resolution array written.  Index rules are ATen's: nearest takes source min(floor(dst * fp32(in/out)), in-1);
+ * bilinear (align_corners=False) takes max(fp32(in/out) * (dst + 0.5) - 0.5, 0), its integer part and the next pixel.
+ *   out [n,out_h,out_w] u8.  Differences from the reference are confined to pixels whose (interpolated) mask value is
+ *   within the contraction error of 0.5 (|logit| < ~2e-5 for nearest; |value - 0.5| < ~1e-5 for bilinear, which
+ *   switches the tensor-core epilogue to its 2-ulp sigmoid).
+ *   workspace (256-byte aligned): tauv_yolact_mask_binary_workspace_bytes(1, H, W, n) — the low-resolution masks. */
+#define TAUV_RESIZE_NEAREST 0
+#define TAUV_RESIZE_BILINEAR 1
+size_t tauv_yolact_mask_binary_workspace_bytes(int B, int H, int W, int top_k);
+int tauv_yolact_mask_binary(const float* proto, const float* coeff, const float* box, int n, int P,
+                            int H, int W, int out_h, int out_w, int mode, uint8_t* out,
+                            void* workspace, size_t workspace_bytes, tauv_stream_t stream);
+
+/* The same for every frame of a batch, straight from the detect() outputs.
+ *   out [B,top_k,out_h,out_w] u8; rows >= n_keep[b] are not written. */
+int tauv_yolact_mask_binary_batched(const float* proto, const float* coeff_all, const int64_t* keep,
+                                    const int32_t* n_keep, const float* keep_box, int B, int N,
+                                    int P, int H, int W, int top_k, int out_h, int out_w, int mode,
+                                    uint8_t* out, void* workspace, size_t workspace_bytes,
+                                    tauv_stream_t stream);
+
 /* box_to_mask(box, img_size) — yolact/model/boxes.py:88-103.  box [4] f32 -> out [H,W] {0,1}. */
 int tauv_box_to_mask(const float* box, int H, int W, float* out, tauv_stream_t stream);
 

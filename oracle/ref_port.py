@@ -368,6 +368,46 @@ def masked_depth_mean(mask_prototype, mask_coeff, box, depth_mm):
     return mean, count
 
 
+def upsample_bilinear_taps(out_size: int, in_size: int):
+    """Taps of ``F.interpolate(x, size, mode="bilinear")`` (align_corners=False; the call at evaluate_batch.py:101):
+    source coordinate max(fp32(in/out) * (i + 0.5) - 0.5, 0), left tap its integer part, right tap one further unless
+    that leaves the image, weights (1 - frac, frac), all in fp32 (ATen UpSample.h, area_pixel_compute_source_index).
+    The multiply-subtract is ONE fused operation in the builds measured (x86 CPU and nvcc both contract it), which
+    shows in the last bits of the weights: the weights torch uses, recovered by interpolating an identity matrix, are
+    reproduced exactly by the fused form and not by the unfused one (tests/test_oracle_vs_golden.py).  The product of
+    two fp32 numbers is exact in float64, so float64 arithmetic rounded once is that fused operation.
+    Returns (i0, i1, w0, w1)."""
+    scale = (torch.tensor(in_size, dtype=torch.float32) / torch.tensor(out_size, dtype=torch.float32)).to(torch.float64)
+    i = torch.arange(out_size, dtype=torch.float64)
+    s = torch.clamp((scale * (i + 0.5) - 0.5).to(torch.float32), min=0.0)
+    i0 = torch.clamp(s.to(torch.int64), max=in_size - 1)
+    i1 = i0 + (i0 < in_size - 1).to(torch.int64)
+    w1 = s - i0.to(torch.float32)
+    return i0, i1, 1.0 - w1, w1
+
+
+def mask_upsampled(mask_prototype, mask_coeff, box, size, mode: str):
+    """yolact_node.py:130-135 (mode "nearest") / evaluate_batch.py:100-101 (mode "bilinear"): assemble_mask, then
+    F.interpolate to `size`.  Returns the resized fp32 masks [n, size[0], size[1]]."""
+    mask = assemble_mask(mask_prototype, mask_coeff, box)
+    if mode == "nearest":
+        iy = upsample_nearest_index(size[0], mask.shape[1])
+        ix = upsample_nearest_index(size[1], mask.shape[2])
+        return mask[:, iy][:, :, ix]
+    assert mode == "bilinear", mode
+    y0, y1, wy0, wy1 = upsample_bilinear_taps(size[0], mask.shape[1])
+    x0, x1, wx0, wx1 = upsample_bilinear_taps(size[1], mask.shape[2])
+    top, bot = mask[:, y0], mask[:, y1]
+    return (wy0.view(1, -1, 1) * (wx0 * top[:, :, x0] + wx1 * top[:, :, x1])
+            + wy1.view(1, -1, 1) * (wx0 * bot[:, :, x0] + wx1 * bot[:, :, x1]))
+
+
+def mask_binary(mask_prototype, mask_coeff, box, size, mode: str):
+    """The resized mask thresholded as its consumers do (`mask_np > 0.5`, yolact_node.py:178; `mask = mask > 0.5`,
+    evaluate_batch.py:102), as uint8."""
+    return (mask_upsampled(mask_prototype, mask_coeff, box, size, mode) > 0.5).to(torch.uint8)
+
+
 def match_anchors(anchor, truth_box, truth_valid, pos_thr: float, neg_thr: float, variances):
     """yolact/model/loss.py:16-22 (+ :62-66 box_encode of the matched truth, here dense over all
     priors).  Returns (match_index [B,N], match_iou [B,N], positive, negative, target [B,N,4])."""

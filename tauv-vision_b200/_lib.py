@@ -77,6 +77,11 @@ _SIGNATURES = {
                                        c_void_p, c_size_t, c_void_p]),
     "tauv_yolact_mask_depth_batched": (c_int, [_F, _F, _I64, _I32, _F, c_int, c_int, c_int, c_int, c_int, c_int,
                                                c_void_p, c_int, c_int, _D, _I64, c_void_p, c_size_t, c_void_p]),
+    "tauv_yolact_mask_binary_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "tauv_yolact_mask_binary": (c_int, [_F, _F, _F, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _U8, c_void_p,
+                                        c_size_t, c_void_p]),
+    "tauv_yolact_mask_binary_batched": (c_int, [_F, _F, _I64, _I32, _F, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                                c_int, c_int, _U8, c_void_p, c_size_t, c_void_p]),
     "tauv_box_to_mask": (c_int, [_F, c_int, c_int, _F, c_void_p]),
     "tauv_yolact_match_anchors": (c_int, [_F, _F, _U8, c_int, c_int, c_int, c_float, c_float, c_float, c_float, _I64,
                                           _F, _U8, _U8, _F, c_void_p]),

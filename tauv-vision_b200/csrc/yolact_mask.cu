@@ -27,6 +27,7 @@ struct MaskArgs {
   int top_k;                 // output rows per frame
   float* out;                // [B,top_k,HW]
   float* logits;             // optional, same shape
+  int precise;               // tensor-core epilogue: ex2 + rcp sigmoid (2 ulp) instead of tanh.approx (5e-4 absolute)
   long long* trace;          // debug (tools/mask_trace.py): per-unit role timestamps of CTA 0, or NULL
   // fused consumer (tauv_yolact_mask_depth*): when acc != NULL no mask is written; instead, per detection, the pooled
   // camera depth of the pixels that are "on" (inside the box, sigmoid > 0.5) is added up
@@ -275,6 +276,135 @@ extern "C" int tauv_yolact_mask_depth_batched(const float* proto, const float* c
   a.proto = proto; a.coeff = coeff_all; a.keep = keep; a.n_keep = n_keep; a.box = (const float4*)keep_box;
   a.n_host = 0; a.N = N; a.P = P; a.H = H; a.W = W; a.top_k = top_k;
   return run_mask_depth(a, B, top_k, depth_mm, Hi, Wi, workspace, workspace_bytes, mean, count, (cudaStream_t)stream);
+}
+
+// ---- binarised masks at the camera / network-input resolution ----------------------------------
+namespace tauv {
+
+// F.interpolate(..., mode="bilinear") with align_corners=False (ATen UpSample.h: area_pixel_compute_source_index):
+// source coordinate = max(fp32(in/out) * (dst + 0.5) - 0.5, 0); the left/top tap is its integer part, the other tap one
+// further unless that leaves the image; weights (1 - frac, frac).  The multiply-subtract is a single fused operation
+// in ATen's builds (CPU and CUDA alike — it shows in the last bits of the weights, see oracle/ref_port.py), hence the
+// explicit fmaf: this library is otherwise built without FMA contraction.
+struct LinearTap {
+  int i0, i1;
+  float w0, w1;
+};
+__device__ __forceinline__ LinearTap linear_tap(int dst, float scale, int in_size) {
+  float s = fmaf(scale, (float)dst + 0.5f, -0.5f);
+  s = s < 0.0f ? 0.0f : s;
+  LinearTap t;
+  t.i0 = min((int)s, in_size - 1);
+  t.i1 = t.i0 + (t.i0 < in_size - 1 ? 1 : 0);
+  t.w1 = s - (float)t.i0;
+  t.w0 = 1.0f - t.w1;
+  return t;
+}
+
+// low [B*top_k][H*W] fp32 masks -> out [B*top_k][Ho*Wo] bytes (1 where the resized mask is > 0.5).  One thread makes
+// VEC horizontally adjacent bytes (VEC == 4 needs Wo % 4 == 0 and a 4-byte aligned output: one 128-byte store per warp).
+// MODE 0: nearest (yolact_node.py:135, followed by the node's `mask_np > 0.5` at :178); 1: bilinear
+// (evaluate_batch.py:101-102).  Rows >= n_keep[b] are not written.
+template <int MODE, int VEC>
+__global__ void __launch_bounds__(256) mask_binary_resize_kernel(const float* __restrict__ low,
+                                                                 const int32_t* __restrict__ n_keep, int n_host, int top_k,
+                                                                 int H, int W, int Ho, int Wo, uint8_t* __restrict__ out) {
+  const int j = blockIdx.y, b = blockIdx.z;
+  if (j >= (n_keep ? n_keep[b] : n_host)) return;
+  const size_t row = (size_t)b * top_k + j;
+  const float* __restrict__ src = low + row * (size_t)H * W;
+  const long long p0 = ((long long)blockIdx.x * 256 + threadIdx.x) * VEC;
+  if (p0 >= (long long)Ho * Wo) return;
+  const int yo = (int)(p0 / Wo), xo = (int)(p0 - (long long)yo * Wo);
+  const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
+  unsigned bits = 0u;
+  if (MODE == 0) {
+    const float* r = src + (size_t)nearest_src(yo, sy, H) * W;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) bits |= (r[nearest_src(xo + v, sx, W)] > 0.5f ? 1u : 0u) << (8 * v);
+  } else {
+    const LinearTap ty = linear_tap(yo, sy, H);
+    const float* r0 = src + (size_t)ty.i0 * W;
+    const float* r1 = src + (size_t)ty.i1 * W;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const LinearTap tx = linear_tap(xo + v, sx, W);
+      const float val = ty.w0 * (tx.w0 * r0[tx.i0] + tx.w1 * r0[tx.i1]) + ty.w1 * (tx.w0 * r1[tx.i0] + tx.w1 * r1[tx.i1]);
+      bits |= (val > 0.5f ? 1u : 0u) << (8 * v);
+    }
+  }
+  uint8_t* dst = out + row * (size_t)Ho * Wo + p0;
+  if (VEC == 4) *reinterpret_cast<uint32_t*>(dst) = bits;
+  else *dst = (uint8_t)bits;
+}
+
+static size_t mask_binary_ws_bytes(int B, int H, int W, int top_k) {
+  return ((size_t)B * top_k * H * W * sizeof(float) + 255) & ~(size_t)255;
+}
+
+static int run_mask_binary(MaskArgs a, int B, int max_rows, int Ho, int Wo, int mode, uint8_t* out, void* workspace,
+                           size_t workspace_bytes, cudaStream_t st) {
+  TAUV_REQUIRE(mode == TAUV_RESIZE_NEAREST || mode == TAUV_RESIZE_BILINEAR, TAUV_E_UNSUPPORTED,
+               "mode must be TAUV_RESIZE_NEAREST or TAUV_RESIZE_BILINEAR; got %d", mode);
+  const size_t need = mask_binary_ws_bytes(B, a.H, a.W, a.top_k);
+  TAUV_REQUIRE(workspace && workspace_bytes >= need, TAUV_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
+  TAUV_REQUIRE((uintptr_t)workspace % 256 == 0, TAUV_E_ALIGN, "workspace must be 256-byte aligned");
+  TAUV_REQUIRE(a.top_k <= 65535, TAUV_E_UNSUPPORTED, "%d masks per frame exceed the built-in limit 65535", a.top_k);
+  a.out = reinterpret_cast<float*>(workspace);
+  a.logits = nullptr;
+  a.precise = mode == TAUV_RESIZE_BILINEAR;
+  const int rc = run_mask(a, B, max_rows, want_simt_env(), st);
+  if (rc) return rc;
+  const long long total = (long long)Ho * Wo;
+  const bool vec = Wo % 4 == 0 && (uintptr_t)out % 4 == 0;
+  const long long per_block = 256LL * (vec ? 4 : 1);
+  const dim3 grid((unsigned)((total + per_block - 1) / per_block), (unsigned)a.top_k, (unsigned)B);
+#define TAUV_RESIZE(MODE, VEC) \
+  mask_binary_resize_kernel<MODE, VEC><<<grid, 256, 0, st>>>(a.out, a.n_keep, a.n_host, a.top_k, a.H, a.W, Ho, Wo, out)
+  if (mode == TAUV_RESIZE_NEAREST) {
+    if (vec) TAUV_RESIZE(0, 4); else TAUV_RESIZE(0, 1);
+  } else {
+    if (vec) TAUV_RESIZE(1, 4); else TAUV_RESIZE(1, 1);
+  }
+#undef TAUV_RESIZE
+  TAUV_LAUNCH_CHECK("mask_binary_resize_kernel");
+  return 0;
+}
+
+}  // namespace tauv
+
+extern "C" size_t tauv_yolact_mask_binary_workspace_bytes(int B, int H, int W, int top_k) {
+  if (B <= 0 || H <= 0 || W <= 0 || top_k <= 0) return 0;
+  return tauv::mask_binary_ws_bytes(B, H, W, top_k);
+}
+
+extern "C" int tauv_yolact_mask_binary(const float* proto, const float* coeff, const float* box, int n, int P, int H, int W,
+                                       int out_h, int out_w, int mode, uint8_t* out, void* workspace,
+                                       size_t workspace_bytes, tauv_stream_t stream) {
+  TAUV_REQUIRE(n >= 0, TAUV_E_SHAPE, "n must be >= 0");
+  if (n == 0) return 0;
+  TAUV_REQUIRE(proto && coeff && out, TAUV_E_NULL, "proto/coeff/out must not be NULL");
+  TAUV_REQUIRE(P > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0, TAUV_E_SHAPE, "bad shape P=%d H=%d W=%d out=%dx%d", P, H, W,
+               out_h, out_w);
+  TAUV_REQUIRE((uintptr_t)box % 16 == 0, TAUV_E_ALIGN, "box must be 16-byte aligned");
+  MaskArgs a{};
+  a.proto = proto; a.coeff = coeff; a.keep = nullptr; a.n_keep = nullptr; a.box = (const float4*)box;
+  a.n_host = n; a.N = 0; a.P = P; a.H = H; a.W = W; a.top_k = n;
+  return run_mask_binary(a, 1, n, out_h, out_w, mode, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int tauv_yolact_mask_binary_batched(const float* proto, const float* coeff_all, const int64_t* keep,
+                                               const int32_t* n_keep, const float* keep_box, int B, int N, int P, int H,
+                                               int W, int top_k, int out_h, int out_w, int mode, uint8_t* out,
+                                               void* workspace, size_t workspace_bytes, tauv_stream_t stream) {
+  TAUV_REQUIRE(proto && coeff_all && keep && n_keep && out, TAUV_E_NULL, "pointers must not be NULL");
+  TAUV_REQUIRE(B > 0 && N > 0 && P > 0 && H > 0 && W > 0 && top_k > 0 && out_h > 0 && out_w > 0, TAUV_E_SHAPE, "bad shape");
+  TAUV_REQUIRE(B <= 65535, TAUV_E_UNSUPPORTED, "B=%d exceeds the built-in limit 65535", B);
+  TAUV_REQUIRE((uintptr_t)keep_box % 16 == 0, TAUV_E_ALIGN, "keep_box must be 16-byte aligned");
+  MaskArgs a{};
+  a.proto = proto; a.coeff = coeff_all; a.keep = keep; a.n_keep = n_keep; a.box = (const float4*)keep_box;
+  a.n_host = 0; a.N = N; a.P = P; a.H = H; a.W = W; a.top_k = top_k;
+  return run_mask_binary(a, B, top_k, out_h, out_w, mode, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 #ifdef TAUV_DEBUG

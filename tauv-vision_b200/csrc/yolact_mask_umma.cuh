@@ -426,13 +426,20 @@ __global__ void __launch_bounds__(UmmaRoles<kDepth>::kThreads, 1) mask_umma_kern
                               __float_as_int(bd.w - py);
               keepm[i] = ~(neg >> 31);  // all ones when the pixel is inside the box
             }
+            if (a.precise) {  // (uniform over the launch)
+              // consumers that interpolate the mask values and threshold the result (tauv_yolact_mask_binary, bilinear)
+              // need fp32-class values: rcp.approx(1 + ex2.approx(-x log2 e)), 2 ulp each, saturating to 0 / 1
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              // sigmoid(x) = 0.5 + 0.5*tanh(x/2): one MUFU op (tanh.approx, |error| <= ~5e-4 on the mask value against
-              // the 2.5e-3 the bf16 contraction is allowed) instead of ex2 + rcp
-              float t;
-              asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(v[j0 + i] * 0.5f));
-              sg[i] = fmaf(t, 0.5f, 0.5f);
+              for (int i = 0; i < 8; ++i) sg[i] = __fdividef(1.0f, 1.0f + exp2f(v[j0 + i] * -1.4426950408889634f));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                // sigmoid(x) = 0.5 + 0.5*tanh(x/2): one MUFU op (tanh.approx, |error| <= ~5e-4 on the mask value
+                // against the 2.5e-3 the bf16 contraction is allowed) instead of ex2 + rcp
+                float t;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(v[j0 + i] * 0.5f));
+                sg[i] = fmaf(t, 0.5f, 0.5f);
+              }
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) stg[j0 + i][quad * 32 + lane] = __int_as_float(__float_as_int(sg[i]) & keepm[i]);

@@ -123,3 +123,67 @@ def masked_depth_mean_batched(mask_prototype: torch.Tensor, mask_coeff: torch.Te
             _lib.fptr(detections.box) if crop else None, B, N, P, H, W, top_k, depth.data_ptr(), Hi, Wi,
             _lib.dptr(mean), _lib.i64ptr(count), workspace.data_ptr(), workspace.numel(), _lib.stream_ptr(dev)))
     return mean, count
+
+
+_RESIZE_MODES = {"nearest": 0, "bilinear": 1}
+
+
+def _resize_args(size, mode):
+    if mode not in _RESIZE_MODES:
+        raise ValueError(f"mode must be 'nearest' or 'bilinear'; got {mode!r}")
+    out_h, out_w = (int(s) for s in size)
+    if out_h <= 0 or out_w <= 0:
+        raise ValueError(f"size must be positive; got {size}")
+    return out_h, out_w, _RESIZE_MODES[mode]
+
+
+def assemble_mask_binary(mask_prototype: torch.Tensor, mask_coeff: torch.Tensor, box: Optional[torch.Tensor], size,
+                         mode: str = "nearest") -> torch.Tensor:
+    """``F.interpolate(assemble_mask(proto, coeff, box)[None], size, mode=mode)[0] > 0.5`` as uint8 — the ROS node's
+    mask (mode "nearest": /root/reference/src/tauv_vision/yolact/node/yolact_node.py:135 and its ``mask_np > 0.5`` at
+    :178) and the evaluation script's (mode "bilinear": yolact/scripts/evaluate_batch.py:101-102), written once, one
+    byte per pixel.  mask_prototype [P,H,W], mask_coeff [n,P], box [n,4] or None -> [n,size[0],size[1]] uint8."""
+    dev = _lib.require_cuda(mask_prototype, mask_coeff, box)
+    proto, coeff = _lib.f32c(mask_prototype), _lib.f32c(mask_coeff)
+    if proto.dim() != 3 or coeff.dim() != 2 or coeff.shape[1] != proto.shape[0]:
+        raise ValueError(f"mask_prototype {tuple(proto.shape)} / mask_coeff {tuple(coeff.shape)} must be [P,H,W] / [n,P]")
+    out_h, out_w, m = _resize_args(size, mode)
+    P, H, W = proto.shape
+    n = coeff.shape[0]
+    bx = _lib.f32c(box) if box is not None else None
+    if bx is not None and tuple(bx.shape) != (n, 4):
+        raise ValueError(f"box must be [{n},4]; got {tuple(bx.shape)}")
+    out = torch.empty((n, out_h, out_w), dtype=torch.uint8, device=dev)
+    if n:
+        lib = _lib.load()
+        ws = torch.empty(lib.tauv_yolact_mask_binary_workspace_bytes(1, H, W, n), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.tauv_yolact_mask_binary(_lib.fptr(proto), _lib.fptr(coeff), _lib.fptr(bx), n, P, H, W, out_h,
+                                                   out_w, m, _lib.u8ptr(out), ws.data_ptr(), ws.numel(),
+                                                   _lib.stream_ptr(dev)))
+    return out
+
+
+def assemble_mask_binary_batched(mask_prototype: torch.Tensor, mask_coeff: torch.Tensor, detections, size,
+                                 mode: str = "nearest", crop: bool = True, out: Optional[torch.Tensor] = None,
+                                 workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``assemble_mask_binary`` for all frames at once from the fused detect() output.  mask_prototype [B,P,H,W],
+    mask_coeff [B,N,P] -> [B,top_k,size[0],size[1]] uint8; rows >= n_keep[b] are left untouched.  No synchronisation."""
+    dev = _lib.require_cuda(mask_prototype, mask_coeff, detections.keep)
+    proto, coeff = _lib.f32c(mask_prototype), _lib.f32c(mask_coeff)
+    B, P, H, W = proto.shape
+    N = coeff.shape[1]
+    top_k = detections.keep.shape[1]
+    out_h, out_w, m = _resize_args(size, mode)
+    lib = _lib.load()
+    need = lib.tauv_yolact_mask_binary_workspace_bytes(B, H, W, top_k)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    if out is None:
+        out = torch.empty((B, top_k, out_h, out_w), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.tauv_yolact_mask_binary_batched(
+            _lib.fptr(proto), _lib.fptr(coeff), _lib.i64ptr(detections.keep), _lib.i32ptr(detections.n_keep),
+            _lib.fptr(detections.box) if crop else None, B, N, P, H, W, top_k, out_h, out_w, m, _lib.u8ptr(out),
+            workspace.data_ptr(), workspace.numel(), _lib.stream_ptr(dev)))
+    return out

@@ -303,6 +303,22 @@ def main():
         arrays.update({f"mean_{tag}_nobox": mean, f"count_{tag}_nobox": count})
     save("yl_mask_depth", **arrays)
 
+    # ---- binarised upsampled masks with the callers' own lines: yolact_node.py:135 (+ `mask_np > 0.5`, :178) and
+    # evaluate_batch.py:101-102; the resized fp32 values are kept as well (float16 is enough to tell how far a pixel
+    # is from the threshold) so that the tests can set pixels within rounding of 0.5 aside
+    arrays = {}
+    for tag, (P_, H_, W_, K_, exact) in {"a": (8, 20, 24, 5, False), "b": (32, 23, 31, 7, True)}.items():
+        proto, coeff, mbox = (synth.mask_inputs_exact if exact else synth.mask_inputs)(P_, H_, W_, K_, seed=97)
+        arrays.update({f"proto_{tag}": proto, f"coeff_{tag}": coeff, f"box_{tag}": mbox})
+        mask = ref_masks.assemble_mask(proto, coeff, mbox)
+        for j, (ho, wo) in enumerate([(45, 72), (2 * H_, 2 * W_), (H_, W_), (13, 17), (97, 64)]):
+            near = F.interpolate(mask.unsqueeze(0), (ho, wo)).squeeze(0)
+            bil = F.interpolate(mask.unsqueeze(0), (ho, wo), mode="bilinear").squeeze(0)
+            arrays.update({f"size_{tag}{j}": np.array([ho, wo]),
+                           f"nearest_{tag}{j}": (near > 0.5).to(torch.uint8), f"bilinear_{tag}{j}": (bil > 0.5).to(torch.uint8),
+                           f"bilinear_dist_{tag}{j}": (bil - 0.5).abs().to(torch.float16)})
+    save("yl_mask_binary", **arrays)
+
     # ---- anchor matching: yolact/model/loss.py:16-22 + :62-66, line by line with the reference's own ops ----
     tb, tv = synth.truth_boxes(3, 6, seed=101)
     g = synth.gen(102)

@@ -161,6 +161,42 @@ def test_upsample_nearest_index_matches_interpolate():
         assert_equal(O.upsample_nearest_index(out_size, in_size), up, f"{in_size} -> {out_size}")
 
 
+def test_upsample_bilinear_taps_match_interpolate():
+    """The oracle's taps and weights are the ones F.interpolate(x, size, mode="bilinear") (evaluate_batch.py:101)
+    uses: interpolating a ramp and a one-hot row reproduces torch's output to rounding."""
+    g = torch.Generator().manual_seed(5)
+    for in_size, out_size in [(138, 550), (276, 720), (20, 45), (24, 72), (23, 46), (31, 31), (20, 13), (276, 277),
+                              (7, 1000), (1000, 7), (1, 5)]:
+        x = torch.rand((1, 1, 1, in_size), generator=g)
+        up = torch.nn.functional.interpolate(x, (1, out_size), mode="bilinear").reshape(-1)
+        i0, i1, w0, w1 = O.upsample_bilinear_taps(out_size, in_size)
+        row = x.reshape(-1)
+        assert_close(w0 * row[i0] + w1 * row[i1], up, rtol=0, atol=2e-7, what=f"{in_size} -> {out_size}")
+        # the weights themselves, recovered exactly: row p of the resized identity holds tap p's weight per output
+        eye = torch.eye(in_size).reshape(1, 1, in_size, in_size)
+        wts = torch.nn.functional.interpolate(eye, (in_size, out_size), mode="bilinear")[0, 0]
+        d = torch.arange(out_size)
+        two = i1 > i0
+        assert_equal(wts[i1, d][two], w1[two], f"right weights {in_size} -> {out_size}")
+        assert_equal(wts[i0, d][two], w0[two], f"left weights {in_size} -> {out_size}")
+
+
+def test_mask_binary_golden():
+    """mask_binary against the callers' own lines frozen from the real reference (yolact_node.py:135 + :178,
+    evaluate_batch.py:101-102).  Nearest is an index map: exact.  Bilinear: exact except where the interpolated value
+    is within fp32 rounding of 0.5 (the golden carries the distance)."""
+    g = golden("yl_mask_binary")
+    for tag in "ab":
+        proto, coeff, box = t(g[f"proto_{tag}"]), t(g[f"coeff_{tag}"]), t(g[f"box_{tag}"])
+        for j in range(5):
+            size = tuple(int(v) for v in g[f"size_{tag}{j}"])
+            assert_equal(O.mask_binary(proto, coeff, box, size, "nearest"), g[f"nearest_{tag}{j}"], f"nearest {tag}{j}")
+            got = O.mask_binary(proto, coeff, box, size, "bilinear").numpy()
+            clear = g[f"bilinear_dist_{tag}{j}"].astype(np.float32) > 1e-5
+            assert clear.mean() > 0.99
+            assert_equal(got[clear], g[f"bilinear_{tag}{j}"][clear], f"bilinear {tag}{j}")
+
+
 def test_mask_depth_golden():
     """masked_depth_mean against the node's own sequence of calls (frozen by make_golden.py)."""
     g = golden("yl_mask_depth")

@@ -201,39 +201,48 @@ def _mask_check(yl, logits_atol):
     assert yl.masks.assemble_mask(proto, coeff[:0], box[:0]).shape == (0, 20, 24)
 
 
-def test_mask_golden_simt(yl, monkeypatch):
-    monkeypatch.setenv("TAUV_MASK_SIMT", "1")
+def _off16(tn):
+    """A copy of `tn` that starts 4 bytes off a 16-byte boundary.  The tensor-core kernel loads coefficient rows with
+    16-byte accesses, so the dispatcher (csrc/yolact_mask_umma.cuh, umma_shape_ok) hands such a call to the CUDA-core
+    kernel: the way to reach that kernel at P == 32 through the public API (release builds have no environment knobs)."""
+    buf = torch.empty(tn.numel() + 4, dtype=tn.dtype, device=tn.device)
+    out = buf[1:1 + tn.numel()].view(tn.shape)
+    assert out.data_ptr() % 16 == 4
+    out.copy_(tn)
+    return out
+
+
+def test_mask_golden_simt(yl):
+    """P = 8 is not a tensor-core shape: the CUDA-core kernel, which keeps the reference's fp32 summation order."""
     _mask_check(yl, 2e-6)
 
 
-def test_mask_golden_tensor_core(yl, monkeypatch):
+def test_mask_golden_tensor_core(yl):
     """P = 8 is not a tensor-core shape (the golden is tiny): this exercises the dispatcher; the tensor-core
     kernel itself is checked in test_mask_vs_oracle_shapes / test_mask_logits_tensor_core."""
-    monkeypatch.delenv("TAUV_MASK_SIMT", raising=False)
     _mask_check(yl, 1e-2)
 
 
-def test_mask_logits_tensor_core(yl, monkeypatch):
+def test_mask_logits_tensor_core(yl):
     """North-star tolerance: |logit error| <= 1e-2 for the bf16 tensor-core contraction.  With the hi/lo operand
     split the kernel is in fact ~1e-5 accurate; assert the spec bound and report the achieved one."""
-    monkeypatch.delenv("TAUV_MASK_SIMT", raising=False)
     proto, coeff, box = synth.mask_inputs(32, 69, 69, 150, seed=77)
     ref = (coeff.double() @ proto.reshape(32, -1).double()).reshape(150, 69, 69)
     m, lg = yl.masks.assemble_mask(proto.to(yl.dev), coeff.to(yl.dev), box.to(yl.dev), return_logits=True)
     err = (lg.cpu().double() - ref).abs().max().item()
     assert err <= 1e-2, err
     assert err <= 1e-4, f"hi/lo split should give fp32-class logits, got {err}"
-    monkeypatch.setenv("TAUV_MASK_SIMT", "1")
-    m2 = yl.masks.assemble_mask(proto.to(yl.dev), coeff.to(yl.dev), box.to(yl.dev))
-    assert_close(m, m2, rtol=0, atol=5e-5, what="tensor-core vs CUDA-core kernel")
+    m2, lg2 = yl.masks.assemble_mask(proto.to(yl.dev), _off16(coeff.to(yl.dev)), box.to(yl.dev), return_logits=True)
+    assert_close(lg2, O.mask_logits(proto, coeff), rtol=0, atol=1e-5, what="CUDA-core kernel (unaligned coefficients)")
+    assert not torch.equal(lg, lg2), "the two calls were meant to take different kernels"
+    assert_close(m, m2, rtol=0, atol=5e-4, what="tensor-core vs CUDA-core kernel")
 
 
 @pytest.mark.parametrize("P,H,W,K", [(32, 138, 138, 100), (32, 276, 276, 37), (16, 64, 40, 130), (48, 30, 36, 5),
                                       (32, 7, 9, 3), (24, 16, 16, 4)])
-def test_mask_vs_oracle_shapes(yl, monkeypatch, P, H, W, K):
+def test_mask_vs_oracle_shapes(yl, P, H, W, K):
     """Tensor-core path where the shape fits (P % 16 == 0, H*W % 4 == 0), CUDA-core path otherwise; both against
     the fp32 oracle.  n > 128 exercises several M tiles; odd sizes exercise ragged pixel tiles."""
-    monkeypatch.delenv("TAUV_MASK_SIMT", raising=False)
     proto, coeff, box = synth.mask_inputs(P, H, W, K, seed=P + H)
     ref = torch.sigmoid(proto.reshape(P, -1).T @ coeff.T).T.reshape(K, H, W)
     crop = torch.stack([O.box_to_mask(box[i], (H, W)) for i in range(K)])
@@ -245,8 +254,7 @@ def test_mask_vs_oracle_shapes(yl, monkeypatch, P, H, W, K):
     assert_close(m2, ref, rtol=0, atol=2.5e-3, what="mask, no crop")
 
 
-def test_mask_batched_matches_single(yl, monkeypatch):
-    monkeypatch.delenv("TAUV_MASK_SIMT", raising=False)
+def test_mask_batched_matches_single(yl):
     d = yl.dev
     B, N, P, H, W, top_k = 3, 500, 32, 48, 52, 40
     g = synth.gen(12)
@@ -268,19 +276,17 @@ def _u16(depth_i32, dev):
 
 
 @pytest.mark.parametrize("simt", [False, True])
-def test_mask_depth_golden(yl, monkeypatch, simt):
+def test_mask_depth_golden(yl, simt):
     """masked_depth_mean against the node's own call sequence (assemble_mask -> F.interpolate -> nanmean of the
     selected depth readings, yolact_node.py:102-103,130-131,178) frozen from the real reference.  Case b has
     half-integer logits from bf16-exact operands and P = 32: the tensor-core epilogue must select exactly the same
     pixels; case a (P = 8) goes through the CUDA-core kernel either way."""
-    if simt:
-        monkeypatch.setenv("TAUV_MASK_SIMT", "1")
-    else:
-        monkeypatch.delenv("TAUV_MASK_SIMT", raising=False)
     g = golden("yl_mask_depth")
     d = yl.dev
     for tag in "ab":
         proto, coeff, box = t(g[f"proto_{tag}"]).to(d), t(g[f"coeff_{tag}"]).to(d), t(g[f"box_{tag}"]).to(d)
+        if simt:
+            coeff = _off16(coeff)
         for j in range(5):
             mean, count = yl.masks.masked_depth_mean(proto, coeff, box, _u16(t(g[f"depth_{tag}{j}"]), d), return_count=True)
             assert_equal(count, g[f"count_{tag}{j}"], f"count {tag}{j}")
@@ -295,11 +301,10 @@ def test_mask_depth_golden(yl, monkeypatch, simt):
 
 @pytest.mark.parametrize("H,W,K,hi,wi", [(138, 138, 100, 360, 640), (276, 276, 37, 720, 1280), (69, 69, 150, 69, 69),
                                           (276, 276, 300, 240, 320)])
-def test_mask_depth_vs_oracle(yl, monkeypatch, H, W, K, hi, wi):
+def test_mask_depth_vs_oracle(yl, H, W, K, hi, wi):
     """Full-size prototype maps, several M tiles (K > 256 takes two launches), up- and down-sampling.  Real-valued
     operands: a camera pixel may legitimately flip where its logit is within the bf16x2 contraction error of zero,
     so counts may differ by the number of such readings (computed in float64) and the mean accordingly."""
-    monkeypatch.delenv("TAUV_MASK_SIMT", raising=False)
     proto, coeff, box = synth.mask_inputs(32, H, W, K, seed=H + K)
     depth = synth.depth_image(hi, wi, seed=hi)
     ref_mean, ref_count = O.masked_depth_mean(proto, coeff, box, depth)
@@ -315,8 +320,7 @@ def test_mask_depth_vs_oracle(yl, monkeypatch, H, W, K, hi, wi):
     assert_close(mean.cpu().numpy()[~clean], ref_mean.numpy()[~clean], rtol=1e-2, what="mean depth (ambiguous readings)")
 
 
-def test_mask_depth_batched_matches_single(yl, monkeypatch):
-    monkeypatch.delenv("TAUV_MASK_SIMT", raising=False)
+def test_mask_depth_batched_matches_single(yl):
     d = yl.dev
     B, N, P, H, W, top_k, hi, wi = 3, 500, 32, 48, 52, 40, 120, 160
     g = synth.gen(12)
@@ -334,6 +338,77 @@ def test_mask_depth_batched_matches_single(yl, monkeypatch):
         assert_equal(count[b, :n], c1, f"frame {b}: count")
         assert_close(mean[b, :n], m1, rtol=0, atol=0, what=f"frame {b}: batched == per-frame call")
         assert bool(torch.isnan(mean[b, n:]).all()) and int(count[b, n:].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("simt", [False, True])
+def test_mask_binary_golden(yl, simt):
+    """assemble_mask_binary against the callers' own lines frozen from the real reference: F.interpolate(mask, size)
+    then `mask_np > 0.5` (yolact_node.py:135, :178) and F.interpolate(..., mode="bilinear") then `mask > 0.5`
+    (evaluate_batch.py:101-102).  Case b (P = 32: the tensor-core kernel unless `simt`) has half-integer logits from
+    bf16-exact operands, so the nearest-mode bytes must be identical; bilinear is identical except where the
+    interpolated value is within rounding of 0.5 (the golden carries each pixel's distance from the threshold)."""
+    g = golden("yl_mask_binary")
+    d = yl.dev
+    for tag in "ab":
+        proto, coeff, box = t(g[f"proto_{tag}"]).to(d), t(g[f"coeff_{tag}"]).to(d), t(g[f"box_{tag}"]).to(d)
+        if simt:
+            coeff = _off16(coeff)
+        for j in range(5):
+            size = tuple(int(v) for v in g[f"size_{tag}{j}"])
+            near = yl.masks.assemble_mask_binary(proto, coeff, box, size)
+            assert near.dtype == torch.uint8 and tuple(near.shape) == (coeff.shape[0],) + size
+            if tag == "b" or simt:
+                assert_equal(near, g[f"nearest_{tag}{j}"], f"nearest {tag}{j}")
+            else:  # real-valued logits summed in another order: a pixel within rounding of logit 0 may flip
+                lg = O.mask_logits(t(g[f"proto_{tag}"]), t(g[f"coeff_{tag}"]))
+                iy, ix = O.upsample_nearest_index(size[0], lg.shape[1]), O.upsample_nearest_index(size[1], lg.shape[2])
+                clear = (lg.abs() > 1e-4)[:, iy][:, :, ix].numpy()
+                assert_equal(near.cpu().numpy()[clear], g[f"nearest_{tag}{j}"][clear], f"nearest {tag}{j}")
+            bil = yl.masks.assemble_mask_binary(proto, coeff, box, size, mode="bilinear").cpu().numpy()
+            clear = g[f"bilinear_dist_{tag}{j}"].astype(np.float32) > 2e-5
+            assert clear.mean() > 0.99
+            assert_equal(bil[clear], g[f"bilinear_{tag}{j}"][clear], f"bilinear {tag}{j}")
+    e = yl.masks.assemble_mask_binary(proto, coeff[:0], box[:0], (11, 13))
+    assert e.shape == (0, 11, 13) and e.dtype == torch.uint8
+    with pytest.raises(ValueError):
+        yl.masks.assemble_mask_binary(proto, coeff, box, (11, 13), mode="bicubic")
+
+
+@pytest.mark.parametrize("H,W,K,ho,wo", [(138, 138, 100, 480, 640), (138, 138, 37, 550, 550), (69, 69, 150, 69, 69),
+                                          (276, 276, 20, 241, 323)])
+@pytest.mark.parametrize("mode", ["nearest", "bilinear"])
+def test_mask_binary_vs_oracle(yl, mode, H, W, K, ho, wo):
+    """Full-size prototype maps, camera (480x640) and network-input (550x550) resolutions, identity and odd sizes
+    (241x323 takes the byte-store path).  Every pixel whose resized fp32 mask value is clear of 0.5 must match the
+    oracle; the rest (within the tensor-core contraction error of the threshold) are counted and must be rare."""
+    proto, coeff, box = synth.mask_inputs(32, H, W, K, seed=H + K)
+    d = yl.dev
+    got = yl.masks.assemble_mask_binary(proto.to(d), coeff.to(d), box.to(d), (ho, wo), mode=mode).cpu()
+    val = O.mask_upsampled(proto, coeff, box, (ho, wo), mode)
+    clear = (val - 0.5).abs() > 5e-5
+    assert float(clear.float().mean()) > 0.999
+    assert_equal(got[clear], (val > 0.5).to(torch.uint8)[clear], f"{mode} {H}x{W} -> {ho}x{wo}")
+    assert int(got.max()) == 1 and 0.01 < float(got.float().mean()) < 0.5  # (not vacuous)
+
+
+def test_mask_binary_batched_matches_single(yl):
+    d = yl.dev
+    B, N, P, H, W, top_k, ho, wo = 3, 500, 32, 48, 52, 40, 120, 160
+    g = synth.gen(12)
+    anchor = torch.cat((torch.rand((1, N, 2), generator=g), torch.rand((1, N, 2), generator=g) * 0.3 + 0.05), -1)
+    cls, enc = synth.yolact_heads(B, N, 7, seed=13, anchor=anchor, separated=True)
+    proto = torch.nn.functional.leaky_relu(torch.randn((B, P, H, W), generator=g)).to(d)
+    coeff = torch.tanh(torch.randn((B, N, P), generator=g)).to(d)
+    det = yl.nms.detect(cls.to(d), enc.to(d), anchor.to(d), CFG, top_k, 0.5, 0.05)
+    for mode in ("nearest", "bilinear"):
+        out = torch.full((B, top_k, ho, wo), 7, dtype=torch.uint8, device=d)
+        yl.masks.assemble_mask_binary_batched(proto, coeff, det, (ho, wo), mode=mode, out=out)
+        for b in range(B):
+            n = int(det.n_keep[b])
+            assert n > 0
+            single = yl.masks.assemble_mask_binary(proto[b], coeff[b, det.keep[b, :n]], det.box[b, :n], (ho, wo), mode=mode)
+            assert_equal(out[b, :n], single, f"{mode} frame {b}: batched == per-frame call")
+            assert bool((out[b, n:] == 7).all()), "rows beyond n_keep are left untouched"
 
 
 def test_match_golden(yl):
