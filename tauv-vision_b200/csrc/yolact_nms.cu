@@ -195,13 +195,23 @@ struct NmsArgs {
   float v0, v1;
   int N, top_k;
   float iou_thr, conf_thr;
-  double iou_mid;          // midpoint between iou_thr and the next float up (exact in double); 0 = no division-free test
-  int iou_mid_inclusive;   // a quotient exactly at the midpoint rounds to iou_thr (even mantissa), i.e. does not suppress
+  float q_lo, q_hi;        // iou_thr * (1 -+ 1e-6): an approximate quotient outside this band decides the test; 0 = off
+  const float* cls;        // [B,N,C1] (only for keep_class)
+  int C1;
+  int32_t* keep_class;     // [B,top_k] argmax over all classes of the kept priors, or NULL
   int64_t* keep;           // [B,top_k]
   int32_t* n_keep;         // [B]
   float4* keep_box;        // [B,top_k,4] or NULL
   float* keep_score;       // [B,top_k] or NULL
+  long long* trace;        // debug (-DTAUV_DEBUG, tools/detect_probe.py): clock64 of frame 0 at the phase boundaries
 };
+
+#ifdef TAUV_DEBUG
+#define NMS_TRACE(i) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[i] = clock64(); } while (0)
+static long long* g_nms_trace = nullptr;
+#else
+#define NMS_TRACE(i) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_frame_kernel(NmsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -209,16 +219,18 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_frame_kernel(NmsArgs a) {
   const int b = blockIdx.x;
   const int N = a.N;
   const int K = min(a.top_k, N);
-  int p2 = 1;
+  int p2 = 32;  // (at least one full tile of the pair test)
   while (p2 < K) p2 <<= 1;
-  unsigned long long* sel = reinterpret_cast<unsigned long long*>(smem_raw);       // [p2]
-  float* cor = reinterpret_cast<float*>(smem_raw + (size_t)p2 * 8);                 // [5][p2] SoA corners+area
+  float4* bxs = reinterpret_cast<float4*>(smem_raw);                                // [p2] boxes of the ranked priors
+  unsigned long long* sel = reinterpret_cast<unsigned long long*>(bxs + p2);       // [p2]
+  float* cor = reinterpret_cast<float*>(sel + p2);                                  // [5][p2] SoA corners+area
   uint32_t* hist = reinterpret_cast<uint32_t*>(cor + 5 * (size_t)p2);               // [2048]
   uint32_t* sup = hist;                                                              // reused: [p2/32]
   __shared__ uint32_t ctl[8];
   __shared__ int s_wsum[kNmsThreads / 32];
   const float* sc = a.score + (size_t)b * N;
 
+  NMS_TRACE(0);
   if (tid == 0) ctl[5] = 0;
   for (int i = tid; i < p2; i += kNmsThreads) sel[i] = 0ull;
   __syncthreads();
@@ -233,7 +245,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_frame_kernel(NmsArgs a) {
   bool ranked = false;
   if (N >= kNmsThreads && N <= kNmsThreads * kNmsRegs && K <= kNmsCand / 2) {
     unsigned long long* cand = reinterpret_cast<unsigned long long*>(hist);  // [kNmsCand] (the histogram is not in use)
-    __shared__ unsigned long long s_wthr[kNmsThreads / 32];
+    __shared__ uint32_t s_wthr[kNmsThreads / 32];
     float v[kNmsRegs];
 #pragma unroll
     for (int u = 0; u < kNmsRegs; ++u) {
@@ -248,46 +260,56 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_frame_kernel(NmsArgs a) {
                  : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
                    "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]),
                    "+f"(v[17]), "+f"(v[18]), "+f"(v[19]));
-    uint32_t mk = 0u, mi = 0u;  // the thread's best key and its (smallest) prior index
+    NMS_TRACE(1);
+    // from here on the registers hold the order-preserving keys; the threshold only needs the 32-bit keys (a tie on
+    // the key at the threshold admits a few more candidates, never fewer than K)
+    uint32_t mk = 0u;
 #pragma unroll
     for (int u = 0; u < kNmsRegs; ++u) {
-      const int i = u * kNmsThreads + tid;
-      const uint32_t k = i < N ? float_to_key(v[u]) : 0u;
-      if (k > mk || u == 0) {
-        mk = k;
-        mi = (uint32_t)i;
-      }
+      const uint32_t k = float_to_key(v[u]);
+      v[u] = __uint_as_float(k);
+      mk = u * kNmsThreads + tid < N ? max(mk, k) : mk;
     }
-    unsigned long long mx = make_composite(mk, mi);
-    for (int i = tid; i < kNmsCand; i += kNmsThreads) cand[i] = 0ull;
+    cand[tid] = 0ull;
+    static_assert(kNmsCand == kNmsThreads, "one candidate slot per thread");
+    uint32_t mx = mk;
 #pragma unroll
     for (int size = 2; size <= 32; size <<= 1) {  // warp bitonic sort, descending: lane 0 ends with the largest
       const bool desc = size == 32 || (lane & size) == 0;
 #pragma unroll
       for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        const unsigned long long y = __shfl_xor_sync(0xffffffffu, mx, stride);
-        const bool take_max = ((lane & stride) == 0) == desc;
-        mx = (take_max == (y > mx)) ? y : mx;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, mx, stride);
+        mx = (((lane & stride) == 0) == desc) ? max(mx, y) : min(mx, y);
       }
     }
-    const unsigned long long wthr = __shfl_sync(0xffffffffu, mx, (K + 31) / 32 - 1);
-    if (lane == 0) s_wthr[warp] = wthr;
+    // Threshold.  The ceil(K/32)-th largest maximum of a warp has that many maxima of its own warp at or above it, so the
+    // SMALLEST of these 32 values has >= K scores at or above it — but also about 3K (measured: 572 candidates for
+    // K = 200), and the ranking below is quadratic in that.  So every warp counts, in the other warps' sorted maxima,
+    // how many are at or above ITS value, and the LARGEST value with a count >= K is taken (~1.2K candidates).
+    __shared__ uint32_t s_max[32 * 33];  // warp w's sorted maxima at [w * 33 ...] (odd stride: the searches below do not collide)
+    const uint32_t wthr = __shfl_sync(0xffffffffu, mx, (K + 31) / 32 - 1);
+    s_max[warp * 33 + lane] = mx;
     __syncthreads();
-    unsigned long long T = s_wthr[lane];
+    {
+      const uint32_t* run = s_max + lane * 33;
+      int c = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long y = __shfl_xor_sync(0xffffffffu, T, o);
-      T = y < T ? y : T;
+      for (int step = 16; step > 0; step >>= 1)
+        if (run[c + step - 1] >= wthr) c += step;
+      if (run[c] >= wthr) ++c;
+      const int total = __reduce_add_sync(0xffffffffu, c);
+      if (lane == 0) s_wthr[warp] = total >= K ? wthr : 0u;
     }
+    __syncthreads();
+    NMS_TRACE(2);
+    const uint32_t T = __reduce_max_sync(0xffffffffu, s_wthr[lane]);
     // append without atomics (640 warp-level adds to one shared counter serialise for ~13 k cycles) and without votes:
     // every thread notes which of its scores qualify, one block-wide prefix over the counts gives it a private range
-    // of the list (the order inside the list does not matter: it is sorted next)
+    // of the list (the order inside the list does not matter: it is ranked next)
     uint32_t tm = 0u;
 #pragma unroll
-    for (int u = 0; u < kNmsRegs; ++u) {
-      const int i = u * kNmsThreads + tid;
-      if (i < N && make_composite(float_to_key(v[u]), (uint32_t)i) >= T) tm |= 1u << u;
-    }
+    for (int u = 0; u < kNmsRegs; ++u)
+      if (u * kNmsThreads + tid < N && __float_as_uint(v[u]) >= T) tm |= 1u << u;
     const unsigned my_cnt = (unsigned)__popc(tm);
     unsigned incl = my_cnt;
 #pragma unroll
@@ -312,14 +334,59 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_frame_kernel(NmsArgs a) {
     if (n_cand <= (unsigned)kNmsCand) {
 #pragma unroll
       for (int u = 0; u < kNmsRegs; ++u)
-        if ((tm >> u) & 1u) cand[base++] = make_composite(float_to_key(v[u]), (uint32_t)(u * kNmsThreads + tid));
+        if ((tm >> u) & 1u) cand[base++] = make_composite(__float_as_uint(v[u]), (uint32_t)(u * kNmsThreads + tid));
     }
     __syncthreads();
+    NMS_TRACE(3);
+#ifdef TAUV_DEBUG
+    if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[8] = n_cand;
+#endif
     if (n_cand <= (unsigned)kNmsCand) {  // (a plateau of equal scores can overflow the list: general path)
-      int pc = p2;
-      while (pc < (int)n_cand) pc <<= 1;
-      block_bitonic_sort_desc_reg<kNmsThreads>(cand, pc);
-      for (int r = tid; r < K; r += kNmsThreads) sel[r] = cand[r];
+      // Rank without a block-wide sort (its 10-15 shared-memory steps cost two 32-warp barriers each: 13 k cycles).
+      // Every warp sorts its own 32 candidates with shuffles; a candidate's rank is then its position in its own run
+      // plus, for every other run, the number of entries above it — a 6-probe binary search per run, all runs
+      // independent of each other.  Composites are distinct, so ranks are; the first K land in sel[].
+      const int nruns = ((int)n_cand + 31) >> 5;
+      unsigned long long x = 0ull;
+      if (warp < nruns) {
+        x = cand[tid];
+#pragma unroll
+        for (int size = 2; size <= 32; size <<= 1) {
+          const bool desc = size == 32 || (lane & size) == 0;
+#pragma unroll
+          for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, stride);
+            const bool take_max = ((lane & stride) == 0) == desc;
+            x = (take_max == (y > x)) ? y : x;
+          }
+        }
+        cand[tid] = x;
+      }
+      __syncthreads();
+      if (warp < nruns && x != 0ull) {  // (a composite is never 0: its low word is the complement of a prior index)
+        int rank = lane;
+        for (int r0 = 0; r0 < nruns; r0 += 4) {  // four searches at a time: their probes are independent loads
+          const unsigned long long* run[4];
+          int c[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            run[q] = cand + min(r0 + q, kNmsCand / 32 - 1) * 32;
+            c[q] = 0;
+          }
+#pragma unroll
+          for (int step = 16; step > 0; step >>= 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (run[q][c[q] + step - 1] > x) c[q] += step;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (run[q][c[q]] > x) ++c[q];
+            rank += (r0 + q == warp || r0 + q >= nruns) ? 0 : c[q];
+          }
+        }
+        if (rank < K) sel[rank] = x;
+      }
       ranked = true;
     }
     __syncthreads();  // (cand aliases hist / sup)
@@ -351,6 +418,17 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_frame_kernel(NmsArgs a) {
     block_bitonic_sort_desc_reg<kNmsThreads>(sel, p2);
   }
 
+  NMS_TRACE(4);
+  // the class rows of the ranked priors are wanted at the very end (argmax of the kept ones) and left the L2 long ago:
+  // ask for them now, so that the DRAM / TLB latency of ~K scattered rows runs under the phases in between
+  if (a.keep_class) {
+    const size_t row_bytes = (size_t)a.C1 * 4;
+    for (int r = warp; r < K; r += kNmsThreads / 32) {
+      const char* row = reinterpret_cast<const char*>(a.cls + ((size_t)b * N + composite_idx(sel[r])) * a.C1);
+      const size_t off = (size_t)lane * 128;
+      if (off < row_bytes + 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + min(off, row_bytes - 4)));
+    }
+  }
   // boxes of the ranked priors -> corners in shared memory (decoded on the fly in detect mode)
   for (int r = tid; r < K; r += kNmsThreads) {
     const uint32_t idx = composite_idx(sel[r]);
@@ -366,11 +444,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_frame_kernel(NmsArgs a) {
     const bool nan_corner = c.y0 != c.y0 || c.x0 != c.x0 || c.y1 != c.y1 || c.x1 != c.x1;
     cor[r] = c.y0; cor[p2 + r] = c.x0; cor[2 * p2 + r] = c.y1; cor[3 * p2 + r] = c.x1;
     cor[4 * p2 + r] = nan_corner ? __int_as_float(0x7fc00000) : c.area;
-    if (a.keep_box) a.keep_box[(size_t)b * a.top_k + r] = bx;  // ranked order for now; compacted below
+    bxs[r] = bx;
   }
   const int T32 = (K + 31) >> 5;
   for (int i = tid; i < T32; i += kNmsThreads) sup[i] = 0u;
   __syncthreads();
+  NMS_TRACE(5);
 
   // Fast NMS: column j is suppressed iff some earlier-ranked i < j has iou(i,j) > thr (nms.py:19-24; a NaN
   // IoU also suppresses because `NaN <= thr` is False).  Tiles (I <= J) of 32x32 pairs, one warp per tile.
@@ -382,97 +461,141 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_frame_kernel(NmsArgs a) {
     while (J * (J + 1) / 2 > t) --J;
     const int I = t - J * (J + 1) / 2;
     const int j = J * 32 + lane;
+    const int jc = min(j, K - 1);  // (lanes past the last column work on a valid one and are masked at the vote)
+    Corners cj;
+    cj.y0 = cor[jc]; cj.x0 = cor[p2 + jc]; cj.y1 = cor[2 * p2 + jc]; cj.x1 = cor[3 * p2 + jc]; cj.area = cor[4 * p2 + jc];
+    // `fl(inter / union) <= thr` without the division (its ~60 instructions, needed by some lane on almost every step,
+    // were a third of the kernel): inter * rcp.approx(union) is within 2^-22 of the real quotient, so outside a band of
+    // 1e-6 around thr it decides the rounded quotient's test too.  Pairs inside the band, and every special case (NaN
+    // corners carry a NaN area; empty, tiny, huge or infinite unions), are noted and take the IEEE division afterwards.
+    // The 32 rows of the tile are straight-line code (no branch between them: their loads and reciprocals overlap).
+    const bool band = a.q_hi > 0.0f;
     bool s = false;
-    if (j < K) {
-      Corners cj;
-      cj.y0 = cor[j]; cj.x0 = cor[p2 + j]; cj.y1 = cor[2 * p2 + j]; cj.x1 = cor[3 * p2 + j]; cj.area = cor[4 * p2 + j];
-      const int i_end = min(I * 32 + 32, j);  // strictly upper triangle
-      for (int i = I * 32; i < i_end; ++i) {
-        Corners ci;
-        ci.y0 = cor[i]; ci.x0 = cor[p2 + i]; ci.y1 = cor[2 * p2 + i]; ci.x1 = cor[3 * p2 + i]; ci.area = cor[4 * p2 + i];
-        // `fl(inter / union) <= thr` without the division: the rounded quotient is <= thr exactly when the real quotient
-        // is below the midpoint m between thr and the next float (at m itself: round-to-even decides), and
-        // inter <= m * union is exact in double (24 x 25 significant bits).  No NaN-propagating min/max either: boxes with
-        // a NaN corner carry a NaN area, which fails `uni > 0` like every other special case (empty or infinite union)
-        // and takes the IEEE path below.  (The divide path is ~60 instructions, and with 32 different columns per warp
-        // some lane needed it on almost every step: this loop was a third of the kernel.)
-        {
-          const float ih = fmaxf(__fsub_rn(fminf(ci.y1, cj.y1), fmaxf(ci.y0, cj.y0)), 0.0f);
-          const float iw = fmaxf(__fsub_rn(fminf(ci.x1, cj.x1), fmaxf(ci.x0, cj.x0)), 0.0f);
-          const float inter = __fmul_rn(ih, iw);
-          const float uni = __fsub_rn(__fadd_rn(ci.area, cj.area), inter);
-          if (a.iou_mid > 0.0 && uni > 0.0f && uni < __int_as_float(0x7f800000)) {
-            const double lhs = (double)inter, rhs = a.iou_mid * (double)uni;
-            s = s || !(a.iou_mid_inclusive ? lhs <= rhs : lhs < rhs);
-            continue;
-          }
-        }
-        const float iou = iou_pair(ci, cj);
-        s = s || !(iou <= a.iou_thr);
-      }
+    unsigned exact = 0u;
+#pragma unroll 8
+    for (int t = 0; t < 32; ++t) {
+      const int i = I * 32 + t;  // (< p2: rows past K hold stale values and are masked by i < j < K)
+      const float y0 = cor[i], x0 = cor[p2 + i], y1 = cor[2 * p2 + i], x1 = cor[3 * p2 + i], ar = cor[4 * p2 + i];
+      const float ih = fmaxf(__fsub_rn(fminf(y1, cj.y1), fmaxf(y0, cj.y0)), 0.0f);
+      const float iw = fmaxf(__fsub_rn(fminf(x1, cj.x1), fmaxf(x0, cj.x0)), 0.0f);
+      const float inter = __fmul_rn(ih, iw);
+      const float uni = __fsub_rn(__fadd_rn(ar, cj.area), inter);
+      float rcp;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(uni));
+      const float q = __fmul_rn(inter, rcp);
+      const bool live = i < j;  // strictly upper triangle
+      const bool fast = band && uni > 1e-30f && uni < 1e30f;
+      const bool above = fast && q > a.q_hi, below = fast && q < a.q_lo;
+      s = s || (live && above);
+      exact |= (live && !above && !below ? 1u : 0u) << t;
     }
+    while (exact) {  // (rare; lane-dependent trip count: no warp-level operation inside)
+      const int i = I * 32 + __ffs(exact) - 1;
+      exact &= exact - 1u;
+      Corners ci;
+      ci.y0 = cor[i]; ci.x0 = cor[p2 + i]; ci.y1 = cor[2 * p2 + i]; ci.x1 = cor[3 * p2 + i]; ci.area = cor[4 * p2 + i];
+      s = s || !(iou_pair(ci, cj) <= a.iou_thr);
+    }
+    s = s && j < K;
     const unsigned bal = __ballot_sync(0xffffffffu, s);
     if (lane == 0 && bal) atomicOr(&sup[J], bal);
   }
   __syncthreads();
 
-  // ordered compaction of the survivors
+  NMS_TRACE(6);
+  // ordered compaction of the survivors (the corner arrays are dead: their space lists the kept prior indices)
+  uint32_t* kidx = reinterpret_cast<uint32_t*>(cor);
   int base = 0;
   const float conf_thr = a.conf_thr;
   for (int start = 0; start < K; start += kNmsThreads) {
     const int r = start + tid;
     bool kp = false;
     unsigned long long c = 0ull;
-    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < K) {
       c = sel[r];
       const float conf = key_to_float(composite_key(c));
       kp = !((sup[r >> 5] >> (r & 31)) & 1u) && (conf >= conf_thr);
-      if (a.keep_box) bx = a.keep_box[(size_t)b * a.top_k + r];
     }
     const unsigned bal = __ballot_sync(0xffffffffu, kp);
     if (lane == 0) s_wsum[warp] = __popc(bal);
     __syncthreads();
     int pos = base + __popc(bal & ((1u << lane) - 1u));
-    int tot = 0;
-    for (int w = 0; w < kNmsThreads / 32; ++w) {
-      if (w < warp) pos += s_wsum[w];
-      tot += s_wsum[w];
+    int tot;
+    {
+      static_assert(kNmsThreads / 32 == 32, "one lane per warp count");
+      const int w = s_wsum[lane];
+      int wincl = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, wincl, o);
+        if (lane >= o) wincl += y;
+      }
+      pos += __shfl_sync(0xffffffffu, wincl - w, warp);
+      tot = __shfl_sync(0xffffffffu, wincl, 31);
     }
     if (kp) {
       a.keep[(size_t)b * a.top_k + pos] = (int64_t)composite_idx(c);
       if (a.keep_score) a.keep_score[(size_t)b * a.top_k + pos] = key_to_float(composite_key(c));
+      if (a.keep_box) a.keep_box[(size_t)b * a.top_k + pos] = bxs[r];
+      kidx[pos] = composite_idx(c);
     }
-    __syncthreads();  // every thread has read its ranked box before anyone overwrites a slot
-    if (kp && a.keep_box) a.keep_box[(size_t)b * a.top_k + pos] = bx;
     base += tot;
     __syncthreads();
   }
   if (tid == 0) a.n_keep[b] = base;
-}
-
-// argmax over ALL classes for the kept priors (yolact_node.py:129 / evaluate_batch.py:93-95)
-__global__ void keep_class_kernel(const float* __restrict__ cls, const int64_t* __restrict__ keep,
-                                  const int32_t* __restrict__ n_keep, int N, int C1, int top_k,
-                                  int32_t* __restrict__ keep_class) {
-  const int b = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (r >= n_keep[b]) return;
-  const float* x = cls + ((size_t)b * N + keep[(size_t)b * top_k + r]) * C1;
-  float best_v = TAUV_NEG_INF;
-  int best_i = 0x7fffffff;
-  for (int j = lane; j < C1; j += 32) {
-    const float t = x[j];
-    if (t > best_v) { best_v = t; best_i = j; }
-  }
+  NMS_TRACE(7);
+  // argmax over ALL classes of the kept priors (yolact_node.py:129 / evaluate_batch.py:93-95): one warp per kept prior,
+  // eight priors' rows in flight per warp (the rows left the L2 long ago: one DRAM round trip instead of eight)
+  if (a.keep_class) {
+    const int C1 = a.C1;
+    const float* cls_b = a.cls + (size_t)b * N * C1;
+    int32_t* kc = a.keep_class + (size_t)b * a.top_k;
+    if (C1 <= 96) {
+      for (int r0 = warp; r0 < base; r0 += 8 * (kNmsThreads / 32)) {
+        float x[8][3];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-    if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
+        for (int q = 0; q < 8; ++q) {
+          const int r = r0 + q * (kNmsThreads / 32);
+          const float* row = cls_b + (size_t)kidx[min(r, base - 1)] * C1;
+#pragma unroll
+          for (int t = 0; t < 3; ++t) x[q][t] = lane + 32 * t < C1 ? __ldg(row + lane + 32 * t) : TAUV_NEG_INF;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int r = r0 + q * (kNmsThreads / 32);
+          if (r >= base) break;  // (warp-uniform)
+          float best_v = TAUV_NEG_INF;
+          int best_i = 0x7fffffff;
+#pragma unroll
+          for (int t = 0; t < 3; ++t)
+            if (x[q][t] > best_v) { best_v = x[q][t]; best_i = lane + 32 * t; }
+          // (best_v is never NaN: `>` does not admit one) first maximum across the lanes with two warp reductions
+          const uint32_t key = float_to_key(best_v);
+          const uint32_t top = __reduce_max_sync(0xffffffffu, key);
+          const int first = __reduce_min_sync(0xffffffffu, key == top ? best_i : 0x7fffffff);
+          if (lane == 0) kc[r] = first == 0x7fffffff ? 0 : first;
+        }
+      }
+    } else {
+      for (int r = warp; r < base; r += kNmsThreads / 32) {
+        const float* row = cls_b + (size_t)kidx[r] * C1;
+        float best_v = TAUV_NEG_INF;
+        int best_i = 0x7fffffff;
+        for (int j = lane; j < C1; j += 32) {
+          const float t = row[j];
+          if (t > best_v) { best_v = t; best_i = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+          if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
+        }
+        if (lane == 0) kc[r] = best_i == 0x7fffffff ? 0 : best_i;
+      }
+    }
   }
-  if (lane == 0) keep_class[(size_t)b * top_k + r] = best_i == 0x7fffffff ? 0 : best_i;
+  NMS_TRACE(9);
 }
 
 static int launch_scores(const float* cls, long long rows, int C1, float* score, int32_t* argmax_all, cudaStream_t st) {
@@ -517,9 +640,9 @@ static int launch_scores(const float* cls, long long rows, int C1, float* score,
 }
 
 static size_t nms_smem(int K) {
-  int p2 = 1;
+  int p2 = 32;
   while (p2 < K) p2 <<= 1;
-  return (size_t)p2 * 8 + (size_t)p2 * 5 * 4 + kRadixBins * 4;
+  return (size_t)p2 * 16 + (size_t)p2 * 8 + (size_t)p2 * 5 * 4 + kRadixBins * 4;
 }
 
 static int run_nms(const float* cls, const float* box, const float* enc, const float* anchor, int anchor_batch, float v0,
@@ -537,25 +660,22 @@ static int run_nms(const float* cls, const float* box, const float* enc, const f
   NmsArgs a;
   a.score = score; a.box = (const float4*)box; a.enc = (const float4*)enc; a.anchor = (const float4*)anchor;
   a.anchor_batch = anchor_batch; a.v0 = v0; a.v1 = v1; a.N = N; a.top_k = top_k; a.iou_thr = iou_thr; a.conf_thr = conf_thr;
-  a.iou_mid = 0.0;
-  a.iou_mid_inclusive = 0;
-  if (iou_thr > 1e-30f && iou_thr < 1e30f) {  // (normal, positive: the midpoint construction below is exact)
-    const float up = nextafterf(iou_thr, INFINITY);
-    uint32_t bits;
-    memcpy(&bits, &iou_thr, sizeof(bits));
-    a.iou_mid = ((double)iou_thr + (double)up) * 0.5;
-    a.iou_mid_inclusive = (bits & 1u) == 0u;
+  a.q_lo = a.q_hi = 0.0f;
+  if (iou_thr > 1e-30f && iou_thr < 1e30f) {  // (normal, positive: the band below is well inside the float range)
+    a.q_lo = (float)((double)iou_thr * (1.0 - 1e-6));
+    a.q_hi = (float)((double)iou_thr * (1.0 + 1e-6));
   }
+  a.cls = cls; a.C1 = C1; a.keep_class = keep_class;
   a.keep = keep; a.n_keep = n_keep; a.keep_box = (float4*)keep_box; a.keep_score = keep_score;
+#ifdef TAUV_DEBUG
+  a.trace = g_nms_trace;
+#else
+  a.trace = nullptr;
+#endif
   const size_t smem = nms_smem(top_k < N ? top_k : N);
   TAUV_CUDA(ensure_dynamic_smem((const void*)(nms_frame_kernel), smem));
   nms_frame_kernel<<<n_frames, kNmsThreads, smem, st>>>(a);
   TAUV_LAUNCH_CHECK("nms_frame_kernel");
-  if (keep_class) {
-    dim3 grid((top_k * 32 + 255) / 256, n_frames);
-    keep_class_kernel<<<grid, 256, 0, st>>>(cls, keep, n_keep, N, C1, top_k, keep_class);
-    TAUV_LAUNCH_CHECK("keep_class_kernel");
-  }
   return 0;
 }
 
@@ -599,3 +719,8 @@ extern "C" int tauv_yolact_detect(const float* cls, const float* enc, const floa
                  confidence_threshold, keep, n_keep, keep_box, keep_score, keep_class, workspace, workspace_bytes,
                  (cudaStream_t)stream);
 }
+
+#ifdef TAUV_DEBUG
+// Debug hook for tools/detect_probe.py (only in -DTAUV_DEBUG builds; process-global, not thread-safe).
+extern "C" void tauv_debug_nms_trace(long long* buf) { tauv::g_nms_trace = buf; }
+#endif
