@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_frame_kernel(NmsArgs a) {
   __shared__ int s_wsum[kNmsThreads / 32];
   const float* sc = a.score + (size_t)b * N;
 
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // (the scores of the launch before; no-op without the attribute)
   NMS_TRACE(0);
   if (tid == 0) ctl[5] = 0;
   for (int i = tid; i < p2; i += kNmsThreads) sel[i] = 0ull;
@@ -674,7 +675,21 @@ static int run_nms(const float* cls, const float* box, const float* enc, const f
 #endif
   const size_t smem = nms_smem(top_k < N ? top_k : N);
   TAUV_CUDA(ensure_dynamic_smem((const void*)(nms_frame_kernel), smem));
-  nms_frame_kernel<<<n_frames, kNmsThreads, smem, st>>>(a);
+  {
+    // programmatic dependent launch: the CTAs are set up while the scores kernel drains and wait (griddepcontrol.wait,
+    // first thing in the kernel) for its completion and memory flush — the launch latency leaves the critical path
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n_frames);
+    cfg.blockDim = dim3(kNmsThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TAUV_CUDA(cudaLaunchKernelEx(&cfg, nms_frame_kernel, a));
+  }
   TAUV_LAUNCH_CHECK("nms_frame_kernel");
   return 0;
 }
