@@ -1631,6 +1631,12 @@ __global__ void gather_at_kernel(const float* __restrict__ src, long long sb, lo
   out[t] = src[b * sb + sel * ssel + c * sc + index[j * 2] * sy + index[j * 2 + 1] * sx];
 }
 
+}  // namespace tauv
+
+#include "centernet_select.cuh"  // round 2: block maxima + select (the default decode path)
+
+namespace tauv {
+
 // ----------------------------------------------------------------------------------------------
 // Host entry points
 // ----------------------------------------------------------------------------------------------
@@ -1798,6 +1804,10 @@ static int run_stage2(int B, int C, int H, int W, int k, int mode, int64_t* inde
 
 static int run_topk(const float* hm, int B, int C, int H, int W, int k, int mode, int64_t* index, int64_t* label,
                     float* score, const BoxArgs& box, void* ws, size_t ws_bytes, cudaStream_t st) {
+  SelPlan sp;
+  if (mode == TAUV_TOPK_SIGMOID_PEAK && (uintptr_t)hm % 16 == 0 && select_plan(B, C, H, W, k, &sp) &&
+      !debug_env("TAUV_OLD_DECODE"))
+    return run_select_decode(hm, B, C, H, W, k, index, label, score, box, ws, ws_bytes, sp, st);
   const FuseOut fo{index, label, score, &box};
   bool fused = false;
   if (int e = run_stage1(hm, B, C, H, W, k, mode, ws, ws_bytes, st, &fo, &fused)) return e;
@@ -1834,7 +1844,10 @@ extern "C" size_t tauv_heatmap_topk_workspace_bytes(int B, int C, int H, int W, 
   TopkPlan p;
   // alignment only affects the load path, never the sizes
   make_plan(B, C, H, W, k, nullptr, &p);
-  return p.cand_bytes + p.count_bytes + p.state_bytes;
+  size_t need = p.cand_bytes + p.count_bytes + p.state_bytes;
+  SelPlan sp;
+  if (select_plan(B, C, H, W, k, &sp) && sp.bm_bytes + sp.bm2_bytes > need) need = sp.bm_bytes + sp.bm2_bytes;
+  return need;
 }
 
 extern "C" int tauv_heatmap_topk(const float* heatmap, int B, int C, int H, int W, int k, int mode, int64_t* index,

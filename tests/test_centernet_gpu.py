@@ -328,6 +328,71 @@ def test_full_batch_properties(cn):
     assert_equal(idx, idx2), assert_equal(lab, lab2), assert_equal(sc, sc2)
 
 
+def _smooth_ranked_logits(B, C, H, W, seed, box=9, passes=1, lo=-6.0, hi=3.0):
+    """A smooth random field (box-filtered noise) whose cells carry the values of separated_logits' ramp in the
+    field's rank order: few 3x3 peaks, hot regions that span many 4x8 blocks, and still no near-ties at the top."""
+    g = synth.gen(seed)
+    ramp = synth.separated_logits(1, C, H, W, seed, lo=lo, hi=hi).flatten().sort().values
+    out = torch.empty((B, C * H * W), dtype=torch.float32)
+    for b in range(B):
+        f = torch.randn((1, C, H + passes * (box - 1), W + passes * (box - 1)), generator=g, dtype=torch.float64)
+        for _ in range(passes):
+            f = torch.nn.functional.avg_pool2d(f, box, 1)
+        f = f.flatten() + 1e-9 * torch.rand(f.numel(), generator=g, dtype=torch.float64)
+        out[b, f.argsort()] = ramp
+    return out.reshape(B, C, H, W)
+
+
+@pytest.mark.parametrize("B,C,H,W,k,box,passes", [(2, 4, 64, 64, 50, 9, 1), (1, 8, 128, 128, 100, 5, 1),
+                                                  (1, 2, 96, 160, 256, 15, 1), (2, 6, 128, 128, 100, 9, 3)])
+def test_select_path_smooth_fields(cn, B, C, H, W, k, box, passes):
+    """Block maxima that are mostly NOT peaks (smooth maps): the select pass must lower its threshold / fall back to
+    the exhaustive segments and still return the reference's ranked peaks exactly."""
+    logits = _smooth_ranked_logits(B, C, H, W, seed=300 + box, box=box, passes=passes)
+    oi, ol, osc = O.heatmap_detect(O.heatmap_nms(torch.sigmoid(logits), 3), k)
+    idx, lab, sc = cn.D.heatmap_peaks(logits.to(cn.dev), k)
+    assert_equal(idx, oi), assert_equal(lab, ol), assert_close(sc, osc, what="score")
+
+
+@pytest.mark.parametrize("B,C,H,W,k", [(2, 3, 13, 12, 17), (1, 1, 1, 8, 3), (3, 2, 41, 36, 64), (1, 7, 50, 20, 256),
+                                       (2, 16, 128, 128, 256), (5, 1, 128, 128, 100), (1, 80, 128, 128, 1)])
+def test_select_path_shapes(cn, B, C, H, W, k):
+    """Aligned maps with W % 4 == 0 take the block-maxima + select path: partial row groups (H % 8 != 0), rows
+    narrower than a warp of blocks, one-plane frames (block-level threshold), k at the path's limit, k = 1."""
+    logits = synth.separated_logits(B, C, H, W, seed=500 + H + k)
+    oi, ol, osc = O.heatmap_detect(O.heatmap_nms(torch.sigmoid(logits), 3), k)
+    idx, lab, sc = cn.D.heatmap_peaks(logits.to(cn.dev), k)
+    assert_equal(idx, oi), assert_equal(lab, ol), assert_close(sc, osc, what="score")
+
+
+def test_select_path_monotone_and_sparse(cn):
+    """Maps with almost no peaks: a ramp along the flat index (one peak per plane: the last cell) and a map that is
+    -200 except three cells — fewer than k positive peaks, so the exhaustive pass runs and the fillers follow."""
+    ramp = torch.linspace(-4.0, 4.0, 2 * 32 * 32).reshape(1, 2, 32, 32)
+    x = torch.full((1, 3, 24, 40), -200.0)
+    x[0, 0, 5, 7], x[0, 2, 23, 39], x[0, 1, 0, 0] = 0.5, 1.5, -1.0
+    for m, k in ((ramp, 20), (x, 12)):
+        oi, ol, osc = O.heatmap_detect(O.heatmap_nms(torch.sigmoid(m), 3), k)
+        idx, lab, sc = cn.D.heatmap_peaks(m.to(cn.dev), k)
+        assert_equal(idx, oi), assert_equal(lab, ol), assert_close(sc, osc, what="score")
+
+
+def test_select_path_repeatable_under_load(cn):
+    """Run-to-run determinism of the two-launch path (programmatic dependent launch, shared-memory appends in
+    arbitrary order): 20 back-to-back runs on plateau-heavy and natural frames give identical outputs."""
+    q = torch.round(synth.natural_logits(6, 8, 64, 64, seed=11) * 2) / 2
+    nat = synth.natural_logits(6, 8, 64, 64, seed=12)
+    for m in (q.to(cn.dev), nat.to(cn.dev)):
+        first = cn.D.heatmap_peaks(m, 100)
+        for _ in range(20):
+            again = cn.D.heatmap_peaks(m, 100)
+            for a, b in zip(first, again):
+                assert_equal(a, b)
+    oi, ol, osc = O.heatmap_detect(O.heatmap_nms(torch.sigmoid(q), 3), 100)
+    idx, lab, sc = cn.D.heatmap_peaks(q.to(cn.dev), 100)
+    assert_equal(idx, oi), assert_equal(lab, ol), assert_close(sc, osc, what="score")
+
+
 # ---- target encode -----------------------------------------------------------------------------------------------
 
 def test_encode_golden(cn):
