@@ -1956,4 +1956,6 @@ extern "C" int tauv_centernet_decode_stage2(int B, int C, int H, int W, int k, c
 // Debug hook for tools/tile_trace.py (only in -DTAUV_DEBUG builds; the default library exports nothing the header does
 // not declare): per-item timestamps of the next tile_topk launches land in `buf` (8 int64 per item; NULL = off).
 extern "C" void tauv_debug_tile_trace(long long* buf) { tauv::g_debug_trace = buf; }
+// the same for select_kernel (tools/select_trace.py): 16 int64 per frame
+extern "C" void tauv_debug_select_trace(long long* buf) { tauv::g_sel_trace = buf; }
 #endif

@@ -31,14 +31,33 @@ constexpr int kBmRows = 8;            // rows of a block (a block = 4 columns x 
 constexpr int kBmThreads = 256;
 constexpr int kSelThreads = 1024;
 constexpr int kSelHotCap = 1024;      // hot groups / hot blocks per attempt
-constexpr int kSelCellCap = 2048;     // hot cells per attempt
 constexpr int kSelCandCap = 2048;     // candidate list (final composites)
 constexpr int kSelMaxK = 256;
 constexpr int kSelSmallSeg = (kSelCandCap - 2 * kSelMaxK) / 32;  // blocks per exhaustive sub-step that cannot overflow
 
+// Division by a launch constant as multiply-high + shift (x < 2^31; the scheme of CUTLASS' FastDivmod): the block and
+// cell index arithmetic of the select pass sits on single-warp dependent chains, where a 32-bit division costs ~100 cycles.
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{d, 0u, 0u};
+  if (d > 1) {
+    int lg = 0;
+    while ((1ull << lg) < d) ++lg;
+    const int p = 31 + lg;
+    f.mul = (uint32_t)(((1ull << p) + d - 1) / d);
+    f.shr = (uint32_t)(p - 32);
+  }
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv_u32(uint32_t x, const FastDiv& f) {
+  return f.d == 1u ? x : (__umulhi(x, f.mul) >> f.shr);
+}
+
 struct BmArgs {
   const float* hm;
-  float* bm;    // [B][n_blk]  block maxima
+  float* bm;    // [B][32 G]   block maxima (n_blk per frame, rows padded to whole groups)
   float* bm2;   // [B][G]      maxima of 32 consecutive blocks
   int C, H, W, W4, n_rg, n_blk, G;
 };
@@ -52,12 +71,43 @@ struct SelArgs {
   int64_t* out_label;
   float* out_score;
   BoxArgs box;
+  FastDiv dW4, dNrg, dHW, dW;  // divisions by W/4, rows groups per plane, H*W, W
+  long long* trace;  // -DTAUV_DEBUG builds only (tools/select_trace.py): 32 int64 per frame, else NULL
 };
+
+#ifdef TAUV_DEBUG
+static long long* g_sel_trace = nullptr;
+#define SEL_STAMP(i)                                                  \
+  do {                                                                \
+    if (a.trace && threadIdx.x == 0) {                                \
+      long long t_;                                                   \
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));           \
+      a.trace[(size_t)blockIdx.x * 32 + sel_rep * 16 + (i)] = t_;                   \
+    }                                                                 \
+  } while (0)
+#define SEL_NOTE(i, v)                                                \
+  do {                                                                \
+    if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 32 + sel_rep * 16 + (i)] = (long long)(v); \
+  } while (0)
+#else
+#define SEL_STAMP(i) do {} while (0)
+#define SEL_NOTE(i, v) do {} while (0)
+#endif
+
+__device__ __forceinline__ void st_keep(float* p, float v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(policy) : "memory");
+}
 
 __global__ void __launch_bounds__(kBmThreads) block_max_kernel(const __grid_constant__ BmArgs a) {
   // the dependent launch (select_kernel) may be set up as soon as every CTA of this grid has started; it waits for
   // this grid's completion and memory flush before it reads anything
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // this grid is itself launched programmatically: its CTAs are set up while the kernel before it in the stream (the
+  // producer of the logits) drains; wait for that kernel's completion and memory flush before the first load
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // the summaries are read again in a few tens of microseconds: keep them in L2 while the read-once logits stream through
+  uint64_t keep;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
   const int b = blockIdx.y;
   const uint32_t i = blockIdx.x * (uint32_t)kBmThreads + threadIdx.x;  // block index inside the frame
   float m = TAUV_NEG_INF;
@@ -79,30 +129,37 @@ __global__ void __launch_bounds__(kBmThreads) block_max_kernel(const __grid_cons
     }
 #pragma unroll
     for (int r = 0; r < kBmRows; ++r) m = fmaxf(m, fmaxf(fmaxf(x[r].x, x[r].y), fmaxf(x[r].z, x[r].w)));
-    a.bm[(size_t)b * a.n_blk + i] = m;
+    st_keep(&a.bm[(size_t)b * a.G * 32 + i], m, keep);
   }
   float g = m;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, o));
-  if ((threadIdx.x & 31) == 0 && valid) a.bm2[(size_t)b * a.G + (i >> 5)] = g;
+  if ((threadIdx.x & 31) == 0 && valid) st_keep(&a.bm2[(size_t)b * a.G + (i >> 5)], g, keep);
 }
 
+constexpr int kSelCellCap = 2048;     // hot cells per attempt
+
 struct __align__(16) SelShared {
-  union {
-    struct {
-      unsigned long long keys[kSelThreads];  // T selection: composite keys of the strided maxima; later: the ranked keys
-      uint32_t hist[kRadixBins];             // radix histogram; later: filler flags
-    } s;
-    unsigned long long cell[kSelCellCap];    // hot cells: logit bits << 32 | flat index (between collect and phase B)
-  } u;
-  unsigned long long cand[kSelCandCap];      // peaks: final composites (score key << 32 | ~flat index)
-  uint32_t hot[kSelHotCap];
+  struct {
+    unsigned long long keys[kSelThreads];  // later: the ranked keys
+    uint32_t hist[kRadixBins];             // T selection: 1024 bins + per-warp columns; exhaustive path: radix histogram;
+  } s;                                     // later: filler flags
+  unsigned long long cand[kSelCandCap];    // peaks: final composites (score key << 32 | ~flat index)
+  uint32_t hot[kSelHotCap];                // fast path: flat index of the block's first cell; exhaustive path: block ids
+  uint32_t hotpos[kSelHotCap];             // fast path: first row << 16 | first column
   uint32_t hgrp[kSelHotCap];
+  uint32_t cell[kSelCellCap];              // hot block ids while they are collected; then the hot cells: flat index,
+  uint32_t cellpos[kSelCellCap];           //   row << 16 | column,
+  float cellx[kSelCellCap];                //   logit,
+  float cellm[kSelCellCap];                //   maximum of the eight neighbours
   uint32_t ctl[8];
-  int n_hgrp, n_hot, n_cell, n_cand, n_out, first_below, flag;
+  int n_hgrp, n_hot, n_xhot, n_xcell, n_cand, n_zero, first_below, flag;
+  uint32_t T_key;
   float s_k, xc_f;
   unsigned long long thr_c;
 };
+
+__device__ __forceinline__ void sel_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ bool sel_is_peak(float x, float m) {
   bool peak = x >= m;
@@ -126,43 +183,116 @@ __device__ __forceinline__ int sel_append(int* counter, bool want) {
   return want ? base + __popc(bal & ((1u << lane) - 1u)) : -1;
 }
 
-// Rank the n candidates (distinct non-zero composites) by counting, write the min(n, k) best in order, and leave the
-// k-th best score in sh->s_k (only meaningful when n >= k).  Returns npos = min(n, k).  All threads call this.
-__device__ __noinline__ int sel_rank_emit(const SelArgs& a, SelShared* sh, int b, int n) {
+// Ordered, contention-free collection: list[...] <- the indices i < n with !(src[i] < T).  The ballots of up to eight
+// rounds are kept in registers, so a warp needs ONE add on the shared counter per eight rounds (same-address
+// shared-memory atomics serialise at ~20 cycles each: one per hit was most of this kernel's time).
+__device__ __forceinline__ void sel_collect(const float* __restrict__ src, int n, float T_f, int* counter, uint32_t* list,
+                                            int cap) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int c0 = 0; c0 < n; c0 += 8 * kSelThreads) {
+    uint32_t m[8];
+    int tot = 0;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      m[it] = 0u;
+      if (c0 + it * kSelThreads < n) {
+        const int i = c0 + it * kSelThreads + tid;
+        m[it] = __ballot_sync(0xffffffffu, i < n && !(src[i < n ? i : 0] < T_f));
+        tot += __popc(m[it]);
+      }
+    }
+    int base = 0;
+    if (lane == 0 && tot) base = atomicAdd(counter, tot);
+    base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      if ((m[it] >> lane) & 1u) {
+        const int slot = base + __popc(m[it] & ((1u << lane) - 1u));
+        if (slot < cap) list[slot] = (uint32_t)(c0 + it * kSelThreads + tid);
+      }
+      base += __popc(m[it]);
+    }
+  }
+}
+
+// a cell that reached T, with the maximum of its neighbours: peak test, sigmoid, final key (0: not a peak / zero score).
+// Dense: one thread per hot cell, a few warps per frame.
+__device__ __noinline__ unsigned long long sel_test_cell(const SelArgs& a, SelShared* sh, int b, int i) {
+  const float x = sh->cellx[i];
+  if (!sel_is_peak(x, sh->cellm[i])) return 0ull;
+  const unsigned long long fin = sel_final_key(x, sh->cell[i]);
+  if (fin != 0ull && a.box.enabled) {  // the gathers of the emit phase: get their lines on the way now
+    const uint32_t pos = sh->cellpos[i];
+    const int iy = (int)(pos >> 16), ix = (int)(pos & 0xffffu);
+    const float* ps = a.box.size + b * a.box.ss[0] + iy * a.box.ss[1] + ix * a.box.ss[2];
+    sel_prefetch_l2(ps);
+    sel_prefetch_l2(ps + a.box.ss[3]);
+    if (a.box.mode == TAUV_BOX_DECODE) {
+      const float* po = a.box.offset + b * a.box.os[0] + iy * a.box.os[1] + ix * a.box.os[2];
+      sel_prefetch_l2(po);
+      sel_prefetch_l2(po + a.box.os[3]);
+    }
+  }
+  return fin;
+}
+
+// Rank the candidates cand[0, n) (distinct composites; 0 = empty slot) by counting, write the min(valid, k) best in
+// order.  When T_key != 0 the last warp meanwhile checks that nothing below the threshold could have made it
+// (sh->flag = 1 if it could): every logit below T must have a score strictly below the k-th best.  Returns
+// npos = min(valid, k).  All threads call this.
+__device__ __noinline__ int sel_rank_emit(const SelArgs& a, SelShared* sh, int b, int n, uint32_t T_key) {
   const int tid = threadIdx.x, k = a.k;
-  unsigned long long* ranked = sh->u.s.keys;
-  const int npos = n < k ? n : k;
-  for (int i0 = 0; i0 < n; i0 += kSelThreads / 8) {
-    const int i = i0 + (tid >> 3), part = tid & 7;
-    const unsigned long long my = i < n ? sh->cand[i] : ~0ull;
+  unsigned long long* ranked = sh->s.keys;
+  const int tpc = n <= kSelThreads / 8 ? 8 : 4;  // threads per candidate
+  const int n2 = (n + 1) >> 1;  // (the caller has zeroed cand[n] when n is odd)
+  for (int i0 = 0; i0 < n; i0 += kSelThreads / tpc) {
+    const int i = i0 + tid / tpc, part = tid & (tpc - 1);
+    const unsigned long long my = i < n ? sh->cand[i] : 0ull;
     int cnt = 0;
-    for (int j = part; j < n; j += 8) cnt += sh->cand[j] > my ? 1 : 0;
+    const ulonglong2* c2 = reinterpret_cast<const ulonglong2*>(sh->cand);  // (cand[n] = 0 when n is odd)
+#pragma unroll 4
+    for (int j = part; j < n2; j += tpc) {
+      const ulonglong2 v = c2[j];
+      cnt += (v.x > my ? 1 : 0) + (v.y > my ? 1 : 0);
+    }
     cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
     cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
-    if (i < n && part == 0 && cnt < k) ranked[cnt] = my;
+    if (tpc == 8) cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+    if (i < n && part == 0) {
+      if (my == 0ull) atomicAdd(&sh->n_zero, 1);
+      else if (cnt < k) ranked[cnt] = my;
+    }
   }
   __syncthreads();
-  const long long hw_elems = (long long)a.H * a.W;
+  const int valid = n - sh->n_zero;
+  const int npos = valid < k ? valid : k;
+  const uint32_t hw_elems = (uint32_t)(a.H * a.W);
   if (tid < npos) {
     const unsigned long long c = ranked[tid];
     const uint32_t flat = composite_idx(c);
     const float s = key_to_float(composite_key(c));
-    const long long lab = flat / hw_elems;
-    const long long rem = flat - lab * hw_elems;
-    const int iy = (int)(rem / a.W), ix = (int)(rem - (long long)iy * a.W);
+    const uint32_t lab = fdiv_u32(flat, a.dHW);
+    const uint32_t rem = flat - lab * hw_elems;
+    const int iy = (int)fdiv_u32(rem, a.dW), ix = (int)(rem - (uint32_t)iy * (uint32_t)a.W);
     const long long slot = (long long)b * k + tid;
     a.out_index[slot * 2 + 0] = iy;
     a.out_index[slot * 2 + 1] = ix;
     a.out_label[slot] = lab;
     a.out_score[slot] = s;
-    if (tid == k - 1) sh->s_k = s;
     if (a.box.enabled) {
       box_one(a.box, b, slot, iy, ix);
       if (s < a.box.thr) atomicMin(&sh->first_below, tid);
     }
+  } else if (tid == kSelThreads - 32 && T_key != 0u) {
+    int bad = 1;
+    if (valid >= k) {
+      const uint32_t rk = reject_key_for_score(key_to_float(composite_key(ranked[k - 1])));
+      bad = (rk != 0u && rk >= T_key) ? 0 : 1;
+    }
+    sh->flag = bad;
   }
   __syncthreads();
+  if (tid == 0 && a.box.enabled && npos == k) a.box.count[b] = sh->first_below;  // (npos < k: sel_finish, after the fillers)
   return npos;
 }
 
@@ -170,8 +300,8 @@ __device__ __noinline__ int sel_rank_emit(const SelArgs& a, SelShared* sh, int b
 __device__ __noinline__ void sel_finish(const SelArgs& a, SelShared* sh, int b, int npos) {
   const int tid = threadIdx.x, k = a.k;
   if (npos < k) {
-    uint32_t* flags = sh->u.s.hist;
-    const unsigned long long* ranked = sh->u.s.keys;
+    uint32_t* flags = sh->s.hist;
+    const unsigned long long* ranked = sh->s.keys;
     for (int i = tid; i < k; i += kSelThreads) flags[i] = 0u;
     __syncthreads();
     if (tid < npos) {
@@ -243,7 +373,7 @@ __device__ __noinline__ void sel_slow_prune(const SelArgs& a, SelShared* sh) {
   const int tid = threadIdx.x, k = a.k;
   const int n = sh->n_cand;  // > k
   const unsigned long long T =
-      block_kth_largest<kSelThreads>([&](int i) { return sh->cand[i]; }, n, k, sh->u.s.hist, sh->ctl);
+      block_kth_largest<kSelThreads>([&](int i) { return sh->cand[i]; }, n, k, sh->s.hist, sh->ctl);
   unsigned long long mine[kSelCandCap / kSelThreads];
 #pragma unroll
   for (int u = 0; u < kSelCandCap / kSelThreads; ++u) {
@@ -308,160 +438,324 @@ __device__ __noinline__ int sel_slow(const SelArgs& a, SelShared* sh, const floa
 }
 
 __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_constant__ SelArgs a) {
-  __shared__ SelShared sh_;
-  SelShared* sh = &sh_;
+  extern __shared__ __align__(128) unsigned char sel_smem[];
+  SelShared* sh = reinterpret_cast<SelShared*>(sel_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   const int k = a.k;
   const int HW = a.H * a.W;
   const float* __restrict__ fhm = a.hm + (size_t)b * a.C * HW;
-  const float* __restrict__ bm = a.bm + (size_t)b * a.n_blk;
+  const float* __restrict__ bm = a.bm + (size_t)b * a.G * 32;  // (rows padded to whole groups: 128-byte aligned)
   const float* __restrict__ bm2 = a.bm2 + (size_t)b * a.G;
+  // Every instruction of a 1024-thread CTA costs >= 8 issue cycles (~15 measured): the phases are written for
+  // instruction count, not for the number of round trips to memory (HBM latency is ~0.4 us; 250 instructions are 2 us).
+  int sel_rep = 0;  // (-DTAUV_SEL_TWICE experiment: the whole pass a second time, with warm caches, traced separately)
+  (void)sel_rep;
   if (tid == 0) sh->first_below = k;
+  SEL_STAMP(0);
+  // The CTA is resident about a microsecond before block_max_kernel completes: use it to take the TLB misses of every
+  // region this pass will touch (the first access of an SM to a page costs ~1 us, and each phase below starts with
+  // one): one load per 64 KB of the frame's logits, of its summaries and of the size / offset / depth planes.  L2-only
+  // loads (.cg): nothing stale can stay in L1, and the values are discarded.
+  {
+    auto touch = [](const void* p) {
+      uint32_t x;
+      asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(x) : "l"(p) : "memory");
+    };
+    const size_t frame_floats = (size_t)a.C * HW;
+    for (size_t off = (size_t)tid * 16384; off < frame_floats; off += (size_t)kSelThreads * 16384) touch(fhm + off);
+    if (tid == kSelThreads - 1) touch(fhm + frame_floats - 1);
+    if (tid >= 32 && tid < 64)
+      for (int off = (tid - 32) * 16384; off < a.n_blk; off += 32 * 16384) touch(bm + off);
+    if (tid == 64) touch(bm + a.n_blk - 1);
+    if (tid == 65) touch(bm2);
+    if (tid == 66) touch(bm2 + a.G - 1);
+    if (a.box.enabled && tid >= 96 && tid < 96 + 16) {
+      const int q = tid - 96, iy = (int)((long long)(a.H - 1) * (q >> 1) / 7), ix = (q & 1) ? a.W - 1 : 0;
+      touch(a.box.size + b * a.box.ss[0] + iy * a.box.ss[1] + ix * a.box.ss[2]);
+      touch(a.box.size + b * a.box.ss[0] + iy * a.box.ss[1] + ix * a.box.ss[2] + a.box.ss[3]);
+      if (a.box.mode == TAUV_BOX_DECODE) {
+        touch(a.box.offset + b * a.box.os[0] + iy * a.box.os[1] + ix * a.box.os[2]);
+        touch(a.box.offset + b * a.box.os[0] + iy * a.box.os[1] + ix * a.box.os[2] + a.box.os[3]);
+      }
+      if (a.box.depth != nullptr) touch(a.box.depth + b * a.box.ds[0] + iy * a.box.ds[1] + ix * a.box.ds[2]);
+    }
+  }
   asm volatile("griddepcontrol.wait;" ::: "memory");  // block_max_kernel has completed and flushed (no-op without the attribute)
+  SEL_STAMP(1);
 
-  int K1 = k + (k >> 3) + 8;
+  int K1 = k + (k >> 3) + 8;  // (a retry doubles the frame's time, and the launch waits for its slowest frame)
   int n = 0;
   bool slow = false;
+  int attempts = 0;
   for (;;) {
-    // ---- 1. threshold: the K1-th largest of <= 1024 strided maxima of the group (or block) maxima ----
+    ++attempts;
+    // ---- 1. threshold T: (a lower bound of) the K1-th largest of 1024 strided maxima of the group (or block) maxima.
+    //         L = the smallest of the warps' j-th largest maxima (32 j >= K1 keys reach it),
+    //         U = the largest key; one 1024-bin histogram of the keys in [L, U] and a suffix count give the bin in which
+    //         the count reaches K1; T = its lower edge. ----
     const bool use_grp = a.G >= 4 * K1;
     const float* __restrict__ lv = use_grp ? bm2 : bm;
     const int nlv = use_grp ? a.G : a.n_blk;
+    uint32_t T_key = 0u;
     float T_f = TAUV_NEG_INF;
     __syncthreads();
-    if (K1 < (nlv < kSelThreads ? nlv : kSelThreads)) {
+    if (K1 <= kSelThreads) {
+      uint32_t* hist = sh->s.hist;  // [0,1024) bins, [1024,1056) warp totals, [1056,1088) j-th largest, [1088,1120) largest
       float tm = TAUV_NEG_INF;
       for (int i = tid; i < nlv; i += kSelThreads) tm = fmaxf(tm, lv[i]);
-      sh->u.s.keys[tid] = make_composite(float_to_key(tm), (uint32_t)tid);
+      const uint32_t key = float_to_key(tm);
+      // the warp's largest key and its j-th largest (with multiplicity), j = ceil(K1 / 32): j warp-wide max reductions
+      const int j = (K1 + 31) >> 5;
+      uint32_t cur = key, mx = __reduce_max_sync(0xffffffffu, cur);
+      if (lane == 0) hist[1088 + warp] = mx;
+      for (int jj = 1; jj < j; ++jj) {
+        const unsigned bal = __ballot_sync(0xffffffffu, cur == mx);
+        if (lane == __ffs(bal) - 1) cur = 0u;
+        mx = __reduce_max_sync(0xffffffffu, cur);
+      }
+      if (lane == 0) hist[1056 + warp] = mx;
+      hist[tid] = 0u;
       __syncthreads();
-      const unsigned long long Tc = block_kth_largest<kSelThreads>([&](int i) { return sh->u.s.keys[i]; }, kSelThreads,
-                                                                   K1, sh->u.s.hist, sh->ctl);
-      T_f = key_to_float(composite_key(Tc));
+      uint32_t Lk = hist[1056 + lane], Uk = hist[1088 + lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        Lk = min(Lk, __shfl_xor_sync(0xffffffffu, Lk, o));
+        Uk = max(Uk, __shfl_xor_sync(0xffffffffu, Uk, o));
+      }
+      const uint32_t range = Uk - Lk;
+      const int shft = range >= 1024u ? 22 - __clz(range) : 0;  // (range >> shft) < 1024
+      if (key >= Lk) atomicAdd(&hist[(key - Lk) >> shft], 1u);
+      __syncthreads();
+      const uint32_t c = hist[tid];
+      uint32_t suf = c;  // inclusive suffix count inside the warp (lane 31 = highest bin)
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_down_sync(0xffffffffu, suf, o);
+        if (lane + o < 32) suf += v;
+      }
+      if (lane == 0) hist[1024 + warp] = suf;
+      __syncthreads();
+      uint32_t wsuf = hist[1024 + lane];  // suffix over the warps' totals
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_down_sync(0xffffffffu, wsuf, o);
+        if (lane + o < 32) wsuf += v;
+      }
+      const uint32_t above = __shfl_sync(0xffffffffu, wsuf, (warp + 1) & 31);
+      suf += warp < 31 ? above : 0u;
+      if (suf >= (uint32_t)K1 && suf - c < (uint32_t)K1) sh->T_key = Lk + ((uint32_t)tid << shft);
+      __syncthreads();
+      T_key = sh->T_key;
+      T_f = key_to_float(T_key);
+      if (!(T_f > TAUV_NEG_INF)) T_key = 0u;
     }
     if (tid == 0) {
       sh->n_hgrp = 0;
       sh->n_hot = 0;
-      sh->n_cell = 0;
-      sh->n_cand = 0;
+      sh->n_xhot = 0;
+      sh->n_xcell = 0;
+      sh->n_zero = 0;
+      sh->flag = 0;
     }
     __syncthreads();
-    // ---- 2. hot groups -> hot blocks ----
+    SEL_STAMP(2);
+    // ---- 2. hot groups -> hot blocks (ids in sh->cell), then their positions ----
+    int nhot;
     if (use_grp) {
-      for (int i0 = 0; i0 < a.G; i0 += kSelThreads) {
-        const int i = i0 + tid;
-        const bool hot = i < a.G && !(bm2[i] < T_f);
-        const int slot = sel_append(&sh->n_hgrp, hot);
-        if (hot && slot < kSelHotCap) sh->hgrp[slot] = (uint32_t)i;
-      }
+      sel_collect(bm2, a.G, T_f, &sh->n_hgrp, sh->hgrp, kSelHotCap);
       __syncthreads();
       const int nh = sh->n_hgrp;
       if (nh > kSelHotCap) { slow = true; break; }
-      for (int j = warp; j < nh; j += kSelThreads / 32) {
-        const int idx = (int)sh->hgrp[j] * 32 + lane;
-        const bool hot = idx < a.n_blk && !(bm[idx < a.n_blk ? idx : 0] < T_f);
-        const int slot = sel_append(&sh->n_hot, hot);
-        if (hot && slot < kSelHotCap) sh->hot[slot] = (uint32_t)idx;
-      }
-    } else {
-      for (int i0 = 0; i0 < a.n_blk; i0 += kSelThreads) {
-        const int i = i0 + tid;
-        const bool hot = i < a.n_blk && !(bm[i < a.n_blk ? i : 0] < T_f);
-        const int slot = sel_append(&sh->n_hot, hot);
-        if (hot && slot < kSelHotCap) sh->hot[slot] = (uint32_t)i;
-      }
-    }
-    __syncthreads();
-    const int nhot = sh->n_hot;
-    if (nhot > kSelHotCap) { slow = true; break; }
-    // ---- 3a. the cells of the hot blocks (one warp per block, one lane per cell): which reach T? ----
-    constexpr int UA = 8;
-    for (int j0 = 0; j0 < nhot; j0 += UA * (kSelThreads / 32)) {
-      float x[UA];
-      uint32_t fl[UA];
+      // eight lanes per hot group, one 128-bit load each.  The group's first hot block (there is one: the group
+      // maximum is a block maximum) takes the group's own slot, further ones (rare) are appended behind the nh slots.
+      const int ne = nh * 8;
+      for (int e0 = 0; e0 < ne; e0 += 2 * kSelThreads) {
+        float4 v[2];
+        int idx[2];
 #pragma unroll
-      for (int u = 0; u < UA; ++u) {
-        const int j = j0 + u * (kSelThreads / 32) + warp;
-        x[u] = TAUV_NEG_INF;
-        fl[u] = 0xffffffffu;
-        if (j < nhot) {
-          const uint32_t blk = sh->hot[j];
-          const uint32_t q = blk / (uint32_t)a.W4, c4 = blk - q * (uint32_t)a.W4;
-          const uint32_t c = q / (uint32_t)a.n_rg, rg = q - c * (uint32_t)a.n_rg;
-          const int r = (int)rg * kBmRows + (lane >> 2), col = (int)c4 * 4 + (lane & 3);
-          if (r < a.H) {
-            fl[u] = c * (uint32_t)HW + (uint32_t)(r * a.W + col);
-            x[u] = fhm[fl[u]];
+        for (int u = 0; u < 2; ++u) {
+          const int e = e0 + u * kSelThreads + tid;
+          idx[u] = e < ne ? (int)sh->hgrp[e >> 3] * 32 + (lane & 7) * 4 : a.n_blk;
+          v[u] = idx[u] < a.n_blk ? *reinterpret_cast<const float4*>(bm + idx[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+          unsigned hm = 0u;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (idx[u] + c < a.n_blk && !(vv[c] < T_f)) hm |= 1u << c;
+          const unsigned bal = __ballot_sync(0xffffffffu, hm != 0u);
+          const unsigned seg = (bal >> (lane & 24)) & 0xffu;         // the eight lanes of this group
+          const int gs = (e0 + u * kSelThreads + tid) >> 3;
+          if (seg == 0u && (lane & 7) == 0 && idx[u] < a.n_blk) sh->cell[gs] = (uint32_t)idx[u];  // (cannot happen)
+          if (hm) {
+            bool first = (lane & 7) == __ffs(seg) - 1;                // the group's first lane with a hot block
+            do {
+              const int c = __ffs(hm) - 1;
+              hm &= hm - 1;
+              int slot = gs;
+              if (!first) slot = nh + atomicAdd(&sh->n_xhot, 1);
+              first = false;
+              if (slot < kSelCellCap) sh->cell[slot] = (uint32_t)(idx[u] + c);
+            } while (hm);
           }
         }
       }
+      __syncthreads();
+      nhot = nh + sh->n_xhot;
+    } else {
+      sel_collect(bm, a.n_blk, T_f, &sh->n_hot, sh->cell, kSelCellCap);
+      __syncthreads();
+      nhot = sh->n_hot;
+    }
+    if (nhot > kSelHotCap) { slow = true; break; }
+    for (int i = tid; i < nhot; i += kSelThreads) {  // (dense: a handful of warps)
+      const uint32_t blk = sh->cell[i];
+      const uint32_t q = fdiv_u32(blk, a.dW4), c4 = blk - q * (uint32_t)a.W4;
+      const uint32_t c = fdiv_u32(q, a.dNrg), rg = q - c * (uint32_t)a.n_rg;
+      const uint32_t r0 = rg * kBmRows, col0 = c4 * 4;
+      sh->hot[i] = c * (uint32_t)HW + r0 * (uint32_t)a.W + col0;
+      sh->hotpos[i] = (r0 << 16) | col0;
+    }
+    __syncthreads();
+    SEL_STAMP(3);
+    // ---- 3a. the rows of the hot blocks: eight lanes per block, one 128-bit load each; cells that reach T are
+    //          queued — the block's first one (there is one: the block maximum) in the block's own slot, further
+    //          ones (7 % of the blocks on noise) behind the nhot slots ----
+    {
+      const int ne = nhot * 8;
+      for (int e0 = 0; e0 < ne; e0 += 2 * kSelThreads) {
+        float4 v[2];
+        uint32_t org[2], pos[2];
 #pragma unroll
-      for (int u = 0; u < UA; ++u) {
-        const bool want = fl[u] != 0xffffffffu && !(x[u] < T_f);
-        const int slot = sel_append(&sh->n_cell, want);
-        if (want && slot < kSelCellCap) sh->u.cell[slot] = ((unsigned long long)__float_as_uint(x[u]) << 32) | fl[u];
+        for (int u = 0; u < 2; ++u) {
+          const int e = e0 + u * kSelThreads + tid;
+          org[u] = 0xffffffffu;
+          pos[u] = 0u;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e < ne) {
+            const uint32_t p = sh->hotpos[e >> 3];
+            const int r = (int)(p >> 16) + (lane & 7);
+            if (r < a.H) {
+              org[u] = sh->hot[e >> 3] + (uint32_t)((lane & 7) * a.W);
+              pos[u] = ((uint32_t)r << 16) | (p & 0xffffu);
+              v[u] = *reinterpret_cast<const float4*>(fhm + org[u]);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+          unsigned hm = 0u;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (org[u] != 0xffffffffu && !(vv[c] < T_f)) hm |= 1u << c;  // (NaN cells pass here and fail the peak test)
+          const unsigned bal = __ballot_sync(0xffffffffu, hm != 0u);
+          const unsigned seg = (bal >> (lane & 24)) & 0xffu;
+          const int bs = (e0 + u * kSelThreads + tid) >> 3;
+          if (seg == 0u && (lane & 7) == 0 && e0 + u * kSelThreads + tid < ne) {  // (cannot happen; keeps the slot defined)
+            sh->cellpos[bs] = sh->hotpos[bs];
+            sh->cellx[bs] = TAUV_NEG_INF;
+            sh->cell[bs] = sh->hot[bs];
+          }
+          if (hm) {
+            bool first = (lane & 7) == __ffs(seg) - 1;
+            do {
+              const int c = __ffs(hm) - 1;
+              hm &= hm - 1;
+              int slot = bs;
+              if (!first) slot = nhot + atomicAdd(&sh->n_xcell, 1);
+              first = false;
+              if (slot < kSelCellCap) {
+                sh->cellpos[slot] = pos[u] + (uint32_t)c;
+                sh->cellx[slot] = c == 0 ? v[u].x : c == 1 ? v[u].y : c == 2 ? v[u].z : v[u].w;
+                sh->cell[slot] = org[u] + (uint32_t)c;  // (flat index; the block ids were consumed before the barrier)
+              }
+            } while (hm);
+          }
+        }
       }
     }
     __syncthreads();
-    const int ncell = sh->n_cell;
-    if (ncell > kSelCellCap) { slow = true; break; }
-    // ---- 3b. 3x3 test, eight lanes per hot cell (one neighbour each) ----
-    for (int i0 = 0; i0 < ncell; i0 += kSelThreads / 8) {
-      const int i = i0 + (tid >> 3), part = tid & 7;
-      float x = 0.0f, v = TAUV_NEG_INF;
-      uint32_t flat = 0;
-      if (i < ncell) {
-        const unsigned long long e = sh->u.cell[i];
-        x = __uint_as_float((uint32_t)(e >> 32));
-        flat = (uint32_t)e;
-        const uint32_t c = flat / (uint32_t)HW, rem = flat - c * (uint32_t)HW;
-        const int r = (int)(rem / (uint32_t)a.W), col = (int)(rem - (uint32_t)r * (uint32_t)a.W);
-        const int p = part + (part >= 4 ? 1 : 0);  // 0..8 without the centre
-        const int dy = p / 3 - 1, dx = p - (p / 3) * 3 - 1;
-        const int rr = r + dy, cc = col + dx;
-        if (rr >= 0 && rr < a.H && cc >= 0 && cc < a.W) v = fhm[(long long)flat + dy * a.W + dx];
+    n = nhot + sh->n_xcell;
+    if (n > kSelCellCap || n > kSelCandCap) { slow = true; break; }
+    SEL_STAMP(11);
+    // ---- 3b. the eight neighbours of every queued cell: eight lanes per cell, one load each ----
+    {
+      const int ne = n * 8;
+      for (int e0 = 0; e0 < ne; e0 += 2 * kSelThreads) {
+        float v[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int e = e0 + u * kSelThreads + tid;
+          v[u] = TAUV_NEG_INF;
+          if (e < ne) {
+            const uint32_t p = sh->cellpos[e >> 3];
+            const int part = lane & 7, pp = part + (part >= 4 ? 1 : 0);  // 0..8 without the centre
+            const int dy = pp / 3 - 1, dx = pp - (pp / 3) * 3 - 1;
+            const int rr = (int)(p >> 16) + dy, cc = (int)(p & 0xffffu) + dx;
+            if (rr >= 0 && rr < a.H && cc >= 0 && cc < a.W) v[u] = fhm[(long long)sh->cell[e >> 3] + dy * a.W + dx];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float m = v[u];
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+          const int e = e0 + u * kSelThreads + tid;
+          if (e < ne && (lane & 7) == 0) sh->cellm[e >> 3] = m;
+        }
       }
-      v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-      v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
-      v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
-      unsigned long long fin = 0ull;
-      if (i < ncell && part == 0 && sel_is_peak(x, v)) fin = sel_final_key(x, flat);
-      const int slot = sel_append(&sh->n_cand, fin != 0ull);
-      if (fin != 0ull) sh->cand[slot] = fin;  // (n_cand <= n_cell <= kSelCandCap)
     }
     __syncthreads();
-    n = sh->n_cand;
-    const bool have_T = T_f > TAUV_NEG_INF;
-    if (n < k && have_T) {  // not enough peaks at or above T: lower it
+    SEL_STAMP(12);
+    // ---- 3c. one thread per queued cell: peak test, sigmoid, final key into the cell's candidate slot ----
+    for (int i = tid; i < n; i += kSelThreads) sh->cand[i] = sel_test_cell(a, sh, b, i);
+    if (tid == kSelThreads - 1 && (n & 1)) sh->cand[n] = 0ull;  // (the rank loop reads pairs; n < kSelCandCap when odd)
+    __syncthreads();
+    SEL_STAMP(4);
+    SEL_NOTE(8, attempts);
+    SEL_NOTE(9, nhot);
+    SEL_NOTE(10, n);
+    // ---- 4. rank, emit, and check that enough peaks reached T and nothing below T could have made it ----
+    const int npos = sel_rank_emit(a, sh, b, n, T_key);
+    SEL_STAMP(5);
+    if (T_key != 0u && sh->flag) {
+      __syncthreads();
+      if (tid == 0) sh->first_below = k;
       K1 *= 4;
       continue;
     }
-    // ---- 4. rank, emit, and check that nothing below T could have made it ----
-    const int npos = sel_rank_emit(a, sh, b, n);
-    if (have_T) {
-      if (tid == 0) {
-        const uint32_t rk = reject_key_for_score(sh->s_k);
-        sh->flag = (rk != 0u && rk >= float_to_key(T_f)) ? 0 : 1;
-      }
+    if (npos < k) sel_finish(a, sh, b, npos);
+    SEL_STAMP(6);
+#ifdef TAUV_SEL_TWICE
+    if (sel_rep == 0) {
+      sel_rep = 1;
+      K1 = k + (k >> 3) + 8;
+      attempts = 0;
       __syncthreads();
-      if (sh->flag) {
-        __syncthreads();
-        if (tid == 0) {
-          sh->flag = 0;
-          sh->first_below = k;
-        }
-        K1 *= 4;
-        continue;
-      }
+      if (tid == 0) sh->first_below = k;
+      SEL_STAMP(1);
+      continue;
     }
-    sel_finish(a, sh, b, npos);
+#endif
     return;
   }
+  SEL_NOTE(8, -attempts);
   if (slow) {
-    if (tid == 0) sh->first_below = k;
+    __syncthreads();
+    if (tid == 0) {
+      sh->first_below = k;
+      sh->n_zero = 0;
+    }
     n = sel_slow(a, sh, fhm, bm);
-    const int npos = sel_rank_emit(a, sh, b, n);
-    sel_finish(a, sh, b, npos);
+    if (tid == 0 && (n & 1) && n < kSelCandCap) sh->cand[n] = 0ull;
+    __syncthreads();
+    const int npos = sel_rank_emit(a, sh, b, n, 0u);
+    if (npos < k) sel_finish(a, sh, b, npos);
   }
 }
 
@@ -475,12 +769,12 @@ static bool select_plan(int B, int C, int H, int W, int k, SelPlan* p) {
   if (W % 4 != 0 || k > kSelMaxK || B > 65535) return false;
   const long long n_rg = (H + kBmRows - 1) / kBmRows;
   const long long n_blk = (long long)C * n_rg * (W / 4);
-  if (n_blk >= (1LL << 26)) return false;
+  if (n_blk >= (1LL << 26) || (long long)C * H * W >= (1LL << 31)) return false;  // (FastDiv: dividends below 2^31)
   p->W4 = W / 4;
   p->n_rg = (int)n_rg;
   p->n_blk = (int)n_blk;
   p->G = (int)((n_blk + 31) / 32);
-  p->bm_bytes = align_up((size_t)B * p->n_blk * 4, 256);
+  p->bm_bytes = align_up((size_t)B * p->G * 32 * 4, 256);
   p->bm2_bytes = align_up((size_t)B * p->G * 4, 256);
   return true;
 }
@@ -496,21 +790,40 @@ static int run_select_decode(const float* hm, int B, int C, int H, int W, int k,
   ba.bm = reinterpret_cast<float*>(ws);
   ba.bm2 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws) + p.bm_bytes);
   ba.C = C; ba.H = H; ba.W = W; ba.W4 = p.W4; ba.n_rg = p.n_rg; ba.n_blk = p.n_blk; ba.G = p.G;
-  block_max_kernel<<<dim3((unsigned)((p.n_blk + kBmThreads - 1) / kBmThreads), (unsigned)B), kBmThreads, 0, st>>>(ba);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((p.n_blk + kBmThreads - 1) / kBmThreads), (unsigned)B);
+    cfg.blockDim = dim3(kBmThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TAUV_CUDA(cudaLaunchKernelEx(&cfg, block_max_kernel, ba));
+  }
   TAUV_LAUNCH_CHECK("block_max_kernel");
   SelArgs sa;
   sa.hm = hm; sa.bm = ba.bm; sa.bm2 = ba.bm2;
   sa.C = C; sa.H = H; sa.W = W; sa.k = k; sa.W4 = p.W4; sa.n_rg = p.n_rg; sa.n_blk = p.n_blk; sa.G = p.G;
   sa.out_index = index; sa.out_label = label; sa.out_score = score;
   sa.box = box;
+  sa.dW4 = make_fastdiv((uint32_t)p.W4);
+  sa.dNrg = make_fastdiv((uint32_t)p.n_rg);
+  sa.dHW = make_fastdiv((uint32_t)(H * W));
+  sa.dW = make_fastdiv((uint32_t)W);
+#ifdef TAUV_DEBUG
+  sa.trace = g_sel_trace;
+#else
+  sa.trace = nullptr;
+#endif
+  TAUV_CUDA(ensure_dynamic_smem((const void*)select_kernel, sizeof(SelShared)));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)B);
   cfg.blockDim = dim3(kSelThreads);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = sizeof(SelShared);
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   TAUV_CUDA(cudaLaunchKernelEx(&cfg, select_kernel, sa));
