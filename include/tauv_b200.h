@@ -115,6 +115,13 @@ int tauv_centernet_decode(const float* heatmap_logits, int B, int C, int H, int 
                           int32_t* count, void* workspace, size_t workspace_bytes,
                           tauv_stream_t stream);
 
+/* Launch 1 of the two tauv_centernet_decode makes for 16-byte aligned maps with W % 4 == 0 and k <= 256, on its own
+ * (bench.py times it with stream events: it is the only pass over the logits, centernet/model/decode.py:182,239-252 read
+ * them three times).  Leaves in the workspace, per frame, the maximum of every block of 4 columns x 8 rows of every
+ * plane and the maximum of every 32 consecutive blocks.  Returns TAUV_E_UNSUPPORTED for other shapes. */
+int tauv_centernet_block_maxima(const float* heatmap_logits, int B, int C, int H, int W, int k,
+                                void* workspace, size_t workspace_bytes, tauv_stream_t stream);
+
 /* The two-launch form of tauv_centernet_decode as separate calls (profiling tools put stream events
  * between them).  stage1 fills the workspace with candidates (reads the logits once); stage2 merges
  * them per frame and does the box arithmetic.  Same workspace, same shapes, same stream for both. */

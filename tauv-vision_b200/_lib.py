@@ -43,6 +43,7 @@ _SIGNATURES = {
     "tauv_centernet_decode": (c_int, [_F, c_int, c_int, c_int, c_int, c_int, _F, _I64, _F, _I64, _F, _I64, c_int,
                                       c_int, c_int, c_int, c_float, _I64, _I64, _F, _D, _F, _F, _I32, c_void_p,
                                       c_size_t, c_void_p]),
+    "tauv_centernet_block_maxima": (c_int, [_F, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "tauv_heatmap_topk_stage1": (c_int, [_F, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "tauv_centernet_decode_stage2": (c_int, [c_int, c_int, c_int, c_int, c_int, _F, _I64, _F, _I64, _F, _I64, c_int,
                                              c_int, c_int, c_int, c_float, _I64, _I64, _F, _D, _F, _F, _I32, c_void_p,

@@ -1896,6 +1896,16 @@ extern "C" int tauv_centernet_decode(const float* heatmap_logits, int B, int C, 
                   workspace_bytes, (cudaStream_t)stream);
 }
 
+extern "C" int tauv_centernet_block_maxima(const float* heatmap_logits, int B, int C, int H, int W, int k, void* workspace,
+                                           size_t workspace_bytes, tauv_stream_t stream) {
+  TAUV_REQUIRE(heatmap_logits, TAUV_E_NULL, "heatmap must not be NULL");
+  if (int e = check_topk_shape(B, C, H, W, k)) return e;
+  SelPlan sp;
+  TAUV_REQUIRE((uintptr_t)heatmap_logits % 16 == 0 && select_plan(B, C, H, W, k, &sp), TAUV_E_UNSUPPORTED,
+               "the block-maxima path needs a 16-byte aligned map with W %% 4 == 0 and k <= %d", kSelMaxK);
+  return run_block_maxima(heatmap_logits, B, C, H, W, workspace, workspace_bytes, sp, (cudaStream_t)stream);
+}
+
 extern "C" int tauv_heatmap_nms(const float* in, float* out, int B, int C, int H, int W, int kernel_size,
                                 int apply_sigmoid, tauv_stream_t stream) {
   TAUV_REQUIRE(in && out, TAUV_E_NULL, "in/out must not be NULL");

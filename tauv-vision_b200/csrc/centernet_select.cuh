@@ -28,7 +28,10 @@
 namespace tauv {
 
 constexpr int kBmRows = 8;            // rows of a block (a block = 4 columns x kBmRows rows of one plane)
-constexpr int kBmThreads = 256;
+#ifndef TAUV_BM_THREADS
+#define TAUV_BM_THREADS 512
+#endif
+constexpr int kBmThreads = TAUV_BM_THREADS;
 constexpr int kSelThreads = 1024;
 constexpr int kSelHotCap = 1024;      // hot groups / hot blocks per attempt
 constexpr int kSelCandCap = 2048;     // candidate list (final composites)
@@ -108,6 +111,10 @@ __global__ void __launch_bounds__(kBmThreads) block_max_kernel(const __grid_cons
   // the summaries are read again in a few tens of microseconds: keep them in L2 while the read-once logits stream through
   uint64_t keep;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+#ifdef TAUV_BM_EVICT1
+  uint64_t first;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(first));
+#endif
   const int b = blockIdx.y;
   const uint32_t i = blockIdx.x * (uint32_t)kBmThreads + threadIdx.x;  // block index inside the frame
   float m = TAUV_NEG_INF;
@@ -121,7 +128,14 @@ __global__ void __launch_bounds__(kBmThreads) block_max_kernel(const __grid_cons
     float4 x[kBmRows];
     if (nr == kBmRows) {  // all eight loads in flight before the first use
 #pragma unroll
-      for (int r = 0; r < kBmRows; ++r) x[r] = ldg_stream4(p + (size_t)r * a.W);
+      for (int r = 0; r < kBmRows; ++r) {
+#ifdef TAUV_BM_EVICT1
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=f"(x[r].x), "=f"(x[r].y), "=f"(x[r].z), "=f"(x[r].w) : "l"(p + (size_t)r * a.W), "l"(first));
+#else
+        x[r] = ldg_stream4(p + (size_t)r * a.W);
+#endif
+      }
     } else {
 #pragma unroll
       for (int r = 0; r < kBmRows; ++r)
@@ -779,9 +793,9 @@ static bool select_plan(int B, int C, int H, int W, int k, SelPlan* p) {
   return true;
 }
 
-static int run_select_decode(const float* hm, int B, int C, int H, int W, int k, int64_t* index, int64_t* label,
-                             float* score, const BoxArgs& box, void* ws, size_t ws_bytes, const SelPlan& p,
-                             cudaStream_t st) {
+// launch 1 of 2: the block maxima of every frame into the workspace (the only pass over the logits)
+static int run_block_maxima(const float* hm, int B, int C, int H, int W, void* ws, size_t ws_bytes, const SelPlan& p,
+                            cudaStream_t st) {
   TAUV_REQUIRE(ws != nullptr && (uintptr_t)ws % 256 == 0, TAUV_E_WORKSPACE, "workspace must be 256-byte aligned");
   TAUV_REQUIRE(ws_bytes >= p.bm_bytes + p.bm2_bytes, TAUV_E_WORKSPACE, "workspace %zu < required %zu", ws_bytes,
                p.bm_bytes + p.bm2_bytes);
@@ -793,19 +807,26 @@ static int run_select_decode(const float* hm, int B, int C, int H, int W, int k,
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)((p.n_blk + kBmThreads - 1) / kBmThreads), (unsigned)B);
-    cfg.blockDim = dim3(kBmThreads);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = st;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    TAUV_CUDA(cudaLaunchKernelEx(&cfg, block_max_kernel, ba));
-  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((p.n_blk + kBmThreads - 1) / kBmThreads), (unsigned)B);
+  cfg.blockDim = dim3(kBmThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TAUV_CUDA(cudaLaunchKernelEx(&cfg, block_max_kernel, ba));
   TAUV_LAUNCH_CHECK("block_max_kernel");
+  return 0;
+}
+
+static int run_select_decode(const float* hm, int B, int C, int H, int W, int k, int64_t* index, int64_t* label,
+                             float* score, const BoxArgs& box, void* ws, size_t ws_bytes, const SelPlan& p,
+                             cudaStream_t st) {
+  if (int e = run_block_maxima(hm, B, C, H, W, ws, ws_bytes, p, st)) return e;
   SelArgs sa;
-  sa.hm = hm; sa.bm = ba.bm; sa.bm2 = ba.bm2;
+  sa.hm = hm;
+  sa.bm = reinterpret_cast<const float*>(ws);
+  sa.bm2 = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(ws) + p.bm_bytes);
   sa.C = C; sa.H = H; sa.W = W; sa.k = k; sa.W4 = p.W4; sa.n_rg = p.n_rg; sa.n_blk = p.n_blk; sa.G = p.G;
   sa.out_index = index; sa.out_label = label; sa.out_score = score;
   sa.box = box;
@@ -819,6 +840,9 @@ static int run_select_decode(const float* hm, int B, int C, int H, int W, int k,
   sa.trace = nullptr;
 #endif
   TAUV_CUDA(ensure_dynamic_smem((const void*)select_kernel, sizeof(SelShared)));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)B);
   cfg.blockDim = dim3(kSelThreads);

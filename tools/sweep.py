@@ -1,5 +1,5 @@
 """Throughput sweep over the BASELINE.json parity/sweep configs (#2 multi-scale, #5 classes x top-k, YOLACT priors x top_k).
-Device-resident inputs, CUDA events, L2 flushed between repetitions.  Prints a markdown table (profiles/r1_sweep.md)."""
+Device-resident inputs, CUDA events, L2 flushed (by a read) between repetitions.  Prints a markdown table (profiles/r2_sweep.md)."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -10,13 +10,17 @@ from tauv_vision_b200.yolact.model import nms, anchors
 from tests import synth
 
 dev = torch.device("cuda", 0)
-flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+flush = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
 PEAK = 6454.3
 
 def timeit(fn, n=7):
+    """Median device time of one call.  Between repetitions the L2 is flushed by READING 256 MB (a fill would leave it
+    full of dirty lines, whose write-back the next kernel then pays for), and a short device-side sleep lets the host
+    enqueue the call before the first event completes (otherwise small shapes time the host's launch path)."""
     ts = []
     for _ in range(n):
-        flush.zero_()
+        flush.sum()
+        torch.cuda._sleep(200000)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
