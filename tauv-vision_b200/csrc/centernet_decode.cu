@@ -554,28 +554,44 @@ __global__ void __launch_bounds__(kTileThreads) tile_topk_kernel(const __grid_co
 // ----------------------------------------------------------------------------------------------
 // Frame-level selection and ranked output (shared by the merge kernel and the cluster kernel's fused tail)
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void box_one(const BoxArgs& g, int b, long long slot, int iy, int ix) {
-  const float h = g.size[b * g.ss[0] + iy * g.ss[1] + ix * g.ss[2]];
-  const float w = g.size[b * g.ss[0] + iy * g.ss[1] + ix * g.ss[2] + g.ss[3]];
-  g.hw[slot * 2 + 0] = h;
-  g.hw[slot * 2 + 1] = w;
+struct BoxVals {
+  float h, w, depth;
+  double y, x;
+};
+// the per-detection arithmetic of decode() / decode_keypoints() for the cell (iy, ix) of frame b
+__device__ __forceinline__ BoxVals box_values(const BoxArgs& g, int b, int iy, int ix) {
+  BoxVals v;
+  v.h = g.size[b * g.ss[0] + iy * g.ss[1] + ix * g.ss[2]];
+  v.w = g.size[b * g.ss[0] + iy * g.ss[1] + ix * g.ss[2] + g.ss[3]];
   if (g.mode == TAUV_BOX_DECODE) {
     // decode.py:214-215: Python doubles
     const float oy = g.offset[b * g.os[0] + iy * g.os[1] + ix * g.os[2]];
     const float ox = g.offset[b * g.os[0] + iy * g.os[1] + ix * g.os[2] + g.os[3]];
-    g.yx[slot * 2 + 0] = __ddiv_rn(__dadd_rn(__dmul_rn((double)g.ratio, (double)iy), (double)oy), (double)g.in_h);
-    g.yx[slot * 2 + 1] = __ddiv_rn(__dadd_rn(__dmul_rn((double)g.ratio, (double)ix), (double)ox), (double)g.in_w);
+    v.y = __ddiv_rn(__dadd_rn(__dmul_rn((double)g.ratio, (double)iy), (double)oy), (double)g.in_h);
+    v.x = __ddiv_rn(__dadd_rn(__dmul_rn((double)g.ratio, (double)ix), (double)ox), (double)g.in_w);
   } else {
     // decode.py:87-88: int64 tensor / int -> fp32 true divide, then float()
-    g.yx[slot * 2 + 0] = (double)__fdiv_rn((float)iy, (float)g.out_h);
-    g.yx[slot * 2 + 1] = (double)__fdiv_rn((float)ix, (float)g.out_w);
+    v.y = (double)__fdiv_rn((float)iy, (float)g.out_h);
+    v.x = (double)__fdiv_rn((float)ix, (float)g.out_w);
   }
+  v.depth = 0.0f;
   if (g.depth != nullptr && g.depth_out != nullptr) {
     const float d = g.depth[b * g.ds[0] + iy * g.ds[1] + ix * g.ds[2]];
     float inv = __fdiv_rn(1.0f, sigmoid_ref(d));
     if (g.mode == TAUV_BOX_DECODE) inv = __fsub_rn(inv, 1.0f);  // decode.py:324
-    g.depth_out[slot] = inv;
+    v.depth = inv;
   }
+  return v;
+}
+__device__ __forceinline__ void box_store(const BoxArgs& g, long long slot, const BoxVals& v) {
+  g.hw[slot * 2 + 0] = v.h;
+  g.hw[slot * 2 + 1] = v.w;
+  g.yx[slot * 2 + 0] = v.y;
+  g.yx[slot * 2 + 1] = v.x;
+  if (g.depth != nullptr && g.depth_out != nullptr) g.depth_out[slot] = v.depth;
+}
+__device__ __forceinline__ void box_one(const BoxArgs& g, int b, long long slot, int iy, int ix) {
+  box_store(g, slot, box_values(g, b, iy, ix));
 }
 
 // Select the k best of pool[0, total) (distinct composite keys, in shared memory) into sel[0, npos), npos = min(k, total),

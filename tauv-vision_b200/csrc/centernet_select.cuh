@@ -166,10 +166,12 @@ struct __align__(16) SelShared {
   uint32_t cellpos[kSelCellCap];           //   row << 16 | column,
   float cellx[kSelCellCap];                //   logit,
   float cellm[kSelCellCap];                //   maximum of the eight neighbours
+  BoxVals cellbox[kSelCellCap];            //   size / offset / depth arithmetic of the cell (idle warps, while the cells are tested)
+  uint32_t rankcell[kSelMaxK];             // the cell behind each ranked key
   uint32_t ctl[8];
   int n_hgrp, n_hot, n_xhot, n_xcell, n_cand, n_zero, first_below, flag;
   uint32_t T_key;
-  float s_k, xc_f;
+  float s_T, xc_f;  // s_T: the sigmoid of the threshold T (computed by an idle warp while the cells are tested)
   unsigned long long thr_c;
 };
 
@@ -231,31 +233,22 @@ __device__ __forceinline__ void sel_collect(const float* __restrict__ src, int n
 
 // a cell that reached T, with the maximum of its neighbours: peak test, sigmoid, final key (0: not a peak / zero score).
 // Dense: one thread per hot cell, a few warps per frame.
-__device__ __noinline__ unsigned long long sel_test_cell(const SelArgs& a, SelShared* sh, int b, int i) {
+__device__ __noinline__ unsigned long long sel_test_cell(const SelShared* sh, int i) {
   const float x = sh->cellx[i];
   if (!sel_is_peak(x, sh->cellm[i])) return 0ull;
-  const unsigned long long fin = sel_final_key(x, sh->cell[i]);
-  if (fin != 0ull && a.box.enabled) {  // the gathers of the emit phase: get their lines on the way now
-    const uint32_t pos = sh->cellpos[i];
-    const int iy = (int)(pos >> 16), ix = (int)(pos & 0xffffu);
-    const float* ps = a.box.size + b * a.box.ss[0] + iy * a.box.ss[1] + ix * a.box.ss[2];
-    sel_prefetch_l2(ps);
-    sel_prefetch_l2(ps + a.box.ss[3]);
-    if (a.box.mode == TAUV_BOX_DECODE) {
-      const float* po = a.box.offset + b * a.box.os[0] + iy * a.box.os[1] + ix * a.box.os[2];
-      sel_prefetch_l2(po);
-      sel_prefetch_l2(po + a.box.os[3]);
-    }
-  }
-  return fin;
+  return sel_final_key(x, sh->cell[i]);
 }
 
 // Rank the candidates cand[0, n) (distinct composites; 0 = empty slot) by counting, write the min(valid, k) best in
-// order.  When T_key != 0 the last warp meanwhile checks that nothing below the threshold could have made it
-// (sh->flag = 1 if it could): every logit below T must have a score strictly below the k-th best.  Returns
+// order.  With a threshold (T_key != 0) the thread that emits rank k - 1 also decides whether the result is complete:
+// every logit x <= T has sigmoid_ref(x) <= sigmoid_ref(T) (1 + 1e-6) (three roundings on a monotone function), so nothing
+// below T can reach the k-th best score s_k if sigmoid_ref(T) < s_k (1 - 2e-5) — the same guard band as
+// reject_key_for_score, without its logarithm.  sh->flag = 1 if that fails or fewer than k peaks reached T.  Returns
 // npos = min(valid, k).  All threads call this.
-__device__ __noinline__ int sel_rank_emit(const SelArgs& a, SelShared* sh, int b, int n, uint32_t T_key) {
+__device__ __noinline__ int sel_rank_emit(const SelArgs& a, SelShared* sh, int b, int n, uint32_t T_key, bool have_box) {
   const int tid = threadIdx.x, k = a.k;
+  const int sel_rep = 0;
+  (void)sel_rep;
   unsigned long long* ranked = sh->s.keys;
   const int tpc = n <= kSelThreads / 8 ? 8 : 4;  // threads per candidate
   const int n2 = (n + 1) >> 1;  // (the caller has zeroed cand[n] when n is odd)
@@ -263,21 +256,27 @@ __device__ __noinline__ int sel_rank_emit(const SelArgs& a, SelShared* sh, int b
     const int i = i0 + tid / tpc, part = tid & (tpc - 1);
     const unsigned long long my = i < n ? sh->cand[i] : 0ull;
     int cnt = 0;
-    const ulonglong2* c2 = reinterpret_cast<const ulonglong2*>(sh->cand);  // (cand[n] = 0 when n is odd)
+    if (my != 0ull) {  // (whole warps beyond the list skip the loop)
+      const ulonglong2* c2 = reinterpret_cast<const ulonglong2*>(sh->cand);  // (cand[n] = 0 when n is odd)
 #pragma unroll 4
-    for (int j = part; j < n2; j += tpc) {
-      const ulonglong2 v = c2[j];
-      cnt += (v.x > my ? 1 : 0) + (v.y > my ? 1 : 0);
+      for (int j = part; j < n2; j += tpc) {
+        const ulonglong2 v = c2[j];
+        cnt += (v.x > my ? 1 : 0) + (v.y > my ? 1 : 0);
+      }
     }
     cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
     cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
     if (tpc == 8) cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
     if (i < n && part == 0) {
       if (my == 0ull) atomicAdd(&sh->n_zero, 1);
-      else if (cnt < k) ranked[cnt] = my;
+      else if (cnt < k) {
+        ranked[cnt] = my;
+        sh->rankcell[cnt] = (uint32_t)i;
+      }
     }
   }
   __syncthreads();
+  SEL_STAMP(13);
   const int valid = n - sh->n_zero;
   const int npos = valid < k ? valid : k;
   const uint32_t hw_elems = (uint32_t)(a.H * a.W);
@@ -293,17 +292,17 @@ __device__ __noinline__ int sel_rank_emit(const SelArgs& a, SelShared* sh, int b
     a.out_index[slot * 2 + 1] = ix;
     a.out_label[slot] = lab;
     a.out_score[slot] = s;
+    if (tid == k - 1 && T_key != 0u) {  // (denormal sigmoids carry no relative guard band: leave those to the exhaustive pass)
+      const float s_T = sh->s_T;
+      sh->flag = ((s_T == 0.0f || s_T >= 1e-30f) && s_T < __fmul_rn(s, 1.0f - 2e-5f)) ? 0 : 1;
+    }
     if (a.box.enabled) {
-      box_one(a.box, b, slot, iy, ix);
+      if (have_box) box_store(a.box, slot, sh->cellbox[sh->rankcell[tid]]);
+      else box_one(a.box, b, slot, iy, ix);
       if (s < a.box.thr) atomicMin(&sh->first_below, tid);
     }
-  } else if (tid == kSelThreads - 32 && T_key != 0u) {
-    int bad = 1;
-    if (valid >= k) {
-      const uint32_t rk = reject_key_for_score(key_to_float(composite_key(ranked[k - 1])));
-      bad = (rk != 0u && rk >= T_key) ? 0 : 1;
-    }
-    sh->flag = bad;
+  } else if (tid == kSelThreads - 32 && T_key != 0u && valid < k) {
+    sh->flag = 1;
   }
   __syncthreads();
   if (tid == 0 && a.box.enabled && npos == k) a.box.count[b] = sh->first_below;  // (npos < k: sel_finish, after the fillers)
@@ -727,15 +726,27 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
     __syncthreads();
     SEL_STAMP(12);
     // ---- 3c. one thread per queued cell: peak test, sigmoid, final key into the cell's candidate slot ----
-    for (int i = tid; i < n; i += kSelThreads) sh->cand[i] = sel_test_cell(a, sh, b, i);
-    if (tid == kSelThreads - 1 && (n & 1)) sh->cand[n] = 0ull;  // (the rank loop reads pairs; n < kSelCandCap when odd)
+    //          (warps 0-7), while the other warps do the size / offset / depth arithmetic of every queued cell — it
+    //          would otherwise sit, with its gathers and two fp64 divisions, at the very end of the pass
+    if (tid < 256) {
+      for (int i = tid; i < n; i += 256) sh->cand[i] = sel_test_cell(sh, i);
+      if (tid == 255) {
+        if (n & 1) sh->cand[n] = 0ull;  // (the rank loop reads pairs; n < kSelCandCap when odd)
+        sh->s_T = sigmoid_ref(T_f);     // (for the completeness test of sel_rank_emit)
+      }
+    } else if (a.box.enabled) {
+      for (int i = tid - 256; i < n; i += kSelThreads - 256) {
+        const uint32_t pos = sh->cellpos[i];
+        sh->cellbox[i] = box_values(a.box, b, (int)(pos >> 16), (int)(pos & 0xffffu));
+      }
+    }
     __syncthreads();
     SEL_STAMP(4);
     SEL_NOTE(8, attempts);
     SEL_NOTE(9, nhot);
     SEL_NOTE(10, n);
     // ---- 4. rank, emit, and check that enough peaks reached T and nothing below T could have made it ----
-    const int npos = sel_rank_emit(a, sh, b, n, T_key);
+    const int npos = sel_rank_emit(a, sh, b, n, T_key, true);
     SEL_STAMP(5);
     if (T_key != 0u && sh->flag) {
       __syncthreads();
@@ -768,7 +779,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
     n = sel_slow(a, sh, fhm, bm);
     if (tid == 0 && (n & 1) && n < kSelCandCap) sh->cand[n] = 0ull;
     __syncthreads();
-    const int npos = sel_rank_emit(a, sh, b, n, 0u);
+    const int npos = sel_rank_emit(a, sh, b, n, 0u, false);
     if (npos < k) sel_finish(a, sh, b, npos);
   }
 }

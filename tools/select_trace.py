@@ -34,7 +34,7 @@ for rep in range(2):
   print("pass", rep + 1, "(the second pass exists only in -DTAUV_SEL_TWICE builds: same work, warm caches)")
   t0 = t[:, 1].min()
   names = {0: "start", 1: "dep wait done", 2: "threshold", 3: "hot blocks", 11: "  rows loaded", 12: "  neighbours", 4: "examined",
-           5: "ranked+emitted", 6: "finished"}
+           13: "  ranked", 5: "ranked+emitted", 6: "finished"}
   print(f"select_kernel phases, B={B} C={C} {H}x{W} k={K} (us after the first CTA passed griddepcontrol.wait; mean / max over frames)")
   for i, nme in names.items():
       col = t[:, i][t[:, i] > 0]
