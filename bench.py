@@ -324,7 +324,8 @@ def median(xs):
 
 def time_kernel(fn, reps=7, warmup=3, inner=4):
     """Median device time (us) per call of fn() over `reps` timings of `inner` back-to-back calls, CUDA events on the
-    current stream (one call between two events on an idle stream would time the host's launch path, not the device).
+    current stream, behind a short device-side spin (one call between two events on an idle stream would time the host's
+    launch path, not the device).
     The YOLACT inputs are several times larger than the 126 MB L2, so every launch streams from HBM."""
     for _ in range(warmup):
         r = fn()
@@ -332,6 +333,7 @@ def time_kernel(fn, reps=7, warmup=3, inner=4):
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        torch.cuda._sleep(1_000_000)  # ~0.5 ms of device-side spin: the host enqueues all `inner` calls meanwhile
         e0.record()
         for _ in range(inner):
             r = fn()
