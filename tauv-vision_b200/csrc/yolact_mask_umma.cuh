@@ -62,6 +62,10 @@ constexpr int kUmmaThreads = (kUmmaEpiWarps + kUmmaProdWarps + 1) * 32;
 #define TAUV_DEPTH_PROD_WARPS 8
 #endif
 constexpr int kUmmaDepthProdWarps = TAUV_DEPTH_PROD_WARPS;
+#ifndef TAUV_MASK_RAW_STAGES
+#define TAUV_MASK_RAW_STAGES 2
+#endif
+constexpr int kUmmaRawStages = TAUV_MASK_RAW_STAGES;  // fp32 prototype tiles in flight from HBM (TMA tensor loads)
 constexpr int kUmmaDepthThreads = (kUmmaEpiWarps + kUmmaDepthProdWarps + 1) * 32;
 template <bool kDepth>
 struct UmmaRoles {
@@ -80,6 +84,10 @@ struct UmmaSmem {
   // 1.6 TB/s (tools/store_bench.cu); 512-byte rows reach 3.9 TB/s.  So the four quadrant warps of a group assemble
   // whole 512-byte rows here and one of them hands each row to the bulk-copy engine.
   __align__(128) float stage[kUmmaGroups][kUmmaStageBufs][32][kUmmaM];  // 16 KB per buffer (one barrier per chunk)
+  // fp32 prototype tiles as the TMA engine delivers them: [stage][plane][pixel of the tile], 16 KB each (round 2: the
+  // producers' plain loads were the reducing kernel's bottleneck — 32 dependent-latency loads per pixel row)
+  __align__(128) float raw[kUmmaRawStages][kUmmaP][kUmmaM];
+  uint64_t raw_full[kUmmaRawStages], raw_empty[kUmmaRawStages];
   uint64_t a_full[kUmmaAStages], a_empty[kUmmaAStages], acc_full[2], acc_empty[2], frame_done;
   uint32_t tmem_base;
 };
@@ -189,7 +197,9 @@ template <bool kDepth>
 __global__ void __launch_bounds__(UmmaRoles<kDepth>::kThreads, 1) mask_umma_kernel(const __grid_constant__ MaskArgs a, int B,
                                                                     int m_base,
                                                                     const __grid_constant__ CUtensorMap out_map,
-                                                                    int use_tma) {
+                                                                    int use_tma,
+                                                                    const __grid_constant__ CUtensorMap in_map,
+                                                                    int use_tma_in) {
   constexpr int kProd = UmmaRoles<kDepth>::kProd;  // producer warps of this mode
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // (round up INSIDE the shared window: pointer arithmetic on the __shared__ array keeps the address space, an integer
@@ -219,6 +229,10 @@ __global__ void __launch_bounds__(UmmaRoles<kDepth>::kThreads, 1) mask_umma_kern
       mbar_init(&sm->acc_empty[s], kUmmaEpiWarps * 32);
     }
     mbar_init(&sm->frame_done, kUmmaEpiWarps * 32);
+    for (int s = 0; s < kUmmaRawStages; ++s) {
+      mbar_init(&sm->raw_full[s], 1);
+      mbar_init(&sm->raw_empty[s], kProd * 32);
+    }
     mbar_fence_init();
   }
   if (tid < kUmmaM) sm->zeros[tid] = 0.0f;
@@ -502,6 +516,37 @@ __global__ void __launch_bounds__(UmmaRoles<kDepth>::kThreads, 1) mask_umma_kern
     uint32_t fills[kUmmaAStages] = {}, frames = 0;
     int st = 0, cur_frame = -1, rows_frame = -1, n_rows = 0;
     int b = b_first, nt = nt_first - 1;
+    // TMA loads of the fp32 prototype tiles (producer thread 0 issues them, kUmmaRawStages tiles ahead of the
+    // conversion): the load cursor walks the same sequence of tiles — frames without detections skipped — as the loop
+    uint32_t raw_fills[kUmmaRawStages] = {}, raw_loads[kUmmaRawStages] = {};
+    int rs = 0, ls = 0, lb = b_first, lnt = nt_first - 1, l_rows_frame = -1, l_rows = 0;
+    long long lu = u0;
+    auto issue_next_load = [&]() {  // producer thread 0 only
+      for (; lu < u1; ++lu) {
+        if (++lnt == n_tiles) {
+          lnt = 0;
+          ++lb;
+        }
+        if (lb != l_rows_frame) {
+          l_rows = frame_rows(a, lb, m_base);
+          l_rows_frame = lb;
+        }
+        if (l_rows == 0) continue;
+        if (raw_loads[ls] > 0) mbar_wait(&sm->raw_empty[ls], (raw_loads[ls] - 1) & 1u);  // every producer is done with it
+        mbar_expect_tx(&sm->raw_full[ls], (uint32_t)sizeof(sm->raw[0]));
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                smem_u32(&sm->raw[ls][0][0])),
+            "l"(&in_map), "r"(lnt * kUmmaM), "r"(lb * kUmmaP), "r"(smem_u32(&sm->raw_full[ls]))
+            : "memory");
+        ++raw_loads[ls];
+        ls = ls + 1 == kUmmaRawStages ? 0 : ls + 1;
+        ++lu;
+        return;
+      }
+    };
+    if (use_tma_in && pt == 0)
+      for (int i = 0; i < kUmmaRawStages; ++i) issue_next_load();
     for (long long u = u0; u < u1; ++u) {
       if (++nt == n_tiles) {
         nt = 0;
@@ -546,7 +591,7 @@ __global__ void __launch_bounds__(UmmaRoles<kDepth>::kThreads, 1) mask_umma_kern
         cur_frame = b;
         ++frames;
       }
-      if (TAUV_MASK_PREFETCH > 0 && u + TAUV_MASK_PREFETCH < u1) {
+      if (!use_tma_in && TAUV_MASK_PREFETCH > 0 && u + TAUV_MASK_PREFETCH < u1) {
         // The producers' cost is the latency of their 32 loads per pixel row (2.8 us per tile straight from HBM under
         // the write stream).  Holding the next tile in registers spills (the kernel is capped at 96 registers by its
         // 17 warps) and a spill waits for the load; an L2 prefetch of a later tile costs two instructions per thread:
@@ -570,7 +615,32 @@ __global__ void __launch_bounds__(UmmaRoles<kDepth>::kThreads, 1) mask_umma_kern
         if (fills[st] > 0) mbar_wait(&sm->a_empty[st], (fills[st] - 1) & 1u);
         if (pt == 0) mask_stamp(a, u - u0, 0);
         // A tile: pixel rows pt, pt + producers, ...; 32 prototype values each -> 4 chunks of 8 bf16 (hi and lo)
-        if constexpr (kProd * 32 == 2 * kUmmaM) {
+        if (use_tma_in) {
+          // the fp32 tile is in shared memory ([plane][pixel]: consecutive lanes read consecutive words)
+          mbar_wait(&sm->raw_full[rs], raw_fills[rs] & 1u);
+          constexpr int kSplit = kProd * 32 / kUmmaM;             // producer threads per pixel row (1 or 2)
+          constexpr int kPlanes = kUmmaP / (kSplit > 0 ? kSplit : 1);
+          if constexpr (kSplit >= 1) {
+            const int pr = pt & (kUmmaM - 1), h = pt >> 7;
+            float f[kPlanes];
+#pragma unroll
+            for (int p = 0; p < kPlanes; ++p) f[p] = sm->raw[rs][kPlanes * h + p][pr];
+#pragma unroll
+            for (int c = 0; c < kPlanes / 8; ++c) {
+              uint4 qh, ql;
+              split_bf16x2(f[8 * c], f[8 * c + 1], qh.x, ql.x);
+              split_bf16x2(f[8 * c + 2], f[8 * c + 3], qh.y, ql.y);
+              split_bf16x2(f[8 * c + 4], f[8 * c + 5], qh.z, ql.z);
+              split_bf16x2(f[8 * c + 6], f[8 * c + 7], qh.w, ql.w);
+              *reinterpret_cast<uint4*>(sm->a[st][0] + sw64_offset(pr, (kPlanes / 8) * h + c)) = qh;
+              *reinterpret_cast<uint4*>(sm->a[st][1] + sw64_offset(pr, (kPlanes / 8) * h + c)) = ql;
+            }
+          }
+          mbar_arrive(&sm->raw_empty[rs]);
+          ++raw_fills[rs];
+          rs = rs + 1 == kUmmaRawStages ? 0 : rs + 1;
+          if (pt == 0) issue_next_load();
+        } else if constexpr (kProd * 32 == 2 * kUmmaM) {
           // two threads per pixel row: planes [16h, 16h + 16) -> chunks 2h, 2h + 1
           const int pr = pt & (kUmmaM - 1), h = pt >> 7;
           const int pix = nt * kUmmaM + pr;
@@ -695,6 +765,30 @@ static bool make_out_map(const MaskArgs& a, int B, CUtensorMap* map) {
                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// proto[B][P][HW] fp32 as a 2-D tensor map {HW, B*P} with box {128 pixels, 32 planes} (pixels beyond HW read as zero)
+static bool make_in_map(const MaskArgs& a, int B, CUtensorMap* map) {
+  const long long HW = (long long)a.H * a.W;
+  if (HW % 4 != 0 || (uintptr_t)a.proto % 16 != 0 || a.P != kUmmaP) return false;
+  static EncodeTiledFn encode = nullptr;  // (idempotent lookup; benign race)
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+      (void)cudaGetLastError();
+      return false;
+    }
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)HW, (cuuint64_t)B * kUmmaP};
+  const cuuint64_t strides[1] = {(cuuint64_t)HW * 4};  // bytes, dim 1
+  const cuuint32_t box[2] = {(cuuint32_t)kUmmaM, (cuuint32_t)kUmmaP};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.proto), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int launch_mask_umma(const MaskArgs& a, int B, int max_rows, cudaStream_t st) {
   const size_t smem = sizeof(UmmaSmem) + 1024;
   const bool depth = a.acc != nullptr;
@@ -706,9 +800,12 @@ static int launch_mask_umma(const MaskArgs& a, int B, int max_rows, cudaStream_t
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   const int use_tma = !depth && !debug_env("TAUV_MASK_NO_TMA") && make_out_map(a, B, &map) ? 1 : 0;
+  CUtensorMap in_map;
+  memset(&in_map, 0, sizeof(in_map));
+  const int use_tma_in = !debug_env("TAUV_MASK_NO_TMA_IN") && make_in_map(a, B, &in_map) ? 1 : 0;
   for (int m_base = 0; m_base < max_rows; m_base += kUmmaNMax) {
-    if (depth) mask_umma_kernel<true><<<(unsigned)grid, kUmmaDepthThreads, smem, st>>>(a, B, m_base, map, 0);
-    else mask_umma_kernel<false><<<(unsigned)grid, kUmmaThreads, smem, st>>>(a, B, m_base, map, use_tma);
+    if (depth) mask_umma_kernel<true><<<(unsigned)grid, kUmmaDepthThreads, smem, st>>>(a, B, m_base, map, 0, in_map, use_tma_in);
+    else mask_umma_kernel<false><<<(unsigned)grid, kUmmaThreads, smem, st>>>(a, B, m_base, map, use_tma, in_map, use_tma_in);
     TAUV_LAUNCH_CHECK("mask_umma_kernel");
   }
   return 0;
