@@ -306,7 +306,7 @@ __device__ __forceinline__ LinearTap linear_tap(int dst, float scale, int in_siz
 // MODE 0: nearest (yolact_node.py:135, followed by the node's `mask_np > 0.5` at :178); 1: bilinear
 // (evaluate_batch.py:101-102).  Rows >= n_keep[b] are not written.
 template <int MODE, int VEC>
-__global__ void __launch_bounds__(256) mask_binary_resize_kernel(const float* __restrict__ low,
+__global__ void __launch_bounds__(256) mask_binary_resize_kernel(const float* __restrict__ low, const float4* __restrict__ box,
                                                                  const int32_t* __restrict__ n_keep, int n_host, int top_k,
                                                                  int H, int W, int Ho, int Wo, uint8_t* __restrict__ out) {
   const int j = blockIdx.y, b = blockIdx.z;
@@ -317,11 +317,18 @@ __global__ void __launch_bounds__(256) mask_binary_resize_kernel(const float* __
   if (p0 >= (long long)Ho * Wo) return;
   const int yo = (int)(p0 / Wo), xo = (int)(p0 - (long long)yo * Wo);
   const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
-  unsigned bits = 0u;
-  if (MODE == 0) {
+  unsigned bits[VEC >= 4 ? VEC / 4 : 1] = {};
+  bool zero = false;
+  if (box) {  // pixels whose source taps lie clear of the crop box (two-pixel margin) are zeros by construction
+    const CropBounds cb = crop_bounds(box[row], H, W);
+    const float ys = ((float)yo + 0.5f) * sy, x0s = ((float)xo + 0.5f) * sx, x1s = ((float)(xo + VEC - 1) + 0.5f) * sx;
+    zero = ys < cb.top - 2.0f || ys > cb.bottom + 3.0f || x1s < cb.left - 2.0f || x0s > cb.right + 3.0f;
+  }
+  if (zero) {
+  } else if (MODE == 0) {
     const float* r = src + (size_t)nearest_src(yo, sy, H) * W;
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) bits |= (r[nearest_src(xo + v, sx, W)] > 0.5f ? 1u : 0u) << (8 * v);
+    for (int v = 0; v < VEC; ++v) bits[v >> 2] |= (r[nearest_src(xo + v, sx, W)] > 0.5f ? 1u : 0u) << (8 * (v & 3));
   } else {
     const LinearTap ty = linear_tap(yo, sy, H);
     const float* r0 = src + (size_t)ty.i0 * W;
@@ -330,12 +337,47 @@ __global__ void __launch_bounds__(256) mask_binary_resize_kernel(const float* __
     for (int v = 0; v < VEC; ++v) {
       const LinearTap tx = linear_tap(xo + v, sx, W);
       const float val = ty.w0 * (tx.w0 * r0[tx.i0] + tx.w1 * r0[tx.i1]) + ty.w1 * (tx.w0 * r1[tx.i0] + tx.w1 * r1[tx.i1]);
-      bits |= (val > 0.5f ? 1u : 0u) << (8 * v);
+      bits[v >> 2] |= (val > 0.5f ? 1u : 0u) << (8 * (v & 3));
     }
   }
   uint8_t* dst = out + row * (size_t)Ho * Wo + p0;
-  if (VEC == 4) *reinterpret_cast<uint32_t*>(dst) = bits;
-  else *dst = (uint8_t)bits;
+  if constexpr (VEC == 16) *reinterpret_cast<uint4*>(dst) = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+  else if constexpr (VEC == 4) *reinterpret_cast<uint32_t*>(dst) = bits[0];
+  else *dst = (uint8_t)bits[0];
+}
+
+// Nearest mode, rows that are multiples of 16 bytes: one thread per (SOURCE row, 16 output pixels).  Nearest resizing
+// repeats a source row in every output row that maps to it (2.6 of them at 276 -> 720), so the 16 bytes are made once
+// and stored that many times; and a source row (or a column chunk) that lies clear of the detection's crop box is
+// zeros by construction (the assembly has applied the same box), so it is stored without being read.
+__global__ void __launch_bounds__(256) mask_binary_nearest16_kernel(const float* __restrict__ low, const float4* __restrict__ box,
+                                                                    const int32_t* __restrict__ n_keep, int n_host, int top_k,
+                                                                    int H, int W, int Ho, int Wo, uint8_t* __restrict__ out) {
+  const int j = blockIdx.y, b = blockIdx.z;
+  if (j >= (n_keep ? n_keep[b] : n_host)) return;
+  const size_t row = (size_t)b * top_k + j;
+  const int chunks = Wo >> 4;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= H * chunks) return;
+  const int r = idx / chunks, xo = (idx - r * chunks) << 4;
+  const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
+  const int y0 = nearest_first_dst(r, sy, H, Ho), y1 = r + 1 < H ? nearest_first_dst(r + 1, sy, H, Ho) : Ho;
+  if (y0 >= y1) return;
+  unsigned bits[4] = {0u, 0u, 0u, 0u};
+  bool zero = false;
+  if (box) {  // (a one-pixel margin keeps this test independent of the rounding of the crop itself)
+    const CropBounds cb = crop_bounds(box[row], H, W);
+    const float x_lo = (float)nearest_src(xo, sx, W), x_hi = (float)nearest_src(xo + 15, sx, W);
+    zero = (float)r < cb.top - 1.0f || (float)r > cb.bottom + 1.0f || x_hi < cb.left - 1.0f || x_lo > cb.right + 1.0f;
+  }
+  if (!zero) {
+    const float* src = low + (row * (size_t)H + r) * W;
+#pragma unroll
+    for (int v = 0; v < 16; ++v) bits[v >> 2] |= (src[nearest_src(xo + v, sx, W)] > 0.5f ? 1u : 0u) << (8 * (v & 3));
+  }
+  const uint4 q = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+  uint8_t* dst = out + row * (size_t)Ho * Wo + xo;
+  for (int yo = y0; yo < y1; ++yo) *reinterpret_cast<uint4*>(dst + (size_t)yo * Wo) = q;
 }
 
 static size_t mask_binary_ws_bytes(int B, int H, int W, int top_k) {
@@ -357,14 +399,22 @@ static int run_mask_binary(MaskArgs a, int B, int max_rows, int Ho, int Wo, int 
   if (rc) return rc;
   const long long total = (long long)Ho * Wo;
   const bool vec = Wo % 4 == 0 && (uintptr_t)out % 4 == 0;
-  const long long per_block = 256LL * (vec ? 4 : 1);
+  // 16 bytes per thread (one 128-bit store, 512 bytes per warp instruction) when the rows allow it: the pass writes one
+  // byte per camera pixel and kept mask — 9.4 GB per 64 frames — and was bound by its 4-byte stores and per-pixel setup
+  const bool vec16 = Wo % 16 == 0 && (uintptr_t)out % 16 == 0;
+  const long long per_block = 256LL * (vec16 ? 16 : vec ? 4 : 1);
   const dim3 grid((unsigned)((total + per_block - 1) / per_block), (unsigned)a.top_k, (unsigned)B);
 #define TAUV_RESIZE(MODE, VEC) \
-  mask_binary_resize_kernel<MODE, VEC><<<grid, 256, 0, st>>>(a.out, a.n_keep, a.n_host, a.top_k, a.H, a.W, Ho, Wo, out)
+  mask_binary_resize_kernel<MODE, VEC><<<grid, 256, 0, st>>>(a.out, reinterpret_cast<const float4*>(a.box), a.n_keep, \
+                                                             a.n_host, a.top_k, a.H, a.W, Ho, Wo, out)
   if (mode == TAUV_RESIZE_NEAREST) {
-    if (vec) TAUV_RESIZE(0, 4); else TAUV_RESIZE(0, 1);
+    if (vec16) {
+      const dim3 g16((unsigned)(((long long)a.H * (Wo >> 4) + 255) / 256), (unsigned)a.top_k, (unsigned)B);
+      mask_binary_nearest16_kernel<<<g16, 256, 0, st>>>(a.out, reinterpret_cast<const float4*>(a.box), a.n_keep, a.n_host,
+                                                        a.top_k, a.H, a.W, Ho, Wo, out);
+    } else if (vec) TAUV_RESIZE(0, 4); else TAUV_RESIZE(0, 1);
   } else {
-    if (vec) TAUV_RESIZE(1, 4); else TAUV_RESIZE(1, 1);
+    if (vec16) TAUV_RESIZE(1, 16); else if (vec) TAUV_RESIZE(1, 4); else TAUV_RESIZE(1, 1);
   }
 #undef TAUV_RESIZE
   TAUV_LAUNCH_CHECK("mask_binary_resize_kernel");

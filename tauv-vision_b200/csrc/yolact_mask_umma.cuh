@@ -46,7 +46,7 @@ constexpr int kUmmaEpiWarps = TAUV_MASK_EPI_WARPS, kUmmaProdWarps = TAUV_MASK_PR
                               // kernel does not care: 1, 2, 3, 6 -> 808-810 us, and holding the next tile in registers: 814)
 #endif
 #ifndef TAUV_MASK_A_STAGES
-#define TAUV_MASK_A_STAGES 3
+#define TAUV_MASK_A_STAGES 2
 #endif
 #ifndef TAUV_MASK_STAGE_BUFS
 #define TAUV_MASK_STAGE_BUFS 2
@@ -63,7 +63,7 @@ constexpr int kUmmaThreads = (kUmmaEpiWarps + kUmmaProdWarps + 1) * 32;
 #endif
 constexpr int kUmmaDepthProdWarps = TAUV_DEPTH_PROD_WARPS;
 #ifndef TAUV_MASK_RAW_STAGES
-#define TAUV_MASK_RAW_STAGES 2
+#define TAUV_MASK_RAW_STAGES 3  // (with 2 A stages: writer 895 us vs 920 with 2 raw + 3 A stages; the reducing kernel does not care)
 #endif
 constexpr int kUmmaRawStages = TAUV_MASK_RAW_STAGES;  // fp32 prototype tiles in flight from HBM (TMA tensor loads)
 constexpr int kUmmaDepthThreads = (kUmmaEpiWarps + kUmmaDepthProdWarps + 1) * 32;

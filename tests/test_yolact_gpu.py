@@ -375,11 +375,11 @@ def test_mask_binary_golden(yl, simt):
 
 
 @pytest.mark.parametrize("H,W,K,ho,wo", [(138, 138, 100, 480, 640), (138, 138, 37, 550, 550), (69, 69, 150, 69, 69),
-                                          (276, 276, 20, 241, 323)])
+                                          (276, 276, 20, 241, 323), (69, 69, 60, 150, 212)])
 @pytest.mark.parametrize("mode", ["nearest", "bilinear"])
 def test_mask_binary_vs_oracle(yl, mode, H, W, K, ho, wo):
     """Full-size prototype maps, camera (480x640) and network-input (550x550) resolutions, identity and odd sizes
-    (241x323 takes the byte-store path).  Every pixel whose resized fp32 mask value is clear of 0.5 must match the
+    (241x323 takes the byte-store path, 150x212 the 4-byte one, rows that are multiples of 16 the 128-bit one).  Every pixel whose resized fp32 mask value is clear of 0.5 must match the
     oracle; the rest (within the tensor-core contraction error of the threshold) are counted and must be rare."""
     proto, coeff, box = synth.mask_inputs(32, H, W, K, seed=H + K)
     d = yl.dev
