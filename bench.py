@@ -14,7 +14,7 @@ Workloads
   mixed (configs[3]): 256 frames, each with a CenterNet head and a YOLACT head, sharded over the N GPUs
       (`shard.frame_range`, strong scaling).  One step = CenterNet decode + YOLACT detect + fused mask/depth consumer of
       the rank's frames; `e2e` additionally copies the packed results to the host and gathers them on rank 0 in frame
-      order (`shard.gather_host`) inside the timed region — the "final host gather" of SURVEY.md section 8e.
+      order (`shard.gather_frames`) inside the timed region — the "final host gather" of SURVEY.md section 8e.
 
 value     : frames/s with inputs resident in HBM; the K-step block is timed `--blocks` (>= 5) times with CUDA events on
             the launching stream and the MEDIAN block is reported (`block_ms` lists them all); max over ranks.
@@ -755,11 +755,12 @@ def run_mixed(ctx):
     # e2e: the same step + device->host copies of the packed results + the host gather on rank 0, in frame order
     def e2e_step():
         cn, yd, mean, cnt = step()
-        local = cn.to_host()                                   # one D2H of the CenterNet detections (synchronises)
-        local.update({"yl_keep": yd.keep.cpu().numpy(), "yl_n_keep": yd.n_keep.cpu().numpy(),
-                      "yl_box": yd.box.cpu().numpy(), "yl_score": yd.score.cpu().numpy(),
-                      "yl_class": yd.class_id.cpu().numpy(), "yl_depth_mean": mean.cpu().numpy()})
-        return shard.gather_host(local), sum(v.nbytes for v in local.values() if v is not None)
+        # the packed results stay on the device; ONE gather (NVLink) and ONE device->host copy on rank 0, frame order
+        local = {"index": cn.index, "label": cn.label, "score": cn.score, "yx": cn.yx, "hw": cn.hw, "count": cn.count,
+                 "yl_keep": yd.keep, "yl_n_keep": yd.n_keep, "yl_box": yd.box, "yl_score": yd.score,
+                 "yl_class": yd.class_id, "yl_depth_mean": mean}
+        nbytes = sum(v.numel() * v.element_size() for v in local.values())
+        return shard.gather_frames(local, MIXED_FRAMES), nbytes
 
     e2e_step()
     ctx.barrier()
@@ -792,9 +793,9 @@ def run_mixed(ctx):
         "cpu_baseline": None,
         "e2e": {"value": MIXED_FRAMES * args.e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps,
-                "note": "inputs resident (the heads are produced on the owning GPU); every step copies the packed "
-                        "CenterNet + YOLACT results to the host and gathers them on rank 0 in frame order "
-                        "(shard.gather_host) inside the timed region, wall clock between barriers"},
+                "note": "inputs resident (the heads are produced on the owning GPU); every step gathers the packed "
+                        "CenterNet + YOLACT results on rank 0 in frame order (shard.gather_frames: one NCCL gather of the "
+                        "device buffers + one device->host copy) inside the timed region, wall clock between barriers"},
         "gpu_launches": (2 + 2 + 3) * K * NB,
         "clocks": clocks.summary(),
     }

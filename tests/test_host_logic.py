@@ -57,6 +57,15 @@ def _gloo_worker(rank: int, world: int, port: int, n_frames: int, q):
         lo, hi = shard.frame_range(rank, world, n_frames)
         local = {"score": mine.numpy() * 10.0, "count": np.arange(lo, hi, dtype=np.int32), "depth": None}
         got = shard.gather_host(local, dst=0)
+        # the packed single-collective form (tensors in, one gather, one host copy on dst)
+        packed = shard.gather_frames({"score": mine * 10.0, "count": torch.arange(lo, hi, dtype=torch.int32),
+                                      "yx": mine.double()[:, :2].reshape(-1, 1, 2)}, n_frames, dst=0)
+        if rank == 0:
+            assert packed["score"][:, 0].tolist() == [10.0 * i for i in range(n_frames)]
+            assert packed["count"].tolist() == list(range(n_frames)) and packed["count"].dtype == np.int32
+            assert packed["yx"].shape == (n_frames, 1, 2) and packed["yx"].dtype == np.float64
+        else:
+            assert packed is None
         # timing reduction used by bench.py: max over ranks
         t = torch.tensor([float(rank + 1)], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -88,6 +97,8 @@ def test_world2_gloo_gather_is_in_frame_order():
 def test_gather_host_without_process_group_is_identity():
     local = {"score": np.zeros((2, 3), np.float32)}
     assert shard.gather_host(local) is local
+    one = shard.gather_frames({"score": torch.ones((2, 3))}, 2)
+    assert one["score"].shape == (2, 3) and one["score"].dtype == np.float32
 
 
 # ---- patch_reference -------------------------------------------------------------------------------------------
