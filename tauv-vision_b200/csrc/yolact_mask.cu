@@ -6,10 +6,11 @@
 //
 // Two implementations behind one entry point:
 //   * mask_umma_kernel (yolact_mask_umma.cuh): the proto x coeff contraction on the 5th-gen tensor cores —
-//     tcgen05.mma kind::f16 (bf16 operands, fp32 accumulate in TMEM), M = 128 detections x N = 256 pixels
-//     per tile, sigmoid + crop applied on the TMEM -> register read-back.  Used whenever the shape fits.
-//   * mask_simt_kernel: exact-fp32 CUDA-core version for shapes the tensor-core tiling does not take
-//     (P not a multiple of 16 or > 64, odd H*W) and as the on-device cross-check in the tests.
+//     tcgen05.mma kind::f16 (bf16 hi/lo operand pairs, fp32 accumulate in TMEM), M = 128 pixels x N <= 256
+//     detections per tile, prototype tiles by TMA tensor loads, sigmoid + crop applied on the TMEM -> register
+//     read-back, rows written by TMA tensor stores.  Used for P == 32 with 16-byte aligned coefficients.
+//   * mask_simt_kernel: exact-fp32 CUDA-core version for every other shape (P != 32, unaligned coefficients) and as
+//     the on-device cross-check in the tests.
 #include "common.cuh"
 #include "yolact_common.cuh"
 
