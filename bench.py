@@ -482,6 +482,18 @@ def run_centernet(ctx):
     t_bm = e0.elapsed_time(e1) / K
     del ws_bm
 
+    # the heatmap term of the training loss fused with the target render: forward, forward + backward
+    tc_f = SimpleNamespace(keypoint_heatmap_sigma=SIGMA, heatmap_focal_loss_a=2.0, heatmap_focal_loss_b=4.0)
+    t_focal, _ = time_kernel(lambda: L.heatmap_focal_loss(logits, truth, mc, tc_f), reps=5, warmup=2)
+    xg = logits.detach().clone().requires_grad_(True)
+
+    def focal_fb():
+        xg.grad = None
+        L.heatmap_focal_loss(xg, truth, mc, tc_f).backward()
+
+    t_focal_fb, _ = time_kernel(focal_fb, reps=5, warmup=2)
+    del xg
+
     # ---- configs[2]: the YOLACT post-process kernels, same run, every rank ----
     yl = None
     if not args.no_yolact:
@@ -523,8 +535,12 @@ def run_centernet(ctx):
         "gaussian_encode_us": t_enc * 1e3,
         "gaussian_encode_gbs": algorithmic_bytes_encode(B_PER_GPU) / (t_enc * 1e-3) / 1e9,
         "gaussian_encode_frac": algorithmic_bytes_encode(B_PER_GPU) / (t_enc * 1e-3) / 1e9 / hbm_gbs,
+        "heatmap_focal_loss_us": t_focal, "heatmap_focal_loss_fwd_bwd_us": t_focal_fb,
+        "heatmap_focal_loss_note": "focal_loss(sigmoid(logits), generate_heatmap(truth)).sum() in one pass over the logits, "
+                                   "no target written (compute-bound: one exp, one log, one IEEE divide per cell); "
+                                   "backward = one more pass that writes the gradient; rank 0's figures",
     }
-    launches = 3 * K * NB + 2 * (K + 3) + (K + 3)  # a decode is 2 launches (block maxima, select), the encode 1
+    launches = 3 * K * NB + 2 * (K + 3) + (K + 3) + 22 * 2 + 22 * 3  # decode = 2 launches, encode 1, focal 2 (+1 backward)
     if yl is not None:
         det_us, mask_us, md_us, sc_us, match_us, mbn_us, mbb_us = vals[6 + NB:6 + NB + 7]
         nk = yl["n_keep_total"]

@@ -183,6 +183,28 @@ int tauv_gaussian_encode(const uint8_t* valid, const int64_t* label, const float
                          int n_objects, int C, int H, int W, int in_h, int in_w,
                          int downsample_ratio, double sigma, float* out, tauv_stream_t stream);
 
+/* The heatmap term of the CenterNet loss fused with its target render:
+ *   focal_loss(sigmoid(logits), generate_heatmap(truth), alpha, beta).sum()  — centernet/model/loss.py:182, :233-236,
+ *   :302-317.  The [B,C,H,W] target is never written.  Forward leaves, per frame, the sums of the two terms
+ *   frame_sums[b] = { sum of (1-p)^alpha log(clamp(p,1e-4)) over the positives (target isclose 1),
+ *                     sum of (1-t)^beta p^alpha log(clamp(1-p,1e-4)) over the other cells }   (double, fixed order)
+ *   and the number of positives frame_pos[b]; with N = sum_b frame_pos[b] the loss is -(sum_p + sum_n)/N for N > 0 and
+ *   -sum_p for N == 0 (loss.py:312-315).  Backward writes d(loss)/d(logits) * grad_out for that N (device scalars, so
+ *   neither call synchronises).  Needs W % 4 == 0, 16-byte aligned logits, <= 32 objects per frame and an 8-byte
+ *   aligned centre tensor (TAUV_E_UNSUPPORTED otherwise: the Python mirror then composes generate_heatmap with
+ *   elementwise torch ops on the GPU).  logits [B,C,H,W] f32 contiguous; truth as for tauv_gaussian_encode. */
+size_t tauv_centernet_focal_loss_workspace_bytes(int B, int C, int H, int W);
+int tauv_centernet_focal_loss(const float* logits, const uint8_t* valid, const int64_t* label,
+                              const float* center, int B, int n_objects, int C, int H, int W, int in_h,
+                              int in_w, int downsample_ratio, double sigma, double alpha, double beta,
+                              double* frame_sums, int64_t* frame_pos, void* workspace,
+                              size_t workspace_bytes, tauv_stream_t stream);
+int tauv_centernet_focal_loss_backward(const float* logits, const uint8_t* valid, const int64_t* label,
+                                       const float* center, int B, int n_objects, int C, int H, int W,
+                                       int in_h, int in_w, int downsample_ratio, double sigma,
+                                       double alpha, double beta, const int64_t* n_pos_total,
+                                       const float* grad_out, float* grad_logits, tauv_stream_t stream);
+
 /* generate_keypoint_heatmap(...) — centernet/model/loss.py:75-135
  *   kp_valid [B,m] u8, kp_label [B,m] i64, kp_center [B,m,2] f32, kp_object_index [B,m] i64,
  *   center [B,n,2] f32 (object centres)

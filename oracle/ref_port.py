@@ -179,6 +179,28 @@ def generate_heatmap(valid, label, center, n_labels: int, out_h: int, out_w: int
     return torch.nan_to_num(out)
 
 
+def focal_loss(prediction: torch.Tensor, truth: torch.Tensor, alpha: float, beta: float) -> torch.Tensor:
+    """loss.py:302-317 — penalty-reduced pixelwise focal loss of CenterNet, elementwise; the caller sums it
+    (loss.py:233-234).  Positives are the cells whose target is (close to) 1; N counts them over the whole batch."""
+    p = torch.isclose(truth, torch.ones(1))
+    N = torch.sum(p)
+    loss_p = ((1 - prediction) ** alpha) * torch.log(torch.clamp(prediction, min=1e-4)) * p.float()
+    loss_n = ((1 - truth) ** beta) * (prediction ** alpha) * torch.log(torch.clamp(1 - prediction, min=1e-4)) * (1 - p.float())
+    if N == 0:
+        return -loss_p
+    return -(loss_p + loss_n) / N
+
+
+def heatmap_focal_loss(logits, valid, label, center, in_h: int, in_w: int, downsample_ratio: int, sigma: float,
+                       alpha: float, beta: float):
+    """loss.py:182 + :233-236 — the heatmap term of the CenterNet loss: render the Gaussian target, focal loss of the
+    sigmoid of the logits against it, summed.  Returns (loss scalar, n_pos)."""
+    B, C, H, W = logits.shape
+    target = generate_heatmap(valid, label, center, C, H, W, in_h, in_w, downsample_ratio, sigma)
+    loss = focal_loss(torch.sigmoid(logits), target, alpha, beta)
+    return loss.sum(), int(torch.isclose(target, torch.ones(1)).sum())
+
+
 def generate_keypoint_heatmap(kp_valid, kp_label, kp_center, kp_object_index, center, n_keypoints: int,
                               out_h: int, out_w: int, in_h: int, in_w: int, downsample_ratio: int,
                               sigma_heatmap: float, sigma_affinity: float):

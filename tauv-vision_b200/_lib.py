@@ -56,6 +56,11 @@ _SIGNATURES = {
     "tauv_depth_decode": (c_int, [_F, c_int64, _F, c_void_p]),
     "tauv_gaussian_encode": (c_int, [_U8, _I64, _F, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double,
                                      _F, c_void_p]),
+    "tauv_centernet_focal_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "tauv_centernet_focal_loss": (c_int, [_F, _U8, _I64, _F, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                          c_double, c_double, c_double, _D, _I64, c_void_p, c_size_t, c_void_p]),
+    "tauv_centernet_focal_loss_backward": (c_int, [_F, _U8, _I64, _F, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                                   c_int, c_double, c_double, c_double, _I64, _F, _F, c_void_p]),
     "tauv_keypoint_encode": (c_int, [_U8, _I64, _F, _I64, _F, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_double, c_double, _F, _F, _F, c_void_p]),
     "tauv_out_index_offset": (c_int, [_F, c_int64, c_int, c_int, c_int, c_int, c_int, _I64, _F, c_void_p]),

@@ -4,8 +4,9 @@
 ``out_index_for_position`` (:138-142), the sub-pixel offset target (:263-264) and
 ``gaussian_splat`` (missing from the snapshot; call sites decode.py:328-332).
 
-The loss arithmetic itself (focal / L1 / angle / depth terms, autograd) is out of scope: it consumes
-the tensors produced here.  Kernels: csrc/gaussian_encode.cu.
+Of the loss arithmetic, the heatmap term — the only one that touches [B,C,H,W] tensors — is here too, fused with
+its target render (``heatmap_focal_loss``, loss.py:182 + :233-236 + :302-317, with autograd); the per-object L1 /
+angle / depth terms stay with the caller.  Kernels: csrc/gaussian_encode.cu.
 """
 from __future__ import annotations
 
@@ -105,3 +106,79 @@ def gaussian_splat(h: int, w: int, cy: int, cx: int, sigma: float, device=None) 
         _lib.check(_lib.load().tauv_gaussian_splat(int(h), int(w), int(cy), int(cx), float(sigma), _lib.fptr(out),
                                                    _lib.stream_ptr(dev)))
     return out
+
+
+def focal_loss(prediction: torch.Tensor, truth: torch.Tensor, alpha: float, beta: float) -> torch.Tensor:
+    """Elementwise penalty-reduced focal loss — reference loss.py:302-317, the same tensor expressions (any device;
+    the reference's callers sum it).  ``heatmap_focal_loss`` is the fused form of
+    ``focal_loss(sigmoid(logits), generate_heatmap(...)).sum()``."""
+    p = torch.isclose(truth, torch.ones(1, device=truth.device))
+    N = torch.sum(p)
+    loss_p = ((1 - prediction) ** alpha) * torch.log(torch.clamp(prediction, min=1e-4)) * p.float()
+    loss_n = ((1 - truth) ** beta) * (prediction ** alpha) * torch.log(torch.clamp(1 - prediction, min=1e-4)) * (1 - p.float())
+    if N == 0:
+        return -loss_p
+    return -(loss_p + loss_n) / N
+
+
+class _HeatmapFocalLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, valid, label, center, geom, sigma, alpha, beta):
+        dev = logits.device
+        B, C, H, W = logits.shape
+        n = valid.shape[1]
+        lib = _lib.load()
+        sums = torch.empty((B, 2), dtype=torch.float64, device=dev)
+        pos = torch.empty((B,), dtype=torch.int64, device=dev)
+        ws = _lib.workspace(dev, lib.tauv_centernet_focal_loss_workspace_bytes(B, C, H, W))
+        with torch.cuda.device(dev):
+            _lib.check(lib.tauv_centernet_focal_loss(
+                _lib.fptr(logits), _lib.u8ptr(valid), _lib.i64ptr(label), _lib.fptr(center), B, n, C, H, W, *geom,
+                float(sigma), float(alpha), float(beta), _lib.dptr(sums), _lib.i64ptr(pos), ws.data_ptr(), ws.numel(),
+                _lib.stream_ptr(dev)))
+        n_pos = pos.sum().reshape(1)
+        sp, sn = sums[:, 0].sum(), sums[:, 1].sum()
+        loss = torch.where(n_pos[0] > 0, -(sp + sn) / n_pos[0].clamp(min=1).to(torch.float64), -sp)
+        ctx.save_for_backward(logits, valid, label, center, n_pos)
+        ctx.meta = (geom, float(sigma), float(alpha), float(beta))
+        ctx.mark_non_differentiable(n_pos)
+        return loss.to(torch.float32), n_pos
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_n):
+        logits, valid, label, center, n_pos = ctx.saved_tensors
+        geom, sigma, alpha, beta = ctx.meta
+        dev = logits.device
+        B, C, H, W = logits.shape
+        grad = torch.empty_like(logits)
+        go = grad_loss.to(torch.float32).contiguous().reshape(1)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().tauv_centernet_focal_loss_backward(
+                _lib.fptr(logits), _lib.u8ptr(valid), _lib.i64ptr(label), _lib.fptr(center), B, valid.shape[1], C, H, W,
+                *geom, sigma, alpha, beta, _lib.i64ptr(n_pos), _lib.fptr(go), _lib.fptr(grad), _lib.stream_ptr(dev)))
+        return grad, None, None, None, None, None, None, None
+
+
+def heatmap_focal_loss(heatmap_logits: torch.Tensor, truth, model_config, train_config, return_n_pos: bool = False):
+    """``focal_loss(F.sigmoid(prediction.heatmap), generate_heatmap(truth, ...), a, b).sum()`` — the heatmap term of the
+    reference's loss (loss.py:182, :233-236) — in one pass over the logits, without materialising the target, with
+    autograd (one more pass writes the gradient).  ``heatmap_logits`` is ``prediction.heatmap`` (pre-sigmoid, [B,C,H,W]);
+    the class count comes from its shape.  Returns the fp32 scalar (and the number of positive cells N if asked)."""
+    dev = _lib.require_cuda(heatmap_logits, truth.valid, truth.label, truth.center)
+    B, C, H, W = heatmap_logits.shape
+    if (H, W) != (int(model_config.out_h), int(model_config.out_w)):
+        raise ValueError(f"heatmap is {H}x{W}, the model's output grid is {model_config.out_h}x{model_config.out_w}")
+    alpha, beta = float(train_config.heatmap_focal_loss_a), float(train_config.heatmap_focal_loss_b)
+    sigma = float(train_config.keypoint_heatmap_sigma)
+    logits = _lib.f32c(heatmap_logits)
+    valid, label, center = _u8(truth.valid), _i64(truth.label), _lib.f32c(truth.center)
+    fused = W % 4 == 0 and logits.data_ptr() % 16 == 0 and valid.shape[1] <= 32 and center.data_ptr() % 8 == 0
+    if not fused:
+        # shapes the fused kernel does not take: the same arithmetic from the rendered target, still on the GPU
+        target = generate_heatmap(truth, model_config, train_config, type("O", (), {"n_labels": C}))
+        loss = focal_loss(torch.sigmoid(logits), target, alpha, beta).sum()
+        n_pos = torch.isclose(target, torch.ones(1, device=dev)).sum().reshape(1)
+        return (loss, n_pos) if return_n_pos else loss
+    geom = (int(model_config.in_h), int(model_config.in_w), int(model_config.downsample_ratio))
+    loss, n_pos = _HeatmapFocalLoss.apply(logits, valid, label, center, geom, sigma, alpha, beta)
+    return (loss, n_pos) if return_n_pos else loss

@@ -509,13 +509,336 @@ static void band_plan(int H, int W, long long planes, int* bands, int* rows) {
   *bands = (H + r - 1) / r;
 }
 
-}  // namespace tauv
 
-using namespace tauv;
+// ----------------------------------------------------------------------------------------------
+// Heatmap focal loss fused with the target render (loss.py:182 + :233-236 + :302-317):
+//   loss = focal_loss(sigmoid(logits), generate_heatmap(truth)).sum()
+// The 335 MB target is never written: every warp renders its chunk of the target in registers (exactly as
+// gaussian_encode_warp_kernel does), reads the same chunk of the logits once, and reduces.  The reference makes ~20
+// elementwise passes over [B,C,H,W] tensors for this term (sigmoid, isclose, two pows, two clamps, two logs, masks,
+// the division by N, the sum) plus the target write.  Forward: per-chunk partial sums (double) and positive counts, summed
+// per frame in a fixed order by a second tiny launch (deterministic).  Backward: the gradient with respect to the logits
+// in one more pass (the target is rendered again rather than stored).
+// ----------------------------------------------------------------------------------------------
+struct FocalPow {
+  float e;
+  int kind;  // 2: x*x, 3: x*x*x (ATen's special cases of pow(tensor, scalar)), 0: powf
+};
+__device__ __forceinline__ float focal_pow(float x, FocalPow p) {
+  if (p.kind == 2) return __fmul_rn(x, x);
+  if (p.kind == 3) return __fmul_rn(__fmul_rn(x, x), x);
+  return powf(x, p.e);
+}
+// d/dx x^e (autograd: e * x^(e-1))
+__device__ __forceinline__ float focal_dpow(float x, FocalPow p) {
+  if (p.kind == 2) return __fmul_rn(2.0f, x);
+  if (p.kind == 3) return __fmul_rn(3.0f, __fmul_rn(x, x));
+  return __fmul_rn(p.e, powf(x, p.e - 1.0f));
+}
+// torch.isclose(t, 1): |t - 1| <= atol + rtol * |1| with the defaults, evaluated in fp32 like ATen does
+__device__ __forceinline__ bool focal_is_pos(float t) {
+  const float allowed = __fadd_rn(1e-8f, __fmul_rn(1e-5f, 1.0f));
+  const float err = fabsf(__fsub_rn(t, 1.0f));
+  return err <= allowed;  // (false for NaN / inf, like isfinite(actual_error) & ...)
+}
+
+// the four target values of strip t of the plane (see gaussian_encode_warp_kernel); mask == 0: zeros
+__device__ __forceinline__ float4 focal_target4(unsigned mask, int cy, int cx, int y, int x, float two_sigma2, bool big) {
+  if (mask == 0u) return make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!big) {
+    int b0 = 0x7fffffff, b1 = b0, b2 = b0, b3 = b0;
+    for (unsigned m = mask; m; m &= m - 1) {
+      const int j = __ffs(m) - 1;
+      const int dy = y - __shfl_sync(0xffffffffu, cy, j), dx = x - __shfl_sync(0xffffffffu, cx, j);
+      const int dy2 = dy * dy;
+      b0 = min(b0, dy2 + dx * dx);
+      b1 = min(b1, dy2 + (dx + 1) * (dx + 1));
+      b2 = min(b2, dy2 + (dx + 2) * (dx + 2));
+      b3 = min(b3, dy2 + (dx + 3) * (dx + 3));
+    }
+    return make_float4(gauss_from_d2(b0, two_sigma2), gauss_from_d2(b1, two_sigma2), gauss_from_d2(b2, two_sigma2),
+                       gauss_from_d2(b3, two_sigma2));
+  }
+  long long b0 = 0x7fffffffffffffffLL, b1 = b0, b2 = b0, b3 = b0;
+  for (unsigned m = mask; m; m &= m - 1) {
+    const int j = __ffs(m) - 1;
+    const long long dy = y - __shfl_sync(0xffffffffu, cy, j), dx = x - __shfl_sync(0xffffffffu, cx, j);
+    const long long dy2 = dy * dy;
+    b0 = min(b0, dy2 + dx * dx);
+    b1 = min(b1, dy2 + (dx + 1) * (dx + 1));
+    b2 = min(b2, dy2 + (dx + 2) * (dx + 2));
+    b3 = min(b3, dy2 + (dx + 3) * (dx + 3));
+  }
+  return make_float4(gauss_from_d2(b0, two_sigma2), gauss_from_d2(b1, two_sigma2), gauss_from_d2(b2, two_sigma2),
+                     gauss_from_d2(b3, two_sigma2));
+}
+
+struct FocalArgs {
+  const float* logits;
+  const uint8_t* valid;
+  const int64_t* label;
+  const float* center;
+  int n_objects, C, H, W;
+  float in_h, in_w, ratio, two_sigma2;
+  FocalPow a, b;
+  int chunks_per_plane;
+  long long n_chunks;
+};
+
+// this warp's chunk: which objects render into its plane (ballot), and their grid cells
+__device__ __forceinline__ unsigned focal_chunk_objects(const FocalArgs& g, long long plane, int lane, int& cy, int& cx,
+                                                        bool& big) {
+  const int c = (int)(plane % g.C);
+  const long long b = plane / g.C;
+  bool mine = false;
+  cy = 0;
+  cx = 0;
+  if (lane < g.n_objects) {
+    const long long i = b * g.n_objects + lane;
+    const uint8_t v = __ldg(g.valid + i);
+    const long long l = __ldg(g.label + i);
+    const float2 yx = __ldg(reinterpret_cast<const float2*>(g.center) + i);
+    if (v && l == c) {
+      mine = true;
+      cy = grid_floor(yx.x, g.in_h, g.ratio);
+      cx = grid_floor(yx.y, g.in_w, g.ratio);
+    }
+  }
+  const unsigned mask = __ballot_sync(0xffffffffu, mine);
+  big = __any_sync(0xffffffffu, mine && (abs(cy) > 20000 || abs(cx) > 20000)) || g.H > 10000 || g.W > 10000;
+  return mask;
+}
+
+__global__ void __launch_bounds__(kEncThreads) focal_forward_kernel(const __grid_constant__ FocalArgs g,
+                                                                    double* __restrict__ part /*[n_chunks][2]*/,
+                                                                    int* __restrict__ part_pos /*[n_chunks]*/) {
+  const int lane = threadIdx.x & 31;
+  const long long chunk_id = (long long)blockIdx.x * (kEncThreads / 32) + (threadIdx.x >> 5);
+  if (chunk_id >= g.n_chunks) return;
+  const long long plane = chunk_id / g.chunks_per_plane;
+  const int chunk = (int)(chunk_id - plane * g.chunks_per_plane);
+  int cy, cx;
+  bool big;
+  const unsigned mask = focal_chunk_objects(g, plane, lane, cy, cx, big);
+  const int S = g.W >> 2;
+  const int plane_strips = g.H * S;
+  const int s0 = chunk * kEncWarpStrips;
+  const int s1 = min(plane_strips, s0 + kEncWarpStrips);
+  const float4* x4 = reinterpret_cast<const float4*>(g.logits + (size_t)plane * g.H * g.W);
+  double acc_p = 0.0, acc_n = 0.0;
+  int n_pos = 0;
+  for (int t0 = s0; t0 < s1; t0 += 32) {  // (warp-uniform trip count: the shuffles of the render need every lane)
+    const int t = t0 + lane;
+    const int y = t / S;
+    const int x = (t - y * S) << 2;
+    const float4 tv = focal_target4(mask, cy, cx, y, x, g.two_sigma2, big);
+    if (t < s1) {
+      const float4 xv = ldg_stream4(reinterpret_cast<const float*>(x4 + t));
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ts[4] = {tv.x, tv.y, tv.z, tv.w};
+      float sp = 0.0f, sn = 0.0f;  // the strip's four terms in fp32, one fp64 add per strip and sum
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float p = sigmoid_ref(xs[i]);
+        float tt = ts[i];
+        if (tt != tt) tt = 0.0f;  // (generate_heatmap ends with nan_to_num)
+        if (mask != 0u && focal_is_pos(tt)) {
+          sp += __fmul_rn(focal_pow(__fsub_rn(1.0f, p), g.a), logf(fmaxf(p, 1e-4f)));
+          ++n_pos;
+        } else {
+          float w = focal_pow(p, g.a);
+          if (mask != 0u) w = __fmul_rn(focal_pow(__fsub_rn(1.0f, tt), g.b), w);
+          sn += __fmul_rn(w, logf(fmaxf(__fsub_rn(1.0f, p), 1e-4f)));
+        }
+      }
+      acc_p += (double)sp;
+      acc_n += (double)sn;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc_p += __shfl_xor_sync(0xffffffffu, acc_p, o);
+    acc_n += __shfl_xor_sync(0xffffffffu, acc_n, o);
+    n_pos += __shfl_xor_sync(0xffffffffu, n_pos, o);
+  }
+  if (lane == 0) {
+    part[chunk_id * 2 + 0] = acc_p;
+    part[chunk_id * 2 + 1] = acc_n;
+    part_pos[chunk_id] = n_pos;
+  }
+}
+
+// one warp per frame: the frame's chunk partials in a fixed order (lane-strided, then a butterfly: deterministic)
+__global__ void __launch_bounds__(32) focal_reduce_kernel(const double* __restrict__ part, const int* __restrict__ part_pos,
+                                                          long long chunks_per_frame, double* __restrict__ frame_sums,
+                                                          int64_t* __restrict__ frame_pos) {
+  const long long b = blockIdx.x;
+  const int lane = threadIdx.x;
+  double sp = 0.0, sn = 0.0;
+  long long np = 0;
+  for (long long i = lane; i < chunks_per_frame; i += 32) {
+    sp += part[(b * chunks_per_frame + i) * 2 + 0];
+    sn += part[(b * chunks_per_frame + i) * 2 + 1];
+    np += part_pos[b * chunks_per_frame + i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sp += __shfl_xor_sync(0xffffffffu, sp, o);
+    sn += __shfl_xor_sync(0xffffffffu, sn, o);
+    np += __shfl_xor_sync(0xffffffffu, np, o);
+  }
+  if (lane == 0) {
+    frame_sums[b * 2 + 0] = sp;
+    frame_sums[b * 2 + 1] = sn;
+    frame_pos[b] = np;
+  }
+}
+
+// d(sum of the loss)/d(logits) * grad_out.  loss = -(loss_p + loss_n) / N for N > 0, -loss_p for N == 0.
+__global__ void __launch_bounds__(kEncThreads) focal_backward_kernel(const __grid_constant__ FocalArgs g,
+                                                                     const int64_t* __restrict__ n_pos_total,
+                                                                     const float* __restrict__ grad_out,
+                                                                     float* __restrict__ grad) {
+  const int lane = threadIdx.x & 31;
+  const long long chunk_id = (long long)blockIdx.x * (kEncThreads / 32) + (threadIdx.x >> 5);
+  if (chunk_id >= g.n_chunks) return;
+  const long long plane = chunk_id / g.chunks_per_plane;
+  const int chunk = (int)(chunk_id - plane * g.chunks_per_plane);
+  int cy, cx;
+  bool big;
+  const unsigned mask = focal_chunk_objects(g, plane, lane, cy, cx, big);
+  const long long N = __ldg(n_pos_total);
+  // autograd: d(-(x)/N) = -1/N (an fp32 division of the incoming gradient by N), or -1 when the negatives are dropped
+  const float go = __ldg(grad_out);
+  const float scale = N > 0 ? -__fdiv_rn(go, (float)N) : -go;
+  const bool with_neg = N > 0;
+  const int S = g.W >> 2;
+  const int plane_strips = g.H * S;
+  const int s0 = chunk * kEncWarpStrips;
+  const int s1 = min(plane_strips, s0 + kEncWarpStrips);
+  const float4* x4 = reinterpret_cast<const float4*>(g.logits + (size_t)plane * g.H * g.W);
+  float4* g4 = reinterpret_cast<float4*>(grad + (size_t)plane * g.H * g.W);
+  for (int t0 = s0; t0 < s1; t0 += 32) {
+    const int t = t0 + lane;
+    const int y = t / S;
+    const int x = (t - y * S) << 2;
+    const float4 tv = focal_target4(mask, cy, cx, y, x, g.two_sigma2, big);
+    if (t < s1) {
+      const float4 xv = ldg_stream4(reinterpret_cast<const float*>(x4 + t));
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ts[4] = {tv.x, tv.y, tv.z, tv.w};
+      float gs[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float p = sigmoid_ref(xs[i]);
+        const float q = __fsub_rn(1.0f, p);
+        float tt = ts[i];
+        if (tt != tt) tt = 0.0f;
+        float dldp;  // d(loss_p + loss_n)/dp
+        if (mask != 0u && focal_is_pos(tt)) {
+          // (1-p)^a log(clamp(p)):  -a (1-p)^(a-1) log(c) + (1-p)^a [p >= 1e-4] / p
+          const float lg = logf(fmaxf(p, 1e-4f));
+          dldp = -focal_dpow(q, g.a) * lg + (p >= 1e-4f ? focal_pow(q, g.a) / p : 0.0f);
+        } else if (with_neg) {
+          // w p^a log(clamp(1-p)),  w = (1-t)^b:  w [a p^(a-1) log(c) - p^a [1-p >= 1e-4] / (1-p)]
+          const float w = mask != 0u ? focal_pow(__fsub_rn(1.0f, tt), g.b) : 1.0f;
+          const float lg = logf(fmaxf(q, 1e-4f));
+          dldp = w * (focal_dpow(p, g.a) * lg - (q >= 1e-4f ? focal_pow(p, g.a) / q : 0.0f));
+        } else {
+          dldp = 0.0f;
+        }
+        gs[i] = scale * dldp * (p * q);  // sigmoid backward: p (1 - p)
+      }
+      g4[t] = make_float4(gs[0], gs[1], gs[2], gs[3]);
+    }
+  }
+}
 
 static float two_sigma_sq(double sigma) {
   if (sigma < 0.1) sigma = 0.1;  // loss.py:60-62 ("tiny sigma!")
   return (float)(2.0 * (sigma * sigma));
+}
+
+static FocalPow make_focal_pow(double e) {
+  FocalPow p;
+  p.e = (float)e;
+  p.kind = e == 2.0 ? 2 : e == 3.0 ? 3 : 0;
+  return p;
+}
+
+static int focal_args(FocalArgs* g, const float* logits, const uint8_t* valid, const int64_t* label, const float* center,
+                      int B, int n_objects, int C, int H, int W, int in_h, int in_w, int downsample_ratio, double sigma,
+                      double alpha, double beta) {
+  TAUV_REQUIRE(logits, TAUV_E_NULL, "logits must not be NULL");
+  TAUV_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && n_objects >= 0, TAUV_E_SHAPE, "bad shape");
+  TAUV_REQUIRE(n_objects == 0 || (valid && label && center), TAUV_E_NULL, "valid/label/center must not be NULL");
+  TAUV_REQUIRE(in_h > 0 && in_w > 0 && downsample_ratio > 0, TAUV_E_SHAPE, "bad model geometry");
+  TAUV_REQUIRE(W % 4 == 0 && (uintptr_t)logits % 16 == 0 && n_objects <= 32 && (uintptr_t)center % 8 == 0,
+               TAUV_E_UNSUPPORTED, "the fused focal loss needs W %% 4 == 0, 16-byte aligned logits and <= 32 objects per frame");
+  g->logits = logits; g->valid = valid; g->label = label; g->center = center;
+  g->n_objects = n_objects; g->C = C; g->H = H; g->W = W;
+  g->in_h = (float)in_h; g->in_w = (float)in_w; g->ratio = (float)downsample_ratio; g->two_sigma2 = two_sigma_sq(sigma);
+  g->a = make_focal_pow(alpha); g->b = make_focal_pow(beta);
+  const long long plane_strips = (long long)H * (W / 4);
+  const long long cpp = (plane_strips + kEncWarpStrips - 1) / kEncWarpStrips;
+  g->chunks_per_plane = (int)cpp;
+  g->n_chunks = (long long)B * C * cpp;
+  TAUV_REQUIRE(cpp < (1LL << 31) && (g->n_chunks + kEncThreads / 32 - 1) / (kEncThreads / 32) < (1LL << 31),
+               TAUV_E_UNSUPPORTED, "grid too large");
+  return 0;
+}
+
+}  // namespace tauv
+
+using namespace tauv;
+
+
+extern "C" size_t tauv_centernet_focal_loss_workspace_bytes(int B, int C, int H, int W) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || W % 4 != 0) return 0;
+  const long long plane_strips = (long long)H * (W / 4);
+  const long long cpp = (plane_strips + kEncWarpStrips - 1) / kEncWarpStrips;
+  const size_t n_chunks = (size_t)B * C * cpp;
+  return align_up(n_chunks * 16, 256) + align_up(n_chunks * 4, 256);
+}
+
+extern "C" int tauv_centernet_focal_loss(const float* logits, const uint8_t* valid, const int64_t* label,
+                                         const float* center, int B, int n_objects, int C, int H, int W, int in_h,
+                                         int in_w, int downsample_ratio, double sigma, double alpha, double beta,
+                                         double* frame_sums, int64_t* frame_pos, void* workspace,
+                                         size_t workspace_bytes, tauv_stream_t stream) {
+  TAUV_REQUIRE(frame_sums && frame_pos, TAUV_E_NULL, "frame_sums/frame_pos must not be NULL");
+  FocalArgs g;
+  if (int e = focal_args(&g, logits, valid, label, center, B, n_objects, C, H, W, in_h, in_w, downsample_ratio, sigma,
+                         alpha, beta))
+    return e;
+  const size_t part_bytes = align_up((size_t)g.n_chunks * 16, 256);
+  TAUV_REQUIRE(workspace != nullptr && (uintptr_t)workspace % 256 == 0, TAUV_E_WORKSPACE, "workspace must be 256-byte aligned");
+  TAUV_REQUIRE(workspace_bytes >= part_bytes + align_up((size_t)g.n_chunks * 4, 256), TAUV_E_WORKSPACE,
+               "workspace %zu too small", workspace_bytes);
+  double* part = reinterpret_cast<double*>(workspace);
+  int* part_pos = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(workspace) + part_bytes);
+  const long long grid = (g.n_chunks + kEncThreads / 32 - 1) / (kEncThreads / 32);
+  focal_forward_kernel<<<(unsigned)grid, kEncThreads, 0, (cudaStream_t)stream>>>(g, part, part_pos);
+  TAUV_LAUNCH_CHECK("focal_forward_kernel");
+  focal_reduce_kernel<<<(unsigned)B, 32, 0, (cudaStream_t)stream>>>(part, part_pos, (long long)C * g.chunks_per_plane,
+                                                                    frame_sums, frame_pos);
+  TAUV_LAUNCH_CHECK("focal_reduce_kernel");
+  return 0;
+}
+
+extern "C" int tauv_centernet_focal_loss_backward(const float* logits, const uint8_t* valid, const int64_t* label,
+                                                  const float* center, int B, int n_objects, int C, int H, int W,
+                                                  int in_h, int in_w, int downsample_ratio, double sigma, double alpha,
+                                                  double beta, const int64_t* n_pos_total, const float* grad_out,
+                                                  float* grad_logits, tauv_stream_t stream) {
+  TAUV_REQUIRE(n_pos_total && grad_out && grad_logits, TAUV_E_NULL, "n_pos_total/grad_out/grad_logits must not be NULL");
+  TAUV_REQUIRE((uintptr_t)grad_logits % 16 == 0, TAUV_E_ALIGN, "grad_logits must be 16-byte aligned");
+  FocalArgs g;
+  if (int e = focal_args(&g, logits, valid, label, center, B, n_objects, C, H, W, in_h, in_w, downsample_ratio, sigma,
+                         alpha, beta))
+    return e;
+  const long long grid = (g.n_chunks + kEncThreads / 32 - 1) / (kEncThreads / 32);
+  focal_backward_kernel<<<(unsigned)grid, kEncThreads, 0, (cudaStream_t)stream>>>(g, n_pos_total, grad_out, grad_logits);
+  TAUV_LAUNCH_CHECK("focal_backward_kernel");
+  return 0;
 }
 
 extern "C" int tauv_gaussian_encode(const uint8_t* valid, const int64_t* label, const float* center, int B,

@@ -223,6 +223,30 @@ def main():
          kp_heatmap=khm, kp_weight=kw, kp_affinity=ka, out_index=oi, offset=off, in_h=96, downsamples=2,
          sigma_h=2.0, sigma_a=3.0)
 
+    # ---- heatmap focal loss on the rendered target (loss.py:233-236, 302-317), with the reference's own autograd
+    # gradient of the summed loss with respect to the logits; second case: no valid object (the N == 0 branch) ------
+    gf = synth.gen(67)
+    fl_logits = (torch.randn((2, 4, 24, 24), generator=gf) * 1.5 - 2.2)
+    fl_logits[0, int(t.label[0, 0]), 23, 0] = 9.0   # a confident hit on an object centre (clamp / saturation region)
+    fl_logits[1, 0, 3, 3] = 12.0                    # a confident false positive: 1 - p is tiny
+    fl_logits[1, 1, 5, 5] = -15.0                   # p below the 1e-4 clamp
+    fl_logits.requires_grad_(True)
+    fl = ref_loss.focal_loss(torch.sigmoid(fl_logits), hm, alpha=tc.heatmap_focal_loss_a, beta=tc.heatmap_focal_loss_b)
+    fl_sum = fl.sum()
+    fl_grad, = torch.autograd.grad(fl_sum, fl_logits)
+    none_valid = PoseSample(img=None, valid=torch.zeros_like(t.valid), label=t.label, center=t.center, size=t.size,
+                            roll=None, pitch=None, yaw=None, depth=None, keypoint_valid=t.keypoint_valid,
+                            keypoint_label=t.keypoint_label, keypoint_center=t.keypoint_center,
+                            keypoint_object_index=t.keypoint_object_index)
+    hm0 = ref_loss.generate_heatmap(none_valid, mce, tc, oce)
+    fl0 = ref_loss.focal_loss(torch.sigmoid(fl_logits), hm0, alpha=tc.heatmap_focal_loss_a, beta=tc.heatmap_focal_loss_b)
+    fl0_sum = fl0.sum()
+    fl0_grad, = torch.autograd.grad(fl0_sum, fl_logits)
+    save("cn_focal", logits=fl_logits.detach(), valid=t.valid, label=t.label, center=t.center, in_h=96, downsamples=2,
+         sigma_h=2.0, alpha=float(tc.heatmap_focal_loss_a), beta=float(tc.heatmap_focal_loss_b), loss=fl.detach(),
+         loss_sum=fl_sum.detach(), n_pos=int(torch.isclose(hm, torch.ones(1)).sum()), grad=fl_grad,
+         loss0_sum=fl0_sum.detach(), grad0=fl0_grad)
+
     # ---- YOLACT anchors ------------------------------------------------------------------------------------
     ycfg = YolactModelConfig(in_w=550, in_h=550, feature_depth=0, n_classes=0, n_prototype_masks=0,
                              n_masknet_layers_pre_upsample=0, n_masknet_layers_post_upsample=0,

@@ -462,6 +462,78 @@ def test_encode_full_size_properties(cn):
     assert (hm.cpu().amax(dim=(2, 3))[~has] == 0).all() and (hm.cpu().amax(dim=(2, 3))[has] == 1).all()
 
 
+# ---- heatmap focal loss fused with the target render --------------------------------------------
+
+def _focal_cfgs(in_hw, ds, sigma, a, b):
+    return (synth.centernet_model_config(in_hw, in_hw, ds),
+            SimpleNamespace(keypoint_heatmap_sigma=sigma, heatmap_focal_loss_a=a, heatmap_focal_loss_b=b))
+
+
+def test_focal_loss_golden(cn):
+    """focal_loss(sigmoid(logits), generate_heatmap(truth)).sum() and its gradient against the values frozen from the
+    reference (its own autograd), including the N == 0 branch.  Tolerances: the loss is a sum of 4.6 k fp32 terms
+    (fp64 accumulation here, fp32 in the reference): 1e-5 relative; the gradient 1e-5 relative with 1e-9 absolute for
+    the cells whose factors cancel."""
+    g = golden("cn_focal")
+    mc, tc = _focal_cfgs(96, 2, float(g["sigma_h"]), float(g["alpha"]), float(g["beta"]))
+    dev = cn.dev
+    for valid, loss_ref, grad_ref, n_ref in ((t(g["valid"]), g["loss_sum"], g["grad"], int(g["n_pos"])),
+                                             (torch.zeros_like(t(g["valid"])), g["loss0_sum"], g["grad0"], 0)):
+        truth = SimpleNamespace(valid=valid.to(dev), label=t(g["label"]).to(dev), center=t(g["center"]).to(dev))
+        logits = t(g["logits"]).to(dev).requires_grad_(True)
+        loss, n_pos = cn.L.heatmap_focal_loss(logits, truth, mc, tc, return_n_pos=True)
+        assert int(n_pos) == n_ref and loss.dtype == torch.float32 and loss.dim() == 0
+        assert_close(loss.detach(), loss_ref, rtol=1e-5, what="focal loss")
+        (loss * 3.0).backward()  # (a non-unit upstream gradient)
+        assert_close(logits.grad / 3.0, grad_ref, rtol=1e-5, atol=1e-9, what="gradient")
+
+
+@pytest.mark.parametrize("B,n,C,H,W,ds,a,b", [(3, 5, 4, 13, 12, 1, 2.0, 4.0), (2, 16, 80, 128, 128, 2, 2.0, 4.0),
+                                              (1, 0, 2, 8, 8, 2, 2.0, 4.0), (2, 32, 3, 40, 20, 1, 3.0, 2.0),
+                                              (2, 7, 9, 30, 44, 2, 1.5, 2.5), (2, 40, 5, 24, 36, 2, 2.0, 4.0),
+                                              (1, 6, 4, 16, 18, 1, 2.0, 4.0)])
+def test_focal_loss_vs_oracle(cn, B, n, C, H, W, ds, a, b):
+    """Forward and backward against the oracle (torch CPU, the reference's expressions with autograd) on other shapes:
+    generic exponents (powf), the full configs[1] frame shape, no objects, the > 32 objects and W % 4 != 0 shapes that
+    take the composed path."""
+    ratio = 2 ** ds
+    tr = synth.pose_truth(B, n, C, seed=40 + H)
+    logits = synth.natural_logits(B, C, H, W, seed=41 + W).clamp(-12, 12)
+    x = logits.clone().requires_grad_(True)
+    target = O.generate_heatmap(tr.valid, tr.label, tr.center, C, H, W, H * ratio, W * ratio, ratio, 2.0)
+    ref = O.focal_loss(torch.sigmoid(x), target, a, b).sum()
+    gref, = torch.autograd.grad(ref, x)
+    mc = SimpleNamespace(in_h=H * ratio, in_w=W * ratio, downsample_ratio=ratio, out_h=H, out_w=W)
+    tc = SimpleNamespace(keypoint_heatmap_sigma=2.0, heatmap_focal_loss_a=a, heatmap_focal_loss_b=b)
+    xd = logits.to(cn.dev).requires_grad_(True)
+    loss, n_pos = cn.L.heatmap_focal_loss(xd, synth.truth_to(tr, cn.dev), mc, tc, return_n_pos=True)
+    assert int(n_pos) == int(torch.isclose(target, torch.ones(1)).sum())
+    assert_close(loss.detach(), ref.detach(), rtol=2e-5, what="focal loss")
+    loss.backward()
+    assert_close(xd.grad, gref, rtol=2e-5, atol=1e-9, what="gradient")
+
+
+def test_focal_loss_full_batch_matches_composition(cn):
+    """BASELINE configs[1] size (64 x 80 x 128 x 128): the fused pass equals the composition of this package's own
+    generate_heatmap with the reference's elementwise expressions on the GPU, is deterministic run to run, and writes no
+    target."""
+    torch.manual_seed(3)
+    dev = cn.dev
+    logits = (torch.randn((64, 80, 128, 128), device=dev) * 1.5 - 2.2).requires_grad_(True)
+    tr = synth.truth_to(synth.pose_truth(64, 16, 80, seed=5), dev)
+    mc, tc = _focal_cfgs(512, 2, 2.0, 2.0, 4.0)
+    loss = cn.L.heatmap_focal_loss(logits, tr, mc, tc)
+    loss.backward()
+    again = cn.L.heatmap_focal_loss(logits.detach(), tr, mc, tc)
+    assert_equal(loss.detach(), again, "deterministic")
+    x2 = logits.detach().clone().requires_grad_(True)
+    target = cn.L.generate_heatmap(tr, mc, tc, SimpleNamespace(n_labels=80))
+    ref = cn.L.focal_loss(torch.sigmoid(x2), target, 2.0, 4.0).sum()
+    ref.backward()
+    assert_close(loss.detach(), ref.detach(), rtol=2e-5, what="loss vs composition")
+    assert_close(logits.grad, x2.grad, rtol=2e-5, atol=1e-10, what="gradient vs composition")
+
+
 def test_angle_depth_golden(cn):
     g = golden("cn_angle_depth")
     pb, po = t(g["bin"]).to(cn.dev), t(g["offset"]).to(cn.dev)

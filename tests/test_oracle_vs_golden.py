@@ -111,6 +111,24 @@ def test_encode_golden():
     assert_equal(O.offset_target(t(g["center"]), 96, 96, 4), g["offset"])
 
 
+def test_focal_loss_golden():
+    """loss.py:302-317 on the rendered target: the oracle restatement against the reference's own values, including
+    its autograd gradient and the N == 0 branch."""
+    g = golden("cn_focal")
+    logits = t(g["logits"]).clone().requires_grad_(True)
+    target = O.generate_heatmap(t(g["valid"]), t(g["label"]), t(g["center"]), 4, 24, 24, 96, 96, 4, float(g["sigma_h"]))
+    loss = O.focal_loss(torch.sigmoid(logits), target, float(g["alpha"]), float(g["beta"]))
+    assert_equal(loss.detach(), g["loss"], "elementwise focal loss")
+    grad, = torch.autograd.grad(loss.sum(), logits)
+    assert_equal(grad, g["grad"], "autograd gradient")
+    total, n_pos = O.heatmap_focal_loss(t(g["logits"]), t(g["valid"]), t(g["label"]), t(g["center"]), 96, 96, 4,
+                                        float(g["sigma_h"]), float(g["alpha"]), float(g["beta"]))
+    assert_equal(total, g["loss_sum"]) and n_pos == int(g["n_pos"])
+    total0, n0 = O.heatmap_focal_loss(t(g["logits"]), torch.zeros_like(t(g["valid"])), t(g["label"]), t(g["center"]), 96,
+                                      96, 4, float(g["sigma_h"]), float(g["alpha"]), float(g["beta"]))
+    assert_equal(total0, g["loss0_sum"]) and n0 == 0
+
+
 def test_anchors_golden():
     g = golden("yl_anchors")
     cfg = synth.yolact_config()
