@@ -52,6 +52,24 @@ def get_anchor(fpn_i: int, fpn_size, config, device=None) -> torch.Tensor:
     return _build([(fpn_i, (int(fpn_size[0]), int(fpn_size[1])))], config, device)
 
 
-def all_anchors(fpn_sizes, config, device=None) -> torch.Tensor:
-    """All levels concatenated, [1, sum_l A*H_l*W_l, 4]   — the torch.cat of model.py:47-58."""
-    return _build([(i, (int(s[0]), int(s[1]))) for i, s in enumerate(fpn_sizes)], config, device)
+_CACHE: dict = {}
+
+
+def all_anchors(fpn_sizes, config, device=None, cache: bool = True) -> torch.Tensor:
+    """All levels concatenated, [1, sum_l A*H_l*W_l, 4]   — the torch.cat of model.py:47-58.
+
+    The priors depend only on the level sizes and four configuration fields, so they are generated once per
+    (sizes, configuration, device) and the same read-only tensor is handed out afterwards (the reference rebuilds
+    them on the CPU and copies them to the GPU on every forward, model.py:47-48).  ``cache=False`` builds a fresh
+    tensor (for callers that write into it)."""
+    levels = [(i, (int(s[0]), int(s[1]))) for i, s in enumerate(fpn_sizes)]
+    if not cache:
+        return _build(levels, config, device)
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    key = (tuple(s for _, s in levels), tuple(float(v) for v in config.anchor_scales),
+           tuple(float(v) for v in config.anchor_aspect_ratios), float(config.in_h), float(config.in_w), dev.type,
+           dev.index if dev.index is not None else torch.cuda.current_device())
+    hit = _CACHE.get(key)
+    if hit is None:
+        hit = _CACHE[key] = _build(levels, config, dev)
+    return hit

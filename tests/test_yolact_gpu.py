@@ -33,6 +33,11 @@ def test_anchors_golden(yl):
     assert full.shape == (1, 19248, 4)
     assert_equal(full[0, t(g["full_sel"]).to(yl.dev)], g["full_rows"])
     assert_equal(full.double().sum(dim=1), g["full_sum"])
+    # generated once per (sizes, configuration, device): the second call hands out the same tensor, cache=False a new one
+    again = yl.anchors.all_anchors(synth.fpn_sizes(550, 550), CFG, yl.dev)
+    assert again.data_ptr() == full.data_ptr()
+    fresh = yl.anchors.all_anchors(synth.fpn_sizes(550, 550), CFG, yl.dev, cache=False)
+    assert fresh.data_ptr() != full.data_ptr() and torch.equal(fresh, full)
 
 
 def test_boxes_golden(yl):
