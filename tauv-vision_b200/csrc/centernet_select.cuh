@@ -504,28 +504,35 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
   for (;;) {
     ++attempts;
     // ---- 1. threshold T: (a lower bound of) the K1-th largest of 1024 strided maxima of the group (or block) maxima.
-    //         L = the smallest of the warps' j-th largest maxima (32 j >= K1 keys reach it),
+    //         L = the smallest of the (full) warps' j-th largest maxima (>= K1 keys reach it),
     //         U = the largest key; one 1024-bin histogram of the keys in [L, U] and a suffix count give the bin in which
     //         the count reaches K1; T = its lower edge. ----
-    const bool use_grp = a.G >= 4 * K1;
+    const bool use_grp = a.G >= 2 * K1;  // (at G = 2 K1 about 1.4 K1 blocks reach T: still tight, and 32x fewer values to look at)
     const float* __restrict__ lv = use_grp ? bm2 : bm;
     const int nlv = use_grp ? a.G : a.n_blk;
     uint32_t T_key = 0u;
     float T_f = TAUV_NEG_INF;
     __syncthreads();
-    if (K1 <= kSelThreads) {
+    // (frames with fewer than 1024 values at this level fill only the first nwf warps: the bracket L comes from those —
+    // a warp of -inf padding would drag L, and with it the histogram's resolution, down to nothing)
+    const int nwf = (nlv < kSelThreads ? nlv : kSelThreads) >> 5;  // warps whose 32 keys are all real
+    if (nwf > 0 && K1 <= 32 * nwf) {
       uint32_t* hist = sh->s.hist;  // [0,1024) bins, [1024,1056) warp totals, [1056,1088) j-th largest, [1088,1120) largest
       float tm = TAUV_NEG_INF;
       for (int i = tid; i < nlv; i += kSelThreads) tm = fmaxf(tm, lv[i]);
       const uint32_t key = float_to_key(tm);
-      // the warp's largest key and its j-th largest (with multiplicity), j = ceil(K1 / 32): j warp-wide max reductions
-      const int j = (K1 + 31) >> 5;
+      // the warp's largest key and its j-th largest (with multiplicity), j = ceil(K1 / nwf): j warp-wide max reductions
+      const int j = (K1 + nwf - 1) / nwf;
       uint32_t cur = key, mx = __reduce_max_sync(0xffffffffu, cur);
       if (lane == 0) hist[1088 + warp] = mx;
-      for (int jj = 1; jj < j; ++jj) {
-        const unsigned bal = __ballot_sync(0xffffffffu, cur == mx);
-        if (lane == __ffs(bal) - 1) cur = 0u;
-        mx = __reduce_max_sync(0xffffffffu, cur);
+      if (warp < nwf) {
+        for (int jj = 1; jj < j; ++jj) {
+          const unsigned bal = __ballot_sync(0xffffffffu, cur == mx);
+          if (lane == __ffs(bal) - 1) cur = 0u;
+          mx = __reduce_max_sync(0xffffffffu, cur);
+        }
+      } else {
+        mx = 0xffffffffu;  // (neutral for the minimum)
       }
       if (lane == 0) hist[1056 + warp] = mx;
       hist[tid] = 0u;
