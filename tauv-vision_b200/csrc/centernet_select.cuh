@@ -2,7 +2,7 @@
 //
 // Replaces the same reference lines as centernet_decode.cu (centernet/model/decode.py:182 sigmoid, :239-252 heatmap_nms,
 // :255-279 heatmap_detect, :204-234 per-detection gather + box arithmetic), for the common case: 128-bit aligned maps
-// with W % 4 == 0, k <= 256, sigmoid + 3x3 peak mode.  Two launches, the second one programmatically dependent:
+// with W % 4 == 0, k <= 1024, sigmoid + 3x3 peak mode.  Two launches, the second one programmatically dependent:
 //
 //   block_max_kernel : the ONLY pass over the logits.  No data-dependent work at all — a thread reads a block of
 //       4 columns x 8 rows of one plane (eight independent 128-bit loads), keeps the maximum, writes it (one float per
@@ -33,10 +33,9 @@ constexpr int kBmRows = 8;            // rows of a block (a block = 4 columns x 
 #endif
 constexpr int kBmThreads = TAUV_BM_THREADS;
 constexpr int kSelThreads = 1024;
-constexpr int kSelHotCap = 1024;      // hot groups / hot blocks per attempt
-constexpr int kSelCandCap = 2048;     // candidate list (final composites)
-constexpr int kSelMaxK = 256;
-constexpr int kSelSmallSeg = (kSelCandCap - 2 * kSelMaxK) / 32;  // blocks per exhaustive sub-step that cannot overflow
+// (capacities: SelTier below — the shared-memory footprint decides whether the CTAs can be set up next to the draining
+// block_max_kernel CTAs: 144 KB can, 204 KB cannot and costs 4 us, so only k > 256 takes the large tier)
+constexpr int kSelMaxK = 1024;
 
 // Division by a launch constant as multiply-high + shift (x < 2^31; the scheme of CUTLASS' FastDivmod): the block and
 // cell index arithmetic of the select pass sits on single-warp dependent chains, where a 32-bit division costs ~100 cycles.
@@ -151,23 +150,38 @@ __global__ void __launch_bounds__(kBmThreads) block_max_kernel(const __grid_cons
   if ((threadIdx.x & 31) == 0 && valid) st_keep(&a.bm2[(size_t)b * a.G + (i >> 5)], g, keep);
 }
 
-constexpr int kSelCellCap = 2048;     // hot cells per attempt
+constexpr int kSelCountRank = 512;    // up to this many candidates are ranked by counting, more by a bitonic sort
 
-struct __align__(16) SelShared {
+// Capacities of the select pass: the small tier serves k <= 256 (everything on the bench path), the large one k <= 1024.
+struct SelTierSmall {
+  static constexpr int kMaxK = 256, kHotCap = 1024, kCellCap = 2048, kBoxCap = 2048;
+};
+struct SelTierLarge {
+  static constexpr int kMaxK = 1024, kHotCap = 2048, kCellCap = 4096, kBoxCap = 2048;
+};
+
+template <class TIER>
+struct __align__(16) SelSharedT {
+  static constexpr int kHotCap = TIER::kHotCap;    // hot groups / hot blocks per attempt
+  static constexpr int kCellCap = TIER::kCellCap;  // hot cells per attempt
+  static constexpr int kCandCap = TIER::kCellCap;  // candidate list (final composites): one slot per hot cell
+  static constexpr int kBoxCap = TIER::kBoxCap;    // cells whose box arithmetic can be done ahead of the ranking
+  static constexpr int kMaxK = TIER::kMaxK;
+  static constexpr int kSmallSeg = (kCandCap - 2 * kMaxK) / 32;  // blocks per exhaustive sub-step that cannot overflow
   struct {
     unsigned long long keys[kSelThreads];  // later: the ranked keys
     uint32_t hist[kRadixBins];             // T selection: 1024 bins + per-warp columns; exhaustive path: radix histogram;
   } s;                                     // later: filler flags
-  unsigned long long cand[kSelCandCap];    // peaks: final composites (score key << 32 | ~flat index)
-  uint32_t hot[kSelHotCap];                // fast path: flat index of the block's first cell; exhaustive path: block ids
-  uint32_t hotpos[kSelHotCap];             // fast path: first row << 16 | first column
-  uint32_t hgrp[kSelHotCap];
-  uint32_t cell[kSelCellCap];              // hot block ids while they are collected; then the hot cells: flat index,
-  uint32_t cellpos[kSelCellCap];           //   row << 16 | column,
-  float cellx[kSelCellCap];                //   logit,
-  float cellm[kSelCellCap];                //   maximum of the eight neighbours
-  BoxVals cellbox[kSelCellCap];            //   size / offset / depth arithmetic of the cell (idle warps, while the cells are tested)
-  uint32_t rankcell[kSelMaxK];             // the cell behind each ranked key
+  unsigned long long cand[kCandCap];       // peaks: final composites (score key << 32 | ~flat index)
+  uint32_t hot[kHotCap];                   // fast path: flat index of the block's first cell; exhaustive path: block ids
+  uint32_t hotpos[kHotCap];                // fast path: first row << 16 | first column
+  uint32_t hgrp[kHotCap];
+  uint32_t cell[kCellCap];                 // hot block ids while they are collected; then the hot cells: flat index,
+  uint32_t cellpos[kCellCap];              //   row << 16 | column,
+  float cellx[kCellCap];                   //   logit,
+  float cellm[kCellCap];                   //   maximum of the eight neighbours
+  BoxVals cellbox[kBoxCap];                //   size / offset / depth arithmetic of the cell (idle warps, while the cells are tested)
+  uint32_t rankcell[kMaxK];                // the cell behind each ranked key
   uint32_t ctl[8];
   int n_hgrp, n_hot, n_xhot, n_xcell, n_cand, n_zero, first_below, flag;
   uint32_t T_key;
@@ -233,7 +247,8 @@ __device__ __forceinline__ void sel_collect(const float* __restrict__ src, int n
 
 // a cell that reached T, with the maximum of its neighbours: peak test, sigmoid, final key (0: not a peak / zero score).
 // Dense: one thread per hot cell, a few warps per frame.
-__device__ __noinline__ unsigned long long sel_test_cell(const SelShared* sh, int i) {
+template <class SH>
+__device__ __noinline__ unsigned long long sel_test_cell(const SH* sh, int i) {
   const float x = sh->cellx[i];
   if (!sel_is_peak(x, sh->cellm[i])) return 0ull;
   return sel_final_key(x, sh->cell[i]);
@@ -245,11 +260,26 @@ __device__ __noinline__ unsigned long long sel_test_cell(const SelShared* sh, in
 // below T can reach the k-th best score s_k if sigmoid_ref(T) < s_k (1 - 2e-5) — the same guard band as
 // reject_key_for_score, without its logarithm.  sh->flag = 1 if that fails or fewer than k peaks reached T.  Returns
 // npos = min(valid, k).  All threads call this.
-__device__ __noinline__ int sel_rank_emit(const SelArgs& a, SelShared* sh, int b, int n, uint32_t T_key, bool have_box) {
+template <class SH>
+__device__ __noinline__ int sel_rank_emit(const SelArgs& a, SH* sh, int b, int n, uint32_t T_key, bool have_box) {
   const int tid = threadIdx.x, k = a.k;
   const int sel_rep = 0;
   (void)sel_rep;
   unsigned long long* ranked = sh->s.keys;
+  if (n > kSelCountRank) {
+    // long lists (k > ~450): counting would cost n^2 / 2048 shared-memory loads per thread — sort instead (zeros last)
+    int p2 = 1;
+    while (p2 < n) p2 <<= 1;
+    for (int i = n + tid; i < p2; i += kSelThreads) sh->cand[i] = 0ull;
+    __syncthreads();
+    block_bitonic_sort_desc<kSelThreads>(sh->cand, p2);
+    for (int i = tid; i < n; i += kSelThreads) {
+      const unsigned long long c = sh->cand[i];
+      if (c == 0ull) atomicAdd(&sh->n_zero, 1);
+      else if (i < k) ranked[i] = c;
+    }
+    have_box = false;  // (the sort has moved the keys away from their cells)
+  } else {
   const int tpc = n <= kSelThreads / 8 ? 8 : 4;  // threads per candidate
   const int n2 = (n + 1) >> 1;  // (the caller has zeroed cand[n] when n is odd)
   for (int i0 = 0; i0 < n; i0 += kSelThreads / tpc) {
@@ -274,6 +304,7 @@ __device__ __noinline__ int sel_rank_emit(const SelArgs& a, SelShared* sh, int b
         sh->rankcell[cnt] = (uint32_t)i;
       }
     }
+  }
   }
   __syncthreads();
   SEL_STAMP(13);
@@ -310,7 +341,8 @@ __device__ __noinline__ int sel_rank_emit(const SelArgs& a, SelShared* sh, int b
 }
 
 // The zero-score tail (fewer than k positive peaks in the whole frame) and the count of leading detections.
-__device__ __noinline__ void sel_finish(const SelArgs& a, SelShared* sh, int b, int npos) {
+template <class SH>
+__device__ __noinline__ void sel_finish(const SelArgs& a, SH* sh, int b, int npos) {
   const int tid = threadIdx.x, k = a.k;
   if (npos < k) {
     uint32_t* flags = sh->s.hist;
@@ -334,7 +366,8 @@ __device__ __noinline__ void sel_finish(const SelArgs& a, SelShared* sh, int b, 
 // One exhaustive step over the blocks [seg0, seg0 + len), len <= kSelThreads: blocks whose maximum reaches the logit
 // filter are examined cell by cell (one warp per block, one lane per cell), peaks at or above the current k-th best
 // key are appended.  Sets sh->flag when the list overflowed (the caller redoes the range in smaller steps).
-__device__ __noinline__ void sel_slow_step(const SelArgs& a, SelShared* sh, const float* __restrict__ fhm,
+template <class SH>
+__device__ __noinline__ void sel_slow_step(const SelArgs& a, SH* sh, const float* __restrict__ fhm,
                                            const float* __restrict__ bm, int seg0, int len) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) sh->n_hot = 0;
@@ -374,7 +407,7 @@ __device__ __noinline__ void sel_slow_step(const SelArgs& a, SelShared* sh, cons
     const bool want = fin != 0ull && fin >= thr_c;
     const int slot = sel_append(&sh->n_cand, want);
     if (want) {
-      if (slot < kSelCandCap) sh->cand[slot] = fin;
+      if (slot < SH::kCandCap) sh->cand[slot] = fin;
       else sh->flag = 1;
     }
   }
@@ -382,21 +415,22 @@ __device__ __noinline__ void sel_slow_step(const SelArgs& a, SelShared* sh, cons
 }
 
 // exact prune of the candidate list to its k best; raises the key threshold and the logit filter
-__device__ __noinline__ void sel_slow_prune(const SelArgs& a, SelShared* sh) {
+template <class SH>
+__device__ __noinline__ void sel_slow_prune(const SelArgs& a, SH* sh) {
   const int tid = threadIdx.x, k = a.k;
   const int n = sh->n_cand;  // > k
   const unsigned long long T =
       block_kth_largest<kSelThreads>([&](int i) { return sh->cand[i]; }, n, k, sh->s.hist, sh->ctl);
-  unsigned long long mine[kSelCandCap / kSelThreads];
+  unsigned long long mine[SH::kCandCap / kSelThreads];
 #pragma unroll
-  for (int u = 0; u < kSelCandCap / kSelThreads; ++u) {
+  for (int u = 0; u < SH::kCandCap / kSelThreads; ++u) {
     const int i = tid + u * kSelThreads;
     mine[u] = i < n ? sh->cand[i] : 0ull;
   }
   if (tid == 0) sh->n_cand = 0;
   __syncthreads();
 #pragma unroll
-  for (int u = 0; u < kSelCandCap / kSelThreads; ++u)
+  for (int u = 0; u < SH::kCandCap / kSelThreads; ++u)
     if (mine[u] >= T && mine[u] != 0ull) sh->cand[atomicAdd(&sh->n_cand, 1)] = mine[u];
   if (tid == 0) {
     sh->thr_c = T;
@@ -410,7 +444,8 @@ __device__ __noinline__ void sel_slow_prune(const SelArgs& a, SelShared* sh) {
 }
 
 // The whole frame, exhaustively, in segments with exact pruning.  Returns the number of candidates left in sh->cand.
-__device__ __noinline__ int sel_slow(const SelArgs& a, SelShared* sh, const float* __restrict__ fhm,
+template <class SH>
+__device__ __noinline__ int sel_slow(const SelArgs& a, SH* sh, const float* __restrict__ fhm,
                                      const float* __restrict__ bm) {
   const int tid = threadIdx.x;
   const int soft = 2 * a.k;
@@ -435,8 +470,8 @@ __device__ __noinline__ int sel_slow(const SelArgs& a, SelShared* sh, const floa
         sh->flag = 0;
       }
       __syncthreads();
-      for (int s = seg; s < seg + len; s += kSelSmallSeg) {
-        int l2 = kSelSmallSeg;
+      for (int s = seg; s < seg + len; s += SH::kSmallSeg) {
+        int l2 = SH::kSmallSeg;
         if (l2 > seg + len - s) l2 = seg + len - s;
         sel_slow_step(a, sh, fhm, bm, s, l2);
         if (sh->n_cand > soft) sel_slow_prune(a, sh);
@@ -450,9 +485,44 @@ __device__ __noinline__ int sel_slow(const SelArgs& a, SelShared* sh, const floa
   return sh->n_cand;
 }
 
+// Large k (K1 > 1024): four strided maxima per thread (4096 in all); leaves every warp's largest key and its
+// ceil(K1 / 32)-th largest in the bracket slots of the histogram array and returns this thread's four keys.
+template <class SH>
+__device__ __noinline__ uint4 sel_bracket_wide(SH* sh, const float* __restrict__ lv, int nlv, int K1) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t* hist = sh->s.hist;
+  float tm[4] = {TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF, TAUV_NEG_INF};
+  for (int i = tid; i < nlv; i += 4 * kSelThreads) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      if (i + v * kSelThreads < nlv) tm[v] = fmaxf(tm[v], lv[i + v * kSelThreads]);
+  }
+  const uint4 key = make_uint4(float_to_key(tm[0]), float_to_key(tm[1]), float_to_key(tm[2]), float_to_key(tm[3]));
+  const int j = (K1 + 31) >> 5;
+  uint32_t c0 = key.x, c1 = key.y, c2 = key.z, c3 = key.w;
+  uint32_t local = max(max(c0, c1), max(c2, c3));
+  uint32_t mx = __reduce_max_sync(0xffffffffu, local);
+  if (lane == 0) hist[1088 + warp] = mx;
+  for (int jj = 1; jj < j; ++jj) {
+    const unsigned bal = __ballot_sync(0xffffffffu, local == mx);
+    if (lane == __ffs(bal) - 1) {  // remove ONE instance of the maximum
+      if (c0 == mx) c0 = 0u;
+      else if (c1 == mx) c1 = 0u;
+      else if (c2 == mx) c2 = 0u;
+      else c3 = 0u;
+      local = max(max(c0, c1), max(c2, c3));
+    }
+    mx = __reduce_max_sync(0xffffffffu, local);
+  }
+  if (lane == 0) hist[1056 + warp] = mx;
+  return key;
+}
+
+template <class TIER>
 __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_constant__ SelArgs a) {
+  using SH = SelSharedT<TIER>;
   extern __shared__ __align__(128) unsigned char sel_smem[];
-  SelShared* sh = reinterpret_cast<SelShared*>(sel_smem);
+  SH* sh = reinterpret_cast<SH*>(sel_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   const int k = a.k;
@@ -516,25 +586,34 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
     // (frames with fewer than 1024 values at this level fill only the first nwf warps: the bracket L comes from those —
     // a warp of -inf padding would drag L, and with it the histogram's resolution, down to nothing)
     const int nwf = (nlv < kSelThreads ? nlv : kSelThreads) >> 5;  // warps whose 32 keys are all real
-    if (nwf > 0 && K1 <= 32 * nwf) {
+    // large k (K1 > 1024): four strided maxima per thread, 4096 in all
+    const bool wide = K1 > 32 * nwf && nlv >= 4 * kSelThreads && K1 <= 4 * kSelThreads;
+    uint32_t key = 0u;
+    uint4 wkey = make_uint4(0u, 0u, 0u, 0u);
+    if (nwf > 0 && (K1 <= 32 * nwf || wide)) {
       uint32_t* hist = sh->s.hist;  // [0,1024) bins, [1024,1056) warp totals, [1056,1088) j-th largest, [1088,1120) largest
-      float tm = TAUV_NEG_INF;
-      for (int i = tid; i < nlv; i += kSelThreads) tm = fmaxf(tm, lv[i]);
-      const uint32_t key = float_to_key(tm);
-      // the warp's largest key and its j-th largest (with multiplicity), j = ceil(K1 / nwf): j warp-wide max reductions
-      const int j = (K1 + nwf - 1) / nwf;
-      uint32_t cur = key, mx = __reduce_max_sync(0xffffffffu, cur);
-      if (lane == 0) hist[1088 + warp] = mx;
-      if (warp < nwf) {
-        for (int jj = 1; jj < j; ++jj) {
-          const unsigned bal = __ballot_sync(0xffffffffu, cur == mx);
-          if (lane == __ffs(bal) - 1) cur = 0u;
-          mx = __reduce_max_sync(0xffffffffu, cur);
-        }
+      if (wide) {
+        wkey = sel_bracket_wide(sh, lv, nlv, K1);  // (out of line: the common case below stays as lean as it was)
       } else {
-        mx = 0xffffffffu;  // (neutral for the minimum)
+        float tm = TAUV_NEG_INF;
+        for (int i = tid; i < nlv; i += kSelThreads) tm = fmaxf(tm, lv[i]);
+        key = float_to_key(tm);
+        // the warp's largest key and its j-th largest (with multiplicity), j = ceil(K1 / nwf): j warp-wide max
+        // reductions; every full warp holds at least j keys at or above its own j-th largest, so >= K1 keys reach L
+        const int j = (K1 + nwf - 1) / nwf;
+        uint32_t cur = key, mx = __reduce_max_sync(0xffffffffu, cur);
+        if (lane == 0) hist[1088 + warp] = mx;
+        if (warp < nwf) {
+          for (int jj = 1; jj < j; ++jj) {
+            const unsigned bal = __ballot_sync(0xffffffffu, cur == mx);
+            if (lane == __ffs(bal) - 1) cur = 0u;
+            mx = __reduce_max_sync(0xffffffffu, cur);
+          }
+        } else {
+          mx = 0xffffffffu;  // (neutral for the minimum)
+        }
+        if (lane == 0) hist[1056 + warp] = mx;
       }
-      if (lane == 0) hist[1056 + warp] = mx;
       hist[tid] = 0u;
       __syncthreads();
       uint32_t Lk = hist[1056 + lane], Uk = hist[1088 + lane];
@@ -545,7 +624,14 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
       }
       const uint32_t range = Uk - Lk;
       const int shft = range >= 1024u ? 22 - __clz(range) : 0;  // (range >> shft) < 1024
-      if (key >= Lk) atomicAdd(&hist[(key - Lk) >> shft], 1u);
+      if (!wide) {
+        if (key >= Lk) atomicAdd(&hist[(key - Lk) >> shft], 1u);
+      } else {
+        if (wkey.x >= Lk) atomicAdd(&hist[(wkey.x - Lk) >> shft], 1u);
+        if (wkey.y >= Lk) atomicAdd(&hist[(wkey.y - Lk) >> shft], 1u);
+        if (wkey.z >= Lk) atomicAdd(&hist[(wkey.z - Lk) >> shft], 1u);
+        if (wkey.w >= Lk) atomicAdd(&hist[(wkey.w - Lk) >> shft], 1u);
+      }
       __syncthreads();
       const uint32_t c = hist[tid];
       uint32_t suf = c;  // inclusive suffix count inside the warp (lane 31 = highest bin)
@@ -583,10 +669,10 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
     // ---- 2. hot groups -> hot blocks (ids in sh->cell), then their positions ----
     int nhot;
     if (use_grp) {
-      sel_collect(bm2, a.G, T_f, &sh->n_hgrp, sh->hgrp, kSelHotCap);
+      sel_collect(bm2, a.G, T_f, &sh->n_hgrp, sh->hgrp, SH::kHotCap);
       __syncthreads();
       const int nh = sh->n_hgrp;
-      if (nh > kSelHotCap) { slow = true; break; }
+      if (nh > SH::kHotCap) { slow = true; break; }
       // eight lanes per hot group, one 128-bit load each.  The group's first hot block (there is one: the group
       // maximum is a block maximum) takes the group's own slot, further ones (rare) are appended behind the nh slots.
       const int ne = nh * 8;
@@ -618,7 +704,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
               int slot = gs;
               if (!first) slot = nh + atomicAdd(&sh->n_xhot, 1);
               first = false;
-              if (slot < kSelCellCap) sh->cell[slot] = (uint32_t)(idx[u] + c);
+              if (slot < SH::kCellCap) sh->cell[slot] = (uint32_t)(idx[u] + c);
             } while (hm);
           }
         }
@@ -626,11 +712,11 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
       __syncthreads();
       nhot = nh + sh->n_xhot;
     } else {
-      sel_collect(bm, a.n_blk, T_f, &sh->n_hot, sh->cell, kSelCellCap);
+      sel_collect(bm, a.n_blk, T_f, &sh->n_hot, sh->cell, SH::kCellCap);
       __syncthreads();
       nhot = sh->n_hot;
     }
-    if (nhot > kSelHotCap) { slow = true; break; }
+    if (nhot > SH::kHotCap) { slow = true; break; }
     for (int i = tid; i < nhot; i += kSelThreads) {  // (dense: a handful of warps)
       const uint32_t blk = sh->cell[i];
       const uint32_t q = fdiv_u32(blk, a.dW4), c4 = blk - q * (uint32_t)a.W4;
@@ -688,7 +774,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
               int slot = bs;
               if (!first) slot = nhot + atomicAdd(&sh->n_xcell, 1);
               first = false;
-              if (slot < kSelCellCap) {
+              if (slot < SH::kCellCap) {
                 sh->cellpos[slot] = pos[u] + (uint32_t)c;
                 sh->cellx[slot] = c == 0 ? v[u].x : c == 1 ? v[u].y : c == 2 ? v[u].z : v[u].w;
                 sh->cell[slot] = org[u] + (uint32_t)c;  // (flat index; the block ids were consumed before the barrier)
@@ -700,7 +786,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
     }
     __syncthreads();
     n = nhot + sh->n_xcell;
-    if (n > kSelCellCap || n > kSelCandCap) { slow = true; break; }
+    if (n > SH::kCellCap) { slow = true; break; }
     SEL_STAMP(11);
     // ---- 3b. the eight neighbours of every queued cell: eight lanes per cell, one load each ----
     {
@@ -741,7 +827,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
         if (n & 1) sh->cand[n] = 0ull;  // (the rank loop reads pairs; n < kSelCandCap when odd)
         sh->s_T = sigmoid_ref(T_f);     // (for the completeness test of sel_rank_emit)
       }
-    } else if (a.box.enabled) {
+    } else if (a.box.enabled && n <= SH::kBoxCap) {
       for (int i = tid - 256; i < n; i += kSelThreads - 256) {
         const uint32_t pos = sh->cellpos[i];
         sh->cellbox[i] = box_values(a.box, b, (int)(pos >> 16), (int)(pos & 0xffffu));
@@ -753,7 +839,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
     SEL_NOTE(9, nhot);
     SEL_NOTE(10, n);
     // ---- 4. rank, emit, and check that enough peaks reached T and nothing below T could have made it ----
-    const int npos = sel_rank_emit(a, sh, b, n, T_key, true);
+    const int npos = sel_rank_emit(a, sh, b, n, T_key, n <= SH::kBoxCap);
     SEL_STAMP(5);
     if (T_key != 0u && sh->flag) {
       __syncthreads();
@@ -784,7 +870,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
       sh->n_zero = 0;
     }
     n = sel_slow(a, sh, fhm, bm);
-    if (tid == 0 && (n & 1) && n < kSelCandCap) sh->cand[n] = 0ull;
+    if (tid == 0 && (n & 1) && n < SH::kCandCap) sh->cand[n] = 0ull;
     __syncthreads();
     const int npos = sel_rank_emit(a, sh, b, n, 0u, false);
     if (npos < k) sel_finish(a, sh, b, npos);
@@ -857,18 +943,24 @@ static int run_select_decode(const float* hm, int B, int C, int H, int W, int k,
 #else
   sa.trace = nullptr;
 #endif
-  TAUV_CUDA(ensure_dynamic_smem((const void*)select_kernel, sizeof(SelShared)));
+  // (the small tier's 144 KB lets the CTAs be set up next to block_max_kernel's last wave; the large tier's 204 KB
+  // does not — measured: 4 us on the whole call — so only k > 256 pays for it)
+  const bool large = k > SelTierSmall::kMaxK;
+  const void* kern = large ? (const void*)select_kernel<SelTierLarge> : (const void*)select_kernel<SelTierSmall>;
+  const size_t sel_smem_bytes = large ? sizeof(SelSharedT<SelTierLarge>) : sizeof(SelSharedT<SelTierSmall>);
+  TAUV_CUDA(ensure_dynamic_smem(kern, sel_smem_bytes));
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)B);
   cfg.blockDim = dim3(kSelThreads);
-  cfg.dynamicSmemBytes = sizeof(SelShared);
+  cfg.dynamicSmemBytes = sel_smem_bytes;
   cfg.stream = st;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  TAUV_CUDA(cudaLaunchKernelEx(&cfg, select_kernel, sa));
+  if (large) TAUV_CUDA(cudaLaunchKernelEx(&cfg, select_kernel<SelTierLarge>, sa));
+  else TAUV_CUDA(cudaLaunchKernelEx(&cfg, select_kernel<SelTierSmall>, sa));
   TAUV_LAUNCH_CHECK("select_kernel");
   return 0;
 }

@@ -355,10 +355,14 @@ def test_select_path_smooth_fields(cn, B, C, H, W, k, box, passes):
 
 
 @pytest.mark.parametrize("B,C,H,W,k", [(2, 3, 13, 12, 17), (1, 1, 1, 8, 3), (3, 2, 41, 36, 64), (1, 7, 50, 20, 256),
-                                       (2, 16, 128, 128, 256), (5, 1, 128, 128, 100), (1, 80, 128, 128, 1)])
+                                       (2, 16, 128, 128, 256), (5, 1, 128, 128, 100), (1, 80, 128, 128, 1),
+                                       (2, 20, 128, 128, 1000), (1, 80, 128, 128, 500), (2, 12, 128, 128, 600),
+                                       (1, 40, 64, 64, 1024)])
 def test_select_path_shapes(cn, B, C, H, W, k):
     """Aligned maps with W % 4 == 0 take the block-maxima + select path: partial row groups (H % 8 != 0), rows
-    narrower than a warp of blocks, one-plane frames (block-level threshold), k at the path's limit, k = 1."""
+    narrower than a warp of blocks, one-plane frames (block-level threshold), k = 1, and the large-k variants: four
+    strided maxima per thread for the threshold (K1 > 1024), candidate lists ranked by a sort instead of by counting,
+    k at the path's limit of 1024."""
     logits = synth.separated_logits(B, C, H, W, seed=500 + H + k)
     oi, ol, osc = O.heatmap_detect(O.heatmap_nms(torch.sigmoid(logits), 3), k)
     idx, lab, sc = cn.D.heatmap_peaks(logits.to(cn.dev), k)
