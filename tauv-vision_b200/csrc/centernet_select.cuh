@@ -888,6 +888,9 @@ static bool select_plan(int B, int C, int H, int W, int k, SelPlan* p) {
   const long long n_rg = (H + kBmRows - 1) / kBmRows;
   const long long n_blk = (long long)C * n_rg * (W / 4);
   if (n_blk >= (1LL << 26) || (long long)C * H * W >= (1LL << 31)) return false;  // (FastDiv: dividends below 2^31)
+  // a frame with fewer blocks than a few times K1 = k + k/8 + 8 has no selective threshold to find: the pass would go
+  // straight to its exhaustive segments, which round 1's kernels do better (C = 1, 128 x 128, k = 1000: 81 vs 67 us)
+  if (n_blk < 4LL * (k + k / 8 + 8) && (long long)k * 4 > 256) return false;
   p->W4 = W / 4;
   p->n_rg = (int)n_rg;
   p->n_blk = (int)n_blk;
