@@ -529,6 +529,20 @@ __device__ __forceinline__ float focal_pow(float x, FocalPow p) {
   if (p.kind == 3) return __fmul_rn(__fmul_rn(x, x), x);
   return powf(x, p.e);
 }
+// the same with the kind known at compile time (alpha is applied to every cell: the run-time tests were a tenth of the
+// forward kernel's instructions)
+template <int KIND>
+__device__ __forceinline__ float focal_pow_k(float x, FocalPow p) {
+  if (KIND == 2) return __fmul_rn(x, x);
+  if (KIND == 3) return __fmul_rn(__fmul_rn(x, x), x);
+  return powf(x, p.e);
+}
+template <int KIND>
+__device__ __forceinline__ float focal_dpow_k(float x, FocalPow p) {
+  if (KIND == 2) return __fmul_rn(2.0f, x);
+  if (KIND == 3) return __fmul_rn(3.0f, __fmul_rn(x, x));
+  return __fmul_rn(p.e, powf(x, p.e - 1.0f));
+}
 // d/dx x^e (autograd: e * x^(e-1))
 __device__ __forceinline__ float focal_dpow(float x, FocalPow p) {
   if (p.kind == 2) return __fmul_rn(2.0f, x);
@@ -609,6 +623,7 @@ __device__ __forceinline__ unsigned focal_chunk_objects(const FocalArgs& g, long
   return mask;
 }
 
+template <int KA>
 __global__ void __launch_bounds__(kEncThreads) focal_forward_kernel(const __grid_constant__ FocalArgs g,
                                                                     double* __restrict__ part /*[n_chunks][2]*/,
                                                                     int* __restrict__ part_pos /*[n_chunks]*/) {
@@ -642,10 +657,10 @@ __global__ void __launch_bounds__(kEncThreads) focal_forward_kernel(const __grid
         float tt = ts[i];
         if (tt != tt) tt = 0.0f;  // (generate_heatmap ends with nan_to_num)
         if (mask != 0u && focal_is_pos(tt)) {
-          sp += __fmul_rn(focal_pow(__fsub_rn(1.0f, p), g.a), logf(fmaxf(p, 1e-4f)));
+          sp += __fmul_rn(focal_pow_k<KA>(__fsub_rn(1.0f, p), g.a), logf(fmaxf(p, 1e-4f)));
           ++n_pos;
         } else {
-          float w = focal_pow(p, g.a);
+          float w = focal_pow_k<KA>(p, g.a);
           if (mask != 0u) w = __fmul_rn(focal_pow(__fsub_rn(1.0f, tt), g.b), w);
           sn += __fmul_rn(w, logf(fmaxf(__fsub_rn(1.0f, p), 1e-4f)));
         }
@@ -694,6 +709,7 @@ __global__ void __launch_bounds__(32) focal_reduce_kernel(const double* __restri
 }
 
 // d(sum of the loss)/d(logits) * grad_out.  loss = -(loss_p + loss_n) / N for N > 0, -loss_p for N == 0.
+template <int KA>
 __global__ void __launch_bounds__(kEncThreads) focal_backward_kernel(const __grid_constant__ FocalArgs g,
                                                                      const int64_t* __restrict__ n_pos_total,
                                                                      const float* __restrict__ grad_out,
@@ -736,12 +752,12 @@ __global__ void __launch_bounds__(kEncThreads) focal_backward_kernel(const __gri
         if (mask != 0u && focal_is_pos(tt)) {
           // (1-p)^a log(clamp(p)):  -a (1-p)^(a-1) log(c) + (1-p)^a [p >= 1e-4] / p
           const float lg = logf(fmaxf(p, 1e-4f));
-          dldp = -focal_dpow(q, g.a) * lg + (p >= 1e-4f ? focal_pow(q, g.a) / p : 0.0f);
+          dldp = -focal_dpow_k<KA>(q, g.a) * lg + (p >= 1e-4f ? focal_pow_k<KA>(q, g.a) / p : 0.0f);
         } else if (with_neg) {
           // w p^a log(clamp(1-p)),  w = (1-t)^b:  w [a p^(a-1) log(c) - p^a [1-p >= 1e-4] / (1-p)]
           const float w = mask != 0u ? focal_pow(__fsub_rn(1.0f, tt), g.b) : 1.0f;
           const float lg = logf(fmaxf(q, 1e-4f));
-          dldp = w * (focal_dpow(p, g.a) * lg - (q >= 1e-4f ? focal_pow(p, g.a) / q : 0.0f));
+          dldp = w * (focal_dpow_k<KA>(p, g.a) * lg - (q >= 1e-4f ? focal_pow_k<KA>(p, g.a) / q : 0.0f));
         } else {
           dldp = 0.0f;
         }
@@ -816,7 +832,9 @@ extern "C" int tauv_centernet_focal_loss(const float* logits, const uint8_t* val
   double* part = reinterpret_cast<double*>(workspace);
   int* part_pos = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(workspace) + part_bytes);
   const long long grid = (g.n_chunks + kEncThreads / 32 - 1) / (kEncThreads / 32);
-  focal_forward_kernel<<<(unsigned)grid, kEncThreads, 0, (cudaStream_t)stream>>>(g, part, part_pos);
+  if (g.a.kind == 2) focal_forward_kernel<2><<<(unsigned)grid, kEncThreads, 0, (cudaStream_t)stream>>>(g, part, part_pos);
+  else if (g.a.kind == 3) focal_forward_kernel<3><<<(unsigned)grid, kEncThreads, 0, (cudaStream_t)stream>>>(g, part, part_pos);
+  else focal_forward_kernel<0><<<(unsigned)grid, kEncThreads, 0, (cudaStream_t)stream>>>(g, part, part_pos);
   TAUV_LAUNCH_CHECK("focal_forward_kernel");
   focal_reduce_kernel<<<(unsigned)B, 32, 0, (cudaStream_t)stream>>>(part, part_pos, (long long)C * g.chunks_per_plane,
                                                                     frame_sums, frame_pos);
@@ -836,7 +854,12 @@ extern "C" int tauv_centernet_focal_loss_backward(const float* logits, const uin
                          alpha, beta))
     return e;
   const long long grid = (g.n_chunks + kEncThreads / 32 - 1) / (kEncThreads / 32);
-  focal_backward_kernel<<<(unsigned)grid, kEncThreads, 0, (cudaStream_t)stream>>>(g, n_pos_total, grad_out, grad_logits);
+  if (g.a.kind == 2)
+    focal_backward_kernel<2><<<(unsigned)grid, kEncThreads, 0, (cudaStream_t)stream>>>(g, n_pos_total, grad_out, grad_logits);
+  else if (g.a.kind == 3)
+    focal_backward_kernel<3><<<(unsigned)grid, kEncThreads, 0, (cudaStream_t)stream>>>(g, n_pos_total, grad_out, grad_logits);
+  else
+    focal_backward_kernel<0><<<(unsigned)grid, kEncThreads, 0, (cudaStream_t)stream>>>(g, n_pos_total, grad_out, grad_logits);
   TAUV_LAUNCH_CHECK("focal_backward_kernel");
   return 0;
 }
