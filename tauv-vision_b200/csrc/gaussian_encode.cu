@@ -145,7 +145,10 @@ __global__ void __launch_bounds__(kEncThreads) gaussian_encode_kernel(
 // ballot says which objects render into this plane; if none do, the chunk is sixteen coalesced 128-bit zero stores per
 // lane, otherwise the matching centres are broadcast with shuffles.  Warps are laid out in memory order, so the CTAs
 // that are resident at any time write one contiguous window of the output, like a plain fill.
-constexpr int kEncWarpStrips = 512;  // 128-bit strips per warp (16 per lane)
+#ifndef TAUV_ENC_WARP_STRIPS
+#define TAUV_ENC_WARP_STRIPS 256  // (measured, tools/variants_encode.sh: 128 -> 61.5 us, 256 -> 56.4, 512 -> 61.8, 1024 -> 68.6, 4096 -> 129 us per 64 frames)
+#endif
+constexpr int kEncWarpStrips = TAUV_ENC_WARP_STRIPS;  // 128-bit strips per warp (8 per lane)
 
 __global__ void __launch_bounds__(kEncThreads) gaussian_encode_warp_kernel(
     const uint8_t* __restrict__ valid, const int64_t* __restrict__ label, const float* __restrict__ center,
