@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(kEncThreads) gaussian_encode_kernel(
 #define TAUV_ENC_WARP_STRIPS 256  // (measured, tools/variants_encode.sh: 128 -> 61.5 us, 256 -> 56.4, 512 -> 61.8, 1024 -> 68.6, 4096 -> 129 us per 64 frames)
 #endif
 constexpr int kEncWarpStrips = TAUV_ENC_WARP_STRIPS;  // 128-bit strips per warp (8 per lane)
+constexpr int kKpWarpStrips = 512;  // the keypoint render (three outputs per strip) keeps 16 strips per lane: 244 vs 263 us
 
 __global__ void __launch_bounds__(kEncThreads) gaussian_encode_warp_kernel(
     const uint8_t* __restrict__ valid, const int64_t* __restrict__ label, const float* __restrict__ center,
@@ -409,8 +410,8 @@ __global__ void __launch_bounds__(kEncThreads) keypoint_encode_warp_kernel(
   }
   const int S = W >> 2;
   const int plane_strips = H * S;
-  const int s0 = chunk * kEncWarpStrips;
-  const int s1 = min(plane_strips, s0 + kEncWarpStrips);
+  const int s0 = chunk * kKpWarpStrips;
+  const int s1 = min(plane_strips, s0 + kKpWarpStrips);
   const size_t hw = (size_t)H * W;
   float4* h4 = reinterpret_cast<float4*>(heatmap + (size_t)plane * hw);
   float4* w4 = reinterpret_cast<float4*>(weight + (size_t)plane * hw);
@@ -928,7 +929,7 @@ extern "C" int tauv_keypoint_encode(const uint8_t* kp_valid, const int64_t* kp_l
   const float tsa = (float)(2.0 * (sigma_affinity * sigma_affinity));
   if (vec && m <= 128 && m > 0) {
     const long long plane_strips = (long long)H * (W / 4);
-    const long long cpp = (plane_strips + kEncWarpStrips - 1) / kEncWarpStrips;
+    const long long cpp = (plane_strips + kKpWarpStrips - 1) / kKpWarpStrips;
     const long long n_chunks = planes * cpp;
     const long long wgrid = (n_chunks + kEncThreads / 32 - 1) / (kEncThreads / 32);
     TAUV_REQUIRE(wgrid < (1LL << 31) && cpp < (1LL << 31), TAUV_E_UNSUPPORTED, "grid too large");
