@@ -466,6 +466,31 @@ def test_encode_full_size_properties(cn):
     assert (hm.cpu().amax(dim=(2, 3))[~has] == 0).all() and (hm.cpu().amax(dim=(2, 3))[has] == 1).all()
 
 
+def test_cluster_kernel_repeatable_under_load(cn):
+    """The round-1 cluster kernel (its lock-free strip queue between the streaming warps and the service warp) still
+    serves raw-value top-k and k > 1024: 150 frames (several units per cluster) of plateau-heavy and of natural maps,
+    15 back-to-back runs each, identical outputs run to run and equal to the oracle."""
+    q = torch.round(synth.natural_logits(150, 4, 64, 64, seed=21) * 2) / 2
+    nat = synth.natural_logits(150, 4, 64, 64, seed=22)
+    for m, k in ((q, 60), (nat, 100)):
+        md = m.to(cn.dev)
+        first = cn.D.heatmap_detect(md, k)
+        for _ in range(15):
+            again = cn.D.heatmap_detect(md, k)
+            for a, b in zip(first, again):
+                assert_equal(a, b)
+        oi, ol, osc = O.heatmap_detect(m, k)
+        assert_equal(first[0], oi), assert_equal(first[1], ol), assert_equal(first[2], osc)
+    big = synth.separated_logits(3, 6, 64, 64, seed=23)
+    first = cn.D.heatmap_peaks(big.to(cn.dev), 1500)  # k > 1024: the cluster kernel with the merge launch
+    for _ in range(5):
+        again = cn.D.heatmap_peaks(big.to(cn.dev), 1500)
+        for a, b in zip(first, again):
+            assert_equal(a, b)
+    oi, ol, osc = O.heatmap_detect(O.heatmap_nms(torch.sigmoid(big), 3), 1500)
+    assert_equal(first[0], oi), assert_equal(first[1], ol), assert_close(first[2], osc, what="score")
+
+
 # ---- heatmap focal loss fused with the target render (SURVEY 8f rank 3) --------------------------------------------
 
 def _focal_cfgs(in_hw, ds, sigma, a, b):
