@@ -19,7 +19,7 @@
 //         3. the peaks >= T get their sigmoid and final sort key (score desc, flat index asc); the rank of a key among
 //            the (distinct) keys is its output slot — no sort;
 //         4. the result is complete iff there are >= k of them AND every logit below T has a score strictly below the
-//            k-th best score (reject_key_for_score, the same guard band as the round-1 kernel).  Otherwise K1 *= 4 and
+//            k-th best score (reject_key_for_score, the same guard band as the round-1 kernel).  Otherwise K1 grows and
 //            again; when that runs out (plateaus, saturated scores, fewer than k peaks) the frame is done exhaustively
 //            in segments with exact pruning (sel_slow) — slow, exact, and only for degenerate maps.
 //       The same threads then gather size / offset / depth through the strided views and do the box arithmetic.
@@ -184,7 +184,7 @@ struct __align__(16) SelSharedT {
   uint32_t rankcell[kMaxK];                // the cell behind each ranked key
   uint32_t ctl[8];
   int n_hgrp, n_hot, n_xhot, n_xcell, n_cand, n_zero, first_below, flag;
-  uint32_t T_key;
+  uint32_t T_key, T_key2;
   float s_T, xc_f;  // s_T: the sigmoid of the threshold T (computed by an idle warp while the cells are tested)
   unsigned long long thr_c;
 };
@@ -261,7 +261,8 @@ __device__ __noinline__ unsigned long long sel_test_cell(const SH* sh, int i) {
 // reject_key_for_score, without its logarithm.  sh->flag = 1 if that fails or fewer than k peaks reached T.  Returns
 // npos = min(valid, k).  All threads call this.
 template <class SH>
-__device__ __noinline__ int sel_rank_emit(const SelArgs& a, SH* sh, int b, int n, uint32_t T_key, bool have_box) {
+__device__ __noinline__ int sel_rank_emit(const SelArgs& a, SH* sh, int b, int n, uint32_t T_key, bool have_box,
+                                          const uint32_t* candcell) {
   const int tid = threadIdx.x, k = a.k;
   const int sel_rep = 0;
   (void)sel_rep;
@@ -301,7 +302,7 @@ __device__ __noinline__ int sel_rank_emit(const SelArgs& a, SH* sh, int b, int n
       if (my == 0ull) atomicAdd(&sh->n_zero, 1);
       else if (cnt < k) {
         ranked[cnt] = my;
-        sh->rankcell[cnt] = (uint32_t)i;
+        sh->rankcell[cnt] = have_box ? candcell[i] : 0u;  // (the queued cell whose box arithmetic is in cellbox[])
       }
     }
   }
@@ -571,6 +572,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
   int n = 0;
   bool slow = false;
   int attempts = 0;
+  uint32_t T_next = 0u;  // a threshold the next attempt takes as it is (step 2: smooth maps)
   for (;;) {
     ++attempts;
     // ---- 1. threshold T: (a lower bound of) the K1-th largest of 1024 strided maxima of the group (or block) maxima.
@@ -588,9 +590,18 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
     const int nwf = (nlv < kSelThreads ? nlv : kSelThreads) >> 5;  // warps whose 32 keys are all real
     // large k (K1 > 1024): four strided maxima per thread, 4096 in all
     const bool wide = K1 > 32 * nwf && nlv >= 4 * kSelThreads && K1 <= 4 * kSelThreads;
+    // The first attempt also takes the threshold for 2 K1 from the same histogram (T2 <= T): on a smooth map — hot
+    // regions that span many blocks, seen in step 2 as several hot blocks per hot group — K1 groups hold fewer than
+    // k peaks more often than not, and a whole second attempt doubles the frame's time.
+    const int K2 = (attempts == 1 && use_grp && !wide && 2 * K1 <= 32 * nwf && a.G >= 4 * K1) ? 2 * K1 : K1;
+    uint32_t T_key2 = 0u;
     uint32_t key = 0u;
     uint4 wkey = make_uint4(0u, 0u, 0u, 0u);
-    if (nwf > 0 && (K1 <= 32 * nwf || wide)) {
+    if (T_next != 0u) {
+      T_key = T_next;
+      T_f = key_to_float(T_key);
+      T_next = 0u;
+    } else if (nwf > 0 && (K1 <= 32 * nwf || wide)) {
       uint32_t* hist = sh->s.hist;  // [0,1024) bins, [1024,1056) warp totals, [1056,1088) j-th largest, [1088,1120) largest
       if (wide) {
         wkey = sel_bracket_wide(sh, lv, nlv, K1);  // (out of line: the common case below stays as lean as it was)
@@ -651,19 +662,30 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
       const uint32_t above = __shfl_sync(0xffffffffu, wsuf, (warp + 1) & 31);
       suf += warp < 31 ? above : 0u;
       if (suf >= (uint32_t)K1 && suf - c < (uint32_t)K1) sh->T_key = Lk + ((uint32_t)tid << shft);
+      // (T2 from the same bracket: the bin in which the count reaches 2 K1, or L itself when fewer keys than that lie
+      // in [L, U] — the bracket guarantees K1 of them and usually holds two or three times as many)
+      if (K2 != K1 && ((suf >= (uint32_t)K2 && suf - c < (uint32_t)K2) || (tid == 0 && suf < (uint32_t)K2)))
+        sh->T_key2 = Lk + ((uint32_t)tid << shft);
       __syncthreads();
       T_key = sh->T_key;
       T_f = key_to_float(T_key);
       if (!(T_f > TAUV_NEG_INF)) T_key = 0u;
+      if (K2 != K1 && T_key != 0u) {
+        T_key2 = sh->T_key2;
+        if (!(T_key2 < T_key) || !(key_to_float(T_key2) > TAUV_NEG_INF)) T_key2 = 0u;
+      }
     }
     if (tid == 0) {
       sh->n_hgrp = 0;
       sh->n_hot = 0;
       sh->n_xhot = 0;
       sh->n_xcell = 0;
+      sh->n_cand = 0;
       sh->n_zero = 0;
       sh->flag = 0;
     }
+    // (the rank loop reads the candidates in pairs: an odd list ends in an empty slot)
+    for (int i = tid; i < SH::kCandCap; i += kSelThreads) sh->cand[i] = 0ull;
     __syncthreads();
     SEL_STAMP(2);
     // ---- 2. hot groups -> hot blocks (ids in sh->cell), then their positions ----
@@ -711,6 +733,11 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
       }
       __syncthreads();
       nhot = nh + sh->n_xhot;
+      if (T_key2 != 0u && 2 * nhot >= 3 * nh) {  // smooth map (noise: 1.07 hot blocks per hot group): step 2 again, with T2
+        K1 = K2;
+        T_next = T_key2;
+        continue;
+      }
     } else {
       sel_collect(bm, a.n_blk, T_f, &sh->n_hot, sh->cell, SH::kCellCap);
       __syncthreads();
@@ -732,6 +759,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
     //          ones (7 % of the blocks on noise) behind the nhot slots ----
     {
       const int ne = nhot * 8;
+      const bool T_ge80 = T_f >= -80.0f;
       for (int e0 = 0; e0 < ne; e0 += 2 * kSelThreads) {
         float4 v[2];
         uint32_t org[2], pos[2];
@@ -754,10 +782,28 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+          // A cell clearly below one of its neighbours INSIDE the block is no peak, whatever lies outside: leave it
+          // out of the queue.  On noise this changes nothing (a block holds one or two cells >= T); on the smooth
+          // maps of a trained head, whose hot regions span whole blocks, it cuts the queue from ~7 cells per hot
+          // block to about one.  ("clearly": by the margin below which sel_is_peak still checks for a sigmoid tie.)
+          const bool live = org[u] != 0xffffffffu;
+          const float w0 = live ? vv[0] : TAUV_NEG_INF, w1 = live ? vv[1] : TAUV_NEG_INF;
+          const float w2 = live ? vv[2] : TAUV_NEG_INF, w3 = live ? vv[3] : TAUV_NEG_INF;
+          // maxima over the columns c-1..c+1 of this row, then over the rows above and below (eight lanes = the eight
+          // rows of a block; a shuffle of width 8 hands the first / last row its own value back, which is neutral)
+          const float h0 = fmaxf(w0, w1), h3 = fmaxf(w2, w3), h1 = fmaxf(h0, w2), h2 = fmaxf(w1, h3);
+          const float nm[4] = {
+              fmaxf(h0, fmaxf(__shfl_up_sync(0xffffffffu, h0, 1, 8), __shfl_down_sync(0xffffffffu, h0, 1, 8))),
+              fmaxf(h1, fmaxf(__shfl_up_sync(0xffffffffu, h1, 1, 8), __shfl_down_sync(0xffffffffu, h1, 1, 8))),
+              fmaxf(h2, fmaxf(__shfl_up_sync(0xffffffffu, h2, 1, 8), __shfl_down_sync(0xffffffffu, h2, 1, 8))),
+              fmaxf(h3, fmaxf(__shfl_up_sync(0xffffffffu, h3, 1, 8), __shfl_down_sync(0xffffffffu, h3, 1, 8)))};
           unsigned hm = 0u;
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (org[u] != 0xffffffffu && !(vv[c] < T_f)) hm |= 1u << c;  // (NaN cells pass here and fail the peak test)
+          for (int c = 0; c < 4; ++c) {
+            // (nm >= the cell itself >= T: with T >= -80 the third condition of sel_is_peak's margin holds by itself)
+            const bool below = (nm[c] - vv[c]) >= 1e-3f && vv[c] <= 4.0f && (T_ge80 || nm[c] >= -80.0f);  // (false for NaN)
+            if (live && !(vv[c] < T_f) && !below) hm |= 1u << c;  // (NaN cells pass here and fail the peak test)
+          }
           const unsigned bal = __ballot_sync(0xffffffffu, hm != 0u);
           const unsigned seg = (bal >> (lane & 24)) & 0xffu;
           const int bs = (e0 + u * kSelThreads + tid) >> 3;
@@ -821,12 +867,22 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
     // ---- 3c. one thread per queued cell: peak test, sigmoid, final key into the cell's candidate slot ----
     //          (warps 0-7), while the other warps do the size / offset / depth arithmetic of every queued cell — it
     //          would otherwise sit, with its gathers and two fp64 divisions, at the very end of the pass
+    //          Only the peaks enter the candidate list (warp-aggregated append; candcell[] remembers the cell behind
+    //          each): on smooth maps most queued cells are not peaks, and ranking costs the square of the list.
+    static_assert(offsetof(SH, hotpos) == offsetof(SH, hot) + sizeof(uint32_t) * SH::kHotCap &&
+                      2 * SH::kHotCap >= SH::kCellCap, "candcell[] spans hot[] and hotpos[]");
+    uint32_t* candcell = sh->hot;  // (hot[] + hotpos[], both dead since 3a: kCellCap entries)
     if (tid < 256) {
-      for (int i = tid; i < n; i += 256) sh->cand[i] = sel_test_cell(sh, i);
-      if (tid == 255) {
-        if (n & 1) sh->cand[n] = 0ull;  // (the rank loop reads pairs; n < kSelCandCap when odd)
-        sh->s_T = sigmoid_ref(T_f);     // (for the completeness test of sel_rank_emit)
+      for (int i0 = 0; i0 < n; i0 += 256) {
+        const int i = i0 + tid;
+        const unsigned long long ck = i < n ? sel_test_cell(sh, i) : 0ull;
+        const int slot = sel_append(&sh->n_cand, ck != 0ull);
+        if (slot >= 0) {
+          sh->cand[slot] = ck;
+          candcell[slot] = (uint32_t)i;
+        }
       }
+      if (tid == 255) sh->s_T = sigmoid_ref(T_f);  // (for the completeness test of sel_rank_emit)
     } else if (a.box.enabled && n <= SH::kBoxCap) {
       for (int i = tid - 256; i < n; i += kSelThreads - 256) {
         const uint32_t pos = sh->cellpos[i];
@@ -838,13 +894,25 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
     SEL_NOTE(8, attempts);
     SEL_NOTE(9, nhot);
     SEL_NOTE(10, n);
+    const int ncand = sh->n_cand;
+    SEL_NOTE(14, ncand);
     // ---- 4. rank, emit, and check that enough peaks reached T and nothing below T could have made it ----
-    const int npos = sel_rank_emit(a, sh, b, n, T_key, n <= SH::kBoxCap);
+    const int npos = sel_rank_emit(a, sh, b, ncand, T_key, n <= SH::kBoxCap, candcell);
     SEL_STAMP(5);
     if (T_key != 0u && sh->flag) {
+      // Not enough peaks at or above T, or the k-th best too close to it: lower T.  The number of blocks that must be
+      // examined per peak found is a property of the map (1.07 on noise, 5-10 on the smooth maps of a trained head,
+      // whose hot regions span many blocks), so the next K1 aims at 1.5 k peaks at the ratio just measured — at most
+      // what the hot-block list holds, once; if that is not enough either, the frame is done exhaustively.
+      const int valid = ncand - sh->n_zero > 0 ? ncand - sh->n_zero : 1;
       __syncthreads();
       if (tid == 0) sh->first_below = k;
-      K1 *= 4;
+      long long next = (long long)K1 * k * 3 / (2 * valid) + 16;
+      if (next < K1 + (K1 >> 1)) next = K1 + (K1 >> 1);
+      if (next > (1 << 20)) next = 1 << 20;
+      const int lim = SH::kHotCap - SH::kHotCap / 8;
+      if (K1 < lim && next > lim) next = lim;
+      K1 = (int)next;
       continue;
     }
     if (npos < k) sel_finish(a, sh, b, npos);
@@ -872,7 +940,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
     n = sel_slow(a, sh, fhm, bm);
     if (tid == 0 && (n & 1) && n < SH::kCandCap) sh->cand[n] = 0ull;
     __syncthreads();
-    const int npos = sel_rank_emit(a, sh, b, n, 0u, false);
+    const int npos = sel_rank_emit(a, sh, b, n, 0u, false, nullptr);
     if (npos < k) sel_finish(a, sh, b, npos);
   }
 }

@@ -354,6 +354,22 @@ def test_select_path_smooth_fields(cn, B, C, H, W, k, box, passes):
     assert_equal(idx, oi), assert_equal(lab, ol), assert_close(sc, osc, what="score")
 
 
+@pytest.mark.parametrize("q,hi", [(0.25, 3.0), (0.001, 3.0), (0.0005, 12.0)])
+def test_select_path_smooth_plateaus_and_saturation(cn, q, hi):
+    """Smooth fields quantised to steps of q: plateaus that span block borders (every plateau cell is a peak), steps
+    below the margin of the in-block pre-filter of the select pass (1e-3), and logits where the fp32 sigmoid saturates
+    so that cells BELOW a neighbour still tie with it — the queue filter may only drop what sel_is_peak would."""
+    g = synth.gen(77)
+    f = torch.randn((2, 6, 64 + 16, 64 + 16), generator=g)
+    for _ in range(2):
+        f = torch.nn.functional.avg_pool2d(f, 9, 1)
+    f = (f - f.min()) / (f.max() - f.min()) * (hi + 6.0) - 6.0
+    logits = (torch.round(f / q) * q).contiguous()
+    oi, ol, osc = O.heatmap_detect(O.heatmap_nms(torch.sigmoid(logits), 3), 100)
+    idx, lab, sc = cn.D.heatmap_peaks(logits.to(cn.dev), 100)
+    assert_equal(idx, oi), assert_equal(lab, ol), assert_close(sc, osc, what="score")
+
+
 @pytest.mark.parametrize("B,C,H,W,k", [(2, 3, 13, 12, 17), (1, 1, 1, 8, 3), (3, 2, 41, 36, 64), (1, 7, 50, 20, 256),
                                        (2, 16, 128, 128, 256), (5, 1, 128, 128, 100), (1, 80, 128, 128, 1),
                                        (2, 20, 128, 128, 1000), (1, 80, 128, 128, 500), (2, 12, 128, 128, 600),

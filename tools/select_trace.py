@@ -12,6 +12,12 @@ a = [int(x) for x in sys.argv[1:]]
 B, C, H, W, K = (a + [64, 80, 128, 128, 100][len(a):])
 g = torch.Generator(device=dev); g.manual_seed(1)
 logits = torch.randn((B, C, H, W), device=dev, generator=g) * 1.5 - 2.2
+if os.environ.get("SMOOTH"):  # box-filtered noise (SMOOTH="box,passes"): the smooth maps of a trained head
+    box, passes = (int(v) for v in os.environ["SMOOTH"].split(","))
+    x = torch.randn((B, C, H + passes * (box - 1), W + passes * (box - 1)), device=dev, generator=g)
+    for _ in range(passes):
+        x = torch.nn.functional.avg_pool2d(x, box, 1)
+    logits = ((x - x.mean()) / x.std() * 1.5 - 2.2).contiguous()
 size = (torch.rand((B, 2, H, W), device=dev, generator=g) * 0.3).permute(0, 2, 3, 1)
 offset = (torch.rand((B, 2, H, W), device=dev, generator=g) * 4).permute(0, 2, 3, 1)
 mc = SimpleNamespace(in_h=H * 4, in_w=W * 4, downsample_ratio=4, out_h=H, out_w=W)
@@ -40,6 +46,6 @@ for rep in range(2):
       col = t[:, i][t[:, i] > 0]
       if len(col):
           print(f"  {nme:16s} {((col - t0) / 1e3).mean():7.2f} {((col - t0) / 1e3).max():7.2f}")
-  print("  attempts per frame:", np.unique(t[:, 8], return_counts=True), " hot blocks mean %.1f max %d, candidates mean %.1f min %d" % (
-      t[:, 9].mean(), t[:, 9].max(), t[:, 10].mean(), t[:, 10].min()))
+  print("  attempts per frame:", np.unique(t[:, 8], return_counts=True), " hot blocks mean %.1f max %d, queued cells mean %.1f min %d" % (
+      t[:, 9].mean(), t[:, 9].max(), t[:, 10].mean(), t[:, 10].min()), " peaks in the list mean %.1f min %d" % (t[:, 14].mean(), t[:, 14].min()))
   print("  CTA launched before the dependency resolved by (us): mean %.2f max %.2f" % (((t[:, 1] - t[:, 0]) / 1e3).mean(), ((t[:, 1] - t[:, 0]) / 1e3).max()))
