@@ -371,6 +371,62 @@ int tauv_yolact_match_anchors(const float* anchor, const float* truth_box,
                               float* match_iou, uint8_t* positive, uint8_t* negative,
                               float* target, tauv_stream_t stream);
 
+/* Classification (hard-negative mining) and box terms of the YOLACT loss, forward — yolact/model/loss.py:26-56
+ * (per-frame target classes, F.cross_entropy(reduction="none"), torch.topk of -softmax[:, 0] over the negative priors
+ * with k = ratio * n_positive, sum over positives + mined negatives) and :58-68 (smooth-L1 over the positives).
+ *   cls [B,N,C1] f32 class logits, enc [B,N,4] predicted box encodings, and from tauv_yolact_match_anchors:
+ *   target [B,N,4], positive / negative [B,N] u8, match_index [B,N] i64; truth_cls [B,M] i64 ->
+ *   selected [B,N] u8 (positives and mined negatives; ties of the background confidence go to the lower prior index),
+ *   pos_list [B,N] i32 (each frame's positives in prior order, first n_pos[b] entries; may be NULL),
+ *   sums [B,2] f64 (sum of the selected cross entropies, sum of the positives' smooth-L1), n_pos [B] i64.
+ * The caller normalises (loss.py:54-57, :70-73): class term = sum(sums[:,0]) / ((1 + ratio) * P), box term =
+ * sum(sums[:,1]) / P with P = sum(n_pos), undivided when P == 0.  Deterministic (fixed summation order). */
+size_t tauv_yolact_class_box_loss_workspace_bytes(int B, int N);
+int tauv_yolact_class_box_loss(const float* cls, const float* enc, const float* target,
+                               const uint8_t* positive, const uint8_t* negative,
+                               const int64_t* match_index, const int64_t* truth_cls, int B, int N,
+                               int C1, int M, int ratio, uint8_t* selected, int32_t* pos_list,
+                               double* sums, int64_t* n_pos, void* workspace, size_t workspace_bytes,
+                               tauv_stream_t stream);
+
+/* Backward of the two terms (what autograd derives from loss.py:26-73): grad_cls [B,N,C1] = g_cls / ((1 + ratio) P) *
+ * selected * (softmax(cls) - onehot(target class)), grad_enc [B,N,4] = g_box / P * positive * smooth_l1'(enc - target);
+ * n_pos_total [1] i64 = P (device), grad_cls_loss / grad_box_loss [1] f32 (device).  Either output (with its incoming
+ * gradient) may be NULL. */
+int tauv_yolact_class_box_loss_backward(const float* cls, const float* enc, const float* target,
+                                        const uint8_t* positive, const uint8_t* selected,
+                                        const int64_t* match_index, const int64_t* truth_cls, int B,
+                                        int N, int C1, int M, int ratio, const int64_t* n_pos_total,
+                                        const float* grad_cls_loss, const float* grad_box_loss,
+                                        float* grad_cls, float* grad_enc, tauv_stream_t stream);
+
+/* Mask term of the YOLACT loss, forward — yolact/model/loss.py:75-115: for every positive prior (pos_list / n_pos of
+ * tauv_yolact_class_box_loss) the BCE between clamp(sigmoid(coeff . proto), 1e-4) and the bilinearly resized mask of
+ * its matched truth (seg == match_index), weighted by box_to_mask(truth_box) * nearest-resized img_valid, over the
+ * resized truth mask's area.
+ *   coeff [B,N,K] f32 (K <= 32), proto [B,K,PH,PW] f32, match_index [B,N] i64, truth_box [B,M,4] f32,
+ *   seg [B,SH,SW] i32 (truth index per pixel), img_valid [B,SH,SW] u8 ->
+ *   tsum [B,N] f32 (resized truth-mask area of each listed positive, in list order; kept for the backward),
+ *   partial [B, tauv_yolact_mask_loss_partials()] f64 whose sum is the sum over positives of (weighted BCE / area),
+ *   positives with an empty resized truth mask skipped (loss.py:93-94).  The caller divides by the batch's positives
+ *   (loss.py:117-120).  Deterministic. */
+int tauv_yolact_mask_loss_partials(void);
+int tauv_yolact_mask_loss(const float* coeff, const float* proto, const int32_t* pos_list,
+                          const int64_t* n_pos, const int64_t* match_index, const float* truth_box,
+                          const int32_t* seg, const uint8_t* img_valid, int B, int N, int K, int M,
+                          int PH, int PW, int SH, int SW, float* tsum, double* partial,
+                          tauv_stream_t stream);
+
+/* Backward of the mask term: grad_coeff [B,N,K] (zero outside the positives) and grad_proto [B,K,PH,PW]; either may be
+ * NULL.  n_pos_total [1] i64 and grad_out [1] f32 on the device.  No atomics: deterministic. */
+int tauv_yolact_mask_loss_backward(const float* coeff, const float* proto, const int32_t* pos_list,
+                                   const int64_t* n_pos, const int64_t* match_index,
+                                   const float* truth_box, const int32_t* seg,
+                                   const uint8_t* img_valid, int B, int N, int K, int M, int PH, int PW,
+                                   int SH, int SW, const float* tsum, const int64_t* n_pos_total,
+                                   const float* grad_out, float* grad_coeff, float* grad_proto,
+                                   tauv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

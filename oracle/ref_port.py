@@ -441,3 +441,60 @@ def match_anchors(anchor, truth_box, truth_valid, pos_thr: float, neg_thr: float
     matched = truth_box[torch.arange(B).unsqueeze(1), match_index]  # [B,N,4]
     target = box_encode(matched, anchor.expand(B, -1, -1), variances)
     return match_index, match_iou, positive, negative, target
+
+
+def yolact_class_box_loss(classification, box_encoding, anchor, truth_valid, truth_classification, truth_box,
+                          pos_thr: float, neg_thr: float, variances, ratio: int):
+    """yolact/model/loss.py:16-73 — anchor matching, then the classification term with hard-negative mining and the
+    box term.  Returns (classification_loss, box_loss, selected [B,N] bool).  The reference's ``torch.topk`` over
+    ``where(negative, -background_confidence, -inf)`` (:40-43) leaves the order of equal entries open; here the lower
+    prior index wins (a stable ascending sort), which is also what the CUDA path does."""
+    match_index, match_iou, positive, negative, _ = match_anchors(anchor, truth_box, truth_valid, pos_thr, neg_thr, variances)
+    B, N = positive.shape
+    cls_sums, box_sums, selected = [], [], torch.zeros((B, N), dtype=torch.bool)
+    for b in range(B):
+        target_class = truth_classification[b, match_index[b]].clone()          # :27
+        target_class[~positive[b]] = 0                                          # :28
+        ce = F.cross_entropy(classification[b], target_class, reduction="none")  # :30-34
+        k = int(ratio * positive[b].sum())                                      # :35-36
+        background = F.softmax(classification[b], dim=-1)[:, 0]                 # :38
+        key = torch.where(negative[b], background, torch.full_like(background, float("inf")))  # :40-43, ascending
+        mined = torch.sort(key, stable=True).indices[:k].detach()
+        sel = positive[b].clone()                                               # :48-50
+        sel[mined] = True
+        selected[b] = sel
+        cls_sums.append((sel.float() * ce).sum())                               # :52
+        pos = positive[b]
+        tgt = box_encode(truth_box[b, match_index[b, pos]].unsqueeze(0), anchor[0, pos].unsqueeze(0), variances).squeeze(0)
+        box_sums.append(F.smooth_l1_loss(box_encoding[b, pos], tgt, reduction="none").sum())   # :61-66
+    P = positive.sum()
+    cls_loss, box_loss = torch.stack(cls_sums).sum(), torch.stack(box_sums).sum()
+    if P > 0:                                                                   # :54-57, :70-73
+        cls_loss, box_loss = cls_loss / ((1 + ratio) * P), box_loss / P
+    return cls_loss, box_loss, selected
+
+
+def yolact_mask_loss(mask_coeff, mask_prototype, anchor, truth_valid, truth_box, truth_seg_map, truth_img_valid,
+                     pos_thr: float, neg_thr: float, variances):
+    """yolact/model/loss.py:75-121 — the mask term: for every positive prior, BCE of the assembled mask against the
+    bilinearly resized mask of its matched truth, inside the truth box and the valid image region, over the resized
+    truth mask's area; positives whose resized truth mask is empty are skipped."""
+    match_index, _, positive, _, _ = match_anchors(anchor, truth_box, truth_valid, pos_thr, neg_thr, variances)
+    B = positive.shape[0]
+    size = mask_prototype.shape[-2:]
+    total = torch.zeros(())
+    for b in range(B):
+        for n in positive[b].nonzero().flatten().tolist():
+            j = int(match_index[b, n])
+            m = (mask_coeff[b, n].view(-1, 1, 1) * mask_prototype[b]).sum(dim=0)             # :82
+            m = torch.clamp(torch.sigmoid(m), min=1e-4)                                     # :83-84
+            t = F.interpolate((truth_seg_map[b] == j).float()[None, None], size, mode="bilinear")[0, 0]  # :86-91
+            if t.sum() == 0:                                                                # :93-94
+                continue
+            bce = F.binary_cross_entropy(torch.clamp(m.reshape(-1), 1e-4, 1 - 1e-4),
+                                         torch.clamp(t.reshape(-1), 1e-4, 1 - 1e-4), reduction="none")  # :96-100
+            valid = F.interpolate(truth_img_valid[b].float()[None, None], size, mode="nearest")[0, 0]   # :102-106
+            w = box_to_mask(truth_box[b, j], size) * valid                                  # :108-111
+            total = total + (w.reshape(-1) * bce).sum() / t.sum()                           # :113
+    P = positive.sum()
+    return total / P if P > 0 else total                                                    # :117-120

@@ -91,6 +91,16 @@ _SIGNATURES = {
     "tauv_box_to_mask": (c_int, [_F, c_int, c_int, _F, c_void_p]),
     "tauv_yolact_match_anchors": (c_int, [_F, _F, _U8, c_int, c_int, c_int, c_float, c_float, c_float, c_float, _I64,
                                           _F, _U8, _U8, _F, c_void_p]),
+    "tauv_yolact_class_box_loss_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "tauv_yolact_class_box_loss": (c_int, [_F, _F, _F, _U8, _U8, _I64, _I64, c_int, c_int, c_int, c_int, c_int, _U8, _I32,
+                                           _D, _I64, c_void_p, c_size_t, c_void_p]),
+    "tauv_yolact_class_box_loss_backward": (c_int, [_F, _F, _F, _U8, _U8, _I64, _I64, c_int, c_int, c_int, c_int, c_int,
+                                                    _I64, _F, _F, _F, _F, c_void_p]),
+    "tauv_yolact_mask_loss_partials": (c_int, []),
+    "tauv_yolact_mask_loss": (c_int, [_F, _F, _I32, _I64, _I64, _F, _I32, _U8, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, c_int, _F, _D, c_void_p]),
+    "tauv_yolact_mask_loss_backward": (c_int, [_F, _F, _I32, _I64, _I64, _F, _I32, _U8, c_int, c_int, c_int, c_int, c_int,
+                                               c_int, c_int, c_int, _F, _I64, _F, _F, _F, c_void_p]),
 }
 
 

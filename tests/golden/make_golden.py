@@ -369,5 +369,63 @@ def main():
          positive=positive, negative=negative, targets=torch.cat(targets, 0), counts=np.array(counts))
 
 
+def yolact_loss_golden():
+    """The reference's own ``loss`` (yolact/model/loss.py:8-125) with its own autograd gradients, on a small case:
+    3 frames (one without a valid truth), 159 priors, 7 classes, 8 prototypes of 20x24, 40x44 segmentation maps."""
+    from tauv_vision.yolact.model import loss as ref_yloss
+    ycfg = YolactModelConfig(in_w=550, in_h=550, feature_depth=0, n_classes=0, n_prototype_masks=0,
+                             n_masknet_layers_pre_upsample=0, n_masknet_layers_post_upsample=0,
+                             n_prediction_head_layers=0, n_classification_layers=0, n_box_layers=0, n_mask_layers=0,
+                             n_fpn_downsample_layers=0, anchor_scales=(24, 48, 96, 192, 384),
+                             anchor_aspect_ratios=(1 / 2, 1, 2), box_variances=(0.1, 0.2), iou_pos_threshold=0.4,
+                             iou_neg_threshold=0.3, negative_example_ratio=3, img_mean=(0, 0, 0), img_stddev=(1, 1, 1))
+    small = [(7, 5), (4, 3), (2, 2), (1, 1), (1, 1)]
+    anchor = torch.cat([ref_anchors.get_anchor(i, s, ycfg) for i, s in enumerate(small)], dim=1)
+    B, M, C1, K, PH, PW, SH, SW = 3, 6, 7, 8, 20, 24, 40, 44
+    N = anchor.shape[1]
+    tb, tv = synth.truth_boxes(B, M, seed=201)
+    g = synth.gen(202)
+    for b in range(B):  # half of the truths sit on (jittered) priors so that positives exist
+        pick = torch.randint(0, N, (3,), generator=g)
+        a = anchor[0, pick]
+        jit = torch.randn((3, 4), generator=g)
+        tb[b, :3] = torch.cat((a[:, :2] + 0.1 * jit[:, :2] * a[:, 2:], a[:, 2:] * (1 + 0.1 * jit[:, 2:])), -1)
+    tb[1, 4] = tb[1, 0]  # a duplicated truth: painted over in the segmentation map, so truth 0's mask is empty (:93-94)
+    tv[0, :3] = True
+    tv[1, 0] = tv[1, 4] = True
+    tv[2] = False        # a frame without any valid truth
+    tcls = torch.randint(1, C1, (B, M), generator=g)
+    seg = torch.full((B, SH, SW), 255, dtype=torch.int64)
+    for b in range(B):
+        for j in range(M):
+            if not tv[b, j]:
+                continue
+            y, x, h, w = (float(v) for v in tb[b, j])
+            y0, y1 = max(int((y - h / 2) * SH), 0), min(int((y + h / 2) * SH) + 1, SH)
+            x0, x1 = max(int((x - w / 2) * SW), 0), min(int((x + w / 2) * SW) + 1, SW)
+            seg[b, y0:y1, x0:x1] = j
+    img_valid = torch.ones((B, SH, SW), dtype=torch.bool)
+    img_valid[:, :3, :] = False
+    img_valid[0, :, -5:] = False
+    cls = (torch.randn((B, N, C1), generator=g) * 2).requires_grad_()
+    enc = (torch.randn((B, N, 4), generator=g) * 0.8).requires_grad_()
+    coeff = torch.tanh(torch.randn((B, N, K), generator=g)).requires_grad_()
+    proto = torch.relu(torch.randn((B, K, PH, PW), generator=g)).requires_grad_()
+    total, (lc, lb, lm) = ref_yloss.loss((cls, enc, coeff, anchor, proto), (tv, tcls, tb, seg, img_valid), ycfg)
+    g_cls, g_enc = torch.autograd.grad(lc + lb, (cls, enc), retain_graph=True)
+    g_coeff, g_proto = torch.autograd.grad(lm, (coeff, proto))
+    iou = ref_boxes.iou_matrix(anchor, tb)
+    match_iou = torch.max(iou * tv.unsqueeze(1).float(), dim=2).values
+    save("yl_loss", anchor=anchor, truth_valid=tv, truth_cls=tcls, truth_box=tb, seg=seg, img_valid=img_valid,
+         cls=cls.detach(), enc=enc.detach(), coeff=coeff.detach(), proto=proto.detach(), total=total.detach(),
+         cls_loss=lc.detach(), box_loss=lb.detach(), mask_loss=lm.detach(), grad_cls=g_cls, grad_enc=g_enc,
+         grad_coeff=g_coeff, grad_proto=g_proto, n_pos=int((match_iou >= 0.4).sum()), pos_thr=0.4, neg_thr=0.3,
+         ratio=3, v0=0.1, v1=0.2)
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["yl_loss"]:
+        yolact_loss_golden()
+    else:
+        main()
+        yolact_loss_golden()

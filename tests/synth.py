@@ -97,9 +97,10 @@ def truth_to(t, device):
 # ---- YOLACT --------------------------------------------------------------------------------------
 
 def yolact_config(in_h=550, in_w=550, scales=(24, 48, 96, 192, 384), ratios=(0.5, 1, 2), variances=(0.1, 0.2),
-                  pos=0.4, neg=0.3):
+                  pos=0.4, neg=0.3, negative_example_ratio=3):
     return SimpleNamespace(in_h=in_h, in_w=in_w, anchor_scales=scales, anchor_aspect_ratios=ratios,
-                           box_variances=variances, iou_pos_threshold=pos, iou_neg_threshold=neg)
+                           box_variances=variances, iou_pos_threshold=pos, iou_neg_threshold=neg,
+                           negative_example_ratio=negative_example_ratio)
 
 
 def fpn_sizes(in_h, in_w):

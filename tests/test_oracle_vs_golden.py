@@ -237,3 +237,23 @@ def test_match_golden():
     assert_equal(pos, g["positive"]), assert_equal(neg, g["negative"])
     assert_equal(tgt[pos], g["targets"], "box_encode targets of the positives")
     assert [int(p.sum()) for p in pos] == g["counts"].tolist()
+
+
+def test_yolact_loss_golden():
+    """yolact/model/loss.py:8-125 — the three terms and, through the oracle's own autograd graph, the reference's
+    gradients with respect to the class logits, the box encodings, the mask coefficients and the prototypes."""
+    g = golden("yl_loss")
+    var = (float(g["v0"]), float(g["v1"]))
+    cls, enc = t(g["cls"]).requires_grad_(), t(g["enc"]).requires_grad_()
+    coeff, proto = t(g["coeff"]).requires_grad_(), t(g["proto"]).requires_grad_()
+    anchor, tv, tb = t(g["anchor"]), t(g["truth_valid"]), t(g["truth_box"])
+    cl, bl, sel = O.yolact_class_box_loss(cls, enc, anchor, tv, t(g["truth_cls"]), tb, float(g["pos_thr"]),
+                                          float(g["neg_thr"]), var, int(g["ratio"]))
+    ml = O.yolact_mask_loss(coeff, proto, anchor, tv, tb, t(g["seg"]), t(g["img_valid"]), float(g["pos_thr"]),
+                            float(g["neg_thr"]), var)
+    assert_equal(cl.detach(), g["cls_loss"]), assert_equal(bl.detach(), g["box_loss"]), assert_equal(ml.detach(), g["mask_loss"])
+    assert int(sel.sum()) == (1 + int(g["ratio"])) * int(g["n_pos"])
+    g_cls, g_enc = torch.autograd.grad(cl + bl, (cls, enc))
+    g_coeff, g_proto = torch.autograd.grad(ml, (coeff, proto))
+    assert_equal(g_cls, g["grad_cls"]), assert_equal(g_enc, g["grad_enc"])
+    assert_equal(g_coeff, g["grad_coeff"]), assert_equal(g_proto, g["grad_proto"])

@@ -466,3 +466,132 @@ def test_match_full_size_vs_oracle(yl):
     assert_equal(m.positive_match, pos), assert_equal(m.negative_match, neg)
     assert int(pos.sum()) > 0
     assert_close(m.box_target[m.positive_match], tgt[pos], atol=1e-6, what="targets")
+
+
+# ---- loss (YOLACT half) ----------------------------------------------------------------------------
+
+def _loss_case(g, d):
+    pred = tuple(t(g[k]).to(d) for k in ("cls", "enc", "coeff", "anchor", "proto"))
+    truth = tuple(t(g[k]).to(d) for k in ("truth_valid", "truth_cls", "truth_box", "seg", "img_valid"))
+    return pred, truth
+
+
+def test_loss_golden(yl):
+    """The reference's own loss values and autograd gradients (yolact/model/loss.py:8-125, tests/golden/make_golden.py):
+    hard-negative mining, a frame without truths, a positive whose resized truth mask is empty."""
+    g = golden("yl_loss")
+    pred, truth = _loss_case(g, yl.dev)
+    cls, enc, coeff, anchor, proto = pred
+    for x in (cls, enc, coeff, proto):
+        x.requires_grad_()
+    total, (lc, lb, lm) = yl.loss.loss(pred, truth, CFG)
+    assert_close(lc, g["cls_loss"], what="classification term"), assert_close(lb, g["box_loss"], what="box term")
+    assert_close(lm, g["mask_loss"], what="mask term"), assert_close(total, g["total"], what="total")
+    total.backward()
+    assert_close(cls.grad, g["grad_cls"], atol=1e-9, what="d/d classification")
+    assert_close(enc.grad, g["grad_enc"], atol=1e-9, what="d/d box_encoding")
+    assert_close(coeff.grad, g["grad_coeff"], rtol=1e-4, atol=1e-8, what="d/d mask_coeff")
+    assert_close(proto.grad, g["grad_proto"], rtol=1e-4, atol=1e-8, what="d/d mask_prototype")
+
+
+@pytest.mark.parametrize("B,N,C1,M,ratio", [(2, 300, 81, 5, 3), (1, 19248, 81, 16, 3), (3, 1000, 4, 3, 0),
+                                            (2, 2500, 33, 40, 7)])
+def test_class_box_loss_vs_oracle(yl, B, N, C1, M, ratio):
+    """Selected sets exact (random logits: no ties in the background confidence), losses and gradients 1e-5 against
+    the oracle's autograd; N not a multiple of 32 or 1024, ratio 0 (no mining), many truths."""
+    d = yl.dev
+    g = synth.gen(7 * N + C1)
+    anchor = torch.cat((torch.rand((1, N, 2), generator=g), torch.rand((1, N, 2), generator=g) * 0.2 + 0.02), -1)
+    tb, tv = synth.truth_boxes(B, M, seed=N + 1)
+    pick = torch.randint(0, N, (B, min(M, 3)), generator=g)
+    tb[:, :pick.shape[1]] = anchor[0, pick] * (1 + 0.05 * torch.randn((B, pick.shape[1], 4), generator=g).clamp(-1, 1))
+    tv[:, :pick.shape[1]] = True
+    tcls = torch.randint(1, C1, (B, M), generator=g)
+    cls = (torch.randn((B, N, C1), generator=g) * 3).requires_grad_()
+    enc = (torch.randn((B, N, 4), generator=g) * 1.5).requires_grad_()
+    cfg = SimpleNamespace(**{**vars(CFG), "negative_example_ratio": ratio})
+    ocl, obl, osel = O.yolact_class_box_loss(cls, enc, anchor, tv, tcls, tb, cfg.iou_pos_threshold, cfg.iou_neg_threshold,
+                                             cfg.box_variances, ratio)
+    og_cls, og_enc = torch.autograd.grad(ocl + 2 * obl, (cls, enc))
+    dcls, denc = cls.detach().to(d).requires_grad_(), enc.detach().to(d).requires_grad_()
+    m = yl.loss.match_anchors(anchor.to(d), tb.to(d), tv.to(d), cfg)
+    r = yl.loss.class_box_loss(dcls, denc, m, tcls.to(d), cfg)
+    assert int(r.n_pos.sum()) > 0
+    assert_equal(r.selected, osel, "positives + mined negatives")
+    for b in range(B):
+        n = int(r.n_pos[b])
+        assert_equal(r.pos_list[b, :n], m.positive_match[b].nonzero().flatten().int(), "positives in prior order")
+    assert_close(r.classification_loss, ocl.detach(), what="classification term")
+    assert_close(r.box_loss, obl.detach(), what="box term")
+    (r.classification_loss + 2 * r.box_loss).backward()
+    assert_close(dcls.grad, og_cls, atol=1e-9, what="d/d classification")
+    assert_close(denc.grad, og_enc, atol=1e-9, what="d/d box_encoding")
+
+
+def test_class_box_loss_ties_and_short_negative_lists(yl):
+    """Equal background confidences at the mining boundary go to the lower prior index, and when ratio * n_positive
+    exceeds the frame's negatives the remaining picks are the lowest-index priors among the rest (the oracle's stable
+    sort); quantised logits make the ties."""
+    d = yl.dev
+    g = synth.gen(55)
+    B, N, C1, M = 2, 640, 5, 4
+    anchor = torch.cat((torch.rand((1, N, 2), generator=g), torch.rand((1, N, 2), generator=g) * 0.2 + 0.02), -1)
+    tb, tv = synth.truth_boxes(B, M, seed=56)
+    tb[:, :2] = anchor[0, torch.randint(0, N, (B, 2), generator=g)]
+    tv[:, :2] = True
+    tcls = torch.randint(1, C1, (B, M), generator=g)
+    cls = torch.round(torch.randn((B, N, C1), generator=g))          # integer logits: many equal softmax rows
+    enc = torch.randn((B, N, 4), generator=g)
+    for ratio in (3, 400):
+        cfg = SimpleNamespace(**{**vars(CFG), "negative_example_ratio": ratio})
+        ocl, obl, osel = O.yolact_class_box_loss(cls, enc, anchor, tv, tcls, tb, cfg.iou_pos_threshold,
+                                                 cfg.iou_neg_threshold, cfg.box_variances, ratio)
+        m = yl.loss.match_anchors(anchor.to(d), tb.to(d), tv.to(d), cfg)
+        r = yl.loss.class_box_loss(cls.to(d), enc.to(d), m, tcls.to(d), cfg)
+        assert_equal(r.selected, osel, f"ratio {ratio}")
+        assert_close(r.classification_loss, ocl, what="classification term")
+
+
+@pytest.mark.parametrize("B,N,K,M,PH,PW,SH,SW", [(2, 400, 32, 5, 138, 138, 550, 550), (1, 200, 12, 3, 17, 23, 40, 31),
+                                                 (2, 300, 32, 4, 64, 64, 64, 64)])
+def test_mask_loss_vs_oracle(yl, B, N, K, M, PH, PW, SH, SW):
+    """Mask term and its gradients against the oracle's autograd: the YOLACT shapes (550 -> 138: non-integer resize
+    scale), odd sizes with upsampling, identity resize; blobs of saturated logits exercise the clamps."""
+    d = yl.dev
+    g = synth.gen(31 * PH + K)
+    anchor = torch.cat((torch.rand((1, N, 2), generator=g) * 0.6 + 0.2, torch.rand((1, N, 2), generator=g) * 0.3 + 0.1), -1)
+    tb, tv = synth.truth_boxes(B, M, seed=PH)
+    pick = torch.randint(0, N, (B, 2), generator=g)
+    tb[:, :2] = anchor[0, pick] * (1 + 0.03 * torch.randn((B, 2, 4), generator=g).clamp(-1, 1))
+    tv[:, :2] = True
+    seg = torch.full((B, SH, SW), -1, dtype=torch.int64)
+    for b in range(B):
+        for j in range(M):
+            y, x, h, w = (float(v) for v in tb[b, j])
+            y0, y1 = max(int((y - h / 2) * SH), 0), min(int((y + h / 2) * SH) + 1, SH)
+            x0, x1 = max(int((x - w / 2) * SW), 0), min(int((x + w / 2) * SW) + 1, SW)
+            blob = torch.rand((max(y1 - y0, 0), max(x1 - x0, 0)), generator=g) < 0.7
+            seg[b, y0:y1, x0:x1][blob] = j
+    img_valid = torch.rand((B, SH, SW), generator=g) < 0.9
+    coeff = (torch.randn((B, N, K), generator=g) * 1.5).requires_grad_()
+    proto = (torch.randn((B, K, PH, PW), generator=g)).requires_grad_()
+    cfg = CFG
+    oml = O.yolact_mask_loss(coeff, proto, anchor, tv, tb, seg, img_valid, cfg.iou_pos_threshold, cfg.iou_neg_threshold,
+                             cfg.box_variances)
+    og_c, og_p = torch.autograd.grad(oml, (coeff, proto))
+    m = yl.loss.match_anchors(anchor.to(d), tb.to(d), tv.to(d), cfg)
+    n_pos = m.positive_match.sum(dim=1)
+    assert int(n_pos.sum()) > 0
+    pos_list = torch.zeros((B, N), dtype=torch.int32, device=d)
+    for b in range(B):
+        idx = m.positive_match[b].nonzero().flatten().int()
+        pos_list[b, :idx.numel()] = idx
+    dc, dp = coeff.detach().to(d).requires_grad_(), proto.detach().to(d).requires_grad_()
+    ml = yl.loss.mask_loss(dc, dp, m, pos_list, n_pos, tb.to(d), seg.to(d), img_valid.to(d))
+    assert_close(ml, oml.detach(), what="mask term")
+    (3 * ml).backward()
+    scale = float(og_c.abs().max())
+    assert_close(dc.grad, 3 * og_c, rtol=1e-4, atol=1e-6 * scale, what="d/d mask_coeff")
+    assert_close(dp.grad, 3 * og_p, rtol=1e-4, atol=1e-6 * float(og_p.abs().max()), what="d/d mask_prototype")
+    again = yl.loss.mask_loss(dc, dp, m, pos_list, n_pos, tb.to(d), seg.to(d), img_valid.to(d))
+    assert_equal(again, ml, "run-to-run")
