@@ -406,7 +406,7 @@ int tauv_yolact_class_box_loss_backward(const float* cls, const float* enc, cons
  * resized truth mask's area.
  *   coeff [B,N,K] f32 (K <= 32), proto [B,K,PH,PW] f32, match_index [B,N] i64, truth_box [B,M,4] f32,
  *   seg [B,SH,SW] i32 (truth index per pixel), img_valid [B,SH,SW] u8 ->
- *   tsum [B,N] f32 (resized truth-mask area of each listed positive, in list order; kept for the backward),
+ *   tsum [B,M] f32 (area of every truth's resized mask; kept for the backward),
  *   partial [B, tauv_yolact_mask_loss_partials()] f64 whose sum is the sum over positives of (weighted BCE / area),
  *   positives with an empty resized truth mask skipped (loss.py:93-94).  The caller divides by the batch's positives
  *   (loss.py:117-120).  Deterministic. */

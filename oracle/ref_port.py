@@ -335,10 +335,10 @@ def nms(classification, box, top_k: int, iou_threshold: float, confidence_thresh
 
 def box_to_mask(box, img_size):
     """boxes.py:88-103 — inclusive crop on integer pixel coordinates."""
-    yg = torch.arange(0, img_size[0], dtype=torch.float)
-    xg = torch.arange(0, img_size[1], dtype=torch.float)
+    yg = torch.arange(0, img_size[0], dtype=torch.float, device=box.device)
+    xg = torch.arange(0, img_size[1], dtype=torch.float, device=box.device)
     yc, xc = torch.meshgrid(yg, xg, indexing="ij")
-    b = box * torch.tensor([img_size[0], img_size[1], img_size[0], img_size[1]])
+    b = box * torch.tensor([img_size[0], img_size[1], img_size[0], img_size[1]], device=box.device)
     left, right = b[1] - b[3] / 2, b[1] + b[3] / 2
     top, bottom = b[0] - b[2] / 2, b[0] + b[2] / 2
     return ((xc >= left) & (xc <= right) & (yc >= top) & (yc <= bottom)).float()
@@ -438,7 +438,7 @@ def match_anchors(anchor, truth_box, truth_valid, pos_thr: float, neg_thr: float
     positive = match_iou >= pos_thr
     negative = match_iou <= neg_thr
     B = truth_box.shape[0]
-    matched = truth_box[torch.arange(B).unsqueeze(1), match_index]  # [B,N,4]
+    matched = truth_box[torch.arange(B, device=truth_box.device).unsqueeze(1), match_index]  # [B,N,4]
     target = box_encode(matched, anchor.expand(B, -1, -1), variances)
     return match_index, match_iou, positive, negative, target
 
@@ -451,7 +451,7 @@ def yolact_class_box_loss(classification, box_encoding, anchor, truth_valid, tru
     prior index wins (a stable ascending sort), which is also what the CUDA path does."""
     match_index, match_iou, positive, negative, _ = match_anchors(anchor, truth_box, truth_valid, pos_thr, neg_thr, variances)
     B, N = positive.shape
-    cls_sums, box_sums, selected = [], [], torch.zeros((B, N), dtype=torch.bool)
+    cls_sums, box_sums, selected = [], [], torch.zeros((B, N), dtype=torch.bool, device=classification.device)
     for b in range(B):
         target_class = truth_classification[b, match_index[b]].clone()          # :27
         target_class[~positive[b]] = 0                                          # :28
@@ -482,7 +482,7 @@ def yolact_mask_loss(mask_coeff, mask_prototype, anchor, truth_valid, truth_box,
     match_index, _, positive, _, _ = match_anchors(anchor, truth_box, truth_valid, pos_thr, neg_thr, variances)
     B = positive.shape[0]
     size = mask_prototype.shape[-2:]
-    total = torch.zeros(())
+    total = torch.zeros((), device=mask_coeff.device)
     for b in range(B):
         for n in positive[b].nonzero().flatten().tolist():
             j = int(match_index[b, n])

@@ -356,11 +356,13 @@ static int loss_tile_grid(long long rows) {
 // box_to_mask(truth_box_j) * nearest-resized img_valid_b, summed and divided by the resized truth mask's area; positives
 // whose resized truth mask is empty are skipped.  The reference loops over the positives in Python (~25 ATen kernels
 // and a [SH, SW] -> [PH, PW] F.interpolate each); here
-//   ymask_forward_kernel        : CTAs walk the frame's positives (pos_list of yloss_frame_kernel), threads the pixels;
-//   ymask_backward_coeff_kernel : same walk, d/d coeff_i = sum over pixels of dlogit * proto (block reduction);
-//   ymask_backward_proto_kernel : a thread per pixel walks the frame's positives with the pixel's K prototype values in
-//                                 registers, d/d proto = sum over positives of dlogit * coeff_i — no atomics, so both
-//                                 gradients are deterministic.
+//   ymask_area_kernel           : the area of every truth's resized mask, once per (truth, frame) — positives share it;
+//   ymask_positive_kernel<0>    : CTAs walk the frame's positives (pos_list of yloss_frame_kernel), threads the pixels
+//                                 of the truth box (the weight is zero outside it);
+//   ymask_positive_kernel<1>    : same walk, d/d coeff_i = sum over pixels of dlogit * proto (block reduction);
+//   ymask_backward_proto_kernel : a thread per pixel walks the frame's positives (records staged in shared memory) with
+//                                 the pixel's K prototype values in registers, d/d proto = sum over positives of
+//                                 dlogit * coeff_i — no atomics, so both gradients are deterministic.
 // Inside the clamps d BCE / d logit = sigmoid - truth (F.binary_cross_entropy's backward times sigmoid'), outside 0.
 constexpr int kMaskLossThreads = 256;
 constexpr int kMaskLossMaxK = 32;
@@ -376,7 +378,7 @@ struct MaskLossArgs {
   const uint8_t* img_valid;    // [B,SH,SW]
   int N, K, M, PH, PW, SH, SW;
   float sy, sx;                // (float)SH / PH, (float)SW / PW: ATen's area_pixel_compute_scale without align_corners
-  float* tsum;                 // [B,N]: resized truth-mask area of each listed positive
+  float* tsum;                 // [B,M]: area of every truth's resized mask
   double* partial;             // [B,gridDim.x] (forward)
   const float* grad_out;       // [1] (backward)
   const int64_t* n_pos_total;  // [1] (backward)
@@ -448,6 +450,37 @@ __device__ __forceinline__ double mask_block_sum(double v, double* s_red) {
   return t;
 }
 
+// the pixels of the prototype grid a crop box can cover (a superset: mask_weight decides pixel by pixel)
+struct MaskBoxRange {
+  int y0, x0, bh, bw;
+};
+__device__ __forceinline__ MaskBoxRange mask_box_range(const CropBounds& c, int PH, int PW) {
+  auto lo = [](float v, int n) { return v > 0.0f ? (v < (float)n ? (int)ceilf(v) : n) : 0; };           // (NaN -> 0)
+  auto hi = [](float v, int n) { return v < (float)(n - 1) ? (v >= 0.0f ? (int)floorf(v) : -1) : n - 1; };  // (NaN -> n - 1)
+  MaskBoxRange r;
+  r.y0 = lo(c.top, PH);
+  r.x0 = lo(c.left, PW);
+  r.bh = max(hi(c.bottom, PH) - r.y0 + 1, 0);
+  r.bw = max(hi(c.right, PW) - r.x0 + 1, 0);
+  return r;
+}
+
+// area[b][j] = sum over the prototype grid of the bilinearly resized mask of truth j (loss.py:86-93, :113): one CTA per
+// (truth, frame) — positives that share a truth share its area — summed in fp64 in a fixed order
+__global__ void __launch_bounds__(kMaskLossThreads) ymask_area_kernel(const MaskLossArgs a) {
+  __shared__ double s_red[kMaskLossThreads / 32];
+  const int j = blockIdx.x, b = blockIdx.y;
+  const int HW = a.PH * a.PW;
+  const int32_t* seg = a.seg + (size_t)b * a.SH * a.SW;
+  double area = 0.0;
+  for (int px = threadIdx.x; px < HW; px += kMaskLossThreads) {
+    const int y = px / a.PW, x = px - y * a.PW;
+    area += (double)mask_truth(mask_px(a, b, y, x), seg, j);
+  }
+  area = mask_block_sum(area, s_red);
+  if (threadIdx.x == 0) a.tsum[(size_t)b * a.M + j] = (float)area;
+}
+
 template <bool BACKWARD>
 __global__ void __launch_bounds__(kMaskLossThreads) ymask_positive_kernel(const MaskLossArgs a) {
   __shared__ float s_coeff[kMaskLossMaxK];
@@ -470,37 +503,37 @@ __global__ void __launch_bounds__(kMaskLossThreads) ymask_positive_kernel(const 
     const int j = (int)(jl < 0 ? 0 : (jl >= a.M ? a.M - 1 : jl));
     const float* tb = a.truth_box + ((size_t)b * a.M + j) * 4;
     const CropBounds crop = crop_bounds(make_float4(tb[0], tb[1], tb[2], tb[3]), a.PH, a.PW);
+    const MaskBoxRange box = mask_box_range(crop, a.PH, a.PW);
+    const int npx = box.bh * box.bw;
+    const float area = a.tsum[(size_t)b * a.M + j];
     __syncthreads();
     if (tid < a.K) s_coeff[tid] = a.coeff[((size_t)b * a.N + n) * a.K + tid];
     __syncthreads();
     if (!BACKWARD) {
-      double num = 0.0, area = 0.0;
-      for (int px = tid; px < HW; px += kMaskLossThreads) {
-        const int y = px / a.PW, x = px - y * a.PW;
-        const MaskPx g = mask_px(a, b, y, x);
-        const float t = mask_truth(g, seg, j);
-        area += (double)t;
-        const float w = mask_weight(g, crop);
-        if (w != 0.0f) {
-          float logit = 0.0f;
-          for (int k = 0; k < a.K; ++k) logit += s_coeff[k] * proto[(size_t)k * HW + px];   // loss.py:82
-          const float m = clamp_unit(fmaxf(sigmoid_ref(logit), 1e-4f)), tc = clamp_unit(t);  // :83-84, :97-98
-          num += (double)(w * -(tc * logf(m) + (1.0f - tc) * logf(1.0f - m)));               // :96-100, :113
+      double num = 0.0;
+      if (area > 0.0f) {   // loss.py:93-94
+        for (int q = tid; q < npx; q += kMaskLossThreads) {
+          const int y = box.y0 + q / box.bw, x = box.x0 + q % box.bw, px = y * a.PW + x;
+          const MaskPx g = mask_px(a, b, y, x);
+          const float w = mask_weight(g, crop);
+          if (w != 0.0f) {
+            float logit = 0.0f;
+            for (int k = 0; k < a.K; ++k) logit += s_coeff[k] * proto[(size_t)k * HW + px];   // loss.py:82
+            const float m = clamp_unit(fmaxf(sigmoid_ref(logit), 1e-4f)), tc = clamp_unit(mask_truth(g, seg, j));  // :83-84, :97-98
+            num += (double)(w * -(tc * logf(m) + (1.0f - tc) * logf(1.0f - m)));               // :96-100, :113
+          }
         }
       }
       num = mask_block_sum(num, s_red);
-      area = mask_block_sum(area, s_red);
-      if (tid == 0) a.tsum[(size_t)b * a.N + i] = (float)area;
-      if (area > 0.0) cta_sum += num / area;   // :93-94, :113
+      if (area > 0.0f) cta_sum += num / (double)area;   // :113
     } else {
-      const float area = a.tsum[(size_t)b * a.N + i];
       float gc[kMaskLossMaxK];
 #pragma unroll
       for (int k = 0; k < kMaskLossMaxK; ++k) gc[k] = 0.0f;
       if (area > 0.0f) {
         const float G = __fdiv_rn(gscale, area);
-        for (int px = tid; px < HW; px += kMaskLossThreads) {
-          const int y = px / a.PW, x = px - y * a.PW;
+        for (int q = tid; q < npx; q += kMaskLossThreads) {
+          const int y = box.y0 + q / box.bw, x = box.x0 + q % box.bw, px = y * a.PW + x;
           const MaskPx g = mask_px(a, b, y, x);
           const float w = mask_weight(g, crop);
           if (w == 0.0f) continue;
@@ -536,11 +569,20 @@ __global__ void __launch_bounds__(kMaskLossThreads) ymask_positive_kernel(const 
   if (!BACKWARD && tid == 0) a.partial[(size_t)b * gridDim.x + blockIdx.x] = cta_sum;
 }
 
+// one record per positive, staged in shared memory for the CTA's 256 pixels
+struct MaskPosRec {
+  float left, right, top, bottom;
+  float G;      // grad_out / (P * area), 0 = skipped
+  int n, j;
+};
+constexpr int kMaskRecChunk = 128;
+
 __global__ void __launch_bounds__(kMaskLossThreads) ymask_backward_proto_kernel(const MaskLossArgs a) {
+  __shared__ MaskPosRec s_rec[kMaskRecChunk];
   const int b = blockIdx.y;
   const int HW = a.PH * a.PW;
   const int px = blockIdx.x * kMaskLossThreads + threadIdx.x;
-  if (px >= HW) return;
+  const bool live = px < HW;
   const int npos = (int)a.n_pos[b];
   const float* proto = a.proto + (size_t)b * a.K * HW;
   const int32_t* seg = a.seg + (size_t)b * a.SH * a.SW;
@@ -549,35 +591,46 @@ __global__ void __launch_bounds__(kMaskLossThreads) ymask_backward_proto_kernel(
   float pv[kMaskLossMaxK], gp[kMaskLossMaxK];
 #pragma unroll
   for (int k = 0; k < kMaskLossMaxK; ++k) {
-    pv[k] = k < a.K ? proto[(size_t)k * HW + px] : 0.0f;
+    pv[k] = (live && k < a.K) ? proto[(size_t)k * HW + px] : 0.0f;
     gp[k] = 0.0f;
   }
-  const int y = px / a.PW, x = px - y * a.PW;
+  const int y = live ? px / a.PW : 0, x = live ? px - y * a.PW : 0;
   const MaskPx g = mask_px(a, b, y, x);
-  for (int i = 0; i < npos; ++i) {
-    const float area = a.tsum[(size_t)b * a.N + i];
-    if (!(area > 0.0f)) continue;
-    const int n = a.pos_list[(size_t)b * a.N + i];
-    long long jl = a.match_index[(size_t)b * a.N + n];
-    const int j = (int)(jl < 0 ? 0 : (jl >= a.M ? a.M - 1 : jl));
-    const float* tb = a.truth_box + ((size_t)b * a.M + j) * 4;
-    const float w = mask_weight(g, crop_bounds(make_float4(tb[0], tb[1], tb[2], tb[3]), a.PH, a.PW));
-    if (w == 0.0f) continue;
-    const float* cf = a.coeff + ((size_t)b * a.N + n) * a.K;   // (the same address in every thread: broadcast loads)
-    float cv[kMaskLossMaxK];
-    float logit = 0.0f;
-#pragma unroll
-    for (int k = 0; k < kMaskLossMaxK; ++k) {
-      cv[k] = k < a.K ? cf[k] : 0.0f;
-      logit += cv[k] * pv[k];
+  for (int i0 = 0; i0 < npos; i0 += kMaskRecChunk) {
+    __syncthreads();
+    for (int r = threadIdx.x; r < kMaskRecChunk && i0 + r < npos; r += kMaskLossThreads) {
+      const int n = a.pos_list[(size_t)b * a.N + i0 + r];
+      long long jl = a.match_index[(size_t)b * a.N + n];
+      const int j = (int)(jl < 0 ? 0 : (jl >= a.M ? a.M - 1 : jl));
+      const float* tb = a.truth_box + ((size_t)b * a.M + j) * 4;
+      const CropBounds c = crop_bounds(make_float4(tb[0], tb[1], tb[2], tb[3]), a.PH, a.PW);
+      const float area = a.tsum[(size_t)b * a.M + j];
+      s_rec[r] = MaskPosRec{c.left, c.right, c.top, c.bottom, area > 0.0f ? __fdiv_rn(gscale, area) : 0.0f, n, j};
     }
-    const float dl = __fdiv_rn(gscale, area) * mask_dlogit(logit, mask_truth(g, seg, j), w);
+    __syncthreads();
+    const int nr = min(kMaskRecChunk, npos - i0);
+    for (int r = 0; r < nr && live; ++r) {
+      const MaskPosRec& rec = s_rec[r];
+      if (!(g.fx >= rec.left && g.fx <= rec.right && g.fy >= rec.top && g.fy <= rec.bottom) || g.valid == 0.0f || rec.G == 0.0f)
+        continue;
+      const float* cf = a.coeff + ((size_t)b * a.N + rec.n) * a.K;   // (the same address in every thread: broadcast loads)
+      float cv[kMaskLossMaxK];
+      float logit = 0.0f;
 #pragma unroll
-    for (int k = 0; k < kMaskLossMaxK; ++k) gp[k] += dl * cv[k];
+      for (int k = 0; k < kMaskLossMaxK; ++k) {
+        cv[k] = k < a.K ? cf[k] : 0.0f;
+        logit += cv[k] * pv[k];
+      }
+      const float dl = rec.G * mask_dlogit(logit, mask_truth(g, seg, rec.j), g.valid);
+#pragma unroll
+      for (int k = 0; k < kMaskLossMaxK; ++k) gp[k] += dl * cv[k];
+    }
   }
+  if (live) {
 #pragma unroll
-  for (int k = 0; k < kMaskLossMaxK; ++k)
-    if (k < a.K) a.grad_proto[((size_t)b * a.K + k) * HW + px] = gp[k];
+    for (int k = 0; k < kMaskLossMaxK; ++k)
+      if (k < a.K) a.grad_proto[((size_t)b * a.K + k) * HW + px] = gp[k];
+  }
 }
 
 constexpr int kMaskLossWalkers = 32;  // CTAs that share a frame's positives
@@ -659,7 +712,7 @@ static int mask_loss_check(const MaskLossArgs& a, int B) {
   TAUV_REQUIRE(B > 0 && a.N > 0 && a.K > 0 && a.M > 0 && a.PH > 0 && a.PW > 0 && a.SH > 0 && a.SW > 0, TAUV_E_SHAPE,
                "bad shape B=%d N=%d K=%d M=%d proto %dx%d seg %dx%d", B, a.N, a.K, a.M, a.PH, a.PW, a.SH, a.SW);
   TAUV_REQUIRE(a.K <= kMaskLossMaxK, TAUV_E_UNSUPPORTED, "K=%d exceeds the built-in limit %d", a.K, kMaskLossMaxK);
-  TAUV_REQUIRE(B <= 65535, TAUV_E_UNSUPPORTED, "B=%d exceeds the built-in limit 65535", B);
+  TAUV_REQUIRE(B <= 65535 && a.M <= 65535, TAUV_E_UNSUPPORTED, "B=%d or M=%d exceeds the built-in limit 65535", B, a.M);
   return 0;
 }
 
@@ -674,6 +727,8 @@ extern "C" int tauv_yolact_mask_loss(const float* coeff, const float* proto, con
                  nullptr, nullptr, nullptr, nullptr};
   if (int rc = mask_loss_check(a, B)) return rc;
   TAUV_REQUIRE(partial, TAUV_E_NULL, "pointers must not be NULL");
+  ymask_area_kernel<<<dim3(M, B), kMaskLossThreads, 0, (cudaStream_t)stream>>>(a);
+  TAUV_LAUNCH_CHECK("ymask_area_kernel");
   ymask_positive_kernel<false><<<dim3(kMaskLossWalkers, B), kMaskLossThreads, 0, (cudaStream_t)stream>>>(a);
   TAUV_LAUNCH_CHECK("ymask_positive_kernel<forward>");
   return 0;

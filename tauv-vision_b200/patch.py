@@ -31,6 +31,7 @@ PATCH_TABLE: Dict[str, Tuple[str, Tuple[str, ...]]] = {
     "tauv_vision.yolact.model.nms": ("tauv_vision_b200.yolact.model.nms", ("nms",)),
     "tauv_vision.yolact.model.masks": ("tauv_vision_b200.yolact.model.masks", ("assemble_mask",)),
     "tauv_vision.yolact.model.anchors": ("tauv_vision_b200.yolact.model.anchors", ("get_anchor",)),
+    "tauv_vision.yolact.model.loss": ("tauv_vision_b200.yolact.model.loss", ("loss",)),   # yolact/scripts/train.py:14,246
 }
 
 

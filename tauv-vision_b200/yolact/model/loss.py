@@ -135,7 +135,7 @@ class _MaskLoss(torch.autograd.Function):
         PH, PW = proto.shape[-2:]
         SH, SW = seg.shape[-2:]
         lib = _lib.load()
-        tsum = torch.empty((B, N), dtype=torch.float32, device=dev)
+        tsum = torch.empty((B, truth_box.shape[1]), dtype=torch.float32, device=dev)
         partial = torch.empty((B, lib.tauv_yolact_mask_loss_partials()), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
             _lib.check(lib.tauv_yolact_mask_loss(

@@ -168,8 +168,9 @@ def test_patched_signatures_match_reference_positional_order():
     """Positional order of every public function = the reference's."""
     import inspect
     from tauv_vision_b200.centernet.model import decode as D, loss as L
-    from tauv_vision_b200.yolact.model import boxes as BX, masks as MK, nms as NM, anchors as AN
+    from tauv_vision_b200.yolact.model import boxes as BX, masks as MK, nms as NM, anchors as AN, loss as YL
     want = {
+        YL.loss: ["prediction", "truth", "config"],
         D.heatmap_nms: ["heatmap", "kernel_size"],
         D.heatmap_detect: ["heatmap", "n_detections"],
         D.decode: ["prediction", "model_config", "n_detections", "score_threshold"],
