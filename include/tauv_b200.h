@@ -427,6 +427,19 @@ int tauv_yolact_mask_loss_backward(const float* coeff, const float* proto, const
                                    const float* grad_out, float* grad_coeff, float* grad_proto,
                                    tauv_stream_t stream);
 
+/* Prediction-head outputs packed into the consumers' layout — yolact/model/prediction_head.py:111-113, :122-124,
+ * :137-140 (permute(0, 2, 3, 1).reshape(B, -1, C), tanh for the mask coefficients) and model.py:55-58 (torch.cat over
+ * the FPN levels): levels[l] [B,CH,H_l,W_l] f32 NCHW (CH = A * C; host array of n_levels <= 8 device pointers),
+ * hw[l] = H_l * W_l (host) -> packed [B, sum_l hw[l] * CH] = [B, N, C] with N = A * sum_l hw[l]; tanh_act != 0 applies
+ * tanh.  One read and one write of every element. */
+int tauv_yolact_pack_heads(const float* const* levels, const int* hw, int n_levels, int B, int CH,
+                           int tanh_act, float* packed, tauv_stream_t stream);
+
+/* Its backward: grad_packed [B,N,C] (and the forward output y_packed when tanh_act) -> grad_levels[l] [B,CH,H_l,W_l]. */
+int tauv_yolact_pack_heads_backward(const float* grad_packed, const float* y_packed, const int* hw,
+                                    int n_levels, int B, int CH, int tanh_act,
+                                    float* const* grad_levels, tauv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -498,3 +498,10 @@ def yolact_mask_loss(mask_coeff, mask_prototype, anchor, truth_valid, truth_box,
             total = total + (w.reshape(-1) * bce).sum() / t.sum()                           # :113
     P = positive.sum()
     return total / P if P > 0 else total                                                    # :117-120
+
+
+def pack_head(levels, channels_per_prior: int, tanh: bool = False):
+    """yolact/model/prediction_head.py:111-113 / :122-124 / :137-140 per level, then model.py:55-58's torch.cat along the
+    prior axis: NCHW head outputs [B, A*C, H_l, W_l] -> [B, sum_l H_l*W_l*A, C]."""
+    out = torch.cat([t.permute(0, 2, 3, 1).reshape(t.size(0), -1, channels_per_prior) for t in levels], dim=1)
+    return torch.tanh(out) if tanh else out

@@ -423,9 +423,46 @@ def yolact_loss_golden():
          ratio=3, v0=0.1, v1=0.2)
 
 
+def yolact_heads_golden():
+    """The reference's own PredictionHead (random weights, no extra layers) on three FPN levels: the NCHW outputs of its
+    three final convolutions (captured by forward hooks) and the tensors it returns, concatenated over the levels the way
+    Yolact.forward does (model.py:43-58), with the reference's autograd gradients back at the convolution outputs."""
+    from tauv_vision.yolact.model.prediction_head import PredictionHead
+    cfg = YolactModelConfig(in_w=550, in_h=550, feature_depth=8, n_classes=6, n_prototype_masks=5,
+                            n_masknet_layers_pre_upsample=0, n_masknet_layers_post_upsample=0,
+                            n_prediction_head_layers=0, n_classification_layers=0, n_box_layers=0, n_mask_layers=0,
+                            n_fpn_downsample_layers=0, anchor_scales=(24, 48, 96), anchor_aspect_ratios=(1 / 2, 1, 2),
+                            box_variances=(0.1, 0.2), iou_pos_threshold=0.4, iou_neg_threshold=0.3,
+                            negative_example_ratio=3, img_mean=(0, 0, 0), img_stddev=(1, 1, 1))
+    torch.manual_seed(7)
+    head = PredictionHead(cfg)
+    captured = {"cls": [], "box": [], "coeff": []}
+    for key, layer in (("cls", head._classification_layer), ("box", head._box_encoding_layer),
+                       ("coeff", head._mask_coeff_layer)):
+        def hook(_m, _i, out, key=key):
+            out.retain_grad()
+            captured[key].append(out)
+        layer.register_forward_hook(hook)
+    g = synth.gen(301)
+    outs = [head(torch.randn((2, 8, h, w), generator=g)) for h, w in ((9, 7), (5, 4), (33, 2))]
+    cls, box, coeff = (torch.cat([o[i] for o in outs], dim=1) for i in range(3))
+    w_cls, w_box, w_coeff = (torch.randn(t.shape, generator=g) for t in (cls, box, coeff))
+    ((cls * w_cls).sum() + (box * w_box).sum() + (coeff * w_coeff).sum()).backward()
+    arrays = dict(cls=cls.detach(), box=box.detach(), coeff=coeff.detach(), w_cls=w_cls, w_box=w_box, w_coeff=w_coeff,
+                  n_classes=6, n_prototype_masks=5, n_levels=3)
+    for key in captured:
+        for l, t_ in enumerate(captured[key]):
+            arrays[f"{key}_level{l}"] = t_.detach()
+            arrays[f"{key}_grad{l}"] = t_.grad
+    save("yl_heads", **arrays)
+
+
 if __name__ == "__main__":
     if sys.argv[1:] == ["yl_loss"]:
         yolact_loss_golden()
+    elif sys.argv[1:] == ["yl_heads"]:
+        yolact_heads_golden()
     else:
         main()
         yolact_loss_golden()
+        yolact_heads_golden()

@@ -257,3 +257,12 @@ def test_yolact_loss_golden():
     g_coeff, g_proto = torch.autograd.grad(ml, (coeff, proto))
     assert_equal(g_cls, g["grad_cls"]), assert_equal(g_enc, g["grad_enc"])
     assert_equal(g_coeff, g["grad_coeff"]), assert_equal(g_proto, g["grad_proto"])
+
+
+def test_pack_heads_golden():
+    """The reference's PredictionHead outputs, concatenated over the levels like Yolact.forward, from the NCHW outputs of
+    its final convolutions (yolact/model/prediction_head.py:111-140, model.py:55-58)."""
+    g = golden("yl_heads")
+    L = int(g["n_levels"])
+    for key, C, th in (("cls", int(g["n_classes"]) + 1, False), ("box", 4, False), ("coeff", int(g["n_prototype_masks"]), True)):
+        assert_equal(O.pack_head([t(g[f"{key}_level{l}"]) for l in range(L)], C, tanh=th), g[key], key)

@@ -595,3 +595,43 @@ def test_mask_loss_vs_oracle(yl, B, N, K, M, PH, PW, SH, SW):
     assert_close(dp.grad, 3 * og_p, rtol=1e-4, atol=1e-6 * float(og_p.abs().max()), what="d/d mask_prototype")
     again = yl.loss.mask_loss(dc, dp, m, pos_list, n_pos, tb.to(d), seg.to(d), img_valid.to(d))
     assert_equal(again, ml, "run-to-run")
+
+
+# ---- head outputs in the consumers' layout ----------------------------------------------------------
+
+def test_pack_heads_golden(yl):
+    """Against the reference's own PredictionHead (forward hooks on its final convolutions, tests/golden/make_golden.py):
+    packed outputs bit-exact for the class logits and box encodings (pure data movement), tanh 1e-6; gradients back at
+    the convolution outputs against the reference's autograd."""
+    from tauv_vision_b200.yolact.model import prediction_head as PH
+    g = golden("yl_heads")
+    d, L = yl.dev, int(g["n_levels"])
+    cfg = SimpleNamespace(n_classes=int(g["n_classes"]), n_prototype_masks=int(g["n_prototype_masks"]))
+    lv = {k: [t(g[f"{k}_level{l}"]).to(d).requires_grad_() for l in range(L)] for k in ("cls", "box", "coeff")}
+    cls, box, coeff = PH.pack_heads(lv["cls"], lv["box"], lv["coeff"], cfg)
+    assert_equal(cls, g["cls"], "classification"), assert_equal(box, g["box"], "box_encoding")
+    assert_close(coeff, g["coeff"], rtol=1e-6, atol=1e-7, what="mask_coeff (tanh)")
+    ((cls * t(g["w_cls"]).to(d)).sum() + (box * t(g["w_box"]).to(d)).sum() + (coeff * t(g["w_coeff"]).to(d)).sum()).backward()
+    for k in ("cls", "box"):
+        for l in range(L):
+            assert_equal(lv[k][l].grad, g[f"{k}_grad{l}"], f"d/d {k} level {l}")
+    for l in range(L):
+        assert_close(lv["coeff"][l].grad, g[f"coeff_grad{l}"], rtol=1e-5, atol=1e-7, what=f"d/d coeff level {l}")
+
+
+def test_pack_heads_full_size_vs_oracle(yl):
+    """The YOLACT shapes: five levels of 550 x 550 (69, 35, 18, 9, 5), three aspect ratios, 81 classes / 32
+    coefficients; the packed rows line up with all_anchors' 19 248 priors."""
+    from tauv_vision_b200.yolact.model import prediction_head as PH
+    d = yl.dev
+    g = synth.gen(77)
+    sizes = synth.fpn_sizes(550, 550)
+    for C, th in ((81, False), (4, False), (32, True)):
+        lv = [torch.randn((2, 3 * C, h, w), generator=g) for h, w in sizes]
+        want = O.pack_head(lv, C, tanh=th)
+        got = PH.pack_head([x.to(d) for x in lv], C, tanh=th)
+        assert got.shape == (2, 19248, C)
+        if th:
+            assert_close(got, want, rtol=1e-6, atol=1e-7, what="tanh")
+        else:
+            assert_equal(got, want, f"C = {C}")
