@@ -182,3 +182,18 @@ def heatmap_focal_loss(heatmap_logits: torch.Tensor, truth, model_config, train_
     geom = (int(model_config.in_h), int(model_config.in_w), int(model_config.downsample_ratio))
     loss, n_pos = _HeatmapFocalLoss.apply(logits, valid, label, center, geom, sigma, alpha, beta)
     return (loss, n_pos) if return_n_pos else loss
+
+
+def keypoint_heatmap_focal_loss(keypoint_heatmap_logits: torch.Tensor, truth, model_config, train_config,
+                                return_n_pos: bool = False):
+    """``focal_loss(F.sigmoid(prediction.keypoint_heatmap), generate_keypoint_heatmap(truth, ...)[0], a, b).sum()`` — the
+    keypoint-heatmap term of the reference's loss before its lambda (loss.py:238-240).  The keypoint heatmap target is
+    rendered exactly like the object heatmap (loss.py:113-116 vs :64-67: same sigma, same floor of the centre, maximum
+    over the instances of a label), so this is the fused pass of ``heatmap_focal_loss`` over the keypoint instances;
+    the channel count comes from the logits' shape."""
+    if float(train_config.keypoint_heatmap_sigma) < 0.1:
+        raise ValueError("keypoint_heatmap_sigma < 0.1: generate_heatmap floors sigma at 0.1 (loss.py:60-62), "
+                         "generate_keypoint_heatmap does not (loss.py:115)")
+    kp = type("KeypointTruth", (), {"valid": truth.keypoint_valid, "label": truth.keypoint_label,
+                                    "center": truth.keypoint_center})
+    return heatmap_focal_loss(keypoint_heatmap_logits, kp, model_config, train_config, return_n_pos=return_n_pos)

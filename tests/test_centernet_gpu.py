@@ -558,6 +558,27 @@ def test_focal_loss_vs_oracle(cn, B, n, C, H, W, ds, a, b):
     assert_close(xd.grad, gref, rtol=2e-5, atol=1e-9, what="gradient")
 
 
+@pytest.mark.parametrize("n_inst", [24, 48])
+def test_keypoint_heatmap_focal_loss_vs_oracle(cn, n_inst):
+    """loss.py:238-240 — the keypoint-heatmap focal term against the oracle's generate_keypoint_heatmap + focal_loss with
+    autograd (24 instances: the fused pass; 48: the composed path)."""
+    B, n_obj, Kp, H, W, ratio = 2, 6, 10, 32, 40, 4
+    tr = synth.pose_truth(B, n_obj, 3, seed=71, n_kp_inst=n_inst, Kp=Kp)
+    logits = synth.natural_logits(B, Kp, H, W, seed=72).clamp(-12, 12)
+    x = logits.clone().requires_grad_(True)
+    target = O.generate_keypoint_heatmap(tr.keypoint_valid, tr.keypoint_label, tr.keypoint_center, tr.keypoint_object_index,
+                                         tr.center, Kp, H, W, H * ratio, W * ratio, ratio, 2.0, 3.0)[0]
+    ref = O.focal_loss(torch.sigmoid(x), target, 2.0, 4.0).sum()
+    gref, = torch.autograd.grad(ref, x)
+    mc = SimpleNamespace(in_h=H * ratio, in_w=W * ratio, downsample_ratio=ratio, out_h=H, out_w=W)
+    tc = SimpleNamespace(keypoint_heatmap_sigma=2.0, heatmap_focal_loss_a=2.0, heatmap_focal_loss_b=4.0)
+    xd = logits.to(cn.dev).requires_grad_(True)
+    loss = cn.L.keypoint_heatmap_focal_loss(xd, synth.truth_to(tr, cn.dev), mc, tc)
+    assert_close(loss.detach(), ref.detach(), rtol=2e-5, what="keypoint heatmap focal loss")
+    loss.backward()
+    assert_close(xd.grad, gref, rtol=2e-5, atol=1e-9, what="gradient")
+
+
 def test_focal_loss_full_batch_matches_composition(cn):
     """BASELINE configs[1] size (64 x 80 x 128 x 128): the fused pass equals the composition of this package's own
     generate_heatmap with the reference's elementwise expressions on the GPU, is deterministic run to run, and writes no
