@@ -569,6 +569,16 @@ def run_centernet(ctx):
             "match_anchors_bytes": 16 * YL_N + 16 * B_PER_GPU * 16 + B_PER_GPU * YL_N * 30,
             "match_anchors_frac": (16 * YL_N + 16 * B_PER_GPU * 16 + B_PER_GPU * YL_N * 30) / (match_us * 1e-6) / 1e9 / hbm_gbs,
         })
+        kernels.update({
+            "yolact_loss_forward_us": yl["loss_forward_us"], "yolact_loss_fwd_bwd_us": yl["loss_fwd_bwd_us"],
+            "yolact_loss_note": f"loss(prediction, truth, config) of yolact/model/loss.py:8-125 through the Python API "
+                                f"(match + class/box terms with hard-negative mining + mask term; 5 launches forward, 9 "
+                                f"with backward) at configs[2]'s shapes, 16 truths per frame, {yl['loss_positives']} "
+                                f"positives in the batch; rank 0's figures",
+            "pack_heads_us": yl["pack_heads_us"],
+            "pack_heads_bytes": 2 * 4 * B_PER_GPU * YL_N * (YL_C1 + 4 + YL_P),
+            "pack_heads_frac": 2 * 4 * B_PER_GPU * YL_N * (YL_C1 + 4 + YL_P) / (yl["pack_heads_us"] * 1e-6) / 1e9 / hbm_gbs,
+        })
         launches += yl["launches"]
     cpu = None
     if not args.no_cpu_baseline and world == 1:  # (the CPU leg is reported at N = 1 only)
@@ -646,9 +656,43 @@ def time_yolact(device, seed, B=B_PER_GPU):
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
-    return {"scores_us": sc_us, "detect_us": det_us, "mask_us": mask_us, "mask_depth_us": md_us, "n_keep_total": nk,
+    # the training-side loss (yolact/model/loss.py:8-125) at the same shapes: 16 truths per frame, half of them on
+    # (jittered) priors so that positives exist, 550 x 550 segmentation maps; and the heads' level outputs -> [B,N,C]
+    from tauv_vision_b200.yolact.model import prediction_head as yl_heads
+    g = torch.Generator(device=device)
+    g.manual_seed(seed + 1)
+    pick = torch.randint(0, YL_N, (B, 8), device=device, generator=g)
+    tb[:, :8] = y.anchor[0][pick] * (1 + 0.05 * torch.randn((B, 8, 4), device=device, generator=g).clamp(-1, 1))
+    tvd[:, :8] = True
+    tcls = torch.randint(1, YL_C1, (B, 16), device=device, generator=g)
+    seg = torch.randint(0, 16, (B, 55, 55), device=device, generator=g, dtype=torch.int32)
+    seg = seg.repeat_interleave(10, 1).repeat_interleave(10, 2).contiguous()
+    img_valid = torch.ones((B, 550, 550), dtype=torch.bool, device=device)
+    y.cfg.negative_example_ratio = 3
+    grads = [t.detach().clone().requires_grad_() for t in (y.cls, y.enc, y.coeff, y.proto)]
+    pred = (grads[0], grads[1], grads[2], y.anchor, grads[3])
+    truth = (tvd, tcls, tb, seg, img_valid)
+    with torch.no_grad():
+        lf_us, _ = time_kernel(lambda: yl_loss.loss(pred, truth, y.cfg), reps=5, warmup=2, inner=2)
+
+    def loss_fb():
+        for t in grads:
+            t.grad = None
+        yl_loss.loss(pred, truth, y.cfg)[0].backward()
+    lfb_us, _ = time_kernel(loss_fb, reps=5, warmup=2, inner=2)
+    n_positive = int(yl_loss.match_anchors(y.anchor, tb, tvd, y.cfg).positive_match.sum().item())
+    del grads, pred
+    sizes = synth.fpn_sizes(550, 550)
+    lv = {c: [torch.randn((B, 3 * c, h, w), device=device, generator=g) for h, w in sizes] for c in (YL_C1, 4, YL_P)}
+    hcfg = SimpleNamespace(n_classes=YL_C1 - 1, n_prototype_masks=YL_P)
+    with torch.no_grad():
+        ph_us, _ = time_kernel(lambda: yl_heads.pack_heads(lv[YL_C1], lv[4], lv[YL_P], hcfg), reps=5, warmup=2, inner=2)
+    del lv
+    return {"loss_forward_us": lf_us, "loss_fwd_bwd_us": lfb_us, "loss_positives": n_positive, "pack_heads_us": ph_us,
+            "scores_us": sc_us, "detect_us": det_us, "mask_us": mask_us, "mask_depth_us": md_us, "n_keep_total": nk,
             "match_us": median(ts[2:]), "mask_binary_nearest_us": mb_us["nearest"],
-            "mask_binary_bilinear_us": mb_us["bilinear"], "launches": 31 * 1 + 31 * 2 + 22 * 1 + 22 * 3 + 7 + 2 * 22 * 2}
+            "mask_binary_bilinear_us": mb_us["bilinear"],
+            "launches": 31 * 1 + 31 * 2 + 22 * 1 + 22 * 3 + 7 + 2 * 22 * 2 + 12 * 5 + 12 * 9 + 1 + 12 * 3}
 
 
 def e2e_centernet(ctx, logits, size, offset, truth, mc, tc, oc):

@@ -684,8 +684,6 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
       sh->n_zero = 0;
       sh->flag = 0;
     }
-    // (the rank loop reads the candidates in pairs: an odd list ends in an empty slot)
-    for (int i = tid; i < SH::kCandCap; i += kSelThreads) sh->cand[i] = 0ull;
     __syncthreads();
     SEL_STAMP(2);
     // ---- 2. hot groups -> hot blocks (ids in sh->cell), then their positions ----
@@ -787,22 +785,30 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
           // maps of a trained head, whose hot regions span whole blocks, it cuts the queue from ~7 cells per hot
           // block to about one.  ("clearly": by the margin below which sel_is_peak still checks for a sigmoid tie.)
           const bool live = org[u] != 0xffffffffu;
-          const float w0 = live ? vv[0] : TAUV_NEG_INF, w1 = live ? vv[1] : TAUV_NEG_INF;
-          const float w2 = live ? vv[2] : TAUV_NEG_INF, w3 = live ? vv[3] : TAUV_NEG_INF;
-          // maxima over the columns c-1..c+1 of this row, then over the rows above and below (eight lanes = the eight
-          // rows of a block; a shuffle of width 8 hands the first / last row its own value back, which is neutral)
-          const float h0 = fmaxf(w0, w1), h3 = fmaxf(w2, w3), h1 = fmaxf(h0, w2), h2 = fmaxf(w1, h3);
-          const float nm[4] = {
-              fmaxf(h0, fmaxf(__shfl_up_sync(0xffffffffu, h0, 1, 8), __shfl_down_sync(0xffffffffu, h0, 1, 8))),
-              fmaxf(h1, fmaxf(__shfl_up_sync(0xffffffffu, h1, 1, 8), __shfl_down_sync(0xffffffffu, h1, 1, 8))),
-              fmaxf(h2, fmaxf(__shfl_up_sync(0xffffffffu, h2, 1, 8), __shfl_down_sync(0xffffffffu, h2, 1, 8))),
-              fmaxf(h3, fmaxf(__shfl_up_sync(0xffffffffu, h3, 1, 8), __shfl_down_sync(0xffffffffu, h3, 1, 8)))};
           unsigned hm = 0u;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            // (nm >= the cell itself >= T: with T >= -80 the third condition of sel_is_peak's margin holds by itself)
-            const bool below = (nm[c] - vv[c]) >= 1e-3f && vv[c] <= 4.0f && (T_ge80 || nm[c] >= -80.0f);  // (false for NaN)
-            if (live && !(vv[c] < T_f) && !below) hm |= 1u << c;  // (NaN cells pass here and fail the peak test)
+          for (int c = 0; c < 4; ++c)
+            if (live && !(vv[c] < T_f)) hm |= 1u << c;  // (NaN cells pass here and fail the peak test)
+          // A block with ONE cell >= T (its maximum) needs no filter: on noise that is 93 % of the blocks, and three
+          // warps in four skip the shuffles below (a warp covers four blocks).
+          const int n_blocks_here = __popc(__ballot_sync(0xffffffffu, (lane & 7) == 0 && e0 + u * kSelThreads + tid < ne));
+          if (__reduce_add_sync(0xffffffffu, (unsigned)__popc(hm)) > (unsigned)n_blocks_here) {
+            const float w0 = live ? vv[0] : TAUV_NEG_INF, w1 = live ? vv[1] : TAUV_NEG_INF;
+            const float w2 = live ? vv[2] : TAUV_NEG_INF, w3 = live ? vv[3] : TAUV_NEG_INF;
+            // maxima over the columns c-1..c+1 of this row, then over the rows above and below (eight lanes = the eight
+            // rows of a block; a shuffle of width 8 hands the first / last row its own value back, which is neutral)
+            const float h0 = fmaxf(w0, w1), h3 = fmaxf(w2, w3), h1 = fmaxf(h0, w2), h2 = fmaxf(w1, h3);
+            const float nm[4] = {
+                fmaxf(h0, fmaxf(__shfl_up_sync(0xffffffffu, h0, 1, 8), __shfl_down_sync(0xffffffffu, h0, 1, 8))),
+                fmaxf(h1, fmaxf(__shfl_up_sync(0xffffffffu, h1, 1, 8), __shfl_down_sync(0xffffffffu, h1, 1, 8))),
+                fmaxf(h2, fmaxf(__shfl_up_sync(0xffffffffu, h2, 1, 8), __shfl_down_sync(0xffffffffu, h2, 1, 8))),
+                fmaxf(h3, fmaxf(__shfl_up_sync(0xffffffffu, h3, 1, 8), __shfl_down_sync(0xffffffffu, h3, 1, 8)))};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              // (nm >= the cell itself >= T: with T >= -80 the third condition of sel_is_peak's margin holds by itself)
+              const bool below = (nm[c] - vv[c]) >= 1e-3f && vv[c] <= 4.0f && (T_ge80 || nm[c] >= -80.0f);  // (false for NaN)
+              if (below) hm &= ~(1u << c);
+            }
           }
           const unsigned bal = __ballot_sync(0xffffffffu, hm != 0u);
           const unsigned seg = (bal >> (lane & 24)) & 0xffu;
@@ -851,6 +857,10 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
             if (rr >= 0 && rr < a.H && cc >= 0 && cc < a.W) v[u] = fhm[(long long)sh->cell[e >> 3] + dy * a.W + dx];
           }
         }
+        // (while the loads are in flight: the rank loop of step 4 reads the candidates in pairs, so an odd list must end
+        // in an empty slot — clear the list the peaks of 3c will be appended to)
+        if (e0 == 0)
+          for (int i = tid; i < SH::kCandCap; i += kSelThreads) sh->cand[i] = 0ull;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           float m = v[u];
