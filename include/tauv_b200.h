@@ -371,6 +371,28 @@ int tauv_yolact_match_anchors(const float* anchor, const float* truth_box,
                               float* match_iou, uint8_t* positive, uint8_t* negative,
                               float* target, tauv_stream_t stream);
 
+/* Keypoint-affinity term of the CenterNet loss fused with its target render — centernet/model/loss.py:244-246 before the
+ * lambda: (affinity_weight.unsqueeze(2) * F.mse_loss(prediction.keypoint_affinity, keypoint_affinity,
+ * reduction="none")).sum() with the weight and the unit-vector field of generate_keypoint_heatmap (loss.py:105-129)
+ * computed on the fly, never written.  pred_affinity [B,Kp,2,H,W] f32 (W % 4 == 0, 16-byte aligned), keypoint truth as in
+ * tauv_keypoint_encode (1 <= m <= 128) -> partial [tauv_keypoint_affinity_loss_partials(B, Kp, H, W)] f64 whose sum is the
+ * term; planes without instances are not read.  Backward: grad_affinity [B,Kp,2,H,W] = 2 * grad_out[0] * weight *
+ * (pred - target). */
+size_t tauv_keypoint_affinity_loss_partials(int B, int Kp, int H, int W);
+int tauv_keypoint_affinity_loss(const float* pred_affinity, const uint8_t* kp_valid,
+                                const int64_t* kp_label, const float* kp_center,
+                                const int64_t* kp_object_index, const float* center, int B, int m,
+                                int n_objects, int Kp, int H, int W, int in_h, int in_w,
+                                int downsample_ratio, double sigma_affinity, double* partial,
+                                tauv_stream_t stream);
+int tauv_keypoint_affinity_loss_backward(const float* pred_affinity, const uint8_t* kp_valid,
+                                         const int64_t* kp_label, const float* kp_center,
+                                         const int64_t* kp_object_index, const float* center, int B,
+                                         int m, int n_objects, int Kp, int H, int W, int in_h, int in_w,
+                                         int downsample_ratio, double sigma_affinity,
+                                         const float* grad_out, float* grad_affinity,
+                                         tauv_stream_t stream);
+
 /* Classification (hard-negative mining) and box terms of the YOLACT loss, forward — yolact/model/loss.py:26-56
  * (per-frame target classes, F.cross_entropy(reduction="none"), torch.topk of -softmax[:, 0] over the negative priors
  * with k = ratio * n_positive, sum over positives + mined negatives) and :58-68 (smooth-L1 over the positives).

@@ -232,6 +232,16 @@ def generate_keypoint_heatmap(kp_valid, kp_label, kp_center, kp_object_index, ce
     return torch.nan_to_num(hm), torch.nan_to_num(wt), torch.nan_to_num(aff)
 
 
+def keypoint_affinity_loss(pred_affinity, kp_valid, kp_label, kp_center, kp_object_index, center, out_h: int, out_w: int,
+                           in_h: int, in_w: int, downsample_ratio: int, sigma_heatmap: float, sigma_affinity: float):
+    """loss.py:244-246 before the lambda — weighted squared error between the predicted keypoint-affinity field
+    [B,Kp,2,H,W] and generate_keypoint_heatmap's unit-vector field, weighted by its affinity weight."""
+    _, weight, target = generate_keypoint_heatmap(kp_valid, kp_label, kp_center, kp_object_index, center,
+                                                  pred_affinity.shape[1], out_h, out_w, in_h, in_w, downsample_ratio,
+                                                  sigma_heatmap, sigma_affinity)
+    return (weight.unsqueeze(2) * F.mse_loss(pred_affinity, target, reduction="none")).sum()
+
+
 def out_index_for_position(position, in_h: int, in_w: int, downsample_ratio: int, out_h: int, out_w: int):
     """loss.py:138-142."""
     return torch.stack((

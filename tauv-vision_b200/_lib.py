@@ -96,6 +96,11 @@ _SIGNATURES = {
                                            _D, _I64, c_void_p, c_size_t, c_void_p]),
     "tauv_yolact_class_box_loss_backward": (c_int, [_F, _F, _F, _U8, _U8, _I64, _I64, c_int, c_int, c_int, c_int, c_int,
                                                     _I64, _F, _F, _F, _F, c_void_p]),
+    "tauv_keypoint_affinity_loss_partials": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "tauv_keypoint_affinity_loss": (c_int, [_F, _U8, _I64, _F, _I64, _F, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                            c_int, c_int, c_double, _D, c_void_p]),
+    "tauv_keypoint_affinity_loss_backward": (c_int, [_F, _U8, _I64, _F, _I64, _F, c_int, c_int, c_int, c_int, c_int, c_int,
+                                                     c_int, c_int, c_int, c_double, _F, _F, c_void_p]),
     "tauv_yolact_pack_heads": (c_int, [POINTER(c_void_p), _I32, c_int, c_int, c_int, c_int, _F, c_void_p]),
     "tauv_yolact_pack_heads_backward": (c_int, [_F, _F, _I32, c_int, c_int, c_int, c_int, POINTER(c_void_p), c_void_p]),
     "tauv_yolact_mask_loss_partials": (c_int, []),

@@ -197,3 +197,60 @@ def keypoint_heatmap_focal_loss(keypoint_heatmap_logits: torch.Tensor, truth, mo
     kp = type("KeypointTruth", (), {"valid": truth.keypoint_valid, "label": truth.keypoint_label,
                                     "center": truth.keypoint_center})
     return heatmap_focal_loss(keypoint_heatmap_logits, kp, model_config, train_config, return_n_pos=return_n_pos)
+
+
+class _KeypointAffinityLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, kv, kl, kc, ko, center, geom, sigma_a):
+        dev = pred.device
+        B, Kp, _, H, W = pred.shape
+        lib = _lib.load()
+        partial = torch.empty((lib.tauv_keypoint_affinity_loss_partials(B, Kp, H, W),), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.tauv_keypoint_affinity_loss(
+                _lib.fptr(pred), _lib.u8ptr(kv), _lib.i64ptr(kl), _lib.fptr(kc), _lib.i64ptr(ko), _lib.fptr(center), B,
+                kv.shape[1], center.shape[1], Kp, H, W, *geom, float(sigma_a), _lib.dptr(partial), _lib.stream_ptr(dev)))
+        ctx.save_for_backward(pred, kv, kl, kc, ko, center)
+        ctx.meta = (geom, float(sigma_a))
+        return partial.sum().to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, kv, kl, kc, ko, center = ctx.saved_tensors
+        geom, sigma_a = ctx.meta
+        dev = pred.device
+        B, Kp, _, H, W = pred.shape
+        grad = torch.empty_like(pred)
+        go = g.to(torch.float32).contiguous().reshape(1)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().tauv_keypoint_affinity_loss_backward(
+                _lib.fptr(pred), _lib.u8ptr(kv), _lib.i64ptr(kl), _lib.fptr(kc), _lib.i64ptr(ko), _lib.fptr(center), B,
+                kv.shape[1], center.shape[1], Kp, H, W, *geom, sigma_a, _lib.fptr(go), _lib.fptr(grad),
+                _lib.stream_ptr(dev)))
+        return grad, None, None, None, None, None, None, None
+
+
+def keypoint_affinity_loss(keypoint_affinity: torch.Tensor, truth, model_config, train_config) -> torch.Tensor:
+    """``(keypoint_affinity_weight.unsqueeze(2) * F.mse_loss(prediction.keypoint_affinity, keypoint_affinity,
+    reduction="none")).sum()`` — the keypoint-affinity term of the reference's loss before its lambda (loss.py:244-246)
+    — with the weight and the target field of ``generate_keypoint_heatmap`` computed on the fly (1.3 GB of targets at
+    Kp = 80 are never written; planes without instances are not even read), with autograd.
+    ``keypoint_affinity`` is ``prediction.keypoint_affinity`` [B,Kp,2,H,W]."""
+    dev = _lib.require_cuda(keypoint_affinity, truth.keypoint_valid, truth.keypoint_label, truth.keypoint_center,
+                            truth.keypoint_object_index, truth.center)
+    if keypoint_affinity.dim() != 5 or keypoint_affinity.shape[2] != 2:
+        raise ValueError(f"keypoint_affinity must be [B,Kp,2,H,W]; got {tuple(keypoint_affinity.shape)}")
+    B, Kp, _, H, W = keypoint_affinity.shape
+    if (H, W) != (int(model_config.out_h), int(model_config.out_w)):
+        raise ValueError(f"affinity field is {H}x{W}, the model's output grid is {model_config.out_h}x{model_config.out_w}")
+    pred = _lib.f32c(keypoint_affinity)
+    kv, kl = _u8(truth.keypoint_valid), _i64(truth.keypoint_label)
+    kc, ko, center = _lib.f32c(truth.keypoint_center), _i64(truth.keypoint_object_index), _lib.f32c(truth.center)
+    m = kv.shape[1]
+    if not (W % 4 == 0 and pred.data_ptr() % 16 == 0 and 1 <= m <= 128 and center.shape[1] > 0):
+        # shapes the fused kernel does not take: the same arithmetic from the rendered targets, still on the GPU
+        _, weight, target = generate_keypoint_heatmap(truth, model_config, train_config, type("O", (), {"n_keypoints": Kp}))
+        return (weight.unsqueeze(2) * (pred - target) ** 2).sum()
+    del dev
+    geom = (int(model_config.in_h), int(model_config.in_w), int(model_config.downsample_ratio))
+    return _KeypointAffinityLoss.apply(pred, kv, kl, kc, ko, center, geom, float(train_config.keypoint_affinity_sigma))

@@ -364,12 +364,18 @@ __global__ void __launch_bounds__(kEncThreads) keypoint_encode_kernel(
 // gaussian_encode_warp_kernel.  Lane l holds instances l, l+32, ... (chunk-major ballots walked in ascending bit order
 // ARE the instance order that decides affinity ties, loss.py:122); a plane without instances is four runs of coalesced zero stores (heatmap, weight,
 // affinity y and x), the others broadcast the matching instances with shuffles.  No shared memory, no block barrier.
-template <int NCH>
+// MODE 0 renders the targets.  MODE 1 / 2 are the keypoint-affinity term of the loss fused with that render
+// (loss.py:244-246: (affinity_weight.unsqueeze(2) * F.mse_loss(prediction.keypoint_affinity, keypoint_affinity,
+// reduction="none")).sum(), before its lambda): MODE 1 reads the predicted field `pred` [B,Kp,2,H,W] and leaves one fp64
+// partial sum per warp chunk in `partial` (planes without instances have weight 0 and are not read at all); MODE 2
+// writes the gradient 2 g w (pred - target) into `affinity` (g = *grad_out).  No target is written in either.
+template <int NCH, int MODE>
 __global__ void __launch_bounds__(kEncThreads) keypoint_encode_warp_kernel(
     const uint8_t* __restrict__ kp_valid, const int64_t* __restrict__ kp_label, const float* __restrict__ kp_center,
     const int64_t* __restrict__ kp_obj, const float* __restrict__ center, int m, int n_objects, int Kp, int H, int W,
     float in_h, float in_w, float ratio, float two_sh2, float two_sa2, int chunks_per_plane, long long n_chunks,
-    float* __restrict__ heatmap, float* __restrict__ weight, float* __restrict__ affinity) {
+    float* __restrict__ heatmap, float* __restrict__ weight, float* __restrict__ affinity,
+    const float* __restrict__ pred, double* __restrict__ partial, const float* __restrict__ grad_out) {
   const int lane = threadIdx.x & 31;
   const long long chunk_id = (long long)blockIdx.x * (kEncThreads / 32) + (threadIdx.x >> 5);
   if (chunk_id >= n_chunks) return;
@@ -417,14 +423,25 @@ __global__ void __launch_bounds__(kEncThreads) keypoint_encode_warp_kernel(
   float4* w4 = reinterpret_cast<float4*>(weight + (size_t)plane * hw);
   float4* y4 = reinterpret_cast<float4*>(affinity + (size_t)plane * 2 * hw);
   float4* x4 = reinterpret_cast<float4*>(affinity + (size_t)plane * 2 * hw + hw);
+  const float4* py4 = reinterpret_cast<const float4*>(pred + (MODE ? (size_t)plane * 2 * hw : 0));
+  const float4* px4 = reinterpret_cast<const float4*>(pred + (MODE ? (size_t)plane * 2 * hw + hw : 0));
   if (any_mask == 0u) {
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE == 1) {
+      if (lane == 0) partial[chunk_id] = 0.0;
+      return;
+    }
 #pragma unroll 4
-    for (int t = s0 + lane; t < s1; t += 32) { h4[t] = z; w4[t] = z; y4[t] = z; x4[t] = z; }
+    for (int t = s0 + lane; t < s1; t += 32) {
+      if (MODE == 0) { h4[t] = z; w4[t] = z; }
+      y4[t] = z; x4[t] = z;
+    }
     return;
   }
   const bool big = __any_sync(0xffffffffu, far) || H > 10000 || W > 10000;
   const float fh = (float)H, fw = (float)W;
+  double acc = 0.0;
+  const float g2 = MODE == 2 ? __fmul_rn(2.0f, *grad_out) : 0.0f;
   for (int t0 = s0; t0 < s1; t0 += 32) {  // (warp-uniform trip count: the shuffles below need every lane)
     const int t = t0 + lane;
     const int y = t / S;
@@ -464,13 +481,35 @@ __global__ void __launch_bounds__(kEncThreads) keypoint_encode_warp_kernel(
       }
     }
     if (t < s1) {
-      h4[t] = make_float4(gauss_from_d2(best[0], two_sh2), gauss_from_d2(best[1], two_sh2), gauss_from_d2(best[2], two_sh2),
-                          gauss_from_d2(best[3], two_sh2));
-      w4[t] = make_float4(gauss_from_d2(best[0], two_sa2), gauss_from_d2(best[1], two_sa2), gauss_from_d2(best[2], two_sa2),
-                          gauss_from_d2(best[3], two_sa2));
-      y4[t] = make_float4(nan_to_num(a0[0], 0.f), nan_to_num(a0[1], 0.f), nan_to_num(a0[2], 0.f), nan_to_num(a0[3], 0.f));
-      x4[t] = make_float4(nan_to_num(a1[0], 0.f), nan_to_num(a1[1], 0.f), nan_to_num(a1[2], 0.f), nan_to_num(a1[3], 0.f));
+      const float4 wv = make_float4(gauss_from_d2(best[0], two_sa2), gauss_from_d2(best[1], two_sa2),
+                                    gauss_from_d2(best[2], two_sa2), gauss_from_d2(best[3], two_sa2));
+      const float4 ty = make_float4(nan_to_num(a0[0], 0.f), nan_to_num(a0[1], 0.f), nan_to_num(a0[2], 0.f), nan_to_num(a0[3], 0.f));
+      const float4 tx = make_float4(nan_to_num(a1[0], 0.f), nan_to_num(a1[1], 0.f), nan_to_num(a1[2], 0.f), nan_to_num(a1[3], 0.f));
+      if (MODE == 0) {
+        h4[t] = make_float4(gauss_from_d2(best[0], two_sh2), gauss_from_d2(best[1], two_sh2), gauss_from_d2(best[2], two_sh2),
+                            gauss_from_d2(best[3], two_sh2));
+        w4[t] = wv;
+        y4[t] = ty;
+        x4[t] = tx;
+      } else {
+        const float4 qy = py4[t], qx = px4[t];
+        const float dy[4] = {qy.x - ty.x, qy.y - ty.y, qy.z - ty.z, qy.w - ty.w};
+        const float dx[4] = {qx.x - tx.x, qx.y - tx.y, qx.z - tx.z, qx.w - tx.w};
+        const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+        if (MODE == 1) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc += (double)(ww[i] * (dy[i] * dy[i])) + (double)(ww[i] * (dx[i] * dx[i]));
+        } else {
+          y4[t] = make_float4(g2 * ww[0] * dy[0], g2 * ww[1] * dy[1], g2 * ww[2] * dy[2], g2 * ww[3] * dy[3]);
+          x4[t] = make_float4(g2 * ww[0] * dx[0], g2 * ww[1] * dx[1], g2 * ww[2] * dx[2], g2 * ww[3] * dx[3]);
+        }
+      }
     }
+  }
+  if (MODE == 1) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) partial[chunk_id] = acc;
   }
 }
 
@@ -934,9 +973,9 @@ extern "C" int tauv_keypoint_encode(const uint8_t* kp_valid, const int64_t* kp_l
     const long long wgrid = (n_chunks + kEncThreads / 32 - 1) / (kEncThreads / 32);
     TAUV_REQUIRE(wgrid < (1LL << 31) && cpp < (1LL << 31), TAUV_E_UNSUPPORTED, "grid too large");
 #define TAUV_KP_WARP(NCH)                                                                                             \
-    keypoint_encode_warp_kernel<NCH><<<(unsigned)wgrid, kEncThreads, 0, (cudaStream_t)stream>>>(                       \
+    keypoint_encode_warp_kernel<NCH, 0><<<(unsigned)wgrid, kEncThreads, 0, (cudaStream_t)stream>>>(                    \
         kp_valid, kp_label, kp_center, kp_object_index, center, m, n_objects, Kp, H, W, (float)in_h, (float)in_w,      \
-        (float)downsample_ratio, tsh, tsa, (int)cpp, n_chunks, heatmap, weight, affinity)
+        (float)downsample_ratio, tsh, tsa, (int)cpp, n_chunks, heatmap, weight, affinity, nullptr, nullptr, nullptr)
     if (m <= 32) TAUV_KP_WARP(1);
     else if (m <= 64) TAUV_KP_WARP(2);
     else TAUV_KP_WARP(4);
@@ -952,6 +991,72 @@ extern "C" int tauv_keypoint_encode(const uint8_t* kp_valid, const int64_t* kp_l
   TAUV_LAUNCH_CHECK("keypoint_encode_kernel");
   return 0;
 }
+
+// Keypoint-affinity term fused with its target render (loss.py:244-246, before the lambda).
+static int kp_affinity_plan(int B, int m, int n_objects, int Kp, int H, int W, int in_h, int in_w, int ratio,
+                            const void* a, const void* b, long long* cpp, long long* n_chunks, long long* wgrid) {
+  TAUV_REQUIRE(B > 0 && Kp > 0 && H > 0 && W > 0 && m > 0 && n_objects > 0, TAUV_E_SHAPE, "bad shape");
+  TAUV_REQUIRE(in_h > 0 && in_w > 0 && ratio > 0, TAUV_E_SHAPE, "bad model geometry");
+  TAUV_REQUIRE(W % 4 == 0 && m <= 128 && (uintptr_t)a % 16 == 0 && (uintptr_t)b % 16 == 0, TAUV_E_UNSUPPORTED,
+               "the fused affinity loss needs W %% 4 == 0, 16-byte aligned tensors and <= 128 keypoint instances per frame");
+  const long long planes = (long long)B * Kp, plane_strips = (long long)H * (W / 4);
+  *cpp = (plane_strips + kKpWarpStrips - 1) / kKpWarpStrips;
+  *n_chunks = planes * *cpp;
+  *wgrid = (*n_chunks + kEncThreads / 32 - 1) / (kEncThreads / 32);
+  TAUV_REQUIRE(*wgrid < (1LL << 31) && *cpp < (1LL << 31), TAUV_E_UNSUPPORTED, "grid too large");
+  return 0;
+}
+
+extern "C" size_t tauv_keypoint_affinity_loss_partials(int B, int Kp, int H, int W) {
+  if (B <= 0 || Kp <= 0 || H <= 0 || W <= 0 || W % 4) return 0;
+  const long long plane_strips = (long long)H * (W / 4);
+  return (size_t)((long long)B * Kp * ((plane_strips + kKpWarpStrips - 1) / kKpWarpStrips));
+}
+
+#define TAUV_KP_LOSS(NCH, MODE, OUT, PRED, PART, GRAD)                                                                \
+  keypoint_encode_warp_kernel<NCH, MODE><<<(unsigned)wgrid, kEncThreads, 0, (cudaStream_t)stream>>>(                   \
+      kp_valid, kp_label, kp_center, kp_object_index, center, m, n_objects, Kp, H, W, (float)in_h, (float)in_w,        \
+      (float)downsample_ratio, 1.0f, tsa, (int)cpp, n_chunks, nullptr, nullptr, OUT, PRED, PART, GRAD)
+
+extern "C" int tauv_keypoint_affinity_loss(const float* pred_affinity, const uint8_t* kp_valid, const int64_t* kp_label,
+                                           const float* kp_center, const int64_t* kp_object_index, const float* center,
+                                           int B, int m, int n_objects, int Kp, int H, int W, int in_h, int in_w,
+                                           int downsample_ratio, double sigma_affinity, double* partial,
+                                           tauv_stream_t stream) {
+  TAUV_REQUIRE(pred_affinity && kp_valid && kp_label && kp_center && kp_object_index && center && partial, TAUV_E_NULL,
+               "pointers must not be NULL");
+  long long cpp, n_chunks, wgrid;
+  if (int rc = kp_affinity_plan(B, m, n_objects, Kp, H, W, in_h, in_w, downsample_ratio, pred_affinity, pred_affinity, &cpp,
+                                &n_chunks, &wgrid))
+    return rc;
+  const float tsa = (float)(2.0 * (sigma_affinity * sigma_affinity));
+  if (m <= 32) TAUV_KP_LOSS(1, 1, nullptr, pred_affinity, partial, nullptr);
+  else if (m <= 64) TAUV_KP_LOSS(2, 1, nullptr, pred_affinity, partial, nullptr);
+  else TAUV_KP_LOSS(4, 1, nullptr, pred_affinity, partial, nullptr);
+  TAUV_LAUNCH_CHECK("keypoint_encode_warp_kernel<loss>");
+  return 0;
+}
+
+extern "C" int tauv_keypoint_affinity_loss_backward(const float* pred_affinity, const uint8_t* kp_valid,
+                                                    const int64_t* kp_label, const float* kp_center,
+                                                    const int64_t* kp_object_index, const float* center, int B, int m,
+                                                    int n_objects, int Kp, int H, int W, int in_h, int in_w,
+                                                    int downsample_ratio, double sigma_affinity, const float* grad_out,
+                                                    float* grad_affinity, tauv_stream_t stream) {
+  TAUV_REQUIRE(pred_affinity && kp_valid && kp_label && kp_center && kp_object_index && center && grad_out && grad_affinity,
+               TAUV_E_NULL, "pointers must not be NULL");
+  long long cpp, n_chunks, wgrid;
+  if (int rc = kp_affinity_plan(B, m, n_objects, Kp, H, W, in_h, in_w, downsample_ratio, pred_affinity, grad_affinity, &cpp,
+                                &n_chunks, &wgrid))
+    return rc;
+  const float tsa = (float)(2.0 * (sigma_affinity * sigma_affinity));
+  if (m <= 32) TAUV_KP_LOSS(1, 2, grad_affinity, pred_affinity, nullptr, grad_out);
+  else if (m <= 64) TAUV_KP_LOSS(2, 2, grad_affinity, pred_affinity, nullptr, grad_out);
+  else TAUV_KP_LOSS(4, 2, grad_affinity, pred_affinity, nullptr, grad_out);
+  TAUV_LAUNCH_CHECK("keypoint_encode_warp_kernel<loss backward>");
+  return 0;
+}
+#undef TAUV_KP_LOSS
 
 extern "C" int tauv_out_index_offset(const float* position, int64_t n, int in_h, int in_w, int downsample_ratio,
                                      int out_h, int out_w, int64_t* index, float* offset, tauv_stream_t stream) {

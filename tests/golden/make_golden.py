@@ -457,8 +457,31 @@ def yolact_heads_golden():
     save("yl_heads", **arrays)
 
 
+def centernet_affinity_golden():
+    """The keypoint-affinity term of the reference's loss (centernet/model/loss.py:244-246, before its lambda) on the
+    targets of the reference's own generate_keypoint_heatmap, with its autograd gradient."""
+    import torch.nn.functional as F
+    mce = cn_model_config(96, 2)  # 24x24 map
+    tc = train_config(2.0, 3.0)
+    oce = object_configs(4, kp_per_object=2)  # 4 labels, 8 keypoint channels
+    t = synth.pose_truth(2, 7, 4, seed=161, n_kp_inst=11, Kp=8)
+    truth = PoseSample(img=None, valid=t.valid, label=t.label, center=t.center, size=t.size, roll=None, pitch=None,
+                       yaw=None, depth=None, keypoint_valid=t.keypoint_valid, keypoint_label=t.keypoint_label,
+                       keypoint_center=t.keypoint_center, keypoint_object_index=t.keypoint_object_index)
+    _, keypoint_affinity_weight, keypoint_affinity = ref_loss.generate_keypoint_heatmap(truth, mce, tc, oce)
+    pred = (torch.randn((2, 8, 2, 24, 24), generator=synth.gen(162)) * 0.7).requires_grad_()
+    l = F.mse_loss(pred, keypoint_affinity, reduction="none")                       # loss.py:245
+    l = (keypoint_affinity_weight.unsqueeze(2) * l).sum()                           # loss.py:246 without the lambda
+    grad, = torch.autograd.grad(l, pred)
+    save("cn_kp_affinity_loss", center=t.center, kp_valid=t.keypoint_valid, kp_label=t.keypoint_label,
+         kp_center=t.keypoint_center, kp_obj=t.keypoint_object_index, pred=pred.detach(), loss=l.detach(), grad=grad,
+         in_h=96, downsamples=2, sigma_h=2.0, sigma_a=3.0)
+
+
 if __name__ == "__main__":
-    if sys.argv[1:] == ["yl_loss"]:
+    if sys.argv[1:] == ["cn_kp_affinity_loss"]:
+        centernet_affinity_golden()
+    elif sys.argv[1:] == ["yl_loss"]:
         yolact_loss_golden()
     elif sys.argv[1:] == ["yl_heads"]:
         yolact_heads_golden()
@@ -466,3 +489,4 @@ if __name__ == "__main__":
         main()
         yolact_loss_golden()
         yolact_heads_golden()
+        centernet_affinity_golden()

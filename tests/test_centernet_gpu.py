@@ -579,6 +579,43 @@ def test_keypoint_heatmap_focal_loss_vs_oracle(cn, n_inst):
     assert_close(xd.grad, gref, rtol=2e-5, atol=1e-9, what="gradient")
 
 
+def test_keypoint_affinity_loss_golden(cn):
+    """loss.py:244-246 on the reference's own targets (tests/golden/make_golden.py), with its autograd gradient."""
+    g = golden("cn_kp_affinity_loss")
+    d = cn.dev
+    mc = synth.centernet_model_config(int(g["in_h"]), int(g["in_h"]), int(g["downsamples"]))
+    tc = SimpleNamespace(keypoint_heatmap_sigma=float(g["sigma_h"]), keypoint_affinity_sigma=float(g["sigma_a"]))
+    truth = SimpleNamespace(center=t(g["center"]).to(d), keypoint_valid=t(g["kp_valid"]).to(d),
+                            keypoint_label=t(g["kp_label"]).to(d), keypoint_center=t(g["kp_center"]).to(d),
+                            keypoint_object_index=t(g["kp_obj"]).to(d))
+    pred = t(g["pred"]).to(d).requires_grad_()
+    l = cn.L.keypoint_affinity_loss(pred, truth, mc, tc)
+    assert_close(l, g["loss"], what="keypoint affinity term")
+    l.backward()
+    assert_close(pred.grad, g["grad"], atol=1e-7, what="gradient")
+
+
+@pytest.mark.parametrize("B,n_obj,Kp,m,H,W,ds", [(2, 5, 6, 40, 32, 48, 2), (1, 16, 80, 100, 128, 128, 2), (2, 3, 4, 9, 20, 18, 1),
+                                                 (2, 4, 3, 150, 16, 16, 2)])
+def test_keypoint_affinity_loss_vs_oracle(cn, B, n_obj, Kp, m, H, W, ds):
+    """Against the oracle's autograd on other shapes: two and four instance chunks per lane (m > 32, m > 64), the full
+    keypoint plane size, and the W % 4 != 0 / m > 128 shapes that take the composed path."""
+    ratio = 2 ** ds
+    tr = synth.pose_truth(B, n_obj, 3, seed=81 + m, n_kp_inst=m, Kp=Kp)
+    pred = torch.randn((B, Kp, 2, H, W), generator=synth.gen(82 + H)) * 0.8
+    x = pred.clone().requires_grad_()
+    ref = O.keypoint_affinity_loss(x, tr.keypoint_valid, tr.keypoint_label, tr.keypoint_center, tr.keypoint_object_index,
+                                   tr.center, H, W, H * ratio, W * ratio, ratio, 2.0, 3.0)
+    gref, = torch.autograd.grad(ref, x)
+    mc = SimpleNamespace(in_h=H * ratio, in_w=W * ratio, downsample_ratio=ratio, out_h=H, out_w=W)
+    tc = SimpleNamespace(keypoint_heatmap_sigma=2.0, keypoint_affinity_sigma=3.0)
+    xd = pred.to(cn.dev).requires_grad_()
+    l = cn.L.keypoint_affinity_loss(xd, synth.truth_to(tr, cn.dev), mc, tc)
+    assert_close(l.detach(), ref.detach(), rtol=2e-5, what="keypoint affinity term")
+    (2 * l).backward()
+    assert_close(xd.grad, 2 * gref, rtol=2e-5, atol=1e-7, what="gradient")
+
+
 def test_focal_loss_full_batch_matches_composition(cn):
     """BASELINE configs[1] size (64 x 80 x 128 x 128): the fused pass equals the composition of this package's own
     generate_heatmap with the reference's elementwise expressions on the GPU, is deterministic run to run, and writes no

@@ -266,3 +266,15 @@ def test_pack_heads_golden():
     L = int(g["n_levels"])
     for key, C, th in (("cls", int(g["n_classes"]) + 1, False), ("box", 4, False), ("coeff", int(g["n_prototype_masks"]), True)):
         assert_equal(O.pack_head([t(g[f"{key}_level{l}"]) for l in range(L)], C, tanh=th), g[key], key)
+
+
+def test_keypoint_affinity_loss_golden():
+    """centernet/model/loss.py:244-246 — the reference's expression on its own targets, and its autograd gradient."""
+    g = golden("cn_kp_affinity_loss")
+    pred = t(g["pred"]).requires_grad_()
+    ratio = 2 ** int(g["downsamples"])
+    l = O.keypoint_affinity_loss(pred, t(g["kp_valid"]), t(g["kp_label"]), t(g["kp_center"]), t(g["kp_obj"]), t(g["center"]),
+                                 24, 24, int(g["in_h"]), int(g["in_h"]), ratio, float(g["sigma_h"]), float(g["sigma_a"]))
+    assert_equal(l.detach(), g["loss"])
+    grad, = torch.autograd.grad(l, pred)
+    assert_equal(grad, g["grad"])
