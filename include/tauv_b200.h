@@ -143,6 +143,12 @@ int tauv_gather_at(const float* src, int64_t sb, int64_t ssel, int64_t sc, int64
                    int64_t sx, int nch, const int64_t* index, const int64_t* label, int B, int k,
                    float* out, tauv_stream_t stream);
 
+/* Backward of tauv_gather_at without a label: dst[b*sb + c*sc + iy*sy + ix*sx] = sum of grad[b,j,c] over the objects j
+ * of frame b whose index[b,j] is (iy, ix), in object order (no atomics); dst must be zero-filled by the caller.  With
+ * tauv_gather_at this is the per-object gather of centernet/model/loss.py:196-227 and its autograd. */
+int tauv_scatter_add_at(const float* grad, const int64_t* index, int B, int k, int nch, float* dst,
+                        int64_t sb, int64_t sc, int64_t sy, int64_t sx, tauv_stream_t stream);
+
 /* The greedy keypoint -> object association of decode_keypoints — decode.py:98-135, on the device
  * (one warp per frame).  Inputs: the ranked objects of tauv_centernet_decode(mode KEYPOINTS)
  * (label [B,k] i64, yx [B,k,2] f64, count [B] i32) and the ranked keypoint peaks of

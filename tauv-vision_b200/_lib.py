@@ -50,6 +50,7 @@ _SIGNATURES = {
                                              c_size_t, c_void_p]),
     "tauv_gather_at": (c_int, [_F, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, _I64, _I64, c_int, c_int, _F,
                                c_void_p]),
+    "tauv_scatter_add_at": (c_int, [_F, _I64, c_int, c_int, c_int, _F, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "tauv_centernet_keypoint_assoc": (c_int, [_I64, _D, _I32, c_int, c_int, _I64, _I64, _F, c_int, _F, _I64, _I32, c_int,
                                               c_int, c_int, c_int, c_double, _U8, _F, _F, _F, c_void_p]),
     "tauv_angle_decode": (c_int, [_F, _F, c_int64, c_double, _F, c_void_p]),

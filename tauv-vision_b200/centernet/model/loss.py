@@ -254,3 +254,50 @@ def keypoint_affinity_loss(keypoint_affinity: torch.Tensor, truth, model_config,
     del dev
     geom = (int(model_config.in_h), int(model_config.in_w), int(model_config.downsample_ratio))
     return _KeypointAffinityLoss.apply(pred, kv, kl, kc, ko, center, geom, float(train_config.keypoint_affinity_sigma))
+
+
+class _GatherAtObjects(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, head, index):
+        dev = head.device
+        B, H, W, C = head.shape
+        n = index.shape[1]
+        out = torch.empty((B, n, C), dtype=torch.float32, device=dev)
+        sb, sy, sx, sc = head.stride()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().tauv_gather_at(_lib.fptr(head), sb, 0, sc, sy, sx, C, _lib.i64ptr(index), None, B, n,
+                                                  _lib.fptr(out), _lib.stream_ptr(dev)))
+        ctx.save_for_backward(index)
+        ctx.shape = (B, H, W, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        index, = ctx.saved_tensors
+        B, H, W, C = ctx.shape
+        dev = grad.device
+        g = grad.to(torch.float32).contiguous()
+        dst = torch.zeros((B, C, H, W), dtype=torch.float32, device=dev).permute(0, 2, 3, 1)  # the heads' own memory layout
+        sb, sy, sx, sc = dst.stride()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().tauv_scatter_add_at(_lib.fptr(g), _lib.i64ptr(index), B, index.shape[1], C, _lib.fptr(dst),
+                                                       sb, sc, sy, sx, _lib.stream_ptr(dev)))
+        return dst, None
+
+
+def gather_at_objects(head: torch.Tensor, out_index: torch.Tensor) -> torch.Tensor:
+    """``out[b, o] = head[b, out_index[b, o, 0], out_index[b, o, 1]]`` for every frame and object in one launch — the
+    Python double loop of the reference's loss (loss.py:196-227: prediction_size, prediction_offset, the angle bins and
+    offsets, prediction_depth), with autograd (objects that share a cell add up, in object order).  ``head`` is one of
+    the prediction's ``[B,H,W,C]`` views (``size``, ``offset``, ``roll_bin`` ... ; read through its strides, never made
+    contiguous) or ``[B,H,W]``; ``out_index`` is ``out_index_for_position(truth.center, model_config)`` [B,n,2].
+    Returns ``[B,n,C]`` (``[B,n]`` for a ``[B,H,W]`` head)."""
+    _lib.require_cuda(head, out_index)
+    squeeze = head.dim() == 3
+    h = head.unsqueeze(-1) if squeeze else head
+    if h.dim() != 4 or out_index.dim() != 3 or out_index.shape[0] != h.shape[0] or out_index.shape[2] != 2:
+        raise ValueError(f"head must be [B,H,W,C] and out_index [B,n,2]; got {tuple(head.shape)}, {tuple(out_index.shape)}")
+    if h.dtype != torch.float32:
+        h = h.float()
+    out = _GatherAtObjects.apply(h, _i64(out_index))
+    return out.squeeze(-1) if squeeze else out

@@ -1647,6 +1647,26 @@ __global__ void gather_at_kernel(const float* __restrict__ src, long long sb, lo
   out[t] = src[b * sb + sel * ssel + c * sc + index[j * 2] * sy + index[j * 2 + 1] * sx];
 }
 
+// backward of gather_at (label == NULL): dst[b, c, iy, ix] += grad[b, j, c].  No atomics: the FIRST object of a frame
+// that sits on a cell adds up, in object order, the gradients of every object on that cell (two objects on one cell
+// happen: loss.py:196-227 gathers at out_index_for_position of every object), the later ones do nothing.
+__global__ void scatter_add_at_kernel(const float* __restrict__ grad, const int64_t* __restrict__ index, long long n, int k,
+                                      int nch, float* __restrict__ dst, long long sb, long long sc, long long sy,
+                                      long long sx) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n * nch) return;
+  const long long j = t / nch;
+  const int c = (int)(t - j * nch);
+  const long long b = j / k, j0 = b * k;
+  const long long iy = index[j * 2], ix = index[j * 2 + 1];
+  for (long long q = j0; q < j; ++q)
+    if (index[q * 2] == iy && index[q * 2 + 1] == ix) return;
+  float acc = grad[t];
+  for (long long q = j + 1; q < j0 + k; ++q)
+    if (index[q * 2] == iy && index[q * 2 + 1] == ix) acc += grad[q * nch + c];
+  dst[b * sb + c * sc + iy * sy + ix * sx] = acc;
+}
+
 }  // namespace tauv
 
 #include "centernet_select.cuh"  // round 2: block maxima + select (the default decode path)
@@ -1950,6 +1970,18 @@ extern "C" int tauv_gather_at(const float* src, int64_t sb, int64_t ssel, int64_
   gather_at_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, sb, ssel, sc, sy, sx, nch,
                                                                                     index, label, n, k, out);
   TAUV_LAUNCH_CHECK("gather_at_kernel");
+  return 0;
+}
+
+extern "C" int tauv_scatter_add_at(const float* grad, const int64_t* index, int B, int k, int nch, float* dst, int64_t sb,
+                                   int64_t sc, int64_t sy, int64_t sx, tauv_stream_t stream) {
+  TAUV_REQUIRE(grad && index && dst, TAUV_E_NULL, "grad/index/dst must not be NULL");
+  TAUV_REQUIRE(B > 0 && k > 0 && nch > 0, TAUV_E_SHAPE, "bad shape");
+  const long long n = (long long)B * k;
+  const long long tot = n * nch;
+  scatter_add_at_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grad, index, n, k, nch, dst, sb, sc,
+                                                                                         sy, sx);
+  TAUV_LAUNCH_CHECK("scatter_add_at_kernel");
   return 0;
 }
 

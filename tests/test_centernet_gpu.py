@@ -616,6 +616,41 @@ def test_keypoint_affinity_loss_vs_oracle(cn, B, n_obj, Kp, m, H, W, ds):
     assert_close(xd.grad, 2 * gref, rtol=2e-5, atol=1e-7, what="gradient")
 
 
+def test_gather_at_objects_matches_the_reference_loop(cn):
+    """loss.py:196-227 — the per-object gathers of the size / offset / angle / depth heads through their permuted views,
+    and the gradient autograd derives from the loop (two objects on one cell add up)."""
+    B, H, W, n = 3, 24, 20, 7
+    g = synth.gen(91)
+    mc = SimpleNamespace(in_h=H * 4, in_w=W * 4, downsample_ratio=4, out_h=H, out_w=W)
+    center = torch.rand((B, n, 2), generator=g)
+    center[0, 1] = center[0, 0]
+    center[0, 4] = center[0, 0]   # three objects on one cell
+    idx_ref = O.out_index_for_position(center, mc.in_h, mc.in_w, 4, H, W)
+    idx = cn.L.out_index_for_position(center.to(cn.dev), mc)
+    assert_equal(idx, idx_ref)
+    for C in (2, 4, 1):
+        nchw = torch.randn((B, C, H, W), generator=g)
+        wgt = torch.randn((B, n, C), generator=g)
+        ref_in = nchw.clone().requires_grad_()
+        view = ref_in.permute(0, 2, 3, 1)
+        want = torch.zeros((B, n, C))
+        rows = []
+        for b in range(B):
+            for o in range(n):
+                rows.append(view[b, idx_ref[b, o, 0], idx_ref[b, o, 1]])     # loss.py:214-227
+        want = torch.stack(rows).reshape(B, n, C)
+        (want * wgt).sum().backward()
+        dev_in = nchw.to(cn.dev).requires_grad_()
+        got = cn.L.gather_at_objects(dev_in.permute(0, 2, 3, 1), idx)
+        assert_equal(got, want.detach(), f"gather C={C}")
+        (got * wgt.to(cn.dev)).sum().backward()
+        assert_close(dev_in.grad, ref_in.grad, rtol=1e-6, atol=1e-7, what=f"gradient C={C}")
+    depth = torch.randn((B, 1, H, W), generator=g)
+    got = cn.L.gather_at_objects(depth.to(cn.dev).permute(0, 2, 3, 1)[..., 0], idx)
+    assert got.shape == (B, n)
+    assert_equal(got, depth[torch.arange(B)[:, None], 0, idx_ref[..., 0], idx_ref[..., 1]])
+
+
 def test_focal_loss_full_batch_matches_composition(cn):
     """BASELINE configs[1] size (64 x 80 x 128 x 128): the fused pass equals the composition of this package's own
     generate_heatmap with the reference's elementwise expressions on the GPU, is deterministic run to run, and writes no
