@@ -378,7 +378,7 @@ struct MaskLossArgs {
   const uint8_t* img_valid;    // [B,SH,SW]
   int N, K, M, PH, PW, SH, SW;
   float sy, sx;                // (float)SH / PH, (float)SW / PW: ATen's area_pixel_compute_scale without align_corners
-  float* tsum;                 // [B,M]: area of every truth's resized mask
+  double* tsum;                // [B,M]: area of every truth's resized mask (u64 fixed point while ymask_area_kernel adds)
   double* partial;             // [B,gridDim.x] (forward)
   const float* grad_out;       // [1] (backward)
   const int64_t* n_pos_total;  // [1] (backward)
@@ -425,6 +425,14 @@ __device__ __forceinline__ float mask_truth(const MaskPx& g, const int32_t* seg,
                    __fmul_rn(g.ly1, __fadd_rn(__fmul_rn(g.lx0, v10), __fmul_rn(g.lx1, v11))));
 }
 
+// the same from the four tap values (the taps of a pixel do not depend on the truth: loaded once, compared many times)
+__device__ __forceinline__ float mask_truth_taps(const MaskPx& g, int s00, int s01, int s10, int s11, int j) {
+  const float v00 = s00 == j ? 1.0f : 0.0f, v01 = s01 == j ? 1.0f : 0.0f;
+  const float v10 = s10 == j ? 1.0f : 0.0f, v11 = s11 == j ? 1.0f : 0.0f;
+  return __fadd_rn(__fmul_rn(g.ly0, __fadd_rn(__fmul_rn(g.lx0, v00), __fmul_rn(g.lx1, v01))),
+                   __fmul_rn(g.ly1, __fadd_rn(__fmul_rn(g.lx0, v10), __fmul_rn(g.lx1, v11))));
+}
+
 __device__ __forceinline__ float mask_weight(const MaskPx& g, const CropBounds& c) {
   return (g.fx >= c.left && g.fx <= c.right && g.fy >= c.top && g.fy <= c.bottom) ? g.valid : 0.0f;
 }
@@ -465,20 +473,45 @@ __device__ __forceinline__ MaskBoxRange mask_box_range(const CropBounds& c, int 
   return r;
 }
 
-// area[b][j] = sum over the prototype grid of the bilinearly resized mask of truth j (loss.py:86-93, :113): one CTA per
-// (truth, frame) — positives that share a truth share its area — summed in fp64 in a fixed order
+// area[b][j] = sum over the prototype grid of the bilinearly resized mask of truth j (loss.py:86-93, :113), for all truths
+// of a frame in ONE pass over the grid: a pixel's four taps each add their bilinear weight to the truth they show.
+// The sums are kept in 2^-40 fixed point (64-bit integer atomics, shared memory first), so they do not depend on the
+// order of the additions: deterministic, and within 1e-7 of the fp32 sum of the resized mask.
+constexpr double kAreaScale = 1099511627776.0;  // 2^40
 __global__ void __launch_bounds__(kMaskLossThreads) ymask_area_kernel(const MaskLossArgs a) {
-  __shared__ double s_red[kMaskLossThreads / 32];
-  const int j = blockIdx.x, b = blockIdx.y;
+  extern __shared__ unsigned long long s_area[];  // [M]
+  const int b = blockIdx.y;
   const int HW = a.PH * a.PW;
   const int32_t* seg = a.seg + (size_t)b * a.SH * a.SW;
-  double area = 0.0;
-  for (int px = threadIdx.x; px < HW; px += kMaskLossThreads) {
+  for (int m = threadIdx.x; m < a.M; m += kMaskLossThreads) s_area[m] = 0ull;
+  __syncthreads();
+  const int px = blockIdx.x * kMaskLossThreads + threadIdx.x;
+  if (px < HW) {
     const int y = px / a.PW, x = px - y * a.PW;
-    area += (double)mask_truth(mask_px(a, b, y, x), seg, j);
+    const MaskPx g = mask_px(a, b, y, x);
+    const int sv[4] = {seg[g.o00], seg[g.o01], seg[g.o10], seg[g.o11]};
+    const float wv[4] = {__fmul_rn(g.ly0, g.lx0), __fmul_rn(g.ly0, g.lx1), __fmul_rn(g.ly1, g.lx0), __fmul_rn(g.ly1, g.lx1)};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double w = 0.0;   // taps that show the same truth are added first: one atomic per distinct truth
+      bool first = true;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (r < q && sv[r] == sv[q]) first = false;
+        if (r >= q && sv[r] == sv[q]) w += (double)wv[r];
+      }
+      if (first && sv[q] >= 0 && sv[q] < a.M && w > 0.0) atomicAdd(&s_area[sv[q]], (unsigned long long)llrint(w * kAreaScale));
+    }
   }
-  area = mask_block_sum(area, s_red);
-  if (threadIdx.x == 0) a.tsum[(size_t)b * a.M + j] = (float)area;
+  __syncthreads();
+  unsigned long long* fx = reinterpret_cast<unsigned long long*>(a.tsum) + (size_t)b * a.M;
+  for (int m = threadIdx.x; m < a.M; m += kMaskLossThreads)
+    if (s_area[m]) atomicAdd(&fx[m], s_area[m]);
+}
+
+__global__ void ymask_area_finish_kernel(double* tsum, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) tsum[t] = (double)reinterpret_cast<const unsigned long long*>(tsum)[t] / kAreaScale;
 }
 
 template <bool BACKWARD>
@@ -505,45 +538,48 @@ __global__ void __launch_bounds__(kMaskLossThreads) ymask_positive_kernel(const 
     const CropBounds crop = crop_bounds(make_float4(tb[0], tb[1], tb[2], tb[3]), a.PH, a.PW);
     const MaskBoxRange box = mask_box_range(crop, a.PH, a.PW);
     const int npx = box.bh * box.bw;
-    const float area = a.tsum[(size_t)b * a.M + j];
+    const double area = a.tsum[(size_t)b * a.M + j];
     __syncthreads();
     if (tid < a.K) s_coeff[tid] = a.coeff[((size_t)b * a.N + n) * a.K + tid];
     __syncthreads();
     if (!BACKWARD) {
       double num = 0.0;
-      if (area > 0.0f) {   // loss.py:93-94
+      if (area > 0.0) {   // loss.py:93-94
         for (int q = tid; q < npx; q += kMaskLossThreads) {
           const int y = box.y0 + q / box.bw, x = box.x0 + q % box.bw, px = y * a.PW + x;
           const MaskPx g = mask_px(a, b, y, x);
           const float w = mask_weight(g, crop);
           if (w != 0.0f) {
+            float pv[kMaskLossMaxK];   // (all K loads in flight before the first use: the loop is latency-bound)
+#pragma unroll
+            for (int k = 0; k < kMaskLossMaxK; ++k) pv[k] = k < a.K ? proto[(size_t)k * HW + px] : 0.0f;
             float logit = 0.0f;
-            for (int k = 0; k < a.K; ++k) logit += s_coeff[k] * proto[(size_t)k * HW + px];   // loss.py:82
+#pragma unroll
+            for (int k = 0; k < kMaskLossMaxK; ++k) logit += k < a.K ? s_coeff[k] * pv[k] : 0.0f;   // loss.py:82
             const float m = clamp_unit(fmaxf(sigmoid_ref(logit), 1e-4f)), tc = clamp_unit(mask_truth(g, seg, j));  // :83-84, :97-98
             num += (double)(w * -(tc * logf(m) + (1.0f - tc) * logf(1.0f - m)));               // :96-100, :113
           }
         }
       }
       num = mask_block_sum(num, s_red);
-      if (area > 0.0f) cta_sum += num / (double)area;   // :113
+      if (area > 0.0) cta_sum += num / area;   // :113
     } else {
       float gc[kMaskLossMaxK];
 #pragma unroll
       for (int k = 0; k < kMaskLossMaxK; ++k) gc[k] = 0.0f;
-      if (area > 0.0f) {
-        const float G = __fdiv_rn(gscale, area);
+      if (area > 0.0) {
+        const float G = __fdiv_rn(gscale, (float)area);
         for (int q = tid; q < npx; q += kMaskLossThreads) {
           const int y = box.y0 + q / box.bw, x = box.x0 + q % box.bw, px = y * a.PW + x;
           const MaskPx g = mask_px(a, b, y, x);
           const float w = mask_weight(g, crop);
           if (w == 0.0f) continue;
-          float pv[kMaskLossMaxK];
+          float pv[kMaskLossMaxK];   // (all K loads in flight before the first use)
+#pragma unroll
+          for (int k = 0; k < kMaskLossMaxK; ++k) pv[k] = k < a.K ? proto[(size_t)k * HW + px] : 0.0f;
           float logit = 0.0f;
 #pragma unroll
-          for (int k = 0; k < kMaskLossMaxK; ++k) {
-            pv[k] = k < a.K ? proto[(size_t)k * HW + px] : 0.0f;
-            logit += k < a.K ? s_coeff[k] * pv[k] : 0.0f;
-          }
+          for (int k = 0; k < kMaskLossMaxK; ++k) logit += k < a.K ? s_coeff[k] * pv[k] : 0.0f;
           const float dl = G * mask_dlogit(logit, mask_truth(g, seg, j), w);
 #pragma unroll
           for (int k = 0; k < kMaskLossMaxK; ++k) gc[k] += dl * pv[k];
@@ -575,10 +611,11 @@ struct MaskPosRec {
   float G;      // grad_out / (P * area), 0 = skipped
   int n, j;
 };
-constexpr int kMaskRecChunk = 128;
+constexpr int kMaskRecChunk = 64;
 
 __global__ void __launch_bounds__(kMaskLossThreads) ymask_backward_proto_kernel(const MaskLossArgs a) {
   __shared__ MaskPosRec s_rec[kMaskRecChunk];
+  __shared__ float s_cf[kMaskRecChunk][kMaskLossMaxK];   // the chunk's coefficient rows
   const int b = blockIdx.y;
   const int HW = a.PH * a.PW;
   const int px = blockIdx.x * kMaskLossThreads + threadIdx.x;
@@ -596,16 +633,22 @@ __global__ void __launch_bounds__(kMaskLossThreads) ymask_backward_proto_kernel(
   }
   const int y = live ? px / a.PW : 0, x = live ? px - y * a.PW : 0;
   const MaskPx g = mask_px(a, b, y, x);
+  // (the four taps of this pixel's bilinear resize do not depend on the positive: loaded once)
+  const int s00 = live ? seg[g.o00] : -1, s01 = live ? seg[g.o01] : -1, s10 = live ? seg[g.o10] : -1, s11 = live ? seg[g.o11] : -1;
   for (int i0 = 0; i0 < npos; i0 += kMaskRecChunk) {
     __syncthreads();
+    for (int e = threadIdx.x; e < kMaskRecChunk * a.K; e += kMaskLossThreads) {
+      const int r = e / a.K, k = e - r * a.K;
+      if (i0 + r < npos) s_cf[r][k] = a.coeff[((size_t)b * a.N + a.pos_list[(size_t)b * a.N + i0 + r]) * a.K + k];
+    }
     for (int r = threadIdx.x; r < kMaskRecChunk && i0 + r < npos; r += kMaskLossThreads) {
       const int n = a.pos_list[(size_t)b * a.N + i0 + r];
       long long jl = a.match_index[(size_t)b * a.N + n];
       const int j = (int)(jl < 0 ? 0 : (jl >= a.M ? a.M - 1 : jl));
       const float* tb = a.truth_box + ((size_t)b * a.M + j) * 4;
       const CropBounds c = crop_bounds(make_float4(tb[0], tb[1], tb[2], tb[3]), a.PH, a.PW);
-      const float area = a.tsum[(size_t)b * a.M + j];
-      s_rec[r] = MaskPosRec{c.left, c.right, c.top, c.bottom, area > 0.0f ? __fdiv_rn(gscale, area) : 0.0f, n, j};
+      const double area = a.tsum[(size_t)b * a.M + j];
+      s_rec[r] = MaskPosRec{c.left, c.right, c.top, c.bottom, area > 0.0 ? __fdiv_rn(gscale, (float)area) : 0.0f, n, j};
     }
     __syncthreads();
     const int nr = min(kMaskRecChunk, npos - i0);
@@ -613,17 +656,15 @@ __global__ void __launch_bounds__(kMaskLossThreads) ymask_backward_proto_kernel(
       const MaskPosRec& rec = s_rec[r];
       if (!(g.fx >= rec.left && g.fx <= rec.right && g.fy >= rec.top && g.fy <= rec.bottom) || g.valid == 0.0f || rec.G == 0.0f)
         continue;
-      const float* cf = a.coeff + ((size_t)b * a.N + rec.n) * a.K;   // (the same address in every thread: broadcast loads)
-      float cv[kMaskLossMaxK];
+      const float* cf = s_cf[r];   // (the same address in every thread: shared-memory broadcasts)
       float logit = 0.0f;
 #pragma unroll
-      for (int k = 0; k < kMaskLossMaxK; ++k) {
-        cv[k] = k < a.K ? cf[k] : 0.0f;
-        logit += cv[k] * pv[k];
-      }
-      const float dl = rec.G * mask_dlogit(logit, mask_truth(g, seg, rec.j), g.valid);
+      for (int k = 0; k < kMaskLossMaxK; ++k)
+        if (k < a.K) logit += cf[k] * pv[k];
+      const float dl = rec.G * mask_dlogit(logit, mask_truth_taps(g, s00, s01, s10, s11, rec.j), g.valid);
 #pragma unroll
-      for (int k = 0; k < kMaskLossMaxK; ++k) gp[k] += dl * cv[k];
+      for (int k = 0; k < kMaskLossMaxK; ++k)
+        if (k < a.K) gp[k] += dl * cf[k];
     }
   }
   if (live) {
@@ -721,14 +762,19 @@ extern "C" int tauv_yolact_mask_loss_partials(void) { return kMaskLossWalkers; }
 extern "C" int tauv_yolact_mask_loss(const float* coeff, const float* proto, const int32_t* pos_list, const int64_t* n_pos,
                                      const int64_t* match_index, const float* truth_box, const int32_t* seg,
                                      const uint8_t* img_valid, int B, int N, int K, int M, int PH, int PW, int SH, int SW,
-                                     float* tsum, double* partial, tauv_stream_t stream) {
+                                     double* tsum, double* partial, tauv_stream_t stream) {
   MaskLossArgs a{coeff, proto, pos_list, n_pos, match_index, truth_box, seg, img_valid, N, K, M, PH, PW, SH, SW,
                  PH > 0 ? (float)SH / (float)PH : 0.f, PW > 0 ? (float)SW / (float)PW : 0.f, tsum, partial,
                  nullptr, nullptr, nullptr, nullptr};
   if (int rc = mask_loss_check(a, B)) return rc;
   TAUV_REQUIRE(partial, TAUV_E_NULL, "pointers must not be NULL");
-  ymask_area_kernel<<<dim3(M, B), kMaskLossThreads, 0, (cudaStream_t)stream>>>(a);
+  TAUV_REQUIRE((size_t)M * sizeof(unsigned long long) <= 48 * 1024, TAUV_E_UNSUPPORTED, "M=%d exceeds the built-in limit 6144", M);
+  TAUV_CUDA(cudaMemsetAsync(tsum, 0, (size_t)B * M * sizeof(double), (cudaStream_t)stream));
+  ymask_area_kernel<<<dim3((PH * PW + kMaskLossThreads - 1) / kMaskLossThreads, B), kMaskLossThreads,
+                      (size_t)M * sizeof(unsigned long long), (cudaStream_t)stream>>>(a);
   TAUV_LAUNCH_CHECK("ymask_area_kernel");
+  ymask_area_finish_kernel<<<(B * M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(tsum, B * M);
+  TAUV_LAUNCH_CHECK("ymask_area_finish_kernel");
   ymask_positive_kernel<false><<<dim3(kMaskLossWalkers, B), kMaskLossThreads, 0, (cudaStream_t)stream>>>(a);
   TAUV_LAUNCH_CHECK("ymask_positive_kernel<forward>");
   return 0;
@@ -737,11 +783,11 @@ extern "C" int tauv_yolact_mask_loss(const float* coeff, const float* proto, con
 extern "C" int tauv_yolact_mask_loss_backward(const float* coeff, const float* proto, const int32_t* pos_list,
                                               const int64_t* n_pos, const int64_t* match_index, const float* truth_box,
                                               const int32_t* seg, const uint8_t* img_valid, int B, int N, int K, int M,
-                                              int PH, int PW, int SH, int SW, const float* tsum,
+                                              int PH, int PW, int SH, int SW, const double* tsum,
                                               const int64_t* n_pos_total, const float* grad_out, float* grad_coeff,
                                               float* grad_proto, tauv_stream_t stream) {
   MaskLossArgs a{coeff, proto, pos_list, n_pos, match_index, truth_box, seg, img_valid, N, K, M, PH, PW, SH, SW,
-                 PH > 0 ? (float)SH / (float)PH : 0.f, PW > 0 ? (float)SW / (float)PW : 0.f, const_cast<float*>(tsum),
+                 PH > 0 ? (float)SH / (float)PH : 0.f, PW > 0 ? (float)SW / (float)PW : 0.f, const_cast<double*>(tsum),
                  nullptr, grad_out, n_pos_total, grad_coeff, grad_proto};
   if (int rc = mask_loss_check(a, B)) return rc;
   TAUV_REQUIRE(n_pos_total && grad_out, TAUV_E_NULL, "pointers must not be NULL");
