@@ -635,33 +635,56 @@ __global__ void __launch_bounds__(kMaskLossThreads) ymask_backward_proto_kernel(
   const MaskPx g = mask_px(a, b, y, x);
   // (the four taps of this pixel's bilinear resize do not depend on the positive: loaded once)
   const int s00 = live ? seg[g.o00] : -1, s01 = live ? seg[g.o01] : -1, s10 = live ? seg[g.o10] : -1, s11 = live ? seg[g.o11] : -1;
+  // the rows and columns this CTA's pixels span: positives whose crop box misses them are not staged at all (a CTA is
+  // about one row of the grid, a box covers a quarter of the rows: three positives in four drop out here)
+  const int p_lo = blockIdx.x * kMaskLossThreads, p_hi = min(p_lo + kMaskLossThreads, HW) - 1;
+  const int y_lo = p_lo / a.PW, y_hi = p_hi / a.PW;
+  const float fy_lo = (float)y_lo, fy_hi = (float)y_hi;
+  const float fx_lo = y_lo == y_hi ? (float)(p_lo - y_lo * a.PW) : 0.0f, fx_hi = y_lo == y_hi ? (float)(p_hi - y_hi * a.PW) : (float)(a.PW - 1);
+  __shared__ int s_kept[2];
+  static_assert(kMaskRecChunk == 64, "the ordered compaction below uses two warps");
   for (int i0 = 0; i0 < npos; i0 += kMaskRecChunk) {
     __syncthreads();
-    for (int e = threadIdx.x; e < kMaskRecChunk * a.K; e += kMaskLossThreads) {
-      const int r = e / a.K, k = e - r * a.K;
-      if (i0 + r < npos) s_cf[r][k] = a.coeff[((size_t)b * a.N + a.pos_list[(size_t)b * a.N + i0 + r]) * a.K + k];
-    }
-    for (int r = threadIdx.x; r < kMaskRecChunk && i0 + r < npos; r += kMaskLossThreads) {
-      const int n = a.pos_list[(size_t)b * a.N + i0 + r];
-      long long jl = a.match_index[(size_t)b * a.N + n];
-      const int j = (int)(jl < 0 ? 0 : (jl >= a.M ? a.M - 1 : jl));
-      const float* tb = a.truth_box + ((size_t)b * a.M + j) * 4;
-      const CropBounds c = crop_bounds(make_float4(tb[0], tb[1], tb[2], tb[3]), a.PH, a.PW);
-      const double area = a.tsum[(size_t)b * a.M + j];
-      s_rec[r] = MaskPosRec{c.left, c.right, c.top, c.bottom, area > 0.0 ? __fdiv_rn(gscale, (float)area) : 0.0f, n, j};
+    if (threadIdx.x < kMaskRecChunk) {   // (warps 0 and 1: one candidate per lane, kept in list order)
+      const int r = threadIdx.x, lane = r & 31;
+      MaskPosRec rec{};
+      bool keep = false;
+      if (i0 + r < npos) {
+        const int n = a.pos_list[(size_t)b * a.N + i0 + r];
+        long long jl = a.match_index[(size_t)b * a.N + n];
+        const int j = (int)(jl < 0 ? 0 : (jl >= a.M ? a.M - 1 : jl));
+        const float* tb = a.truth_box + ((size_t)b * a.M + j) * 4;
+        const CropBounds c = crop_bounds(make_float4(tb[0], tb[1], tb[2], tb[3]), a.PH, a.PW);
+        const double area = a.tsum[(size_t)b * a.M + j];
+        rec = MaskPosRec{c.left, c.right, c.top, c.bottom, area > 0.0 ? __fdiv_rn(gscale, (float)area) : 0.0f, n, j};
+        keep = rec.G != 0.0f && c.bottom >= fy_lo && c.top <= fy_hi && c.right >= fx_lo && c.left <= fx_hi;  // (false for NaN)
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) s_kept[r >> 5] = __popc(bal);
+      asm volatile("bar.sync 1, 64;" ::: "memory");
+      const int slot = (r >= 32 ? s_kept[0] : 0) + __popc(bal & ((1u << lane) - 1u));
+      if (keep) s_rec[slot] = rec;
     }
     __syncthreads();
-    const int nr = min(kMaskRecChunk, npos - i0);
+    const int nr = s_kept[0] + s_kept[1];
+    for (int e = threadIdx.x; e < nr * a.K; e += kMaskLossThreads) {
+      const int r = e / a.K, k = e - r * a.K;
+      s_cf[r][k] = a.coeff[((size_t)b * a.N + s_rec[r].n) * a.K + k];
+    }
+    __syncthreads();
     for (int r = 0; r < nr && live; ++r) {
       const MaskPosRec& rec = s_rec[r];
-      if (!(g.fx >= rec.left && g.fx <= rec.right && g.fy >= rec.top && g.fy <= rec.bottom) || g.valid == 0.0f || rec.G == 0.0f)
-        continue;
+      if (!(g.fx >= rec.left && g.fx <= rec.right && g.fy >= rec.top && g.fy <= rec.bottom) || g.valid == 0.0f) continue;
       const float* cf = s_cf[r];   // (the same address in every thread: shared-memory broadcasts)
-      float logit = 0.0f;
+      float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
 #pragma unroll
-      for (int k = 0; k < kMaskLossMaxK; ++k)
-        if (k < a.K) logit += cf[k] * pv[k];
-      const float dl = rec.G * mask_dlogit(logit, mask_truth_taps(g, s00, s01, s10, s11, rec.j), g.valid);
+      for (int k = 0; k < kMaskLossMaxK; k += 4) {
+        if (k < a.K) l0 += cf[k] * pv[k];
+        if (k + 1 < a.K) l1 += cf[k + 1] * pv[k + 1];
+        if (k + 2 < a.K) l2 += cf[k + 2] * pv[k + 2];
+        if (k + 3 < a.K) l3 += cf[k + 3] * pv[k + 3];
+      }
+      const float dl = rec.G * mask_dlogit((l0 + l1) + (l2 + l3), mask_truth_taps(g, s00, s01, s10, s11, rec.j), g.valid);
 #pragma unroll
       for (int k = 0; k < kMaskLossMaxK; ++k)
         if (k < a.K) gp[k] += dl * cf[k];
