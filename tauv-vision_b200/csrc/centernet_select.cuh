@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
   int n = 0;
   bool slow = false;
   int attempts = 0;
-  uint32_t T_next = 0u;  // a threshold the next attempt takes as it is (step 2: smooth maps)
+  bool take_T2 = false;  // the next attempt takes sh->T_key2 as its threshold (step 2: smooth maps)
   for (;;) {
     ++attempts;
     // ---- 1. threshold T: (a lower bound of) the K1-th largest of 1024 strided maxima of the group (or block) maxima.
@@ -597,10 +597,10 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
     uint32_t T_key2 = 0u;
     uint32_t key = 0u;
     uint4 wkey = make_uint4(0u, 0u, 0u, 0u);
-    if (T_next != 0u) {
-      T_key = T_next;
+    if (take_T2) {
+      T_key = sh->T_key2;
       T_f = key_to_float(T_key);
-      T_next = 0u;
+      take_T2 = false;
     } else if (nwf > 0 && (K1 <= 32 * nwf || wide)) {
       uint32_t* hist = sh->s.hist;  // [0,1024) bins, [1024,1056) warp totals, [1056,1088) j-th largest, [1088,1120) largest
       if (wide) {
@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const __grid_con
       nhot = nh + sh->n_xhot;
       if (T_key2 != 0u && 2 * nhot >= 3 * nh) {  // smooth map (noise: 1.07 hot blocks per hot group): step 2 again, with T2
         K1 = K2;
-        T_next = T_key2;
+        take_T2 = true;
         continue;
       }
     } else {
