@@ -144,12 +144,19 @@ __global__ void __launch_bounds__(256) match_anchors_kernel(
       const float ih = __fsub_rn(fminf(ca.y1, s0.z), fmaxf(ca.y0, s0.x));
       const float iw = __fsub_rn(fminf(ca.x1, s0.w), fmaxf(ca.x0, s0.y));
       const float uni0 = __fadd_rn(ca.area, s1.x);
-      if (a_ok && s1.z != 0.0f && (ih <= 0.0f || iw <= 0.0f) && uni0 > 0.0f && uni0 <= 3.0e38f) {
+      const bool finite = a_ok && s1.z != 0.0f;
+      if (finite && (ih <= 0.0f || iw <= 0.0f) && uni0 > 0.0f && uni0 <= 3.0e38f) {
         v = 0.0f;
+      } else if (finite) {
+        // no NaN anywhere: fminf / fmaxf ARE torch.min / torch.max, and ih, iw, uni0 above are iou_pair's own terms
+        // (boxes.py:68-83) — the NaN-propagating version below is 40 instructions that every lane of the warp would
+        // step through for the sake of the few that overlap this truth
+        const float inter = __fmul_rn(fmaxf(ih, 0.0f), fmaxf(iw, 0.0f));
+        v = __fmul_rn(__fdiv_rn(inter, __fsub_rn(uni0, inter)), s1.y);  // iou * truth_valid.float()
       } else {
         Corners cb;
         cb.y0 = s0.x; cb.x0 = s0.y; cb.y1 = s0.z; cb.x1 = s0.w; cb.area = s1.x;
-        v = __fmul_rn(iou_pair(ca, cb), s1.y);  // iou * truth_valid.float()
+        v = __fmul_rn(iou_pair(ca, cb), s1.y);
       }
       // torch.max(dim): first maximum wins; a NaN wins over everything that came before it.  (A culled truth is an
       // exact +0: it can only ever be the maximum as truth 0, which is what best / best_m start from.)
