@@ -650,6 +650,7 @@ def time_yolact(device, seed, B=B_PER_GPU):
     ts = []
     for _ in range(7):
         y.proto.sum()
+        torch.cuda._sleep(400_000)  # (device-side spin: the wrapper's five allocations and its launch are enqueued meanwhile)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         yl_loss.match_anchors(y.anchor, tb, tvd, y.cfg)
