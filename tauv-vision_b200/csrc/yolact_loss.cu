@@ -515,7 +515,7 @@ __global__ void ymask_area_finish_kernel(double* tsum, int n) {
 }
 
 template <bool BACKWARD>
-__global__ void __launch_bounds__(kMaskLossThreads) ymask_positive_kernel(const MaskLossArgs a) {
+__global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_positive_kernel(const MaskLossArgs a) {
   __shared__ float s_coeff[kMaskLossMaxK];
   __shared__ double s_red[kMaskLossThreads / 32];
   __shared__ float s_gc[kMaskLossThreads / 32][kMaskLossMaxK];
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(kMaskLossThreads) ymask_positive_kernel(const 
     const int npx = box.bh * box.bw;
     const double area = a.tsum[(size_t)b * a.M + j];
     __syncthreads();
-    if (tid < a.K) s_coeff[tid] = a.coeff[((size_t)b * a.N + n) * a.K + tid];
+    if (tid < kMaskLossMaxK) s_coeff[tid] = tid < a.K ? a.coeff[((size_t)b * a.N + n) * a.K + tid] : 0.0f;
     __syncthreads();
     if (!BACKWARD) {
       double num = 0.0;
@@ -574,15 +574,23 @@ __global__ void __launch_bounds__(kMaskLossThreads) ymask_positive_kernel(const 
           const MaskPx g = mask_px(a, b, y, x);
           const float w = mask_weight(g, crop);
           if (w == 0.0f) continue;
-          float pv[kMaskLossMaxK];   // (all K loads in flight before the first use)
-#pragma unroll
-          for (int k = 0; k < kMaskLossMaxK; ++k) pv[k] = k < a.K ? proto[(size_t)k * HW + px] : 0.0f;
+          // sixteen prototype loads in flight at a time; the first sixteen are read again (from L1) for the
+          // accumulation — holding all 32 next to the 32 accumulators took 219 registers: one CTA per SM
           float logit = 0.0f;
+          float pv[16];
 #pragma unroll
-          for (int k = 0; k < kMaskLossMaxK; ++k) logit += k < a.K ? s_coeff[k] * pv[k] : 0.0f;
+          for (int k = 0; k < 16; ++k) pv[k] = k < a.K ? proto[(size_t)k * HW + px] : 0.0f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) logit += s_coeff[k] * pv[k];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) pv[k] = 16 + k < a.K ? proto[(size_t)(16 + k) * HW + px] : 0.0f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) logit += s_coeff[16 + k] * pv[k];
           const float dl = G * mask_dlogit(logit, mask_truth(g, seg, j), w);
 #pragma unroll
-          for (int k = 0; k < kMaskLossMaxK; ++k) gc[k] += dl * pv[k];
+          for (int k = 0; k < 16; ++k) gc[16 + k] += dl * pv[k];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) gc[k] += dl * (k < a.K ? proto[(size_t)k * HW + px] : 0.0f);
         }
       }
       // K sums over the CTA: warp shuffles, then the eight warps' values in a fixed order
