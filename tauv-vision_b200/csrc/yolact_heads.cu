@@ -81,7 +81,67 @@ __global__ void __launch_bounds__(kHeadTile * 8) head_pack_kernel(const HeadPack
   }
 }
 
-static int head_pack_plan(HeadPackArgs* a, const int* hw, int n_levels, int B, int CH) {
+// The same with whole output rows per CTA (CH * (PT + 1) floats of shared memory): a CTA takes PT consecutive cells of a
+// level and ALL their CH channels, so what it writes (forward) or reads (backward) in the packed tensor is one contiguous
+// block of PT * CH floats — full sectors, whatever CH is (243 floats per row are never 128-byte aligned: 32 x 32 tiles
+// touch five sectors per 128-byte store and waste the partial channel tile).
+template <bool BACKWARD>
+__global__ void __launch_bounds__(kHeadTile * 8) head_pack_rows_kernel(const HeadPackArgs a, int PT) {
+  extern __shared__ float s_rows[];  // [CH][PT + 1]
+  int l = 0;
+  while (l + 1 < a.n_levels && (int)blockIdx.x >= a.tile_base[l + 1]) ++l;
+  const int hw = a.hw[l];
+  const int hw0 = (blockIdx.x - a.tile_base[l]) * PT;
+  const int npix = min(PT, hw - hw0);
+  const int b = blockIdx.y, tid = threadIdx.x, nthr = kHeadTile * 8;
+  const int S = PT + 1;
+  const size_t lvl_off = (size_t)b * a.CH * hw + hw0;
+  const size_t packed_off = (size_t)b * a.rows * a.CH + (size_t)(a.row_base[l] + hw0) * a.CH;
+  const int n_el = npix * a.CH;
+  const int dch = nthr % a.CH, dp = nthr / a.CH;   // a step of nthr elements of the packed block, as (cell, channel)
+  if (!BACKWARD) {
+    const float* in = a.lvl_in[l] + lvl_off;
+    for (int idx = tid; idx < a.CH * PT; idx += nthr) {   // (PT is a multiple of 32: a warp reads one channel's cells)
+      const int ch = idx / PT, p = idx - ch * PT;
+      if (p < npix) s_rows[ch * S + p] = in[(size_t)ch * hw + p];
+    }
+    __syncthreads();
+    int p = tid / a.CH, ch = tid - p * a.CH;
+    for (int e = tid; e < n_el; e += nthr) {
+      const float v = s_rows[ch * S + p];
+      a.packed[packed_off + e] = a.tanh_act ? tanhf(v) : v;
+      ch += dch;
+      p += dp;
+      if (ch >= a.CH) { ch -= a.CH; ++p; }
+    }
+  } else {
+    int p = tid / a.CH, ch = tid - p * a.CH;
+    for (int e = tid; e < n_el; e += nthr) {
+      float g = a.grad_packed[packed_off + e];
+      if (a.tanh_act) {
+        const float y = a.y_packed[packed_off + e];
+        g = g * (1.0f - y * y);
+      }
+      s_rows[ch * S + p] = g;
+      ch += dch;
+      p += dp;
+      if (ch >= a.CH) { ch -= a.CH; ++p; }
+    }
+    __syncthreads();
+    float* out = a.lvl_out[l] + lvl_off;
+    for (int idx = tid; idx < a.CH * PT; idx += nthr) {
+      const int ch2 = idx / PT, p2 = idx - ch2 * PT;
+      if (p2 < npix) out[(size_t)ch2 * hw + p2] = s_rows[ch2 * S + p2];
+    }
+  }
+}
+
+// Measured at B = 64 (tools/heads_once.py): whole rows win for narrow heads (A*C = 12: 23.2 -> 18.1 us — the 32 x 32 tiles
+// are 5/8 empty there) and lose for wide ones (243: 179 -> 296 us, 96: 90 -> 132 us: more index arithmetic per element
+// than the tile kernel, which is what bounds both), so only heads narrower than a tile take them.
+static int head_rows_pt(int CH) { return CH < kHeadTile ? 256 : 0; }
+
+static int head_pack_plan(HeadPackArgs* a, const int* hw, int n_levels, int B, int CH, int PT) {
   TAUV_REQUIRE(hw, TAUV_E_NULL, "pointers must not be NULL");
   TAUV_REQUIRE(n_levels > 0 && n_levels <= kHeadLevels, TAUV_E_UNSUPPORTED, "n_levels=%d outside 1..%d", n_levels, kHeadLevels);
   TAUV_REQUIRE(B > 0 && B <= 65535 && CH > 0, TAUV_E_SHAPE, "bad shape B=%d CH=%d", B, CH);
@@ -92,7 +152,8 @@ static int head_pack_plan(HeadPackArgs* a, const int* hw, int n_levels, int B, i
     a->row_base[l] = (int)rows;
     a->tile_base[l] = (int)tiles;
     rows += hw[l];
-    tiles += (long long)((hw[l] + kHeadTile - 1) / kHeadTile) * ((CH + kHeadTile - 1) / kHeadTile);
+    tiles += PT ? (long long)((hw[l] + PT - 1) / PT)
+                : (long long)((hw[l] + kHeadTile - 1) / kHeadTile) * ((CH + kHeadTile - 1) / kHeadTile);
   }
   TAUV_REQUIRE(rows * CH < (1LL << 31) && tiles < (1LL << 31), TAUV_E_UNSUPPORTED, "level sizes too large");
   a->tile_base[n_levels] = (int)tiles;
@@ -110,14 +171,21 @@ extern "C" int tauv_yolact_pack_heads(const float* const* levels, const int* hw,
                                       int tanh_act, float* packed, tauv_stream_t stream) {
   TAUV_REQUIRE(levels && packed, TAUV_E_NULL, "pointers must not be NULL");
   HeadPackArgs a{};
-  if (int rc = head_pack_plan(&a, hw, n_levels, B, CH)) return rc;
+  const int PT = CH > 0 ? head_rows_pt(CH) : 0;
+  if (int rc = head_pack_plan(&a, hw, n_levels, B, CH, PT)) return rc;
   for (int l = 0; l < n_levels; ++l) {
     TAUV_REQUIRE(levels[l], TAUV_E_NULL, "level %d is NULL", l);
     a.lvl_in[l] = levels[l];
   }
   a.tanh_act = tanh_act;
   a.packed = packed;
-  head_pack_kernel<false><<<dim3(a.tile_base[n_levels], B), kHeadTile * 8, 0, (cudaStream_t)stream>>>(a);
+  if (PT) {
+    const size_t smem = (size_t)CH * (PT + 1) * sizeof(float);
+    if (smem > 48 * 1024) TAUV_CUDA(ensure_dynamic_smem((const void*)head_pack_rows_kernel<false>, smem));
+    head_pack_rows_kernel<false><<<dim3(a.tile_base[n_levels], B), kHeadTile * 8, smem, (cudaStream_t)stream>>>(a, PT);
+  } else {
+    head_pack_kernel<false><<<dim3(a.tile_base[n_levels], B), kHeadTile * 8, 0, (cudaStream_t)stream>>>(a);
+  }
   TAUV_LAUNCH_CHECK("head_pack_kernel<forward>");
   return 0;
 }
@@ -127,7 +195,8 @@ extern "C" int tauv_yolact_pack_heads_backward(const float* grad_packed, const f
                                                tauv_stream_t stream) {
   TAUV_REQUIRE(grad_packed && grad_levels && (!tanh_act || y_packed), TAUV_E_NULL, "pointers must not be NULL");
   HeadPackArgs a{};
-  if (int rc = head_pack_plan(&a, hw, n_levels, B, CH)) return rc;
+  const int PT = CH > 0 ? head_rows_pt(CH) : 0;
+  if (int rc = head_pack_plan(&a, hw, n_levels, B, CH, PT)) return rc;
   for (int l = 0; l < n_levels; ++l) {
     TAUV_REQUIRE(grad_levels[l], TAUV_E_NULL, "level %d is NULL", l);
     a.lvl_out[l] = grad_levels[l];
@@ -135,7 +204,13 @@ extern "C" int tauv_yolact_pack_heads_backward(const float* grad_packed, const f
   a.tanh_act = tanh_act;
   a.grad_packed = grad_packed;
   a.y_packed = y_packed;
-  head_pack_kernel<true><<<dim3(a.tile_base[n_levels], B), kHeadTile * 8, 0, (cudaStream_t)stream>>>(a);
+  if (PT) {
+    const size_t smem = (size_t)CH * (PT + 1) * sizeof(float);
+    if (smem > 48 * 1024) TAUV_CUDA(ensure_dynamic_smem((const void*)head_pack_rows_kernel<true>, smem));
+    head_pack_rows_kernel<true><<<dim3(a.tile_base[n_levels], B), kHeadTile * 8, smem, (cudaStream_t)stream>>>(a, PT);
+  } else {
+    head_pack_kernel<true><<<dim3(a.tile_base[n_levels], B), kHeadTile * 8, 0, (cudaStream_t)stream>>>(a);
+  }
   TAUV_LAUNCH_CHECK("head_pack_kernel<backward>");
   return 0;
 }
