@@ -514,7 +514,9 @@ __global__ void ymask_area_finish_kernel(double* tsum, int n) {
   if (t < n) tsum[t] = (double)reinterpret_cast<const unsigned long long*>(tsum)[t] / kAreaScale;
 }
 
-template <bool BACKWARD>
+// (FULLK: K == 32, the YOLACT head — the per-channel `k < K` tests of the unrolled loops cost an ISETP each per pixel,
+// there are only seven predicate registers to keep them in)
+template <bool BACKWARD, bool FULLK>
 __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_positive_kernel(const MaskLossArgs a) {
   __shared__ float s_coeff[kMaskLossMaxK];
   __shared__ double s_red[kMaskLossThreads / 32];
@@ -552,10 +554,10 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_positive_kernel(con
           if (w != 0.0f) {
             float pv[kMaskLossMaxK];   // (all K loads in flight before the first use: the loop is latency-bound)
 #pragma unroll
-            for (int k = 0; k < kMaskLossMaxK; ++k) pv[k] = k < a.K ? proto[(size_t)k * HW + px] : 0.0f;
+            for (int k = 0; k < kMaskLossMaxK; ++k) pv[k] = (FULLK || k < a.K) ? proto[(size_t)k * HW + px] : 0.0f;
             float logit = 0.0f;
 #pragma unroll
-            for (int k = 0; k < kMaskLossMaxK; ++k) logit += k < a.K ? s_coeff[k] * pv[k] : 0.0f;   // loss.py:82
+            for (int k = 0; k < kMaskLossMaxK; ++k) logit += s_coeff[k] * pv[k];   // loss.py:82 (s_coeff and pv are zero beyond K)
             const float m = clamp_unit(fmaxf(sigmoid_ref(logit), 1e-4f)), tc = clamp_unit(mask_truth(g, seg, j));  // :83-84, :97-98
             num += (double)(w * -(tc * logf(m) + (1.0f - tc) * logf(1.0f - m)));               // :96-100, :113
           }
@@ -579,18 +581,18 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_positive_kernel(con
           float logit = 0.0f;
           float pv[16];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) pv[k] = k < a.K ? proto[(size_t)k * HW + px] : 0.0f;
+          for (int k = 0; k < 16; ++k) pv[k] = (FULLK || k < a.K) ? proto[(size_t)k * HW + px] : 0.0f;
 #pragma unroll
           for (int k = 0; k < 16; ++k) logit += s_coeff[k] * pv[k];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) pv[k] = 16 + k < a.K ? proto[(size_t)(16 + k) * HW + px] : 0.0f;
+          for (int k = 0; k < 16; ++k) pv[k] = (FULLK || 16 + k < a.K) ? proto[(size_t)(16 + k) * HW + px] : 0.0f;
 #pragma unroll
           for (int k = 0; k < 16; ++k) logit += s_coeff[16 + k] * pv[k];
           const float dl = G * mask_dlogit(logit, mask_truth(g, seg, j), w);
 #pragma unroll
           for (int k = 0; k < 16; ++k) gc[16 + k] += dl * pv[k];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) gc[k] += dl * (k < a.K ? proto[(size_t)k * HW + px] : 0.0f);
+          for (int k = 0; k < 16; ++k) gc[k] += dl * ((FULLK || k < a.K) ? proto[(size_t)k * HW + px] : 0.0f);
         }
       }
       // K sums over the CTA: warp shuffles, then the eight warps' values in a fixed order
@@ -621,7 +623,8 @@ struct MaskPosRec {
 };
 constexpr int kMaskRecChunk = 64;
 
-__global__ void __launch_bounds__(kMaskLossThreads) ymask_backward_proto_kernel(const MaskLossArgs a) {
+template <bool FULLK>
+__global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_backward_proto_kernel(const MaskLossArgs a) {
   __shared__ MaskPosRec s_rec[kMaskRecChunk];
   __shared__ float s_cf[kMaskRecChunk][kMaskLossMaxK];   // the chunk's coefficient rows
   const int b = blockIdx.y;
@@ -636,7 +639,7 @@ __global__ void __launch_bounds__(kMaskLossThreads) ymask_backward_proto_kernel(
   float pv[kMaskLossMaxK], gp[kMaskLossMaxK];
 #pragma unroll
   for (int k = 0; k < kMaskLossMaxK; ++k) {
-    pv[k] = (live && k < a.K) ? proto[(size_t)k * HW + px] : 0.0f;
+    pv[k] = (live && (FULLK || k < a.K)) ? proto[(size_t)k * HW + px] : 0.0f;
     gp[k] = 0.0f;
   }
   const int y = live ? px / a.PW : 0, x = live ? px - y * a.PW : 0;
@@ -675,9 +678,9 @@ __global__ void __launch_bounds__(kMaskLossThreads) ymask_backward_proto_kernel(
     }
     __syncthreads();
     const int nr = s_kept[0] + s_kept[1];
-    for (int e = threadIdx.x; e < nr * a.K; e += kMaskLossThreads) {
-      const int r = e / a.K, k = e - r * a.K;
-      s_cf[r][k] = a.coeff[((size_t)b * a.N + s_rec[r].n) * a.K + k];
+    for (int e = threadIdx.x; e < nr * kMaskLossMaxK; e += kMaskLossThreads) {
+      const int r = e / kMaskLossMaxK, k = e - r * kMaskLossMaxK;
+      s_cf[r][k] = k < a.K ? a.coeff[((size_t)b * a.N + s_rec[r].n) * a.K + k] : 0.0f;   // (zero beyond K)
     }
     __syncthreads();
     for (int r = 0; r < nr && live; ++r) {
@@ -687,21 +690,21 @@ __global__ void __launch_bounds__(kMaskLossThreads) ymask_backward_proto_kernel(
       float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
 #pragma unroll
       for (int k = 0; k < kMaskLossMaxK; k += 4) {
-        if (k < a.K) l0 += cf[k] * pv[k];
-        if (k + 1 < a.K) l1 += cf[k + 1] * pv[k + 1];
-        if (k + 2 < a.K) l2 += cf[k + 2] * pv[k + 2];
-        if (k + 3 < a.K) l3 += cf[k + 3] * pv[k + 3];
+        l0 += cf[k] * pv[k];   // (cf and pv are zero beyond K)
+        l1 += cf[k + 1] * pv[k + 1];
+        l2 += cf[k + 2] * pv[k + 2];
+        l3 += cf[k + 3] * pv[k + 3];
       }
       const float dl = rec.G * mask_dlogit((l0 + l1) + (l2 + l3), mask_truth_taps(g, s00, s01, s10, s11, rec.j), g.valid);
 #pragma unroll
       for (int k = 0; k < kMaskLossMaxK; ++k)
-        if (k < a.K) gp[k] += dl * cf[k];
+        if (FULLK || k < a.K) gp[k] += dl * cf[k];
     }
   }
   if (live) {
 #pragma unroll
     for (int k = 0; k < kMaskLossMaxK; ++k)
-      if (k < a.K) a.grad_proto[((size_t)b * a.K + k) * HW + px] = gp[k];
+      if (FULLK || k < a.K) a.grad_proto[((size_t)b * a.K + k) * HW + px] = gp[k];
   }
 }
 
@@ -806,7 +809,8 @@ extern "C" int tauv_yolact_mask_loss(const float* coeff, const float* proto, con
   TAUV_LAUNCH_CHECK("ymask_area_kernel");
   ymask_area_finish_kernel<<<(B * M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(tsum, B * M);
   TAUV_LAUNCH_CHECK("ymask_area_finish_kernel");
-  ymask_positive_kernel<false><<<dim3(kMaskLossWalkers, B), kMaskLossThreads, 0, (cudaStream_t)stream>>>(a);
+  if (K == kMaskLossMaxK) ymask_positive_kernel<false, true><<<dim3(kMaskLossWalkers, B), kMaskLossThreads, 0, (cudaStream_t)stream>>>(a);
+  else ymask_positive_kernel<false, false><<<dim3(kMaskLossWalkers, B), kMaskLossThreads, 0, (cudaStream_t)stream>>>(a);
   TAUV_LAUNCH_CHECK("ymask_positive_kernel<forward>");
   return 0;
 }
@@ -824,12 +828,14 @@ extern "C" int tauv_yolact_mask_loss_backward(const float* coeff, const float* p
   TAUV_REQUIRE(n_pos_total && grad_out, TAUV_E_NULL, "pointers must not be NULL");
   if (grad_coeff) {
     TAUV_CUDA(cudaMemsetAsync(grad_coeff, 0, (size_t)B * N * K * sizeof(float), (cudaStream_t)stream));
-    ymask_positive_kernel<true><<<dim3(kMaskLossWalkers, B), kMaskLossThreads, 0, (cudaStream_t)stream>>>(a);
+    if (K == kMaskLossMaxK) ymask_positive_kernel<true, true><<<dim3(kMaskLossWalkers, B), kMaskLossThreads, 0, (cudaStream_t)stream>>>(a);
+    else ymask_positive_kernel<true, false><<<dim3(kMaskLossWalkers, B), kMaskLossThreads, 0, (cudaStream_t)stream>>>(a);
     TAUV_LAUNCH_CHECK("ymask_positive_kernel<backward>");
   }
   if (grad_proto) {
-    ymask_backward_proto_kernel<<<dim3((PH * PW + kMaskLossThreads - 1) / kMaskLossThreads, B), kMaskLossThreads, 0,
-                                  (cudaStream_t)stream>>>(a);
+    const dim3 pgrid((PH * PW + kMaskLossThreads - 1) / kMaskLossThreads, B);
+    if (K == kMaskLossMaxK) ymask_backward_proto_kernel<true><<<pgrid, kMaskLossThreads, 0, (cudaStream_t)stream>>>(a);
+    else ymask_backward_proto_kernel<false><<<pgrid, kMaskLossThreads, 0, (cudaStream_t)stream>>>(a);
     TAUV_LAUNCH_CHECK("ymask_backward_proto_kernel");
   }
   return 0;
