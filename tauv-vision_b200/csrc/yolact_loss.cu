@@ -540,6 +540,7 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_positive_kernel(con
     const CropBounds crop = crop_bounds(make_float4(tb[0], tb[1], tb[2], tb[3]), a.PH, a.PW);
     const MaskBoxRange box = mask_box_range(crop, a.PH, a.PW);
     const int npx = box.bh * box.bw;
+    const int bwd = max(box.bw, 1), step_y = kMaskLossThreads / bwd, step_x = kMaskLossThreads - step_y * bwd;
     const double area = a.tsum[(size_t)b * a.M + j];
     __syncthreads();
     if (tid < kMaskLossMaxK) s_coeff[tid] = tid < a.K ? a.coeff[((size_t)b * a.N + n) * a.K + tid] : 0.0f;
@@ -547,8 +548,10 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_positive_kernel(con
     if (!BACKWARD) {
       double num = 0.0;
       if (area > 0.0) {   // loss.py:93-94
-        for (int q = tid; q < npx; q += kMaskLossThreads) {
-          const int y = box.y0 + q / box.bw, x = box.x0 + q % box.bw, px = y * a.PW + x;
+        int ry = tid / bwd, rx = tid - ry * bwd;   // (the pixel's row and column inside the box, kept incrementally)
+        for (int q = tid; q < npx; q += kMaskLossThreads, ry += step_y, rx += step_x) {
+          if (rx >= bwd) { rx -= bwd; ++ry; }
+          const int y = box.y0 + ry, x = box.x0 + rx, px = y * a.PW + x;
           const MaskPx g = mask_px(a, b, y, x);
           const float w = mask_weight(g, crop);
           if (w != 0.0f) {
@@ -571,8 +574,10 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_positive_kernel(con
       for (int k = 0; k < kMaskLossMaxK; ++k) gc[k] = 0.0f;
       if (area > 0.0) {
         const float G = __fdiv_rn(gscale, (float)area);
-        for (int q = tid; q < npx; q += kMaskLossThreads) {
-          const int y = box.y0 + q / box.bw, x = box.x0 + q % box.bw, px = y * a.PW + x;
+        int ry = tid / bwd, rx = tid - ry * bwd;
+        for (int q = tid; q < npx; q += kMaskLossThreads, ry += step_y, rx += step_x) {
+          if (rx >= bwd) { rx -= bwd; ++ry; }
+          const int y = box.y0 + ry, x = box.x0 + rx, px = y * a.PW + x;
           const MaskPx g = mask_px(a, b, y, x);
           const float w = mask_weight(g, crop);
           if (w == 0.0f) continue;
