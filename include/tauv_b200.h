@@ -435,15 +435,18 @@ int tauv_yolact_class_box_loss_backward(const float* cls, const float* enc, cons
  *   coeff [B,N,K] f32 (K <= 32), proto [B,K,PH,PW] f32, match_index [B,N] i64, truth_box [B,M,4] f32,
  *   seg [B,SH,SW] i32 (truth index per pixel), img_valid [B,SH,SW] u8 ->
  *   tsum [B,M] f64 (area of every truth's resized mask; kept for the backward),
+ *   records [tauv_yolact_mask_loss_records_bytes(B, N)] bytes, 16-byte aligned (one 32-byte record per listed positive:
+ *   crop box, area, prior, truth — gathered once per call; kept for the backward),
  *   partial [B, tauv_yolact_mask_loss_partials()] f64 whose sum is the sum over positives of (weighted BCE / area),
  *   positives with an empty resized truth mask skipped (loss.py:93-94).  The caller divides by the batch's positives
  *   (loss.py:117-120).  Deterministic. */
 int tauv_yolact_mask_loss_partials(void);
+size_t tauv_yolact_mask_loss_records_bytes(int B, int N);
 int tauv_yolact_mask_loss(const float* coeff, const float* proto, const int32_t* pos_list,
                           const int64_t* n_pos, const int64_t* match_index, const float* truth_box,
                           const int32_t* seg, const uint8_t* img_valid, int B, int N, int K, int M,
-                          int PH, int PW, int SH, int SW, double* tsum, double* partial,
-                          tauv_stream_t stream);
+                          int PH, int PW, int SH, int SW, double* tsum, void* records,
+                          double* partial, tauv_stream_t stream);
 
 /* Backward of the mask term: grad_coeff [B,N,K] (zero outside the positives) and grad_proto [B,K,PH,PW]; either may be
  * NULL.  n_pos_total [1] i64 and grad_out [1] f32 on the device.  No atomics: deterministic. */
@@ -451,7 +454,8 @@ int tauv_yolact_mask_loss_backward(const float* coeff, const float* proto, const
                                    const int64_t* n_pos, const int64_t* match_index,
                                    const float* truth_box, const int32_t* seg,
                                    const uint8_t* img_valid, int B, int N, int K, int M, int PH, int PW,
-                                   int SH, int SW, const double* tsum, const int64_t* n_pos_total,
+                                   int SH, int SW, const double* tsum, const void* records,
+                                   const int64_t* n_pos_total,
                                    const float* grad_out, float* grad_coeff, float* grad_proto,
                                    tauv_stream_t stream);
 

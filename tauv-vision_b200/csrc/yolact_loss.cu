@@ -367,6 +367,16 @@ static int loss_tile_grid(long long rows) {
 constexpr int kMaskLossThreads = 256;
 constexpr int kMaskLossMaxK = 32;
 
+// What the walks need to know about a positive, gathered once per call: reaching it through pos_list -> match_index ->
+// truth_box / area is a chain of four dependent loads (~2.5 us) that every CTA paid per positive (the per-pixel proto
+// backward: per chunk of positives, with two CTAs resident per SM — most of its time).
+struct __align__(16) MaskRec {
+  float left, right, top, bottom;   // crop_bounds of the matched truth's box on the prototype grid
+  float area;                       // of the truth's resized mask (0: the positive is skipped, loss.py:93-94)
+  int n, j;                         // prior, truth
+  int pad;
+};
+
 struct MaskLossArgs {
   const float* coeff;          // [B,N,K]
   const float* proto;          // [B,K,PH,PW]
@@ -379,6 +389,7 @@ struct MaskLossArgs {
   int N, K, M, PH, PW, SH, SW;
   float sy, sx;                // (float)SH / PH, (float)SW / PW: ATen's area_pixel_compute_scale without align_corners
   double* tsum;                // [B,M]: area of every truth's resized mask (u64 fixed point while ymask_area_kernel adds)
+  struct MaskRec* recs;        // [B,N]: one record per listed positive (ymask_records_kernel), first n_pos[b] entries
   double* partial;             // [B,gridDim.x] (forward)
   const float* grad_out;       // [1] (backward)
   const int64_t* n_pos_total;  // [1] (backward)
@@ -514,6 +525,17 @@ __global__ void ymask_area_finish_kernel(double* tsum, int n) {
   if (t < n) tsum[t] = (double)reinterpret_cast<const unsigned long long*>(tsum)[t] / kAreaScale;
 }
 
+__global__ void __launch_bounds__(256) ymask_records_kernel(const MaskLossArgs a) {
+  const int b = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= (int)a.n_pos[b]) return;
+  const int n = a.pos_list[(size_t)b * a.N + i];
+  long long jl = a.match_index[(size_t)b * a.N + n];
+  const int j = (int)(jl < 0 ? 0 : (jl >= a.M ? a.M - 1 : jl));
+  const float* tb = a.truth_box + ((size_t)b * a.M + j) * 4;
+  const CropBounds c = crop_bounds(make_float4(tb[0], tb[1], tb[2], tb[3]), a.PH, a.PW);
+  a.recs[(size_t)b * a.N + i] = MaskRec{c.left, c.right, c.top, c.bottom, (float)a.tsum[(size_t)b * a.M + j], n, j, 0};
+}
+
 // (FULLK: K == 32, the YOLACT head — the per-channel `k < K` tests of the unrolled loops cost an ISETP each per pixel,
 // there are only seven predicate registers to keep them in)
 template <bool BACKWARD, bool FULLK>
@@ -533,21 +555,19 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_positive_kernel(con
     gscale = P > 0 ? __fdiv_rn(*a.grad_out, (float)P) : *a.grad_out;   // loss.py:117-120
   }
   for (int i = blockIdx.x; i < npos; i += gridDim.x) {
-    const int n = a.pos_list[(size_t)b * a.N + i];
-    long long jl = a.match_index[(size_t)b * a.N + n];
-    const int j = (int)(jl < 0 ? 0 : (jl >= a.M ? a.M - 1 : jl));
-    const float* tb = a.truth_box + ((size_t)b * a.M + j) * 4;
-    const CropBounds crop = crop_bounds(make_float4(tb[0], tb[1], tb[2], tb[3]), a.PH, a.PW);
+    const MaskRec rec = a.recs[(size_t)b * a.N + i];
+    const int n = rec.n, j = rec.j;
+    const CropBounds crop{rec.left, rec.right, rec.top, rec.bottom};
     const MaskBoxRange box = mask_box_range(crop, a.PH, a.PW);
     const int npx = box.bh * box.bw;
     const int bwd = max(box.bw, 1), step_y = kMaskLossThreads / bwd, step_x = kMaskLossThreads - step_y * bwd;
-    const double area = a.tsum[(size_t)b * a.M + j];
+    const float area = rec.area;
     __syncthreads();
     if (tid < kMaskLossMaxK) s_coeff[tid] = tid < a.K ? a.coeff[((size_t)b * a.N + n) * a.K + tid] : 0.0f;
     __syncthreads();
     if (!BACKWARD) {
       double num = 0.0;
-      if (area > 0.0) {   // loss.py:93-94
+      if (area > 0.0f) {   // loss.py:93-94
         int ry = tid / bwd, rx = tid - ry * bwd;   // (the pixel's row and column inside the box, kept incrementally)
         for (int q = tid; q < npx; q += kMaskLossThreads, ry += step_y, rx += step_x) {
           if (rx >= bwd) { rx -= bwd; ++ry; }
@@ -567,13 +587,13 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_positive_kernel(con
         }
       }
       num = mask_block_sum(num, s_red);
-      if (area > 0.0) cta_sum += num / area;   // :113
+      if (area > 0.0f) cta_sum += num / (double)area;   // :113
     } else {
       float gc[kMaskLossMaxK];
 #pragma unroll
       for (int k = 0; k < kMaskLossMaxK; ++k) gc[k] = 0.0f;
-      if (area > 0.0) {
-        const float G = __fdiv_rn(gscale, (float)area);
+      if (area > 0.0f) {
+        const float G = __fdiv_rn(gscale, area);
         int ry = tid / bwd, rx = tid - ry * bwd;
         for (int q = tid; q < npx; q += kMaskLossThreads, ry += step_y, rx += step_x) {
           if (rx >= bwd) { rx -= bwd; ++ry; }
@@ -666,13 +686,8 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_backward_proto_kern
       MaskPosRec rec{};
       bool keep = false;
       if (i0 + r < npos) {
-        const int n = a.pos_list[(size_t)b * a.N + i0 + r];
-        long long jl = a.match_index[(size_t)b * a.N + n];
-        const int j = (int)(jl < 0 ? 0 : (jl >= a.M ? a.M - 1 : jl));
-        const float* tb = a.truth_box + ((size_t)b * a.M + j) * 4;
-        const CropBounds c = crop_bounds(make_float4(tb[0], tb[1], tb[2], tb[3]), a.PH, a.PW);
-        const double area = a.tsum[(size_t)b * a.M + j];
-        rec = MaskPosRec{c.left, c.right, c.top, c.bottom, area > 0.0 ? __fdiv_rn(gscale, (float)area) : 0.0f, n, j};
+        const MaskRec c = a.recs[(size_t)b * a.N + i0 + r];
+        rec = MaskPosRec{c.left, c.right, c.top, c.bottom, c.area > 0.0f ? __fdiv_rn(gscale, c.area) : 0.0f, c.n, c.j};
         keep = rec.G != 0.0f && c.bottom >= fy_lo && c.top <= fy_hi && c.right >= fx_lo && c.left <= fx_hi;  // (false for NaN)
       }
       const unsigned bal = __ballot_sync(0xffffffffu, keep);
@@ -787,8 +802,10 @@ extern "C" int tauv_yolact_class_box_loss_backward(const float* cls, const float
 }
 
 static int mask_loss_check(const MaskLossArgs& a, int B) {
-  TAUV_REQUIRE(a.coeff && a.proto && a.pos_list && a.n_pos && a.match_index && a.truth_box && a.seg && a.img_valid && a.tsum,
+  TAUV_REQUIRE(a.coeff && a.proto && a.pos_list && a.n_pos && a.match_index && a.truth_box && a.seg && a.img_valid && a.tsum &&
+                   a.recs,
                TAUV_E_NULL, "pointers must not be NULL");
+  TAUV_REQUIRE((uintptr_t)a.recs % 16 == 0, TAUV_E_ALIGN, "records must be 16-byte aligned");
   TAUV_REQUIRE(B > 0 && a.N > 0 && a.K > 0 && a.M > 0 && a.PH > 0 && a.PW > 0 && a.SH > 0 && a.SW > 0, TAUV_E_SHAPE,
                "bad shape B=%d N=%d K=%d M=%d proto %dx%d seg %dx%d", B, a.N, a.K, a.M, a.PH, a.PW, a.SH, a.SW);
   TAUV_REQUIRE(a.K <= kMaskLossMaxK, TAUV_E_UNSUPPORTED, "K=%d exceeds the built-in limit %d", a.K, kMaskLossMaxK);
@@ -797,13 +814,16 @@ static int mask_loss_check(const MaskLossArgs& a, int B) {
 }
 
 extern "C" int tauv_yolact_mask_loss_partials(void) { return kMaskLossWalkers; }
+extern "C" size_t tauv_yolact_mask_loss_records_bytes(int B, int N) {
+  return B > 0 && N > 0 ? (size_t)B * N * sizeof(MaskRec) : 0;
+}
 
 extern "C" int tauv_yolact_mask_loss(const float* coeff, const float* proto, const int32_t* pos_list, const int64_t* n_pos,
                                      const int64_t* match_index, const float* truth_box, const int32_t* seg,
                                      const uint8_t* img_valid, int B, int N, int K, int M, int PH, int PW, int SH, int SW,
-                                     double* tsum, double* partial, tauv_stream_t stream) {
+                                     double* tsum, void* records, double* partial, tauv_stream_t stream) {
   MaskLossArgs a{coeff, proto, pos_list, n_pos, match_index, truth_box, seg, img_valid, N, K, M, PH, PW, SH, SW,
-                 PH > 0 ? (float)SH / (float)PH : 0.f, PW > 0 ? (float)SW / (float)PW : 0.f, tsum, partial,
+                 PH > 0 ? (float)SH / (float)PH : 0.f, PW > 0 ? (float)SW / (float)PW : 0.f, tsum, (MaskRec*)records, partial,
                  nullptr, nullptr, nullptr, nullptr};
   if (int rc = mask_loss_check(a, B)) return rc;
   TAUV_REQUIRE(partial, TAUV_E_NULL, "pointers must not be NULL");
@@ -814,6 +834,8 @@ extern "C" int tauv_yolact_mask_loss(const float* coeff, const float* proto, con
   TAUV_LAUNCH_CHECK("ymask_area_kernel");
   ymask_area_finish_kernel<<<(B * M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(tsum, B * M);
   TAUV_LAUNCH_CHECK("ymask_area_finish_kernel");
+  ymask_records_kernel<<<dim3((N + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(a);
+  TAUV_LAUNCH_CHECK("ymask_records_kernel");
   if (K == kMaskLossMaxK) ymask_positive_kernel<false, true><<<dim3(kMaskLossWalkers, B), kMaskLossThreads, 0, (cudaStream_t)stream>>>(a);
   else ymask_positive_kernel<false, false><<<dim3(kMaskLossWalkers, B), kMaskLossThreads, 0, (cudaStream_t)stream>>>(a);
   TAUV_LAUNCH_CHECK("ymask_positive_kernel<forward>");
@@ -824,11 +846,11 @@ extern "C" int tauv_yolact_mask_loss_backward(const float* coeff, const float* p
                                               const int64_t* n_pos, const int64_t* match_index, const float* truth_box,
                                               const int32_t* seg, const uint8_t* img_valid, int B, int N, int K, int M,
                                               int PH, int PW, int SH, int SW, const double* tsum,
-                                              const int64_t* n_pos_total, const float* grad_out, float* grad_coeff,
+                                              const void* records, const int64_t* n_pos_total, const float* grad_out, float* grad_coeff,
                                               float* grad_proto, tauv_stream_t stream) {
   MaskLossArgs a{coeff, proto, pos_list, n_pos, match_index, truth_box, seg, img_valid, N, K, M, PH, PW, SH, SW,
                  PH > 0 ? (float)SH / (float)PH : 0.f, PW > 0 ? (float)SW / (float)PW : 0.f, const_cast<double*>(tsum),
-                 nullptr, grad_out, n_pos_total, grad_coeff, grad_proto};
+                 (MaskRec*)const_cast<void*>(records), nullptr, grad_out, n_pos_total, grad_coeff, grad_proto};
   if (int rc = mask_loss_check(a, B)) return rc;
   TAUV_REQUIRE(n_pos_total && grad_out, TAUV_E_NULL, "pointers must not be NULL");
   if (grad_coeff) {

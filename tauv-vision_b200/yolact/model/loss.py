@@ -137,20 +137,21 @@ class _MaskLoss(torch.autograd.Function):
         lib = _lib.load()
         tsum = torch.empty((B, truth_box.shape[1]), dtype=torch.float64, device=dev)
         partial = torch.empty((B, lib.tauv_yolact_mask_loss_partials()), dtype=torch.float64, device=dev)
+        recs = torch.empty((lib.tauv_yolact_mask_loss_records_bytes(B, N),), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(lib.tauv_yolact_mask_loss(
                 _lib.fptr(coeff), _lib.fptr(proto), _lib.i32ptr(pos_list), _lib.i64ptr(n_pos), _lib.i64ptr(match_index),
                 _lib.fptr(truth_box), _lib.i32ptr(seg), _lib.u8ptr(img_valid), B, N, K, truth_box.shape[1], PH, PW, SH, SW,
-                _lib.dptr(tsum), _lib.dptr(partial), _lib.stream_ptr(dev)))
+                _lib.dptr(tsum), recs.data_ptr(), _lib.dptr(partial), _lib.stream_ptr(dev)))
         P = n_pos.sum().reshape(1)
         tot = partial.sum()
         out = torch.where(P[0] > 0, tot / P[0].clamp(min=1).to(torch.float64), tot).to(torch.float32)   # loss.py:117-120
-        ctx.save_for_backward(coeff, proto, pos_list, n_pos, match_index, truth_box, seg, img_valid, tsum, P)
+        ctx.save_for_backward(coeff, proto, pos_list, n_pos, match_index, truth_box, seg, img_valid, tsum, recs, P)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        coeff, proto, pos_list, n_pos, match_index, truth_box, seg, img_valid, tsum, P = ctx.saved_tensors
+        coeff, proto, pos_list, n_pos, match_index, truth_box, seg, img_valid, tsum, recs, P = ctx.saved_tensors
         dev = coeff.device
         B, N, K = coeff.shape
         PH, PW = proto.shape[-2:]
@@ -164,7 +165,7 @@ class _MaskLoss(torch.autograd.Function):
                 _lib.check(_lib.load().tauv_yolact_mask_loss_backward(
                     _lib.fptr(coeff), _lib.fptr(proto), _lib.i32ptr(pos_list), _lib.i64ptr(n_pos),
                     _lib.i64ptr(match_index), _lib.fptr(truth_box), _lib.i32ptr(seg), _lib.u8ptr(img_valid), B, N, K,
-                    truth_box.shape[1], PH, PW, SH, SW, _lib.dptr(tsum), _lib.i64ptr(P), _lib.fptr(go),
+                    truth_box.shape[1], PH, PW, SH, SW, _lib.dptr(tsum), recs.data_ptr(), _lib.i64ptr(P), _lib.fptr(go),
                     _lib.fptr(gc) if need_c else None, _lib.fptr(gp) if need_p else None, _lib.stream_ptr(dev)))
         return gc, gp, None, None, None, None, None, None
 
