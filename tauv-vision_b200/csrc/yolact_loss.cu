@@ -356,13 +356,15 @@ static int loss_tile_grid(long long rows) {
 // box_to_mask(truth_box_j) * nearest-resized img_valid_b, summed and divided by the resized truth mask's area; positives
 // whose resized truth mask is empty are skipped.  The reference loops over the positives in Python (~25 ATen kernels
 // and a [SH, SW] -> [PH, PW] F.interpolate each); here
-//   ymask_area_kernel           : the area of every truth's resized mask, once per (truth, frame) — positives share it;
+//   ymask_area_kernel           : the areas of all truths' resized masks in one pass per frame (fixed-point integer
+//                                 atomics: order-independent) — positives matched to one truth share them;
+//   ymask_records_kernel        : crop box, area, prior and truth of every listed positive, gathered once per call;
 //   ymask_positive_kernel<0>    : CTAs walk the frame's positives (pos_list of yloss_frame_kernel), threads the pixels
 //                                 of the truth box (the weight is zero outside it);
 //   ymask_positive_kernel<1>    : same walk, d/d coeff_i = sum over pixels of dlogit * proto (block reduction);
 //   ymask_backward_proto_kernel : a thread per pixel walks the frame's positives (records staged in shared memory) with
 //                                 the pixel's K prototype values in registers, d/d proto = sum over positives of
-//                                 dlogit * coeff_i — no atomics, so both gradients are deterministic.
+//                                 dlogit * coeff_i — no floating-point atomics, so both gradients are deterministic.
 // Inside the clamps d BCE / d logit = sigmoid - truth (F.binary_cross_entropy's backward times sigmoid'), outside 0.
 constexpr int kMaskLossThreads = 256;
 constexpr int kMaskLossMaxK = 32;
