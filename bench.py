@@ -606,6 +606,13 @@ def run_centernet(ctx):
                                          "algorithmic_bytes": bm_bytes, "achieved": bm_bytes / (t_bm * 1e-3) / 1e9,
                                          "frac": bm_bytes / (t_bm * 1e-3) / 1e9 / hbm_gbs,
                                          "how": "tauv_centernet_block_maxima alone, events, back to back"},
+                     "step": {"algorithmic_bytes": algorithmic_bytes_decode(B_PER_GPU) + algorithmic_bytes_encode(B_PER_GPU),
+                              "us": med_ms * 1e3 / K,
+                              "frac": (algorithmic_bytes_decode(B_PER_GPU) + algorithmic_bytes_encode(B_PER_GPU))
+                                      / (med_ms * 1e-3 / K) / 1e9 / hbm_gbs,
+                              "how": "decode + encode bytes over the whole timed step (median block / steps): the "
+                                     "write-back of the encode's dirty lines is paid inside the decode, so the step "
+                                     "as a whole is the bandwidth figure that does not depend on which launch pays it"},
                      "note": "frac is the whole decode call (both launches) inside the timed steps, where it follows the "
                              "target encode and streams while that kernel's dirty L2 lines (up to 126 MB) are written "
                              "back; isolated = the call back to back with itself"},
