@@ -301,7 +301,14 @@ __global__ void __launch_bounds__(kLossTileWarps * 32) ycls_backward_kernel(
     const bool sel = lane < nrows && selected[row0 + lane] != 0;
     float* dst = grad + row0 * C1;
     if (!__any_sync(0xffffffffu, sel)) {  // (all but a few per cent of the blocks)
-      for (int e = lane; e < n_el; e += 32) dst[e] = 0.0f;
+      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {   // 128-bit stores: a quarter of the instructions
+        const int n16 = n_el >> 2;
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int q = lane; q < n16; q += 32) d4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = (n16 << 2) + lane; e < n_el; e += 32) dst[e] = 0.0f;
+      } else {
+        for (int e = lane; e < n_el; e += 32) dst[e] = 0.0f;
+      }
       continue;
     }
     const int t = sel ? loss_target_class(positive, match_index, truth_cls, row0 + lane, N, M, C1) : 0;
