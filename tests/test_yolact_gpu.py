@@ -635,3 +635,28 @@ def test_pack_heads_full_size_vs_oracle(yl):
             assert_close(got, want, rtol=1e-6, atol=1e-7, what="tanh")
         else:
             assert_equal(got, want, f"C = {C}")
+
+
+def test_loss_is_run_to_run_identical(yl):
+    """No floating-point atomics anywhere in the loss: two runs of loss() + backward on the same inputs give bit-identical
+    values and gradients (fixed summation orders, fixed-point area sums, ordered compactions)."""
+    d = yl.dev
+    g = synth.gen(123)
+    B, N, C1, K, M, PH, PW, SH, SW = 4, 3000, 21, 32, 6, 69, 69, 200, 200
+    anchor = torch.cat((torch.rand((1, N, 2), generator=g) * 0.8 + 0.1, torch.rand((1, N, 2), generator=g) * 0.3 + 0.05), -1).to(d)
+    tb, tv = synth.truth_boxes(B, M, seed=124)
+    tb[:, :3] = anchor[0, torch.randint(0, N, (B, 3), generator=g)].cpu()
+    tv[:, :3] = True
+    truth = (tv.to(d), torch.randint(1, C1, (B, M), generator=g).to(d), tb.to(d),
+             torch.randint(0, M, (B, SH, SW), generator=g).to(d), (torch.rand((B, SH, SW), generator=g) < 0.9).to(d))
+    base = [torch.randn((B, N, C1), generator=g), torch.randn((B, N, 4), generator=g), torch.randn((B, N, K), generator=g),
+            torch.randn((B, K, PH, PW), generator=g)]
+    runs = []
+    for _ in range(2):
+        xs = [x.to(d).requires_grad_() for x in base]
+        total, parts = yl.loss.loss((xs[0], xs[1], xs[2], anchor, xs[3]), truth, CFG)
+        total.backward()
+        runs.append([total.detach(), *[p.detach() for p in parts], *[x.grad for x in xs]])
+    assert float(runs[0][3]) > 0 and float(runs[0][1]) > 0
+    for a_, b_ in zip(*runs):
+        assert torch.equal(a_, b_)
