@@ -461,6 +461,26 @@ def run_centernet(ctx):
     torch.cuda.synchronize()
     t_dec_iso = e0.elapsed_time(e1) / K
 
+    # the same call on SMOOTH maps (box-filtered noise, 9 x 9 twice: ~1 % of the cells are peaks and the hot regions span
+    # many blocks — what a trained head emits), back to back: the data-dependent half of the decode, for the record
+    g_s = torch.Generator(device=device)
+    g_s.manual_seed(99 + rank)
+    sm = torch.randn((B_PER_GPU, C, H + 16, W + 16), device=device, generator=g_s)
+    for _ in range(2):
+        sm = torch.nn.functional.avg_pool2d(sm, 9, 1)
+    sm = ((sm - sm.mean()) / sm.std() * 1.5 - 2.2).contiguous()
+    pred_s = SimpleNamespace(heatmap=sm, size=size, offset=offset, depth=None)
+    for _ in range(3):
+        D.decode_packed(pred_s, mc, K_DET, THR, out=det_buf)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(20):
+        D.decode_packed(pred_s, mc, K_DET, THR, out=det_buf)
+    e1.record()
+    torch.cuda.synchronize()
+    t_dec_smooth = e0.elapsed_time(e1) / 20
+    del sm, pred_s
+
     # the dominant kernel alone (launch 1 of the decode's 2): the block maxima of the batch, back to back
     from tauv_vision_b200 import _lib
     lib_ = __import__("tauv_vision_b200").load_library()
@@ -532,6 +552,9 @@ def run_centernet(ctx):
     bm_bytes = 4 * B_PER_GPU * C * H * W + 4 * B_PER_GPU * (n_blk + (n_blk + 31) // 32)
     kernels = {
         "decode_us": t_dec * 1e3, "decode_isolated_us": t_dec_iso * 1e3,
+        "decode_smooth_maps_us": t_dec_smooth * 1e3,
+        "decode_smooth_maps_note": "the decode back to back on box-filtered noise (9 x 9, twice): hot regions that span "
+                                   "many blocks, as a trained head emits; rank 0's figure",
         "gaussian_encode_us": t_enc * 1e3,
         "gaussian_encode_gbs": algorithmic_bytes_encode(B_PER_GPU) / (t_enc * 1e-3) / 1e9,
         "gaussian_encode_frac": algorithmic_bytes_encode(B_PER_GPU) / (t_enc * 1e-3) / 1e9 / hbm_gbs,
