@@ -459,6 +459,14 @@ int tauv_yolact_mask_loss_backward(const float* coeff, const float* proto, const
                                    const float* grad_out, float* grad_coeff, float* grad_proto,
                                    tauv_stream_t stream);
 
+/* Normalisation of the loss terms — yolact/model/loss.py:54-57, :70-73, :117-120 — from the per-frame sums of
+ * tauv_yolact_class_box_loss (sums [B,2], may be NULL) and / or the partial sums of tauv_yolact_mask_loss (mask_partial
+ * [n_partial], may be NULL): losses[0] = class term, losses[1] = box term, losses[2] = mask term (only the ones whose
+ * input is given are written), n_pos_total [1] = the batch's positives P (may be NULL).  One small launch, fixed order. */
+int tauv_yolact_loss_reduce(const double* sums, const int64_t* n_pos, int B, int ratio,
+                            const double* mask_partial, int n_partial, float* losses,
+                            int64_t* n_pos_total, tauv_stream_t stream);
+
 /* Prediction-head outputs packed into the consumers' layout — yolact/model/prediction_head.py:111-113, :122-124,
  * :137-140 (permute(0, 2, 3, 1).reshape(B, -1, C), tanh for the mask coefficients) and model.py:55-58 (torch.cat over
  * the FPN levels): levels[l] [B,CH,H_l,W_l] f32 NCHW (CH = A * C; host array of n_levels <= 8 device pointers),

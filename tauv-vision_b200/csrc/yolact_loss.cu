@@ -737,6 +737,52 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_backward_proto_kern
   }
 }
 
+// The normalisation of the three terms (loss.py:54-57, :70-73, :117-120) in one small launch: P = the batch's positives;
+// class term = sum / ((1 + ratio) P), box and mask terms = sum / P, undivided when P == 0.  Fixed summation order.
+__global__ void __launch_bounds__(256) yloss_reduce_kernel(const double* __restrict__ sums, const int64_t* __restrict__ n_pos,
+                                                           int B, int ratio, const double* __restrict__ mask_partial,
+                                                           int n_partial, float* __restrict__ losses,
+                                                           int64_t* __restrict__ n_pos_total) {
+  __shared__ double s_v[3][256];
+  __shared__ long long s_p[256];
+  const int tid = threadIdx.x;
+  double c = 0.0, bx = 0.0, mk = 0.0;
+  long long P = 0;
+  for (int i = tid; i < B; i += 256) {
+    P += n_pos[i];
+    if (sums) {
+      c += sums[2 * i];
+      bx += sums[2 * i + 1];
+    }
+  }
+  if (mask_partial)
+    for (int i = tid; i < n_partial; i += 256) mk += mask_partial[i];
+  s_v[0][tid] = c;
+  s_v[1][tid] = bx;
+  s_v[2][tid] = mk;
+  s_p[tid] = P;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) {
+      s_v[0][tid] += s_v[0][tid + o];
+      s_v[1][tid] += s_v[1][tid + o];
+      s_v[2][tid] += s_v[2][tid + o];
+      s_p[tid] += s_p[tid + o];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const long long Pt = s_p[0];
+    const double d = Pt > 0 ? (double)Pt : 1.0;
+    if (n_pos_total) *n_pos_total = Pt;
+    if (sums) {
+      losses[0] = (float)(Pt > 0 ? s_v[0][0] / ((1.0 + ratio) * d) : s_v[0][0]);
+      losses[1] = (float)(Pt > 0 ? s_v[1][0] / d : s_v[1][0]);
+    }
+    if (mask_partial) losses[2] = (float)(Pt > 0 ? s_v[2][0] / d : s_v[2][0]);
+  }
+}
+
 constexpr int kMaskLossWalkers = 32;  // CTAs that share a frame's positives
 
 }  // namespace tauv
@@ -874,5 +920,15 @@ extern "C" int tauv_yolact_mask_loss_backward(const float* coeff, const float* p
     else ymask_backward_proto_kernel<false><<<pgrid, kMaskLossThreads, 0, (cudaStream_t)stream>>>(a);
     TAUV_LAUNCH_CHECK("ymask_backward_proto_kernel");
   }
+  return 0;
+}
+
+extern "C" int tauv_yolact_loss_reduce(const double* sums, const int64_t* n_pos, int B, int ratio,
+                                       const double* mask_partial, int n_partial, float* losses,
+                                       int64_t* n_pos_total, tauv_stream_t stream) {
+  TAUV_REQUIRE(n_pos && losses && (sums || mask_partial), TAUV_E_NULL, "pointers must not be NULL");
+  TAUV_REQUIRE(B > 0 && ratio >= 0 && n_partial >= 0, TAUV_E_SHAPE, "bad shape B=%d ratio=%d n_partial=%d", B, ratio, n_partial);
+  yloss_reduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sums, n_pos, B, ratio, mask_partial, n_partial, losses, n_pos_total);
+  TAUV_LAUNCH_CHECK("yloss_reduce_kernel");
   return 0;
 }

@@ -69,11 +69,12 @@ class _ClassBoxLoss(torch.autograd.Function):
                 _lib.i64ptr(match_index), _lib.i64ptr(truth_cls), B, N, C1, M, int(ratio), _lib.u8ptr(selected),
                 _lib.i32ptr(pos_list), _lib.dptr(sums), _lib.i64ptr(n_pos), ws.data_ptr(), ws.numel(),
                 _lib.stream_ptr(dev)))
-        P = n_pos.sum().reshape(1)
-        tot = sums.sum(dim=0)
-        Pd = P[0].clamp(min=1).to(torch.float64)
-        cls_loss = torch.where(P[0] > 0, tot[0] / ((1 + int(ratio)) * Pd), tot[0]).to(torch.float32)   # loss.py:54-57
-        box_loss = torch.where(P[0] > 0, tot[1] / Pd, tot[1]).to(torch.float32)                        # loss.py:70-73
+        losses = torch.empty((3,), dtype=torch.float32, device=dev)
+        P = torch.empty((1,), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):   # loss.py:54-57, :70-73: the normalisation, one small launch
+            _lib.check(lib.tauv_yolact_loss_reduce(_lib.dptr(sums), _lib.i64ptr(n_pos), B, int(ratio), None, 0,
+                                                   _lib.fptr(losses), _lib.i64ptr(P), _lib.stream_ptr(dev)))
+        cls_loss, box_loss = losses[0], losses[1]
         ctx.save_for_backward(cls, enc, target, positive, selected, match_index, truth_cls, P)
         ctx.ratio = int(ratio)
         ctx.mark_non_differentiable(selected, pos_list, n_pos)
@@ -143,9 +144,12 @@ class _MaskLoss(torch.autograd.Function):
                 _lib.fptr(coeff), _lib.fptr(proto), _lib.i32ptr(pos_list), _lib.i64ptr(n_pos), _lib.i64ptr(match_index),
                 _lib.fptr(truth_box), _lib.i32ptr(seg), _lib.u8ptr(img_valid), B, N, K, truth_box.shape[1], PH, PW, SH, SW,
                 _lib.dptr(tsum), recs.data_ptr(), _lib.dptr(partial), _lib.stream_ptr(dev)))
-        P = n_pos.sum().reshape(1)
-        tot = partial.sum()
-        out = torch.where(P[0] > 0, tot / P[0].clamp(min=1).to(torch.float64), tot).to(torch.float32)   # loss.py:117-120
+        losses = torch.empty((3,), dtype=torch.float32, device=dev)
+        P = torch.empty((1,), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):   # loss.py:117-120: the normalisation, one small launch
+            _lib.check(lib.tauv_yolact_loss_reduce(None, _lib.i64ptr(n_pos), B, 0, _lib.dptr(partial), partial.numel(),
+                                                   _lib.fptr(losses), _lib.i64ptr(P), _lib.stream_ptr(dev)))
+        out = losses[2]
         ctx.save_for_backward(coeff, proto, pos_list, n_pos, match_index, truth_box, seg, img_valid, tsum, recs, P)
         return out
 
