@@ -595,7 +595,7 @@ def run_centernet(ctx):
         kernels.update({
             "yolact_loss_forward_us": yl["loss_forward_us"], "yolact_loss_fwd_bwd_us": yl["loss_fwd_bwd_us"],
             "yolact_loss_note": f"loss(prediction, truth, config) of yolact/model/loss.py:8-125 through the Python API "
-                                f"(match + class/box terms with hard-negative mining + mask term; 7 launches forward, 11 "
+                                f"(match + class/box terms with hard-negative mining + mask term; 9 launches forward, 13 "
                                 f"with backward) at configs[2]'s shapes, 16 truths per frame, {yl['loss_positives']} "
                                 f"positives in the batch; rank 0's figures",
             "pack_heads_us": yl["pack_heads_us"],
@@ -723,7 +723,7 @@ def time_yolact(device, seed, B=B_PER_GPU):
             "scores_us": sc_us, "detect_us": det_us, "mask_us": mask_us, "mask_depth_us": md_us, "n_keep_total": nk,
             "match_us": median(ts[2:]), "mask_binary_nearest_us": mb_us["nearest"],
             "mask_binary_bilinear_us": mb_us["bilinear"],
-            "launches": 31 * 1 + 31 * 2 + 22 * 1 + 22 * 3 + 7 + 2 * 22 * 2 + 12 * 7 + 12 * 11 + 1 + 12 * 3}
+            "launches": 31 * 1 + 31 * 2 + 22 * 1 + 22 * 3 + 7 + 2 * 22 * 2 + 12 * 9 + 12 * 13 + 1 + 12 * 3}
 
 
 def e2e_centernet(ctx, logits, size, offset, truth, mc, tc, oc):
