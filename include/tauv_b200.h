@@ -205,6 +205,10 @@ int tauv_centernet_focal_loss(const float* logits, const uint8_t* valid, const i
                               int in_w, int downsample_ratio, double sigma, double alpha, double beta,
                               double* frame_sums, int64_t* frame_pos, void* workspace,
                               size_t workspace_bytes, tauv_stream_t stream);
+/* The batch's loss from the per-frame sums of tauv_centernet_focal_loss (loss.py:313-317, summed): loss [1] f32 =
+ * -(sum_p + sum_n) / N with N = the batch's positive cells, -sum_p when N == 0; n_pos_total [1] i64 = N. */
+int tauv_centernet_focal_loss_reduce(const double* frame_sums, const int64_t* frame_pos, int B,
+                                     float* loss, int64_t* n_pos_total, tauv_stream_t stream);
 int tauv_centernet_focal_loss_backward(const float* logits, const uint8_t* valid, const int64_t* label,
                                        const float* center, int B, int n_objects, int C, int H, int W,
                                        int in_h, int in_w, int downsample_ratio, double sigma,

@@ -60,6 +60,7 @@ _SIGNATURES = {
     "tauv_centernet_focal_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "tauv_centernet_focal_loss": (c_int, [_F, _U8, _I64, _F, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                           c_double, c_double, c_double, _D, _I64, c_void_p, c_size_t, c_void_p]),
+    "tauv_centernet_focal_loss_reduce": (c_int, [_D, _I64, c_int, _F, _I64, c_void_p]),
     "tauv_centernet_focal_loss_backward": (c_int, [_F, _U8, _I64, _F, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                                    c_int, c_double, c_double, c_double, _I64, _F, _F, c_void_p]),
     "tauv_keypoint_encode": (c_int, [_U8, _I64, _F, _I64, _F, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -136,13 +136,15 @@ class _HeatmapFocalLoss(torch.autograd.Function):
                 _lib.fptr(logits), _lib.u8ptr(valid), _lib.i64ptr(label), _lib.fptr(center), B, n, C, H, W, *geom,
                 float(sigma), float(alpha), float(beta), _lib.dptr(sums), _lib.i64ptr(pos), ws.data_ptr(), ws.numel(),
                 _lib.stream_ptr(dev)))
-        n_pos = pos.sum().reshape(1)
-        sp, sn = sums[:, 0].sum(), sums[:, 1].sum()
-        loss = torch.where(n_pos[0] > 0, -(sp + sn) / n_pos[0].clamp(min=1).to(torch.float64), -sp)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        n_pos = torch.empty((1,), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):   # the normalisation (loss.py:313-317), one small launch
+            _lib.check(lib.tauv_centernet_focal_loss_reduce(_lib.dptr(sums), _lib.i64ptr(pos), B, _lib.fptr(loss),
+                                                            _lib.i64ptr(n_pos), _lib.stream_ptr(dev)))
         ctx.save_for_backward(logits, valid, label, center, n_pos)
         ctx.meta = (geom, float(sigma), float(alpha), float(beta))
         ctx.mark_non_differentiable(n_pos)
-        return loss.to(torch.float32), n_pos
+        return loss, n_pos
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_n):

@@ -751,6 +751,31 @@ __global__ void __launch_bounds__(32) focal_reduce_kernel(const double* __restri
   }
 }
 
+// the batch's loss from the frames' sums (loss.py:313-317 summed): N = all positive cells; -(sp + sn) / N, or -sp when
+// N == 0.  One warp, fixed order.
+__global__ void __launch_bounds__(32) focal_finish_kernel(const double* __restrict__ frame_sums,
+                                                          const int64_t* __restrict__ frame_pos, int B,
+                                                          float* __restrict__ loss, int64_t* __restrict__ n_pos_total) {
+  const int lane = threadIdx.x;
+  double sp = 0.0, sn = 0.0;
+  long long np = 0;
+  for (int i = lane; i < B; i += 32) {
+    sp += frame_sums[2 * i];
+    sn += frame_sums[2 * i + 1];
+    np += frame_pos[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sp += __shfl_xor_sync(0xffffffffu, sp, o);
+    sn += __shfl_xor_sync(0xffffffffu, sn, o);
+    np += __shfl_xor_sync(0xffffffffu, np, o);
+  }
+  if (lane == 0) {
+    *loss = (float)(np > 0 ? -(sp + sn) / (double)np : -sp);
+    *n_pos_total = np;
+  }
+}
+
 // d(sum of the loss)/d(logits) * grad_out.  loss = -(loss_p + loss_n) / N for N > 0, -loss_p for N == 0.
 template <int KA>
 __global__ void __launch_bounds__(kEncThreads) focal_backward_kernel(const __grid_constant__ FocalArgs g,
@@ -882,6 +907,15 @@ extern "C" int tauv_centernet_focal_loss(const float* logits, const uint8_t* val
   focal_reduce_kernel<<<(unsigned)B, 32, 0, (cudaStream_t)stream>>>(part, part_pos, (long long)C * g.chunks_per_plane,
                                                                     frame_sums, frame_pos);
   TAUV_LAUNCH_CHECK("focal_reduce_kernel");
+  return 0;
+}
+
+extern "C" int tauv_centernet_focal_loss_reduce(const double* frame_sums, const int64_t* frame_pos, int B, float* loss,
+                                               int64_t* n_pos_total, tauv_stream_t stream) {
+  TAUV_REQUIRE(frame_sums && frame_pos && loss && n_pos_total, TAUV_E_NULL, "pointers must not be NULL");
+  TAUV_REQUIRE(B > 0, TAUV_E_SHAPE, "bad shape B=%d", B);
+  focal_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(frame_sums, frame_pos, B, loss, n_pos_total);
+  TAUV_LAUNCH_CHECK("focal_finish_kernel");
   return 0;
 }
 
