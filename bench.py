@@ -696,7 +696,7 @@ def time_yolact(device, seed, B=B_PER_GPU):
     tb[:, :8] = y.anchor[0][pick] * (1 + 0.05 * torch.randn((B, 8, 4), device=device, generator=g).clamp(-1, 1))
     tvd[:, :8] = True
     tcls = torch.randint(1, YL_C1, (B, 16), device=device, generator=g)
-    seg = torch.randint(0, 16, (B, 55, 55), device=device, generator=g, dtype=torch.int32)
+    seg = torch.randint(0, 16, (B, 55, 55), device=device, generator=g, dtype=torch.uint8)   # (the dataset's type)
     seg = seg.repeat_interleave(10, 1).repeat_interleave(10, 2).contiguous()
     img_valid = torch.ones((B, 550, 550), dtype=torch.bool, device=device)
     y.cfg.negative_example_ratio = 3

@@ -437,7 +437,8 @@ int tauv_yolact_class_box_loss_backward(const float* cls, const float* enc, cons
  * its matched truth (seg == match_index), weighted by box_to_mask(truth_box) * nearest-resized img_valid, over the
  * resized truth mask's area.
  *   coeff [B,N,K] f32 (K <= 32), proto [B,K,PH,PW] f32, match_index [B,N] i64, truth_box [B,M,4] f32,
- *   seg [B,SH,SW] i32 (truth index per pixel), img_valid [B,SH,SW] u8 ->
+ *   seg [B,SH,SW] (truth index per pixel; seg_bytes = 1: uint8 as the reference's dataset holds it, 4: int32,
+ *   8: int64), img_valid [B,SH,SW] u8 ->
  *   tsum [B,M] f64 (area of every truth's resized mask; kept for the backward),
  *   records [tauv_yolact_mask_loss_records_bytes(B, N)] bytes, 16-byte aligned (one 32-byte record per listed positive:
  *   crop box, area, prior, truth — gathered once per call; kept for the backward),
@@ -448,7 +449,8 @@ int tauv_yolact_mask_loss_partials(void);
 size_t tauv_yolact_mask_loss_records_bytes(int B, int N);
 int tauv_yolact_mask_loss(const float* coeff, const float* proto, const int32_t* pos_list,
                           const int64_t* n_pos, const int64_t* match_index, const float* truth_box,
-                          const int32_t* seg, const uint8_t* img_valid, int B, int N, int K, int M,
+                          const void* seg, int seg_bytes, const uint8_t* img_valid, int B, int N, int K,
+                          int M,
                           int PH, int PW, int SH, int SW, double* tsum, void* records,
                           double* partial, tauv_stream_t stream);
 
@@ -456,7 +458,7 @@ int tauv_yolact_mask_loss(const float* coeff, const float* proto, const int32_t*
  * NULL.  n_pos_total [1] i64 and grad_out [1] f32 on the device.  No atomics: deterministic. */
 int tauv_yolact_mask_loss_backward(const float* coeff, const float* proto, const int32_t* pos_list,
                                    const int64_t* n_pos, const int64_t* match_index,
-                                   const float* truth_box, const int32_t* seg,
+                                   const float* truth_box, const void* seg, int seg_bytes,
                                    const uint8_t* img_valid, int B, int N, int K, int M, int PH, int PW,
                                    int SH, int SW, const double* tsum, const void* records,
                                    const int64_t* n_pos_total,

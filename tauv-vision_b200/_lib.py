@@ -108,9 +108,9 @@ _SIGNATURES = {
     "tauv_yolact_loss_reduce": (c_int, [_D, _I64, c_int, c_int, _D, c_int, _F, _I64, c_void_p]),
     "tauv_yolact_mask_loss_partials": (c_int, []),
     "tauv_yolact_mask_loss_records_bytes": (c_size_t, [c_int, c_int]),
-    "tauv_yolact_mask_loss": (c_int, [_F, _F, _I32, _I64, _I64, _F, _I32, _U8, c_int, c_int, c_int, c_int, c_int, c_int,
+    "tauv_yolact_mask_loss": (c_int, [_F, _F, _I32, _I64, _I64, _F, c_void_p, c_int, _U8, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_int, _D, c_void_p, _D, c_void_p]),
-    "tauv_yolact_mask_loss_backward": (c_int, [_F, _F, _I32, _I64, _I64, _F, _I32, _U8, c_int, c_int, c_int, c_int, c_int,
+    "tauv_yolact_mask_loss_backward": (c_int, [_F, _F, _I32, _I64, _I64, _F, c_void_p, c_int, _U8, c_int, c_int, c_int, c_int, c_int,
                                                c_int, c_int, c_int, _D, c_void_p, _I64, _F, _F, _F, c_void_p]),
 }
 

@@ -386,6 +386,19 @@ struct __align__(16) MaskRec {
   int pad;
 };
 
+// The segmentation map as the caller holds it: uint8 in the reference's dataset (segmentation_dataset.py:98-99), int32 or
+// int64 elsewhere — read in place (a converted copy of 64 x 550 x 550 values is a pass of its own).
+struct SegView {
+  const void* p;
+  int bytes;   // 1 (unsigned), 4 or 8 (signed)
+  __device__ __forceinline__ int operator[](int i) const {
+    if (bytes == 1) return (int)static_cast<const uint8_t*>(p)[i];
+    if (bytes == 4) return static_cast<const int32_t*>(p)[i];
+    const long long v = static_cast<const long long*>(p)[i];
+    return v < -1 || v > 0x7fffffffLL ? -1 : (int)v;   // (no truth index lies out there)
+  }
+};
+
 struct MaskLossArgs {
   const float* coeff;          // [B,N,K]
   const float* proto;          // [B,K,PH,PW]
@@ -393,7 +406,8 @@ struct MaskLossArgs {
   const int64_t* n_pos;        // [B]
   const int64_t* match_index;  // [B,N]
   const float* truth_box;      // [B,M,4]
-  const int32_t* seg;          // [B,SH,SW]
+  const void* seg;             // [B,SH,SW], seg_bytes per element
+  int seg_bytes;
   const uint8_t* img_valid;    // [B,SH,SW]
   int N, K, M, PH, PW, SH, SW;
   float sy, sx;                // (float)SH / PH, (float)SW / PW: ATen's area_pixel_compute_scale without align_corners
@@ -438,7 +452,7 @@ __device__ __forceinline__ MaskPx mask_px(const MaskLossArgs& a, int b, int y, i
   return g;
 }
 
-__device__ __forceinline__ float mask_truth(const MaskPx& g, const int32_t* seg, int j) {
+__device__ __forceinline__ float mask_truth(const MaskPx& g, const SegView& seg, int j) {
   const float v00 = seg[g.o00] == j ? 1.0f : 0.0f, v01 = seg[g.o01] == j ? 1.0f : 0.0f;
   const float v10 = seg[g.o10] == j ? 1.0f : 0.0f, v11 = seg[g.o11] == j ? 1.0f : 0.0f;
   return __fadd_rn(__fmul_rn(g.ly0, __fadd_rn(__fmul_rn(g.lx0, v00), __fmul_rn(g.lx1, v01))),
@@ -502,7 +516,7 @@ __global__ void __launch_bounds__(kMaskLossThreads) ymask_area_kernel(const Mask
   extern __shared__ unsigned long long s_area[];  // [M]
   const int b = blockIdx.y;
   const int HW = a.PH * a.PW;
-  const int32_t* seg = a.seg + (size_t)b * a.SH * a.SW;
+  const SegView seg{static_cast<const char*>(a.seg) + (size_t)b * a.SH * a.SW * a.seg_bytes, a.seg_bytes};
   for (int m = threadIdx.x; m < a.M; m += kMaskLossThreads) s_area[m] = 0ull;
   __syncthreads();
   const int px = blockIdx.x * kMaskLossThreads + threadIdx.x;
@@ -556,7 +570,7 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_positive_kernel(con
   const int npos = (int)a.n_pos[b];
   const int HW = a.PH * a.PW;
   const float* proto = a.proto + (size_t)b * a.K * HW;
-  const int32_t* seg = a.seg + (size_t)b * a.SH * a.SW;
+  const SegView seg{static_cast<const char*>(a.seg) + (size_t)b * a.SH * a.SW * a.seg_bytes, a.seg_bytes};
   double cta_sum = 0.0;
   float gscale = 0.0f;
   if (BACKWARD) {
@@ -667,7 +681,7 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_backward_proto_kern
   const bool live = px < HW;
   const int npos = (int)a.n_pos[b];
   const float* proto = a.proto + (size_t)b * a.K * HW;
-  const int32_t* seg = a.seg + (size_t)b * a.SH * a.SW;
+  const SegView seg{static_cast<const char*>(a.seg) + (size_t)b * a.SH * a.SW * a.seg_bytes, a.seg_bytes};
   const long long P = *a.n_pos_total;
   const float gscale = P > 0 ? __fdiv_rn(*a.grad_out, (float)P) : *a.grad_out;
   float pv[kMaskLossMaxK], gp[kMaskLossMaxK];
@@ -861,6 +875,8 @@ static int mask_loss_check(const MaskLossArgs& a, int B) {
                    a.recs,
                TAUV_E_NULL, "pointers must not be NULL");
   TAUV_REQUIRE((uintptr_t)a.recs % 16 == 0, TAUV_E_ALIGN, "records must be 16-byte aligned");
+  TAUV_REQUIRE(a.seg_bytes == 1 || a.seg_bytes == 4 || a.seg_bytes == 8, TAUV_E_UNSUPPORTED, "seg_bytes=%d (1, 4 or 8)", a.seg_bytes);
+  TAUV_REQUIRE((uintptr_t)a.seg % a.seg_bytes == 0, TAUV_E_ALIGN, "seg is not aligned to its element size");
   TAUV_REQUIRE(B > 0 && a.N > 0 && a.K > 0 && a.M > 0 && a.PH > 0 && a.PW > 0 && a.SH > 0 && a.SW > 0, TAUV_E_SHAPE,
                "bad shape B=%d N=%d K=%d M=%d proto %dx%d seg %dx%d", B, a.N, a.K, a.M, a.PH, a.PW, a.SH, a.SW);
   TAUV_REQUIRE(a.K <= kMaskLossMaxK, TAUV_E_UNSUPPORTED, "K=%d exceeds the built-in limit %d", a.K, kMaskLossMaxK);
@@ -874,10 +890,10 @@ extern "C" size_t tauv_yolact_mask_loss_records_bytes(int B, int N) {
 }
 
 extern "C" int tauv_yolact_mask_loss(const float* coeff, const float* proto, const int32_t* pos_list, const int64_t* n_pos,
-                                     const int64_t* match_index, const float* truth_box, const int32_t* seg,
+                                     const int64_t* match_index, const float* truth_box, const void* seg, int seg_bytes,
                                      const uint8_t* img_valid, int B, int N, int K, int M, int PH, int PW, int SH, int SW,
                                      double* tsum, void* records, double* partial, tauv_stream_t stream) {
-  MaskLossArgs a{coeff, proto, pos_list, n_pos, match_index, truth_box, seg, img_valid, N, K, M, PH, PW, SH, SW,
+  MaskLossArgs a{coeff, proto, pos_list, n_pos, match_index, truth_box, seg, seg_bytes, img_valid, N, K, M, PH, PW, SH, SW,
                  PH > 0 ? (float)SH / (float)PH : 0.f, PW > 0 ? (float)SW / (float)PW : 0.f, tsum, (MaskRec*)records, partial,
                  nullptr, nullptr, nullptr, nullptr};
   if (int rc = mask_loss_check(a, B)) return rc;
@@ -899,11 +915,11 @@ extern "C" int tauv_yolact_mask_loss(const float* coeff, const float* proto, con
 
 extern "C" int tauv_yolact_mask_loss_backward(const float* coeff, const float* proto, const int32_t* pos_list,
                                               const int64_t* n_pos, const int64_t* match_index, const float* truth_box,
-                                              const int32_t* seg, const uint8_t* img_valid, int B, int N, int K, int M,
+                                              const void* seg, int seg_bytes, const uint8_t* img_valid, int B, int N, int K, int M,
                                               int PH, int PW, int SH, int SW, const double* tsum,
                                               const void* records, const int64_t* n_pos_total, const float* grad_out, float* grad_coeff,
                                               float* grad_proto, tauv_stream_t stream) {
-  MaskLossArgs a{coeff, proto, pos_list, n_pos, match_index, truth_box, seg, img_valid, N, K, M, PH, PW, SH, SW,
+  MaskLossArgs a{coeff, proto, pos_list, n_pos, match_index, truth_box, seg, seg_bytes, img_valid, N, K, M, PH, PW, SH, SW,
                  PH > 0 ? (float)SH / (float)PH : 0.f, PW > 0 ? (float)SW / (float)PW : 0.f, const_cast<double*>(tsum),
                  (MaskRec*)const_cast<void*>(records), nullptr, grad_out, n_pos_total, grad_coeff, grad_proto};
   if (int rc = mask_loss_check(a, B)) return rc;

@@ -142,7 +142,8 @@ class _MaskLoss(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.tauv_yolact_mask_loss(
                 _lib.fptr(coeff), _lib.fptr(proto), _lib.i32ptr(pos_list), _lib.i64ptr(n_pos), _lib.i64ptr(match_index),
-                _lib.fptr(truth_box), _lib.i32ptr(seg), _lib.u8ptr(img_valid), B, N, K, truth_box.shape[1], PH, PW, SH, SW,
+                _lib.fptr(truth_box), seg.data_ptr(), seg.element_size(), _lib.u8ptr(img_valid), B, N, K, truth_box.shape[1], PH, PW,
+                SH, SW,
                 _lib.dptr(tsum), recs.data_ptr(), _lib.dptr(partial), _lib.stream_ptr(dev)))
         losses = torch.empty((3,), dtype=torch.float32, device=dev)
         P = torch.empty((1,), dtype=torch.int64, device=dev)
@@ -168,7 +169,7 @@ class _MaskLoss(torch.autograd.Function):
             with torch.cuda.device(dev):
                 _lib.check(_lib.load().tauv_yolact_mask_loss_backward(
                     _lib.fptr(coeff), _lib.fptr(proto), _lib.i32ptr(pos_list), _lib.i64ptr(n_pos),
-                    _lib.i64ptr(match_index), _lib.fptr(truth_box), _lib.i32ptr(seg), _lib.u8ptr(img_valid), B, N, K,
+                    _lib.i64ptr(match_index), _lib.fptr(truth_box), seg.data_ptr(), seg.element_size(), _lib.u8ptr(img_valid), B, N, K,
                     truth_box.shape[1], PH, PW, SH, SW, _lib.dptr(tsum), recs.data_ptr(), _lib.i64ptr(P), _lib.fptr(go),
                     _lib.fptr(gc) if need_c else None, _lib.fptr(gp) if need_p else None, _lib.stream_ptr(dev)))
         return gc, gp, None, None, None, None, None, None
@@ -186,7 +187,9 @@ def mask_loss(mask_coeff: torch.Tensor, mask_prototype: torch.Tensor, match: Anc
     coeff, proto = _lib.f32c(mask_coeff), _lib.f32c(mask_prototype)
     if coeff.dim() != 3 or proto.dim() != 4 or proto.shape[:2] != (coeff.shape[0], coeff.shape[2]):
         raise ValueError(f"mask_coeff must be [B,N,K] and mask_prototype [B,K,PH,PW]; got {tuple(coeff.shape)}, {tuple(proto.shape)}")
-    seg = truth_seg_map.contiguous().to(torch.int32)
+    seg = truth_seg_map.contiguous()   # read in place: uint8 (the reference's dataset), int32 or int64
+    if seg.dtype not in (torch.uint8, torch.int32, torch.int64):
+        seg = seg.to(torch.int32)
     valid = truth_img_valid.contiguous()
     valid = valid.view(torch.uint8) if valid.dtype == torch.bool else (valid != 0).view(torch.uint8)
     return _MaskLoss.apply(coeff, proto, pos_list, n_pos, match.match_index, _lib.f32c(truth_box), seg, valid)

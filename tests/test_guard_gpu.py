@@ -91,7 +91,7 @@ def test_yolact_loss_entries_stay_inside_their_buffers(cuda_device, lib):
     part = Guarded((B, lib.tauv_yolact_mask_loss_partials()), torch.float64, d)
     recs = Guarded((lib.tauv_yolact_mask_loss_records_bytes(B, N),), torch.uint8, d)
     args = (_f(coeff), _f(proto), _ptr(pl.t, ctypes.c_int32), _ptr(npos.t, ctypes.c_int64), _ptr(m.match_index, ctypes.c_int64),
-            _f(tb), _ptr(seg, ctypes.c_int32), _ptr(valid, ctypes.c_uint8), B, N, K, M, PH, PW, SH, SW)
+            _f(tb), seg.data_ptr(), 4, _ptr(valid, ctypes.c_uint8), B, N, K, M, PH, PW, SH, SW)
     _lib.check(lib.tauv_yolact_mask_loss(*args, _ptr(tsum.t, ctypes.c_double), recs.t.data_ptr(), _ptr(part.t, ctypes.c_double),
                                          _lib.stream_ptr(d)))
     torch.cuda.synchronize()

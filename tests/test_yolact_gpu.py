@@ -595,6 +595,16 @@ def test_mask_loss_vs_oracle(yl, B, N, K, M, PH, PW, SH, SW):
     assert_close(dp.grad, 3 * og_p, rtol=1e-4, atol=1e-6 * float(og_p.abs().max()), what="d/d mask_prototype")
     again = yl.loss.mask_loss(dc, dp, m, pos_list, n_pos, tb.to(d), seg.to(d), img_valid.to(d))
     assert_equal(again, ml, "run-to-run")
+    # the segmentation map is read in place in the caller's type: uint8 as the reference's dataset holds it
+    # (segmentation_dataset.py:98-99; 255 = no object), int32, int64 — the same bits out of all three
+    for dtype, none in ((torch.uint8, 255), (torch.int32, -1)):
+        s = torch.where(seg < 0, torch.full_like(seg, none), seg).to(dtype).to(d)
+        dc2, dp2 = coeff.detach().to(d).requires_grad_(), proto.detach().to(d).requires_grad_()
+        ml2 = yl.loss.mask_loss(dc2, dp2, m, pos_list, n_pos, tb.to(d), s, img_valid.to(d))
+        assert_equal(ml2, ml, f"seg as {dtype}")
+        (3 * ml2).backward()
+        assert_equal(dc2.grad, dc.grad, f"d/d mask_coeff, seg as {dtype}")
+        assert_equal(dp2.grad, dp.grad, f"d/d mask_prototype, seg as {dtype}")
 
 
 # ---- head outputs in the consumers' layout ----------------------------------------------------------

@@ -19,7 +19,7 @@ tb[:, :M // 2] = anchor[0].cpu()[pick] * (1 + 0.05 * torch.randn((B, M // 2, 4),
 tv[:, :M // 2] = True
 tb, tv = tb.to(dev), tv.to(dev)
 tcls = torch.randint(1, C1, (B, M), device=dev, generator=g)
-seg = torch.randint(0, M, (B, SH // 10, SH // 10), device=dev, generator=g).repeat_interleave(10, 1).repeat_interleave(10, 2)[:, :SH, :SH].contiguous()
+seg = torch.randint(0, M, (B, SH // 10, SH // 10), device=dev, generator=g, dtype=torch.uint8).repeat_interleave(10, 1).repeat_interleave(10, 2)[:, :SH, :SH].contiguous()
 valid = torch.ones((B, SH, SH), dtype=torch.bool, device=dev)
 cls = (torch.randn((B, N, C1), device=dev, generator=g) * 2).requires_grad_()
 enc = (torch.randn((B, N, 4), device=dev, generator=g)).requires_grad_()
