@@ -562,8 +562,8 @@ __global__ void __launch_bounds__(256) ymask_records_kernel(const MaskLossArgs a
 // (FULLK: K == 32, the YOLACT head — the per-channel `k < K` tests of the unrolled loops cost an ISETP each per pixel,
 // there are only seven predicate registers to keep them in)
 template <bool BACKWARD, bool FULLK>
-__global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_positive_kernel(const MaskLossArgs a) {
-  __shared__ float s_coeff[kMaskLossMaxK];
+__global__ void __launch_bounds__(kMaskLossThreads, BACKWARD ? 2 : 3) ymask_positive_kernel(const MaskLossArgs a) {
+  __shared__ float s_coeff2[2][kMaskLossMaxK];
   __shared__ double s_red[kMaskLossThreads / 32];
   __shared__ float s_gc[kMaskLossThreads / 32][kMaskLossMaxK];
   const int tid = threadIdx.x, b = blockIdx.y;
@@ -571,13 +571,17 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_positive_kernel(con
   const int HW = a.PH * a.PW;
   const float* proto = a.proto + (size_t)b * a.K * HW;
   const SegView seg{static_cast<const char*>(a.seg) + (size_t)b * a.SH * a.SW * a.seg_bytes, a.seg_bytes};
-  double cta_sum = 0.0;
+  // forward: every thread keeps its own sum over the CTA's positives of (its pixels' BCE) / area — ONE block sum at the
+  // end instead of one per positive (ten shuffles and two barriers each: 15 % of the stall samples), and the coefficient
+  // row double-buffered: one barrier per positive instead of four.  The order of the additions is fixed: run-to-run identical.
+  double thread_sum = 0.0;
   float gscale = 0.0f;
   if (BACKWARD) {
     const long long P = *a.n_pos_total;
     gscale = P > 0 ? __fdiv_rn(*a.grad_out, (float)P) : *a.grad_out;   // loss.py:117-120
   }
-  for (int i = blockIdx.x; i < npos; i += gridDim.x) {
+  int it = 0;
+  for (int i = blockIdx.x; i < npos; i += gridDim.x, ++it) {
     const MaskRec rec = a.recs[(size_t)b * a.N + i];
     const int n = rec.n, j = rec.j;
     const CropBounds crop{rec.left, rec.right, rec.top, rec.bottom};
@@ -585,12 +589,14 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_positive_kernel(con
     const int npx = box.bh * box.bw;
     const int bwd = max(box.bw, 1), step_y = kMaskLossThreads / bwd, step_x = kMaskLossThreads - step_y * bwd;
     const float area = rec.area;
-    __syncthreads();
+    float* s_coeff = s_coeff2[BACKWARD ? 0 : (it & 1)];
+    if (BACKWARD) __syncthreads();   // (forward: the buffer written here was last read two positives ago, a barrier in between)
     if (tid < kMaskLossMaxK) s_coeff[tid] = tid < a.K ? a.coeff[((size_t)b * a.N + n) * a.K + tid] : 0.0f;
     __syncthreads();
     if (!BACKWARD) {
       double num = 0.0;
       if (area > 0.0f) {   // loss.py:93-94
+        const double inv_area = 1.0 / (double)area;   // (independent of the pixel loop: its latency hides under the loads)
         int ry = tid / bwd, rx = tid - ry * bwd;   // (the pixel's row and column inside the box, kept incrementally)
         for (int q = tid; q < npx; q += kMaskLossThreads, ry += step_y, rx += step_x) {
           if (rx >= bwd) { rx -= bwd; ++ry; }
@@ -608,9 +614,8 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_positive_kernel(con
             num += (double)(w * -(tc * logf(m) + (1.0f - tc) * logf(1.0f - m)));               // :96-100, :113
           }
         }
+        thread_sum += num * inv_area;   // :113
       }
-      num = mask_block_sum(num, s_red);
-      if (area > 0.0f) cta_sum += num / (double)area;   // :113
     } else {
       float gc[kMaskLossMaxK];
 #pragma unroll
@@ -644,14 +649,20 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_positive_kernel(con
         }
       }
       // K sums over the CTA: warp shuffles, then the eight warps' values in a fixed order
+      // (a butterfly that halves the values a lane holds at every step — 31 shuffles instead of 32 x 5: lane l ends up
+      // with the warp's sum for channel l; the order of the additions is fixed)
       const int lane = tid & 31, warp = tid >> 5;
+      static_assert(kMaskLossMaxK == 32, "the butterfly below is written for 32 channels");
 #pragma unroll
-      for (int k = 0; k < kMaskLossMaxK; ++k) {
-        float v = gc[k];
+      for (int o = 16; o > 0; o >>= 1) {
+        const bool upper = (lane & o) != 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_gc[warp][k] = v;
+        for (int k = 0; k < o; ++k) {
+          const float send = upper ? gc[k] : gc[k + o], keep = upper ? gc[k + o] : gc[k];
+          gc[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
       }
+      s_gc[warp][lane] = gc[0];
       __syncthreads();
       if (tid < a.K) {
         float v = 0.0f;
@@ -660,7 +671,10 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_positive_kernel(con
       }
     }
   }
-  if (!BACKWARD && tid == 0) a.partial[(size_t)b * gridDim.x + blockIdx.x] = cta_sum;
+  if (!BACKWARD) {
+    const double cta_sum = mask_block_sum(thread_sum, s_red);
+    if (tid == 0) a.partial[(size_t)b * gridDim.x + blockIdx.x] = cta_sum;
+  }
 }
 
 // one record per positive, staged in shared memory for the CTA's 256 pixels
