@@ -559,6 +559,10 @@ __global__ void __launch_bounds__(256) ymask_records_kernel(const MaskLossArgs a
   a.recs[(size_t)b * a.N + i] = MaskRec{c.left, c.right, c.top, c.bottom, (float)a.tsum[(size_t)b * a.M + j], n, j, 0};
 }
 
+// The K-term dot products and gradient accumulations use explicit fmaf: the library is built with --fmad=false (every
+// expression that feeds a comparison rounds like ATen), which would make each term an FMUL + FADD pair — twice the
+// instructions of these issue-bound loops; the reference's own `@` (loss.py:82) is a BLAS matmul whose rounding is not
+// specified either.
 // (FULLK: K == 32, the YOLACT head — the per-channel `k < K` tests of the unrolled loops cost an ISETP each per pixel,
 // there are only seven predicate registers to keep them in)
 template <bool BACKWARD, bool FULLK>
@@ -609,7 +613,7 @@ __global__ void __launch_bounds__(kMaskLossThreads, BACKWARD ? 2 : 3) ymask_posi
             for (int k = 0; k < kMaskLossMaxK; ++k) pv[k] = (FULLK || k < a.K) ? proto[(size_t)k * HW + px] : 0.0f;
             float logit = 0.0f;
 #pragma unroll
-            for (int k = 0; k < kMaskLossMaxK; ++k) logit += s_coeff[k] * pv[k];   // loss.py:82 (s_coeff and pv are zero beyond K)
+            for (int k = 0; k < kMaskLossMaxK; ++k) logit = fmaf(s_coeff[k], pv[k], logit);   // loss.py:82 (s_coeff and pv are zero beyond K)
             const float m = clamp_unit(fmaxf(sigmoid_ref(logit), 1e-4f)), tc = clamp_unit(mask_truth(g, seg, j));  // :83-84, :97-98
             num += (double)(w * -(tc * logf(m) + (1.0f - tc) * logf(1.0f - m)));               // :96-100, :113
           }
@@ -636,16 +640,16 @@ __global__ void __launch_bounds__(kMaskLossThreads, BACKWARD ? 2 : 3) ymask_posi
 #pragma unroll
           for (int k = 0; k < 16; ++k) pv[k] = (FULLK || k < a.K) ? proto[(size_t)k * HW + px] : 0.0f;
 #pragma unroll
-          for (int k = 0; k < 16; ++k) logit += s_coeff[k] * pv[k];
+          for (int k = 0; k < 16; ++k) logit = fmaf(s_coeff[k], pv[k], logit);
 #pragma unroll
           for (int k = 0; k < 16; ++k) pv[k] = (FULLK || 16 + k < a.K) ? proto[(size_t)(16 + k) * HW + px] : 0.0f;
 #pragma unroll
-          for (int k = 0; k < 16; ++k) logit += s_coeff[16 + k] * pv[k];
+          for (int k = 0; k < 16; ++k) logit = fmaf(s_coeff[16 + k], pv[k], logit);
           const float dl = G * mask_dlogit(logit, mask_truth(g, seg, j), w);
 #pragma unroll
-          for (int k = 0; k < 16; ++k) gc[16 + k] += dl * pv[k];
+          for (int k = 0; k < 16; ++k) gc[16 + k] = fmaf(dl, pv[k], gc[16 + k]);
 #pragma unroll
-          for (int k = 0; k < 16; ++k) gc[k] += dl * ((FULLK || k < a.K) ? proto[(size_t)k * HW + px] : 0.0f);
+          for (int k = 0; k < 16; ++k) gc[k] = fmaf(dl, (FULLK || k < a.K) ? proto[(size_t)k * HW + px] : 0.0f, gc[k]);
         }
       }
       // K sums over the CTA: warp shuffles, then the eight warps' values in a fixed order
@@ -747,15 +751,15 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_backward_proto_kern
       float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
 #pragma unroll
       for (int k = 0; k < kMaskLossMaxK; k += 4) {
-        l0 += cf[k] * pv[k];   // (cf and pv are zero beyond K)
-        l1 += cf[k + 1] * pv[k + 1];
-        l2 += cf[k + 2] * pv[k + 2];
-        l3 += cf[k + 3] * pv[k + 3];
+        l0 = fmaf(cf[k], pv[k], l0);   // (cf and pv are zero beyond K)
+        l1 = fmaf(cf[k + 1], pv[k + 1], l1);
+        l2 = fmaf(cf[k + 2], pv[k + 2], l2);
+        l3 = fmaf(cf[k + 3], pv[k + 3], l3);
       }
       const float dl = rec.G * mask_dlogit((l0 + l1) + (l2 + l3), mask_truth_taps(g, s00, s01, s10, s11, rec.j), g.valid);
 #pragma unroll
       for (int k = 0; k < kMaskLossMaxK; ++k)
-        if (FULLK || k < a.K) gp[k] += dl * cf[k];
+        if (FULLK || k < a.K) gp[k] = fmaf(dl, cf[k], gp[k]);
     }
   }
   if (live) {
