@@ -688,6 +688,7 @@ struct MaskPosRec {
   int n, j;
 };
 constexpr int kMaskRecChunk = 64;
+constexpr int kMaskTileW = 32, kMaskTileH = kMaskLossThreads / 32;   // ymask_backward_proto_kernel's tile of pixels
 
 template <bool FULLK>
 __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_backward_proto_kernel(const MaskLossArgs a) {
@@ -695,8 +696,14 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_backward_proto_kern
   __shared__ float s_cf[kMaskRecChunk][kMaskLossMaxK];   // the chunk's coefficient rows
   const int b = blockIdx.y;
   const int HW = a.PH * a.PW;
-  const int px = blockIdx.x * kMaskLossThreads + threadIdx.x;
-  const bool live = px < HW;
+  // a CTA is a tile of 32 x 8 pixels (a warp = 32 consecutive pixels of a row: coalesced): a crop box covers most of a
+  // tile or misses it, so the eight warps between two barriers have the same work, and fewer boxes touch a tile than touch
+  // a whole row of the grid (256 consecutive pixels, the first layout: `barrier` was its top stall reason)
+  const int tiles_x = (a.PW + kMaskTileW - 1) / kMaskTileW;
+  const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
+  const int y = tile_y * kMaskTileH + (threadIdx.x >> 5), x = tile_x * kMaskTileW + (threadIdx.x & 31);
+  const bool live = y < a.PH && x < a.PW;
+  const int px = live ? y * a.PW + x : 0;
   const int npos = (int)a.n_pos[b];
   const float* proto = a.proto + (size_t)b * a.K * HW;
   const SegView seg{static_cast<const char*>(a.seg) + (size_t)b * a.SH * a.SW * a.seg_bytes, a.seg_bytes};
@@ -708,16 +715,12 @@ __global__ void __launch_bounds__(kMaskLossThreads, 2) ymask_backward_proto_kern
     pv[k] = (live && (FULLK || k < a.K)) ? proto[(size_t)k * HW + px] : 0.0f;
     gp[k] = 0.0f;
   }
-  const int y = live ? px / a.PW : 0, x = live ? px - y * a.PW : 0;
-  const MaskPx g = mask_px(a, b, y, x);
+  const MaskPx g = mask_px(a, b, live ? y : 0, live ? x : 0);
   // (the four taps of this pixel's bilinear resize do not depend on the positive: loaded once)
   const int s00 = live ? seg[g.o00] : -1, s01 = live ? seg[g.o01] : -1, s10 = live ? seg[g.o10] : -1, s11 = live ? seg[g.o11] : -1;
-  // the rows and columns this CTA's pixels span: positives whose crop box misses them are not staged at all (a CTA is
-  // about one row of the grid, a box covers a quarter of the rows: three positives in four drop out here)
-  const int p_lo = blockIdx.x * kMaskLossThreads, p_hi = min(p_lo + kMaskLossThreads, HW) - 1;
-  const int y_lo = p_lo / a.PW, y_hi = p_hi / a.PW;
-  const float fy_lo = (float)y_lo, fy_hi = (float)y_hi;
-  const float fx_lo = y_lo == y_hi ? (float)(p_lo - y_lo * a.PW) : 0.0f, fx_hi = y_lo == y_hi ? (float)(p_hi - y_hi * a.PW) : (float)(a.PW - 1);
+  // the rows and columns this CTA's tile spans: positives whose crop box misses it are not staged at all
+  const float fy_lo = (float)(tile_y * kMaskTileH), fy_hi = (float)min(tile_y * kMaskTileH + kMaskTileH - 1, a.PH - 1);
+  const float fx_lo = (float)(tile_x * kMaskTileW), fx_hi = (float)min(tile_x * kMaskTileW + kMaskTileW - 1, a.PW - 1);
   __shared__ int s_kept[2];
   static_assert(kMaskRecChunk == 64, "the ordered compaction below uses two warps");
   for (int i0 = 0; i0 < npos; i0 += kMaskRecChunk) {
@@ -949,7 +952,7 @@ extern "C" int tauv_yolact_mask_loss_backward(const float* coeff, const float* p
     TAUV_LAUNCH_CHECK("ymask_positive_kernel<backward>");
   }
   if (grad_proto) {
-    const dim3 pgrid((PH * PW + kMaskLossThreads - 1) / kMaskLossThreads, B);
+    const dim3 pgrid(((PW + kMaskTileW - 1) / kMaskTileW) * ((PH + kMaskTileH - 1) / kMaskTileH), B);
     if (K == kMaskLossMaxK) ymask_backward_proto_kernel<true><<<pgrid, kMaskLossThreads, 0, (cudaStream_t)stream>>>(a);
     else ymask_backward_proto_kernel<false><<<pgrid, kMaskLossThreads, 0, (cudaStream_t)stream>>>(a);
     TAUV_LAUNCH_CHECK("ymask_backward_proto_kernel");
